@@ -1,0 +1,157 @@
+// Descriptors shared by the host (part store / plan compiler) and the sm_100a kernels.
+// Everything here is POD and is copied to the device verbatim.
+#pragma once
+#include <cstdint>
+
+namespace fgpu {
+
+constexpr int kMaxSlots = 48;    // distinct columns one query may touch
+constexpr int kMaxLeaves = 32;   // predicate leaves (one bit each in the per-row leaf mask)
+constexpr int kMaxKeys = 40;     // group-by / distinct key columns
+constexpr int kMaxAggs = 8;
+constexpr int kMaxProg = 48;     // arithmetic ops over all aggregate expressions
+constexpr int kMaxFilterProg = 96;
+constexpr int kMaxKeyWords = 6;  // packed key = up to 6 x 64 bit
+constexpr int kMaxNumBufs = 4;   // numeric columns that need smem staging (nullable / dict-encoded)
+
+constexpr uint32_t kNullIdx = 0xffffffffu;
+
+// One run of an RLE/bit-packed hybrid stream (same layout as HostRun).
+struct Run {
+  uint32_t start;  // first value ordinal of the run within the chunk
+  uint32_t off;    // bit-packed: byte offset of the packed payload in the chunk's stream section
+  uint32_t val;    // RLE: the repeated value
+  uint32_t meta;   // bit0 1 = bit-packed; bits 8..15 bit width
+};
+
+enum ChunkKind : uint8_t {
+  CK_ABSENT = 0,    // column not in this row group (dynamic column missing): all rows NULL
+  CK_PLAIN64 = 1,   // PLAIN int64/double: `values` is a dense 8-byte array of the non-null values
+  CK_DICT_STR = 2,  // RLE_DICTIONARY strings: hybrid indices -> lut -> global dictionary id
+  CK_DICT64 = 3     // RLE_DICTIONARY int64/double: hybrid indices -> dict64 (8-byte values)
+};
+
+// One column chunk (row group x column) resident in HBM.  All pointers are device pointers into the
+// part's single allocation; every section is 128-byte aligned and padded by 16 readable bytes.
+struct ChunkDesc {
+  uint8_t kind;
+  uint8_t has_nulls;  // definition levels stored and at least one NULL
+  uint8_t _pad[2];
+  uint32_t n_rows;
+  uint32_t n_values;  // non-null values
+  uint32_t n_runs;    // value runs (excluding the sentinel)
+  uint32_t n_defruns;
+  uint32_t dict_size;
+  const uint8_t* values;         // PLAIN64: aligned values; DICT*: concatenated hybrid index streams
+  const Run* runs;               // DICT*: run directory (+1 sentinel with start == n_values)
+  const uint32_t* tile_run;      // DICT*: per tile, index of the run holding the tile's first value
+  const uint8_t* def;            // concatenated definition-level hybrid streams (has_nulls)
+  const Run* def_runs;           // (+1 sentinel with start == n_rows)
+  const uint32_t* tile_defrun;   // per tile, index of the def run holding the tile's first row
+  const uint32_t* tile_val0;     // per tile, number of non-null values before the tile (has_nulls)
+  const uint32_t* lut;           // CK_DICT_STR: chunk dictionary index -> global dictionary id
+  const int64_t* dict64;         // CK_DICT64: chunk dictionary values (raw 8 bytes each)
+};
+
+enum SlotType : uint8_t { ST_I64 = 0, ST_F64 = 1, ST_DICT = 2 };
+
+enum LeafMode : uint8_t { LM_EVAL = 0, LM_ALL = 1, LM_NONE = 2 };
+
+// Predicate leaf "column op literal" (binaryscalarexpr.go:41-152).  op uses logicalplan.Op values.
+struct LeafDesc {
+  uint8_t slot;
+  uint8_t op;
+  uint8_t cmp_float;  // compare as double (float column, or int column against float literal)
+  uint8_t _pad;
+  uint32_t _pad2;
+  int64_t lit_i;
+  double lit_f;
+};
+
+// Per (row group, leaf): how the leaf behaves on that row group.
+struct LeafRt {
+  uint8_t mode;         // LeafMode; ALL/NONE encode the missing-column rules (binaryscalarexpr.go:47-73)
+  uint8_t null_result;  // dictionary leaves: result for NULL rows (== NULL selects nulls, :205-212)
+  uint8_t _pad[6];
+  const uint8_t* lut;   // dictionary leaves: result per chunk-local dictionary index
+};
+
+struct KeyDesc {
+  uint8_t slot;
+  uint8_t is_int64;  // key is a raw int64 column (takes a whole 64-bit word)
+  uint8_t word;      // packed mode: which 64-bit key word
+  uint8_t shift;     // packed mode: bit offset inside the word
+  uint32_t bits;     // packed mode: field width
+  uint32_t dense_stride;  // dense mode: multiplier of (gid + 1)
+  uint32_t _pad;
+};
+
+enum ProgOpCode : uint8_t { PO_LOAD = 0, PO_CONST = 1, PO_ADD = 2, PO_SUB = 3, PO_MUL = 4, PO_DIV = 5 };
+struct ProgOp {
+  uint8_t op;
+  uint8_t slot;
+  uint8_t _pad[6];
+  int64_t imm;  // PO_CONST: int64 or the bits of a double
+};
+
+struct AggDesc {
+  uint8_t func;      // logicalplan.AggFunc value
+  uint8_t is_float;  // expression evaluates in float64
+  uint8_t prog_off;
+  uint8_t prog_len;
+  uint32_t _pad;
+};
+
+enum TableMode : int32_t { TM_DENSE = 0, TM_HASH = 1 };
+
+// Everything one launch of the fused scan kernel needs.
+struct QueryDesc {
+  int32_t n_slots, n_leaves, n_keys, n_aggs;
+  int32_t n_filter_prog;  // 0 = no filter
+  int32_t table_mode;
+  int32_t key_words;
+  int32_t tile_rows;
+  int32_t n_rg;
+  uint32_t n_tiles;
+  uint32_t table_slots;  // dense: number of slots; hash: capacity (power of two)
+  uint32_t n_numbufs;    // numeric staging buffers in use
+  uint8_t slot_type[kMaxSlots];
+  int8_t slot_numbuf[kMaxSlots];  // numeric slot -> staging buffer index, -1 = read directly from HBM
+  uint8_t slot_used_by_leaf[kMaxSlots];
+  uint8_t filter_prog[kMaxFilterProg];  // postfix: 0..31 push leaf; 0x80 AND; 0x81 OR
+  LeafDesc leaves[kMaxLeaves];
+  KeyDesc keys[kMaxKeys];
+  AggDesc aggs[kMaxAggs];
+  ProgOp prog[kMaxProg];
+  // per row group tables
+  const ChunkDesc* chunks;        // [n_rg][n_slots]
+  const LeafRt* leaf_rt;          // [n_rg][n_leaves]
+  const uint32_t* rg_first_tile;  // [n_rg + 1]
+  const uint32_t* rg_rows;        // [n_rg]
+  // aggregate table
+  unsigned long long* t_rows;  // rows per slot (also every Count aggregate)
+  long long* t_agg[kMaxAggs];  // per aggregate, int64 or double bits
+  uint32_t* t_tag;             // hash mode: 0 empty, 1 locked, else fingerprint|2
+  unsigned long long* t_keys;  // hash mode: [capacity][key_words]
+  unsigned long long* counters;  // [0] rows selected, [1] table overflow flag
+};
+
+// Dense/hash table -> compacted result rows.
+struct FinalizeDesc {
+  int32_t table_mode, key_words, n_keys, n_aggs;
+  uint32_t table_slots;
+  uint32_t max_out;
+  KeyDesc keys[kMaxKeys];
+  uint32_t dense_radix[kMaxKeys];  // dense mode: (card + 1) per key
+  const unsigned long long* t_rows;
+  const long long* t_agg[kMaxAggs];
+  const uint32_t* t_tag;
+  const unsigned long long* t_keys;
+  // outputs
+  long long* out_keys;  // [n_keys][max_out] : gid+1 code (0 = NULL) or raw int64
+  long long* out_aggs;  // [n_aggs][max_out]
+  unsigned long long* out_rows;  // [max_out]
+  unsigned int* out_count;
+};
+
+}  // namespace fgpu

@@ -1,0 +1,1302 @@
+// libfrostgpu host engine: context, part registry uploads, plan compilation, execution, result
+// export, and the extern "C" surface of include/frostgpu.h.
+//
+// There is deliberately no CPU execution path in this file: without a CUDA device fgpu_init fails
+// with FGPU_ERR_NO_DEVICE and nothing else can run.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/frostgpu.h"
+#include "arrow_export.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "part_store.h"
+
+using namespace fgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      cudaGetLastError();                                                                      \
+      return fail(_e == cudaErrorMemoryAllocation ? FGPU_ERR_OOM : FGPU_ERR_CUDA,              \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+    }                                                                                          \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t bytes) {
+    reset();
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) n = bytes;
+    else p = nullptr;
+    return e;
+  }
+};
+
+struct ExprNode {
+  int32_t kind = 0, op = 0, left = -1, right = -1;
+  std::string name;
+  int32_t lit_type = FGPU_SCALAR_NULL;
+  int64_t lit_i = 0;
+  double lit_f = 0;
+  std::string lit_bytes;
+  fgpu_match_fn match = nullptr;
+  void* match_user = nullptr;
+};
+
+const char* op_string(int op) {  // logicalplan.Op.String(), expr.go:35-72
+  switch (op) {
+    case FGPU_OP_EQ: return "==";
+    case FGPU_OP_NOT_EQ: return "!=";
+    case FGPU_OP_LT: return "<";
+    case FGPU_OP_LT_EQ: return "<=";
+    case FGPU_OP_GT: return ">";
+    case FGPU_OP_GT_EQ: return ">=";
+    case FGPU_OP_REGEX_MATCH: return "=~";
+    case FGPU_OP_REGEX_NOT_MATCH: return "!~";
+    case FGPU_OP_AND: return "&&";
+    case FGPU_OP_OR: return "||";
+    case FGPU_OP_ADD: return "+";
+    case FGPU_OP_SUB: return "-";
+    case FGPU_OP_MUL: return "*";
+    case FGPU_OP_DIV: return "/";
+    case FGPU_OP_CONTAINS: return "contains";
+    case FGPU_OP_NOT_CONTAINS: return "not contains";
+    default: return "?";
+  }
+}
+
+const char* agg_string(int f) {  // logicalplan.AggFunc.String(), expr.go:731-750
+  switch (f) {
+    case FGPU_AGG_SUM: return "sum";
+    case FGPU_AGG_MIN: return "min";
+    case FGPU_AGG_MAX: return "max";
+    case FGPU_AGG_COUNT: return "count";
+    case FGPU_AGG_AVG: return "avg";
+    default: return "?";
+  }
+}
+
+}  // namespace
+
+struct fgpu_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int tile_rows = kTileRows;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::mutex mu;
+  std::map<std::string, Table> tables;
+};
+
+struct fgpu_query {
+  fgpu_ctx* ctx = nullptr;
+  std::string table;
+  int32_t kind = 0;
+  std::vector<ExprNode> exprs;
+  int32_t filter = -1;
+  std::vector<int32_t> group_by;
+  std::vector<fgpu_agg> aggs;
+
+  std::string expr_name(int i) const {  // Expr.Name(), expr.go:181,326,568,623
+    const ExprNode& e = exprs[size_t(i)];
+    switch (e.kind) {
+      case FGPU_EXPR_COLUMN:
+      case FGPU_EXPR_DYNCOLUMN: return e.name;
+      case FGPU_EXPR_LITERAL: {
+        if (e.lit_type == FGPU_SCALAR_INT64) return std::to_string(e.lit_i);
+        if (e.lit_type == FGPU_SCALAR_FLOAT64) {
+          char buf[64];
+          snprintf(buf, sizeof buf, "%g", e.lit_f);
+          return buf;
+        }
+        if (e.lit_type == FGPU_SCALAR_STRING) return e.lit_bytes;
+        return "null";
+      }
+      case FGPU_EXPR_BINARY: return expr_name(e.left) + " " + op_string(e.op) + " " + expr_name(e.right);
+    }
+    return "?";
+  }
+};
+
+struct KeyOut {
+  std::string name;
+  bool is_int64 = false;
+  const GlobalDict* dict = nullptr;
+  std::vector<std::string> dict_snapshot;  // values by (unified) id at execute time
+};
+
+struct fgpu_result {
+  fgpu_ctx* ctx = nullptr;
+  fgpu_stats stats{};
+  // compiled state kept for partial/merge
+  QueryDesc qd{};
+  FinalizeDesc fd{};
+  DevBuf table, qdesc_dev, aux;
+  size_t table_bytes = 0;
+  std::vector<KeyOut> keys;
+  std::vector<std::string> agg_names;
+  std::vector<uint8_t> agg_is_float;
+  // finished records
+  std::vector<std::vector<OwnedColumn>> records;
+  std::vector<int64_t> record_rows;
+  size_t next = 0;
+  bool finalized = false;
+};
+
+namespace {
+
+struct VisibleRG {
+  Part* part;
+  RowGroupHost* rg;
+};
+
+int bit_width_u32(uint64_t max_value) {
+  int w = 0;
+  while (w < 64 && (max_value >> w) != 0) w++;
+  return w;
+}
+
+// One predicate leaf on the host.
+struct LeafHost {
+  std::string column;
+  int slot = -1;  // -1: column absent from every visible row group
+  int op = 0;
+  const ExprNode* lit = nullptr;
+  const ExprNode* bin = nullptr;
+  std::vector<int8_t> by_gid;  // dictionary leaves: cached result per local global id (-1 = not evaluated)
+};
+
+bool bytes_contains(const std::string& hay, const std::string& needle) {
+  if (needle.empty()) return true;
+  return hay.find(needle) != std::string::npos;
+}
+
+// Missing-column rules, binaryscalarexpr.go:47-73 and regexpfilter.go:23-33.  Returns LM_ALL / LM_NONE.
+uint8_t missing_column_mode(const LeafHost& l) {
+  const ExprNode& lit = *l.lit;
+  switch (l.op) {
+    case FGPU_OP_EQ:
+      if (lit.lit_type == FGPU_SCALAR_STRING && !lit.lit_bytes.empty()) return LM_NONE;
+      return LM_ALL;
+    case FGPU_OP_NOT_EQ:
+      if (lit.lit_type == FGPU_SCALAR_NULL) return LM_NONE;
+      return LM_ALL;
+    case FGPU_OP_LT: case FGPU_OP_LT_EQ: case FGPU_OP_GT: case FGPU_OP_GT_EQ:
+      return LM_NONE;
+    case FGPU_OP_REGEX_MATCH:
+    case FGPU_OP_REGEX_NOT_MATCH: {
+      bool empty_match = l.bin->match ? l.bin->match(l.bin->match_user, reinterpret_cast<const uint8_t*>(""), 0) != 0 : false;
+      bool not_match = l.op == FGPU_OP_REGEX_NOT_MATCH;
+      return ((not_match && !empty_match) || (!not_match && empty_match)) ? LM_ALL : LM_NONE;
+    }
+    default:
+      return LM_ALL;  // contains / not contains fall through to "all rows" (:71)
+  }
+}
+
+// Result of a dictionary leaf for one dictionary value (non-NULL row).
+bool dict_leaf_value(const LeafHost& l, const std::string& v) {
+  const ExprNode& lit = *l.lit;
+  switch (l.op) {
+    case FGPU_OP_EQ: return lit.lit_type != FGPU_SCALAR_NULL && v == lit.lit_bytes;
+    case FGPU_OP_NOT_EQ: return lit.lit_type == FGPU_SCALAR_NULL ? true : v != lit.lit_bytes;
+    case FGPU_OP_CONTAINS:
+      return lit.lit_type == FGPU_SCALAR_NULL ? true : bytes_contains(v, lit.lit_bytes);
+    case FGPU_OP_NOT_CONTAINS:
+      return lit.lit_type == FGPU_SCALAR_NULL ? true : !bytes_contains(v, lit.lit_bytes);
+    case FGPU_OP_REGEX_MATCH:
+      return l.bin->match(l.bin->match_user, reinterpret_cast<const uint8_t*>(v.data()), v.size()) != 0;
+    case FGPU_OP_REGEX_NOT_MATCH:
+      return l.bin->match(l.bin->match_user, reinterpret_cast<const uint8_t*>(v.data()), v.size()) == 0;
+  }
+  return false;
+}
+
+struct Compiled {
+  std::vector<VisibleRG> rgs;
+  std::vector<std::string> slot_names;
+  std::vector<uint8_t> slot_types;
+  std::vector<LeafHost> leaves;
+  std::vector<uint8_t> filter_prog;
+  std::vector<KeyOut> keys;
+  std::vector<int> key_slots;
+  QueryDesc qd{};
+  std::vector<uint32_t> dense_radix;
+  uint64_t total_rows = 0;
+  uint64_t group_bound = 0;
+};
+
+int32_t compile_filter(const fgpu_query& q, int node, Compiled* c, std::map<std::string, int>& slot_of) {
+  const ExprNode& e = q.exprs[size_t(node)];
+  if (e.kind != FGPU_EXPR_BINARY) return fail(FGPU_ERR_UNSUPPORTED, "unsupported boolean expression");
+  if (e.op == FGPU_OP_AND || e.op == FGPU_OP_OR) {
+    int32_t rc = compile_filter(q, e.left, c, slot_of);
+    if (rc) return rc;
+    rc = compile_filter(q, e.right, c, slot_of);
+    if (rc) return rc;
+    c->filter_prog.push_back(e.op == FGPU_OP_AND ? 0x80 : 0x81);
+    return FGPU_OK;
+  }
+  switch (e.op) {
+    case FGPU_OP_EQ: case FGPU_OP_NOT_EQ: case FGPU_OP_LT: case FGPU_OP_LT_EQ: case FGPU_OP_GT: case FGPU_OP_GT_EQ:
+    case FGPU_OP_REGEX_MATCH: case FGPU_OP_REGEX_NOT_MATCH: case FGPU_OP_CONTAINS: case FGPU_OP_NOT_CONTAINS:
+      break;
+    default:
+      return fail(FGPU_ERR_UNSUPPORTED, std::string("unsupported filter operator ") + op_string(e.op));
+  }
+  const ExprNode& l = q.exprs[size_t(e.left)];
+  const ExprNode& r = q.exprs[size_t(e.right)];
+  if (l.kind != FGPU_EXPR_COLUMN) return fail(FGPU_ERR_INVALID, "left side of binary expression must be a column");
+  if (r.kind != FGPU_EXPR_LITERAL) return fail(FGPU_ERR_INVALID, "right side of binary expression must be a literal");
+  if ((e.op == FGPU_OP_REGEX_MATCH || e.op == FGPU_OP_REGEX_NOT_MATCH) && !e.match)
+    return fail(FGPU_ERR_INVALID, "regex leaf without a matcher");
+  if (c->leaves.size() >= size_t(kMaxLeaves)) return fail(FGPU_ERR_UNSUPPORTED, "too many predicate leaves");
+  LeafHost lh;
+  lh.column = l.name;
+  lh.op = e.op;
+  lh.lit = &r;
+  lh.bin = &e;
+  auto it = slot_of.find(l.name);
+  lh.slot = (it == slot_of.end()) ? -1 : it->second;
+  c->filter_prog.push_back(uint8_t(c->leaves.size()));
+  c->leaves.push_back(std::move(lh));
+  return FGPU_OK;
+}
+
+int32_t compile_agg_expr(const fgpu_query& q, int node, std::map<std::string, int>& slot_of, const Compiled& c,
+                         std::vector<ProgOp>* prog, bool* any_float, bool* any_int_col) {
+  const ExprNode& e = q.exprs[size_t(node)];
+  if (e.kind == FGPU_EXPR_COLUMN) {
+    auto it = slot_of.find(e.name);
+    if (it == slot_of.end()) return fail(FGPU_ERR_NOT_FOUND, "aggregate field(s) not found [\"" + e.name + "\"], aggregations are not possible without it");
+    uint8_t t = c.slot_types[size_t(it->second)];
+    if (t == ST_DICT) return fail(FGPU_ERR_UNSUPPORTED, "aggregation over a non-numeric column: " + e.name);
+    if (t == ST_F64) *any_float = true; else *any_int_col = true;
+    ProgOp op{};
+    op.op = PO_LOAD;
+    op.slot = uint8_t(it->second);
+    prog->push_back(op);
+    return FGPU_OK;
+  }
+  if (e.kind == FGPU_EXPR_LITERAL) {
+    ProgOp op{};
+    op.op = PO_CONST;
+    if (e.lit_type == FGPU_SCALAR_INT64) op.imm = e.lit_i;
+    else if (e.lit_type == FGPU_SCALAR_FLOAT64) { std::memcpy(&op.imm, &e.lit_f, 8); op.slot = 1; *any_float = true; }
+    else return fail(FGPU_ERR_UNSUPPORTED, "non-numeric literal in arithmetic expression");
+    prog->push_back(op);
+    return FGPU_OK;
+  }
+  if (e.kind == FGPU_EXPR_BINARY && e.op >= FGPU_OP_ADD && e.op <= FGPU_OP_DIV) {
+    int32_t rc = compile_agg_expr(q, e.left, slot_of, c, prog, any_float, any_int_col);
+    if (rc) return rc;
+    rc = compile_agg_expr(q, e.right, slot_of, c, prog, any_float, any_int_col);
+    if (rc) return rc;
+    ProgOp op{};
+    op.op = uint8_t(PO_ADD + (e.op - FGPU_OP_ADD));
+    prog->push_back(op);
+    return FGPU_OK;
+  }
+  return fail(FGPU_ERR_UNSUPPORTED, "unsupported aggregate expression");
+}
+
+void collect_columns(const fgpu_query& q, int node, std::vector<std::string>* out) {
+  if (node < 0) return;
+  const ExprNode& e = q.exprs[size_t(node)];
+  if (e.kind == FGPU_EXPR_COLUMN) out->push_back(e.name);
+  if (e.kind == FGPU_EXPR_BINARY) {
+    collect_columns(q, e.left, out);
+    collect_columns(q, e.right, out);
+  }
+}
+
+// Resolves the plan against the visible row groups and fills everything of QueryDesc that does
+// not need device memory.
+int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
+  auto tit = ctx->tables.find(q.table);
+  if (tit == ctx->tables.end()) return fail(FGPU_ERR_NOT_FOUND, "table not found: " + q.table);
+  Table& table = tit->second;
+  for (auto& p : table.parts) {
+    if (p->tx > tx) continue;  // index/lsm.go:416
+    for (auto& rg : p->rgs) {
+      c->rgs.push_back({p.get(), &rg});
+      c->total_rows += rg.n_rows;
+    }
+  }
+  // every column name present in a visible row group, in name order, with its type
+  std::map<std::string, uint8_t> present;
+  for (const VisibleRG& v : c->rgs) {
+    for (auto& kv : v.rg->cols) {
+      uint8_t t = kv.second.phys == PT_BYTE_ARRAY ? ST_DICT : (kv.second.phys == PT_DOUBLE ? ST_F64 : ST_I64);
+      if (kv.second.phys != PT_BYTE_ARRAY && kv.second.phys != PT_DOUBLE && kv.second.phys != PT_INT64) t = 0xff;
+      auto it = present.find(kv.first);
+      if (it == present.end()) present.emplace(kv.first, t);
+      else if (it->second != t) return fail(FGPU_ERR_UNSUPPORTED, "column " + kv.first + " changes type between parts");
+    }
+  }
+  std::map<std::string, int> slot_of;
+  auto want = [&](const std::string& name) -> int32_t {
+    if (slot_of.count(name)) return FGPU_OK;
+    auto it = present.find(name);
+    if (it == present.end()) return FGPU_OK;  // absent everywhere: handled by the callers
+    if (it->second == 0xff) return fail(FGPU_ERR_UNSUPPORTED, "column " + name + " has a type the GPU engine does not read");
+    if (c->slot_names.size() >= size_t(kMaxSlots)) return fail(FGPU_ERR_UNSUPPORTED, "query touches too many columns");
+    slot_of[name] = int(c->slot_names.size());
+    c->slot_names.push_back(name);
+    c->slot_types.push_back(it->second);
+    return FGPU_OK;
+  };
+  // group-by / distinct columns
+  std::vector<std::string> key_names;
+  for (int32_t g : q.group_by) {
+    const ExprNode& e = q.exprs[size_t(g)];
+    if (e.kind == FGPU_EXPR_COLUMN) {
+      if (present.count(e.name)) key_names.push_back(e.name);
+    } else if (e.kind == FGPU_EXPR_DYNCOLUMN) {
+      std::string prefix = e.name + ".";  // DynamicColumn.MatchColumn, expr.go:564
+      for (auto& kv : present)
+        if (kv.first.compare(0, prefix.size(), prefix) == 0) key_names.push_back(kv.first);
+    } else {
+      return fail(FGPU_ERR_UNSUPPORTED, "computed group-by expressions are not supported on the GPU path");
+    }
+  }
+  {
+    std::vector<std::string> uniq;
+    for (auto& n : key_names)
+      if (std::find(uniq.begin(), uniq.end(), n) == uniq.end()) uniq.push_back(n);
+    key_names.swap(uniq);
+  }
+  if (key_names.size() > size_t(kMaxKeys)) return fail(FGPU_ERR_UNSUPPORTED, "too many group-by columns");
+  for (auto& n : key_names) {
+    int32_t rc = want(n);
+    if (rc) return rc;
+  }
+  // filter + aggregate input columns
+  std::vector<std::string> cols;
+  collect_columns(q, q.filter, &cols);
+  for (const fgpu_agg& a : q.aggs) collect_columns(q, a.expr, &cols);
+  for (auto& n : cols) {
+    int32_t rc = want(n);
+    if (rc) return rc;
+  }
+  QueryDesc& qd = c->qd;
+  qd.n_slots = int32_t(c->slot_names.size());
+  for (int s = 0; s < qd.n_slots; s++) {
+    qd.slot_type[s] = c->slot_types[size_t(s)];
+    qd.slot_numbuf[s] = -1;
+  }
+  // filter
+  if (q.filter >= 0) {
+    int32_t rc = compile_filter(q, q.filter, c, slot_of);
+    if (rc) return rc;
+    if (c->filter_prog.size() > size_t(kMaxFilterProg)) return fail(FGPU_ERR_UNSUPPORTED, "filter expression too large");
+    // stack depth check (the kernel keeps the stack in 32 bits)
+    int depth = 0, maxd = 0;
+    for (uint8_t op : c->filter_prog) {
+      if (op < 0x80) depth++; else depth--;
+      maxd = std::max(maxd, depth);
+    }
+    if (maxd > 30) return fail(FGPU_ERR_UNSUPPORTED, "filter expression too deep");
+    qd.n_filter_prog = int32_t(c->filter_prog.size());
+    std::memcpy(qd.filter_prog, c->filter_prog.data(), c->filter_prog.size());
+  }
+  qd.n_leaves = int32_t(c->leaves.size());
+  for (int l = 0; l < qd.n_leaves; l++) {
+    LeafHost& lh = c->leaves[size_t(l)];
+    LeafDesc& ld = qd.leaves[l];
+    ld.slot = uint8_t(lh.slot < 0 ? 0xff : lh.slot);
+    ld.op = uint8_t(lh.op);
+    if (lh.slot < 0) continue;
+    qd.slot_used_by_leaf[lh.slot] = 1;
+    uint8_t st = c->slot_types[size_t(lh.slot)];
+    const ExprNode& lit = *lh.lit;
+    if (st == ST_DICT) {
+      switch (lh.op) {
+        case FGPU_OP_EQ: case FGPU_OP_NOT_EQ: case FGPU_OP_CONTAINS: case FGPU_OP_NOT_CONTAINS:
+          if (lit.lit_type != FGPU_SCALAR_NULL && lit.lit_type != FGPU_SCALAR_STRING)
+            return fail(FGPU_ERR_UNSUPPORTED, "dictionary column compared with a non-string literal");
+          break;
+        case FGPU_OP_REGEX_MATCH: case FGPU_OP_REGEX_NOT_MATCH:
+          break;
+        default:  // binaryscalarexpr.go:100-108
+          return fail(FGPU_ERR_INVALID, std::string("unsupported operator: ") + op_string(lh.op));
+      }
+    } else {
+      if (lh.op < FGPU_OP_EQ || lh.op > FGPU_OP_GT_EQ)
+        return fail(FGPU_ERR_UNSUPPORTED, std::string("operator ") + op_string(lh.op) + " on a numeric column");
+      if (lit.lit_type == FGPU_SCALAR_STRING) return fail(FGPU_ERR_UNSUPPORTED, "numeric column compared with a string literal");
+      ld.cmp_float = (st == ST_F64) || lit.lit_type == FGPU_SCALAR_FLOAT64;
+      ld.lit_i = lit.lit_i;
+      ld.lit_f = lit.lit_type == FGPU_SCALAR_FLOAT64 ? lit.lit_f : double(lit.lit_i);
+    }
+  }
+  // aggregates
+  if (q.aggs.size() > size_t(kMaxAggs)) return fail(FGPU_ERR_UNSUPPORTED, "too many aggregates");
+  qd.n_aggs = int32_t(q.aggs.size());
+  std::vector<ProgOp> prog;
+  for (size_t a = 0; a < q.aggs.size(); a++) {
+    AggDesc& ad = qd.aggs[a];
+    int f = q.aggs[a].func;
+    if (f != FGPU_AGG_SUM && f != FGPU_AGG_MIN && f != FGPU_AGG_MAX && f != FGPU_AGG_COUNT)
+      return fail(FGPU_ERR_UNSUPPORTED, std::string("aggregate function not supported on the GPU path: ") + agg_string(f));
+    ad.func = uint8_t(f);
+    bool any_float = false, any_int_col = false;
+    size_t off = prog.size();
+    int32_t rc = compile_agg_expr(q, q.aggs[a].expr, slot_of, *c, &prog, &any_float, &any_int_col);
+    if (rc) return rc;
+    if (any_float && any_int_col) return fail(FGPU_ERR_UNSUPPORTED, "arithmetic mixes int64 and float64 columns");
+    if (any_float) {  // integer literals take part as doubles
+      for (size_t p = off; p < prog.size(); p++)
+        if (prog[p].op == PO_CONST && prog[p].slot == 0) {
+          double d = double(prog[p].imm);
+          std::memcpy(&prog[p].imm, &d, 8);
+        }
+    }
+    ad.is_float = any_float;
+    ad.prog_off = uint8_t(off);
+    ad.prog_len = uint8_t(prog.size() - off);
+    // the aggregated column must exist in every record (aggregate.go:367-380)
+    std::vector<std::string> acols;
+    collect_columns(q, q.aggs[a].expr, &acols);
+    for (const VisibleRG& v : c->rgs)
+      for (auto& n : acols)
+        if (!v.rg->cols.count(n))
+          return fail(FGPU_ERR_NOT_FOUND, "aggregate field(s) not found [\"" + n + "\"], aggregations are not possible without it");
+  }
+  if (prog.size() > size_t(kMaxProg)) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expressions too large");
+  for (size_t p = 0; p < prog.size(); p++) qd.prog[p] = prog[p];
+  // numeric staging buffers: any numeric slot that some visible chunk stores nullable or dictionary-encoded
+  int nb = 0;
+  for (int s = 0; s < qd.n_slots; s++) {
+    if (qd.slot_type[s] == ST_DICT) continue;
+    bool need = false;
+    for (const VisibleRG& v : c->rgs) {
+      auto it = v.rg->cols.find(c->slot_names[size_t(s)]);
+      if (it == v.rg->cols.end()) continue;
+      if (it->second.desc.kind != CK_PLAIN64 || it->second.desc.has_nulls) need = true;
+    }
+    if (need) {
+      if (nb >= kMaxNumBufs) return fail(FGPU_ERR_UNSUPPORTED, "too many nullable / dictionary-encoded numeric columns in one query");
+      qd.slot_numbuf[s] = int8_t(nb++);
+    }
+  }
+  qd.n_numbufs = uint32_t(nb);
+  // keys and table shape
+  qd.n_keys = int32_t(key_names.size());
+  bool all_dict = true;
+  long double product = 1;
+  c->dense_radix.assign(key_names.size(), 0);
+  for (size_t k = 0; k < key_names.size(); k++) {
+    int slot = slot_of.at(key_names[k]);
+    KeyOut ko;
+    ko.name = key_names[k];
+    ko.is_int64 = c->slot_types[size_t(slot)] != ST_DICT;
+    if (c->slot_types[size_t(slot)] == ST_F64) return fail(FGPU_ERR_UNSUPPORTED, "float64 group-by columns are not supported");
+    if (ko.is_int64) {
+      all_dict = false;
+      product *= 1e18L;
+    } else {
+      ko.dict = &table.dicts.at(key_names[k]);
+      uint32_t card = ko.dict->cardinality();
+      c->dense_radix[k] = card + 1;
+      product *= (long double)(card + 1);
+    }
+    c->keys.push_back(std::move(ko));
+    c->key_slots.push_back(slot);
+    qd.keys[k].slot = uint8_t(slot);
+    qd.keys[k].is_int64 = c->keys.back().is_int64;
+  }
+  long double bound = std::min<long double>(product, (long double)std::max<uint64_t>(c->total_rows, 1));
+  c->group_bound = uint64_t(bound);
+  const uint64_t kDenseMax = 1ull << 22;
+  if (all_dict && product <= (long double)kDenseMax) {
+    qd.table_mode = TM_DENSE;
+    qd.key_words = 1;
+    uint64_t stride = 1;
+    for (size_t k = key_names.size(); k-- > 0;) {
+      qd.keys[k].dense_stride = uint32_t(stride);
+      stride *= c->dense_radix[k];
+    }
+    qd.table_slots = uint32_t(std::max<uint64_t>(stride, 1));
+  } else {
+    qd.table_mode = TM_HASH;
+    int word = 0, used = 0;
+    for (size_t k = 0; k < key_names.size(); k++) {
+      if (c->keys[k].is_int64) continue;
+      int bits = std::max(1, bit_width_u32(c->dense_radix[k] - 1));
+      if (used + bits > 64) { word++; used = 0; }
+      qd.keys[k].word = uint8_t(word);
+      qd.keys[k].shift = uint8_t(used);
+      qd.keys[k].bits = uint32_t(bits);
+      used += bits;
+    }
+    int words = (used > 0 || word > 0) ? word + 1 : 0;
+    for (size_t k = 0; k < key_names.size(); k++) {
+      if (!c->keys[k].is_int64) continue;
+      qd.keys[k].word = uint8_t(words++);
+      qd.keys[k].shift = 0;
+      qd.keys[k].bits = 64;
+    }
+    if (words > kMaxKeyWords) return fail(FGPU_ERR_UNSUPPORTED, "group key wider than the packed-key limit");
+    qd.key_words = std::max(words, 1);
+    uint64_t cap = 1024;
+    while (cap < 2 * c->group_bound && cap < (1ull << 28)) cap <<= 1;
+    qd.table_slots = uint32_t(cap);
+  }
+  qd.tile_rows = ctx->tile_rows;
+  qd.n_rg = int32_t(c->rgs.size());
+  return FGPU_OK;
+}
+
+size_t table_layout(const QueryDesc& qd, size_t* off_aggs, size_t* off_tags, size_t* off_keys) {
+  size_t S = qd.table_slots;
+  int n_stored = 0;
+  for (int a = 0; a < qd.n_aggs; a++)
+    if (qd.aggs[a].func != FGPU_AGG_COUNT) n_stored++;
+  *off_aggs = S * 8;
+  *off_tags = S * 8 * size_t(1 + n_stored);
+  size_t tags = (qd.table_mode == TM_HASH) ? ((S * 4 + 7) & ~size_t(7)) : 0;
+  *off_keys = *off_tags + tags;
+  size_t keys = (qd.table_mode == TM_HASH) ? S * 8 * size_t(qd.key_words) : 0;
+  return *off_keys + keys;
+}
+
+void bind_table(QueryDesc* qd, uint8_t* base) {
+  size_t off_aggs, off_tags, off_keys;
+  table_layout(*qd, &off_aggs, &off_tags, &off_keys);
+  size_t S = qd->table_slots;
+  qd->t_rows = reinterpret_cast<unsigned long long*>(base);
+  int pos = 0;
+  for (int a = 0; a < kMaxAggs; a++) qd->t_agg[a] = nullptr;
+  for (int a = 0; a < qd->n_aggs; a++) {
+    if (qd->aggs[a].func == FGPU_AGG_COUNT) continue;
+    qd->t_agg[a] = reinterpret_cast<long long*>(base + off_aggs + size_t(pos) * S * 8);
+    pos++;
+  }
+  qd->t_tag = qd->table_mode == TM_HASH ? reinterpret_cast<uint32_t*>(base + off_tags) : nullptr;
+  qd->t_keys = qd->table_mode == TM_HASH ? reinterpret_cast<unsigned long long*>(base + off_keys) : nullptr;
+}
+
+// Runs init + scan.  On success the result owns the device table.
+int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* res) {
+  Compiled c;
+  int32_t rc = compile(ctx, q, tx, &c);
+  if (rc) return rc;
+  QueryDesc& qd = c.qd;
+  const int n_rg = qd.n_rg, n_slots = qd.n_slots, n_leaves = qd.n_leaves;
+  fgpu_stats& st = res->stats;
+  st.rows_scanned = c.total_rows;
+  st.row_groups = uint32_t(n_rg);
+
+  // ---- per row group tables: chunk descriptors, leaf runtime, leaf LUTs, tile prefix -----------
+  std::vector<ChunkDesc> chunks(size_t(n_rg) * std::max(n_slots, 1));
+  std::vector<LeafRt> lrt(size_t(n_rg) * std::max(n_leaves, 1));
+  std::vector<uint32_t> first_tile(size_t(n_rg) + 1), rg_rows(std::max(n_rg, 1));
+  std::vector<uint8_t> lutbytes;
+  std::vector<std::pair<size_t, size_t>> lut_fix;  // (index into lrt, offset into lutbytes)
+  uint32_t tiles = 0;
+  for (int g = 0; g < n_rg; g++) {
+    RowGroupHost& rg = *c.rgs[size_t(g)].rg;
+    first_tile[size_t(g)] = tiles;
+    rg_rows[size_t(g)] = rg.n_rows;
+    tiles += (rg.n_rows + uint32_t(ctx->tile_rows) - 1) / uint32_t(ctx->tile_rows);
+    for (int s = 0; s < n_slots; s++) {
+      ChunkDesc d{};
+      d.kind = CK_ABSENT;
+      d.n_rows = rg.n_rows;
+      auto it = rg.cols.find(c.slot_names[size_t(s)]);
+      if (it != rg.cols.end()) {
+        ChunkHost& ch = it->second;
+        if (!ch.error.empty())
+          return fail(FGPU_ERR_UNSUPPORTED, "column " + c.slot_names[size_t(s)] + ": " + ch.error);
+        d = ch.desc;
+        st.algorithmic_bytes += ch.stored_bytes;
+        st.metadata_bytes += ch.meta_bytes;
+      }
+      chunks[size_t(g) * n_slots + s] = d;
+    }
+    for (int l = 0; l < n_leaves; l++) {
+      LeafHost& lh = c.leaves[size_t(l)];
+      LeafRt rt{};
+      auto it = lh.slot < 0 ? rg.cols.end() : rg.cols.find(lh.column);
+      if (it == rg.cols.end()) {
+        rt.mode = missing_column_mode(lh);
+      } else if (c.slot_types[size_t(lh.slot)] == ST_DICT) {
+        rt.mode = LM_EVAL;
+        rt.null_result = (lh.op == FGPU_OP_EQ && lh.lit->lit_type == FGPU_SCALAR_NULL) ? 1 : 0;
+        const GlobalDict& gd = ctx->tables.at(q.table).dicts.at(lh.column);
+        if (lh.by_gid.size() < gd.values.size()) lh.by_gid.resize(gd.values.size(), -1);
+        const ChunkHost& ch = it->second;
+        size_t off = lutbytes.size();
+        lutbytes.resize(off + ch.lut_host.size() + 1);
+        for (size_t i = 0; i < ch.lut_host.size(); i++) {
+          uint32_t gid = ch.lut_host[i];
+          if (lh.by_gid[gid] < 0) lh.by_gid[gid] = dict_leaf_value(lh, gd.values[gid]) ? 1 : 0;
+          lutbytes[off + i] = uint8_t(lh.by_gid[gid]);
+        }
+        lut_fix.emplace_back(size_t(g) * n_leaves + l, off);
+      } else {
+        rt.mode = (lh.lit->lit_type == FGPU_SCALAR_NULL) ? LM_NONE : LM_EVAL;
+      }
+      lrt[size_t(g) * n_leaves + l] = rt;
+    }
+  }
+  first_tile[size_t(n_rg)] = tiles;
+  qd.n_tiles = tiles;
+
+  // ---- device memory -----------------------------------------------------------------------
+  size_t off_aggs, off_tags, off_keys;
+  size_t tbytes = table_layout(qd, &off_aggs, &off_tags, &off_keys);
+  CUDA_TRY(res->table.alloc(tbytes));
+  res->table_bytes = tbytes;
+  bind_table(&qd, static_cast<uint8_t*>(res->table.p));
+
+  auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  size_t o_chunks = 0;
+  size_t o_lrt = align16(o_chunks + chunks.size() * sizeof(ChunkDesc));
+  size_t o_first = align16(o_lrt + lrt.size() * sizeof(LeafRt));
+  size_t o_rows = align16(o_first + first_tile.size() * 4);
+  size_t o_lut = align16(o_rows + rg_rows.size() * 4);
+  size_t o_cnt = align16(o_lut + lutbytes.size());
+  size_t aux_bytes = o_cnt + 64;
+  CUDA_TRY(res->aux.alloc(aux_bytes));
+  uint8_t* aux = static_cast<uint8_t*>(res->aux.p);
+  for (auto& fx : lut_fix) lrt[fx.first].lut = aux + o_lut + fx.second;
+  std::vector<uint8_t> hostaux(aux_bytes, 0);
+  std::memcpy(hostaux.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
+  std::memcpy(hostaux.data() + o_lrt, lrt.data(), lrt.size() * sizeof(LeafRt));
+  std::memcpy(hostaux.data() + o_first, first_tile.data(), first_tile.size() * 4);
+  std::memcpy(hostaux.data() + o_rows, rg_rows.data(), rg_rows.size() * 4);
+  if (!lutbytes.empty()) std::memcpy(hostaux.data() + o_lut, lutbytes.data(), lutbytes.size());
+  qd.chunks = reinterpret_cast<const ChunkDesc*>(aux + o_chunks);
+  qd.leaf_rt = reinterpret_cast<const LeafRt*>(aux + o_lrt);
+  qd.rg_first_tile = reinterpret_cast<const uint32_t*>(aux + o_first);
+  qd.rg_rows = reinterpret_cast<const uint32_t*>(aux + o_rows);
+  qd.counters = reinterpret_cast<unsigned long long*>(aux + o_cnt);
+  CUDA_TRY(res->qdesc_dev.alloc(sizeof(QueryDesc)));
+
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
+  CUDA_TRY(cudaMemcpyAsync(aux, hostaux.data(), aux_bytes, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(res->qdesc_dev.p, &qd, sizeof(QueryDesc), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(launch_table_init(qd, s));
+  CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
+  CUDA_TRY(launch_scan(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
+  CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
+  st.kernel_launches += 1 + (tiles ? 1 : 0);
+  st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
+  unsigned long long counters[8] = {0};
+  CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // hostaux / counters stay valid until here
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+  st.scan_kernel_ms = ms;
+  st.rows_selected = counters[0];
+  st.d2h_bytes += 64;
+  if (counters[1]) return fail(FGPU_ERR_UNSUPPORTED, "aggregate hash table overflow (more groups than the sized capacity)");
+
+  // keep what finalize / merge need
+  res->qd = qd;
+  res->keys = std::move(c.keys);
+  for (KeyOut& k : res->keys) {
+    if (k.dict) {
+      uint32_t card = k.dict->cardinality();
+      k.dict_snapshot.reserve(card);
+      for (uint32_t i = 0; i < card; i++) k.dict_snapshot.push_back(k.dict->value(i));
+      k.dict = nullptr;
+    }
+  }
+  for (size_t a = 0; a < q.aggs.size(); a++) {
+    res->agg_names.push_back(std::string(agg_string(q.aggs[a].func)) + "(" + q.expr_name(q.aggs[a].expr) + ")");
+    // Count yields int64; Sum/Min/Max keep the input type (aggregate.go:734-950)
+    res->agg_is_float.push_back(qd.aggs[a].func != FGPU_AGG_COUNT && qd.aggs[a].is_float);
+  }
+  FinalizeDesc& fd = res->fd;
+  fd = FinalizeDesc{};
+  fd.table_mode = qd.table_mode;
+  fd.key_words = qd.key_words;
+  fd.n_keys = qd.n_keys;
+  fd.n_aggs = qd.n_aggs;
+  fd.table_slots = qd.table_slots;
+  for (int k = 0; k < qd.n_keys; k++) {
+    fd.keys[k] = qd.keys[k];
+    fd.dense_radix[k] = c.dense_radix[size_t(k)] ? c.dense_radix[size_t(k)] : 1;
+  }
+  fd.t_rows = qd.t_rows;
+  for (int a = 0; a < kMaxAggs; a++) fd.t_agg[a] = qd.t_agg[a];
+  fd.t_tag = qd.t_tag;
+  fd.t_keys = qd.t_keys;
+  return FGPU_OK;
+}
+
+// Table -> host columns -> one Arrow record.
+int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
+  FinalizeDesc& fd = res->fd;
+  cudaStream_t s = ctx->stream;
+  // Upper bound of result rows: every slot could be occupied; count first to size the output.
+  // (k_finalize with max_out == 0 only counts.)
+  DevBuf cnt;
+  CUDA_TRY(cnt.alloc(16));
+  CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
+  fd.out_count = static_cast<unsigned int*>(cnt.p);
+  fd.max_out = 0;
+  fd.out_keys = nullptr;
+  fd.out_aggs = nullptr;
+  fd.out_rows = nullptr;
+  CUDA_TRY(launch_finalize(fd, s));
+  unsigned int n_groups = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_groups, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  res->stats.kernel_launches += 1;
+  res->stats.groups = n_groups;
+  const size_t G = n_groups;
+  const int nk = fd.n_keys, na = fd.n_aggs;
+  std::vector<long long> h_keys(size_t(nk) * G), h_aggs(size_t(na) * G);
+  if (G > 0) {
+    DevBuf out;
+    size_t bytes = (size_t(nk) + size_t(na) + 1) * G * 8;
+    CUDA_TRY(out.alloc(bytes));
+    CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
+    fd.max_out = n_groups;
+    fd.out_keys = static_cast<long long*>(out.p);
+    fd.out_aggs = fd.out_keys + size_t(nk) * G;
+    fd.out_rows = reinterpret_cast<unsigned long long*>(fd.out_aggs + size_t(na) * G);
+    CUDA_TRY(launch_finalize(fd, s));
+    res->stats.kernel_launches += 1;
+    if (nk) CUDA_TRY(cudaMemcpyAsync(h_keys.data(), fd.out_keys, size_t(nk) * G * 8, cudaMemcpyDeviceToHost, s));
+    if (na) CUDA_TRY(cudaMemcpyAsync(h_aggs.data(), fd.out_aggs, size_t(na) * G * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    res->stats.d2h_bytes += (size_t(nk) + size_t(na)) * G * 8;
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+  res->stats.total_device_ms = ms;
+
+  // ---- build Arrow columns (aggregate.go:551-625: group columns first, then aggregates) --------
+  std::vector<OwnedColumn> cols;
+  for (int k = 0; k < nk; k++) {
+    const KeyOut& ko = res->keys[size_t(k)];
+    OwnedColumn col;
+    col.name = ko.name;
+    col.length = int64_t(G);
+    const long long* codes = h_keys.data() + size_t(k) * G;
+    if (ko.is_int64) {
+      col.format = "l";
+      col.data.resize(G * 8);
+      std::memcpy(col.data.data(), codes, G * 8);
+    } else {
+      // dictionary<uint32, binary> holding only the values this result uses
+      col.format = "I";
+      col.validity.assign((G + 7) / 8, 0);
+      col.data.resize(G * 4);
+      uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
+      std::vector<uint32_t> used;
+      used.reserve(G);
+      for (size_t i = 0; i < G; i++)
+        if (codes[i] != 0) used.push_back(uint32_t(codes[i] - 1));
+      std::sort(used.begin(), used.end());
+      used.erase(std::unique(used.begin(), used.end()), used.end());
+      for (size_t i = 0; i < G; i++) {
+        if (codes[i] == 0) {
+          idx[i] = 0;
+          col.null_count++;
+        } else {
+          idx[i] = uint32_t(std::lower_bound(used.begin(), used.end(), uint32_t(codes[i] - 1)) - used.begin());
+          set_bit(col.validity, int64_t(i));
+        }
+      }
+      if (col.null_count == 0) col.validity.clear();
+      auto dict = std::make_unique<OwnedColumn>();
+      dict->format = "z";
+      dict->length = int64_t(used.size());
+      dict->offsets.push_back(0);
+      for (uint32_t gid : used) {
+        const std::string& v = ko.dict_snapshot[gid];
+        dict->data.insert(dict->data.end(), v.begin(), v.end());
+        dict->offsets.push_back(int32_t(dict->data.size()));
+      }
+      col.dictionary = std::move(dict);
+    }
+    cols.push_back(std::move(col));
+  }
+  for (int a = 0; a < na; a++) {
+    OwnedColumn col;
+    col.name = res->agg_names[size_t(a)];
+    col.format = res->agg_is_float[size_t(a)] ? "g" : "l";
+    col.length = int64_t(G);
+    col.data.resize(G * 8);
+    std::memcpy(col.data.data(), h_aggs.data() + size_t(a) * G, G * 8);
+    cols.push_back(std::move(col));
+  }
+  res->stats.algorithmic_bytes += (size_t(nk) + size_t(na)) * G * 8;
+  if (G > 0 || true) {
+    res->records.push_back(std::move(cols));
+    res->record_rows.push_back(int64_t(G));
+  }
+  res->finalized = true;
+  res->table.reset();
+  res->aux.reset();
+  res->qdesc_dev.reset();
+  return FGPU_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+extern "C" {
+
+const char* fgpu_last_error(void) { return g_err.c_str(); }
+int32_t fgpu_abi_version(void) { return FGPU_ABI_VERSION; }
+
+int32_t fgpu_init(const fgpu_config* cfg, fgpu_ctx** out) {
+  if (!cfg || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  if (cfg->abi_version != FGPU_ABI_VERSION) return fail(FGPU_ERR_INVALID, "ABI version mismatch");
+  if (cfg->tile_rows != 0 && cfg->tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 or 2048");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(FGPU_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (cfg->device < 0 || cfg->device >= n) return fail(FGPU_ERR_INVALID, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  auto ctx = std::make_unique<fgpu_ctx>();
+  ctx->device = cfg->device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
+  *out = ctx.release();
+  return FGPU_OK;
+}
+
+int32_t fgpu_shutdown(fgpu_ctx* ctx) {
+  if (!ctx) return FGPU_OK;
+  cudaSetDevice(ctx->device);
+  for (auto& t : ctx->tables)
+    for (auto& p : t.second.parts)
+      if (p->dev) cudaFree(p->dev);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return FGPU_OK;
+}
+
+int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx, const uint8_t* file,
+                              uint64_t len, int32_t flags) {
+  if (!ctx || !table || !file) return fail(FGPU_ERR_INVALID, "null argument");
+  if (flags != FGPU_PUT_DEFAULT) return fail(FGPU_ERR_UNSUPPORTED, "put flags other than FGPU_PUT_DEFAULT are not implemented yet");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Table& t = ctx->tables[table];
+  for (auto& p : t.parts)
+    if (p->id == part_id) return fail(FGPU_ERR_INVALID, "part id already registered");
+  auto part = std::make_unique<Part>();
+  part->id = part_id;
+  part->tx = tx;
+  std::string err;
+  if (!build_part_image(file, len, ctx->tile_rows, &t, part.get(), &err)) return fail(FGPU_ERR_PARQUET, err);
+  void* dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, part->image.size()));
+  cudaError_t e = cudaMemcpyAsync(dev, part->image.data(), part->image.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    return fail(FGPU_ERR_CUDA, std::string("part upload: ") + cudaGetErrorString(e));
+  }
+  part->dev = dev;
+  part->dev_bytes = part->image.size();
+  patch_part_pointers(part.get(), static_cast<const uint8_t*>(dev));
+  std::vector<uint8_t>().swap(part->image);
+  // new dictionary entries invalidate a previously installed cross-rank id space
+  for (auto& d : t.dicts)
+    if (!d.second.unified.empty() && d.second.unified.size() != d.second.values.size()) {
+      d.second.unified.clear();
+      d.second.unified_values.clear();
+    }
+  t.parts.push_back(std::move(part));
+  return FGPU_OK;
+}
+
+int32_t fgpu_part_put_arrow(fgpu_ctx*, const char*, uint64_t, uint64_t, struct ArrowSchema* schema, struct ArrowArray* array) {
+  if (schema && schema->release) schema->release(schema);
+  if (array && array->release) array->release(array);
+  return fail(FGPU_ERR_UNSUPPORTED, "L0 Arrow-record parts are not implemented yet (SURVEY.md 8f N1)");
+}
+
+int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {
+  if (!ctx || !table) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->tables.find(table);
+  if (it == ctx->tables.end()) return fail(FGPU_ERR_NOT_FOUND, std::string("table not found: ") + table);
+  auto& parts = it->second.parts;
+  for (size_t i = 0; i < parts.size(); i++) {
+    if (parts[i]->id == part_id) {
+      cudaSetDevice(ctx->device);
+      if (parts[i]->dev) cudaFree(parts[i]->dev);
+      parts.erase(parts.begin() + long(i));
+      return FGPU_OK;
+    }
+  }
+  return fail(FGPU_ERR_NOT_FOUND, "part not found");
+}
+
+int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
+  if (!ctx || !table) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->tables.find(table);
+  if (it == ctx->tables.end()) return FGPU_OK;
+  cudaSetDevice(ctx->device);
+  for (auto& p : it->second.parts)
+    if (p->dev) cudaFree(p->dev);
+  ctx->tables.erase(it);
+  return FGPU_OK;
+}
+
+int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** out) {
+  if (!ctx || !plan || !out || !plan->table) return fail(FGPU_ERR_INVALID, "null argument");
+  if (plan->kind != FGPU_PLAN_AGGREGATE && plan->kind != FGPU_PLAN_DISTINCT)
+    return fail(FGPU_ERR_UNSUPPORTED, "only AGGREGATE and DISTINCT plans are implemented");
+  auto q = std::make_unique<fgpu_query>();
+  q->ctx = ctx;
+  q->table = plan->table;
+  q->kind = plan->kind;
+  q->filter = plan->filter;
+  auto check = [&](int32_t i) { return i >= 0 && i < plan->n_exprs; };
+  for (int32_t i = 0; i < plan->n_exprs; i++) {
+    const fgpu_expr& e = plan->exprs[i];
+    ExprNode n;
+    n.kind = e.kind;
+    n.op = e.op;
+    n.left = e.left;
+    n.right = e.right;
+    if (e.kind == FGPU_EXPR_COLUMN || e.kind == FGPU_EXPR_DYNCOLUMN) {
+      if (!e.name) return fail(FGPU_ERR_INVALID, "column expression without a name");
+      n.name = e.name;
+    } else if (e.kind == FGPU_EXPR_LITERAL) {
+      n.lit_type = e.literal.type;
+      n.lit_i = e.literal.i64;
+      n.lit_f = e.literal.f64;
+      if (e.literal.type == FGPU_SCALAR_STRING) {
+        if (e.literal.len && !e.literal.bytes) return fail(FGPU_ERR_INVALID, "string literal without bytes");
+        n.lit_bytes.assign(reinterpret_cast<const char*>(e.literal.bytes), size_t(e.literal.len));
+      }
+    } else if (e.kind == FGPU_EXPR_BINARY) {
+      if (!check(e.left) || !check(e.right) || e.left >= i || e.right >= i)
+        return fail(FGPU_ERR_INVALID, "binary expression children must precede their parent");
+      n.match = e.match;
+      n.match_user = e.match_user;
+    } else {
+      return fail(FGPU_ERR_INVALID, "unknown expression kind");
+    }
+    q->exprs.push_back(std::move(n));
+  }
+  if (plan->filter >= 0 && !check(plan->filter)) return fail(FGPU_ERR_INVALID, "filter index out of range");
+  for (int32_t i = 0; i < plan->n_group_by; i++) {
+    if (!check(plan->group_by[i])) return fail(FGPU_ERR_INVALID, "group-by index out of range");
+    q->group_by.push_back(plan->group_by[i]);
+  }
+  if (plan->kind == FGPU_PLAN_DISTINCT && plan->n_aggs != 0) return fail(FGPU_ERR_INVALID, "DISTINCT plan with aggregates");
+  if (plan->kind == FGPU_PLAN_AGGREGATE && plan->n_aggs == 0) return fail(FGPU_ERR_INVALID, "AGGREGATE plan without aggregates");
+  for (int32_t i = 0; i < plan->n_aggs; i++) {
+    if (!check(plan->aggs[i].expr)) return fail(FGPU_ERR_INVALID, "aggregate expression index out of range");
+    q->aggs.push_back(plan->aggs[i]);
+  }
+  *out = q.release();
+  return FGPU_OK;
+}
+
+int32_t fgpu_query_free(fgpu_query* q) {
+  delete q;
+  return FGPU_OK;
+}
+
+int32_t fgpu_query_execute(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out) {
+  if (!ctx || !q || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto res = std::make_unique<fgpu_result>();
+  res->ctx = ctx;
+  int32_t rc = run_scan(ctx, *q, tx_watermark, res.get());
+  if (rc) return rc;
+  rc = finalize_result(ctx, res.get());
+  if (rc) return rc;
+  *out = res.release();
+  return FGPU_OK;
+}
+
+int32_t fgpu_query_execute_partial(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out, void** dev_ptr,
+                                   uint64_t* nbytes) {
+  if (!ctx || !q || !out || !dev_ptr || !nbytes) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto res = std::make_unique<fgpu_result>();
+  res->ctx = ctx;
+  int32_t rc = run_scan(ctx, *q, tx_watermark, res.get());
+  if (rc) return rc;
+  *dev_ptr = res->table.p;
+  *nbytes = res->table_bytes;
+  *out = res.release();
+  return FGPU_OK;
+}
+
+int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* gathered, uint64_t nbytes, int32_t n) {
+  if (!ctx || !r) return fail(FGPU_ERR_INVALID, "null argument");
+  if (r->finalized) return fail(FGPU_ERR_INVALID, "result already finalised");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (n > 0) {
+    if (!gathered) return fail(FGPU_ERR_INVALID, "null gathered buffer");
+    if (nbytes != r->table_bytes) return fail(FGPU_ERR_INVALID, "partial table size differs between ranks (dictionaries not unified?)");
+    // Start from an empty table and fold every rank's partial in, this rank's own included.
+    DevBuf merged;
+    CUDA_TRY(merged.alloc(r->table_bytes));
+    QueryDesc qd = r->qd;
+    bind_table(&qd, static_cast<uint8_t*>(merged.p));
+    CUDA_TRY(launch_table_init(qd, ctx->stream));
+    for (int32_t i = 0; i < n; i++) {
+      CUDA_TRY(launch_merge(qd, static_cast<const uint8_t*>(gathered) + size_t(i) * nbytes, ctx->stream));
+      r->stats.kernel_launches++;
+    }
+    unsigned long long counters[8] = {0};
+    CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (counters[1]) return fail(FGPU_ERR_UNSUPPORTED, "aggregate hash table overflow while merging partials");
+    std::swap(r->table.p, merged.p);
+    std::swap(r->table.n, merged.n);
+    r->qd = qd;
+    r->fd.t_rows = qd.t_rows;
+    for (int a = 0; a < kMaxAggs; a++) r->fd.t_agg[a] = qd.t_agg[a];
+    r->fd.t_tag = qd.t_tag;
+    r->fd.t_keys = qd.t_keys;
+  }
+  return finalize_result(ctx, r);
+}
+
+int32_t fgpu_result_next(fgpu_result* r, struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  if (!r || !out_schema || !out_array) return fail(FGPU_ERR_INVALID, "null argument");
+  if (!r->finalized) return fail(FGPU_ERR_INVALID, "partial result: call fgpu_result_merge_partials first");
+  if (r->next >= r->records.size()) return fail(FGPU_ERR_END, "no more records");
+  export_record(std::move(r->records[r->next]), r->record_rows[r->next], out_schema, out_array);
+  r->next++;
+  return FGPU_OK;
+}
+
+int32_t fgpu_result_stats(const fgpu_result* r, fgpu_stats* out) {
+  if (!r || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  *out = r->stats;
+  return FGPU_OK;
+}
+
+int32_t fgpu_result_free(fgpu_result* r) {
+  if (r) {
+    if (r->ctx) cudaSetDevice(r->ctx->device);
+    delete r;
+  }
+  return FGPU_OK;
+}
+
+int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, uint8_t* buf, uint64_t cap,
+                         uint64_t* out_len, uint32_t* out_count) {
+  if (!ctx || !table || !column || !out_len || !out_count) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->tables.find(table);
+  *out_len = 0;
+  *out_count = 0;
+  if (it == ctx->tables.end()) return FGPU_OK;
+  auto dit = it->second.dicts.find(column);
+  if (dit == it->second.dicts.end()) return FGPU_OK;
+  const GlobalDict& d = dit->second;
+  uint64_t need = 0;
+  for (auto& v : d.values) need += 4 + v.size();
+  *out_len = need;
+  *out_count = uint32_t(d.values.size());
+  if (!buf) return FGPU_OK;
+  if (cap < need) return fail(FGPU_ERR_INVALID, "buffer too small");
+  uint8_t* p = buf;
+  for (auto& v : d.values) {
+    uint32_t l = uint32_t(v.size());
+    std::memcpy(p, &l, 4);
+    p += 4;
+    std::memcpy(p, v.data(), v.size());
+    p += v.size();
+  }
+  return FGPU_OK;
+}
+
+int32_t fgpu_dict_unify(fgpu_ctx* ctx, const char* table, const char* column, const uint8_t* unified, uint64_t len,
+                        uint32_t count) {
+  if (!ctx || !table || !column || (!unified && len)) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Table& t = ctx->tables[table];
+  GlobalDict& d = t.dicts[column];
+  std::vector<std::string> uv;
+  std::unordered_map<std::string, uint32_t> uidx;
+  const uint8_t* p = unified;
+  const uint8_t* end = unified + len;
+  for (uint32_t i = 0; i < count; i++) {
+    if (end - p < 4) return fail(FGPU_ERR_INVALID, "unified dictionary blob truncated");
+    uint32_t l;
+    std::memcpy(&l, p, 4);
+    p += 4;
+    if (l > uint64_t(end - p)) return fail(FGPU_ERR_INVALID, "unified dictionary blob truncated");
+    std::string s(reinterpret_cast<const char*>(p), l);
+    p += l;
+    uidx.emplace(s, uint32_t(uv.size()));
+    uv.push_back(std::move(s));
+  }
+  std::vector<uint32_t> map(d.values.size());
+  for (size_t i = 0; i < d.values.size(); i++) {
+    auto it = uidx.find(d.values[i]);
+    if (it == uidx.end()) return fail(FGPU_ERR_INVALID, "unified dictionary misses a local entry of column " + std::string(column));
+    map[i] = it->second;
+  }
+  // rewrite the per-chunk device LUTs of this column to unified ids
+  for (auto& part : t.parts) {
+    for (auto& rg : part->rgs) {
+      auto it = rg.cols.find(column);
+      if (it == rg.cols.end() || it->second.desc.kind != CK_DICT_STR || it->second.lut_host.empty()) continue;
+      std::vector<uint32_t> l2(it->second.lut_host.size());
+      for (size_t i = 0; i < l2.size(); i++) l2[i] = map[it->second.lut_host[i]];
+      CUDA_TRY(cudaMemcpy(const_cast<uint32_t*>(it->second.desc.lut), l2.data(), l2.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  d.unified = std::move(map);
+  d.unified_values = std::move(uv);
+  return FGPU_OK;
+}
+
+int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_id, const char* column,
+                                struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  if (!ctx || !table || !column || !out_schema || !out_array) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto it = ctx->tables.find(table);
+  if (it == ctx->tables.end()) return fail(FGPU_ERR_NOT_FOUND, std::string("table not found: ") + table);
+  Part* part = nullptr;
+  for (auto& p : it->second.parts)
+    if (p->id == part_id) part = p.get();
+  if (!part) return fail(FGPU_ERR_NOT_FOUND, "part not found");
+  uint64_t total = 0;
+  int phys = -1;
+  for (auto& rg : part->rgs) {
+    auto c = rg.cols.find(column);
+    if (c == rg.cols.end()) return fail(FGPU_ERR_NOT_FOUND, std::string("column not found: ") + column);
+    if (!c->second.error.empty()) return fail(FGPU_ERR_UNSUPPORTED, std::string(column) + ": " + c->second.error);
+    phys = c->second.phys;
+    total += rg.n_rows;
+  }
+  const bool is_str = phys == PT_BYTE_ARRAY;
+  DevBuf d_vals, d_valid;
+  CUDA_TRY(d_vals.alloc(total * (is_str ? 4 : 8)));
+  if (!is_str) CUDA_TRY(d_valid.alloc(total));
+  uint64_t row = 0;
+  for (auto& rg : part->rgs) {
+    const ChunkDesc& cd = rg.cols.at(column).desc;
+    CUDA_TRY(launch_decode(cd, is_str ? static_cast<int32_t*>(d_vals.p) + row : nullptr,
+                           is_str ? nullptr : static_cast<long long*>(d_vals.p) + row,
+                           is_str ? nullptr : static_cast<uint8_t*>(d_valid.p) + row, ctx->sm_count, ctx->stream));
+    row += rg.n_rows;
+  }
+  OwnedColumn col;
+  col.name = column;
+  col.length = int64_t(total);
+  if (is_str) {
+    std::vector<int32_t> ids(total);
+    CUDA_TRY(cudaMemcpyAsync(ids.data(), d_vals.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const GlobalDict& gd = it->second.dicts.at(column);
+    col.format = "I";
+    col.validity.assign((total + 7) / 8, 0);
+    col.data.resize(total * 4);
+    uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
+    for (uint64_t i = 0; i < total; i++) {
+      if (ids[i] < 0) { idx[i] = 0; col.null_count++; }
+      else { idx[i] = uint32_t(ids[i]); set_bit(col.validity, int64_t(i)); }
+    }
+    if (col.null_count == 0) col.validity.clear();
+    auto dict = std::make_unique<OwnedColumn>();
+    dict->format = "z";
+    dict->length = int64_t(gd.cardinality());
+    dict->offsets.push_back(0);
+    for (uint32_t g = 0; g < gd.cardinality(); g++) {
+      const std::string& v = gd.value(g);
+      dict->data.insert(dict->data.end(), v.begin(), v.end());
+      dict->offsets.push_back(int32_t(dict->data.size()));
+    }
+    col.dictionary = std::move(dict);
+  } else {
+    col.format = phys == PT_DOUBLE ? "g" : "l";
+    col.data.resize(total * 8);
+    std::vector<uint8_t> valid(total);
+    CUDA_TRY(cudaMemcpyAsync(col.data.data(), d_vals.p, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(valid.data(), d_valid.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    col.validity.assign((total + 7) / 8, 0);
+    for (uint64_t i = 0; i < total; i++) {
+      if (valid[i]) set_bit(col.validity, int64_t(i));
+      else col.null_count++;
+    }
+    if (col.null_count == 0) col.validity.clear();
+  }
+  export_column(std::move(col), out_schema, out_array);
+  return FGPU_OK;
+}
+
+int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_rows, char* buf, uint64_t cap,
+                              uint64_t* out_len) {
+  if (!file || !out_len) return fail(FGPU_ERR_INVALID, "null argument");
+  if (tile_rows == 0) tile_rows = kTileRows;
+  if (tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 or 2048");
+  std::string err;
+  std::string js = describe_part_json(file, len, tile_rows, &err);
+  if (js.empty()) return fail(FGPU_ERR_PARQUET, err);
+  *out_len = js.size();
+  if (!buf) return FGPU_OK;
+  if (cap < js.size()) return fail(FGPU_ERR_INVALID, "buffer too small");
+  std::memcpy(buf, js.data(), js.size());
+  return FGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+#include "part_store.h"
+
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+
+namespace fgpu {
+namespace {
+
+constexpr size_t kAlign = 128;
+constexpr size_t kTailPad = 16;
+
+struct ImageWriter {
+  std::vector<uint8_t>& buf;
+  explicit ImageWriter(std::vector<uint8_t>& b) : buf(b) {}
+  size_t begin() {
+    size_t n = (buf.size() + kAlign - 1) / kAlign * kAlign;
+    buf.resize(n, 0);
+    return n;
+  }
+  void append(const void* p, size_t n) {
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    buf.insert(buf.end(), b, b + n);
+  }
+  void end() { buf.resize(buf.size() + kTailPad, 0); }
+  int64_t section(const void* p, size_t n) {
+    size_t off = begin();
+    append(p, n);
+    end();
+    return int64_t(off);
+  }
+};
+
+inline void or_bits(std::vector<uint64_t>& bm, uint64_t pos, uint64_t bits8) {
+  size_t w = size_t(pos >> 6);
+  unsigned sh = unsigned(pos & 63);
+  bm[w] |= bits8 << sh;
+  if (sh > 56 && w + 1 < bm.size()) bm[w + 1] |= bits8 >> (64 - sh);
+}
+
+inline void set_range(std::vector<uint64_t>& bm, uint64_t pos, uint64_t len) {
+  uint64_t end = pos + len;
+  while (pos < end) {
+    size_t w = size_t(pos >> 6);
+    unsigned sh = unsigned(pos & 63);
+    uint64_t take = std::min<uint64_t>(64 - sh, end - pos);
+    uint64_t mask = (take == 64) ? ~0ull : (((1ull << take) - 1ull) << sh);
+    bm[w] |= mask;
+    pos += take;
+  }
+}
+
+inline uint64_t popcount_range(const std::vector<uint64_t>& bm, uint64_t pos, uint64_t end) {
+  uint64_t n = 0;
+  while (pos < end) {
+    size_t w = size_t(pos >> 6);
+    unsigned sh = unsigned(pos & 63);
+    uint64_t take = std::min<uint64_t>(64 - sh, end - pos);
+    uint64_t mask = (take == 64) ? ~0ull : (((1ull << take) - 1ull) << sh);
+    n += uint64_t(__builtin_popcountll(bm[w] & mask));
+    pos += take;
+  }
+  return n;
+}
+
+bool is_dict_encoding(int32_t e) { return e == ENC_RLE_DICTIONARY || e == ENC_PLAIN_DICTIONARY; }
+
+// Builds every section of one column chunk into the image.
+void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, int tile_rows, GlobalDict* dict,
+                 ImageWriter& w, ChunkHost* out) {
+  out->phys = leaf.phys;
+  out->stored_bytes = uint64_t(cm.total_compressed_size);
+  out->desc.n_rows = n_rows;
+  if (!cm.error.empty()) { out->error = cm.error; return; }
+  if (leaf.phys != PT_INT64 && leaf.phys != PT_DOUBLE && leaf.phys != PT_BYTE_ARRAY) {
+    out->error = "unsupported physical type " + std::to_string(leaf.phys);
+    return;
+  }
+  if (leaf.is_unsigned) { out->error = "uint64 columns are not supported"; return; }
+  if (leaf.max_def > 1) { out->error = "nested optional columns are not supported"; return; }
+  bool any_dict = false, any_plain = false;
+  for (const PageInfo& pg : cm.pages) {
+    if (is_dict_encoding(pg.encoding)) any_dict = true;
+    else if (pg.encoding == ENC_PLAIN) any_plain = true;
+    else { out->error = "unsupported page encoding " + std::to_string(pg.encoding); return; }
+  }
+  if (any_dict && any_plain) { out->error = "column chunk mixes dictionary and PLAIN pages"; return; }
+  if (leaf.phys == PT_BYTE_ARRAY && any_plain) { out->error = "PLAIN byte-array pages are not supported"; return; }
+  const uint32_t T = uint32_t(tile_rows);
+  const uint32_t n_tiles = (n_rows + T - 1) / T;
+
+  // ---- definition levels --------------------------------------------------------------------
+  std::string err;
+  std::vector<uint8_t> defstream;
+  std::vector<HostRun> defruns;
+  std::vector<uint64_t> valid;  // bitset, only when max_def == 1
+  std::vector<uint32_t> page_nn(cm.pages.size());
+  uint32_t n_values = n_rows;
+  if (leaf.max_def == 1) {
+    valid.assign((size_t(n_rows) + 63) / 64 + 1, 0);
+    uint32_t row = 0;
+    for (size_t p = 0; p < cm.pages.size(); p++) {
+      const PageInfo& pg = cm.pages[p];
+      size_t first = defruns.size();
+      // a merged RLE run may extend the previous page's last run: remember where this page starts
+      uint32_t page_start = row;
+      if (!walk_hybrid(pg.def, pg.def_len, 1, pg.num_values, row, uint32_t(defstream.size()), &defruns, &err)) {
+        out->error = "definition levels: " + err;
+        return;
+      }
+      defstream.insert(defstream.end(), pg.def, pg.def + pg.def_len);
+      (void)first;
+      row += pg.num_values;
+      (void)page_start;
+    }
+    if (row != n_rows) { out->error = "definition levels do not cover the row group"; return; }
+    for (size_t k = 0; k < defruns.size(); k++) {
+      const HostRun& r = defruns[k];
+      uint32_t end = (k + 1 < defruns.size()) ? defruns[k + 1].start : n_rows;
+      uint32_t len = end - r.start;
+      if ((r.meta & 1u) == 0) {
+        if (r.val) set_range(valid, r.start, len);
+      } else {
+        for (uint32_t done = 0; done < len; done += 8) {
+          uint64_t b = defstream[r.off + done / 8];
+          if (len - done < 8) b &= (1ull << (len - done)) - 1ull;
+          or_bits(valid, uint64_t(r.start) + done, b);
+        }
+      }
+    }
+    row = 0;
+    uint64_t total_valid = 0;
+    for (size_t p = 0; p < cm.pages.size(); p++) {
+      const PageInfo& pg = cm.pages[p];
+      uint64_t nn = popcount_range(valid, row, uint64_t(row) + pg.num_values);
+      if (pg.num_nulls >= 0 && uint64_t(pg.num_values) - uint64_t(pg.num_nulls) != nn) {
+        out->error = "page num_nulls disagrees with its definition levels";
+        return;
+      }
+      page_nn[p] = uint32_t(nn);
+      total_valid += nn;
+      row += pg.num_values;
+    }
+    n_values = uint32_t(total_valid);
+  } else {
+    for (size_t p = 0; p < cm.pages.size(); p++) page_nn[p] = cm.pages[p].num_values;
+  }
+  const bool has_nulls = (n_values != n_rows);
+
+  // ---- values -------------------------------------------------------------------------------
+  std::vector<uint8_t> vstream;
+  std::vector<HostRun> vruns;
+  if (any_dict || (!any_plain && leaf.phys == PT_BYTE_ARRAY)) {
+    uint32_t vo = 0;
+    for (size_t p = 0; p < cm.pages.size(); p++) {
+      const PageInfo& pg = cm.pages[p];
+      if (page_nn[p] == 0) continue;
+      if (pg.values_len < 1) { out->error = "dictionary-index page without bit width"; return; }
+      int bw = pg.values[0];
+      if (bw > 32) { out->error = "dictionary index bit width > 32"; return; }
+      if (!walk_hybrid(pg.values + 1, pg.values_len - 1, bw, page_nn[p], vo, uint32_t(vstream.size()), &vruns, &err)) {
+        out->error = "dictionary indices: " + err;
+        return;
+      }
+      vstream.insert(vstream.end(), pg.values + 1, pg.values + pg.values_len);
+      vo += page_nn[p];
+    }
+    out->desc.kind = (leaf.phys == PT_BYTE_ARRAY) ? CK_DICT_STR : CK_DICT64;
+  } else {
+    vstream.reserve(size_t(n_values) * 8);
+    for (size_t p = 0; p < cm.pages.size(); p++) {
+      const PageInfo& pg = cm.pages[p];
+      uint64_t need = uint64_t(page_nn[p]) * 8;
+      if (need > pg.values_len) { out->error = "PLAIN page shorter than its value count"; return; }
+      vstream.insert(vstream.end(), pg.values, pg.values + need);
+    }
+    out->desc.kind = CK_PLAIN64;
+  }
+
+  // ---- dictionary ---------------------------------------------------------------------------
+  std::vector<int64_t> dict64;
+  uint32_t dict_size = 0;
+  if (out->desc.kind == CK_DICT_STR) {
+    const uint8_t* p = cm.dict;
+    const uint8_t* end = cm.dict + cm.dict_len;
+    out->lut_host.reserve(cm.dict_num_values);
+    for (uint32_t i = 0; i < cm.dict_num_values; i++) {
+      if (end - p < 4) { out->error = "dictionary page truncated"; return; }
+      uint32_t l;
+      std::memcpy(&l, p, 4);
+      p += 4;
+      if (l > uint64_t(end - p)) { out->error = "dictionary entry overruns page"; return; }
+      out->lut_host.push_back(dict->intern(reinterpret_cast<const char*>(p), l));
+      p += l;
+    }
+    dict_size = cm.dict_num_values;
+  } else if (out->desc.kind == CK_DICT64) {
+    if (uint64_t(cm.dict_num_values) * 8 > cm.dict_len) { out->error = "numeric dictionary page truncated"; return; }
+    dict64.resize(cm.dict_num_values);
+    std::memcpy(dict64.data(), cm.dict, size_t(cm.dict_num_values) * 8);
+    dict_size = cm.dict_num_values;
+  }
+  if (out->desc.kind != CK_PLAIN64) {
+    for (const HostRun& r : vruns)
+      if ((r.meta & 1u) == 0 && r.val >= dict_size) { out->error = "dictionary index out of range"; return; }
+    if (n_values > 0 && dict_size == 0) { out->error = "dictionary-encoded values without a dictionary page"; return; }
+  }
+
+  // ---- tile indexes ----------------------------------------------------------------------------
+  std::vector<uint32_t> tile_val0(n_tiles), tile_defrun, tile_run;
+  if (has_nulls) {
+    uint64_t acc = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) {
+      tile_val0[t] = uint32_t(acc);
+      uint64_t b = uint64_t(t) * T, e = std::min<uint64_t>(uint64_t(n_rows), b + T);
+      acc += popcount_range(valid, b, e);
+    }
+    tile_defrun.resize(n_tiles);
+    size_t k = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) {
+      while (k + 1 < defruns.size() && defruns[k + 1].start <= t * T) k++;
+      tile_defrun[t] = uint32_t(k);
+    }
+  } else {
+    for (uint32_t t = 0; t < n_tiles; t++) tile_val0[t] = t * T;
+  }
+  if (out->desc.kind != CK_PLAIN64) {
+    tile_run.resize(n_tiles);
+    size_t k = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) {
+      while (k + 1 < vruns.size() && vruns[k + 1].start <= tile_val0[t]) k++;
+      tile_run[t] = uint32_t(k);
+    }
+  }
+
+  // ---- write sections ----------------------------------------------------------------------------
+  const size_t before = w.buf.size();
+  out->desc.has_nulls = has_nulls ? 1 : 0;
+  out->desc.n_values = n_values;
+  out->desc.dict_size = dict_size;
+  out->off_values = w.section(vstream.data(), vstream.size());
+  if (out->desc.kind != CK_PLAIN64) {
+    out->desc.n_runs = uint32_t(vruns.size());
+    HostRun sentinel{n_values, 0, 0, 0};
+    vruns.push_back(sentinel);
+    out->off_runs = w.section(vruns.data(), vruns.size() * sizeof(HostRun));
+    out->off_tile_run = w.section(tile_run.data(), tile_run.size() * 4);
+  }
+  if (has_nulls) {
+    out->desc.n_defruns = uint32_t(defruns.size());
+    HostRun sentinel{n_rows, 0, 0, 0};
+    defruns.push_back(sentinel);
+    out->off_def = w.section(defstream.data(), defstream.size());
+    out->off_def_runs = w.section(defruns.data(), defruns.size() * sizeof(HostRun));
+    out->off_tile_defrun = w.section(tile_defrun.data(), tile_defrun.size() * 4);
+    out->off_tile_val0 = w.section(tile_val0.data(), tile_val0.size() * 4);
+  }
+  if (out->desc.kind == CK_DICT_STR) out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
+  if (out->desc.kind == CK_DICT64) out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
+  const size_t payload = vstream.size() + (has_nulls ? defstream.size() : 0);
+  out->meta_bytes = (w.buf.size() - before) - std::min(w.buf.size() - before, payload);
+}
+
+}  // namespace
+
+bool build_part_image(const uint8_t* file, uint64_t len, int tile_rows, Table* table, Part* part, std::string* err) {
+  ParsedFile pf;
+  if (!parse_parquet(file, len, &pf, err)) return false;
+  part->file_bytes = len;
+  part->columns.clear();
+  for (const SchemaLeaf& l : pf.leaves) part->columns.push_back(l.name);
+  part->image.clear();
+  part->image.reserve(size_t(len) + size_t(len) / 4 + 4096);
+  ImageWriter w(part->image);
+  for (const RowGroupMeta& rg : pf.row_groups) {
+    if (rg.num_rows == 0) continue;
+    if (rg.num_rows > 0x7fffffffll) { *err = "row group with more than 2^31 rows"; return false; }
+    RowGroupHost h;
+    h.n_rows = uint32_t(rg.num_rows);
+    for (size_t c = 0; c < rg.chunks.size(); c++) {
+      const SchemaLeaf& leaf = pf.leaves[c];
+      GlobalDict* dict = (leaf.phys == PT_BYTE_ARRAY) ? &table->dicts[leaf.name] : nullptr;
+      ChunkHost ch;
+      build_chunk(rg.chunks[c], leaf, h.n_rows, tile_rows, dict, w, &ch);
+      h.cols.emplace(leaf.name, std::move(ch));
+    }
+    part->rgs.push_back(std::move(h));
+  }
+  if (part->image.empty()) part->image.resize(kAlign, 0);
+  return true;
+}
+
+void patch_part_pointers(Part* part, const uint8_t* base) {
+  for (RowGroupHost& rg : part->rgs) {
+    for (auto& kv : rg.cols) {
+      ChunkHost& c = kv.second;
+      if (!c.error.empty()) continue;
+      auto at = [&](int64_t off) -> const uint8_t* { return off < 0 ? nullptr : base + off; };
+      c.desc.values = at(c.off_values);
+      c.desc.runs = reinterpret_cast<const Run*>(at(c.off_runs));
+      c.desc.tile_run = reinterpret_cast<const uint32_t*>(at(c.off_tile_run));
+      c.desc.def = at(c.off_def);
+      c.desc.def_runs = reinterpret_cast<const Run*>(at(c.off_def_runs));
+      c.desc.tile_defrun = reinterpret_cast<const uint32_t*>(at(c.off_tile_defrun));
+      c.desc.tile_val0 = reinterpret_cast<const uint32_t*>(at(c.off_tile_val0));
+      c.desc.lut = reinterpret_cast<const uint32_t*>(at(c.off_lut));
+      c.desc.dict64 = reinterpret_cast<const int64_t*>(at(c.off_dict64));
+    }
+  }
+}
+
+// ---- host-only description (tests without a GPU) ---------------------------------------------------
+namespace {
+void json_escape(std::ostringstream& o, const std::string& s) {
+  o << '"';
+  for (unsigned char ch : s) {
+    if (ch == '"' || ch == '\\') o << '\\' << ch;
+    else if (ch < 0x20 || ch >= 0x7f) {
+      char buf[8];
+      snprintf(buf, sizeof buf, "\\u%04x", ch);
+      o << buf;
+    } else o << ch;
+  }
+  o << '"';
+}
+}  // namespace
+
+std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows, std::string* err) {
+  Table table;
+  Part part;
+  if (!build_part_image(file, len, tile_rows, &table, &part, err)) return "";
+  patch_part_pointers(&part, part.image.data());  // pointers into the host image
+  const uint32_t T = uint32_t(tile_rows);
+  std::ostringstream o;
+  o << "{\"image_bytes\":" << part.image.size() << ",\"file_bytes\":" << len << ",\"row_groups\":[";
+  for (size_t g = 0; g < part.rgs.size(); g++) {
+    const RowGroupHost& rg = part.rgs[g];
+    if (g) o << ',';
+    o << "{\"n_rows\":" << rg.n_rows << ",\"columns\":{";
+    bool firstc = true;
+    for (const std::string& name : part.columns) {
+      const ChunkHost& c = rg.cols.at(name);
+      if (!firstc) o << ',';
+      firstc = false;
+      json_escape(o, name);
+      o << ":{";
+      if (!c.error.empty()) {
+        o << "\"error\":";
+        json_escape(o, c.error);
+        o << '}';
+        continue;
+      }
+      const ChunkDesc& d = c.desc;
+      o << "\"kind\":" << int(d.kind) << ",\"has_nulls\":" << int(d.has_nulls) << ",\"n_values\":" << d.n_values
+        << ",\"n_runs\":" << d.n_runs << ",\"n_defruns\":" << d.n_defruns << ",\"dict_size\":" << d.dict_size
+        << ",\"stored_bytes\":" << c.stored_bytes << ",\"meta_bytes\":" << c.meta_bytes;
+      // Decode through the same directories / tile indexes the kernel uses (small inputs only).
+      if (rg.n_rows <= 65536) {
+        std::vector<HostRun> vruns, druns;
+        if (d.runs) vruns.assign(reinterpret_cast<const HostRun*>(d.runs), reinterpret_cast<const HostRun*>(d.runs) + d.n_runs + 1);
+        if (d.def_runs) druns.assign(reinterpret_cast<const HostRun*>(d.def_runs), reinterpret_cast<const HostRun*>(d.def_runs) + d.n_defruns + 1);
+        const GlobalDict* gd = nullptr;
+        if (d.kind == CK_DICT_STR) gd = &table.dicts.at(name);
+        o << ",\"decoded\":[";
+        uint32_t vord = 0;
+        bool tiles_ok = true;
+        for (uint32_t r = 0; r < rg.n_rows; r++) {
+          if (r) o << ',';
+          if (d.has_nulls && r % T == 0 && d.tile_val0[r / T] != vord) tiles_ok = false;
+          if (r % T == 0) {
+            uint32_t v0 = d.has_nulls ? d.tile_val0[r / T] : r;
+            if (d.kind != CK_PLAIN64 && v0 < d.n_values) {
+              uint32_t fr = d.tile_run[r / T];
+              if (!(vruns[fr].start <= v0 && vruns[fr + 1].start > v0)) tiles_ok = false;
+            }
+            if (d.has_nulls) {
+              uint32_t fr = d.tile_defrun[r / T];
+              if (!(druns[fr].start <= r && druns[fr + 1].start > r)) tiles_ok = false;
+            }
+          }
+          bool valid = true;
+          if (d.has_nulls) valid = hybrid_value_at(d.def, druns, r) != 0;
+          if (!valid) { o << "null"; continue; }
+          if (d.kind == CK_PLAIN64) {
+            int64_t v;
+            std::memcpy(&v, d.values + size_t(vord) * 8, 8);
+            if (c.phys == PT_DOUBLE) {
+              double f;
+              std::memcpy(&f, &v, 8);
+              char buf[40];
+              snprintf(buf, sizeof buf, "%.17g", f);
+              o << buf;
+            } else o << v;
+          } else {
+            uint32_t idx = hybrid_value_at(d.values, vruns, vord);
+            if (d.kind == CK_DICT_STR) json_escape(o, gd->values[d.lut[idx]]);
+            else if (c.phys == PT_DOUBLE) {
+              double f;
+              std::memcpy(&f, &d.dict64[idx], 8);
+              char buf[40];
+              snprintf(buf, sizeof buf, "%.17g", f);
+              o << buf;
+            } else o << d.dict64[idx];
+          }
+          vord++;
+        }
+        o << "],\"tile_index_ok\":" << (tiles_ok ? "true" : "false");
+      }
+      o << '}';
+    }
+    o << "}}";
+  }
+  o << "]}";
+  return o.str();
+}
+
+}  // namespace fgpu

@@ -1,0 +1,269 @@
+/*
+ * frostgpu.h — C-ABI of libfrostgpu.so, the B200 (sm_100a) execution engine for FrostDB's
+ * TableScan -> PredicateFilter -> Projection -> HashAggregate/Distinct path.
+ *
+ * The reference (polarsignals/frostdb, pure Go) has no FFI for this path; its seam is the Go
+ * interface physicalplan.ScanPhysicalPlan{Execute,Draw} (query/physicalplan/physicalplan.go:32-35)
+ * fed by logicalplan.TableReader.Iterator (query/logicalplan/logicalplan.go:221-241).  Every entry
+ * point below names the reference code whose job it takes over.  The cgo binding a FrostDB
+ * maintainer would add is shown in INTEGRATION.md and go/physicalplan_gpu.go.
+ *
+ * Conventions: every function returns int32 status (FGPU_OK == 0, negative == error); the
+ * message of the last error on the calling thread is fgpu_last_error().  No exceptions cross the
+ * boundary, nothing aborts the process, and the library never calls back into the host from a
+ * thread it owns (the only callback, fgpu_match_fn, runs synchronously on the calling thread).
+ * All pointers are plain host pointers unless a parameter is explicitly documented as a device
+ * pointer.  No torch / C++ types appear in any signature.
+ */
+#ifndef FROSTGPU_H
+#define FROSTGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGPU_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------------------------- */
+enum {
+  FGPU_OK = 0,
+  FGPU_ERR_INVALID = -1,     /* bad argument / malformed plan                                     */
+  FGPU_ERR_PARQUET = -2,     /* malformed or unsupported Parquet file                             */
+  FGPU_ERR_UNSUPPORTED = -3, /* legal FrostDB plan the GPU path does not cover (caller keeps Go)  */
+  FGPU_ERR_CUDA = -4,        /* CUDA runtime failure (message has the cudaError string)           */
+  FGPU_ERR_NOT_FOUND = -5,   /* unknown table / part / column                                     */
+  FGPU_ERR_OOM = -6,         /* device or host allocation failed                                  */
+  FGPU_ERR_NO_DEVICE = -7,   /* no CUDA device: the library never falls back to a CPU path        */
+  FGPU_ERR_END = -8          /* fgpu_result_next: no more records                                 */
+};
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ------ */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+/* ---- opaque handles ------------------------------------------------------------------------ */
+typedef struct fgpu_ctx fgpu_ctx;       /* one per process per device                            */
+typedef struct fgpu_query fgpu_query;   /* a prepared (validated, compiled) plan                 */
+typedef struct fgpu_result fgpu_result; /* the records one Execute produced                      */
+
+typedef struct fgpu_config {
+  int32_t abi_version; /* FGPU_ABI_VERSION                                                        */
+  int32_t device;      /* CUDA device ordinal; one ctx drives exactly one GPU                     */
+  int32_t tile_rows;   /* 0 = default (2048); rows decoded per CTA iteration                      */
+  int32_t flags;       /* reserved, 0                                                             */
+  uint64_t staging_bytes; /* pinned host staging for uploads; 0 = default (256 MiB)              */
+} fgpu_config;
+
+/* ---- plan descriptor: POD mirror of the optimised logicalplan.LogicalPlan ------------------- */
+
+/* logicalplan.Op values, query/logicalplan/expr.go:13-33 (numeric values identical). */
+enum {
+  FGPU_OP_UNKNOWN = 0, FGPU_OP_EQ, FGPU_OP_NOT_EQ, FGPU_OP_LT, FGPU_OP_LT_EQ, FGPU_OP_GT,
+  FGPU_OP_GT_EQ, FGPU_OP_REGEX_MATCH, FGPU_OP_REGEX_NOT_MATCH, FGPU_OP_AND, FGPU_OP_OR,
+  FGPU_OP_ADD, FGPU_OP_SUB, FGPU_OP_MUL, FGPU_OP_DIV, FGPU_OP_CONTAINS, FGPU_OP_NOT_CONTAINS
+};
+
+/* logicalplan.AggFunc values, query/logicalplan/expr.go:718-729 (numeric values identical).
+ * Avg never reaches the engine: Builder.Aggregate rewrites it to Sum+Count+Div
+ * (query/logicalplan/builder.go:205-238). */
+enum {
+  FGPU_AGG_UNKNOWN = 0, FGPU_AGG_SUM, FGPU_AGG_MIN, FGPU_AGG_MAX, FGPU_AGG_COUNT, FGPU_AGG_AVG,
+  FGPU_AGG_UNIQUE, FGPU_AGG_AND
+};
+
+enum { FGPU_SCALAR_NULL = 0, FGPU_SCALAR_INT64 = 1, FGPU_SCALAR_FLOAT64 = 2, FGPU_SCALAR_STRING = 3 };
+
+typedef struct fgpu_scalar { /* scalar.Scalar of a logicalplan.LiteralExpr                       */
+  int32_t type;
+  int32_t _pad;
+  int64_t i64;
+  double f64;
+  const uint8_t* bytes; /* FGPU_SCALAR_STRING: not NUL-terminated                                */
+  uint64_t len;
+} fgpu_scalar;
+
+/* Host-evaluated string matcher for regex leaves (Go's regexp semantics stay in Go): returns
+ * non-zero when the dictionary entry matches.  Invoked synchronously, on the thread that called
+ * fgpu_query_execute, once per distinct dictionary entry — never per row
+ * (replaces the per-row loops of query/physicalplan/regexpfilter.go:85-165). */
+typedef int32_t (*fgpu_match_fn)(void* user, const uint8_t* bytes, uint64_t len);
+
+enum { FGPU_EXPR_COLUMN = 1, FGPU_EXPR_DYNCOLUMN = 2, FGPU_EXPR_LITERAL = 3, FGPU_EXPR_BINARY = 4 };
+
+typedef struct fgpu_expr { /* one node of a logicalplan.Expr tree, children by index            */
+  int32_t kind;        /* FGPU_EXPR_*                                                            */
+  int32_t op;          /* BINARY: FGPU_OP_*                                                      */
+  int32_t left, right; /* BINARY: indices into fgpu_plan.exprs                                   */
+  const char* name;    /* COLUMN: exact column name; DYNCOLUMN: prefix (matches "name.*",
+                          logicalplan.DynamicColumn.MatchColumn expr.go:564)                     */
+  fgpu_scalar literal; /* LITERAL                                                                */
+  fgpu_match_fn match; /* BINARY with REGEX_MATCH/REGEX_NOT_MATCH: matcher for the pattern       */
+  void* match_user;
+} fgpu_expr;
+
+typedef struct fgpu_agg { /* logicalplan.AggregationFunction{Func, Expr}                         */
+  int32_t func; /* FGPU_AGG_SUM/MIN/MAX/COUNT                                                    */
+  int32_t expr; /* index of the aggregated expression (COLUMN or arithmetic BINARY)              */
+} fgpu_agg;
+
+enum {
+  FGPU_PLAN_AGGREGATE = 1, /* TableScan [-> Filter] [-> Projection] -> Aggregation               */
+  FGPU_PLAN_DISTINCT = 2,  /* TableScan [-> Filter] -> Projection -> Distinct                    */
+  FGPU_PLAN_FILTER = 3     /* TableScan -> Filter -> Projection(columns): compacted rows          */
+};
+
+typedef struct fgpu_plan {
+  const char* table;      /* logicalplan.TableScan.TableName                                     */
+  int32_t kind;           /* FGPU_PLAN_*                                                         */
+  int32_t n_exprs;
+  const fgpu_expr* exprs;
+  int32_t filter;         /* root of TableScan.Filter (after FilterPushDown), or -1               */
+  int32_t n_group_by;     /* AGGREGATE: Aggregation.GroupExprs; DISTINCT/FILTER: output columns   */
+  const int32_t* group_by;
+  int32_t n_aggs;
+  const fgpu_agg* aggs;   /* AGGREGATE: Aggregation.AggExprs                                     */
+} fgpu_plan;
+
+typedef struct fgpu_stats {
+  uint64_t rows_scanned;      /* rows of visible row groups                                       */
+  uint64_t rows_selected;     /* rows that passed the predicate                                   */
+  uint64_t groups;            /* result rows                                                     */
+  uint64_t algorithmic_bytes; /* stored bytes of the projected column chunks + result bytes      */
+  uint64_t metadata_bytes;    /* run directories / tile indexes / LUTs the kernels also read      */
+  uint32_t kernel_launches;   /* kernels of this library launched by the Execute                  */
+  uint32_t row_groups;
+  float scan_kernel_ms;       /* device time of the fused scan kernel (CUDA events)               */
+  float total_device_ms;      /* first launch to last result byte on the host                     */
+  float h2d_ms;               /* uploads performed inside this Execute (streamed parts)           */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+} fgpu_stats;
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+
+/* Creates the engine for one GPU: streams, memory pools, pinned staging.  Fails with
+ * FGPU_ERR_NO_DEVICE when no CUDA device is usable.  Go side: constructed once by the new
+ * physicalplan.Option next to WithOverrideInput (physicalplan.go:279-285). */
+int32_t fgpu_init(const fgpu_config* cfg, fgpu_ctx** out);
+int32_t fgpu_shutdown(fgpu_ctx* ctx);
+const char* fgpu_last_error(void);
+int32_t fgpu_abi_version(void);
+
+/* ---- part registry: replaces Table.Iterator / collectRowGroups / LSM.Scan -------------------
+ * (table.go:740-868,1179-1242; index/lsm.go:401-454).  A part is one immutable Parquet file as
+ * produced by compaction (table.go:1267 compactParts) or one L0 Arrow record (parts/arrow.go). */
+
+enum {
+  FGPU_PUT_DEFAULT = 0,
+  FGPU_PUT_BORROW_PINNED = 1 /* `file` is page-locked memory that outlives the part: column
+                                chunks are not copied at put time but streamed H2D by the
+                                queries that project them (the reference reads only projected
+                                columns too, optimize.go:36-73)                                  */
+};
+
+/* Parses footer + page headers on the host, registers dictionary entries in the table's global
+ * dictionaries, builds the run directories / tile indexes and (unless BORROW_PINNED) uploads the
+ * page payloads to HBM.  The buffer is copied: the caller may free it on return.
+ * `tx` is the part's transaction id (parts.Part.TX()). */
+int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx,
+                              const uint8_t* file, uint64_t len, int32_t flags);
+
+/* L0 Arrow-record part (parts/arrow.go:14-55) through the Arrow C Data Interface; the library
+ * calls release() on both structs before returning.  Supported column types: int64, float64,
+ * dictionary<uint32|int32, binary|utf8>. */
+int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx,
+                            struct ArrowSchema* schema, struct ArrowArray* array);
+
+int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id);
+int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table);
+
+/* ---- query: replaces physicalplan.Build's TableScan->PredicateFilter->Projection->
+ * HashAggregate/Distinction chain (physicalplan.go:287-516; filter.go; aggregate.go; distinct.go)
+ * and Synchronizer + final HashAggregate (synchronize.go:16-53, physicalplan.go:438-471). ------ */
+
+int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** out);
+
+/* Blocking.  Scans every part of the table with tx <= tx_watermark (lsm.go:416) and produces the
+ * final records.  Thread-safe for concurrent calls on one ctx. */
+int32_t fgpu_query_execute(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out);
+
+/* Next result record as an Arrow struct array (one child per output column).  Ownership passes
+ * to the caller through the release callbacks.  Group-by columns are dictionary<uint32, binary>
+ * (or int64), aggregate columns are named "sum(value)", "count(value)", ... exactly as
+ * aggregate.go:615-618 names them.  Returns FGPU_ERR_END after the last record. */
+int32_t fgpu_result_next(fgpu_result* r, struct ArrowSchema* out_schema, struct ArrowArray* out_array);
+int32_t fgpu_result_stats(const fgpu_result* r, fgpu_stats* out);
+int32_t fgpu_result_free(fgpu_result* r);
+int32_t fgpu_query_free(fgpu_query* q);
+
+/* ---- multi-GPU (one process per GPU): the partial -> Synchronizer -> final split -------------
+ * (physicalplan.go:438-471).  A rank scans its own parts into a device-resident partial table;
+ * the host moves the flat partial buffers between ranks with one collective
+ * (ncclAllGather / torch.distributed.all_gather on the device pointer) and any rank merges. */
+
+/* Strings of the table's global dictionary for `column` in id order (id 0 first), as one
+ * length-prefixed blob: repeated {uint32 LE length, bytes}.  Call with buf == NULL to size. */
+int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, uint8_t* buf,
+                         uint64_t cap, uint64_t* out_len, uint32_t* out_count);
+/* Installs the cross-rank id space: `unified` is the blob format above holding the union
+ * dictionary; afterwards partial tables of all ranks are keyed by unified ids. */
+int32_t fgpu_dict_unify(fgpu_ctx* ctx, const char* table, const char* column,
+                        const uint8_t* unified, uint64_t len, uint32_t count);
+
+/* Scan only.  `*dev_ptr` is a DEVICE pointer to a position-independent partial table of
+ * `*nbytes` bytes (same size on every rank for the same query + unified dictionaries). */
+int32_t fgpu_query_execute_partial(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark,
+                                   fgpu_result** out, void** dev_ptr, uint64_t* nbytes);
+/* Merges `n` partial tables laid out back to back at DEVICE pointer `gathered` (each `nbytes`
+ * long, e.g. the output of an all-gather) into `r` and finalises it. */
+int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* gathered,
+                                   uint64_t nbytes, int32_t n);
+
+/* ---- standalone K1: decode one column of one part to Arrow buffers on the device and return
+ * them on the host (replaces ParquetConverter.Convert, pqarrow/arrow.go:264-373, for tests and
+ * for Filter-only consumers). ------------------------------------------------------------------ */
+int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_id,
+                                const char* column, struct ArrowSchema* out_schema,
+                                struct ArrowArray* out_array);
+
+/* ---- host-only introspection (works without a GPU; used by the CPU test-suite) --------------- */
+
+/* Parses a Parquet file exactly as fgpu_part_put_parquet does (footer, page walk, run
+ * directories) and writes a JSON description into buf.  Call with buf == NULL to size. */
+int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_rows, char* buf,
+                              uint64_t cap, uint64_t* out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FROSTGPU_H */
