@@ -1,0 +1,96 @@
+"""GPU results against an independent library (pyarrow/Acero) on random tables: a second opinion
+next to the oracle-based parity tests."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+from frostdb_b200 import dynparquet as dp
+from frostdb_b200 import logicalplan as lp
+from frostdb_b200 import query
+from tests.util import make_columns, rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _collect(qb):
+    out = []
+    qb.Execute(None, lambda ctx, r: out.append(r))
+    return out
+
+
+def _setup(store, name, parts, schema=None):
+    db = store.DB(None, "test")
+    store.engine.drop_table(name) if name in db.tables else None
+    db.tables.pop(name, None)
+    t = db.Table(name, schema or dp.SampleDefinitionWithFloat())
+    bufs = []
+    for cols, opts in parts:
+        buf = dp.write_part(t.schema, cols, **opts)
+        bufs.append(buf)
+        t.InsertParquet(buf)
+    ref = pa.concat_tables([dp.read_part(b) for b in bufs], promote_options="default")
+    return db, ref
+
+
+@pytest.mark.parametrize("sort", [True, False])
+@pytest.mark.parametrize("page_version", ["2.0", "1.0"])
+def test_groupby_sum_count_min_max(store, sort, page_version):
+    n = 50_000
+    parts = []
+    for p in range(3):
+        cols = make_columns(n, 100 + p, {"a": (7, 0.0), "b": (300, 0.1), "c": (3, 0.5)}, with_float=True,
+                            float_null_p=0.2, t0=1_000_000 + p * n)
+        parts.append((cols, dict(sort=sort, row_group_size=17_000, data_page_size=8192, data_page_version=page_version)))
+    db, ref = _setup(store, "t_gb", parts)
+    eng = query.NewEngine(None, db.TableProvider())
+    got = _collect(eng.ScanTable("t_gb").Aggregate(
+        [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value")), lp.Min(lp.Col("value")), lp.Max(lp.Col("value")),
+         lp.Sum(lp.Col("floatvalue")), lp.Min(lp.Col("timestamp"))],
+        [lp.Col("labels.a"), lp.Col("labels.b")]))
+    names = ["labels.a", "labels.b", "sum(value)", "count(value)", "min(value)", "max(value)", "min(timestamp)"]
+    rows = rows_of(got, names)
+    exp_t = ref.group_by(["labels.a", "labels.b"], use_threads=False).aggregate(
+        [("value", "sum"), ("value", "count"), ("value", "min"), ("value", "max"), ("timestamp", "min")])
+    exp = rows_of([b for b in exp_t.select(["labels.a", "labels.b", "value_sum", "value_count", "value_min",
+                                            "value_max", "timestamp_min"]).to_batches()])
+    assert rows == exp
+    # float sums within 1e-9 relative (NULL floatvalue contributes 0)
+    fs = {r[:2]: r[2] for r in rows_of(got, ["labels.a", "labels.b", "sum(floatvalue)"])}
+    exp_f = ref.group_by(["labels.a", "labels.b"], use_threads=False).aggregate([("floatvalue", "sum")])
+    for a, b, s in rows_of(exp_f.select(["labels.a", "labels.b", "floatvalue_sum"]).to_batches()):
+        s = 0.0 if s is None else s
+        assert fs[(a, b)] == pytest.approx(s, rel=1e-9, abs=1e-9)
+
+
+def test_filter_int_and_dict(store):
+    n = 40_000
+    cols = make_columns(n, 7, {"a": (5, 0.0), "b": (50, 0.3)}, t0=0)
+    db, ref = _setup(store, "t_f", [(cols, dict(row_group_size=9_000, data_page_size=4096))], dp.SampleDefinition())
+    eng = query.NewEngine(None, db.TableProvider())
+    f = lp.And(lp.Col("timestamp").GtEq(lp.Literal(10_000)), lp.Col("timestamp").Lt(lp.Literal(30_000)),
+               lp.Or(lp.Col("labels.b").Eq(lp.Literal("v000007")), lp.Col("labels.b").Eq(lp.Literal(None))))
+    got = _collect(eng.ScanTable("t_f").Filter(f).Aggregate([lp.Sum(lp.Col("value")), lp.Count(lp.Col("value"))],
+                                                           [lp.Col("labels.a")]))
+    rows = rows_of(got, ["labels.a", "sum(value)", "count(value)"])
+    ts, b = ref["timestamp"], ref["labels.b"].cast(pa.string())
+    mask = pc.and_(pc.and_(pc.greater_equal(ts, 10_000), pc.less(ts, 30_000)),
+                   pc.or_(pc.fill_null(pc.equal(b, "v000007"), False), pc.is_null(b)))
+    sub = ref.filter(mask)
+    exp_t = sub.group_by(["labels.a"], use_threads=False).aggregate([("value", "sum"), ("value", "count")])
+    exp = rows_of(exp_t.select(["labels.a", "value_sum", "value_count"]).to_batches())
+    assert rows == exp
+
+
+def test_decode_column_matches_pyarrow(store):
+    n = 30_000
+    cols = make_columns(n, 3, {"a": (9, 0.0), "b": (70_000, 0.05), "c": (2, 0.9)}, with_float=True, float_null_p=0.4)
+    db, ref = _setup(store, "t_dec", [(cols, dict(row_group_size=11_000, data_page_size=2048))])
+    for name in ["labels.a", "labels.b", "labels.c", "timestamp", "value", "floatvalue", "stacktrace"]:
+        got = store.engine.decode_column("t_dec", 0, name)
+        if pa.types.is_dictionary(got.type):
+            got = got.dictionary_decode().cast(pa.string())
+        exp = ref[name].combine_chunks()
+        if pa.types.is_dictionary(exp.type):
+            exp = exp.dictionary_decode()
+        assert got.to_pylist() == exp.cast(got.type).to_pylist(), name
