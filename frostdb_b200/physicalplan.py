@@ -278,8 +278,9 @@ class Limiter(PhysicalPlan):
         self.next.Callback(ctx, r.slice(0, take))
 
 
-def Build(engine, plan: lp.LogicalPlan) -> OutputPlan:
+def Build(engine, plan: lp.LogicalPlan, scan_factory=None) -> OutputPlan:
     """Pattern-matches the GPU-executable prefix and chains the remaining host operators."""
+    scan_factory = scan_factory or GPUScan
     nodes = plan.chain()
     if not nodes or nodes[0].TableScan is None:
         raise _lib.FrostGPUError(_lib.FGPU_ERR_INVALID, "plan must start with a TableScan")
@@ -289,18 +290,41 @@ def Build(engine, plan: lp.LogicalPlan) -> OutputPlan:
     while i < len(nodes) and nodes[i].Filter is not None:  # FilterPushDown: filters fold into the scan
         filter_expr = nodes[i].Filter.Expr if filter_expr is None else lp.And(filter_expr, nodes[i].Filter.Expr)
         i += 1
+    def passthrough(proj) -> bool:
+        # Projection feeding the aggregate (sqlparse pre-projection): plain / dynamic columns and the
+        # arithmetic the aggregate expressions repeat; the fused scan reads what it needs itself.
+        def ok(e):
+            if isinstance(e, lp.AliasExpr):
+                return False
+            if isinstance(e, (lp.Column, lp.DynamicColumn)):
+                return True
+            return isinstance(e, lp.BinaryExpr) and lp.OpAdd <= e.Op <= lp.OpDiv and ok_operand(e.Left) and ok_operand(e.Right)
+
+        def ok_operand(e):
+            return isinstance(e, (lp.Column, lp.LiteralExpr)) or ok(e)
+        return all(ok(e) for e in proj.Exprs)
+
+    if (i + 1 < len(nodes) and nodes[i].Projection is not None and nodes[i + 1].Aggregation is not None
+            and passthrough(nodes[i].Projection)):
+        i += 1
     gpu: Optional[GPUScan] = None
     if i < len(nodes) and nodes[i].Aggregation is not None:
         a = nodes[i].Aggregation
-        gpu = GPUScan(engine, scan.TableName, filter_expr, _lib.PLAN_AGGREGATE, a.GroupExprs, a.AggExprs)
+        gpu = scan_factory(engine, scan.TableName, filter_expr, _lib.PLAN_AGGREGATE, a.GroupExprs, a.AggExprs)
         i += 1
     elif i + 1 < len(nodes) and nodes[i].Projection is not None and nodes[i + 1].Distinct is not None:
         d = nodes[i + 1].Distinct
-        gpu = GPUScan(engine, scan.TableName, filter_expr, _lib.PLAN_DISTINCT, d.Exprs, [])
+        gpu = scan_factory(engine, scan.TableName, filter_expr, _lib.PLAN_DISTINCT, d.Exprs, [])
         i += 2
+    elif (i < len(nodes) and nodes[i].Projection is not None
+          and all(isinstance(e, (lp.Column, lp.DynamicColumn)) for e in nodes[i].Projection.Exprs)):
+        # TableScan -> Filter -> Projection(columns): compacted rows (PredicateFilter + Projection)
+        gpu = scan_factory(engine, scan.TableName, filter_expr, _lib.PLAN_FILTER, nodes[i].Projection.Exprs, [])
+        i += 1
     else:
         raise _lib.FrostGPUError(_lib.FGPU_ERR_UNSUPPORTED,
-                                 "the GPU engine covers TableScan[->Filter]->Aggregation|Distinct; keep this plan on the Go operators")
+                                 "the GPU engine covers TableScan[->Filter]->Aggregation|Distinct|Projection(columns); "
+                                 "keep this plan on the Go operators")
     out = OutputPlan()
     out.scan = gpu
     prev = gpu

@@ -43,14 +43,18 @@ class GPUEngine:
         self.close()
 
     # ---- parts -------------------------------------------------------------------------------
-    def put_parquet(self, table: str, buf: bytes, tx: Optional[int] = None, part_id: Optional[int] = None) -> int:
+    def put_parquet(self, table: str, buf, tx: Optional[int] = None, part_id: Optional[int] = None) -> int:
         lib = _lib.load()
         pid = self._next_part.get(table, 0) if part_id is None else part_id
         self._next_part[table] = max(self._next_part.get(table, 0), pid + 1)
         if tx is None:
             tx = self._watermarks.get(table, 0) + 1
-        src = (C.c_char * len(buf)).from_buffer_copy(buf)
-        _lib.check(lib.fgpu_part_put_parquet(self.handle, table.encode(), pid, tx, C.addressof(src), len(buf), 0))
+        if isinstance(buf, (bytes, bytearray, memoryview)):
+            src = (C.c_char * len(buf)).from_buffer_copy(buf)
+            addr, n = C.addressof(src), len(buf)
+        else:  # numpy uint8 array: no copy
+            addr, n = buf.ctypes.data, buf.nbytes
+        _lib.check(lib.fgpu_part_put_parquet(self.handle, table.encode(), pid, tx, addr, n, 0))
         self._watermarks[table] = max(self._watermarks.get(table, 0), tx)
         return pid
 

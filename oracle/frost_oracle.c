@@ -406,7 +406,7 @@ static int decode_chunk(const o_part* part, const o_leaf* leaf, const o_chunk* c
 /* Query model                                                                                       */
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct { const char* name; o_col col; int present; } rec_col;
-typedef struct { int64_t n; int n_cols; rec_col* cols; } record; /* one Arrow record (one row group) */
+typedef struct { int64_t n; int n_cols; rec_col* cols; int qidx; } record; /* one Arrow record (one row group) */
 
 static rec_col* rec_find(record* r, const char* name) {
   for (int i = 0; i < r->n_cols; i++) if (r->cols[i].present && strcmp(r->cols[i].name, name) == 0) return &r->cols[i];
@@ -827,7 +827,7 @@ static void* worker_main(void* arg) {
     o_part* part = q->queue[i].part; o_rg* rg = &part->rgs[q->queue[i].rg];
     if (q->max_rows > 0) { int64_t before = __sync_fetch_and_add(&q->rows_taken, rg->num_rows); if (before >= q->max_rows) break; }
     /* Convert: decode the physically projected columns of this row group (optimize.go:36-73) */
-    record rec; rec.n = rg->num_rows; rec.n_cols = part->n_leaves; rec.cols = xcalloc((size_t)part->n_leaves + 1, sizeof(rec_col));
+    record rec; rec.qidx = i; rec.n = rg->num_rows; rec.n_cols = part->n_leaves; rec.cols = xcalloc((size_t)part->n_leaves + 1, sizeof(rec_col));
     for (int c = 0; c < part->n_leaves && !w->rc; c++) {
       rec.cols[c].name = part->leaves[c].name;
       if (!proj_wants(q, part->leaves[c].name)) continue;
@@ -843,7 +843,7 @@ static void* worker_main(void* arg) {
       free(bm);
     }
     w->rows_selected += rec.n;
-    if (rec.n > 0 && ha_callback(&w->agg, q->plan, &rec, w->agg_is_float, w->err)) { w->rc = -1; record_free(&rec); break; }
+    if (q->plan->kind != FGPU_PLAN_FILTER && rec.n > 0 && ha_callback(&w->agg, q->plan, &rec, w->agg_is_float, w->err)) { w->rc = -1; record_free(&rec); break; }
     /* group key strings point into the record's dictionaries (which point into the file): keep the
        per-record dictionary arrays alive until the result is built */
     if (w->n_kept == w->cap_kept) { w->cap_kept = w->cap_kept ? w->cap_kept * 2 : 16; w->kept = xrealloc(w->kept, (size_t)w->cap_kept * sizeof(record)); }
@@ -924,6 +924,52 @@ int oracle_execute(oracle_table* t, const fgpu_plan* plan, uint64_t tx_watermark
   if (!rc) for (int i = 0; i < n_threads; i++) { ha_merge(&r->fin, &r->workers[i].agg, plan, aif); r->rows_scanned += r->workers[i].rows_scanned; r->rows_selected += r->workers[i].rows_selected; }
   free(q.queue); free(q.proj); free(q.proj_dyn);
   if (rc) { oracle_result_free(r); return -1; }
+  if (plan->kind == FGPU_PLAN_FILTER) {
+    /* Filter -> Projection(columns): the compacted rows themselves, in scan order. */
+    int total_recs = 0; for (int i = 0; i < n_threads; i++) total_recs += r->workers[i].n_kept;
+    record** recs = xcalloc((size_t)total_recs + 1, sizeof(record*)); int nr = 0;
+    for (int i = 0; i < n_threads; i++) for (int k = 0; k < r->workers[i].n_kept; k++) recs[nr++] = &r->workers[i].kept[k];
+    for (int a = 1; a < nr; a++) { record* x = recs[a]; int b = a - 1; while (b >= 0 && recs[b]->qidx > x->qidx) { recs[b + 1] = recs[b]; b--; } recs[b + 1] = x; }
+    hashagg* f = &r->fin; int64_t rows = 0;
+    for (int a = 0; a < nr; a++) {
+      if (recs[a]->n == 0) continue;
+      rows += recs[a]->n;
+      for (int ci = 0; ci < recs[a]->n_cols; ci++) {
+        if (!recs[a]->cols[ci].present) continue;
+        const char* fname = recs[a]->cols[ci].name;
+        for (int g = 0; g < plan->n_group_by; g++) {
+          const fgpu_expr* ge = &plan->exprs[plan->group_by[g]];
+          int match = 0;
+          if (ge->kind == FGPU_EXPR_COLUMN) match = strcmp(ge->name, fname) == 0;
+          else if (ge->kind == FGPU_EXPR_DYNCOLUMN) { size_t pl = strlen(ge->name); match = strncmp(ge->name, fname, pl) == 0 && fname[pl] == '.'; }
+          if (match) { int t = recs[a]->cols[ci].col.type; ha_keycol(f, fname, t == C_DICT ? 0 : (t == C_F64 ? 2 : 1)); }
+        }
+      }
+    }
+    r->n_groups = rows; r->n_keys = f->n_keycols; r->n_aggs = 0;
+    r->key_names = xcalloc((size_t)r->n_keys + 1, sizeof(char*)); r->key_is_int = xcalloc((size_t)r->n_keys + 1, 1);
+    size_t kg = (size_t)r->n_keys * (size_t)rows;
+    r->key_str = xcalloc(kg + 1, sizeof(*r->key_str)); r->key_len = xcalloc(kg + 1, 8); r->key_int = xcalloc(kg + 1, 8);
+    r->aggs = xcalloc(1, 8); r->agg_is_float = xcalloc(1, 1);
+    for (int k = 0; k < r->n_keys; k++) { r->key_names[k] = strdup(f->keycol_name[k]); r->key_is_int[k] = f->keycol_is_int[k]; }
+    int64_t base = 0;
+    for (int a = 0; a < nr; a++) {
+      record* rec = recs[a];
+      for (int k = 0; k < r->n_keys; k++) {
+        rec_col* c = rec_find(rec, r->key_names[k]);
+        for (int64_t i = 0; i < rec->n; i++) {
+          size_t o = (size_t)k * (size_t)rows + (size_t)(base + i);
+          if (!c || (c->col.valid && !c->col.valid[i])) { r->key_len[o] = -1; continue; }
+          if (c->col.type == C_DICT) { r->key_str[o] = c->col.dval[c->col.idx[i]]; r->key_len[o] = c->col.dlen[c->col.idx[i]]; }
+          else { r->key_int[o] = c->col.i64[i]; r->key_len[o] = 0; }
+        }
+      }
+      base += rec->n;
+    }
+    free(recs);
+    *out = r;
+    return 0;
+  }
   hashagg* f = &r->fin;
   r->n_groups = f->n_groups; r->n_keys = f->n_keycols; r->n_aggs = plan->n_aggs;
   r->key_names = xcalloc((size_t)r->n_keys + 1, sizeof(char*)); r->key_is_int = xcalloc((size_t)r->n_keys + 1, 1);
