@@ -12,7 +12,7 @@ constexpr int kMaxAggs = 8;
 constexpr int kMaxProg = 48;     // arithmetic ops over all aggregate expressions
 constexpr int kMaxFilterProg = 96;
 constexpr int kMaxKeyWords = 6;  // packed key = up to 6 x 64 bit
-constexpr int kMaxNumBufs = 4;   // numeric columns that need smem staging (nullable / dict-encoded)
+constexpr int kMaxOut = 40;      // projected columns of a rows (filter-only) plan
 
 constexpr uint32_t kNullIdx = 0xffffffffu;
 
@@ -44,11 +44,11 @@ struct ChunkDesc {
   uint32_t dict_size;
   const uint8_t* values;         // PLAIN64: aligned values; DICT*: concatenated hybrid index streams
   const Run* runs;               // DICT*: run directory (+1 sentinel with start == n_values)
-  const uint32_t* tile_run;      // DICT*: per tile, index of the run holding the tile's first value
+  const uint32_t* tile_run;      // DICT*: per 256-row chunk, index of the run holding the chunk's first value
   const uint8_t* def;            // concatenated definition-level hybrid streams (has_nulls)
   const Run* def_runs;           // (+1 sentinel with start == n_rows)
-  const uint32_t* tile_defrun;   // per tile, index of the def run holding the tile's first row
-  const uint32_t* tile_val0;     // per tile, number of non-null values before the tile (has_nulls)
+  const uint32_t* tile_defrun;   // per 256-row chunk, index of the def run holding the chunk's first row
+  const uint32_t* tile_val0;     // per 256-row chunk, number of non-null values before the chunk (has_nulls)
   const uint32_t* lut;           // CK_DICT_STR: chunk dictionary index -> global dictionary id
   const int64_t* dict64;         // CK_DICT64: chunk dictionary values (raw 8 bytes each)
 };
@@ -103,6 +103,7 @@ struct AggDesc {
 };
 
 enum TableMode : int32_t { TM_DENSE = 0, TM_HASH = 1 };
+enum FilterKind : int32_t { FK_PROGRAM = 0, FK_AND = 1, FK_OR = 2 };  // conjunction / disjunction of leaves: one mask test
 
 // Everything one launch of the fused scan kernel needs.
 struct QueryDesc {
@@ -114,9 +115,11 @@ struct QueryDesc {
   int32_t n_rg;
   uint32_t n_tiles;
   uint32_t table_slots;  // dense: number of slots; hash: capacity (power of two)
-  uint32_t n_numbufs;    // numeric staging buffers in use
+  int32_t filter_kind;   // FilterKind
+  uint32_t filter_mask;  // FK_AND / FK_OR: the participating leaf bits
+  int32_t n_out;         // rows plan: projected columns
   uint8_t slot_type[kMaxSlots];
-  int8_t slot_numbuf[kMaxSlots];  // numeric slot -> staging buffer index, -1 = read directly from HBM
+  uint8_t out_slot[kMaxOut];
   uint8_t slot_used_by_leaf[kMaxSlots];
   uint8_t filter_prog[kMaxFilterProg];  // postfix: 0..31 push leaf; 0x80 AND; 0x81 OR
   LeafDesc leaves[kMaxLeaves];
@@ -133,7 +136,11 @@ struct QueryDesc {
   long long* t_agg[kMaxAggs];  // per aggregate, int64 or double bits
   uint32_t* t_tag;             // hash mode: 0 empty, 1 locked, else fingerprint|2
   unsigned long long* t_keys;  // hash mode: [capacity][key_words]
-  unsigned long long* counters;  // [0] rows selected, [1] table overflow flag
+  unsigned long long* counters;  // [0] rows selected, [1] table overflow flag, [2] tile ticket (rows plan)
+  // rows plan outputs
+  void* out_data[kMaxOut];       // int32 global ids (dictionary columns) or raw 8-byte values
+  uint8_t* out_valid[kMaxOut];   // numeric columns: 0/1 per output row
+  unsigned long long* tile_state;  // [n_tiles] decoupled look-back state
 };
 
 // Dense/hash table -> compacted result rows.

@@ -155,6 +155,7 @@ struct fgpu_query {
 struct KeyOut {
   std::string name;
   bool is_int64 = false;
+  bool is_float = false;
   const GlobalDict* dict = nullptr;
   std::vector<std::string> dict_snapshot;  // values by (unified) id at execute time
 };
@@ -175,6 +176,7 @@ struct fgpu_result {
   std::vector<int64_t> record_rows;
   size_t next = 0;
   bool finalized = false;
+  bool rows_plan = false;
 };
 
 namespace {
@@ -347,9 +349,7 @@ void collect_columns(const fgpu_query& q, int node, std::vector<std::string>* ou
 // Resolves the plan against the visible row groups and fills everything of QueryDesc that does
 // not need device memory.
 int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
-  auto tit = ctx->tables.find(q.table);
-  if (tit == ctx->tables.end()) return fail(FGPU_ERR_NOT_FOUND, "table not found: " + q.table);
-  Table& table = tit->second;
+  Table& table = ctx->tables[q.table];  // a table without parts scans nothing (empty LSM)
   for (auto& p : table.parts) {
     if (p->tx > tx) continue;  // index/lsm.go:416
     for (auto& rg : p->rgs) {
@@ -417,7 +417,6 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   qd.n_slots = int32_t(c->slot_names.size());
   for (int s = 0; s < qd.n_slots; s++) {
     qd.slot_type[s] = c->slot_types[size_t(s)];
-    qd.slot_numbuf[s] = -1;
   }
   // filter
   if (q.filter >= 0) {
@@ -433,6 +432,16 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     if (maxd > 30) return fail(FGPU_ERR_UNSUPPORTED, "filter expression too deep");
     qd.n_filter_prog = int32_t(c->filter_prog.size());
     std::memcpy(qd.filter_prog, c->filter_prog.data(), c->filter_prog.size());
+    // pure conjunctions / disjunctions of leaves reduce to one mask test per row
+    bool all_and = true, all_or = true;
+    uint32_t mask = 0;
+    for (uint8_t op : c->filter_prog) {
+      if (op < 0x80) mask |= 1u << op;
+      else if (op == 0x80) all_or = false;
+      else all_and = false;
+    }
+    qd.filter_mask = mask;
+    qd.filter_kind = all_and ? FK_AND : (all_or ? FK_OR : FK_PROGRAM);
   }
   qd.n_leaves = int32_t(c->leaves.size());
   for (int l = 0; l < qd.n_leaves; l++) {
@@ -499,22 +508,34 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   }
   if (prog.size() > size_t(kMaxProg)) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expressions too large");
   for (size_t p = 0; p < prog.size(); p++) qd.prog[p] = prog[p];
-  // numeric staging buffers: any numeric slot that some visible chunk stores nullable or dictionary-encoded
-  int nb = 0;
-  for (int s = 0; s < qd.n_slots; s++) {
-    if (qd.slot_type[s] == ST_DICT) continue;
-    bool need = false;
-    for (const VisibleRG& v : c->rgs) {
-      auto it = v.rg->cols.find(c->slot_names[size_t(s)]);
-      if (it == v.rg->cols.end()) continue;
-      if (it->second.desc.kind != CK_PLAIN64 || it->second.desc.has_nulls) need = true;
+  // the kernel evaluates aggregate expressions on an operand stack of three 8-row vectors
+  for (size_t a = 0; a < q.aggs.size(); a++) {
+    int depth = 0, maxd = 0;
+    for (int p = qd.aggs[a].prog_off; p < qd.aggs[a].prog_off + qd.aggs[a].prog_len; p++) {
+      depth += (prog[size_t(p)].op == PO_LOAD || prog[size_t(p)].op == PO_CONST) ? 1 : -1;
+      maxd = std::max(maxd, depth);
     }
-    if (need) {
-      if (nb >= kMaxNumBufs) return fail(FGPU_ERR_UNSUPPORTED, "too many nullable / dictionary-encoded numeric columns in one query");
-      qd.slot_numbuf[s] = int8_t(nb++);
-    }
+    if (maxd > 3) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expression nests too deeply for the GPU path");
   }
-  qd.n_numbufs = uint32_t(nb);
+  qd.tile_rows = ctx->tile_rows;
+  qd.n_rg = int32_t(c->rgs.size());
+  if (q.kind == FGPU_PLAN_FILTER) {
+    // Filter -> Projection(columns): the resolved columns are the output, no table
+    if (key_names.size() > size_t(kMaxOut)) return fail(FGPU_ERR_UNSUPPORTED, "too many projected columns");
+    qd.n_out = int32_t(key_names.size());
+    for (size_t k = 0; k < key_names.size(); k++) {
+      int slot = slot_of.at(key_names[k]);
+      qd.out_slot[k] = uint8_t(slot);
+      KeyOut ko;
+      ko.name = key_names[k];
+      ko.is_int64 = c->slot_types[size_t(slot)] != ST_DICT;
+      ko.is_float = c->slot_types[size_t(slot)] == ST_F64;
+      if (!ko.is_int64) ko.dict = &table.dicts.at(key_names[k]);
+      c->keys.push_back(std::move(ko));
+      c->key_slots.push_back(slot);
+    }
+    return FGPU_OK;
+  }
   // keys and table shape
   qd.n_keys = int32_t(key_names.size());
   bool all_dict = true;
@@ -577,8 +598,6 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     while (cap < 2 * c->group_bound && cap < (1ull << 28)) cap <<= 1;
     qd.table_slots = uint32_t(cap);
   }
-  qd.tile_rows = ctx->tile_rows;
-  qd.n_rg = int32_t(c->rgs.size());
   return FGPU_OK;
 }
 
@@ -679,11 +698,36 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   qd.n_tiles = tiles;
 
   // ---- device memory -----------------------------------------------------------------------
-  size_t off_aggs, off_tags, off_keys;
-  size_t tbytes = table_layout(qd, &off_aggs, &off_tags, &off_keys);
-  CUDA_TRY(res->table.alloc(tbytes));
-  res->table_bytes = tbytes;
-  bind_table(&qd, static_cast<uint8_t*>(res->table.p));
+  const bool rows_plan = q.kind == FGPU_PLAN_FILTER;
+  if (!rows_plan) {
+    size_t off_aggs, off_tags, off_keys;
+    size_t tbytes = table_layout(qd, &off_aggs, &off_tags, &off_keys);
+    CUDA_TRY(res->table.alloc(tbytes));
+    res->table_bytes = tbytes;
+    bind_table(&qd, static_cast<uint8_t*>(res->table.p));
+  }
+  // rows plan: one output array per projected column (worst case every row is selected) + look-back state
+  std::vector<size_t> out_off(size_t(qd.n_out)), valid_off(size_t(qd.n_out));
+  size_t out_bytes = 0, state_off = 0;
+  if (rows_plan) {
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    for (int o = 0; o < qd.n_out; o++) {
+      bool dict = qd.slot_type[qd.out_slot[o]] == ST_DICT;
+      out_off[size_t(o)] = out_bytes;
+      out_bytes = al(out_bytes + size_t(c.total_rows) * (dict ? 4 : 8));
+      valid_off[size_t(o)] = out_bytes;
+      if (!dict) out_bytes = al(out_bytes + size_t(c.total_rows));
+    }
+    state_off = out_bytes;
+    out_bytes = al(out_bytes + size_t(tiles) * 8);
+    CUDA_TRY(res->table.alloc(out_bytes));
+    uint8_t* ob = static_cast<uint8_t*>(res->table.p);
+    for (int o = 0; o < qd.n_out; o++) {
+      qd.out_data[o] = ob + out_off[size_t(o)];
+      qd.out_valid[o] = ob + valid_off[size_t(o)];
+    }
+    qd.tile_state = reinterpret_cast<unsigned long long*>(ob + state_off);
+  }
 
   auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
   size_t o_chunks = 0;
@@ -713,11 +757,17 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
   CUDA_TRY(cudaMemcpyAsync(aux, hostaux.data(), aux_bytes, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(res->qdesc_dev.p, &qd, sizeof(QueryDesc), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(launch_table_init(qd, s));
-  CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
-  CUDA_TRY(launch_scan(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
+  if (rows_plan) {
+    CUDA_TRY(cudaMemsetAsync(qd.tile_state, 0, size_t(tiles) * 8, s));
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
+    CUDA_TRY(launch_rows(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
+  } else {
+    CUDA_TRY(launch_table_init(qd, s));
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
+    CUDA_TRY(launch_scan(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
+  }
   CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
-  st.kernel_launches += 1 + (tiles ? 1 : 0);
+  st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0);
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
   unsigned long long counters[8] = {0};
   CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));
@@ -740,6 +790,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       k.dict = nullptr;
     }
   }
+  res->rows_plan = rows_plan;
   for (size_t a = 0; a < q.aggs.size(); a++) {
     res->agg_names.push_back(std::string(agg_string(q.aggs[a].func)) + "(" + q.expr_name(q.aggs[a].expr) + ")");
     // Count yields int64; Sum/Min/Max keep the input type (aggregate.go:734-950)
@@ -764,7 +815,86 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
 }
 
 // Table -> host columns -> one Arrow record.
+// Rows plan: selected rows of the projected columns -> one Arrow record (filter.go:276-323 + Projection).
+int32_t finalize_rows(fgpu_ctx* ctx, fgpu_result* res) {
+  cudaStream_t s = ctx->stream;
+  const QueryDesc& qd = res->qd;
+  const size_t R = size_t(res->stats.rows_selected);
+  res->stats.groups = R;
+  std::vector<OwnedColumn> cols;
+  for (int o = 0; o < qd.n_out; o++) {
+    const KeyOut& ko = res->keys[size_t(o)];
+    OwnedColumn col;
+    col.name = ko.name;
+    col.length = int64_t(R);
+    if (!ko.is_int64) {
+      std::vector<int32_t> ids(R);
+      if (R) CUDA_TRY(cudaMemcpyAsync(ids.data(), qd.out_data[o], R * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      res->stats.d2h_bytes += R * 4;
+      col.format = "I";
+      col.validity.assign((R + 7) / 8, 0);
+      col.data.resize(R * 4);
+      uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
+      std::vector<int32_t> remap(ko.dict_snapshot.size(), -1);
+      for (size_t i = 0; i < R; i++)
+        if (ids[i] >= 0) remap[size_t(ids[i])] = 0;
+      auto dict = std::make_unique<OwnedColumn>();
+      dict->format = "z";
+      dict->offsets.push_back(0);
+      int32_t next = 0;
+      for (size_t g = 0; g < remap.size(); g++) {
+        if (remap[g] < 0) continue;
+        remap[g] = next++;
+        const std::string& v = ko.dict_snapshot[g];
+        dict->data.insert(dict->data.end(), v.begin(), v.end());
+        dict->offsets.push_back(int32_t(dict->data.size()));
+      }
+      dict->length = next;
+      for (size_t i = 0; i < R; i++) {
+        if (ids[i] < 0) { idx[i] = 0; col.null_count++; }
+        else { idx[i] = uint32_t(remap[size_t(ids[i])]); set_bit(col.validity, int64_t(i)); }
+      }
+      if (col.null_count == 0) col.validity.clear();
+      col.dictionary = std::move(dict);
+    } else {
+      col.format = ko.is_float ? "g" : "l";
+      col.data.resize(R * 8);
+      std::vector<uint8_t> valid(R);
+      if (R) {
+        CUDA_TRY(cudaMemcpyAsync(col.data.data(), qd.out_data[o], R * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(valid.data(), qd.out_valid[o], R, cudaMemcpyDeviceToHost, s));
+      }
+      CUDA_TRY(cudaStreamSynchronize(s));
+      res->stats.d2h_bytes += R * 9;
+      col.validity.assign((R + 7) / 8, 0);
+      for (size_t i = 0; i < R; i++) {
+        if (valid[i]) set_bit(col.validity, int64_t(i));
+        else col.null_count++;
+      }
+      if (col.null_count == 0) col.validity.clear();
+    }
+    res->stats.algorithmic_bytes += R * (ko.is_int64 ? 8 : 4);
+    cols.push_back(std::move(col));
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+  res->stats.total_device_ms = ms;
+  if (R > 0) {  // an empty selection emits no record (filter.go:264-266)
+    res->records.push_back(std::move(cols));
+    res->record_rows.push_back(int64_t(R));
+  }
+  res->finalized = true;
+  res->table.reset();
+  res->aux.reset();
+  res->qdesc_dev.reset();
+  return FGPU_OK;
+}
+
 int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
+  if (res->rows_plan) return finalize_rows(ctx, res);
   FinalizeDesc& fd = res->fd;
   cudaStream_t s = ctx->stream;
   // Upper bound of result rows: every slot could be occupied; count first to size the output.
@@ -865,7 +995,7 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
     cols.push_back(std::move(col));
   }
   res->stats.algorithmic_bytes += (size_t(nk) + size_t(na)) * G * 8;
-  if (G > 0 || true) {
+  if (G > 0) {  // finishAggregate skips empty aggregates (aggregate.go:547-549)
     res->records.push_back(std::move(cols));
     res->record_rows.push_back(int64_t(G));
   }
@@ -889,7 +1019,7 @@ int32_t fgpu_abi_version(void) { return FGPU_ABI_VERSION; }
 int32_t fgpu_init(const fgpu_config* cfg, fgpu_ctx** out) {
   if (!cfg || !out) return fail(FGPU_ERR_INVALID, "null argument");
   if (cfg->abi_version != FGPU_ABI_VERSION) return fail(FGPU_ERR_INVALID, "ABI version mismatch");
-  if (cfg->tile_rows != 0 && cfg->tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 or 2048");
+  if (cfg->tile_rows != 0 && cfg->tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 (default)");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -935,7 +1065,7 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   part->id = part_id;
   part->tx = tx;
   std::string err;
-  if (!build_part_image(file, len, ctx->tile_rows, &t, part.get(), &err)) return fail(FGPU_ERR_PARQUET, err);
+  if (!build_part_image(file, len, kIndexRows, &t, part.get(), &err)) return fail(FGPU_ERR_PARQUET, err);
   void* dev = nullptr;
   CUDA_TRY(cudaMalloc(&dev, part->image.size()));
   cudaError_t e = cudaMemcpyAsync(dev, part->image.data(), part->image.size(), cudaMemcpyHostToDevice, ctx->stream);
@@ -995,8 +1125,8 @@ int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
 
 int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** out) {
   if (!ctx || !plan || !out || !plan->table) return fail(FGPU_ERR_INVALID, "null argument");
-  if (plan->kind != FGPU_PLAN_AGGREGATE && plan->kind != FGPU_PLAN_DISTINCT)
-    return fail(FGPU_ERR_UNSUPPORTED, "only AGGREGATE and DISTINCT plans are implemented");
+  if (plan->kind != FGPU_PLAN_AGGREGATE && plan->kind != FGPU_PLAN_DISTINCT && plan->kind != FGPU_PLAN_FILTER)
+    return fail(FGPU_ERR_INVALID, "unknown plan kind");
   auto q = std::make_unique<fgpu_query>();
   q->ctx = ctx;
   q->table = plan->table;
@@ -1036,7 +1166,7 @@ int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** ou
     if (!check(plan->group_by[i])) return fail(FGPU_ERR_INVALID, "group-by index out of range");
     q->group_by.push_back(plan->group_by[i]);
   }
-  if (plan->kind == FGPU_PLAN_DISTINCT && plan->n_aggs != 0) return fail(FGPU_ERR_INVALID, "DISTINCT plan with aggregates");
+  if (plan->kind != FGPU_PLAN_AGGREGATE && plan->n_aggs != 0) return fail(FGPU_ERR_INVALID, "DISTINCT / FILTER plan with aggregates");
   if (plan->kind == FGPU_PLAN_AGGREGATE && plan->n_aggs == 0) return fail(FGPU_ERR_INVALID, "AGGREGATE plan without aggregates");
   for (int32_t i = 0; i < plan->n_aggs; i++) {
     if (!check(plan->aggs[i].expr)) return fail(FGPU_ERR_INVALID, "aggregate expression index out of range");
@@ -1072,6 +1202,7 @@ int32_t fgpu_query_execute_partial(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_wat
   CUDA_TRY(cudaSetDevice(ctx->device));
   auto res = std::make_unique<fgpu_result>();
   res->ctx = ctx;
+  if (q->kind == FGPU_PLAN_FILTER) return fail(FGPU_ERR_INVALID, "rows plans have no partial table: execute them per rank");
   int32_t rc = run_scan(ctx, *q, tx_watermark, res.get());
   if (rc) return rc;
   *dev_ptr = res->table.p;
@@ -1288,9 +1419,9 @@ int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_ro
                               uint64_t* out_len) {
   if (!file || !out_len) return fail(FGPU_ERR_INVALID, "null argument");
   if (tile_rows == 0) tile_rows = kTileRows;
-  if (tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 or 2048");
+  if (tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 (default)");
   std::string err;
-  std::string js = describe_part_json(file, len, tile_rows, &err);
+  std::string js = describe_part_json(file, len, kIndexRows, &err);
   if (js.empty()) return fail(FGPU_ERR_PARQUET, err);
   *out_len = js.size();
   if (!buf) return FGPU_OK;

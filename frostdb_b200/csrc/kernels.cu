@@ -1,20 +1,27 @@
 // sm_100a kernels of libfrostgpu.
 //
-//   k_scan      K1+K2+K4/K5 fused: per 2048-row tile, decode the projected column chunks from their
-//               stored Parquet encoding (PLAIN / RLE-bit-packed hybrid / RLE_DICTIONARY) in shared
-//               memory, evaluate the predicate tree into a per-row selection, and fold the selected
-//               rows into the aggregate table with warp-aggregated atomics.  Replaces
-//               ParquetConverter.Convert (pqarrow/arrow.go:264-373) + PredicateFilter.Callback
-//               (query/physicalplan/filter.go:255-323) + HashAggregate.Callback
-//               (query/physicalplan/aggregate.go:263-490) + Distinction.Callback (distinct.go:70-170).
-//   k_finalize  K6: aggregate table -> compacted result columns (finishAggregate, aggregate.go:543-633).
-//   k_merge     K6: folds gathered partial tables of other ranks into the local table
-//               (Synchronizer + final HashAggregate, synchronize.go:16-53, physicalplan.go:438-471).
-//   k_decode    K1 standalone: one column chunk -> dense Arrow-style buffers.
+//   k_scan<KW>   K1+K2+K4/K5 fused.  Every warp streams one 256-row chunk of a row group at a time:
+//                it walks the stored Parquet encodings of the projected column chunks directly in HBM
+//                (PLAIN int64/double, RLE/bit-packed hybrid definition levels and dictionary indices)
+//                with per-lane run cursors seeded from a 256-row chunk index, evaluates the predicate
+//                leaves into per-row bits, and folds the selected rows into the aggregate table.
+//                Rows whose group does not change inside a warp (the common case for parts sorted in
+//                compaction order) are accumulated in registers and flushed with ONE warp-reduced
+//                atomic per aggregate when the group changes; mixed groups fall back to
+//                __match_any_sync peer reduction.  Replaces ParquetConverter.Convert
+//                (pqarrow/arrow.go:264-373), PredicateFilter.Callback (filter.go:255-323),
+//                HashAggregate.Callback (aggregate.go:263-490), Distinction.Callback (distinct.go:70-170).
+//   k_rows       K1+K2+K3: same decode + predicate, then order-preserving stream compaction
+//                (warp ballot + decoupled look-back prefix over tiles) of the projected columns:
+//                PredicateFilter.filter() (filter.go:276-323) + Projection.
+//   k_finalize   K6: aggregate table -> compacted result columns (finishAggregate, aggregate.go:543-633).
+//   k_merge      K6: folds gathered partial tables into the local one (Synchronizer + final
+//                HashAggregate, synchronize.go:16-53, physicalplan.go:438-471).
+//   k_decode     K1 standalone: one column chunk -> dense buffers.
 //
-// This is HBM-bound integer/indexing work: no tensor cores.  Loads of PLAIN columns are coalesced
-// 8-byte-per-lane streams, hybrid streams are read through 4-byte aligned windows, atomics are
-// aggregated per warp with __match_any_sync before touching the table.
+// HBM-bound integer / indexing work: no tensor cores.  No shared-memory staging is needed because a
+// warp's 32 lanes always touch 32 consecutive rows (256 B of a PLAIN column per load instruction, the
+// same few bytes of a hybrid stream).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -26,103 +33,37 @@ namespace fgpu {
 
 namespace {
 
-constexpr int NT = kScanThreads;      // threads per CTA
-constexpr int RPT = kRowsPerThread;   // rows per thread
-constexpr int TILE = NT * RPT;        // rows per tile
-constexpr int NWARP = NT / 32;
-static_assert(TILE == kTileRows, "tile size mismatch");
-static_assert(RPT == 8, "blocked decode assumes 8 rows per thread");
+constexpr int NT = kScanThreads;     // threads per CTA
+constexpr int NWARP = NT / 32;       // warps per CTA = chunks per tile
+constexpr int STEPS = kIndexRows / 32;  // 32-row steps per chunk
+constexpr int TILE = kTileRows;
+static_assert(NWARP * kIndexRows == TILE, "tile = one chunk per warp");
+static_assert(STEPS == 4, "unrolled for 4 steps");
 
-struct SmemLayout {
-  uint16_t* ridx;      // [TILE] run index per value slot (scratch of the hybrid expander)
-  uint32_t* tmp;       // [TILE] decoded values of the column being processed
-  uint32_t* leafbits;  // [TILE] one bit per predicate leaf
-  uint8_t* vbyte;      // [NT] validity of 8 consecutive rows
-  uint16_t* vrank;     // [NT] number of valid rows before each group of 8
-  uint32_t* wscr;      // [64] cross-warp scratch
-  unsigned long long* keyw;  // [key_words][TILE] packed group key (dense mode: word 0 = slot index)
-  long long* numbuf;   // [n_numbufs][TILE] staged numeric columns
-  uint32_t* numnull;   // [n_numbufs][TILE/32] null bits of staged numeric columns
+constexpr uint32_t kNoSlot = 0xffffffffu;
+constexpr uint32_t FULL = 0xffffffffu;
+
+// ---- hybrid stream cursor ------------------------------------------------------------------------------
+struct HybCur {
+  const Run* runs;
+  const uint8_t* stream;
+  uint32_t k, start, end, val, meta, off;
 };
 
-__device__ __forceinline__ SmemLayout carve(uint8_t* base, int key_words, int n_numbufs) {
-  SmemLayout s;
-  size_t off = 0;
-  s.keyw = reinterpret_cast<unsigned long long*>(base + off);
-  off += size_t(key_words) * TILE * 8;
-  s.numbuf = reinterpret_cast<long long*>(base + off);
-  off += size_t(n_numbufs) * TILE * 8;
-  s.tmp = reinterpret_cast<uint32_t*>(base + off);
-  off += TILE * 4;
-  s.leafbits = reinterpret_cast<uint32_t*>(base + off);
-  off += TILE * 4;
-  s.ridx = reinterpret_cast<uint16_t*>(base + off);
-  off += TILE * 2;
-  s.numnull = reinterpret_cast<uint32_t*>(base + off);
-  off += size_t(n_numbufs) * (TILE / 32) * 4;
-  s.wscr = reinterpret_cast<uint32_t*>(base + off);
-  off += 64 * 4;
-  s.vrank = reinterpret_cast<uint16_t*>(base + off);
-  off += NT * 2;
-  s.vbyte = base + off;
-  return s;
+__device__ __forceinline__ void hc_load(HybCur& c) {
+  uint4 r = __ldg(reinterpret_cast<const uint4*>(c.runs + c.k));
+  c.start = r.x;
+  c.off = r.y;
+  c.val = r.z;
+  c.meta = r.w;
+  c.end = __ldg(&c.runs[c.k + 1].start);
 }
-
-// ---- block-wide helpers ---------------------------------------------------------------------------
-
-// In-place inclusive max-scan over ridx[0..TILE).  Markers are increasing run indices, so the
-// running maximum at a position is the run that covers it.
-__device__ __forceinline__ void block_max_scan_u16(uint16_t* ridx, uint32_t* wscr) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint4 v = reinterpret_cast<uint4*>(ridx)[tid];
-  uint32_t a[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16,
-                   v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
-#pragma unroll
-  for (int i = 1; i < 8; i++) a[i] = max(a[i], a[i - 1]);
-  uint32_t incl = a[7];
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl = max(incl, o);
-  }
-  uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) excl = 0;
-  if (lane == 31) wscr[warp] = incl;
-  __syncthreads();
-  uint32_t base = excl;
-  for (int w = 0; w < warp; w++) base = max(base, wscr[w]);
-#pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = max(a[i], base);
-  v.x = a[0] | (a[1] << 16);
-  v.y = a[2] | (a[3] << 16);
-  v.z = a[4] | (a[5] << 16);
-  v.w = a[6] | (a[7] << 16);
-  reinterpret_cast<uint4*>(ridx)[tid] = v;
-  __syncthreads();
+__device__ __forceinline__ void hc_init(HybCur& c, const Run* runs, const uint8_t* stream, uint32_t k0) {
+  c.runs = runs;
+  c.stream = stream;
+  c.k = k0;
+  hc_load(c);
 }
-
-// Exclusive sum-scan of one value per thread; returns the exclusive prefix, *total = block sum.
-__device__ __forceinline__ uint32_t block_excl_sum(uint32_t x, uint32_t* wscr, uint32_t* total) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t incl = x;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += o;
-  }
-  if (lane == 31) wscr[32 + warp] = incl;
-  __syncthreads();
-  uint32_t base = 0, tot = 0;
-  for (int w = 0; w < NWARP; w++) {
-    uint32_t t = wscr[32 + w];
-    if (w < warp) base += t;
-    tot += t;
-  }
-  *total = tot;
-  __syncthreads();
-  return base + incl - x;
-}
-
 __device__ __forceinline__ uint32_t extract_bits(const uint8_t* stream, uint32_t off, uint64_t bit, uint32_t w) {
   uint64_t byte = uint64_t(off) + (bit >> 3);
   const uint32_t* wp = reinterpret_cast<const uint32_t*>(stream) + (byte >> 2);
@@ -132,81 +73,102 @@ __device__ __forceinline__ uint32_t extract_bits(const uint8_t* stream, uint32_t
   uint32_t mask = (w >= 32) ? 0xffffffffu : ((1u << w) - 1u);
   return v & mask;
 }
-
-// Expands `nv` values of a hybrid stream starting at value ordinal v0 into out[0..nv).
-// first_run is the directory index of the run that holds ordinal v0.  Blocked mapping: thread t
-// produces slots 8t..8t+7.  Ends with a barrier: out[] is visible to the whole CTA on return.
-__device__ __forceinline__ void decode_hybrid(const uint8_t* __restrict__ stream, const Run* __restrict__ runs,
-                                              uint32_t first_run, uint32_t n_runs, uint32_t v0, uint32_t nv,
-                                              uint32_t* out, uint16_t* ridx, uint32_t* wscr) {
-  const int tid = threadIdx.x;
-  reinterpret_cast<uint4*>(ridx)[tid] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  const uint32_t vend = v0 + nv;
-  for (uint32_t k = first_run + 1 + tid; k < n_runs; k += NT) {
-    uint32_t st = __ldg(&runs[k].start);
-    if (st >= vend) break;
-    ridx[st - v0] = uint16_t(k - first_run);
+// Value at ordinal `ord` (ordinals are requested in increasing order per lane).
+__device__ __forceinline__ uint32_t hc_get(HybCur& c, uint32_t ord) {
+  while (ord >= c.end) {
+    c.k++;
+    hc_load(c);
   }
-  __syncthreads();
-  block_max_scan_u16(ridx, wscr);
-  const uint32_t s0 = uint32_t(tid) * RPT;
-  if (s0 < nv) {
-    uint4 rv = reinterpret_cast<const uint4*>(ridx)[tid];
-    uint32_t rr[8] = {rv.x & 0xffffu, rv.x >> 16, rv.y & 0xffffu, rv.y >> 16,
-                      rv.z & 0xffffu, rv.z >> 16, rv.w & 0xffffu, rv.w >> 16};
-    uint32_t cur = 0xffffffffu;
-    uint4 r = make_uint4(0, 0, 0, 0);
+  if ((c.meta & 1u) == 0) return c.val;
+  uint32_t w = (c.meta >> 8) & 0xffu;
+  return extract_bits(c.stream, c.off, uint64_t(ord - c.start) * w, w);
+}
+
+// Decodes the chunk's 8 x 32 rows of a dictionary-encoded column: idx[j] = chunk-local dictionary
+// index of row (c0 + 32 j + lane), kNullIdx for NULL / out of range / absent column.
+__device__ __forceinline__ void decode_dict_chunk(const ChunkDesc& c, uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane,
+                                                  uint32_t (&idx)[STEPS]) {
+  if (c.kind == CK_ABSENT) {
 #pragma unroll
-    for (int j = 0; j < RPT; j++) {
-      uint32_t s = s0 + j;
-      if (s < nv) {
-        if (rr[j] != cur) {
-          cur = rr[j];
-          r = __ldg(reinterpret_cast<const uint4*>(runs + first_run + cur));
-        }
-        uint32_t val;
-        if ((r.w & 1u) == 0) {
-          val = r.z;
-        } else {
-          uint32_t w = (r.w >> 8) & 0xffu;
-          val = extract_bits(stream, r.y, uint64_t(v0 + s - r.x) * w, w);
-        }
-        out[s] = val;
-      }
+    for (int j = 0; j < STEPS; j++) idx[j] = kNullIdx;
+    return;
+  }
+  const uint32_t lt = (1u << lane) - 1u;
+  HybCur vc, dc;
+  uint32_t vbase = c0;
+  const bool nulls = c.has_nulls;
+  if (nulls) {
+    hc_init(dc, c.def_runs, c.def, __ldg(&c.tile_defrun[chunk]));
+    vbase = __ldg(&c.tile_val0[chunk]);
+  }
+  hc_init(vc, c.runs, c.values, __ldg(&c.tile_run[chunk]));
+#pragma unroll
+  for (int j = 0; j < STEPS; j++) {
+    uint32_t r = c0 + j * 32 + lane;
+    bool valid = r < n_rows;
+    uint32_t ord = r;
+    if (nulls) {
+      if (valid) valid = hc_get(dc, r) != 0;
+      unsigned m = __ballot_sync(FULL, valid);
+      ord = vbase + __popc(m & lt);
+      vbase += __popc(m);
     }
+    idx[j] = valid ? hc_get(vc, ord) : kNullIdx;
   }
-  __syncthreads();
 }
 
-// Definition levels of the tile -> vbyte/vrank; returns the number of valid rows.
-__device__ __forceinline__ uint32_t decode_validity(const ChunkDesc& c, uint32_t tile_in_rg, uint32_t r0, uint32_t n,
-                                                    const SmemLayout& sm) {
-  decode_hybrid(c.def, c.def_runs, __ldg(&c.tile_defrun[tile_in_rg]), c.n_defruns, r0, n, sm.tmp, sm.ridx, sm.wscr);
-  const int tid = threadIdx.x;
-  uint32_t byte = 0;
+// Decodes the chunk's rows of a numeric column: bits[j] raw 8 bytes (0 for NULL, as
+// builder.AppendValue leaves NULL slots: pqarrow/builder/utils.go:54-58, optbuilders.go:337-340),
+// nullmask bit j set when the row is NULL / absent / out of range.
+__device__ __forceinline__ void decode_num_chunk(const ChunkDesc& c, uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane,
+                                                 long long (&bits)[STEPS], uint32_t& nullmask) {
+  nullmask = 0;
+  if (c.kind == CK_ABSENT) {
 #pragma unroll
-  for (int j = 0; j < RPT; j++) {
-    uint32_t s = uint32_t(tid) * RPT + j;
-    if (s < n && sm.tmp[s] != 0) byte |= 1u << j;
+    for (int j = 0; j < STEPS; j++) bits[j] = 0;
+    nullmask = (1u << STEPS) - 1u;
+    return;
   }
-  uint32_t total;
-  uint32_t excl = block_excl_sum(__popc(byte), sm.wscr, &total);
-  sm.vbyte[tid] = uint8_t(byte);
-  sm.vrank[tid] = uint16_t(excl);
-  __syncthreads();
-  return total;
+  const long long* vals = reinterpret_cast<const long long*>(c.values);
+  if (c.kind == CK_PLAIN64 && !c.has_nulls) {
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+      uint32_t r = c0 + j * 32 + lane;
+      bool inb = r < n_rows;
+      bits[j] = inb ? __ldg(vals + r) : 0;
+      if (!inb) nullmask |= 1u << j;
+    }
+    return;
+  }
+  const uint32_t lt = (1u << lane) - 1u;
+  HybCur vc, dc;
+  uint32_t vbase = c0;
+  const bool nulls = c.has_nulls;
+  if (nulls) {
+    hc_init(dc, c.def_runs, c.def, __ldg(&c.tile_defrun[chunk]));
+    vbase = __ldg(&c.tile_val0[chunk]);
+  }
+  const bool dict = c.kind == CK_DICT64;
+  if (dict) hc_init(vc, c.runs, c.values, __ldg(&c.tile_run[chunk]));
+#pragma unroll
+  for (int j = 0; j < STEPS; j++) {
+    uint32_t r = c0 + j * 32 + lane;
+    bool valid = r < n_rows;
+    uint32_t ord = r;
+    if (nulls) {
+      if (valid) valid = hc_get(dc, r) != 0;
+      unsigned m = __ballot_sync(FULL, valid);
+      ord = vbase + __popc(m & lt);
+      vbase += __popc(m);
+    }
+    long long v = 0;
+    if (valid) v = dict ? __ldg(&c.dict64[hc_get(vc, ord)]) : __ldg(vals + ord);
+    bits[j] = v;
+    if (!valid) nullmask |= 1u << j;
+  }
 }
 
-__device__ __forceinline__ bool row_valid(const SmemLayout& sm, uint32_t i, uint32_t* pos) {
-  uint32_t byte = sm.vbyte[i >> 3];
-  uint32_t bit = i & 7u;
-  *pos = uint32_t(sm.vrank[i >> 3]) + __popc(byte & ((1u << bit) - 1u));
-  return (byte >> bit) & 1u;
-}
-
-// ---- predicate / expression evaluation ---------------------------------------------------------------
-
+// ---- predicate --------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool cmp_i64(uint8_t op, long long a, long long b) {
   switch (op) {
     case 1: return a == b;
@@ -214,8 +176,7 @@ __device__ __forceinline__ bool cmp_i64(uint8_t op, long long a, long long b) {
     case 3: return a < b;
     case 4: return a <= b;
     case 5: return a > b;
-    case 6: return a >= b;
-    default: return false;
+    default: return a >= b;
   }
 }
 __device__ __forceinline__ bool cmp_f64(uint8_t op, double a, double b) {
@@ -225,14 +186,14 @@ __device__ __forceinline__ bool cmp_f64(uint8_t op, double a, double b) {
     case 3: return a < b;
     case 4: return a <= b;
     case 5: return a > b;
-    case 6: return a >= b;
-    default: return false;
+    default: return a >= b;
   }
 }
 
 __device__ __forceinline__ bool eval_filter(const QueryDesc& q, uint32_t bits) {
-  // postfix program over leaf bits; stack kept in a 32-bit word
-  uint32_t stack = 0;
+  if (q.filter_kind == FK_AND) return (bits & q.filter_mask) == q.filter_mask;
+  if (q.filter_kind == FK_OR) return (bits & q.filter_mask) != 0;
+  uint32_t stack = 0;  // postfix program over leaf bits; stack kept in a 32-bit word
   int sp = 0;
   for (int i = 0; i < q.n_filter_prog; i++) {
     uint8_t op = q.filter_prog[i];
@@ -250,75 +211,127 @@ __device__ __forceinline__ bool eval_filter(const QueryDesc& q, uint32_t bits) {
   return stack & 1u;
 }
 
-struct NumVal {
-  long long bits;
-  bool null;
-};
-
-// Value of numeric slot `slot` for tile row i (raw 0 for NULL, as builder.AppendValue leaves it:
-// pqarrow/builder/utils.go:54-58 + optbuilders.go:337-340).
-__device__ __forceinline__ NumVal load_num(const QueryDesc& q, const ChunkDesc* __restrict__ chunks, const SmemLayout& sm,
-                                           int slot, uint32_t r0, uint32_t i) {
-  NumVal v;
-  int nb = q.slot_numbuf[slot];
-  const ChunkDesc& c = chunks[slot];
-  if (c.kind == CK_ABSENT) {
-    v.bits = 0;
-    v.null = true;
-  } else if (nb < 0 || (c.kind == CK_PLAIN64 && !c.has_nulls)) {
-    v.bits = __ldg(reinterpret_cast<const long long*>(c.values) + r0 + i);
-    v.null = false;
-  } else {
-    v.bits = sm.numbuf[size_t(nb) * TILE + i];
-    v.null = (sm.numnull[nb * (TILE / 32) + (i >> 5)] >> (i & 31)) & 1u;
+// Evaluates every predicate leaf of the chunk: leafbits[j] bit l = leaf l selects row j.
+// NULL semantics: binaryscalarexpr.go:143-150 (numeric NULL never selected), :165-172,:205-212
+// (dictionary == NULL / != NULL), missing columns :47-73 (LM_ALL / LM_NONE precomputed on the host).
+__device__ __forceinline__ void eval_leaves(const QueryDesc& q, const ChunkDesc* __restrict__ chunks, const LeafRt* __restrict__ lrt,
+                                            uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane, uint32_t (&leafbits)[STEPS]) {
+  uint32_t cbits = 0;
+  for (int l = 0; l < q.n_leaves; l++)
+    if (lrt[l].mode == LM_ALL) cbits |= 1u << l;
+#pragma unroll
+  for (int j = 0; j < STEPS; j++) leafbits[j] = cbits;
+  for (int slot = 0; slot < q.n_slots; slot++) {
+    if (!q.slot_used_by_leaf[slot]) continue;
+    const ChunkDesc& c = chunks[slot];
+    if (q.slot_type[slot] == ST_DICT) {
+      uint32_t idx[STEPS];
+      decode_dict_chunk(c, chunk, c0, n_rows, lane, idx);
+      for (int l = 0; l < q.n_leaves; l++) {
+        if (q.leaves[l].slot != slot || lrt[l].mode != LM_EVAL) continue;
+        const uint8_t* lut = lrt[l].lut;
+        const uint32_t nullres = lrt[l].null_result;
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) {
+          uint32_t r = (idx[j] == kNullIdx) ? nullres : uint32_t(__ldg(lut + idx[j]));
+          leafbits[j] |= (r & 1u) << l;
+        }
+      }
+    } else {
+      long long bits[STEPS];
+      uint32_t nullmask;
+      decode_num_chunk(c, chunk, c0, n_rows, lane, bits, nullmask);
+      const bool f64col = q.slot_type[slot] == ST_F64;
+      for (int l = 0; l < q.n_leaves; l++) {
+        const LeafDesc& ld = q.leaves[l];
+        if (ld.slot != slot || lrt[l].mode != LM_EVAL) continue;
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) {
+          bool r = false;
+          if (!((nullmask >> j) & 1u)) {
+            if (ld.cmp_float) {
+              double x = f64col ? __longlong_as_double(bits[j]) : double(bits[j]);
+              r = cmp_f64(ld.op, x, ld.lit_f);
+            } else {
+              r = cmp_i64(ld.op, bits[j], ld.lit_i);
+            }
+          }
+          leafbits[j] |= uint32_t(r) << l;
+        }
+      }
+    }
   }
-  return v;
 }
 
-__device__ __forceinline__ long long eval_prog(const QueryDesc& q, const AggDesc& a, const ChunkDesc* __restrict__ chunks,
-                                               const SmemLayout& sm, uint32_t r0, uint32_t i) {
-  // Arithmetic ignores validity and Div by zero yields NULL, i.e. a raw 0 in the aggregated
-  // array (query/physicalplan/project.go:169-395, :216-218).
-  long long st[8];
+// ---- aggregate expressions ----------------------------------------------------------------------------------
+// Arithmetic ignores validity and Div by zero yields NULL, i.e. a raw 0 in the aggregated array
+// (query/physicalplan/project.go:169-395, :216-218).
+__device__ __forceinline__ long long apply_arith(uint8_t op, bool is_float, long long lb, long long rb) {
+  if (is_float) {
+    double l = __longlong_as_double(lb), r = __longlong_as_double(rb), x;
+    switch (op) {
+      case PO_ADD: x = l + r; break;
+      case PO_SUB: x = l - r; break;
+      case PO_MUL: x = l * r; break;
+      default: x = (r == 0.0) ? 0.0 : l / r; break;
+    }
+    return __double_as_longlong(x);
+  }
+  unsigned long long l = (unsigned long long)lb, r = (unsigned long long)rb;
+  switch (op) {
+    case PO_ADD: return (long long)(l + r);
+    case PO_SUB: return (long long)(l - r);
+    case PO_MUL: return (long long)(l * r);
+    default:
+      if (rb == 0) return 0;
+      if (rb == -1) return (long long)(0ull - l);  // Go wraps INT64_MIN / -1
+      return lb / rb;
+  }
+}
+
+// Values of aggregate `a` for the chunk's rows.  Evaluated column-at-a-time over a small operand stack
+// of 8-row vectors (depth <= 3; deeper expressions are rejected by the host).
+__device__ __forceinline__ void eval_agg_values(const QueryDesc& q, const AggDesc& a, const ChunkDesc* __restrict__ chunks,
+                                                uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane, long long (&out)[STEPS]) {
+  long long s1[STEPS], s2[STEPS];
   int sp = 0;
   for (int p = a.prog_off; p < a.prog_off + a.prog_len; p++) {
     const ProgOp& o = q.prog[p];
-    if (o.op == PO_LOAD) {
-      st[sp++] = load_num(q, chunks, sm, o.slot, r0, i).bits;
-    } else if (o.op == PO_CONST) {
-      st[sp++] = o.imm;
-    } else {
-      long long rb = st[--sp], lb = st[--sp], res;
-      if (a.is_float) {
-        double l = __longlong_as_double(lb), r = __longlong_as_double(rb), x;
-        switch (o.op) {
-          case PO_ADD: x = l + r; break;
-          case PO_SUB: x = l - r; break;
-          case PO_MUL: x = l * r; break;
-          default: x = (r == 0.0) ? 0.0 : l / r; break;
-        }
-        res = __double_as_longlong(x);
+    if (o.op == PO_LOAD || o.op == PO_CONST) {
+      long long v[STEPS];
+      if (o.op == PO_LOAD) {
+        uint32_t nm;
+        decode_num_chunk(chunks[o.slot], chunk, c0, n_rows, lane, v, nm);
       } else {
-        unsigned long long l = (unsigned long long)lb, r = (unsigned long long)rb;
-        switch (o.op) {
-          case PO_ADD: res = (long long)(l + r); break;
-          case PO_SUB: res = (long long)(l - r); break;
-          case PO_MUL: res = (long long)(l * r); break;
-          default:
-            if (rb == 0) res = 0;
-            else if (rb == -1) res = (long long)(0ull - l);  // avoids INT64_MIN / -1 trap semantics; Go wraps
-            else res = lb / rb;
-            break;
-        }
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) v[j] = o.imm;
       }
-      st[sp++] = res;
+      if (sp == 0) {
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) out[j] = v[j];
+      } else if (sp == 1) {
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) s1[j] = v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) s2[j] = v[j];
+      }
+      sp++;
+    } else {
+      // binary op on the two topmost vectors
+      if (sp == 2) {
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) out[j] = apply_arith(o.op, a.is_float, out[j], s1[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) s1[j] = apply_arith(o.op, a.is_float, s1[j], s2[j]);
+      }
+      sp--;
     }
   }
-  return st[0];
 }
 
-// ---- aggregate table -----------------------------------------------------------------------------------
-
+// ---- aggregate table ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33;
   x *= 0xff51afd7ed558ccdull;
@@ -331,10 +344,13 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 // Exact-key open addressing: a slot is claimed by CAS on its tag (0 -> 1), the key words are
 // written, then the tag is published as fingerprint|2.  Unlike the reference, which keys groups
 // only by a 64-bit hash (aggregate.go:411), equal tags are confirmed against the stored key.
-__device__ __forceinline__ uint32_t hash_find_or_insert(const QueryDesc& q, const unsigned long long* kw, bool* overflow) {
+template <int KW>
+__device__ __forceinline__ uint32_t hash_find_or_insert(const QueryDesc& q, const unsigned long long (&kw)[KW], bool* overflow) {
   const int W = q.key_words;
   uint64_t h = 0x9e3779b97f4a7c15ull;
-  for (int w = 0; w < W; w++) h = mix64(h ^ kw[w]) + 0x9e3779b97f4a7c15ull * (w + 1);
+#pragma unroll
+  for (int w = 0; w < KW; w++)
+    if (w < W) h = mix64(h ^ kw[w]) + 0x9e3779b97f4a7c15ull * (w + 1);
   const uint32_t fp = uint32_t(h >> 32) | 2u;
   const uint32_t mask = q.table_slots - 1;
   uint32_t s = uint32_t(h) & mask;
@@ -345,7 +361,9 @@ __device__ __forceinline__ uint32_t hash_find_or_insert(const QueryDesc& q, cons
     if (t == 0) {
       uint32_t old = atomicCAS(q.t_tag + s, 0u, 1u);
       if (old == 0) {
-        for (int w = 0; w < W; w++) keys[size_t(s) * W + w] = kw[w];
+#pragma unroll
+        for (int w = 0; w < KW; w++)
+          if (w < W) keys[size_t(s) * W + w] = kw[w];
         __threadfence();
         tag[s] = fp;
         return s;
@@ -355,7 +373,9 @@ __device__ __forceinline__ uint32_t hash_find_or_insert(const QueryDesc& q, cons
     while (t == 1u) t = tag[s];
     if (t == fp) {
       bool eq = true;
-      for (int w = 0; w < W; w++) eq &= (keys[size_t(s) * W + w] == kw[w]);
+#pragma unroll
+      for (int w = 0; w < KW; w++)
+        if (w < W) eq &= (keys[size_t(s) * W + w] == kw[w]);
       if (eq) return s;
     }
     s = (s + 1) & mask;
@@ -365,12 +385,14 @@ __device__ __forceinline__ uint32_t hash_find_or_insert(const QueryDesc& q, cons
 }
 
 template <typename T, typename Op>
-__device__ __forceinline__ T peer_reduce(T v, unsigned peers, int lane, Op op) {
-  if (peers == 0xffffffffu) {
+__device__ __forceinline__ T warp_reduce(T v, Op op) {
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
-    return v;
-  }
+  for (int d = 16; d >= 1; d >>= 1) v = op(v, __shfl_xor_sync(FULL, v, d));
+  return v;
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T peer_reduce(T v, unsigned peers, int lane, Op op) {
   const int cnt = __popc(peers);
   if (cnt == 1) return v;
   const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -416,21 +438,55 @@ __device__ __forceinline__ void apply_agg(uint8_t func, bool is_float, long long
   }
 }
 
-__device__ __forceinline__ long long reduce_agg(uint8_t func, bool is_float, long long bits, unsigned peers, int lane) {
+__device__ __forceinline__ long long agg_identity(uint8_t func, bool is_float) {
+  if (func == 2) return is_float ? 0x7ff0000000000000ll : 0x7fffffffffffffffll;
+  if (func == 3) return is_float ? (long long)0xfff0000000000000ull : (long long)0x8000000000000000ull;
+  return 0;  // sum: +0 (int) / +0.0 (double)
+}
+
+__device__ __forceinline__ long long agg_combine(uint8_t func, bool is_float, long long a, long long b) {
   if (func == 1) {
-    if (is_float)
-      return __double_as_longlong(peer_reduce(__longlong_as_double(bits), peers, lane, [](double a, double b) { return a + b; }));
-    return (long long)peer_reduce((unsigned long long)bits, peers, lane,
-                                  [](unsigned long long a, unsigned long long b) { return a + b; });
-  } else if (func == 2) {
-    if (is_float)
-      return __double_as_longlong(peer_reduce(__longlong_as_double(bits), peers, lane, [](double a, double b) { return (b < a) ? b : a; }));
-    return peer_reduce(bits, peers, lane, [](long long a, long long b) { return (b < a) ? b : a; });
-  } else {
-    if (is_float)
-      return __double_as_longlong(peer_reduce(__longlong_as_double(bits), peers, lane, [](double a, double b) { return (b > a) ? b : a; }));
-    return peer_reduce(bits, peers, lane, [](long long a, long long b) { return (b > a) ? b : a; });
+    if (is_float) return __double_as_longlong(__longlong_as_double(a) + __longlong_as_double(b));
+    return (long long)((unsigned long long)a + (unsigned long long)b);
   }
+  if (func == 2) {
+    if (is_float) return (__longlong_as_double(b) < __longlong_as_double(a)) ? b : a;
+    return (b < a) ? b : a;
+  }
+  if (is_float) return (__longlong_as_double(b) > __longlong_as_double(a)) ? b : a;
+  return (b > a) ? b : a;
+}
+
+// Warp-reduces the per-lane partial of one aggregate and lets lane 0 apply it to the table cell.
+__device__ __noinline__ void flush_agg(uint8_t func, bool is_float, long long* cell, long long acc, int lane) {
+  acc = warp_reduce(acc, [=](long long a, long long b) { return agg_combine(func, is_float, a, b); });
+  if (lane == 0) apply_agg(func, is_float, cell, acc);
+}
+
+// One step whose active lanes belong to different groups: peer reduction per distinct group.
+__device__ __noinline__ void mixed_agg(uint8_t func, bool is_float, long long* column, uint32_t slot, bool active, long long bits,
+                                       int lane) {
+  unsigned amask = __ballot_sync(FULL, active);
+  if (!active) return;
+  unsigned peers = __match_any_sync(amask, slot);
+  long long r = peer_reduce(bits, peers, lane, [=](long long a, long long b) { return agg_combine(func, is_float, a, b); });
+  if (lane == __ffs(peers) - 1) apply_agg(func, is_float, column + slot, r);
+}
+__device__ __noinline__ void mixed_rows(unsigned long long* rows, uint32_t slot, bool active, int lane) {
+  unsigned amask = __ballot_sync(FULL, active);
+  if (!active) return;
+  unsigned peers = __match_any_sync(amask, slot);
+  if (lane == __ffs(peers) - 1) atomicAdd(rows + slot, (unsigned long long)__popc(peers));
+}
+
+// Locates the row group of a tile (rg_first_tile ascending, n_rg + 1 entries).
+__device__ __forceinline__ int find_rg(const uint32_t* __restrict__ first_tile, int n_rg, uint32_t tile) {
+  int lo = 0, hi = n_rg;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(&first_tile[mid]) <= tile) lo = mid; else hi = mid;
+  }
+  return lo;
 }
 
 }  // namespace
@@ -438,204 +494,334 @@ __device__ __forceinline__ long long reduce_agg(uint8_t func, bool is_float, lon
 // ======================================================================================================
 // k_scan
 // ======================================================================================================
+template <int KW>
 __global__ void __launch_bounds__(NT) k_scan(const QueryDesc* __restrict__ qp) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const QueryDesc& q = *qp;
-  const SmemLayout sm = carve(smem_raw, q.key_words, int(q.n_numbufs));
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ QueryDesc sq;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(qp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
+    for (uint32_t i = threadIdx.x; i < sizeof(QueryDesc) / 4; i += NT) dst[i] = src[i];
+  }
+  __syncthreads();
+  const QueryDesc& q = sq;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool dense = q.table_mode == TM_DENSE;
+
+  // warp-uniform running group + per-lane partial aggregates carried across chunks
+  uint32_t cur_slot = kNoSlot;
+  uint32_t cur_cnt = 0;
+  long long acc[kMaxAggs];
+#pragma unroll 1
+  for (int a = 0; a < q.n_aggs; a++) acc[a] = agg_identity(q.aggs[a].func, q.aggs[a].is_float);
   unsigned long long selected_local = 0;
   bool overflow = false;
+  // hash mode: last key -> slot of this lane
+  unsigned long long last_kw[KW];
+  uint32_t last_slot = kNoSlot;
+#pragma unroll
+  for (int w = 0; w < KW; w++) last_kw[w] = ~0ull;
 
   for (uint32_t tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x) {
-    // locate the row group of this tile (rg_first_tile is ascending, n_rg + 1 entries)
-    int lo = 0, hi = q.n_rg;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (__ldg(&q.rg_first_tile[mid]) <= tile) lo = mid; else hi = mid;
-    }
-    const int rg = lo;
+    const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
     const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
-    const uint32_t r0 = tile_in_rg * TILE;
-    const uint32_t rg_rows = __ldg(&q.rg_rows[rg]);
-    const uint32_t n = min(uint32_t(TILE), rg_rows - r0);
+    const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
+    const uint32_t chunk = tile_in_rg * NWARP + warp;  // 256-row chunk index inside the row group
+    const uint32_t c0 = chunk * kIndexRows;
+    if (c0 >= n_rows) continue;  // warp-uniform
     const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
     const LeafRt* __restrict__ lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
 
-    // reset per-row state (strided mapping: row i = j*NT + tid is owned by one thread throughout)
+    // ---- predicate -> active mask per step ----------------------------------------------------
+    uint32_t actbits = 0;  // bit j: this lane's row of step j is selected
+    if (q.n_filter_prog > 0) {
+      uint32_t leafbits[STEPS];
+      eval_leaves(q, chunks, lrt, chunk, c0, n_rows, lane, leafbits);
 #pragma unroll
-    for (int j = 0; j < RPT; j++) {
-      uint32_t i = j * NT + tid;
-      sm.leafbits[i] = 0;
-      for (int w = 0; w < q.key_words; w++) sm.keyw[size_t(w) * TILE + i] = 0;
-    }
-    // constant leaves (missing-column rules) contribute their bit up front
-    {
-      uint32_t cbits = 0;
-      for (int l = 0; l < q.n_leaves; l++)
-        if (lrt[l].mode == LM_ALL) cbits |= 1u << l;
-      if (cbits) {
-#pragma unroll
-        for (int j = 0; j < RPT; j++) sm.leafbits[j * NT + tid] = cbits;
+      for (int j = 0; j < STEPS; j++) {
+        bool inb = c0 + j * 32 + lane < n_rows;
+        if (inb && eval_filter(q, leafbits[j])) actbits |= 1u << j;
       }
-    }
-    __syncthreads();
-
-    // ---- per column: decode, then feed keys / leaves / staging ------------------------------------
-    for (int slot = 0; slot < q.n_slots; slot++) {
-      const ChunkDesc& c = chunks[slot];
-      const uint8_t stype = q.slot_type[slot];
-      if (stype == ST_DICT) {
-        uint32_t nv = n, v0 = r0;
-        const bool absent = (c.kind == CK_ABSENT);
-        const bool nulls = !absent && c.has_nulls;
-        if (!absent) {
-          if (nulls) {
-            nv = decode_validity(c, tile_in_rg, r0, n, sm);
-            v0 = __ldg(&c.tile_val0[tile_in_rg]);
-          }
-          decode_hybrid(c.values, c.runs, __ldg(&c.tile_run[tile_in_rg]), c.n_runs, v0, nv, sm.tmp, sm.ridx, sm.wscr);
-        }
+    } else {
 #pragma unroll
-        for (int j = 0; j < RPT; j++) {
-          uint32_t i = j * NT + tid;
-          if (i >= n) continue;
-          uint32_t idx = kNullIdx;
-          if (!absent) {
-            if (nulls) {
-              uint32_t pos;
-              if (row_valid(sm, i, &pos)) idx = sm.tmp[pos];
-            } else {
-              idx = sm.tmp[i];
-            }
-          }
-          // group keys on this column
-          for (int k = 0; k < q.n_keys; k++) {
-            const KeyDesc& kd = q.keys[k];
-            if (kd.slot != slot) continue;
-            uint64_t code = (idx == kNullIdx) ? 0ull : uint64_t(__ldg(&c.lut[idx])) + 1ull;
-            if (q.table_mode == TM_DENSE) sm.keyw[i] += code * kd.dense_stride;
-            else sm.keyw[size_t(kd.word) * TILE + i] |= code << kd.shift;
-          }
-          // predicate leaves on this column
-          if (q.slot_used_by_leaf[slot]) {
-            uint32_t bits = 0;
-            for (int l = 0; l < q.n_leaves; l++) {
-              if (q.leaves[l].slot != slot || lrt[l].mode != LM_EVAL) continue;
-              uint32_t r = (idx == kNullIdx) ? lrt[l].null_result : __ldg(&lrt[l].lut[idx]);
-              bits |= (r & 1u) << l;
-            }
-            sm.leafbits[i] |= bits;
-          }
-        }
-        __syncthreads();  // tmp / vbyte are reused by the next column
+      for (int j = 0; j < STEPS; j++)
+        if (c0 + j * 32 + lane < n_rows) actbits |= 1u << j;
+    }
+    if (__ballot_sync(FULL, actbits != 0) == 0) continue;  // nothing selected in this chunk
+
+    // ---- group key per row ---------------------------------------------------------------------
+    unsigned long long kw[KW][STEPS];
+#pragma unroll
+    for (int w = 0; w < KW; w++)
+#pragma unroll
+      for (int j = 0; j < STEPS; j++) kw[w][j] = 0;
+    for (int k = 0; k < q.n_keys; k++) {
+      const KeyDesc& kd = q.keys[k];
+      const ChunkDesc& c = chunks[kd.slot];
+      if (kd.is_int64) {
+        long long v[STEPS];
+        uint32_t nm;
+        decode_num_chunk(c, chunk, c0, n_rows, lane, v, nm);
+        // NULL and 0 hash alike in the reference (dynparquet/hashed.go:254-262): NULL slots hold 0
+#pragma unroll
+        for (int w = 0; w < KW; w++)
+          if (w == kd.word)
+#pragma unroll
+            for (int j = 0; j < STEPS; j++) kw[w][j] = (unsigned long long)v[j];
       } else {
-        // numeric column: stage when nullable or dictionary-encoded, else it is read in place
-        const int nb = q.slot_numbuf[slot];
-        const bool staged = (nb >= 0) && c.kind != CK_ABSENT && !(c.kind == CK_PLAIN64 && !c.has_nulls);
-        if (staged) {
-          uint32_t nv = n, v0 = r0;
-          if (c.has_nulls) {
-            nv = decode_validity(c, tile_in_rg, r0, n, sm);
-            v0 = __ldg(&c.tile_val0[tile_in_rg]);
-          }
-          if (c.kind == CK_DICT64)
-            decode_hybrid(c.values, c.runs, __ldg(&c.tile_run[tile_in_rg]), c.n_runs, v0, nv, sm.tmp, sm.ridx, sm.wscr);
-          long long* nbuf = sm.numbuf + size_t(nb) * TILE;
-          uint32_t* nnull = sm.numnull + nb * (TILE / 32);
+        uint32_t idx[STEPS];
+        decode_dict_chunk(c, chunk, c0, n_rows, lane, idx);
+        const uint32_t* lut = c.lut;
 #pragma unroll
-          for (int j = 0; j < RPT; j++) {
-            uint32_t i = j * NT + tid;
-            bool valid = i < n;
-            uint32_t pos = i;
-            if (valid && c.has_nulls) valid = row_valid(sm, i, &pos);
-            long long val = 0;
-            if (valid) {
-              if (c.kind == CK_DICT64) val = __ldg(&c.dict64[sm.tmp[pos]]);
-              else val = __ldg(reinterpret_cast<const long long*>(c.values) + v0 + pos);
-            }
-            nbuf[i] = val;
-            unsigned nullmask = __ballot_sync(0xffffffffu, !valid);
-            if (lane == 0) nnull[i >> 5] = nullmask;
-          }
-          __syncthreads();
-        }
-        // leaves on this numeric column and int64 group keys
-        const bool has_key = [&] {
-          for (int k = 0; k < q.n_keys; k++)
-            if (q.keys[k].slot == slot) return true;
-          return false;
-        }();
-        if (q.slot_used_by_leaf[slot] || has_key) {
+        for (int j = 0; j < STEPS; j++) {
+          unsigned long long code = (idx[j] == kNullIdx) ? 0ull : (unsigned long long)__ldg(lut + idx[j]) + 1ull;
+          if (dense) {
+            kw[0][j] += code * kd.dense_stride;
+          } else {
 #pragma unroll
-          for (int j = 0; j < RPT; j++) {
-            uint32_t i = j * NT + tid;
-            if (i >= n) continue;
-            NumVal v = load_num(q, chunks, sm, slot, r0, i);
-            if (q.slot_used_by_leaf[slot]) {
-              uint32_t bits = 0;
-              for (int l = 0; l < q.n_leaves; l++) {
-                const LeafDesc& ld = q.leaves[l];
-                if (ld.slot != slot || lrt[l].mode != LM_EVAL) continue;
-                bool r = false;
-                if (!v.null) {  // NULL compares to NULL: not selected (binaryscalarexpr.go:143-150)
-                  if (ld.cmp_float) {
-                    double x = (stype == ST_F64) ? __longlong_as_double(v.bits) : double(v.bits);
-                    r = cmp_f64(ld.op, x, ld.lit_f);
-                  } else {
-                    r = cmp_i64(ld.op, v.bits, ld.lit_i);
-                  }
-                }
-                bits |= uint32_t(r) << l;
-              }
-              sm.leafbits[i] |= bits;
-            }
-            if (has_key) {
-              for (int k = 0; k < q.n_keys; k++) {
-                const KeyDesc& kd = q.keys[k];
-                if (kd.slot != slot) continue;
-                // NULL and 0 hash alike in the reference (dynparquet/hashed.go:254-262)
-                sm.keyw[size_t(kd.word) * TILE + i] = v.null ? 0ull : (unsigned long long)v.bits;
-              }
-            }
+            for (int w = 0; w < KW; w++)
+              if (w == kd.word) kw[w][j] |= code << kd.shift;
           }
         }
       }
     }
-    __syncthreads();
-
-    // ---- selection + aggregation (strided mapping, whole warps stay converged for the ballots) ----
-#pragma unroll 1
-    for (int j = 0; j < RPT; j++) {
-      uint32_t i = j * NT + tid;
-      bool active = i < n;
-      if (active && q.n_filter_prog > 0) active = eval_filter(q, sm.leafbits[i]);
-      unsigned amask = __ballot_sync(0xffffffffu, active);
+    // ---- table slot per row ----------------------------------------------------------------------
+    uint32_t slot[STEPS];
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+      slot[j] = kNoSlot;
+      if (!((actbits >> j) & 1u)) continue;
+      if (dense) {
+        slot[j] = uint32_t(kw[0][j]);
+      } else {
+        bool same = last_slot != kNoSlot;
+#pragma unroll
+        for (int w = 0; w < KW; w++) same &= (kw[w][j] == last_kw[w]);
+        if (!same) {
+          unsigned long long key[KW];
+#pragma unroll
+          for (int w = 0; w < KW; w++) key[w] = kw[w][j];
+          last_slot = hash_find_or_insert<KW>(q, key, &overflow);
+#pragma unroll
+          for (int w = 0; w < KW; w++) last_kw[w] = key[w];
+        }
+        slot[j] = last_slot;
+      }
+    }
+    // ---- step classification: 0 = nothing selected, else uniform group (ustep) or mixed ------------
+    uint32_t uslot[STEPS];   // warp-uniform: group of the step, kNoSlot when mixed or empty
+    uint32_t mixedbits = 0;  // warp-uniform: bit j set when the step's active lanes span several groups
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+      bool active = (actbits >> j) & 1u;
+      unsigned amask = __ballot_sync(FULL, active);
+      uslot[j] = kNoSlot;
       if (amask == 0) continue;
       if (lane == 0) selected_local += __popc(amask);
-      if (!active) continue;
-      uint32_t slot_idx;
-      if (q.table_mode == TM_DENSE) {
-        slot_idx = uint32_t(sm.keyw[i]);
-      } else {
-        unsigned long long kw[kMaxKeyWords];
-        for (int w = 0; w < q.key_words; w++) kw[w] = sm.keyw[size_t(w) * TILE + i];
-        slot_idx = hash_find_or_insert(q, kw, &overflow);
-      }
-      unsigned peers = __match_any_sync(amask, slot_idx);
-      int leader = __ffs(peers) - 1;
-      if (lane == leader) atomicAdd(q.t_rows + slot_idx, (unsigned long long)__popc(peers));
-      for (int a = 0; a < q.n_aggs; a++) {
-        const AggDesc& ad = q.aggs[a];
-        if (ad.func == 4 /*count*/) continue;  // = rows of the group (aggregate.go:937-950)
-        long long bits = eval_prog(q, ad, chunks, sm, r0, i);
-        bits = reduce_agg(ad.func, ad.is_float, bits, peers, lane);
-        if (lane == leader) apply_agg(ad.func, ad.is_float, q.t_agg[a] + slot_idx, bits);
+      uint32_t s = __shfl_sync(FULL, slot[j], __ffs(amask) - 1);
+      bool uni = __all_sync(FULL, !active || slot[j] == s);
+      if (uni) uslot[j] = s;
+      else mixedbits |= 1u << j;
+    }
+    // ---- rows-per-group counter (also every Count aggregate, aggregate.go:937-950) ----------------
+    {
+      uint32_t cs = cur_slot;
+#pragma unroll
+      for (int j = 0; j < STEPS; j++) {
+        bool active = (actbits >> j) & 1u;
+        if ((mixedbits >> j) & 1u) {
+          if (cs != kNoSlot) {
+            uint32_t t = __reduce_add_sync(FULL, cur_cnt);
+            if (lane == 0 && t) atomicAdd(q.t_rows + cs, (unsigned long long)t);
+            cur_cnt = 0;
+            cs = kNoSlot;
+          }
+          mixed_rows(q.t_rows, slot[j], active, lane);
+        } else if (uslot[j] != kNoSlot) {
+          if (uslot[j] != cs) {
+            if (cs != kNoSlot) {
+              uint32_t t = __reduce_add_sync(FULL, cur_cnt);
+              if (lane == 0 && t) atomicAdd(q.t_rows + cs, (unsigned long long)t);
+              cur_cnt = 0;
+            }
+            cs = uslot[j];
+          }
+          cur_cnt += active ? 1u : 0u;
+        }
       }
     }
-    __syncthreads();
+    // ---- aggregates: per-lane partials while the warp stays in one group ----------------------------
+    // (acc[] is indexed dynamically on purpose: it is touched once per chunk, the per-row work runs on `part`)
+#pragma unroll 1
+    for (int a = 0; a < q.n_aggs; a++) {
+      const AggDesc& ad = q.aggs[a];
+      if (ad.func == 4 /*count*/) continue;
+      long long v[STEPS];
+      eval_agg_values(q, ad, chunks, chunk, c0, n_rows, lane, v);
+      uint32_t cs = cur_slot;
+      long long part = acc[a];
+      const long long ident = agg_identity(ad.func, ad.is_float);
+#pragma unroll
+      for (int j = 0; j < STEPS; j++) {
+        bool active = (actbits >> j) & 1u;
+        if ((mixedbits >> j) & 1u) {
+          if (cs != kNoSlot) {
+            flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
+            part = ident;
+            cs = kNoSlot;
+          }
+          mixed_agg(ad.func, ad.is_float, q.t_agg[a], slot[j], active, v[j], lane);
+        } else if (uslot[j] != kNoSlot) {
+          if (uslot[j] != cs) {
+            if (cs != kNoSlot) {
+              flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
+              part = ident;
+            }
+            cs = uslot[j];
+          }
+          if (active) part = agg_combine(ad.func, ad.is_float, part, v[j]);
+        }
+      }
+      acc[a] = part;
+    }
+    // the running group after this chunk (identical for every aggregate by construction)
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+      if ((mixedbits >> j) & 1u) cur_slot = kNoSlot;
+      else if (uslot[j] != kNoSlot) cur_slot = uslot[j];
+    }
+  }
+  // ---- final flush ---------------------------------------------------------------------------------
+  if (cur_slot != kNoSlot) {
+    uint32_t t = __reduce_add_sync(FULL, cur_cnt);
+    if (lane == 0 && t) atomicAdd(q.t_rows + cur_slot, (unsigned long long)t);
+#pragma unroll 1
+    for (int a = 0; a < q.n_aggs; a++) {
+      if (q.aggs[a].func == 4) continue;
+      flush_agg(q.aggs[a].func, q.aggs[a].is_float, q.t_agg[a] + cur_slot, acc[a], lane);
+    }
   }
   if (lane == 0 && selected_local) atomicAdd(q.counters + 0, selected_local);
   if (overflow) atomicExch(q.counters + 1, 1ull);
+}
+
+// ======================================================================================================
+// k_rows: predicate + order-preserving compaction of the projected columns
+// ======================================================================================================
+__global__ void __launch_bounds__(NT) k_rows(const QueryDesc* __restrict__ qp) {
+  __shared__ QueryDesc sq;
+  __shared__ uint32_t warp_cnt[NWARP];
+  __shared__ unsigned long long tile_base_s;
+  __shared__ uint32_t tile_ticket;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(qp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
+    for (uint32_t i = threadIdx.x; i < sizeof(QueryDesc) / 4; i += NT) dst[i] = src[i];
+  }
+  __syncthreads();
+  const QueryDesc& q = sq;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  volatile unsigned long long* state = q.tile_state;  // [n_tiles]: bits 62..63 flag (1 aggregate, 2 prefix), low bits value
+
+  for (;;) {
+    // tiles are handed out in order so that every predecessor of a tile is running or finished
+    if (threadIdx.x == 0) tile_ticket = atomicAdd(reinterpret_cast<unsigned int*>(q.counters + 2), 1u);
+    __syncthreads();
+    const uint32_t tile = tile_ticket;
+    if (tile >= q.n_tiles) break;
+    const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
+    const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
+    const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
+    const uint32_t chunk = tile_in_rg * NWARP + warp;
+    const uint32_t c0 = chunk * kIndexRows;
+    const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
+    const LeafRt* __restrict__ lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+
+    uint32_t actbits = 0;
+    if (c0 < n_rows) {
+      if (q.n_filter_prog > 0) {
+        uint32_t leafbits[STEPS];
+        eval_leaves(q, chunks, lrt, chunk, c0, n_rows, lane, leafbits);
+#pragma unroll
+        for (int j = 0; j < STEPS; j++)
+          if (c0 + j * 32 + lane < n_rows && eval_filter(q, leafbits[j])) actbits |= 1u << j;
+      } else {
+#pragma unroll
+        for (int j = 0; j < STEPS; j++)
+          if (c0 + j * 32 + lane < n_rows) actbits |= 1u << j;
+      }
+    }
+    // rank of every selected row inside the warp's chunk, in row order
+    uint32_t rank[STEPS];
+    uint32_t wtotal = 0;
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+      unsigned m = __ballot_sync(FULL, (actbits >> j) & 1u);
+      rank[j] = wtotal + __popc(m & lt);
+      wtotal += __popc(m);
+    }
+    if (lane == 0) warp_cnt[warp] = wtotal;
+    __syncthreads();
+    uint32_t wbase = 0, ttotal = 0;
+    for (int w = 0; w < NWARP; w++) {
+      if (w < warp) wbase += warp_cnt[w];
+      ttotal += warp_cnt[w];
+    }
+    // decoupled look-back over the preceding tiles (one warp, 32 predecessors per probe)
+    if (warp == 0) {
+      if (lane == 0) state[tile] = (1ull << 62) | ttotal;
+      __threadfence();
+      unsigned long long excl = 0;
+      int64_t look = int64_t(tile) - 1;
+      while (look >= 0) {
+        int64_t t = look - lane;
+        unsigned long long s = (t >= 0) ? state[t] : (2ull << 62);
+        while (__any_sync(FULL, (s >> 62) == 0)) s = (t >= 0) ? state[t] : (2ull << 62);  // predecessors publish soon
+        unsigned pmask = __ballot_sync(FULL, (s >> 62) == 2);
+        int first_prefix = pmask ? __ffs(pmask) - 1 : 32;
+        unsigned long long contrib = (lane <= first_prefix) ? (s & ((1ull << 62) - 1)) : 0;
+        contrib = warp_reduce(contrib, [](unsigned long long a, unsigned long long b) { return a + b; });
+        excl += contrib;
+        if (pmask) break;
+        look -= 32;
+      }
+      if (lane == 0) {
+        state[tile] = (2ull << 62) | (excl + ttotal);
+        tile_base_s = excl;
+      }
+    }
+    __syncthreads();
+    const unsigned long long base = tile_base_s + wbase;
+    // ---- write the projected columns of the selected rows ---------------------------------------
+    if (c0 < n_rows && wtotal > 0) {
+      for (int o = 0; o < q.n_out; o++) {
+        const int slot = q.out_slot[o];
+        const ChunkDesc& c = chunks[slot];
+        if (q.slot_type[slot] == ST_DICT) {
+          uint32_t idx[STEPS];
+          decode_dict_chunk(c, chunk, c0, n_rows, lane, idx);
+          int32_t* out = reinterpret_cast<int32_t*>(q.out_data[o]);
+#pragma unroll
+          for (int j = 0; j < STEPS; j++)
+            if ((actbits >> j) & 1u) out[base + rank[j]] = (idx[j] == kNullIdx) ? -1 : int32_t(__ldg(c.lut + idx[j]));
+        } else {
+          long long v[STEPS];
+          uint32_t nm;
+          decode_num_chunk(c, chunk, c0, n_rows, lane, v, nm);
+          long long* out = reinterpret_cast<long long*>(q.out_data[o]);
+          uint8_t* valid = q.out_valid[o];
+#pragma unroll
+          for (int j = 0; j < STEPS; j++)
+            if ((actbits >> j) & 1u) {
+              out[base + rank[j]] = v[j];
+              valid[base + rank[j]] = ((nm >> j) & 1u) ? 0 : 1;
+            }
+        }
+      }
+    }
+    if (threadIdx.x == 0 && tile + 1 == q.n_tiles) q.counters[0] = tile_base_s + ttotal;  // total selected rows
+    __syncthreads();
+  }
 }
 
 // ======================================================================================================
@@ -648,10 +834,7 @@ __global__ void k_table_init(QueryDesc q) {
     if (q.table_mode == TM_HASH) q.t_tag[s] = 0;
     for (int a = 0; a < q.n_aggs; a++) {
       const AggDesc& ad = q.aggs[a];
-      long long init = 0;
-      if (ad.func == 2) init = ad.is_float ? 0x7ff0000000000000ll : 0x7fffffffffffffffll;
-      if (ad.func == 3) init = ad.is_float ? (long long)0xfff0000000000000ull : (long long)0x8000000000000000ull;
-      if (ad.func != 4) q.t_agg[a][s] = init;
+      if (ad.func != 4) q.t_agg[a][s] = agg_identity(ad.func, ad.is_float);
     }
   }
 }
@@ -686,7 +869,7 @@ __global__ void k_finalize(FinalizeDesc f) {
 
 // ======================================================================================================
 // k_merge: fold one remote partial table (same QueryDesc shape) into the local one.
-// Partial layout (position independent): [rows u64 x S][agg_0 i64 x S]...[tags u32 x S][keys u64 x S*W]
+// Partial layout (position independent): [rows u64 x S][stored agg i64 x S]...[tags u32 x S (8-aligned)][keys u64 x S*W]
 // ======================================================================================================
 __global__ void k_merge(QueryDesc q, const uint8_t* __restrict__ partial) {
   const size_t S = q.table_slots;
@@ -695,7 +878,6 @@ __global__ void k_merge(QueryDesc q, const uint8_t* __restrict__ partial) {
   int n_stored = 0;
   int agg_pos[kMaxAggs];
   for (int a = 0; a < q.n_aggs; a++) agg_pos[a] = (q.aggs[a].func == 4) ? -1 : n_stored++;
-  const uint32_t* p_tag = reinterpret_cast<const uint32_t*>(partial + S * 8 * (1 + n_stored));
   const unsigned long long* p_keys =
       reinterpret_cast<const unsigned long long*>(partial + S * 8 * (1 + n_stored) + ((S * 4 + 7) & ~size_t(7)));
   bool overflow = false;
@@ -708,9 +890,8 @@ __global__ void k_merge(QueryDesc q, const uint8_t* __restrict__ partial) {
       dst = uint32_t(s);
     } else {
       unsigned long long kw[kMaxKeyWords];
-      for (int w = 0; w < q.key_words; w++) kw[w] = p_keys[s * q.key_words + w];
-      (void)p_tag;
-      dst = hash_find_or_insert(q, kw, &overflow);
+      for (int w = 0; w < kMaxKeyWords; w++) kw[w] = (w < q.key_words) ? p_keys[s * q.key_words + w] : 0;
+      dst = hash_find_or_insert<kMaxKeyWords>(q, kw, &overflow);
       if (overflow) break;
     }
     atomicAdd(q.t_rows + dst, rows);
@@ -727,103 +908,98 @@ __global__ void k_merge(QueryDesc q, const uint8_t* __restrict__ partial) {
 //   DICT_STR : out_i32[row] = global dictionary id, -1 for NULL
 //   numeric  : out_i64[row] = value (0 for NULL), out_valid[row] = 0/1
 // ======================================================================================================
-__global__ void __launch_bounds__(NT) k_decode(ChunkDesc c, uint32_t n_tiles, int32_t* __restrict__ out_i32,
+__global__ void __launch_bounds__(NT) k_decode(ChunkDesc c, uint32_t n_chunks, int32_t* __restrict__ out_i32,
                                                long long* __restrict__ out_i64, uint8_t* __restrict__ out_valid) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const SmemLayout sm = carve(smem_raw, 0, 0);
-  const int tid = threadIdx.x;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t r0 = tile * TILE;
-    const uint32_t n = min(uint32_t(TILE), c.n_rows - r0);
-    uint32_t nv = n, v0 = r0;
-    if (c.has_nulls) {
-      nv = decode_validity(c, tile, r0, n, sm);
-      v0 = __ldg(&c.tile_val0[tile]);
-    }
-    if (c.kind == CK_DICT_STR || c.kind == CK_DICT64)
-      decode_hybrid(c.values, c.runs, __ldg(&c.tile_run[tile]), c.n_runs, v0, nv, sm.tmp, sm.ridx, sm.wscr);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t chunk = blockIdx.x * NWARP + warp; chunk < n_chunks; chunk += gridDim.x * NWARP) {
+    const uint32_t c0 = chunk * kIndexRows;
+    if (c.kind == CK_DICT_STR) {
+      uint32_t idx[STEPS];
+      decode_dict_chunk(c, chunk, c0, c.n_rows, lane, idx);
 #pragma unroll
-    for (int j = 0; j < RPT; j++) {
-      uint32_t i = j * NT + tid;
-      if (i >= n) continue;
-      bool valid = true;
-      uint32_t pos = i;
-      if (c.has_nulls) valid = row_valid(sm, i, &pos);
-      if (c.kind == CK_DICT_STR) {
-        out_i32[r0 + i] = valid ? int32_t(__ldg(&c.lut[sm.tmp[pos]])) : -1;
-      } else {
-        long long v = 0;
-        if (valid) {
-          if (c.kind == CK_DICT64) v = __ldg(&c.dict64[sm.tmp[pos]]);
-          else v = __ldg(reinterpret_cast<const long long*>(c.values) + v0 + pos);
+      for (int j = 0; j < STEPS; j++) {
+        uint32_t r = c0 + j * 32 + lane;
+        if (r < c.n_rows) out_i32[r] = (idx[j] == kNullIdx) ? -1 : int32_t(__ldg(c.lut + idx[j]));
+      }
+    } else {
+      long long v[STEPS];
+      uint32_t nm;
+      decode_num_chunk(c, chunk, c0, c.n_rows, lane, v, nm);
+#pragma unroll
+      for (int j = 0; j < STEPS; j++) {
+        uint32_t r = c0 + j * 32 + lane;
+        if (r < c.n_rows) {
+          out_i64[r] = v[j];
+          out_valid[r] = ((nm >> j) & 1u) ? 0 : 1;
         }
-        out_i64[r0 + i] = v;
-        out_valid[r0 + i] = valid ? 1 : 0;
       }
     }
-    __syncthreads();
   }
 }
 
 // ======================================================================================================
 // host launchers
 // ======================================================================================================
-size_t scan_smem_bytes(int key_words, int n_numbufs) {
-  return size_t(key_words) * TILE * 8 + size_t(n_numbufs) * TILE * 8 + TILE * 4 + TILE * 4 + TILE * 2 +
-         size_t(n_numbufs) * (TILE / 32) * 4 + 64 * 4 + NT * 2 + NT + 16;
+namespace {
+template <int KW>
+cudaError_t launch_scan_kw(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<KW>, NT, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
+  if (grid > q.n_tiles) grid = q.n_tiles;
+  k_scan<KW><<<grid, NT, 0, st>>>(d_q);
+  return cudaGetLastError();
 }
+int grid_for(size_t n) {
+  int blocks = int((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return blocks < 1 ? 1 : blocks;
+}
+}  // namespace
 
 cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st) {
-  int blocks = int((size_t(q.table_slots) + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  k_table_init<<<blocks, 256, 0, st>>>(q);
+  k_table_init<<<grid_for(q.table_slots), 256, 0, st>>>(q);
   return cudaGetLastError();
 }
 
 cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
   if (q.n_tiles == 0) return cudaSuccess;
-  size_t smem = scan_smem_bytes(q.key_words, int(q.n_numbufs));
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  if (q.table_mode == TM_DENSE || q.key_words <= 1) return launch_scan_kw<1>(d_q, q, sm_count, st);
+  if (q.key_words == 2) return launch_scan_kw<2>(d_q, q, sm_count, st);
+  return launch_scan_kw<kMaxKeyWords>(d_q, q, sm_count, st);
+}
+
+cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
+  if (q.n_tiles == 0) return cudaSuccess;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan, NT, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rows, NT, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
   if (grid > q.n_tiles) grid = q.n_tiles;
-  k_scan<<<grid, NT, smem, st>>>(d_q);
+  k_rows<<<grid, NT, 0, st>>>(d_q);
   return cudaGetLastError();
 }
 
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st) {
-  int blocks = int((size_t(f.table_slots) + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  k_finalize<<<blocks, 256, 0, st>>>(f);
+  k_finalize<<<grid_for(f.table_slots), 256, 0, st>>>(f);
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t st) {
-  int blocks = int((size_t(q.table_slots) + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  k_merge<<<blocks, 256, 0, st>>>(q, static_cast<const uint8_t*>(partial));
+  k_merge<<<grid_for(q.table_slots), 256, 0, st>>>(q, static_cast<const uint8_t*>(partial));
   return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const ChunkDesc& c, int32_t* out_i32, long long* out_i64, uint8_t* out_valid, int sm_count,
                           cudaStream_t st) {
-  uint32_t n_tiles = (c.n_rows + TILE - 1) / TILE;
-  if (n_tiles == 0) return cudaSuccess;
-  size_t smem = scan_smem_bytes(0, 0);
-  uint32_t grid = uint32_t(sm_count) * 4;
-  if (grid > n_tiles) grid = n_tiles;
-  k_decode<<<grid, NT, smem, st>>>(c, n_tiles, out_i32, out_i64, out_valid);
+  uint32_t n_chunks = (c.n_rows + kIndexRows - 1) / kIndexRows;
+  if (n_chunks == 0) return cudaSuccess;
+  uint32_t grid = (n_chunks + NWARP - 1) / NWARP;
+  if (grid > uint32_t(sm_count) * 8) grid = uint32_t(sm_count) * 8;
+  k_decode<<<grid, NT, 0, st>>>(c, n_chunks, out_i32, out_i64, out_valid);
   return cudaGetLastError();
 }
 

@@ -79,7 +79,7 @@ typedef struct fgpu_result fgpu_result; /* the records one Execute produced     
 typedef struct fgpu_config {
   int32_t abi_version; /* FGPU_ABI_VERSION                                                        */
   int32_t device;      /* CUDA device ordinal; one ctx drives exactly one GPU                     */
-  int32_t tile_rows;   /* 0 = default (2048); rows decoded per CTA iteration                      */
+  int32_t tile_rows;   /* 0 = default; rows decoded per CTA iteration (fixed at build time)        */
   int32_t flags;       /* reserved, 0                                                             */
   uint64_t staging_bytes; /* pinned host staging for uploads; 0 = default (256 MiB)              */
 } fgpu_config;
