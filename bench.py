@@ -203,16 +203,17 @@ def main():
     file_bytes = sum(b.nbytes for b in bufs)
 
     eng = GPUEngine(local)
-    t_up = time.perf_counter()
-    for b in bufs:
-        eng.put_parquet(TABLE, b)
-    t_up = time.perf_counter() - t_up
-
-    # cross-rank dictionary ids: union of every rank's dictionaries, rank order (one-time, at upload)
+    # cross-rank dictionary ids: union of every rank's dictionary entries, in rank order, preloaded
+    # before the parts are put (one-time, at upload)
     key_cols = ["labels.l00", "labels.l01"]
     if world > 1:
         for col in key_cols:
-            mine = eng.dict_export(TABLE, col)
+            seen, mine = set(), []
+            for b in bufs:
+                for v in _lib.parquet_dict_values(b, col):
+                    if v not in seen:
+                        seen.add(v)
+                        mine.append(v)
             allv = [None] * world
             dist.all_gather_object(allv, mine)
             seen, union = set(), []
@@ -221,7 +222,11 @@ def main():
                     if v not in seen:
                         seen.add(v)
                         union.append(v)
-            eng.dict_unify(TABLE, col, union)
+            eng.dict_preload(TABLE, col, union)
+    t_up = time.perf_counter()
+    for b in bufs:
+        eng.put_parquet(TABLE, b)
+    t_up = time.perf_counter() - t_up
 
     filt, aggs, groups = headline_query_exprs(first_row, rows_per_gpu)
     scan = GPUScan(eng, TABLE, filt, _lib.PLAN_AGGREGATE, groups, aggs)

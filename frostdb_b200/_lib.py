@@ -119,7 +119,8 @@ _SIGNATURES = {
     "fgpu_result_free": ([C.c_void_p], C.c_int32),
     "fgpu_query_free": ([C.c_void_p], C.c_int32),
     "fgpu_dict_export": ([C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)], C.c_int32),
-    "fgpu_dict_unify": ([C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32], C.c_int32),
+    "fgpu_dict_preload": ([C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32], C.c_int32),
+    "fgpu_parquet_dict_values": ([C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)], C.c_int32),
     "fgpu_query_execute_partial": ([C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)], C.c_int32),
     "fgpu_result_merge_partials": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32], C.c_int32),
     "fgpu_part_decode_column": ([C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_void_p], C.c_int32),
@@ -164,3 +165,27 @@ def describe_parquet(buf: bytes, tile_rows: int = 0) -> dict:
     out = C.create_string_buffer(n.value)
     check(lib.fgpu_parquet_describe(C.addressof(src), len(buf), tile_rows, C.addressof(out), n.value, C.byref(n)))
     return json.loads(out.raw[: n.value].decode("utf-8"))
+
+
+def _parse_blob(raw: bytes, count: int):
+    out, p = [], 0
+    for _ in range(count):
+        l = int.from_bytes(raw[p:p + 4], "little")
+        out.append(raw[p + 4:p + 4 + l])
+        p += 4 + l
+    return out
+
+
+def parquet_dict_values(buf, column: str):
+    """Host-only: distinct dictionary entries of `column` in a Parquet file (bytes or numpy uint8 array)."""
+    lib = load()
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        src = (C.c_char * len(buf)).from_buffer_copy(buf)
+        addr, n = C.addressof(src), len(buf)
+    else:
+        addr, n = buf.ctypes.data, buf.nbytes
+    ln, cnt = C.c_uint64(0), C.c_uint32(0)
+    check(lib.fgpu_parquet_dict_values(addr, n, column.encode(), None, 0, C.byref(ln), C.byref(cnt)))
+    out = C.create_string_buffer(max(ln.value, 1))
+    check(lib.fgpu_parquet_dict_values(addr, n, column.encode(), C.addressof(out), ln.value, C.byref(ln), C.byref(cnt)))
+    return _parse_blob(out.raw, cnt.value)

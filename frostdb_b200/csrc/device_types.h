@@ -13,6 +13,8 @@ constexpr int kMaxProg = 48;     // arithmetic ops over all aggregate expression
 constexpr int kMaxFilterProg = 96;
 constexpr int kMaxKeyWords = 6;  // packed key = up to 6 x 64 bit
 constexpr int kMaxOut = 40;      // projected columns of a rows (filter-only) plan
+constexpr int kMaxStagePlain = 4;   // PLAIN columns staged through the shared-memory ring per tile
+constexpr int kMaxStageSeeds = 12;  // hybrid streams whose chunk seeds are staged per tile
 
 constexpr uint32_t kNullIdx = 0xffffffffu;
 
@@ -31,6 +33,21 @@ enum ChunkKind : uint8_t {
   CK_DICT64 = 3     // RLE_DICTIONARY int64/double: hybrid indices -> dict64 (8-byte values)
 };
 
+// Cursor seed of one hybrid stream for one 128-row chunk: the run that holds the chunk's first value,
+// copied out of the run directory so that a warp starts decoding with a single 32-byte read (the
+// producer warp stages the 8 seeds of a tile into shared memory with one bulk copy).
+struct Seed {
+  uint32_t k;      // index of that run in the directory
+  uint32_t start;  // = runs[k].start
+  uint32_t end;    // = runs[k + 1].start
+  uint32_t off;    // = runs[k].off
+  uint32_t val;    // = runs[k].val
+  uint32_t meta;   // = runs[k].meta
+  uint32_t val0;   // value stream: ordinal of the chunk's first value; def stream: non-null values before the chunk
+  uint32_t _pad;
+};
+static_assert(sizeof(Seed) == 32, "seed is one 32-byte sector");
+
 // One column chunk (row group x column) resident in HBM.  All pointers are device pointers into the
 // part's single allocation; every section is 128-byte aligned and padded by 16 readable bytes.
 struct ChunkDesc {
@@ -42,15 +59,15 @@ struct ChunkDesc {
   uint32_t n_runs;    // value runs (excluding the sentinel)
   uint32_t n_defruns;
   uint32_t dict_size;
-  const uint8_t* values;         // PLAIN64: aligned values; DICT*: concatenated hybrid index streams
-  const Run* runs;               // DICT*: run directory (+1 sentinel with start == n_values)
-  const uint32_t* tile_run;      // DICT*: per 256-row chunk, index of the run holding the chunk's first value
-  const uint8_t* def;            // concatenated definition-level hybrid streams (has_nulls)
-  const Run* def_runs;           // (+1 sentinel with start == n_rows)
-  const uint32_t* tile_defrun;   // per 256-row chunk, index of the def run holding the chunk's first row
-  const uint32_t* tile_val0;     // per 256-row chunk, number of non-null values before the chunk (has_nulls)
-  const uint32_t* lut;           // CK_DICT_STR: chunk dictionary index -> global dictionary id
-  const int64_t* dict64;         // CK_DICT64: chunk dictionary values (raw 8 bytes each)
+  const uint8_t* values;   // PLAIN64: aligned values; DICT*: concatenated hybrid index streams
+  const Run* runs;         // DICT*: run directory (+1 sentinel with start == n_values); CK_DICT_STR: the
+                           // value of an RLE run is already the GLOBAL dictionary id
+  const Seed* seeds;       // DICT*: one per 128-row chunk
+  const uint8_t* def;      // concatenated definition-level hybrid streams (has_nulls)
+  const Run* def_runs;     // (+1 sentinel with start == n_rows)
+  const Seed* def_seeds;   // has_nulls: one per 128-row chunk (val0 = non-null values before the chunk)
+  const uint32_t* lut;     // CK_DICT_STR: chunk dictionary index -> global dictionary id (bit-packed runs)
+  const int64_t* dict64;   // CK_DICT64: chunk dictionary values (raw 8 bytes each)
 };
 
 enum SlotType : uint8_t { ST_I64 = 0, ST_F64 = 1, ST_DICT = 2 };
@@ -73,7 +90,7 @@ struct LeafRt {
   uint8_t mode;         // LeafMode; ALL/NONE encode the missing-column rules (binaryscalarexpr.go:47-73)
   uint8_t null_result;  // dictionary leaves: result for NULL rows (== NULL selects nulls, :205-212)
   uint8_t _pad[6];
-  const uint8_t* lut;   // dictionary leaves: result per chunk-local dictionary index
+  const uint8_t* lut;   // dictionary leaves: result per GLOBAL dictionary id
 };
 
 struct KeyDesc {
@@ -118,6 +135,12 @@ struct QueryDesc {
   int32_t filter_kind;   // FilterKind
   uint32_t filter_mask;  // FK_AND / FK_OR: the participating leaf bits
   int32_t n_out;         // rows plan: projected columns
+  int32_t n_stage_plain, n_stage_seeds, n_stages;  // shared-memory ring shape (scan kernel)
+  uint8_t stage_plain_slot[kMaxStagePlain];   // staged PLAIN buffer p holds this slot
+  uint8_t stage_seed_slot[kMaxStageSeeds];    // staged seed block t belongs to this slot ...
+  uint8_t stage_seed_is_def[kMaxStageSeeds];  // ... and is its definition-level stream (1) or value stream (0)
+  int8_t slot_plain_stage[kMaxSlots];         // slot -> staged PLAIN buffer, -1 = read from HBM
+  int8_t slot_seed_stage[kMaxSlots][2];       // slot -> staged seed block of [0] values, [1] def levels, -1 = read from HBM
   uint8_t slot_type[kMaxSlots];
   uint8_t out_slot[kMaxOut];
   uint8_t slot_used_by_leaf[kMaxSlots];

@@ -157,7 +157,7 @@ struct KeyOut {
   bool is_int64 = false;
   bool is_float = false;
   const GlobalDict* dict = nullptr;
-  std::vector<std::string> dict_snapshot;  // values by (unified) id at execute time
+  std::vector<std::string> dict_snapshot;  // values by id at execute time
 };
 
 struct fgpu_result {
@@ -199,7 +199,7 @@ struct LeafHost {
   int op = 0;
   const ExprNode* lit = nullptr;
   const ExprNode* bin = nullptr;
-  std::vector<int8_t> by_gid;  // dictionary leaves: cached result per local global id (-1 = not evaluated)
+  size_t lut_off = size_t(-1);  // dictionary leaves: offset of the per-global-id result bytes in the LUT blob
 };
 
 bool bytes_contains(const std::string& hay, const std::string& needle) {
@@ -357,6 +357,13 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       c->total_rows += rg.n_rows;
     }
   }
+  if (c->rgs.empty()) {  // nothing to scan: no records, exactly like an Iterator over an empty LSM
+    c->qd.table_mode = TM_DENSE;
+    c->qd.key_words = 1;
+    c->qd.table_slots = 1;
+    c->qd.tile_rows = ctx->tile_rows;
+    return FGPU_OK;
+  }
   // every column name present in a visible row group, in name order, with its type
   std::map<std::string, uint8_t> present;
   for (const VisibleRG& v : c->rgs) {
@@ -417,6 +424,46 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   qd.n_slots = int32_t(c->slot_names.size());
   for (int s = 0; s < qd.n_slots; s++) {
     qd.slot_type[s] = c->slot_types[size_t(s)];
+  }
+  // shared-memory ring of the scan kernel: stage every numeric slot's PLAIN slice (up to kMaxStagePlain)
+  // and the chunk seeds of every hybrid stream (up to kMaxStageSeeds); the rest is read from HBM directly
+  for (int s = 0; s < kMaxSlots; s++) {
+    qd.slot_plain_stage[s] = -1;
+    qd.slot_seed_stage[s][0] = qd.slot_seed_stage[s][1] = -1;
+  }
+  for (int s = 0; s < qd.n_slots; s++) {
+    bool any_plain = false, any_vals = false, any_def = false;
+    for (const VisibleRG& v : c->rgs) {
+      auto it = v.rg->cols.find(c->slot_names[size_t(s)]);
+      if (it == v.rg->cols.end()) continue;
+      const ChunkDesc& d = it->second.desc;
+      if (d.kind == CK_PLAIN64 && !d.has_nulls) any_plain = true;
+      if (d.kind == CK_DICT_STR || d.kind == CK_DICT64) any_vals = true;
+      if (d.has_nulls) any_def = true;
+    }
+    if (any_plain && qd.n_stage_plain < kMaxStagePlain) {
+      qd.slot_plain_stage[s] = int8_t(qd.n_stage_plain);
+      qd.stage_plain_slot[qd.n_stage_plain++] = uint8_t(s);
+    }
+    if (any_vals && qd.n_stage_seeds < kMaxStageSeeds) {
+      qd.slot_seed_stage[s][0] = int8_t(qd.n_stage_seeds);
+      qd.stage_seed_slot[qd.n_stage_seeds] = uint8_t(s);
+      qd.stage_seed_is_def[qd.n_stage_seeds++] = 0;
+    }
+    if (any_def && qd.n_stage_seeds < kMaxStageSeeds) {
+      qd.slot_seed_stage[s][1] = int8_t(qd.n_stage_seeds);
+      qd.stage_seed_slot[qd.n_stage_seeds] = uint8_t(s);
+      qd.stage_seed_is_def[qd.n_stage_seeds++] = 1;
+    }
+  }
+  {
+    size_t per_stage = size_t(qd.n_stage_plain) * kTileRows * 8 + size_t(qd.n_stage_seeds) * (kTileRows / kIndexRows) * sizeof(Seed);
+    int stages = 0;
+    if (per_stage > 0) {
+      stages = int(std::min<size_t>(4, (96 * 1024) / per_stage));
+      if (stages < 2) stages = 2;
+    }
+    qd.n_stages = stages;
   }
   // filter
   if (q.filter >= 0) {
@@ -677,17 +724,14 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       } else if (c.slot_types[size_t(lh.slot)] == ST_DICT) {
         rt.mode = LM_EVAL;
         rt.null_result = (lh.op == FGPU_OP_EQ && lh.lit->lit_type == FGPU_SCALAR_NULL) ? 1 : 0;
-        const GlobalDict& gd = ctx->tables.at(q.table).dicts.at(lh.column);
-        if (lh.by_gid.size() < gd.values.size()) lh.by_gid.resize(gd.values.size(), -1);
-        const ChunkHost& ch = it->second;
-        size_t off = lutbytes.size();
-        lutbytes.resize(off + ch.lut_host.size() + 1);
-        for (size_t i = 0; i < ch.lut_host.size(); i++) {
-          uint32_t gid = ch.lut_host[i];
-          if (lh.by_gid[gid] < 0) lh.by_gid[gid] = dict_leaf_value(lh, gd.values[gid]) ? 1 : 0;
-          lutbytes[off + i] = uint8_t(lh.by_gid[gid]);
+        if (lh.lut_off == size_t(-1)) {
+          // one result byte per GLOBAL dictionary id, evaluated once per distinct dictionary entry
+          const GlobalDict& gd = ctx->tables.at(q.table).dicts.at(lh.column);
+          lh.lut_off = lutbytes.size();
+          lutbytes.resize(lh.lut_off + gd.values.size() + 1);
+          for (size_t g = 0; g < gd.values.size(); g++) lutbytes[lh.lut_off + g] = dict_leaf_value(lh, gd.values[g]) ? 1 : 0;
         }
-        lut_fix.emplace_back(size_t(g) * n_leaves + l, off);
+        lut_fix.emplace_back(size_t(g) * n_leaves + l, lh.lut_off);
       } else {
         rt.mode = (lh.lit->lit_type == FGPU_SCALAR_NULL) ? LM_NONE : LM_EVAL;
       }
@@ -1078,12 +1122,6 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   part->dev_bytes = part->image.size();
   patch_part_pointers(part.get(), static_cast<const uint8_t*>(dev));
   std::vector<uint8_t>().swap(part->image);
-  // new dictionary entries invalidate a previously installed cross-rank id space
-  for (auto& d : t.dicts)
-    if (!d.second.unified.empty() && d.second.unified.size() != d.second.values.size()) {
-      d.second.unified.clear();
-      d.second.unified_values.clear();
-    }
   t.parts.push_back(std::move(part));
   return FGPU_OK;
 }
@@ -1218,7 +1256,7 @@ int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* ga
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (n > 0) {
     if (!gathered) return fail(FGPU_ERR_INVALID, "null gathered buffer");
-    if (nbytes != r->table_bytes) return fail(FGPU_ERR_INVALID, "partial table size differs between ranks (dictionaries not unified?)");
+    if (nbytes != r->table_bytes) return fail(FGPU_ERR_INVALID, "partial table size differs between ranks (dictionaries not preloaded identically?)");
     // Start from an empty table and fold every rank's partial in, this rank's own included.
     DevBuf merged;
     CUDA_TRY(merged.alloc(r->table_bytes));
@@ -1295,46 +1333,63 @@ int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, u
   return FGPU_OK;
 }
 
-int32_t fgpu_dict_unify(fgpu_ctx* ctx, const char* table, const char* column, const uint8_t* unified, uint64_t len,
-                        uint32_t count) {
-  if (!ctx || !table || !column || (!unified && len)) return fail(FGPU_ERR_INVALID, "null argument");
+int32_t fgpu_dict_preload(fgpu_ctx* ctx, const char* table, const char* column, const uint8_t* blob, uint64_t len, uint32_t count) {
+  if (!ctx || !table || !column || (!blob && len)) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  Table& t = ctx->tables[table];
-  GlobalDict& d = t.dicts[column];
-  std::vector<std::string> uv;
-  std::unordered_map<std::string, uint32_t> uidx;
-  const uint8_t* p = unified;
-  const uint8_t* end = unified + len;
+  GlobalDict& d = ctx->tables[table].dicts[column];
+  const uint8_t* p = blob;
+  const uint8_t* end = blob + len;
   for (uint32_t i = 0; i < count; i++) {
-    if (end - p < 4) return fail(FGPU_ERR_INVALID, "unified dictionary blob truncated");
+    if (end - p < 4) return fail(FGPU_ERR_INVALID, "dictionary blob truncated");
     uint32_t l;
     std::memcpy(&l, p, 4);
     p += 4;
-    if (l > uint64_t(end - p)) return fail(FGPU_ERR_INVALID, "unified dictionary blob truncated");
-    std::string s(reinterpret_cast<const char*>(p), l);
+    if (l > uint64_t(end - p)) return fail(FGPU_ERR_INVALID, "dictionary blob truncated");
+    d.intern(reinterpret_cast<const char*>(p), l);
     p += l;
-    uidx.emplace(s, uint32_t(uv.size()));
-    uv.push_back(std::move(s));
   }
-  std::vector<uint32_t> map(d.values.size());
-  for (size_t i = 0; i < d.values.size(); i++) {
-    auto it = uidx.find(d.values[i]);
-    if (it == uidx.end()) return fail(FGPU_ERR_INVALID, "unified dictionary misses a local entry of column " + std::string(column));
-    map[i] = it->second;
-  }
-  // rewrite the per-chunk device LUTs of this column to unified ids
-  for (auto& part : t.parts) {
-    for (auto& rg : part->rgs) {
-      auto it = rg.cols.find(column);
-      if (it == rg.cols.end() || it->second.desc.kind != CK_DICT_STR || it->second.lut_host.empty()) continue;
-      std::vector<uint32_t> l2(it->second.lut_host.size());
-      for (size_t i = 0; i < l2.size(); i++) l2[i] = map[it->second.lut_host[i]];
-      CUDA_TRY(cudaMemcpy(const_cast<uint32_t*>(it->second.desc.lut), l2.data(), l2.size() * 4, cudaMemcpyHostToDevice));
+  return FGPU_OK;
+}
+
+int32_t fgpu_parquet_dict_values(const uint8_t* file, uint64_t len, const char* column, uint8_t* buf, uint64_t cap, uint64_t* out_len,
+                                 uint32_t* out_count) {
+  if (!file || !column || !out_len || !out_count) return fail(FGPU_ERR_INVALID, "null argument");
+  ParsedFile pf;
+  std::string err;
+  if (!parse_parquet(file, len, &pf, &err)) return fail(FGPU_ERR_PARQUET, err);
+  GlobalDict d;  // first-seen order over the file's row groups
+  for (size_t c = 0; c < pf.leaves.size(); c++) {
+    if (pf.leaves[c].name != column) continue;
+    for (const RowGroupMeta& rg : pf.row_groups) {
+      const ChunkMeta& cm = rg.chunks[c];
+      if (!cm.error.empty()) return fail(FGPU_ERR_PARQUET, std::string(column) + ": " + cm.error);
+      const uint8_t* p = cm.dict;
+      const uint8_t* end = cm.dict + cm.dict_len;
+      for (uint32_t i = 0; i < cm.dict_num_values; i++) {
+        if (end - p < 4) return fail(FGPU_ERR_PARQUET, "dictionary page truncated");
+        uint32_t l;
+        std::memcpy(&l, p, 4);
+        p += 4;
+        if (l > uint64_t(end - p)) return fail(FGPU_ERR_PARQUET, "dictionary entry overruns page");
+        d.intern(reinterpret_cast<const char*>(p), l);
+        p += l;
+      }
     }
   }
-  d.unified = std::move(map);
-  d.unified_values = std::move(uv);
+  uint64_t need = 0;
+  for (auto& v : d.values) need += 4 + v.size();
+  *out_len = need;
+  *out_count = uint32_t(d.values.size());
+  if (!buf) return FGPU_OK;
+  if (cap < need) return fail(FGPU_ERR_INVALID, "buffer too small");
+  uint8_t* o = buf;
+  for (auto& v : d.values) {
+    uint32_t l = uint32_t(v.size());
+    std::memcpy(o, &l, 4);
+    o += 4;
+    std::memcpy(o, v.data(), v.size());
+    o += v.size();
+  }
   return FGPU_OK;
 }
 

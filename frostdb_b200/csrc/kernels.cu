@@ -1,9 +1,9 @@
 // sm_100a kernels of libfrostgpu.
 //
-//   k_scan<KW>   K1+K2+K4/K5 fused.  Every warp streams one 256-row chunk of a row group at a time:
+//   k_scan<KW>   K1+K2+K4/K5 fused.  Every consumer warp streams one 128-row chunk of a row group at a time:
 //                it walks the stored Parquet encodings of the projected column chunks directly in HBM
 //                (PLAIN int64/double, RLE/bit-packed hybrid definition levels and dictionary indices)
-//                with per-lane run cursors seeded from a 256-row chunk index, evaluates the predicate
+//                with per-lane run cursors seeded from a per-chunk seed, evaluates the predicate
 //                leaves into per-row bits, and folds the selected rows into the aggregate table.
 //                Rows whose group does not change inside a warp (the common case for parts sorted in
 //                compaction order) are accumulated in registers and flushed with ONE warp-reduced
@@ -19,9 +19,11 @@
 //                HashAggregate, synchronize.go:16-53, physicalplan.go:438-471).
 //   k_decode     K1 standalone: one column chunk -> dense buffers.
 //
-// HBM-bound integer / indexing work: no tensor cores.  No shared-memory staging is needed because a
-// warp's 32 lanes always touch 32 consecutive rows (256 B of a PLAIN column per load instruction, the
-// same few bytes of a hybrid stream).
+// HBM-bound integer / indexing work: no tensor cores.  In k_scan a dedicated producer warp keeps a
+// shared-memory ring of tiles full with cp.async.bulk (TMA bulk copies completing on mbarriers): the
+// PLAIN column slices of the tile and the 8 cursor seeds of every hybrid stream.  The 8 consumer warps
+// therefore never wait on an HBM round trip in the common case; what they still read from global
+// memory (run directory entries past the seed, bit-packed payload, LUTs) is small and L2 resident.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -43,10 +45,42 @@ static_assert(STEPS == 4, "unrolled for 4 steps");
 constexpr uint32_t kNoSlot = 0xffffffffu;
 constexpr uint32_t FULL = 0xffffffffu;
 
+// ---- mbarrier / bulk-copy primitives (sm_90+ PTX) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- hybrid stream cursor ------------------------------------------------------------------------------
 struct HybCur {
   const Run* runs;
   const uint8_t* stream;
+  const uint32_t* lut;  // string dictionaries: bit-packed index -> global id (RLE values are global ids already)
   uint32_t k, start, end, val, meta, off;
 };
 
@@ -58,11 +92,20 @@ __device__ __forceinline__ void hc_load(HybCur& c) {
   c.meta = r.w;
   c.end = __ldg(&c.runs[c.k + 1].start);
 }
-__device__ __forceinline__ void hc_init(HybCur& c, const Run* runs, const uint8_t* stream, uint32_t k0) {
+// `seed` may live in shared memory (staged by the producer) or in global memory.
+__device__ __forceinline__ uint32_t hc_init(HybCur& c, const Run* runs, const uint8_t* stream, const uint32_t* lut, const Seed* seed) {
+  const uint4 a = *reinterpret_cast<const uint4*>(seed);
+  const uint4 b = *(reinterpret_cast<const uint4*>(seed) + 1);
   c.runs = runs;
   c.stream = stream;
-  c.k = k0;
-  hc_load(c);
+  c.lut = lut;
+  c.k = a.x;
+  c.start = a.y;
+  c.end = a.z;
+  c.off = a.w;
+  c.val = b.x;
+  c.meta = b.y;
+  return b.z;  // val0
 }
 __device__ __forceinline__ uint32_t extract_bits(const uint8_t* stream, uint32_t off, uint64_t bit, uint32_t w) {
   uint64_t byte = uint64_t(off) + (bit >> 3);
@@ -81,27 +124,37 @@ __device__ __forceinline__ uint32_t hc_get(HybCur& c, uint32_t ord) {
   }
   if ((c.meta & 1u) == 0) return c.val;
   uint32_t w = (c.meta >> 8) & 0xffu;
-  return extract_bits(c.stream, c.off, uint64_t(ord - c.start) * w, w);
+  uint32_t v = extract_bits(c.stream, c.off, uint64_t(ord - c.start) * w, w);
+  return c.lut ? __ldg(c.lut + v) : v;
 }
 
-// Decodes the chunk's 8 x 32 rows of a dictionary-encoded column: idx[j] = chunk-local dictionary
-// index of row (c0 + 32 j + lane), kNullIdx for NULL / out of range / absent column.
-__device__ __forceinline__ void decode_dict_chunk(const ChunkDesc& c, uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane,
-                                                  uint32_t (&idx)[STEPS]) {
+// Seeds of the chunk's streams: staged copies in shared memory when the producer provided them.
+struct ChunkSeeds {
+  const Seed* val;  // value stream seed of this chunk (shared or global), nullptr when the column has none
+  const Seed* def;  // definition-level stream seed
+};
+__device__ __forceinline__ ChunkSeeds global_seeds(const ChunkDesc& c, uint32_t chunk) {
+  ChunkSeeds s;
+  s.val = (c.kind == CK_DICT_STR || c.kind == CK_DICT64) ? c.seeds + chunk : nullptr;
+  s.def = c.has_nulls ? c.def_seeds + chunk : nullptr;
+  return s;
+}
+
+// Decodes the chunk's STEPS x 32 rows of a dictionary-encoded string column: gid[j] = GLOBAL dictionary
+// id of row (c0 + 32 j + lane), kNullIdx for NULL / out of range / absent column.
+__device__ __forceinline__ void decode_dict_chunk(const ChunkDesc& c, const ChunkSeeds& sd, uint32_t c0, uint32_t n_rows, int lane,
+                                                  uint32_t (&gid)[STEPS]) {
   if (c.kind == CK_ABSENT) {
 #pragma unroll
-    for (int j = 0; j < STEPS; j++) idx[j] = kNullIdx;
+    for (int j = 0; j < STEPS; j++) gid[j] = kNullIdx;
     return;
   }
   const uint32_t lt = (1u << lane) - 1u;
   HybCur vc, dc;
   uint32_t vbase = c0;
   const bool nulls = c.has_nulls;
-  if (nulls) {
-    hc_init(dc, c.def_runs, c.def, __ldg(&c.tile_defrun[chunk]));
-    vbase = __ldg(&c.tile_val0[chunk]);
-  }
-  hc_init(vc, c.runs, c.values, __ldg(&c.tile_run[chunk]));
+  if (nulls) vbase = hc_init(dc, c.def_runs, c.def, nullptr, sd.def);
+  hc_init(vc, c.runs, c.values, c.lut, sd.val);
 #pragma unroll
   for (int j = 0; j < STEPS; j++) {
     uint32_t r = c0 + j * 32 + lane;
@@ -113,15 +166,16 @@ __device__ __forceinline__ void decode_dict_chunk(const ChunkDesc& c, uint32_t c
       ord = vbase + __popc(m & lt);
       vbase += __popc(m);
     }
-    idx[j] = valid ? hc_get(vc, ord) : kNullIdx;
+    gid[j] = valid ? hc_get(vc, ord) : kNullIdx;
   }
 }
 
 // Decodes the chunk's rows of a numeric column: bits[j] raw 8 bytes (0 for NULL, as
 // builder.AppendValue leaves NULL slots: pqarrow/builder/utils.go:54-58, optbuilders.go:337-340),
-// nullmask bit j set when the row is NULL / absent / out of range.
-__device__ __forceinline__ void decode_num_chunk(const ChunkDesc& c, uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane,
-                                                 long long (&bits)[STEPS], uint32_t& nullmask) {
+// nullmask bit j set when the row is NULL / absent / out of range.  `staged` is the tile's slice of a
+// PLAIN column in shared memory (indexed by row - tile_r0) or nullptr.
+__device__ __forceinline__ void decode_num_chunk(const ChunkDesc& c, const ChunkSeeds& sd, const long long* staged, uint32_t tile_r0,
+                                                 uint32_t c0, uint32_t n_rows, int lane, long long (&bits)[STEPS], uint32_t& nullmask) {
   nullmask = 0;
   if (c.kind == CK_ABSENT) {
 #pragma unroll
@@ -135,7 +189,9 @@ __device__ __forceinline__ void decode_num_chunk(const ChunkDesc& c, uint32_t ch
     for (int j = 0; j < STEPS; j++) {
       uint32_t r = c0 + j * 32 + lane;
       bool inb = r < n_rows;
-      bits[j] = inb ? __ldg(vals + r) : 0;
+      long long v = 0;
+      if (inb) v = staged ? staged[r - tile_r0] : __ldg(vals + r);
+      bits[j] = v;
       if (!inb) nullmask |= 1u << j;
     }
     return;
@@ -144,12 +200,9 @@ __device__ __forceinline__ void decode_num_chunk(const ChunkDesc& c, uint32_t ch
   HybCur vc, dc;
   uint32_t vbase = c0;
   const bool nulls = c.has_nulls;
-  if (nulls) {
-    hc_init(dc, c.def_runs, c.def, __ldg(&c.tile_defrun[chunk]));
-    vbase = __ldg(&c.tile_val0[chunk]);
-  }
+  if (nulls) vbase = hc_init(dc, c.def_runs, c.def, nullptr, sd.def);
   const bool dict = c.kind == CK_DICT64;
-  if (dict) hc_init(vc, c.runs, c.values, __ldg(&c.tile_run[chunk]));
+  if (dict) hc_init(vc, c.runs, c.values, nullptr, sd.val);
 #pragma unroll
   for (int j = 0; j < STEPS; j++) {
     uint32_t r = c0 + j * 32 + lane;
@@ -166,6 +219,46 @@ __device__ __forceinline__ void decode_num_chunk(const ChunkDesc& c, uint32_t ch
     bits[j] = v;
     if (!valid) nullmask |= 1u << j;
   }
+}
+
+// What the consumer knows about the tile it is working on.
+struct TileCtx {
+  const QueryDesc* q;
+  const ChunkDesc* chunks;  // [n_slots] of the row group
+  const LeafRt* lrt;        // [n_leaves] of the row group
+  const uint8_t* stage;     // shared-memory stage of this tile (nullptr: nothing staged, read HBM)
+  uint32_t tile_r0;         // first row of the tile inside the row group
+  uint32_t chunk;           // this warp's chunk index inside the row group
+  uint32_t chunk_in_tile;
+  uint32_t c0;              // first row of the chunk
+  uint32_t n_rows;          // rows of the row group
+};
+__device__ __forceinline__ size_t stage_plain_bytes() { return size_t(TILE) * 8; }
+__device__ __forceinline__ size_t stage_seed_bytes() { return size_t(NWARP) * sizeof(Seed); }
+__device__ __forceinline__ const long long* staged_plain(const TileCtx& t, int slot) {
+  if (!t.stage) return nullptr;
+  int p = t.q->slot_plain_stage[slot];
+  if (p < 0) return nullptr;
+  const ChunkDesc& c = t.chunks[slot];
+  if (c.kind != CK_PLAIN64 || c.has_nulls) return nullptr;
+  return reinterpret_cast<const long long*>(t.stage + size_t(p) * stage_plain_bytes());
+}
+__device__ __forceinline__ ChunkSeeds seeds_for(const TileCtx& t, int slot) {
+  const ChunkDesc& c = t.chunks[slot];
+  ChunkSeeds s = global_seeds(c, t.chunk);
+  if (t.stage) {
+    const uint8_t* base = t.stage + size_t(t.q->n_stage_plain) * stage_plain_bytes();
+    int sv = t.q->slot_seed_stage[slot][0], sdf = t.q->slot_seed_stage[slot][1];
+    if (s.val && sv >= 0) s.val = reinterpret_cast<const Seed*>(base + size_t(sv) * stage_seed_bytes()) + t.chunk_in_tile;
+    if (s.def && sdf >= 0) s.def = reinterpret_cast<const Seed*>(base + size_t(sdf) * stage_seed_bytes()) + t.chunk_in_tile;
+  }
+  return s;
+}
+__device__ __forceinline__ void tile_dict(const TileCtx& t, int slot, int lane, uint32_t (&gid)[STEPS]) {
+  decode_dict_chunk(t.chunks[slot], seeds_for(t, slot), t.c0, t.n_rows, lane, gid);
+}
+__device__ __forceinline__ void tile_num(const TileCtx& t, int slot, int lane, long long (&bits)[STEPS], uint32_t& nullmask) {
+  decode_num_chunk(t.chunks[slot], seeds_for(t, slot), staged_plain(t, slot), t.tile_r0, t.c0, t.n_rows, lane, bits, nullmask);
 }
 
 // ---- predicate --------------------------------------------------------------------------------------------
@@ -214,8 +307,9 @@ __device__ __forceinline__ bool eval_filter(const QueryDesc& q, uint32_t bits) {
 // Evaluates every predicate leaf of the chunk: leafbits[j] bit l = leaf l selects row j.
 // NULL semantics: binaryscalarexpr.go:143-150 (numeric NULL never selected), :165-172,:205-212
 // (dictionary == NULL / != NULL), missing columns :47-73 (LM_ALL / LM_NONE precomputed on the host).
-__device__ __forceinline__ void eval_leaves(const QueryDesc& q, const ChunkDesc* __restrict__ chunks, const LeafRt* __restrict__ lrt,
-                                            uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane, uint32_t (&leafbits)[STEPS]) {
+__device__ __forceinline__ void eval_leaves(const TileCtx& t, int lane, uint32_t (&leafbits)[STEPS]) {
+  const QueryDesc& q = *t.q;
+  const LeafRt* __restrict__ lrt = t.lrt;
   uint32_t cbits = 0;
   for (int l = 0; l < q.n_leaves; l++)
     if (lrt[l].mode == LM_ALL) cbits |= 1u << l;
@@ -223,24 +317,23 @@ __device__ __forceinline__ void eval_leaves(const QueryDesc& q, const ChunkDesc*
   for (int j = 0; j < STEPS; j++) leafbits[j] = cbits;
   for (int slot = 0; slot < q.n_slots; slot++) {
     if (!q.slot_used_by_leaf[slot]) continue;
-    const ChunkDesc& c = chunks[slot];
     if (q.slot_type[slot] == ST_DICT) {
-      uint32_t idx[STEPS];
-      decode_dict_chunk(c, chunk, c0, n_rows, lane, idx);
+      uint32_t gid[STEPS];
+      tile_dict(t, slot, lane, gid);
       for (int l = 0; l < q.n_leaves; l++) {
         if (q.leaves[l].slot != slot || lrt[l].mode != LM_EVAL) continue;
         const uint8_t* lut = lrt[l].lut;
         const uint32_t nullres = lrt[l].null_result;
 #pragma unroll
         for (int j = 0; j < STEPS; j++) {
-          uint32_t r = (idx[j] == kNullIdx) ? nullres : uint32_t(__ldg(lut + idx[j]));
+          uint32_t r = (gid[j] == kNullIdx) ? nullres : uint32_t(__ldg(lut + gid[j]));
           leafbits[j] |= (r & 1u) << l;
         }
       }
     } else {
       long long bits[STEPS];
       uint32_t nullmask;
-      decode_num_chunk(c, chunk, c0, n_rows, lane, bits, nullmask);
+      tile_num(t, slot, lane, bits, nullmask);
       const bool f64col = q.slot_type[slot] == ST_F64;
       for (int l = 0; l < q.n_leaves; l++) {
         const LeafDesc& ld = q.leaves[l];
@@ -261,6 +354,24 @@ __device__ __forceinline__ void eval_leaves(const QueryDesc& q, const ChunkDesc*
       }
     }
   }
+}
+
+// Selected rows of the chunk: bit j = this lane's row of step j passes the predicate.
+__device__ __forceinline__ uint32_t chunk_selection(const TileCtx& t, int lane) {
+  const QueryDesc& q = *t.q;
+  uint32_t actbits = 0;
+  if (q.n_filter_prog > 0) {
+    uint32_t leafbits[STEPS];
+    eval_leaves(t, lane, leafbits);
+#pragma unroll
+    for (int j = 0; j < STEPS; j++)
+      if (t.c0 + j * 32 + lane < t.n_rows && eval_filter(q, leafbits[j])) actbits |= 1u << j;
+  } else {
+#pragma unroll
+    for (int j = 0; j < STEPS; j++)
+      if (t.c0 + j * 32 + lane < t.n_rows) actbits |= 1u << j;
+  }
+  return actbits;
 }
 
 // ---- aggregate expressions ----------------------------------------------------------------------------------
@@ -291,8 +402,8 @@ __device__ __forceinline__ long long apply_arith(uint8_t op, bool is_float, long
 
 // Values of aggregate `a` for the chunk's rows.  Evaluated column-at-a-time over a small operand stack
 // of 8-row vectors (depth <= 3; deeper expressions are rejected by the host).
-__device__ __forceinline__ void eval_agg_values(const QueryDesc& q, const AggDesc& a, const ChunkDesc* __restrict__ chunks,
-                                                uint32_t chunk, uint32_t c0, uint32_t n_rows, int lane, long long (&out)[STEPS]) {
+__device__ __forceinline__ void eval_agg_values(const TileCtx& t, const AggDesc& a, int lane, long long (&out)[STEPS]) {
+  const QueryDesc& q = *t.q;
   long long s1[STEPS], s2[STEPS];
   int sp = 0;
   for (int p = a.prog_off; p < a.prog_off + a.prog_len; p++) {
@@ -301,7 +412,7 @@ __device__ __forceinline__ void eval_agg_values(const QueryDesc& q, const AggDes
       long long v[STEPS];
       if (o.op == PO_LOAD) {
         uint32_t nm;
-        decode_num_chunk(chunks[o.slot], chunk, c0, n_rows, lane, v, nm);
+        tile_num(t, o.slot, lane, v, nm);
       } else {
 #pragma unroll
         for (int j = 0; j < STEPS; j++) v[j] = o.imm;
@@ -318,7 +429,6 @@ __device__ __forceinline__ void eval_agg_values(const QueryDesc& q, const AggDes
       }
       sp++;
     } else {
-      // binary op on the two topmost vectors
       if (sp == 2) {
 #pragma unroll
         for (int j = 0; j < STEPS; j++) out[j] = apply_arith(o.op, a.is_float, out[j], s1[j]);
@@ -494,19 +604,91 @@ __device__ __forceinline__ int find_rg(const uint32_t* __restrict__ first_tile, 
 // ======================================================================================================
 // k_scan
 // ======================================================================================================
+// Shared-memory ring: n_stages stages, each = n_stage_plain x (TILE x 8 B) + n_stage_seeds x (8 seeds x 32 B).
+// Warps 0..7 consume, warp 8 produces.  full[s]: 1 arrival (producer, with expect_tx); empty[s]: 8 arrivals.
+constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ size_t stage_bytes(const QueryDesc& q) {
+  return size_t(q.n_stage_plain) * stage_plain_bytes() + size_t(q.n_stage_seeds) * stage_seed_bytes();
+}
+
 template <int KW>
-__global__ void __launch_bounds__(NT) k_scan(const QueryDesc* __restrict__ qp) {
+__global__ void __launch_bounds__(NT + 32) k_scan(const QueryDesc* __restrict__ qp) {
+  extern __shared__ __align__(128) uint8_t ring[];
   __shared__ QueryDesc sq;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(qp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
-    for (uint32_t i = threadIdx.x; i < sizeof(QueryDesc) / 4; i += NT) dst[i] = src[i];
+    for (uint32_t i = threadIdx.x; i < sizeof(QueryDesc) / 4; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
   const QueryDesc& q = sq;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool dense = q.table_mode == TM_DENSE;
+  const int S = q.n_stages;
+  const size_t sbytes = stage_bytes(q);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NWARP);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
+  if (warp == NWARP) {
+    // ================= producer warp: keeps the ring full =================
+    if (lane == 0 && S > 0) {
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x, it++) {
+        const int st = int(it % uint32_t(S));
+        const uint32_t ph = (it / uint32_t(S)) & 1u;
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
+        const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
+        const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
+        const uint32_t r0 = tile_in_rg * TILE;
+        const uint32_t n = min(uint32_t(TILE), n_rows - r0);
+        const uint32_t n_chunks = (n + kIndexRows - 1) / kIndexRows;
+        const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
+        uint8_t* stage = ring + size_t(st) * sbytes;
+        // pass 1: bytes of this stage
+        uint32_t bytes = 0;
+        const uint32_t plain_sz = (n * 8u + 15u) & ~15u;
+        const uint32_t seed_sz = n_chunks * uint32_t(sizeof(Seed));
+        for (int p = 0; p < q.n_stage_plain; p++) {
+          const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
+          if (c.kind == CK_PLAIN64 && !c.has_nulls) bytes += plain_sz;
+        }
+        for (int t = 0; t < q.n_stage_seeds; t++) {
+          const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
+          const bool present = q.stage_seed_is_def[t] ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
+          if (present) bytes += seed_sz;
+        }
+        mbar_expect_tx(&full_bar[st], bytes);
+        // pass 2: issue the copies
+        for (int p = 0; p < q.n_stage_plain; p++) {
+          const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
+          if (c.kind == CK_PLAIN64 && !c.has_nulls)
+            bulk_g2s(stage + size_t(p) * stage_plain_bytes(), c.values + size_t(r0) * 8, plain_sz, &full_bar[st]);
+        }
+        uint8_t* seed_base = stage + size_t(q.n_stage_plain) * stage_plain_bytes();
+        for (int t = 0; t < q.n_stage_seeds; t++) {
+          const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
+          const bool is_def = q.stage_seed_is_def[t];
+          const bool present = is_def ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
+          if (present)
+            bulk_g2s(seed_base + size_t(t) * stage_seed_bytes(), (is_def ? c.def_seeds : c.seeds) + size_t(tile_in_rg) * NWARP, seed_sz,
+                     &full_bar[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= consumer warps =================
+  const bool dense = q.table_mode == TM_DENSE;
   // warp-uniform running group + per-lane partial aggregates carried across chunks
   uint32_t cur_slot = kNoSlot;
   uint32_t cur_cnt = 0;
@@ -521,179 +703,179 @@ __global__ void __launch_bounds__(NT) k_scan(const QueryDesc* __restrict__ qp) {
 #pragma unroll
   for (int w = 0; w < KW; w++) last_kw[w] = ~0ull;
 
-  for (uint32_t tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x) {
+  uint32_t it = 0;
+  for (uint32_t tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x, it++) {
+    const int st = S > 0 ? int(it % uint32_t(S)) : 0;
+    const uint32_t ph = S > 0 ? (it / uint32_t(S)) & 1u : 0;
     const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
     const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
-    const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
-    const uint32_t chunk = tile_in_rg * NWARP + warp;  // 256-row chunk index inside the row group
-    const uint32_t c0 = chunk * kIndexRows;
-    if (c0 >= n_rows) continue;  // warp-uniform
-    const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
-    const LeafRt* __restrict__ lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+    TileCtx t;
+    t.q = &q;
+    t.n_rows = __ldg(&q.rg_rows[rg]);
+    t.tile_r0 = tile_in_rg * TILE;
+    t.chunk_in_tile = uint32_t(warp);
+    t.chunk = tile_in_rg * NWARP + warp;  // 128-row chunk index inside the row group
+    t.c0 = t.chunk * kIndexRows;
+    t.chunks = q.chunks + size_t(rg) * q.n_slots;
+    t.lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+    t.stage = S > 0 ? ring + size_t(st) * sbytes : nullptr;
+    if (S > 0) mbar_wait(&full_bar[st], ph);
 
-    // ---- predicate -> active mask per step ----------------------------------------------------
-    uint32_t actbits = 0;  // bit j: this lane's row of step j is selected
-    if (q.n_filter_prog > 0) {
-      uint32_t leafbits[STEPS];
-      eval_leaves(q, chunks, lrt, chunk, c0, n_rows, lane, leafbits);
-#pragma unroll
-      for (int j = 0; j < STEPS; j++) {
-        bool inb = c0 + j * 32 + lane < n_rows;
-        if (inb && eval_filter(q, leafbits[j])) actbits |= 1u << j;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < STEPS; j++)
-        if (c0 + j * 32 + lane < n_rows) actbits |= 1u << j;
-    }
-    if (__ballot_sync(FULL, actbits != 0) == 0) continue;  // nothing selected in this chunk
-
-    // ---- group key per row ---------------------------------------------------------------------
-    unsigned long long kw[KW][STEPS];
-#pragma unroll
-    for (int w = 0; w < KW; w++)
-#pragma unroll
-      for (int j = 0; j < STEPS; j++) kw[w][j] = 0;
-    for (int k = 0; k < q.n_keys; k++) {
-      const KeyDesc& kd = q.keys[k];
-      const ChunkDesc& c = chunks[kd.slot];
-      if (kd.is_int64) {
-        long long v[STEPS];
-        uint32_t nm;
-        decode_num_chunk(c, chunk, c0, n_rows, lane, v, nm);
-        // NULL and 0 hash alike in the reference (dynparquet/hashed.go:254-262): NULL slots hold 0
+    if (t.c0 < t.n_rows) {
+      // ---- predicate -> active mask per step ----------------------------------------------------
+      const uint32_t actbits = chunk_selection(t, lane);
+      if (__ballot_sync(FULL, actbits != 0) != 0) {
+        // ---- group key per row -------------------------------------------------------------------
+        unsigned long long kw[KW][STEPS];
 #pragma unroll
         for (int w = 0; w < KW; w++)
-          if (w == kd.word)
 #pragma unroll
-            for (int j = 0; j < STEPS; j++) kw[w][j] = (unsigned long long)v[j];
-      } else {
-        uint32_t idx[STEPS];
-        decode_dict_chunk(c, chunk, c0, n_rows, lane, idx);
-        const uint32_t* lut = c.lut;
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) {
-          unsigned long long code = (idx[j] == kNullIdx) ? 0ull : (unsigned long long)__ldg(lut + idx[j]) + 1ull;
-          if (dense) {
-            kw[0][j] += code * kd.dense_stride;
-          } else {
+          for (int j = 0; j < STEPS; j++) kw[w][j] = 0;
+        for (int k = 0; k < q.n_keys; k++) {
+          const KeyDesc& kd = q.keys[k];
+          if (kd.is_int64) {
+            long long v[STEPS];
+            uint32_t nm;
+            tile_num(t, kd.slot, lane, v, nm);
+            // NULL and 0 hash alike in the reference (dynparquet/hashed.go:254-262): NULL slots hold 0
 #pragma unroll
             for (int w = 0; w < KW; w++)
-              if (w == kd.word) kw[w][j] |= code << kd.shift;
-          }
-        }
-      }
-    }
-    // ---- table slot per row ----------------------------------------------------------------------
-    uint32_t slot[STEPS];
+              if (w == kd.word)
 #pragma unroll
-    for (int j = 0; j < STEPS; j++) {
-      slot[j] = kNoSlot;
-      if (!((actbits >> j) & 1u)) continue;
-      if (dense) {
-        slot[j] = uint32_t(kw[0][j]);
-      } else {
-        bool same = last_slot != kNoSlot;
+                for (int j = 0; j < STEPS; j++) kw[w][j] = (unsigned long long)v[j];
+          } else {
+            uint32_t gid[STEPS];
+            tile_dict(t, kd.slot, lane, gid);
 #pragma unroll
-        for (int w = 0; w < KW; w++) same &= (kw[w][j] == last_kw[w]);
-        if (!same) {
-          unsigned long long key[KW];
+            for (int j = 0; j < STEPS; j++) {
+              unsigned long long code = (gid[j] == kNullIdx) ? 0ull : (unsigned long long)gid[j] + 1ull;
+              if (dense) {
+                kw[0][j] += code * kd.dense_stride;
+              } else {
 #pragma unroll
-          for (int w = 0; w < KW; w++) key[w] = kw[w][j];
-          last_slot = hash_find_or_insert<KW>(q, key, &overflow);
-#pragma unroll
-          for (int w = 0; w < KW; w++) last_kw[w] = key[w];
-        }
-        slot[j] = last_slot;
-      }
-    }
-    // ---- step classification: 0 = nothing selected, else uniform group (ustep) or mixed ------------
-    uint32_t uslot[STEPS];   // warp-uniform: group of the step, kNoSlot when mixed or empty
-    uint32_t mixedbits = 0;  // warp-uniform: bit j set when the step's active lanes span several groups
-#pragma unroll
-    for (int j = 0; j < STEPS; j++) {
-      bool active = (actbits >> j) & 1u;
-      unsigned amask = __ballot_sync(FULL, active);
-      uslot[j] = kNoSlot;
-      if (amask == 0) continue;
-      if (lane == 0) selected_local += __popc(amask);
-      uint32_t s = __shfl_sync(FULL, slot[j], __ffs(amask) - 1);
-      bool uni = __all_sync(FULL, !active || slot[j] == s);
-      if (uni) uslot[j] = s;
-      else mixedbits |= 1u << j;
-    }
-    // ---- rows-per-group counter (also every Count aggregate, aggregate.go:937-950) ----------------
-    {
-      uint32_t cs = cur_slot;
-#pragma unroll
-      for (int j = 0; j < STEPS; j++) {
-        bool active = (actbits >> j) & 1u;
-        if ((mixedbits >> j) & 1u) {
-          if (cs != kNoSlot) {
-            uint32_t t = __reduce_add_sync(FULL, cur_cnt);
-            if (lane == 0 && t) atomicAdd(q.t_rows + cs, (unsigned long long)t);
-            cur_cnt = 0;
-            cs = kNoSlot;
-          }
-          mixed_rows(q.t_rows, slot[j], active, lane);
-        } else if (uslot[j] != kNoSlot) {
-          if (uslot[j] != cs) {
-            if (cs != kNoSlot) {
-              uint32_t t = __reduce_add_sync(FULL, cur_cnt);
-              if (lane == 0 && t) atomicAdd(q.t_rows + cs, (unsigned long long)t);
-              cur_cnt = 0;
+                for (int w = 0; w < KW; w++)
+                  if (w == kd.word) kw[w][j] |= code << kd.shift;
+              }
             }
-            cs = uslot[j];
           }
-          cur_cnt += active ? 1u : 0u;
         }
-      }
-    }
-    // ---- aggregates: per-lane partials while the warp stays in one group ----------------------------
-    // (acc[] is indexed dynamically on purpose: it is touched once per chunk, the per-row work runs on `part`)
+        // ---- table slot per row --------------------------------------------------------------------
+        uint32_t slot[STEPS];
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) {
+          slot[j] = kNoSlot;
+          if (!((actbits >> j) & 1u)) continue;
+          if (dense) {
+            slot[j] = uint32_t(kw[0][j]);
+          } else {
+            bool same = last_slot != kNoSlot;
+#pragma unroll
+            for (int w = 0; w < KW; w++) same &= (kw[w][j] == last_kw[w]);
+            if (!same) {
+              unsigned long long key[KW];
+#pragma unroll
+              for (int w = 0; w < KW; w++) key[w] = kw[w][j];
+              last_slot = hash_find_or_insert<KW>(q, key, &overflow);
+#pragma unroll
+              for (int w = 0; w < KW; w++) last_kw[w] = key[w];
+            }
+            slot[j] = last_slot;
+          }
+        }
+        // ---- step classification: empty, one group for the whole warp (uslot), or mixed -------------
+        uint32_t uslot[STEPS];   // warp-uniform: group of the step, kNoSlot when mixed or empty
+        uint32_t mixedbits = 0;  // warp-uniform: bit j set when the step's active lanes span several groups
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) {
+          bool active = (actbits >> j) & 1u;
+          unsigned amask = __ballot_sync(FULL, active);
+          uslot[j] = kNoSlot;
+          if (amask == 0) continue;
+          if (lane == 0) selected_local += __popc(amask);
+          uint32_t s = __shfl_sync(FULL, slot[j], __ffs(amask) - 1);
+          bool uni = __all_sync(FULL, !active || slot[j] == s);
+          if (uni) uslot[j] = s;
+          else mixedbits |= 1u << j;
+        }
+        // ---- rows-per-group counter (also every Count aggregate, aggregate.go:937-950) ---------------
+        {
+          uint32_t cs = cur_slot;
+#pragma unroll
+          for (int j = 0; j < STEPS; j++) {
+            bool active = (actbits >> j) & 1u;
+            if ((mixedbits >> j) & 1u) {
+              if (cs != kNoSlot) {
+                uint32_t tt = __reduce_add_sync(FULL, cur_cnt);
+                if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+                cur_cnt = 0;
+                cs = kNoSlot;
+              }
+              mixed_rows(q.t_rows, slot[j], active, lane);
+            } else if (uslot[j] != kNoSlot) {
+              if (uslot[j] != cs) {
+                if (cs != kNoSlot) {
+                  uint32_t tt = __reduce_add_sync(FULL, cur_cnt);
+                  if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+                  cur_cnt = 0;
+                }
+                cs = uslot[j];
+              }
+              cur_cnt += active ? 1u : 0u;
+            }
+          }
+        }
+        // ---- aggregates: per-lane partials while the warp stays in one group --------------------------
+        // (acc[] is indexed dynamically on purpose: it is touched once per chunk, the per-row work runs on `part`)
 #pragma unroll 1
-    for (int a = 0; a < q.n_aggs; a++) {
-      const AggDesc& ad = q.aggs[a];
-      if (ad.func == 4 /*count*/) continue;
-      long long v[STEPS];
-      eval_agg_values(q, ad, chunks, chunk, c0, n_rows, lane, v);
-      uint32_t cs = cur_slot;
-      long long part = acc[a];
-      const long long ident = agg_identity(ad.func, ad.is_float);
+        for (int a = 0; a < q.n_aggs; a++) {
+          const AggDesc& ad = q.aggs[a];
+          if (ad.func == 4 /*count*/) continue;
+          long long v[STEPS];
+          eval_agg_values(t, ad, lane, v);
+          uint32_t cs = cur_slot;
+          long long part = acc[a];
+          const long long ident = agg_identity(ad.func, ad.is_float);
 #pragma unroll
-      for (int j = 0; j < STEPS; j++) {
-        bool active = (actbits >> j) & 1u;
-        if ((mixedbits >> j) & 1u) {
-          if (cs != kNoSlot) {
-            flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
-            part = ident;
-            cs = kNoSlot;
-          }
-          mixed_agg(ad.func, ad.is_float, q.t_agg[a], slot[j], active, v[j], lane);
-        } else if (uslot[j] != kNoSlot) {
-          if (uslot[j] != cs) {
-            if (cs != kNoSlot) {
-              flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
-              part = ident;
+          for (int j = 0; j < STEPS; j++) {
+            bool active = (actbits >> j) & 1u;
+            if ((mixedbits >> j) & 1u) {
+              if (cs != kNoSlot) {
+                flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
+                part = ident;
+                cs = kNoSlot;
+              }
+              mixed_agg(ad.func, ad.is_float, q.t_agg[a], slot[j], active, v[j], lane);
+            } else if (uslot[j] != kNoSlot) {
+              if (uslot[j] != cs) {
+                if (cs != kNoSlot) {
+                  flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
+                  part = ident;
+                }
+                cs = uslot[j];
+              }
+              if (active) part = agg_combine(ad.func, ad.is_float, part, v[j]);
             }
-            cs = uslot[j];
           }
-          if (active) part = agg_combine(ad.func, ad.is_float, part, v[j]);
+          acc[a] = part;
+        }
+        // the running group after this chunk (identical for every aggregate by construction)
+#pragma unroll
+        for (int j = 0; j < STEPS; j++) {
+          if ((mixedbits >> j) & 1u) cur_slot = kNoSlot;
+          else if (uslot[j] != kNoSlot) cur_slot = uslot[j];
         }
       }
-      acc[a] = part;
     }
-    // the running group after this chunk (identical for every aggregate by construction)
-#pragma unroll
-    for (int j = 0; j < STEPS; j++) {
-      if ((mixedbits >> j) & 1u) cur_slot = kNoSlot;
-      else if (uslot[j] != kNoSlot) cur_slot = uslot[j];
+    // this warp is done with the stage
+    if (S > 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
   }
   // ---- final flush ---------------------------------------------------------------------------------
   if (cur_slot != kNoSlot) {
-    uint32_t t = __reduce_add_sync(FULL, cur_cnt);
-    if (lane == 0 && t) atomicAdd(q.t_rows + cur_slot, (unsigned long long)t);
+    uint32_t tt = __reduce_add_sync(FULL, cur_cnt);
+    if (lane == 0 && tt) atomicAdd(q.t_rows + cur_slot, (unsigned long long)tt);
 #pragma unroll 1
     for (int a = 0; a < q.n_aggs; a++) {
       if (q.aggs[a].func == 4) continue;
@@ -731,26 +913,19 @@ __global__ void __launch_bounds__(NT) k_rows(const QueryDesc* __restrict__ qp) {
     if (tile >= q.n_tiles) break;
     const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
     const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
-    const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
-    const uint32_t chunk = tile_in_rg * NWARP + warp;
-    const uint32_t c0 = chunk * kIndexRows;
-    const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
-    const LeafRt* __restrict__ lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+    TileCtx t;
+    t.q = &q;
+    t.n_rows = __ldg(&q.rg_rows[rg]);
+    t.tile_r0 = tile_in_rg * TILE;
+    t.chunk_in_tile = uint32_t(warp);
+    t.chunk = tile_in_rg * NWARP + warp;
+    t.c0 = t.chunk * kIndexRows;
+    t.chunks = q.chunks + size_t(rg) * q.n_slots;
+    t.lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+    t.stage = nullptr;
 
     uint32_t actbits = 0;
-    if (c0 < n_rows) {
-      if (q.n_filter_prog > 0) {
-        uint32_t leafbits[STEPS];
-        eval_leaves(q, chunks, lrt, chunk, c0, n_rows, lane, leafbits);
-#pragma unroll
-        for (int j = 0; j < STEPS; j++)
-          if (c0 + j * 32 + lane < n_rows && eval_filter(q, leafbits[j])) actbits |= 1u << j;
-      } else {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++)
-          if (c0 + j * 32 + lane < n_rows) actbits |= 1u << j;
-      }
-    }
+    if (t.c0 < t.n_rows) actbits = chunk_selection(t, lane);
     // rank of every selected row inside the warp's chunk, in row order
     uint32_t rank[STEPS];
     uint32_t wtotal = 0;
@@ -774,9 +949,9 @@ __global__ void __launch_bounds__(NT) k_rows(const QueryDesc* __restrict__ qp) {
       unsigned long long excl = 0;
       int64_t look = int64_t(tile) - 1;
       while (look >= 0) {
-        int64_t t = look - lane;
-        unsigned long long s = (t >= 0) ? state[t] : (2ull << 62);
-        while (__any_sync(FULL, (s >> 62) == 0)) s = (t >= 0) ? state[t] : (2ull << 62);  // predecessors publish soon
+        int64_t tt = look - lane;
+        unsigned long long s = (tt >= 0) ? state[tt] : (2ull << 62);
+        while (__any_sync(FULL, (s >> 62) == 0)) s = (tt >= 0) ? state[tt] : (2ull << 62);  // predecessors publish soon
         unsigned pmask = __ballot_sync(FULL, (s >> 62) == 2);
         int first_prefix = pmask ? __ffs(pmask) - 1 : 32;
         unsigned long long contrib = (lane <= first_prefix) ? (s & ((1ull << 62) - 1)) : 0;
@@ -786,6 +961,7 @@ __global__ void __launch_bounds__(NT) k_rows(const QueryDesc* __restrict__ qp) {
         look -= 32;
       }
       if (lane == 0) {
+        __threadfence();
         state[tile] = (2ull << 62) | (excl + ttotal);
         tile_base_s = excl;
       }
@@ -793,21 +969,20 @@ __global__ void __launch_bounds__(NT) k_rows(const QueryDesc* __restrict__ qp) {
     __syncthreads();
     const unsigned long long base = tile_base_s + wbase;
     // ---- write the projected columns of the selected rows ---------------------------------------
-    if (c0 < n_rows && wtotal > 0) {
+    if (t.c0 < t.n_rows && wtotal > 0) {
       for (int o = 0; o < q.n_out; o++) {
         const int slot = q.out_slot[o];
-        const ChunkDesc& c = chunks[slot];
         if (q.slot_type[slot] == ST_DICT) {
-          uint32_t idx[STEPS];
-          decode_dict_chunk(c, chunk, c0, n_rows, lane, idx);
+          uint32_t gid[STEPS];
+          tile_dict(t, slot, lane, gid);
           int32_t* out = reinterpret_cast<int32_t*>(q.out_data[o]);
 #pragma unroll
           for (int j = 0; j < STEPS; j++)
-            if ((actbits >> j) & 1u) out[base + rank[j]] = (idx[j] == kNullIdx) ? -1 : int32_t(__ldg(c.lut + idx[j]));
+            if ((actbits >> j) & 1u) out[base + rank[j]] = (gid[j] == kNullIdx) ? -1 : int32_t(gid[j]);
         } else {
           long long v[STEPS];
           uint32_t nm;
-          decode_num_chunk(c, chunk, c0, n_rows, lane, v, nm);
+          tile_num(t, slot, lane, v, nm);
           long long* out = reinterpret_cast<long long*>(q.out_data[o]);
           uint8_t* valid = q.out_valid[o];
 #pragma unroll
@@ -913,18 +1088,19 @@ __global__ void __launch_bounds__(NT) k_decode(ChunkDesc c, uint32_t n_chunks, i
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t chunk = blockIdx.x * NWARP + warp; chunk < n_chunks; chunk += gridDim.x * NWARP) {
     const uint32_t c0 = chunk * kIndexRows;
+    const ChunkSeeds sd = global_seeds(c, chunk);
     if (c.kind == CK_DICT_STR) {
-      uint32_t idx[STEPS];
-      decode_dict_chunk(c, chunk, c0, c.n_rows, lane, idx);
+      uint32_t gid[STEPS];
+      decode_dict_chunk(c, sd, c0, c.n_rows, lane, gid);
 #pragma unroll
       for (int j = 0; j < STEPS; j++) {
         uint32_t r = c0 + j * 32 + lane;
-        if (r < c.n_rows) out_i32[r] = (idx[j] == kNullIdx) ? -1 : int32_t(__ldg(c.lut + idx[j]));
+        if (r < c.n_rows) out_i32[r] = (gid[j] == kNullIdx) ? -1 : int32_t(gid[j]);
       }
     } else {
       long long v[STEPS];
       uint32_t nm;
-      decode_num_chunk(c, chunk, c0, c.n_rows, lane, v, nm);
+      decode_num_chunk(c, sd, nullptr, 0, c0, c.n_rows, lane, v, nm);
 #pragma unroll
       for (int j = 0; j < STEPS; j++) {
         uint32_t r = c0 + j * 32 + lane;
@@ -943,13 +1119,20 @@ __global__ void __launch_bounds__(NT) k_decode(ChunkDesc c, uint32_t n_chunks, i
 namespace {
 template <int KW>
 cudaError_t launch_scan_kw(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
+  const size_t smem = size_t(q.n_stages) * (size_t(q.n_stage_plain) * TILE * 8 + size_t(q.n_stage_seeds) * NWARP * sizeof(Seed));
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_scan<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<KW>, NT, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<KW>, NT + 32, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
   if (grid > q.n_tiles) grid = q.n_tiles;
-  k_scan<KW><<<grid, NT, 0, st>>>(d_q);
+  k_scan<KW><<<grid, NT + 32, smem, st>>>(d_q);
   return cudaGetLastError();
 }
 int grid_for(size_t n) {

@@ -559,7 +559,7 @@ bool walk_hybrid(const uint8_t* data, uint32_t len, int w, uint32_t count, uint3
   return true;
 }
 
-uint32_t hybrid_value_at(const uint8_t* stream, const std::vector<HostRun>& runs, uint32_t ordinal) {
+uint32_t hybrid_value_at(const uint8_t* stream, const std::vector<HostRun>& runs, uint32_t ordinal, bool* was_rle) {
   // binary search the last run with start <= ordinal
   size_t lo = 0, hi = runs.size();
   while (hi - lo > 1) {
@@ -567,6 +567,7 @@ uint32_t hybrid_value_at(const uint8_t* stream, const std::vector<HostRun>& runs
     if (runs[mid].start <= ordinal) lo = mid; else hi = mid;
   }
   const HostRun& r = runs[lo];
+  if (was_rle) *was_rle = (r.meta & 1u) == 0;
   if ((r.meta & 1u) == 0) return r.val;
   uint32_t w = (r.meta >> 8) & 0xff;
   if (w == 0) return 0;

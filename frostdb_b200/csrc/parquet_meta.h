@@ -85,6 +85,6 @@ bool walk_hybrid(const uint8_t* data, uint32_t len, int w, uint32_t count, uint3
                  uint32_t off0, std::vector<HostRun>* runs, std::string* err);
 
 // Reads value i of a hybrid stream described by runs (host-side reference used by describe/tests).
-uint32_t hybrid_value_at(const uint8_t* stream, const std::vector<HostRun>& runs, uint32_t ordinal);
+uint32_t hybrid_value_at(const uint8_t* stream, const std::vector<HostRun>& runs, uint32_t ordinal, bool* was_rle = nullptr);
 
 }  // namespace fgpu

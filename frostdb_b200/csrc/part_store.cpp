@@ -206,32 +206,49 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
     if (n_values > 0 && dict_size == 0) { out->error = "dictionary-encoded values without a dictionary page"; return; }
   }
 
-  // ---- tile indexes ----------------------------------------------------------------------------
-  std::vector<uint32_t> tile_val0(n_tiles), tile_defrun, tile_run;
+  // ---- RLE run values of string dictionaries become global ids (no LUT hop for run-length data) ----
+  if (out->desc.kind == CK_DICT_STR)
+    for (HostRun& r : vruns)
+      if ((r.meta & 1u) == 0) r.val = out->lut_host[r.val];
+
+  // ---- chunk seeds ------------------------------------------------------------------------------
+  const uint32_t n_chunks = n_tiles;  // `tile_rows` is the seed granularity (kIndexRows)
+  std::vector<uint32_t> chunk_val0(n_chunks);
   if (has_nulls) {
     uint64_t acc = 0;
-    for (uint32_t t = 0; t < n_tiles; t++) {
-      tile_val0[t] = uint32_t(acc);
+    for (uint32_t t = 0; t < n_chunks; t++) {
+      chunk_val0[t] = uint32_t(acc);
       uint64_t b = uint64_t(t) * T, e = std::min<uint64_t>(uint64_t(n_rows), b + T);
       acc += popcount_range(valid, b, e);
     }
-    tile_defrun.resize(n_tiles);
-    size_t k = 0;
-    for (uint32_t t = 0; t < n_tiles; t++) {
-      while (k + 1 < defruns.size() && defruns[k + 1].start <= t * T) k++;
-      tile_defrun[t] = uint32_t(k);
-    }
   } else {
-    for (uint32_t t = 0; t < n_tiles; t++) tile_val0[t] = t * T;
+    for (uint32_t t = 0; t < n_chunks; t++) chunk_val0[t] = t * T;
   }
-  if (out->desc.kind != CK_PLAIN64) {
-    tile_run.resize(n_tiles);
+  auto make_seeds = [&](const std::vector<HostRun>& runs, uint32_t total, bool is_def) {
+    std::vector<Seed> seeds(n_chunks);
     size_t k = 0;
-    for (uint32_t t = 0; t < n_tiles; t++) {
-      while (k + 1 < vruns.size() && vruns[k + 1].start <= tile_val0[t]) k++;
-      tile_run[t] = uint32_t(k);
+    for (uint32_t t = 0; t < n_chunks; t++) {
+      uint32_t first = is_def ? t * T : chunk_val0[t];
+      while (k + 1 < runs.size() && runs[k + 1].start <= first) k++;
+      Seed sd{};
+      sd.val0 = chunk_val0[t];
+      if (runs.empty() || first >= total) {  // nothing left to decode from this chunk on
+        sd.k = uint32_t(runs.size());
+        sd.start = total;
+        sd.end = 0xffffffffu;
+      } else {
+        const HostRun& r = runs[k];
+        sd.k = uint32_t(k);
+        sd.start = r.start;
+        sd.end = (k + 1 < runs.size()) ? runs[k + 1].start : total;
+        sd.off = r.off;
+        sd.val = r.val;
+        sd.meta = r.meta;
+      }
+      seeds[t] = sd;
     }
-  }
+    return seeds;
+  };
 
   // ---- write sections ----------------------------------------------------------------------------
   const size_t before = w.buf.size();
@@ -240,20 +257,21 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   out->desc.dict_size = dict_size;
   out->off_values = w.section(vstream.data(), vstream.size());
   if (out->desc.kind != CK_PLAIN64) {
+    std::vector<Seed> seeds = make_seeds(vruns, n_values, false);
     out->desc.n_runs = uint32_t(vruns.size());
     HostRun sentinel{n_values, 0, 0, 0};
     vruns.push_back(sentinel);
     out->off_runs = w.section(vruns.data(), vruns.size() * sizeof(HostRun));
-    out->off_tile_run = w.section(tile_run.data(), tile_run.size() * 4);
+    out->off_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
   }
   if (has_nulls) {
+    std::vector<Seed> seeds = make_seeds(defruns, n_rows, true);
     out->desc.n_defruns = uint32_t(defruns.size());
     HostRun sentinel{n_rows, 0, 0, 0};
     defruns.push_back(sentinel);
     out->off_def = w.section(defstream.data(), defstream.size());
     out->off_def_runs = w.section(defruns.data(), defruns.size() * sizeof(HostRun));
-    out->off_tile_defrun = w.section(tile_defrun.data(), tile_defrun.size() * 4);
-    out->off_tile_val0 = w.section(tile_val0.data(), tile_val0.size() * 4);
+    out->off_def_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
   }
   if (out->desc.kind == CK_DICT_STR) out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
   if (out->desc.kind == CK_DICT64) out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
@@ -298,11 +316,10 @@ void patch_part_pointers(Part* part, const uint8_t* base) {
       auto at = [&](int64_t off) -> const uint8_t* { return off < 0 ? nullptr : base + off; };
       c.desc.values = at(c.off_values);
       c.desc.runs = reinterpret_cast<const Run*>(at(c.off_runs));
-      c.desc.tile_run = reinterpret_cast<const uint32_t*>(at(c.off_tile_run));
+      c.desc.seeds = reinterpret_cast<const Seed*>(at(c.off_seeds));
       c.desc.def = at(c.off_def);
       c.desc.def_runs = reinterpret_cast<const Run*>(at(c.off_def_runs));
-      c.desc.tile_defrun = reinterpret_cast<const uint32_t*>(at(c.off_tile_defrun));
-      c.desc.tile_val0 = reinterpret_cast<const uint32_t*>(at(c.off_tile_val0));
+      c.desc.def_seeds = reinterpret_cast<const Seed*>(at(c.off_def_seeds));
       c.desc.lut = reinterpret_cast<const uint32_t*>(at(c.off_lut));
       c.desc.dict64 = reinterpret_cast<const int64_t*>(at(c.off_dict64));
     }
@@ -366,16 +383,21 @@ std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows,
         bool tiles_ok = true;
         for (uint32_t r = 0; r < rg.n_rows; r++) {
           if (r) o << ',';
-          if (d.has_nulls && r % T == 0 && d.tile_val0[r / T] != vord) tiles_ok = false;
           if (r % T == 0) {
-            uint32_t v0 = d.has_nulls ? d.tile_val0[r / T] : r;
-            if (d.kind != CK_PLAIN64 && v0 < d.n_values) {
-              uint32_t fr = d.tile_run[r / T];
-              if (!(vruns[fr].start <= v0 && vruns[fr + 1].start > v0)) tiles_ok = false;
+            auto seed_ok = [&](const Seed& sd, const std::vector<HostRun>& runs, uint32_t first, uint32_t total) {
+              if (first >= total) return true;
+              if (sd.k >= runs.size() - 1) return false;
+              const HostRun& rr = runs[sd.k];
+              return rr.start <= first && runs[sd.k + 1].start > first && sd.start == rr.start && sd.end == runs[sd.k + 1].start &&
+                     sd.off == rr.off && sd.val == rr.val && sd.meta == rr.meta;
+            };
+            if (d.kind != CK_PLAIN64) {
+              const Seed& sd = d.seeds[r / T];
+              if (sd.val0 != vord || !seed_ok(sd, vruns, vord, d.n_values)) tiles_ok = false;
             }
             if (d.has_nulls) {
-              uint32_t fr = d.tile_defrun[r / T];
-              if (!(druns[fr].start <= r && druns[fr + 1].start > r)) tiles_ok = false;
+              const Seed& sd = d.def_seeds[r / T];
+              if (sd.val0 != vord || !seed_ok(sd, druns, r, rg.n_rows)) tiles_ok = false;
             }
           }
           bool valid = true;
@@ -392,8 +414,9 @@ std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows,
               o << buf;
             } else o << v;
           } else {
-            uint32_t idx = hybrid_value_at(d.values, vruns, vord);
-            if (d.kind == CK_DICT_STR) json_escape(o, gd->values[d.lut[idx]]);
+            bool was_rle = false;
+            uint32_t idx = hybrid_value_at(d.values, vruns, vord, &was_rle);
+            if (d.kind == CK_DICT_STR) json_escape(o, gd->values[was_rle ? idx : d.lut[idx]]);
             else if (c.phys == PT_DOUBLE) {
               double f;
               std::memcpy(&f, &d.dict64[idx], 8);

@@ -19,9 +19,6 @@ namespace fgpu {
 struct GlobalDict {
   std::vector<std::string> values;
   std::unordered_map<std::string, uint32_t> index;
-  // Cross-rank id space (fgpu_dict_unify): local id -> unified id; empty = identity.
-  std::vector<uint32_t> unified;
-  std::vector<std::string> unified_values;
   uint32_t intern(const char* p, size_t n) {
     std::string s(p, n);
     auto it = index.find(s);
@@ -31,8 +28,8 @@ struct GlobalDict {
     index.emplace(std::move(s), id);
     return id;
   }
-  uint32_t cardinality() const { return uint32_t(unified_values.empty() ? values.size() : unified_values.size()); }
-  const std::string& value(uint32_t id) const { return unified_values.empty() ? values[id] : unified_values[id]; }
+  uint32_t cardinality() const { return uint32_t(values.size()); }
+  const std::string& value(uint32_t id) const { return values[id]; }
 };
 
 struct ChunkHost {
@@ -43,8 +40,8 @@ struct ChunkHost {
   std::string error;           // non-empty: unreadable; an error only if a query projects it
   std::vector<uint32_t> lut_host;  // CK_DICT_STR: chunk dictionary index -> *local* global id
   // section offsets inside the part image (patched into desc after upload)
-  int64_t off_values = -1, off_runs = -1, off_tile_run = -1, off_def = -1, off_def_runs = -1, off_tile_defrun = -1,
-          off_tile_val0 = -1, off_lut = -1, off_dict64 = -1;
+  int64_t off_values = -1, off_runs = -1, off_seeds = -1, off_def = -1, off_def_runs = -1, off_def_seeds = -1, off_lut = -1,
+          off_dict64 = -1;
 };
 
 struct RowGroupHost {

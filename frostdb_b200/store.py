@@ -106,10 +106,11 @@ class GPUEngine:
             p += 4 + l
         return out
 
-    def dict_unify(self, table: str, column: str, values: List[bytes]) -> None:
+    def dict_preload(self, table: str, column: str, values: List[bytes]) -> None:
+        """Interns `values` in order (call with the same list on every rank before putting parts)."""
         blob = b"".join(len(v).to_bytes(4, "little") + v for v in values)
         src = (C.c_char * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
-        _lib.check(_lib.load().fgpu_dict_unify(self.handle, table.encode(), column.encode(), C.addressof(src), len(blob), len(values)))
+        _lib.check(_lib.load().fgpu_dict_preload(self.handle, table.encode(), column.encode(), C.addressof(src), len(blob), len(values)))
 
 
 class Table:

@@ -235,10 +235,15 @@ int32_t fgpu_query_free(fgpu_query* q);
  * length-prefixed blob: repeated {uint32 LE length, bytes}.  Call with buf == NULL to size. */
 int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, uint8_t* buf,
                          uint64_t cap, uint64_t* out_len, uint32_t* out_count);
-/* Installs the cross-rank id space: `unified` is the blob format above holding the union
- * dictionary; afterwards partial tables of all ranks are keyed by unified ids. */
-int32_t fgpu_dict_unify(fgpu_ctx* ctx, const char* table, const char* column,
-                        const uint8_t* unified, uint64_t len, uint32_t count);
+/* Cross-rank id space: interns the given strings (blob format above), in order, into the table's
+ * dictionary of `column`.  Every rank preloads the same union list BEFORE putting its parts, so the
+ * ids — and therefore the partial tables — agree across ranks.  Entries already present keep their id. */
+int32_t fgpu_dict_preload(fgpu_ctx* ctx, const char* table, const char* column,
+                          const uint8_t* blob, uint64_t len, uint32_t count);
+/* Host-only: the distinct dictionary entries of `column` in one Parquet file (first-seen order),
+ * in the blob format above.  Lets a rank contribute its strings to the union without uploading. */
+int32_t fgpu_parquet_dict_values(const uint8_t* file, uint64_t len, const char* column,
+                                 uint8_t* buf, uint64_t cap, uint64_t* out_len, uint32_t* out_count);
 
 /* Scan only.  `*dev_ptr` is a DEVICE pointer to a position-independent partial table of
  * `*nbytes` bytes (same size on every rank for the same query + unified dictionaries). */
