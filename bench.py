@@ -311,7 +311,7 @@ def main():
         return d2h
 
     e2e = None
-    if world == 1:
+    if world == 1 and not os.environ.get("FROSTGPU_SKIP_E2E"):
         e2e_step()  # warm
         sync_all()
         t0 = time.perf_counter()

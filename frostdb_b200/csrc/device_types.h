@@ -135,7 +135,12 @@ struct QueryDesc {
   int32_t filter_kind;   // FilterKind
   uint32_t filter_mask;  // FK_AND / FK_OR: the participating leaf bits
   int32_t n_out;         // rows plan: projected columns
-  int32_t n_stage_plain, n_stage_seeds, n_stages;  // shared-memory ring shape (scan kernel)
+  int32_t n_stage_plain, n_stage_seeds, n_stages;  // staged PLAIN slices / seeds per vector (scan kernel)
+  int32_t vl;            // rows per warp vector (scan kernel)
+  int32_t n_ring;        // ring depth per warp
+  uint32_t slot_bytes;   // bytes of one ring slot
+  uint32_t wr_bytes;     // per-warp shared-memory region: size and section offsets
+  uint32_t wr_ring, wr_act, wr_leaf, wr_slot, wr_keyw, wr_tmp1, wr_tmp2, wr_acc;
   uint8_t stage_plain_slot[kMaxStagePlain];   // staged PLAIN buffer p holds this slot
   uint8_t stage_seed_slot[kMaxStageSeeds];    // staged seed block t belongs to this slot ...
   uint8_t stage_seed_is_def[kMaxStageSeeds];  // ... and is its definition-level stream (1) or value stream (0)

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -456,15 +457,6 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       qd.stage_seed_is_def[qd.n_stage_seeds++] = 1;
     }
   }
-  {
-    size_t per_stage = size_t(qd.n_stage_plain) * kTileRows * 8 + size_t(qd.n_stage_seeds) * (kTileRows / kIndexRows) * sizeof(Seed);
-    int stages = 0;
-    if (per_stage > 0) {
-      stages = int(std::min<size_t>(4, (96 * 1024) / per_stage));
-      if (stages < 2) stages = 2;
-    }
-    qd.n_stages = stages;
-  }
   // filter
   if (q.filter >= 0) {
     int32_t rc = compile_filter(q, q.filter, c, slot_of);
@@ -555,14 +547,14 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   }
   if (prog.size() > size_t(kMaxProg)) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expressions too large");
   for (size_t p = 0; p < prog.size(); p++) qd.prog[p] = prog[p];
-  // the kernel evaluates aggregate expressions on an operand stack of three 8-row vectors
+  // the kernel evaluates aggregate expressions on an operand stack of two shared-memory vectors
   for (size_t a = 0; a < q.aggs.size(); a++) {
     int depth = 0, maxd = 0;
     for (int p = qd.aggs[a].prog_off; p < qd.aggs[a].prog_off + qd.aggs[a].prog_len; p++) {
       depth += (prog[size_t(p)].op == PO_LOAD || prog[size_t(p)].op == PO_CONST) ? 1 : -1;
       maxd = std::max(maxd, depth);
     }
-    if (maxd > 3) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expression nests too deeply for the GPU path");
+    if (maxd > 2) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expression nests too deeply for the GPU path");
   }
   qd.tile_rows = ctx->tile_rows;
   qd.n_rg = int32_t(c->rgs.size());
@@ -645,6 +637,38 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     while (cap < 2 * c->group_bound && cap < (1ull << 28)) cap <<= 1;
     qd.table_slots = uint32_t(cap);
   }
+  // ---- scan kernel: vector length, ring depth and the per-warp shared-memory layout ----------------
+  {
+    auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    int vl = envi("FROSTGPU_VL", 256);
+    if (vl != 128 && vl != 256 && vl != 512) vl = 256;
+    int ring = envi("FROSTGPU_RING", 2);
+    if (ring < 2) ring = 2;
+    if (ring > 4) ring = 4;
+    bool any_expr = false;
+    for (int a = 0; a < qd.n_aggs; a++)
+      if (qd.aggs[a].func != FGPU_AGG_COUNT && !(qd.aggs[a].prog_len == 1 && qd.prog[qd.aggs[a].prog_off].op == PO_LOAD)) any_expr = true;
+    auto r128 = [](size_t x) { return (x + 127) & ~size_t(127); };
+    for (;;) {
+      size_t off = r128(size_t(ring) * 8);
+      size_t slot = r128(size_t(qd.n_stage_plain) * vl * 8 + size_t(qd.n_stage_seeds) * sizeof(Seed));
+      if (slot == 0) slot = 128;
+      qd.slot_bytes = uint32_t(slot);
+      qd.wr_ring = uint32_t(off); off += size_t(ring) * slot;
+      qd.wr_act = uint32_t(off); off = r128(off + size_t(vl / 32) * 4);
+      qd.wr_leaf = uint32_t(off); off = r128(off + ((qd.n_filter_prog > 0 && qd.filter_kind != FK_AND) ? size_t(vl) * 4 : 0));
+      qd.wr_slot = uint32_t(off); off = r128(off + size_t(vl) * 4);
+      qd.wr_keyw = uint32_t(off); off = r128(off + (qd.table_mode == TM_HASH ? size_t(qd.key_words) * vl * 8 : 0));
+      qd.wr_tmp1 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
+      qd.wr_tmp2 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
+      qd.wr_acc = uint32_t(off); off = r128(off + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4 + 32 * 4);
+      qd.wr_bytes = uint32_t(off);
+      if (size_t(qd.wr_bytes) * (kVecThreads / 32) <= 200 * 1024 || vl == 128) break;
+      vl /= 2;  // many staged columns / wide keys: shorter vectors
+    }
+    qd.vl = vl;
+    qd.n_ring = ring;
+  }
   return FGPU_OK;
 }
 
@@ -695,11 +719,12 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   std::vector<uint8_t> lutbytes;
   std::vector<std::pair<size_t, size_t>> lut_fix;  // (index into lrt, offset into lutbytes)
   uint32_t tiles = 0;
+  const uint32_t tile_len = q.kind == FGPU_PLAN_FILTER ? uint32_t(kTileRows) : uint32_t(qd.vl);  // rows plan: CTA tiles; scan: warp vectors
   for (int g = 0; g < n_rg; g++) {
     RowGroupHost& rg = *c.rgs[size_t(g)].rg;
     first_tile[size_t(g)] = tiles;
     rg_rows[size_t(g)] = rg.n_rows;
-    tiles += (rg.n_rows + uint32_t(ctx->tile_rows) - 1) / uint32_t(ctx->tile_rows);
+    tiles += (rg.n_rows + tile_len - 1) / tile_len;
     for (int s = 0; s < n_slots; s++) {
       ChunkDesc d{};
       d.kind = CK_ABSENT;

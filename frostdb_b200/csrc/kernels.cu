@@ -602,22 +602,500 @@ __device__ __forceinline__ int find_rg(const uint32_t* __restrict__ first_tile, 
 }  // namespace
 
 // ======================================================================================================
-// k_scan
+// k_scan — vectorized, warp-private execution
 // ======================================================================================================
-// Shared-memory ring: n_stages stages, each = n_stage_plain x (TILE x 8 B) + n_stage_seeds x (8 seeds x 32 B).
-// Warps 0..7 consume, warp 8 produces.  full[s]: 1 arrival (producer, with expect_tx); empty[s]: 8 arrivals.
-constexpr int kMaxStages = 8;
+// Every warp owns vectors of q.vl rows (128..512, a multiple of 128) of one row group and works through
+// them column at a time, like a vectorized CPU engine works through cache-resident vectors: per-row
+// intermediates (selection bits, table slot, packed key words, expression temporaries) live in the
+// warp's private shared-memory region, so the only per-lane state is the cursor of the ONE column
+// being decoded.  The fixed cost of resolving a column (descriptor, seeds, staging) is paid once per
+// vector instead of once per 128 rows, which is what made the previous version instruction bound.
+// Lane 0 of the warp keeps a private ring of q.n_ring slots filled with cp.async.bulk copies (TMA)
+// of the vector's PLAIN column slices and hybrid-stream seeds, issued n_ring-1 vectors ahead.
 
-__device__ __forceinline__ size_t stage_bytes(const QueryDesc& q) {
-  return size_t(q.n_stage_plain) * stage_plain_bytes() + size_t(q.n_stage_seeds) * stage_seed_bytes();
+struct VecCtx {
+  const QueryDesc* q;
+  const ChunkDesc* chunks;  // [n_slots] of the row group
+  const LeafRt* lrt;        // [n_leaves]
+  const uint8_t* slotmem;   // ring slot of this vector (PLAIN slices, then seeds)
+  uint32_t r0;              // first row of the vector inside the row group
+  uint32_t n_rows;          // rows of the row group
+  uint32_t chunk;           // index of the vector's first 128-row chunk inside the row group
+  int steps;                // 32-row steps in this vector
+};
+
+// Streams the rows of one dictionary-encoded string column through the vector: next() must be called by
+// all lanes, once per step, in step order.
+struct DictReader {
+  HybCur vc, dc;
+  uint32_t vbase, lt;
+  bool absent, nulls;
+  __device__ __forceinline__ void init(const VecCtx& v, int slot, int lane) {
+    const ChunkDesc& c = v.chunks[slot];
+    absent = c.kind == CK_ABSENT;
+    nulls = !absent && c.has_nulls;
+    lt = (1u << lane) - 1u;
+    vbase = v.r0;
+    if (absent) return;
+    const uint8_t* seeds = v.slotmem + size_t(v.q->n_stage_plain) * v.q->vl * 8;
+    const int sv = v.q->slot_seed_stage[slot][0], sd = v.q->slot_seed_stage[slot][1];
+    if (nulls) vbase = hc_init(dc, c.def_runs, c.def, nullptr, sd >= 0 ? reinterpret_cast<const Seed*>(seeds) + sd : c.def_seeds + v.chunk);
+    hc_init(vc, c.runs, c.values, c.lut, sv >= 0 ? reinterpret_cast<const Seed*>(seeds) + sv : c.seeds + v.chunk);
+  }
+  // global dictionary id of row r (this lane's row of the current step), kNullIdx for NULL / out of range
+  __device__ __forceinline__ uint32_t next(uint32_t r, uint32_t n_rows) {
+    if (absent) return kNullIdx;
+    bool valid = r < n_rows;
+    uint32_t ord = r;
+    if (nulls) {
+      if (valid) valid = hc_get(dc, r) != 0;
+      unsigned m = __ballot_sync(FULL, valid);
+      ord = vbase + __popc(m & lt);
+      vbase += __popc(m);
+    }
+    return valid ? hc_get(vc, ord) : kNullIdx;
+  }
+};
+
+// Same for a numeric column: raw 8 bytes per row (0 for NULL) + null flag.
+struct NumReader {
+  HybCur vc, dc;
+  const long long* staged;  // shared-memory slice indexed by (row - r0), or nullptr
+  const long long* vals;
+  const long long* dict64;
+  uint32_t vbase, lt, r0;
+  uint8_t mode;  // 0 absent, 1 plain direct (staged or global), 2 cursor path
+  bool nulls, dict;
+  __device__ __forceinline__ void init(const VecCtx& v, int slot, int lane) {
+    const ChunkDesc& c = v.chunks[slot];
+    r0 = v.r0;
+    lt = (1u << lane) - 1u;
+    staged = nullptr;
+    if (c.kind == CK_ABSENT) { mode = 0; return; }
+    vals = reinterpret_cast<const long long*>(c.values);
+    if (c.kind == CK_PLAIN64 && !c.has_nulls) {
+      mode = 1;
+      const int p = v.q->slot_plain_stage[slot];
+      if (p >= 0) staged = reinterpret_cast<const long long*>(v.slotmem + size_t(p) * v.q->vl * 8);
+      return;
+    }
+    mode = 2;
+    nulls = c.has_nulls;
+    dict = c.kind == CK_DICT64;
+    dict64 = reinterpret_cast<const long long*>(c.dict64);
+    vbase = v.r0;
+    const uint8_t* seeds = v.slotmem + size_t(v.q->n_stage_plain) * v.q->vl * 8;
+    const int sv = v.q->slot_seed_stage[slot][0], sd = v.q->slot_seed_stage[slot][1];
+    if (nulls) vbase = hc_init(dc, c.def_runs, c.def, nullptr, sd >= 0 ? reinterpret_cast<const Seed*>(seeds) + sd : c.def_seeds + v.chunk);
+    if (dict) hc_init(vc, c.runs, c.values, nullptr, sv >= 0 ? reinterpret_cast<const Seed*>(seeds) + sv : c.seeds + v.chunk);
+  }
+  __device__ __forceinline__ long long next(uint32_t r, uint32_t n_rows, bool& null) {
+    if (mode == 1) {
+      null = r >= n_rows;
+      if (null) return 0;
+      return staged ? staged[r - r0] : __ldg(vals + r);
+    }
+    if (mode == 0) { null = true; return 0; }
+    bool valid = r < n_rows;
+    uint32_t ord = r;
+    if (nulls) {
+      if (valid) valid = hc_get(dc, r) != 0;
+      unsigned m = __ballot_sync(FULL, valid);
+      ord = vbase + __popc(m & lt);
+      vbase += __popc(m);
+    }
+    null = !valid;
+    if (!valid) return 0;
+    return dict ? __ldg(dict64 + hc_get(vc, ord)) : __ldg(vals + ord);
+  }
+};
+
+// Per-warp shared-memory region (offsets precomputed by the host in QueryDesc.wr_*).
+struct WarpMem {
+  uint64_t* full;            // [n_ring] mbarriers
+  uint8_t* ring;             // [n_ring][slot_bytes]
+  uint32_t* act;             // [vl/32] selection ballot per step
+  uint32_t* leafw;           // [vl] per-row leaf bits (FK_PROGRAM only)
+  uint32_t* slotv;           // [vl] table slot per row
+  unsigned long long* keyw;  // [key_words][vl] packed key words (hash mode)
+  long long* tmp1;           // [vl] expression temporaries
+  long long* tmp2;
+  long long* acc;            // [kMaxAggs][32] per-lane partial of every aggregate
+  unsigned long long* lastkw;  // [kMaxKeyWords][32] hash mode: last key of each lane ...
+  uint32_t* lastslot;        // [32] ... and its slot
+  uint32_t* cnt;             // [32] per-lane pending row count of the running group
+  unsigned long long* selected;  // [1] selected rows seen by this warp
+};
+
+__device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
+  WarpMem m;
+  m.full = reinterpret_cast<uint64_t*>(base);
+  m.ring = base + q.wr_ring;
+  m.act = reinterpret_cast<uint32_t*>(base + q.wr_act);
+  m.leafw = reinterpret_cast<uint32_t*>(base + q.wr_leaf);
+  m.slotv = reinterpret_cast<uint32_t*>(base + q.wr_slot);
+  m.keyw = reinterpret_cast<unsigned long long*>(base + q.wr_keyw);
+  m.tmp1 = reinterpret_cast<long long*>(base + q.wr_tmp1);
+  m.tmp2 = reinterpret_cast<long long*>(base + q.wr_tmp2);
+  m.acc = reinterpret_cast<long long*>(base + q.wr_acc);
+  m.lastkw = reinterpret_cast<unsigned long long*>(base + q.wr_acc + size_t(kMaxAggs) * 32 * 8);
+  m.selected = m.lastkw + size_t(kMaxKeyWords) * 32;
+  m.lastslot = reinterpret_cast<uint32_t*>(m.selected + 2);
+  m.cnt = m.lastslot + 32;
+  return m;
 }
 
-template <int KW>
-__global__ void __launch_bounds__(NT + 32) k_scan(const QueryDesc* __restrict__ qp) {
-  extern __shared__ __align__(128) uint8_t ring[];
+// lane 0: fill ring slot `rs` with vector `vec`
+__device__ __forceinline__ void issue_vector(const QueryDesc& q, const WarpMem& m, uint32_t vec, int rs) {
+  const int rg = find_rg(q.rg_first_tile, q.n_rg, vec);
+  const uint32_t vec_in_rg = vec - __ldg(&q.rg_first_tile[rg]);
+  const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
+  const uint32_t r0 = vec_in_rg * q.vl;
+  const uint32_t n = min(uint32_t(q.vl), n_rows - r0);
+  const uint32_t chunk = r0 / kIndexRows;
+  const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
+  uint8_t* dst = m.ring + size_t(rs) * q.slot_bytes;
+  const uint32_t plain_sz = (n * 8u + 15u) & ~15u;
+  uint32_t bytes = 0;
+  for (int p = 0; p < q.n_stage_plain; p++) {
+    const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
+    if (c.kind == CK_PLAIN64 && !c.has_nulls) bytes += plain_sz;
+  }
+  for (int t = 0; t < q.n_stage_seeds; t++) {
+    const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
+    const bool present = q.stage_seed_is_def[t] ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
+    if (present) bytes += uint32_t(sizeof(Seed));
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot vs. the async writes
+  mbar_expect_tx(&m.full[rs], bytes);
+  for (int p = 0; p < q.n_stage_plain; p++) {
+    const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
+    if (c.kind == CK_PLAIN64 && !c.has_nulls) bulk_g2s(dst + size_t(p) * q.vl * 8, c.values + size_t(r0) * 8, plain_sz, &m.full[rs]);
+  }
+  uint8_t* seed_base = dst + size_t(q.n_stage_plain) * q.vl * 8;
+  for (int t = 0; t < q.n_stage_seeds; t++) {
+    const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
+    const bool is_def = q.stage_seed_is_def[t];
+    const bool present = is_def ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
+    if (present) bulk_g2s(seed_base + size_t(t) * sizeof(Seed), (is_def ? c.def_seeds : c.seeds) + chunk, uint32_t(sizeof(Seed)), &m.full[rs]);
+  }
+}
+
+// ---- selection -------------------------------------------------------------------------------------------
+// act[s] = ballot over the 32 rows of step s that pass the predicate.
+__device__ __noinline__ uint32_t vec_selection(const VecCtx& v, const WarpMem& m, int lane) {
+  const QueryDesc& q = *v.q;
+  const int steps = v.steps;
+  for (int s = lane; s < steps; s += 32) {
+    const uint32_t first = v.r0 + uint32_t(s) * 32;
+    const uint32_t left = v.n_rows > first ? v.n_rows - first : 0;
+    m.act[s] = left >= 32 ? FULL : ((1u << left) - 1u);  // rows inside the row group
+  }
+  __syncwarp();
+  if (q.n_filter_prog == 0) {
+    uint32_t any = 0;
+    #pragma unroll 1
+    for (int s = 0; s < steps; s++) any |= m.act[s];
+    return any;
+  }
+  const bool prog = q.filter_kind == FK_PROGRAM;
+  const bool is_or = q.filter_kind == FK_OR;
+  if (prog) {
+    for (int i = lane; i < q.vl; i += 32) m.leafw[i] = 0;
+  } else if (is_or) {
+    // disjunction: start from nothing selected, remember the in-range mask in leafw
+    for (int s = lane; s < steps; s += 32) {
+      m.leafw[s] = m.act[s];
+      m.act[s] = 0;
+    }
+  }
+  __syncwarp();
+  for (int l = 0; l < q.n_leaves; l++) {
+    const LeafDesc& ld = q.leaves[l];
+    const LeafRt& rt = v.lrt[l];
+    if (rt.mode != LM_EVAL) {
+      const bool all = rt.mode == LM_ALL;
+      if (prog) {
+        if (all)
+          for (int i = lane; i < q.vl; i += 32) m.leafw[i] |= 1u << l;
+      } else if (is_or) {
+        if (all)
+          for (int s = lane; s < steps; s += 32) m.act[s] = m.leafw[s];
+      } else if (!all) {
+        for (int s = lane; s < steps; s += 32) m.act[s] = 0;
+      }
+      __syncwarp();
+      continue;
+    }
+    if (q.slot_type[ld.slot] == ST_DICT) {
+      DictReader rd;
+      rd.init(v, ld.slot, lane);
+      const uint8_t* lut = rt.lut;
+      const uint32_t nullres = rt.null_result;
+      #pragma unroll 1
+      for (int s = 0; s < steps; s++) {
+        const uint32_t r = v.r0 + uint32_t(s) * 32 + lane;
+        const uint32_t gid = rd.next(r, v.n_rows);
+        const bool res = r < v.n_rows && ((gid == kNullIdx) ? nullres : uint32_t(__ldg(lut + gid))) != 0;
+        if (prog) {
+          if (res) m.leafw[s * 32 + lane] |= 1u << l;
+        } else {
+          const unsigned b = __ballot_sync(FULL, res);
+          if (lane == 0) m.act[s] = is_or ? (m.act[s] | b) : (m.act[s] & b);
+        }
+      }
+    } else {
+      NumReader rd;
+      rd.init(v, ld.slot, lane);
+      const bool f64col = q.slot_type[ld.slot] == ST_F64;
+      const uint8_t op = ld.op;
+      const bool cf = ld.cmp_float;
+      const long long li = ld.lit_i;
+      const double lf = ld.lit_f;
+      #pragma unroll 1
+      for (int s = 0; s < steps; s++) {
+        const uint32_t r = v.r0 + uint32_t(s) * 32 + lane;
+        bool null;
+        const long long bits = rd.next(r, v.n_rows, null);
+        bool res = false;
+        if (!null) res = cf ? cmp_f64(op, f64col ? __longlong_as_double(bits) : double(bits), lf) : cmp_i64(op, bits, li);
+        if (prog) {
+          if (res) m.leafw[s * 32 + lane] |= 1u << l;
+        } else {
+          const unsigned b = __ballot_sync(FULL, res);
+          if (lane == 0) m.act[s] = is_or ? (m.act[s] | b) : (m.act[s] & b);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (prog) {
+    #pragma unroll 1
+    for (int s = 0; s < steps; s++) {
+      const bool res = eval_filter(q, m.leafw[s * 32 + lane]);
+      const unsigned b = __ballot_sync(FULL, res);
+      if (lane == 0) m.act[s] &= b;
+    }
+    __syncwarp();
+  }
+  uint32_t any = 0;
+  #pragma unroll 1
+  for (int s = 0; s < steps; s++) any |= m.act[s];
+  return any;
+}
+
+// ---- aggregate input vector -------------------------------------------------------------------------------
+// Evaluates an aggregate expression over the vector into out[] (raw 8-byte values, NULL slots 0).
+__device__ __noinline__ void vec_eval_expr(const VecCtx& v, const WarpMem& m, const AggDesc& a, int lane, long long* out) {
+  const QueryDesc& q = *v.q;
+  long long* stack[3] = {out, m.tmp2, nullptr};
+  // operand i of the stack lives in: 0 -> out, 1 -> tmp2, 2 -> acc scratch is not available: depth 3 uses leafw+slot? (host limits depth to 2 here)
+  int sp = 0;
+  for (int p = a.prog_off; p < a.prog_off + a.prog_len; p++) {
+    const ProgOp& o = q.prog[p];
+    if (o.op == PO_LOAD) {
+      NumReader rd;
+      rd.init(v, o.slot, lane);
+      long long* dst = stack[sp];
+      #pragma unroll 1
+      for (int s = 0; s < v.steps; s++) {
+        bool null;
+        dst[s * 32 + lane] = rd.next(v.r0 + uint32_t(s) * 32 + lane, v.n_rows, null);
+      }
+      sp++;
+    } else if (o.op == PO_CONST) {
+      long long* dst = stack[sp];
+      #pragma unroll 1
+      for (int s = 0; s < v.steps; s++) dst[s * 32 + lane] = o.imm;
+      sp++;
+    } else {
+      long long* l = stack[sp - 2];
+      const long long* r = stack[sp - 1];
+      #pragma unroll 1
+      for (int s = 0; s < v.steps; s++) l[s * 32 + lane] = apply_arith(o.op, a.is_float, l[s * 32 + lane], r[s * 32 + lane]);
+      sp--;
+    }
+  }
+}
+
+// ---- table slot per row ----------------------------------------------------------------------------------
+__device__ __noinline__ void vec_slots_dense(const VecCtx& v, const WarpMem& m, int lane) {
+  const QueryDesc& q = *v.q;
+  bool first = true;
+  for (int k = 0; k < q.n_keys; k++) {
+    const KeyDesc& kd = q.keys[k];
+    DictReader rd;
+    rd.init(v, kd.slot, lane);
+    const uint32_t stride = kd.dense_stride;
+#pragma unroll 1
+    for (int s = 0; s < v.steps; s++) {
+      const uint32_t gid = rd.next(v.r0 + uint32_t(s) * 32 + lane, v.n_rows);
+      const uint32_t add = (gid == kNullIdx) ? 0u : (gid + 1u) * stride;
+      m.slotv[s * 32 + lane] = first ? add : m.slotv[s * 32 + lane] + add;
+    }
+    first = false;
+  }
+  if (first)
+    for (int s = 0; s < v.steps; s++) m.slotv[s * 32 + lane] = 0;  // no keys: one global group
+  __syncwarp();
+}
+
+// Hash mode: packed key words per row in shared memory, then find-or-insert (with a per-lane
+// last-key cache in m.lastkw: sorted parts repeat the previous row's key most of the time).
+__device__ __noinline__ bool vec_slots_hash(const VecCtx& v, const WarpMem& m, int lane) {
+  const QueryDesc& q = *v.q;
+  const int W = q.key_words;
+  bool overflow = false;
+  for (int w = 0; w < W; w++)
+    for (int s = 0; s < v.steps; s++) m.keyw[size_t(w) * q.vl + s * 32 + lane] = 0;
+  for (int k = 0; k < q.n_keys; k++) {
+    const KeyDesc& kd = q.keys[k];
+    unsigned long long* kwp = m.keyw + size_t(kd.word) * q.vl;
+    if (kd.is_int64) {
+      NumReader rd;
+      rd.init(v, kd.slot, lane);
+#pragma unroll 1
+      for (int s = 0; s < v.steps; s++) {
+        bool null;
+        // NULL and 0 hash alike in the reference (dynparquet/hashed.go:254-262): NULL slots hold 0
+        kwp[s * 32 + lane] = (unsigned long long)rd.next(v.r0 + uint32_t(s) * 32 + lane, v.n_rows, null);
+      }
+    } else {
+      DictReader rd;
+      rd.init(v, kd.slot, lane);
+      const uint32_t shift = kd.shift;
+#pragma unroll 1
+      for (int s = 0; s < v.steps; s++) {
+        const uint32_t gid = rd.next(v.r0 + uint32_t(s) * 32 + lane, v.n_rows);
+        const unsigned long long code = (gid == kNullIdx) ? 0ull : (unsigned long long)gid + 1ull;
+        kwp[s * 32 + lane] |= code << shift;
+      }
+    }
+  }
+  unsigned long long* lastkw = m.lastkw + lane;  // [kMaxKeyWords][32]
+  uint32_t last_slot = m.lastslot[lane];
+#pragma unroll 1
+  for (int s = 0; s < v.steps; s++) {
+    uint32_t sl = kNoSlot;
+    if ((m.act[s] >> lane) & 1u) {
+      unsigned long long key[kMaxKeyWords];
+      bool same = last_slot != kNoSlot;
+#pragma unroll
+      for (int w = 0; w < kMaxKeyWords; w++) {
+        key[w] = (w < W) ? m.keyw[size_t(w) * q.vl + s * 32 + lane] : 0ull;
+        same &= (w >= W) || key[w] == lastkw[w * 32];
+      }
+      if (!same) {
+        last_slot = hash_find_or_insert<kMaxKeyWords>(q, key, &overflow);
+#pragma unroll
+        for (int w = 0; w < kMaxKeyWords; w++)
+          if (w < W) lastkw[w * 32] = key[w];
+      }
+      sl = last_slot;
+    }
+    m.slotv[s * 32 + lane] = sl;
+  }
+  m.lastslot[lane] = last_slot;
+  __syncwarp();
+  return overflow;
+}
+
+// ---- rows-per-group counter (also every Count aggregate, aggregate.go:937-950) ------------------------------
+// Returns the running group after the vector; m.cnt[lane] carries this lane's pending row count.
+__device__ __noinline__ uint32_t vec_count_rows(const VecCtx& v, const WarpMem& m, int lane, uint32_t cur_slot) {
+  const QueryDesc& q = *v.q;
+  uint32_t cs = cur_slot;
+  uint32_t cnt = m.cnt[lane];
+  uint32_t selected = 0;
+#pragma unroll 1
+  for (int s = 0; s < v.steps; s++) {
+    const unsigned amask = m.act[s];
+    if (amask == 0) continue;
+    const bool active = (amask >> lane) & 1u;
+    const uint32_t sl = m.slotv[s * 32 + lane];
+    selected += __popc(amask);
+    const uint32_t s0 = __shfl_sync(FULL, sl, __ffs(amask) - 1);
+    const bool uni = __all_sync(FULL, !active || sl == s0);
+    if (!uni) {
+      if (cs != kNoSlot) {
+        const uint32_t tt = __reduce_add_sync(FULL, cnt);
+        if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+        cnt = 0;
+        cs = kNoSlot;
+      }
+      mixed_rows(q.t_rows, sl, active, lane);
+    } else {
+      if (s0 != cs) {
+        if (cs != kNoSlot) {
+          const uint32_t tt = __reduce_add_sync(FULL, cnt);
+          if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+          cnt = 0;
+        }
+        cs = s0;
+      }
+      cnt += active ? 1u : 0u;
+    }
+  }
+  m.cnt[lane] = cnt;
+  if (lane == 0) m.selected[0] += selected;
+  return cs;
+}
+
+// ---- one aggregate over the vector: per-lane partial while the warp stays in one group ------------------------
+__device__ __noinline__ void vec_aggregate(const VecCtx& v, const WarpMem& m, int a, int lane, uint32_t cur_slot) {
+  const QueryDesc& q = *v.q;
+  const AggDesc& ad = q.aggs[a];
+  const uint8_t func = ad.func;
+  const bool isf = ad.is_float;
+  const long long ident = agg_identity(func, isf);
+  long long* cells = q.t_agg[a];
+  // input: a column read in place, or an expression evaluated into tmp1
+  const bool simple = ad.prog_len == 1 && q.prog[ad.prog_off].op == PO_LOAD;
+  NumReader rd;
+  if (simple) rd.init(v, q.prog[ad.prog_off].slot, lane);
+  else vec_eval_expr(v, m, ad, lane, m.tmp1);
+  __syncwarp();
+  uint32_t cs = cur_slot;
+  long long part = m.acc[a * 32 + lane];
+#pragma unroll 1
+  for (int s = 0; s < v.steps; s++) {
+    long long val;
+    if (simple) {
+      bool null;
+      val = rd.next(v.r0 + uint32_t(s) * 32 + lane, v.n_rows, null);  // every step: the cursor must see all rows
+    } else {
+      val = m.tmp1[s * 32 + lane];
+    }
+    const unsigned amask = m.act[s];
+    if (amask == 0) continue;
+    const bool active = (amask >> lane) & 1u;
+    const uint32_t sl = m.slotv[s * 32 + lane];
+    const uint32_t s0 = __shfl_sync(FULL, sl, __ffs(amask) - 1);
+    const bool uni = __all_sync(FULL, !active || sl == s0);
+    if (!uni) {
+      if (cs != kNoSlot) {
+        flush_agg(func, isf, cells + cs, part, lane);
+        part = ident;
+        cs = kNoSlot;
+      }
+      mixed_agg(func, isf, cells, sl, active, val, lane);
+    } else {
+      if (s0 != cs) {
+        if (cs != kNoSlot) {
+          flush_agg(func, isf, cells + cs, part, lane);
+          part = ident;
+        }
+        cs = s0;
+      }
+      if (active) part = agg_combine(func, isf, part, val);
+    }
+  }
+  m.acc[a * 32 + lane] = part;
+}
+
+__global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
+  extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ QueryDesc sq;
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(qp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
@@ -626,263 +1104,69 @@ __global__ void __launch_bounds__(NT + 32) k_scan(const QueryDesc* __restrict__ 
   __syncthreads();
   const QueryDesc& q = sq;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int S = q.n_stages;
-  const size_t sbytes = stage_bytes(q);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; s++) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], NWARP);
-    }
+  const WarpMem m = warp_mem(q, dyn + size_t(warp) * q.wr_bytes);
+  const int D = q.n_ring;
+  if (lane == 0) {
+    for (int s = 0; s < D; s++) mbar_init(&m.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    m.selected[0] = 0;
   }
-  __syncthreads();
+  m.cnt[lane] = 0;
+  m.lastslot[lane] = kNoSlot;
+  for (int a = 0; a < q.n_aggs; a++) m.acc[a * 32 + lane] = agg_identity(q.aggs[a].func, q.aggs[a].is_float);
+  __syncwarp();
 
-  if (warp == NWARP) {
-    // ================= producer warp: keeps the ring full =================
-    if (lane == 0 && S > 0) {
-      uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x, it++) {
-        const int st = int(it % uint32_t(S));
-        const uint32_t ph = (it / uint32_t(S)) & 1u;
-        mbar_wait(&empty_bar[st], ph ^ 1u);
-        const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
-        const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
-        const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
-        const uint32_t r0 = tile_in_rg * TILE;
-        const uint32_t n = min(uint32_t(TILE), n_rows - r0);
-        const uint32_t n_chunks = (n + kIndexRows - 1) / kIndexRows;
-        const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
-        uint8_t* stage = ring + size_t(st) * sbytes;
-        // pass 1: bytes of this stage
-        uint32_t bytes = 0;
-        const uint32_t plain_sz = (n * 8u + 15u) & ~15u;
-        const uint32_t seed_sz = n_chunks * uint32_t(sizeof(Seed));
-        for (int p = 0; p < q.n_stage_plain; p++) {
-          const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
-          if (c.kind == CK_PLAIN64 && !c.has_nulls) bytes += plain_sz;
-        }
-        for (int t = 0; t < q.n_stage_seeds; t++) {
-          const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
-          const bool present = q.stage_seed_is_def[t] ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
-          if (present) bytes += seed_sz;
-        }
-        mbar_expect_tx(&full_bar[st], bytes);
-        // pass 2: issue the copies
-        for (int p = 0; p < q.n_stage_plain; p++) {
-          const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
-          if (c.kind == CK_PLAIN64 && !c.has_nulls)
-            bulk_g2s(stage + size_t(p) * stage_plain_bytes(), c.values + size_t(r0) * 8, plain_sz, &full_bar[st]);
-        }
-        uint8_t* seed_base = stage + size_t(q.n_stage_plain) * stage_plain_bytes();
-        for (int t = 0; t < q.n_stage_seeds; t++) {
-          const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
-          const bool is_def = q.stage_seed_is_def[t];
-          const bool present = is_def ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
-          if (present)
-            bulk_g2s(seed_base + size_t(t) * stage_seed_bytes(), (is_def ? c.def_seeds : c.seeds) + size_t(tile_in_rg) * NWARP, seed_sz,
-                     &full_bar[st]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ================= consumer warps =================
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;  // global warp id
+  const uint32_t GW = gridDim.x * (blockDim.x >> 5);
   const bool dense = q.table_mode == TM_DENSE;
-  // warp-uniform running group + per-lane partial aggregates carried across chunks
-  uint32_t cur_slot = kNoSlot;
-  uint32_t cur_cnt = 0;
-  long long acc[kMaxAggs];
-#pragma unroll 1
-  for (int a = 0; a < q.n_aggs; a++) acc[a] = agg_identity(q.aggs[a].func, q.aggs[a].is_float);
-  unsigned long long selected_local = 0;
+  uint32_t cur_slot = kNoSlot;  // warp-uniform running group
   bool overflow = false;
-  // hash mode: last key -> slot of this lane
-  unsigned long long last_kw[KW];
-  uint32_t last_slot = kNoSlot;
-#pragma unroll
-  for (int w = 0; w < KW; w++) last_kw[w] = ~0ull;
 
+  // prologue: fill the ring
+  if (lane == 0)
+    for (int d = 0; d < D - 1; d++) {
+      const uint32_t vec = gw + uint32_t(d) * GW;
+      if (vec < q.n_tiles) issue_vector(q, m, vec, d);
+    }
   uint32_t it = 0;
-  for (uint32_t tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x, it++) {
-    const int st = S > 0 ? int(it % uint32_t(S)) : 0;
-    const uint32_t ph = S > 0 ? (it / uint32_t(S)) & 1u : 0;
-    const int rg = find_rg(q.rg_first_tile, q.n_rg, tile);
-    const uint32_t tile_in_rg = tile - __ldg(&q.rg_first_tile[rg]);
-    TileCtx t;
-    t.q = &q;
-    t.n_rows = __ldg(&q.rg_rows[rg]);
-    t.tile_r0 = tile_in_rg * TILE;
-    t.chunk_in_tile = uint32_t(warp);
-    t.chunk = tile_in_rg * NWARP + warp;  // 128-row chunk index inside the row group
-    t.c0 = t.chunk * kIndexRows;
-    t.chunks = q.chunks + size_t(rg) * q.n_slots;
-    t.lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
-    t.stage = S > 0 ? ring + size_t(st) * sbytes : nullptr;
-    if (S > 0) mbar_wait(&full_bar[st], ph);
+  for (uint32_t vec = gw; vec < q.n_tiles; vec += GW, it++) {
+    const int rs = int(it % uint32_t(D));
+    if (lane == 0) {
+      const uint32_t ahead = vec + uint32_t(D - 1) * GW;
+      if (ahead < q.n_tiles) issue_vector(q, m, ahead, int((it + uint32_t(D) - 1) % uint32_t(D)));
+    }
+    const int rg = find_rg(q.rg_first_tile, q.n_rg, vec);
+    VecCtx v;
+    v.q = &q;
+    v.n_rows = __ldg(&q.rg_rows[rg]);
+    v.r0 = (vec - __ldg(&q.rg_first_tile[rg])) * q.vl;
+    v.chunk = v.r0 / kIndexRows;
+    v.chunks = q.chunks + size_t(rg) * q.n_slots;
+    v.lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+    v.slotmem = m.ring + size_t(rs) * q.slot_bytes;
+    v.steps = int((min(uint32_t(q.vl), v.n_rows - v.r0) + 31) / 32);
+    mbar_wait(&m.full[rs], (it / uint32_t(D)) & 1u);
 
-    if (t.c0 < t.n_rows) {
-      // ---- predicate -> active mask per step ----------------------------------------------------
-      const uint32_t actbits = chunk_selection(t, lane);
-      if (__ballot_sync(FULL, actbits != 0) != 0) {
-        // ---- group key per row -------------------------------------------------------------------
-        unsigned long long kw[KW][STEPS];
-#pragma unroll
-        for (int w = 0; w < KW; w++)
-#pragma unroll
-          for (int j = 0; j < STEPS; j++) kw[w][j] = 0;
-        for (int k = 0; k < q.n_keys; k++) {
-          const KeyDesc& kd = q.keys[k];
-          if (kd.is_int64) {
-            long long v[STEPS];
-            uint32_t nm;
-            tile_num(t, kd.slot, lane, v, nm);
-            // NULL and 0 hash alike in the reference (dynparquet/hashed.go:254-262): NULL slots hold 0
-#pragma unroll
-            for (int w = 0; w < KW; w++)
-              if (w == kd.word)
-#pragma unroll
-                for (int j = 0; j < STEPS; j++) kw[w][j] = (unsigned long long)v[j];
-          } else {
-            uint32_t gid[STEPS];
-            tile_dict(t, kd.slot, lane, gid);
-#pragma unroll
-            for (int j = 0; j < STEPS; j++) {
-              unsigned long long code = (gid[j] == kNullIdx) ? 0ull : (unsigned long long)gid[j] + 1ull;
-              if (dense) {
-                kw[0][j] += code * kd.dense_stride;
-              } else {
-#pragma unroll
-                for (int w = 0; w < KW; w++)
-                  if (w == kd.word) kw[w][j] |= code << kd.shift;
-              }
-            }
-          }
-        }
-        // ---- table slot per row --------------------------------------------------------------------
-        uint32_t slot[STEPS];
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) {
-          slot[j] = kNoSlot;
-          if (!((actbits >> j) & 1u)) continue;
-          if (dense) {
-            slot[j] = uint32_t(kw[0][j]);
-          } else {
-            bool same = last_slot != kNoSlot;
-#pragma unroll
-            for (int w = 0; w < KW; w++) same &= (kw[w][j] == last_kw[w]);
-            if (!same) {
-              unsigned long long key[KW];
-#pragma unroll
-              for (int w = 0; w < KW; w++) key[w] = kw[w][j];
-              last_slot = hash_find_or_insert<KW>(q, key, &overflow);
-#pragma unroll
-              for (int w = 0; w < KW; w++) last_kw[w] = key[w];
-            }
-            slot[j] = last_slot;
-          }
-        }
-        // ---- step classification: empty, one group for the whole warp (uslot), or mixed -------------
-        uint32_t uslot[STEPS];   // warp-uniform: group of the step, kNoSlot when mixed or empty
-        uint32_t mixedbits = 0;  // warp-uniform: bit j set when the step's active lanes span several groups
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) {
-          bool active = (actbits >> j) & 1u;
-          unsigned amask = __ballot_sync(FULL, active);
-          uslot[j] = kNoSlot;
-          if (amask == 0) continue;
-          if (lane == 0) selected_local += __popc(amask);
-          uint32_t s = __shfl_sync(FULL, slot[j], __ffs(amask) - 1);
-          bool uni = __all_sync(FULL, !active || slot[j] == s);
-          if (uni) uslot[j] = s;
-          else mixedbits |= 1u << j;
-        }
-        // ---- rows-per-group counter (also every Count aggregate, aggregate.go:937-950) ---------------
-        {
-          uint32_t cs = cur_slot;
-#pragma unroll
-          for (int j = 0; j < STEPS; j++) {
-            bool active = (actbits >> j) & 1u;
-            if ((mixedbits >> j) & 1u) {
-              if (cs != kNoSlot) {
-                uint32_t tt = __reduce_add_sync(FULL, cur_cnt);
-                if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
-                cur_cnt = 0;
-                cs = kNoSlot;
-              }
-              mixed_rows(q.t_rows, slot[j], active, lane);
-            } else if (uslot[j] != kNoSlot) {
-              if (uslot[j] != cs) {
-                if (cs != kNoSlot) {
-                  uint32_t tt = __reduce_add_sync(FULL, cur_cnt);
-                  if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
-                  cur_cnt = 0;
-                }
-                cs = uslot[j];
-              }
-              cur_cnt += active ? 1u : 0u;
-            }
-          }
-        }
-        // ---- aggregates: per-lane partials while the warp stays in one group --------------------------
-        // (acc[] is indexed dynamically on purpose: it is touched once per chunk, the per-row work runs on `part`)
-#pragma unroll 1
-        for (int a = 0; a < q.n_aggs; a++) {
-          const AggDesc& ad = q.aggs[a];
-          if (ad.func == 4 /*count*/) continue;
-          long long v[STEPS];
-          eval_agg_values(t, ad, lane, v);
-          uint32_t cs = cur_slot;
-          long long part = acc[a];
-          const long long ident = agg_identity(ad.func, ad.is_float);
-#pragma unroll
-          for (int j = 0; j < STEPS; j++) {
-            bool active = (actbits >> j) & 1u;
-            if ((mixedbits >> j) & 1u) {
-              if (cs != kNoSlot) {
-                flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
-                part = ident;
-                cs = kNoSlot;
-              }
-              mixed_agg(ad.func, ad.is_float, q.t_agg[a], slot[j], active, v[j], lane);
-            } else if (uslot[j] != kNoSlot) {
-              if (uslot[j] != cs) {
-                if (cs != kNoSlot) {
-                  flush_agg(ad.func, ad.is_float, q.t_agg[a] + cs, part, lane);
-                  part = ident;
-                }
-                cs = uslot[j];
-              }
-              if (active) part = agg_combine(ad.func, ad.is_float, part, v[j]);
-            }
-          }
-          acc[a] = part;
-        }
-        // the running group after this chunk (identical for every aggregate by construction)
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) {
-          if ((mixedbits >> j) & 1u) cur_slot = kNoSlot;
-          else if (uslot[j] != kNoSlot) cur_slot = uslot[j];
-        }
-      }
+    if (vec_selection(v, m, lane) != 0) {
+      if (dense) vec_slots_dense(v, m, lane);
+      else overflow |= vec_slots_hash(v, m, lane);
+      const uint32_t end_slot = vec_count_rows(v, m, lane, cur_slot);
+      for (int a = 0; a < q.n_aggs; a++)
+        if (q.aggs[a].func != 4 /*count*/) vec_aggregate(v, m, a, lane, cur_slot);
+      cur_slot = end_slot;
     }
-    // this warp is done with the stage
-    if (S > 0) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[st]);
-    }
+    __syncwarp();  // every lane is done with ring slot rs before lane 0 refills it next iteration
   }
   // ---- final flush ---------------------------------------------------------------------------------
   if (cur_slot != kNoSlot) {
-    uint32_t tt = __reduce_add_sync(FULL, cur_cnt);
+    const uint32_t tt = __reduce_add_sync(FULL, m.cnt[lane]);
     if (lane == 0 && tt) atomicAdd(q.t_rows + cur_slot, (unsigned long long)tt);
-#pragma unroll 1
     for (int a = 0; a < q.n_aggs; a++) {
       if (q.aggs[a].func == 4) continue;
-      flush_agg(q.aggs[a].func, q.aggs[a].is_float, q.t_agg[a] + cur_slot, acc[a], lane);
+      flush_agg(q.aggs[a].func, q.aggs[a].is_float, q.t_agg[a] + cur_slot, m.acc[a * 32 + lane], lane);
     }
   }
-  if (lane == 0 && selected_local) atomicAdd(q.counters + 0, selected_local);
+  if (lane == 0 && m.selected[0]) atomicAdd(q.counters + 0, m.selected[0]);
   if (overflow) atomicExch(q.counters + 1, 1ull);
 }
 
@@ -1117,24 +1401,6 @@ __global__ void __launch_bounds__(NT) k_decode(ChunkDesc c, uint32_t n_chunks, i
 // host launchers
 // ======================================================================================================
 namespace {
-template <int KW>
-cudaError_t launch_scan_kw(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
-  const size_t smem = size_t(q.n_stages) * (size_t(q.n_stage_plain) * TILE * 8 + size_t(q.n_stage_seeds) * NWARP * sizeof(Seed));
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_scan<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<KW>, NT + 32, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
-  if (grid > q.n_tiles) grid = q.n_tiles;
-  k_scan<KW><<<grid, NT + 32, smem, st>>>(d_q);
-  return cudaGetLastError();
-}
 int grid_for(size_t n) {
   int blocks = int((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -1149,9 +1415,23 @@ cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st) {
 
 cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
   if (q.n_tiles == 0) return cudaSuccess;
-  if (q.table_mode == TM_DENSE || q.key_words <= 1) return launch_scan_kw<1>(d_q, q, sm_count, st);
-  if (q.key_words == 2) return launch_scan_kw<2>(d_q, q, sm_count, st);
-  return launch_scan_kw<kMaxKeyWords>(d_q, q, sm_count, st);
+  const int warps = kVecThreads / 32;
+  const size_t smem = size_t(q.wr_bytes) * warps;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan, kVecThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
+  const uint32_t need = (q.n_tiles + warps - 1) / warps;
+  if (grid > need) grid = need;
+  k_scan<<<grid, kVecThreads, smem, st>>>(d_q);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {

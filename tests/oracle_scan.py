@@ -19,7 +19,7 @@ class OracleScan(pp.GPUScan):
 
     def Execute(self, ctx, pool=None) -> None:
         plan, keep = self._plan()
-        table: orc.OracleTable = self.engine.tables[self.table_name]
+        table: orc.OracleTable = self.engine.tables.setdefault(self.table_name, orc.OracleTable())
         try:
             res = table.execute(plan, threads=self.threads)
         except orc.OracleError as e:
