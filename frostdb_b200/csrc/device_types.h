@@ -137,6 +137,7 @@ struct QueryDesc {
   int32_t n_out;         // rows plan: projected columns
   int32_t n_stage_plain, n_stage_seeds, n_stages;  // staged PLAIN slices / seeds per vector (scan kernel)
   int32_t vl;            // rows per warp vector (scan kernel)
+  int32_t fast_ok;       // query shape qualifies for the fused register-only pass (vec_fast)
   int32_t n_ring;        // ring depth per warp
   uint32_t slot_bytes;   // bytes of one ring slot
   uint32_t wr_bytes;     // per-warp shared-memory region: size and section offsets

@@ -668,6 +668,22 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     }
     qd.vl = vl;
     qd.n_ring = ring;
+    // fused fast path: conjunction of numeric leaves, dense dictionary keys, simple aggregates
+    bool fast = qd.table_mode == TM_DENSE && (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) && qd.n_leaves <= 4 && qd.n_keys <= 3 &&
+                !getenv("FROSTGPU_NO_FAST");
+    for (int l = 0; l < qd.n_leaves && fast; l++) {
+      const LeafHost& lh = c->leaves[size_t(l)];
+      if (lh.slot >= 0 && c->slot_types[size_t(lh.slot)] == ST_DICT) fast = false;
+      if (lh.slot >= 0 && lh.lit->lit_type == FGPU_SCALAR_NULL) fast = false;
+    }
+    int stored = 0;
+    for (int a = 0; a < qd.n_aggs && fast; a++) {
+      if (qd.aggs[a].func == FGPU_AGG_COUNT) continue;
+      stored++;
+      if (!(qd.aggs[a].prog_len == 1 && qd.prog[qd.aggs[a].prog_off].op == PO_LOAD)) fast = false;
+    }
+    if (stored > 2) fast = false;
+    qd.fast_ok = fast ? 1 : 0;
   }
   return FGPU_OK;
 }

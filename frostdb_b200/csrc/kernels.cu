@@ -1093,6 +1093,172 @@ __device__ __noinline__ void vec_aggregate(const VecCtx& v, const WarpMem& m, in
   m.acc[a * 32 + lane] = part;
 }
 
+// ---- fused fast path ---------------------------------------------------------------------------------------
+// The dominant query shape runs in ONE pass over the vector with everything in registers:
+//   filter  = conjunction of <= 4 comparisons on PLAIN non-null int64/double columns (or no filter)
+//   keys    = <= 3 dictionary-string columns without NULLs in this row group, dense table
+//   aggs    = counts + <= 2 Sum/Min/Max over PLAIN non-null columns read in place
+// Eligibility of the QUERY is decided by the host (q.fast_ok); eligibility of the ROW GROUP (column
+// kinds) is checked here, and `false` sends the vector down the general vectorized path.
+constexpr int kFastLeaves = 4, kFastKeys = 3, kFastAggs = 2;
+
+__device__ __noinline__ bool vec_fast(const VecCtx& v, const WarpMem& m, int lane, uint32_t* cur_slot_io) {
+  const QueryDesc& q = *v.q;
+  const int nl = q.n_leaves, nk = q.n_keys;
+  // ---- resolve columns (warp-uniform) ----
+  const long long* lcol[kFastLeaves];
+  long long li[kFastLeaves];
+  double lf[kFastLeaves];
+  uint32_t lflags[kFastLeaves];  // 1 lt, 2 eq, 4 gt selects; 8 compare as double; 16 column is double
+#pragma unroll
+  for (int l = 0; l < kFastLeaves; l++) {
+    lcol[l] = nullptr; li[l] = 0; lf[l] = 0; lflags[l] = 0;
+    if (l >= nl) continue;
+    const LeafDesc& ld = q.leaves[l];
+    const uint8_t mode = v.lrt[l].mode;
+    if (mode == LM_NONE) {  // conjunction with an always-false leaf: nothing selected in this row group
+      return true;
+    }
+    if (mode == LM_ALL) { lflags[l] = 7u | 32u; continue; }  // always true: skip the column
+    const ChunkDesc& c = v.chunks[ld.slot];
+    const int p = q.slot_plain_stage[ld.slot];
+    if (c.kind != CK_PLAIN64 || c.has_nulls || p < 0) return false;
+    lcol[l] = reinterpret_cast<const long long*>(v.slotmem + size_t(p) * q.vl * 8);
+    li[l] = ld.lit_i;
+    lf[l] = ld.lit_f;
+    uint32_t f = 0;
+    switch (ld.op) {
+      case 1: f = 2; break;      // ==
+      case 2: f = 1 | 4; break;  // !=
+      case 3: f = 1; break;      // <
+      case 4: f = 1 | 2; break;  // <=
+      case 5: f = 4; break;      // >
+      default: f = 4 | 2; break; // >=
+    }
+    if (ld.cmp_float) f |= 8;
+    if (q.slot_type[ld.slot] == ST_F64) f |= 16;
+    lflags[l] = f;
+  }
+  HybCur kc[kFastKeys];
+  uint32_t kstride[kFastKeys];
+  bool kuse[kFastKeys];
+#pragma unroll
+  for (int k = 0; k < kFastKeys; k++) {
+    kuse[k] = false; kstride[k] = 0;
+    if (k >= nk) continue;
+    const KeyDesc& kd = q.keys[k];
+    const ChunkDesc& c = v.chunks[kd.slot];
+    if (c.kind == CK_ABSENT) continue;  // absent column: NULL for every row, contributes 0
+    if (c.kind != CK_DICT_STR || c.has_nulls) return false;
+    const int sv = q.slot_seed_stage[kd.slot][0];
+    const uint8_t* seeds = v.slotmem + size_t(q.n_stage_plain) * q.vl * 8;
+    hc_init(kc[k], c.runs, c.values, c.lut, sv >= 0 ? reinterpret_cast<const Seed*>(seeds) + sv : c.seeds + v.chunk);
+    kstride[k] = kd.dense_stride;
+    kuse[k] = true;
+  }
+  int ai[kFastAggs];
+  const long long* acol[kFastAggs];
+  uint32_t afunc[kFastAggs];  // func | isf << 8
+  long long part[kFastAggs];
+  int na = 0;
+#pragma unroll
+  for (int a = 0; a < kFastAggs; a++) { ai[a] = -1; acol[a] = nullptr; afunc[a] = 0; part[a] = 0; }
+  for (int a = 0; a < q.n_aggs; a++) {
+    const AggDesc& ad = q.aggs[a];
+    if (ad.func == 4) continue;
+    const int slot = q.prog[ad.prog_off].slot;
+    const ChunkDesc& c = v.chunks[slot];
+    const int p = q.slot_plain_stage[slot];
+    if (c.kind != CK_PLAIN64 || c.has_nulls || p < 0) return false;
+    const long long* col = reinterpret_cast<const long long*>(v.slotmem + size_t(p) * q.vl * 8);
+#pragma unroll
+    for (int x = 0; x < kFastAggs; x++)
+      if (x == na) { ai[x] = a; acol[x] = col; afunc[x] = uint32_t(ad.func) | (uint32_t(ad.is_float) << 8); part[x] = m.acc[a * 32 + lane]; }
+    na++;
+  }
+  // ---- the pass ----
+  uint32_t cs = *cur_slot_io;
+  uint32_t cnt = m.cnt[lane];
+  uint32_t selected = 0;
+  const uint32_t n_in = min(uint32_t(q.vl), v.n_rows - v.r0);
+#pragma unroll 1
+  for (int s = 0; s < v.steps; s++) {
+    const uint32_t idx = uint32_t(s) * 32 + lane;
+    bool act = idx < n_in;
+#pragma unroll
+    for (int l = 0; l < kFastLeaves; l++) {
+      if (l >= nl || (lflags[l] & 32u)) continue;
+      const long long x = act ? lcol[l][idx] : 0;
+      bool lt, eq;
+      if (lflags[l] & 8u) {
+        const double d = (lflags[l] & 16u) ? __longlong_as_double(x) : double(x);
+        lt = d < lf[l];
+        eq = d == lf[l];
+        const bool gt = d > lf[l];  // NaN: none of the three
+        act = act && ((lt && (lflags[l] & 1u)) || (eq && (lflags[l] & 2u)) || (gt && (lflags[l] & 4u)));
+      } else {
+        lt = x < li[l];
+        eq = x == li[l];
+        act = act && ((lt && (lflags[l] & 1u)) || (eq && (lflags[l] & 2u)) || (!lt && !eq && (lflags[l] & 4u)));
+      }
+    }
+    const unsigned amask = __ballot_sync(FULL, act);
+    if (amask == 0) continue;
+    uint32_t slot = 0;
+    const uint32_t r = v.r0 + idx;
+#pragma unroll
+    for (int k = 0; k < kFastKeys; k++)
+      if (kuse[k] && act) slot += (hc_get(kc[k], r) + 1u) * kstride[k];
+    selected += __popc(amask);
+    const uint32_t s0 = __shfl_sync(FULL, slot, __ffs(amask) - 1);
+    const bool uni = __all_sync(FULL, !act || slot == s0);
+    if (uni) {
+      if (s0 != cs) {
+        if (cs != kNoSlot) {
+          const uint32_t tt = __reduce_add_sync(FULL, cnt);
+          if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+          cnt = 0;
+#pragma unroll
+          for (int x = 0; x < kFastAggs; x++)
+            if (x < na) {
+              flush_agg(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, q.t_agg[ai[x]] + cs, part[x], lane);
+              part[x] = agg_identity(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0);
+            }
+        }
+        cs = s0;
+      }
+      cnt += act ? 1u : 0u;
+#pragma unroll
+      for (int x = 0; x < kFastAggs; x++)
+        if (x < na && act) part[x] = agg_combine(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, part[x], acol[x][idx]);
+    } else {
+      if (cs != kNoSlot) {
+        const uint32_t tt = __reduce_add_sync(FULL, cnt);
+        if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+        cnt = 0;
+#pragma unroll
+        for (int x = 0; x < kFastAggs; x++)
+          if (x < na) {
+            flush_agg(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, q.t_agg[ai[x]] + cs, part[x], lane);
+            part[x] = agg_identity(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0);
+          }
+        cs = kNoSlot;
+      }
+      mixed_rows(q.t_rows, slot, act, lane);
+#pragma unroll
+      for (int x = 0; x < kFastAggs; x++)
+        if (x < na) mixed_agg(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, q.t_agg[ai[x]], slot, act, act ? acol[x][idx] : 0, lane);
+    }
+  }
+  m.cnt[lane] = cnt;
+#pragma unroll
+  for (int x = 0; x < kFastAggs; x++)
+    if (x < na) m.acc[ai[x] * 32 + lane] = part[x];
+  if (lane == 0) m.selected[0] += selected;
+  *cur_slot_io = cs;
+  return true;
+}
+
 __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ QueryDesc sq;
@@ -1147,7 +1313,9 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
     v.steps = int((min(uint32_t(q.vl), v.n_rows - v.r0) + 31) / 32);
     mbar_wait(&m.full[rs], (it / uint32_t(D)) & 1u);
 
-    if (vec_selection(v, m, lane) != 0) {
+    if (q.fast_ok && vec_fast(v, m, lane, &cur_slot)) {
+      // handled in one fused pass
+    } else if (vec_selection(v, m, lane) != 0) {
       if (dense) vec_slots_dense(v, m, lane);
       else overflow |= vec_slots_hash(v, m, lane);
       const uint32_t end_slot = vec_count_rows(v, m, lane, cur_slot);
