@@ -662,6 +662,8 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       qd.wr_tmp1 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
       qd.wr_tmp2 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
       qd.wr_acc = uint32_t(off); off = r128(off + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4 + 32 * 4);
+      qd.wr_cdesc = uint32_t(off); off = r128(off + size_t(std::max(qd.n_slots, 1)) * sizeof(ChunkDesc));
+      qd.wr_clrt = uint32_t(off); off = r128(off + size_t(std::max(qd.n_leaves, 1)) * sizeof(LeafRt));
       qd.wr_bytes = uint32_t(off);
       if (size_t(qd.wr_bytes) * (kVecThreads / 32) <= 200 * 1024 || vl == 128) break;
       vl /= 2;  // many staged columns / wide keys: shorter vectors

@@ -725,6 +725,8 @@ struct WarpMem {
   uint32_t* lastslot;        // [32] ... and its slot
   uint32_t* cnt;             // [32] per-lane pending row count of the running group
   unsigned long long* selected;  // [1] selected rows seen by this warp
+  ChunkDesc* cdesc;          // [n_slots] descriptors of the row group the warp is working on
+  LeafRt* clrt;              // [n_leaves]
 };
 
 __device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
@@ -742,18 +744,18 @@ __device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
   m.selected = m.lastkw + size_t(kMaxKeyWords) * 32;
   m.lastslot = reinterpret_cast<uint32_t*>(m.selected + 2);
   m.cnt = m.lastslot + 32;
+  m.cdesc = reinterpret_cast<ChunkDesc*>(base + q.wr_cdesc);
+  m.clrt = reinterpret_cast<LeafRt*>(base + q.wr_clrt);
   return m;
 }
 
-// lane 0: fill ring slot `rs` with vector `vec`
-__device__ __forceinline__ void issue_vector(const QueryDesc& q, const WarpMem& m, uint32_t vec, int rs) {
-  const int rg = find_rg(q.rg_first_tile, q.n_rg, vec);
-  const uint32_t vec_in_rg = vec - __ldg(&q.rg_first_tile[rg]);
-  const uint32_t n_rows = __ldg(&q.rg_rows[rg]);
+// lane 0: fill ring slot `rs` with vector `vec` of row group `rg` (chunks = that row group's descriptors)
+__device__ __forceinline__ void issue_vector(const QueryDesc& q, const WarpMem& m, uint32_t vec, int rs, uint32_t rg_first, uint32_t n_rows,
+                                             const ChunkDesc* chunks) {
+  const uint32_t vec_in_rg = vec - rg_first;
   const uint32_t r0 = vec_in_rg * q.vl;
   const uint32_t n = min(uint32_t(q.vl), n_rows - r0);
   const uint32_t chunk = r0 / kIndexRows;
-  const ChunkDesc* __restrict__ chunks = q.chunks + size_t(rg) * q.n_slots;
   uint8_t* dst = m.ring + size_t(rs) * q.slot_bytes;
   const uint32_t plain_sz = (n * 8u + 15u) & ~15u;
   uint32_t bytes = 0;
@@ -1101,6 +1103,7 @@ __device__ __noinline__ void vec_aggregate(const VecCtx& v, const WarpMem& m, in
 // Eligibility of the QUERY is decided by the host (q.fast_ok); eligibility of the ROW GROUP (column
 // kinds) is checked here, and `false` sends the vector down the general vectorized path.
 constexpr int kFastLeaves = 4, kFastKeys = 3, kFastAggs = 2;
+constexpr int kRgSmem = 2048;  // row groups whose prefix table fits the CTA's shared memory
 
 __device__ __noinline__ bool vec_fast(const VecCtx& v, const WarpMem& m, int lane, uint32_t* cur_slot_io) {
   const QueryDesc& q = *v.q;
@@ -1262,6 +1265,7 @@ __device__ __noinline__ bool vec_fast(const VecCtx& v, const WarpMem& m, int lan
 __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ QueryDesc sq;
+  __shared__ uint32_t s_first[kRgSmem + 1];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(qp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
@@ -1269,9 +1273,14 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
   }
   __syncthreads();
   const QueryDesc& q = sq;
+  const bool rg_in_smem = q.n_rg <= kRgSmem;
+  if (rg_in_smem)
+    for (int i = threadIdx.x; i <= q.n_rg; i += blockDim.x) s_first[i] = __ldg(&q.rg_first_tile[i]);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const WarpMem m = warp_mem(q, dyn + size_t(warp) * q.wr_bytes);
   const int D = q.n_ring;
+  uint32_t cached_rows = 0;
   if (lane == 0) {
     for (int s = 0; s < D; s++) mbar_init(&m.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1288,27 +1297,52 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
   uint32_t cur_slot = kNoSlot;  // warp-uniform running group
   bool overflow = false;
 
+  // Row-group lookup without pointer chasing: the prefix table sits in shared memory and every warp
+  // walks it monotonically (its vectors only move forward); the descriptors of the row group a warp
+  // is in are cached in the warp's shared-memory region.
+  auto first_tile = [&](int i) -> uint32_t { return rg_in_smem ? s_first[i] : __ldg(&q.rg_first_tile[i]); };
+  int rg = 0, rg_a = 0;          // row group of the vector being processed / being prefetched
+  int cached_rg = -1;
+  auto descs_of = [&](int g) -> const ChunkDesc* { return g == cached_rg ? m.cdesc : q.chunks + size_t(g) * q.n_slots; };
+
   // prologue: fill the ring
   if (lane == 0)
     for (int d = 0; d < D - 1; d++) {
       const uint32_t vec = gw + uint32_t(d) * GW;
-      if (vec < q.n_tiles) issue_vector(q, m, vec, d);
+      if (vec >= q.n_tiles) break;
+      while (vec >= first_tile(rg_a + 1)) rg_a++;
+      issue_vector(q, m, vec, d, first_tile(rg_a), __ldg(&q.rg_rows[rg_a]), q.chunks + size_t(rg_a) * q.n_slots);
     }
   uint32_t it = 0;
   for (uint32_t vec = gw; vec < q.n_tiles; vec += GW, it++) {
     const int rs = int(it % uint32_t(D));
+    while (vec >= first_tile(rg + 1)) rg++;
+    if (rg != cached_rg) {  // warp-uniform: copy this row group's descriptors into shared memory
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(q.chunks + size_t(rg) * q.n_slots);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(m.cdesc);
+      for (uint32_t i = lane; i < uint32_t(q.n_slots) * sizeof(ChunkDesc) / 4; i += 32) dst[i] = __ldg(src + i);
+      src = reinterpret_cast<const uint32_t*>(q.leaf_rt + size_t(rg) * q.n_leaves);
+      dst = reinterpret_cast<uint32_t*>(m.clrt);
+      for (uint32_t i = lane; i < uint32_t(q.n_leaves) * sizeof(LeafRt) / 4; i += 32) dst[i] = __ldg(src + i);
+      cached_rg = rg;
+      cached_rows = __ldg(&q.rg_rows[rg]);
+      __syncwarp();
+    }
     if (lane == 0) {
       const uint32_t ahead = vec + uint32_t(D - 1) * GW;
-      if (ahead < q.n_tiles) issue_vector(q, m, ahead, int((it + uint32_t(D) - 1) % uint32_t(D)));
+      if (ahead < q.n_tiles) {
+        while (ahead >= first_tile(rg_a + 1)) rg_a++;
+        issue_vector(q, m, ahead, int((it + uint32_t(D) - 1) % uint32_t(D)), first_tile(rg_a),
+                     rg_a == cached_rg ? cached_rows : __ldg(&q.rg_rows[rg_a]), descs_of(rg_a));
+      }
     }
-    const int rg = find_rg(q.rg_first_tile, q.n_rg, vec);
     VecCtx v;
     v.q = &q;
-    v.n_rows = __ldg(&q.rg_rows[rg]);
-    v.r0 = (vec - __ldg(&q.rg_first_tile[rg])) * q.vl;
+    v.n_rows = cached_rows;
+    v.r0 = (vec - first_tile(rg)) * q.vl;
     v.chunk = v.r0 / kIndexRows;
-    v.chunks = q.chunks + size_t(rg) * q.n_slots;
-    v.lrt = q.leaf_rt + size_t(rg) * q.n_leaves;
+    v.chunks = m.cdesc;
+    v.lrt = m.clrt;
     v.slotmem = m.ring + size_t(rs) * q.slot_bytes;
     v.steps = int((min(uint32_t(q.vl), v.n_rows - v.r0) + 31) / 32);
     mbar_wait(&m.full[rs], (it / uint32_t(D)) & 1u);
