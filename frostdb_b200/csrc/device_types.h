@@ -74,15 +74,19 @@ enum SlotType : uint8_t { ST_I64 = 0, ST_F64 = 1, ST_DICT = 2 };
 
 enum LeafMode : uint8_t { LM_EVAL = 0, LM_ALL = 1, LM_NONE = 2 };
 
-// Predicate leaf "column op literal" (binaryscalarexpr.go:41-152).  op uses logicalplan.Op values.
+// Predicate leaf "column op literal" (binaryscalarexpr.go:41-152), canonicalised by the host:
+// numeric comparisons become "value inside the inclusive range [lo, hi]", optionally negated
+// (== v -> [v,v]; != v -> not [v,v]; < v -> [min, v-1]; >= v -> [v, max]; ...), so the kernels
+// run one branch-free range test per leaf, and conjunctions of comparisons on the same column
+// (timestamp >= a AND timestamp < b) are intersected into ONE leaf.
 struct LeafDesc {
   uint8_t slot;
-  uint8_t op;
+  uint8_t op;         // original logicalplan.Op (dictionary leaves)
   uint8_t cmp_float;  // compare as double (float column, or int column against float literal)
-  uint8_t _pad;
+  uint8_t neg;        // numeric: select rows OUTSIDE the range
   uint32_t _pad2;
-  int64_t lit_i;
-  double lit_f;
+  int64_t lo_i, hi_i;
+  double lo_f, hi_f;
 };
 
 // Per (row group, leaf): how the leaf behaves on that row group.
@@ -141,7 +145,7 @@ struct QueryDesc {
   int32_t n_ring;        // ring depth per warp
   uint32_t slot_bytes;   // bytes of one ring slot
   uint32_t wr_bytes;     // per-warp shared-memory region: size and section offsets
-  uint32_t wr_ring, wr_act, wr_leaf, wr_slot, wr_keyw, wr_tmp1, wr_tmp2, wr_acc, wr_cdesc, wr_clrt;
+  uint32_t wr_ring, wr_act, wr_leaf, wr_slot, wr_keyw, wr_tmp1, wr_tmp2, wr_acc, wr_cdesc, wr_clrt, wr_fplan;
   uint8_t stage_plain_slot[kMaxStagePlain];   // staged PLAIN buffer p holds this slot
   uint8_t stage_seed_slot[kMaxStageSeeds];    // staged seed block t belongs to this slot ...
   uint8_t stage_seed_is_def[kMaxStageSeeds];  // ... and is its definition-level stream (1) or value stream (0)

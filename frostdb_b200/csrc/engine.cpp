@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -201,6 +202,11 @@ struct LeafHost {
   const ExprNode* lit = nullptr;
   const ExprNode* bin = nullptr;
   size_t lut_off = size_t(-1);  // dictionary leaves: offset of the per-global-id result bytes in the LUT blob
+  // numeric leaves, canonical form (see LeafDesc)
+  bool numeric = false, never = false, neg = false, cmp_float = false, null_literal = false;
+  int64_t lo_i = 0, hi_i = 0;
+  double lo_f = 0, hi_f = 0;
+  uint8_t missing_mode = LM_ALL;  // behaviour on row groups that lack the column
 };
 
 bool bytes_contains(const std::string& hay, const std::string& needle) {
@@ -482,14 +488,10 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     qd.filter_mask = mask;
     qd.filter_kind = all_and ? FK_AND : (all_or ? FK_OR : FK_PROGRAM);
   }
-  qd.n_leaves = int32_t(c->leaves.size());
-  for (int l = 0; l < qd.n_leaves; l++) {
-    LeafHost& lh = c->leaves[size_t(l)];
-    LeafDesc& ld = qd.leaves[l];
-    ld.slot = uint8_t(lh.slot < 0 ? 0xff : lh.slot);
-    ld.op = uint8_t(lh.op);
+  for (size_t l = 0; l < c->leaves.size(); l++) {
+    LeafHost& lh = c->leaves[l];
+    lh.missing_mode = missing_column_mode(lh);
     if (lh.slot < 0) continue;
-    qd.slot_used_by_leaf[lh.slot] = 1;
     uint8_t st = c->slot_types[size_t(lh.slot)];
     const ExprNode& lit = *lh.lit;
     if (st == ST_DICT) {
@@ -507,10 +509,87 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       if (lh.op < FGPU_OP_EQ || lh.op > FGPU_OP_GT_EQ)
         return fail(FGPU_ERR_UNSUPPORTED, std::string("operator ") + op_string(lh.op) + " on a numeric column");
       if (lit.lit_type == FGPU_SCALAR_STRING) return fail(FGPU_ERR_UNSUPPORTED, "numeric column compared with a string literal");
-      ld.cmp_float = (st == ST_F64) || lit.lit_type == FGPU_SCALAR_FLOAT64;
-      ld.lit_i = lit.lit_i;
-      ld.lit_f = lit.lit_type == FGPU_SCALAR_FLOAT64 ? lit.lit_f : double(lit.lit_i);
+      lh.numeric = true;
+      lh.null_literal = lit.lit_type == FGPU_SCALAR_NULL;  // arrow compute against NULL: nothing selected (:143-150)
+      lh.cmp_float = (st == ST_F64) || lit.lit_type == FGPU_SCALAR_FLOAT64;
+      const int64_t kMin = std::numeric_limits<int64_t>::min(), kMax = std::numeric_limits<int64_t>::max();
+      const double kInf = std::numeric_limits<double>::infinity();
+      if (lh.cmp_float) {
+        const double v = lit.lit_type == FGPU_SCALAR_FLOAT64 ? lit.lit_f : double(lit.lit_i);
+        lh.lo_f = kInf; lh.hi_f = -kInf;  // empty
+        if (!std::isnan(v)) {
+          switch (lh.op) {
+            case FGPU_OP_EQ: lh.lo_f = lh.hi_f = v; break;
+            case FGPU_OP_NOT_EQ: lh.lo_f = lh.hi_f = v; lh.neg = true; break;
+            case FGPU_OP_LT: lh.lo_f = -kInf; lh.hi_f = std::nextafter(v, -kInf); break;
+            case FGPU_OP_LT_EQ: lh.lo_f = -kInf; lh.hi_f = v; break;
+            case FGPU_OP_GT: lh.lo_f = std::nextafter(v, kInf); lh.hi_f = kInf; break;
+            default: lh.lo_f = v; lh.hi_f = kInf; break;
+          }
+          if (lh.op == FGPU_OP_LT && v == -kInf) { lh.lo_f = kInf; lh.hi_f = -kInf; }
+          if (lh.op == FGPU_OP_GT && v == kInf) { lh.lo_f = kInf; lh.hi_f = -kInf; }
+        } else if (lh.op == FGPU_OP_NOT_EQ) {
+          lh.neg = true;  // x != NaN holds for every non-NULL x
+        }
+      } else {
+        const int64_t v = lit.lit_i;
+        lh.lo_i = kMax; lh.hi_i = kMin;  // empty
+        switch (lh.op) {
+          case FGPU_OP_EQ: lh.lo_i = lh.hi_i = v; break;
+          case FGPU_OP_NOT_EQ: lh.lo_i = lh.hi_i = v; lh.neg = true; break;
+          case FGPU_OP_LT: if (v != kMin) { lh.lo_i = kMin; lh.hi_i = v - 1; } break;
+          case FGPU_OP_LT_EQ: lh.lo_i = kMin; lh.hi_i = v; break;
+          case FGPU_OP_GT: if (v != kMax) { lh.lo_i = v + 1; lh.hi_i = kMax; } break;
+          default: lh.lo_i = v; lh.hi_i = kMax; break;
+        }
+      }
     }
+  }
+  // Conjunction: comparisons on the same numeric column intersect into one range leaf
+  // (timestamp >= a AND timestamp < b  ->  timestamp in [a, b-1]); a missing column keeps the
+  // strictest of the merged leaves' missing-column behaviours.
+  if (qd.filter_kind == FK_AND && !getenv("FROSTGPU_NO_FUSE")) {
+    std::vector<LeafHost> fused;
+    for (LeafHost& lh : c->leaves) {
+      bool merged = false;
+      if (lh.numeric && !lh.neg && !lh.null_literal && lh.slot >= 0) {
+        for (LeafHost& f : fused) {
+          if (!f.numeric || f.neg || f.null_literal || f.slot != lh.slot || f.cmp_float != lh.cmp_float) continue;
+          if (f.cmp_float) { f.lo_f = std::max(f.lo_f, lh.lo_f); f.hi_f = std::min(f.hi_f, lh.hi_f); }
+          else { f.lo_i = std::max(f.lo_i, lh.lo_i); f.hi_i = std::min(f.hi_i, lh.hi_i); }
+          if (lh.missing_mode == LM_NONE) f.missing_mode = LM_NONE;
+          merged = true;
+          break;
+        }
+      }
+      if (!merged) fused.push_back(lh);
+    }
+    if (fused.size() != c->leaves.size()) {
+      c->leaves.swap(fused);
+      c->filter_prog.clear();
+      for (size_t l = 0; l < c->leaves.size(); l++) {
+        c->filter_prog.push_back(uint8_t(l));
+        if (l > 0) c->filter_prog.push_back(0x80);
+      }
+      qd.n_filter_prog = int32_t(c->filter_prog.size());
+      std::memset(qd.filter_prog, 0, sizeof qd.filter_prog);
+      std::memcpy(qd.filter_prog, c->filter_prog.data(), c->filter_prog.size());
+      qd.filter_mask = (c->leaves.size() >= 32) ? 0xffffffffu : ((1u << c->leaves.size()) - 1u);
+    }
+  }
+  qd.n_leaves = int32_t(c->leaves.size());
+  for (int l = 0; l < qd.n_leaves; l++) {
+    const LeafHost& lh = c->leaves[size_t(l)];
+    LeafDesc& ld = qd.leaves[l];
+    ld = LeafDesc{};
+    ld.slot = uint8_t(lh.slot < 0 ? 0xff : lh.slot);
+    ld.op = uint8_t(lh.op);
+    if (lh.slot < 0) continue;
+    qd.slot_used_by_leaf[lh.slot] = 1;
+    ld.cmp_float = lh.cmp_float;
+    ld.neg = lh.neg;
+    ld.lo_i = lh.lo_i; ld.hi_i = lh.hi_i;
+    ld.lo_f = lh.lo_f; ld.hi_f = lh.hi_f;
   }
   // aggregates
   if (q.aggs.size() > size_t(kMaxAggs)) return fail(FGPU_ERR_UNSUPPORTED, "too many aggregates");
@@ -664,6 +743,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       qd.wr_acc = uint32_t(off); off = r128(off + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4 + 32 * 4);
       qd.wr_cdesc = uint32_t(off); off = r128(off + size_t(std::max(qd.n_slots, 1)) * sizeof(ChunkDesc));
       qd.wr_clrt = uint32_t(off); off = r128(off + size_t(std::max(qd.n_leaves, 1)) * sizeof(LeafRt));
+      qd.wr_fplan = uint32_t(off); off = r128(off + 512);
       qd.wr_bytes = uint32_t(off);
       if (size_t(qd.wr_bytes) * (kVecThreads / 32) <= 200 * 1024 || vl == 128) break;
       vl /= 2;  // many staged columns / wide keys: shorter vectors
@@ -671,12 +751,12 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     qd.vl = vl;
     qd.n_ring = ring;
     // fused fast path: conjunction of numeric leaves, dense dictionary keys, simple aggregates
-    bool fast = qd.table_mode == TM_DENSE && (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) && qd.n_leaves <= 4 && qd.n_keys <= 3 &&
+    bool fast = qd.table_mode == TM_DENSE && (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) && qd.n_leaves <= 2 && qd.n_keys <= 3 &&
                 !getenv("FROSTGPU_NO_FAST");
     for (int l = 0; l < qd.n_leaves && fast; l++) {
       const LeafHost& lh = c->leaves[size_t(l)];
       if (lh.slot >= 0 && c->slot_types[size_t(lh.slot)] == ST_DICT) fast = false;
-      if (lh.slot >= 0 && lh.lit->lit_type == FGPU_SCALAR_NULL) fast = false;
+      if (lh.slot >= 0 && lh.null_literal) fast = false;
     }
     int stored = 0;
     for (int a = 0; a < qd.n_aggs && fast; a++) {
@@ -763,7 +843,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       LeafRt rt{};
       auto it = lh.slot < 0 ? rg.cols.end() : rg.cols.find(lh.column);
       if (it == rg.cols.end()) {
-        rt.mode = missing_column_mode(lh);
+        rt.mode = lh.missing_mode;
       } else if (c.slot_types[size_t(lh.slot)] == ST_DICT) {
         rt.mode = LM_EVAL;
         rt.null_result = (lh.op == FGPU_OP_EQ && lh.lit->lit_type == FGPU_SCALAR_NULL) ? 1 : 0;
@@ -776,7 +856,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         }
         lut_fix.emplace_back(size_t(g) * n_leaves + l, lh.lut_off);
       } else {
-        rt.mode = (lh.lit->lit_type == FGPU_SCALAR_NULL) ? LM_NONE : LM_EVAL;
+        rt.mode = lh.null_literal ? LM_NONE : LM_EVAL;
       }
       lrt[size_t(g) * n_leaves + l] = rt;
     }

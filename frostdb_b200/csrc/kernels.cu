@@ -262,25 +262,16 @@ __device__ __forceinline__ void tile_num(const TileCtx& t, int slot, int lane, l
 }
 
 // ---- predicate --------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool cmp_i64(uint8_t op, long long a, long long b) {
-  switch (op) {
-    case 1: return a == b;
-    case 2: return a != b;
-    case 3: return a < b;
-    case 4: return a <= b;
-    case 5: return a > b;
-    default: return a >= b;
+// Canonical numeric leaf: value inside [lo, hi] (inclusive), optionally negated.  NaN is never inside.
+__device__ __forceinline__ bool leaf_range(const LeafDesc& ld, long long bits, bool f64col) {
+  bool in;
+  if (ld.cmp_float) {
+    const double x = f64col ? __longlong_as_double(bits) : double(bits);
+    in = x >= ld.lo_f && x <= ld.hi_f;
+  } else {
+    in = bits >= ld.lo_i && bits <= ld.hi_i;
   }
-}
-__device__ __forceinline__ bool cmp_f64(uint8_t op, double a, double b) {
-  switch (op) {
-    case 1: return a == b;
-    case 2: return a != b;
-    case 3: return a < b;
-    case 4: return a <= b;
-    case 5: return a > b;
-    default: return a >= b;
-  }
+  return in != (ld.neg != 0);
 }
 
 __device__ __forceinline__ bool eval_filter(const QueryDesc& q, uint32_t bits) {
@@ -342,12 +333,7 @@ __device__ __forceinline__ void eval_leaves(const TileCtx& t, int lane, uint32_t
         for (int j = 0; j < STEPS; j++) {
           bool r = false;
           if (!((nullmask >> j) & 1u)) {
-            if (ld.cmp_float) {
-              double x = f64col ? __longlong_as_double(bits[j]) : double(bits[j]);
-              r = cmp_f64(ld.op, x, ld.lit_f);
-            } else {
-              r = cmp_i64(ld.op, bits[j], ld.lit_i);
-            }
+            r = leaf_range(ld, bits[j], f64col);
           }
           leafbits[j] |= uint32_t(r) << l;
         }
@@ -710,6 +696,7 @@ struct NumReader {
   }
 };
 
+struct FastPlan;
 // Per-warp shared-memory region (offsets precomputed by the host in QueryDesc.wr_*).
 struct WarpMem {
   uint64_t* full;            // [n_ring] mbarriers
@@ -727,6 +714,7 @@ struct WarpMem {
   unsigned long long* selected;  // [1] selected rows seen by this warp
   ChunkDesc* cdesc;          // [n_slots] descriptors of the row group the warp is working on
   LeafRt* clrt;              // [n_leaves]
+  struct FastPlan* fplan;    // resolved fast-path plan of that row group
 };
 
 __device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
@@ -746,6 +734,7 @@ __device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
   m.cnt = m.lastslot + 32;
   m.cdesc = reinterpret_cast<ChunkDesc*>(base + q.wr_cdesc);
   m.clrt = reinterpret_cast<LeafRt*>(base + q.wr_clrt);
+  m.fplan = reinterpret_cast<struct FastPlan*>(base + q.wr_fplan);
   return m;
 }
 
@@ -850,17 +839,12 @@ __device__ __noinline__ uint32_t vec_selection(const VecCtx& v, const WarpMem& m
       NumReader rd;
       rd.init(v, ld.slot, lane);
       const bool f64col = q.slot_type[ld.slot] == ST_F64;
-      const uint8_t op = ld.op;
-      const bool cf = ld.cmp_float;
-      const long long li = ld.lit_i;
-      const double lf = ld.lit_f;
-      #pragma unroll 1
+#pragma unroll 1
       for (int s = 0; s < steps; s++) {
         const uint32_t r = v.r0 + uint32_t(s) * 32 + lane;
         bool null;
         const long long bits = rd.next(r, v.n_rows, null);
-        bool res = false;
-        if (!null) res = cf ? cmp_f64(op, f64col ? __longlong_as_double(bits) : double(bits), lf) : cmp_i64(op, bits, li);
+        const bool res = !null && leaf_range(ld, bits, f64col);
         if (prog) {
           if (res) m.leafw[s * 32 + lane] |= 1u << l;
         } else {
@@ -1097,169 +1081,256 @@ __device__ __noinline__ void vec_aggregate(const VecCtx& v, const WarpMem& m, in
 
 // ---- fused fast path ---------------------------------------------------------------------------------------
 // The dominant query shape runs in ONE pass over the vector with everything in registers:
-//   filter  = conjunction of <= 4 comparisons on PLAIN non-null int64/double columns (or no filter)
+//   filter  = conjunction of <= 2 range leaves on PLAIN non-null int64/double columns (or no filter)
 //   keys    = <= 3 dictionary-string columns without NULLs in this row group, dense table
 //   aggs    = counts + <= 2 Sum/Min/Max over PLAIN non-null columns read in place
-// Eligibility of the QUERY is decided by the host (q.fast_ok); eligibility of the ROW GROUP (column
-// kinds) is checked here, and `false` sends the vector down the general vectorized path.
-constexpr int kFastLeaves = 4, kFastKeys = 3, kFastAggs = 2;
+// Eligibility of the QUERY is decided by the host (q.fast_ok).  Eligibility of the ROW GROUP (column
+// kinds) is resolved once per row group into a FastPlan kept in the warp's shared memory; a row group
+// that does not qualify sends its vectors down the general vectorized path.
+constexpr int kFastLeaves = 2, kFastKeys = 3, kFastAggs = 2;
 constexpr int kRgSmem = 2048;  // row groups whose prefix table fits the CTA's shared memory
 
-__device__ __noinline__ bool vec_fast(const VecCtx& v, const WarpMem& m, int lane, uint32_t* cur_slot_io) {
-  const QueryDesc& q = *v.q;
-  const int nl = q.n_leaves, nk = q.n_keys;
-  // ---- resolve columns (warp-uniform) ----
-  const long long* lcol[kFastLeaves];
-  long long li[kFastLeaves];
-  double lf[kFastLeaves];
-  uint32_t lflags[kFastLeaves];  // 1 lt, 2 eq, 4 gt selects; 8 compare as double; 16 column is double
-#pragma unroll
-  for (int l = 0; l < kFastLeaves; l++) {
-    lcol[l] = nullptr; li[l] = 0; lf[l] = 0; lflags[l] = 0;
-    if (l >= nl) continue;
+struct FastLeaf {
+  uint32_t col_off;  // byte offset of the staged column inside a ring slot
+  uint32_t flags;    // 1 compare as double, 2 column is double, 4 negate
+  long long lo_i, hi_i;
+  double lo_f, hi_f;
+};
+struct FastKey {
+  const Run* runs;
+  const uint8_t* stream;
+  const uint32_t* lut;
+  const Seed* seeds;    // global seeds of the row group
+  int32_t seed_off;     // byte offset of the staged seed inside a ring slot, -1 = read the global one
+  uint32_t stride;
+};
+struct FastAgg {
+  uint32_t col_off;
+  uint32_t func;  // AggFunc | is_float << 8
+  int32_t index;  // index into q.aggs / q.t_agg
+  uint32_t _pad;
+};
+struct FastPlan {
+  uint32_t ok, none, nl, nk, na, _pad;
+  FastLeaf leaf[kFastLeaves];
+  FastKey key[kFastKeys];
+  FastAgg agg[kFastAggs];
+};
+
+__device__ __forceinline__ long long lds64(uint32_t a) {
+  long long v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+
+// lane 0 builds the plan of the warp's current row group from the cached descriptors
+__device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc* chunks, const LeafRt* lrt, FastPlan* fp) {
+  fp->ok = 0;
+  fp->none = 0;
+  uint32_t nl = 0, nk = 0, na = 0;
+  for (int l = 0; l < q.n_leaves; l++) {
     const LeafDesc& ld = q.leaves[l];
-    const uint8_t mode = v.lrt[l].mode;
-    if (mode == LM_NONE) {  // conjunction with an always-false leaf: nothing selected in this row group
-      return true;
-    }
-    if (mode == LM_ALL) { lflags[l] = 7u | 32u; continue; }  // always true: skip the column
-    const ChunkDesc& c = v.chunks[ld.slot];
+    const uint8_t mode = lrt[l].mode;
+    if (mode == LM_NONE) { fp->none = 1; continue; }
+    if (mode == LM_ALL) continue;
+    const ChunkDesc& c = chunks[ld.slot];
     const int p = q.slot_plain_stage[ld.slot];
-    if (c.kind != CK_PLAIN64 || c.has_nulls || p < 0) return false;
-    lcol[l] = reinterpret_cast<const long long*>(v.slotmem + size_t(p) * q.vl * 8);
-    li[l] = ld.lit_i;
-    lf[l] = ld.lit_f;
-    uint32_t f = 0;
-    switch (ld.op) {
-      case 1: f = 2; break;      // ==
-      case 2: f = 1 | 4; break;  // !=
-      case 3: f = 1; break;      // <
-      case 4: f = 1 | 2; break;  // <=
-      case 5: f = 4; break;      // >
-      default: f = 4 | 2; break; // >=
-    }
-    if (ld.cmp_float) f |= 8;
-    if (q.slot_type[ld.slot] == ST_F64) f |= 16;
-    lflags[l] = f;
+    if (c.kind != CK_PLAIN64 || c.has_nulls || p < 0 || nl >= uint32_t(kFastLeaves)) return;
+    FastLeaf& f = fp->leaf[nl++];
+    f.col_off = uint32_t(p) * uint32_t(q.vl) * 8u;
+    f.flags = (ld.cmp_float ? 1u : 0u) | (q.slot_type[ld.slot] == ST_F64 ? 2u : 0u) | (ld.neg ? 4u : 0u);
+    f.lo_i = ld.lo_i; f.hi_i = ld.hi_i; f.lo_f = ld.lo_f; f.hi_f = ld.hi_f;
   }
-  HybCur kc[kFastKeys];
-  uint32_t kstride[kFastKeys];
-  bool kuse[kFastKeys];
-#pragma unroll
-  for (int k = 0; k < kFastKeys; k++) {
-    kuse[k] = false; kstride[k] = 0;
-    if (k >= nk) continue;
+  for (int k = 0; k < q.n_keys; k++) {
     const KeyDesc& kd = q.keys[k];
-    const ChunkDesc& c = v.chunks[kd.slot];
-    if (c.kind == CK_ABSENT) continue;  // absent column: NULL for every row, contributes 0
-    if (c.kind != CK_DICT_STR || c.has_nulls) return false;
+    const ChunkDesc& c = chunks[kd.slot];
+    if (c.kind == CK_ABSENT) continue;  // NULL for every row: contributes 0 to the dense slot
+    if (c.kind != CK_DICT_STR || c.has_nulls || nk >= uint32_t(kFastKeys)) return;
+    FastKey& f = fp->key[nk++];
+    f.runs = c.runs; f.stream = c.values; f.lut = c.lut; f.seeds = c.seeds;
     const int sv = q.slot_seed_stage[kd.slot][0];
-    const uint8_t* seeds = v.slotmem + size_t(q.n_stage_plain) * q.vl * 8;
-    hc_init(kc[k], c.runs, c.values, c.lut, sv >= 0 ? reinterpret_cast<const Seed*>(seeds) + sv : c.seeds + v.chunk);
-    kstride[k] = kd.dense_stride;
-    kuse[k] = true;
+    f.seed_off = sv >= 0 ? int32_t(uint32_t(q.n_stage_plain) * uint32_t(q.vl) * 8u + uint32_t(sv) * uint32_t(sizeof(Seed))) : -1;
+    f.stride = kd.dense_stride;
   }
-  int ai[kFastAggs];
-  const long long* acol[kFastAggs];
-  uint32_t afunc[kFastAggs];  // func | isf << 8
-  long long part[kFastAggs];
-  int na = 0;
-#pragma unroll
-  for (int a = 0; a < kFastAggs; a++) { ai[a] = -1; acol[a] = nullptr; afunc[a] = 0; part[a] = 0; }
   for (int a = 0; a < q.n_aggs; a++) {
     const AggDesc& ad = q.aggs[a];
     if (ad.func == 4) continue;
     const int slot = q.prog[ad.prog_off].slot;
-    const ChunkDesc& c = v.chunks[slot];
+    const ChunkDesc& c = chunks[slot];
     const int p = q.slot_plain_stage[slot];
-    if (c.kind != CK_PLAIN64 || c.has_nulls || p < 0) return false;
-    const long long* col = reinterpret_cast<const long long*>(v.slotmem + size_t(p) * q.vl * 8);
-#pragma unroll
-    for (int x = 0; x < kFastAggs; x++)
-      if (x == na) { ai[x] = a; acol[x] = col; afunc[x] = uint32_t(ad.func) | (uint32_t(ad.is_float) << 8); part[x] = m.acc[a * 32 + lane]; }
-    na++;
+    if (c.kind != CK_PLAIN64 || c.has_nulls || p < 0 || na >= uint32_t(kFastAggs)) return;
+    FastAgg& f = fp->agg[na++];
+    f.col_off = uint32_t(p) * uint32_t(q.vl) * 8u;
+    f.func = uint32_t(ad.func) | (uint32_t(ad.is_float) << 8);
+    f.index = a;
   }
-  // ---- the pass ----
-  uint32_t cs = *cur_slot_io;
-  uint32_t cnt = m.cnt[lane];
-  uint32_t selected = 0;
-  const uint32_t n_in = min(uint32_t(q.vl), v.n_rows - v.r0);
+  fp->nl = nl; fp->nk = nk; fp->na = na;
+  fp->ok = 1;
+}
+
+__device__ __forceinline__ bool fast_leaf_test(const FastLeaf& f, long long x) {
+  bool in;
+  if (f.flags & 1u) {
+    const double d = (f.flags & 2u) ? __longlong_as_double(x) : double(x);
+    in = d >= f.lo_f && d <= f.hi_f;
+  } else {
+    in = x >= f.lo_i && x <= f.hi_i;
+  }
+  return in != ((f.flags & 4u) != 0);
+}
+
+// Slim run cursor of the fast path: the directory / stream / LUT pointers stay in the FastPlan.
+struct KCur {
+  uint32_t k, start, end, val, meta, off;
+};
+__device__ __forceinline__ void kc_advance(KCur& c, const FastKey& fk, uint32_t ord) {
+  while (ord >= c.end) {
+    c.k++;
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(fk.runs + c.k));
+    c.start = r.x; c.off = r.y; c.val = r.z; c.meta = r.w;
+    c.end = __ldg(&fk.runs[c.k + 1].start);
+  }
+}
+__device__ __forceinline__ uint32_t kc_get(KCur& c, const FastKey& fk, uint32_t ord) {
+  if (ord >= c.end) kc_advance(c, fk, ord);
+  if ((c.meta & 1u) == 0) return c.val;
+  const uint32_t w = (c.meta >> 8) & 0xffu;
+  return __ldg(fk.lut + extract_bits(fk.stream, c.off, uint64_t(ord - c.start) * w, w));
+}
+
+template <int NL, int NK, int NA>
+__device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t slot_saddr,
+                                            const uint8_t* slotmem, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
+                                            uint32_t cur_slot) {
+  // leaves: the active bound pair as raw 64-bit words
+  long long llo[NL > 0 ? NL : 1], lhi[NL > 0 ? NL : 1];
+  uint32_t lflags[NL > 0 ? NL : 1], lcol[NL > 0 ? NL : 1];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const FastLeaf& f = fp.leaf[l];
+    lflags[l] = f.flags;
+    lcol[l] = slot_saddr + f.col_off + uint32_t(lane) * 8u;
+    llo[l] = (f.flags & 1u) ? __double_as_longlong(f.lo_f) : f.lo_i;
+    lhi[l] = (f.flags & 1u) ? __double_as_longlong(f.hi_f) : f.hi_i;
+  }
+  KCur kc[NK > 0 ? NK : 1];
+  uint32_t kstride[NK > 0 ? NK : 1];
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    const FastKey& fk = fp.key[k];
+    const Seed* sd = fk.seed_off >= 0 ? reinterpret_cast<const Seed*>(slotmem + fk.seed_off) : fk.seeds + chunk;
+    const uint4 a = *reinterpret_cast<const uint4*>(sd);
+    const uint2 b = *(reinterpret_cast<const uint2*>(sd) + 2);
+    kc[k].k = a.x; kc[k].start = a.y; kc[k].end = a.z; kc[k].off = a.w; kc[k].val = b.x; kc[k].meta = b.y;
+    kstride[k] = fk.stride;
+  }
+  uint32_t acol[NA > 0 ? NA : 1], afunc[NA > 0 ? NA : 1];
+  long long part[NA > 0 ? NA : 1];
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    acol[a] = slot_saddr + fp.agg[a].col_off + uint32_t(lane) * 8u;
+    afunc[a] = fp.agg[a].func;
+    part[a] = m.acc[fp.agg[a].index * 32 + lane];
+  }
+  uint32_t cs = cur_slot, cnt = m.cnt[lane], selected = 0;
 #pragma unroll 1
-  for (int s = 0; s < v.steps; s++) {
-    const uint32_t idx = uint32_t(s) * 32 + lane;
+  for (int s = 0; s < steps; s++) {
+    const uint32_t idx = uint32_t(s) * 32u + uint32_t(lane);
     bool act = idx < n_in;
 #pragma unroll
-    for (int l = 0; l < kFastLeaves; l++) {
-      if (l >= nl || (lflags[l] & 32u)) continue;
-      const long long x = act ? lcol[l][idx] : 0;
-      bool lt, eq;
-      if (lflags[l] & 8u) {
-        const double d = (lflags[l] & 16u) ? __longlong_as_double(x) : double(x);
-        lt = d < lf[l];
-        eq = d == lf[l];
-        const bool gt = d > lf[l];  // NaN: none of the three
-        act = act && ((lt && (lflags[l] & 1u)) || (eq && (lflags[l] & 2u)) || (gt && (lflags[l] & 4u)));
+    for (int l = 0; l < NL; l++) {
+      const long long x = lds64(lcol[l] + uint32_t(s) * 256u);
+      bool in;
+      if (lflags[l] & 1u) {
+        const double d = (lflags[l] & 2u) ? __longlong_as_double(x) : double(x);
+        in = d >= __longlong_as_double(llo[l]) && d <= __longlong_as_double(lhi[l]);
       } else {
-        lt = x < li[l];
-        eq = x == li[l];
-        act = act && ((lt && (lflags[l] & 1u)) || (eq && (lflags[l] & 2u)) || (!lt && !eq && (lflags[l] & 4u)));
+        in = x >= llo[l] && x <= lhi[l];
       }
+      act = act && (in != ((lflags[l] & 4u) != 0));
     }
     const unsigned amask = __ballot_sync(FULL, act);
     if (amask == 0) continue;
     uint32_t slot = 0;
-    const uint32_t r = v.r0 + idx;
+    const uint32_t r = r0 + idx;
 #pragma unroll
-    for (int k = 0; k < kFastKeys; k++)
-      if (kuse[k] && act) slot += (hc_get(kc[k], r) + 1u) * kstride[k];
+    for (int k = 0; k < NK; k++)
+      if (act) slot += (kc_get(kc[k], fp.key[k], r) + 1u) * kstride[k];
     selected += __popc(amask);
     const uint32_t s0 = __shfl_sync(FULL, slot, __ffs(amask) - 1);
     const bool uni = __all_sync(FULL, !act || slot == s0);
-    if (uni) {
-      if (s0 != cs) {
-        if (cs != kNoSlot) {
-          const uint32_t tt = __reduce_add_sync(FULL, cnt);
-          if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
-          cnt = 0;
-#pragma unroll
-          for (int x = 0; x < kFastAggs; x++)
-            if (x < na) {
-              flush_agg(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, q.t_agg[ai[x]] + cs, part[x], lane);
-              part[x] = agg_identity(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0);
-            }
-        }
-        cs = s0;
-      }
+    if (uni && s0 == cs) {  // the common case: still in the running group
       cnt += act ? 1u : 0u;
 #pragma unroll
-      for (int x = 0; x < kFastAggs; x++)
-        if (x < na && act) part[x] = agg_combine(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, part[x], acol[x][idx]);
-    } else {
-      if (cs != kNoSlot) {
-        const uint32_t tt = __reduce_add_sync(FULL, cnt);
-        if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
-        cnt = 0;
-#pragma unroll
-        for (int x = 0; x < kFastAggs; x++)
-          if (x < na) {
-            flush_agg(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, q.t_agg[ai[x]] + cs, part[x], lane);
-            part[x] = agg_identity(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0);
-          }
-        cs = kNoSlot;
+      for (int a = 0; a < NA; a++) {
+        const long long val = lds64(acol[a] + uint32_t(s) * 256u);
+        if (afunc[a] == 1u) part[a] = (long long)((unsigned long long)part[a] + (act ? (unsigned long long)val : 0ull));  // Sum(int64)
+        else if (act) part[a] = agg_combine(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, part[a], val);
       }
+      continue;
+    }
+    // group change or mixed step: flush what the warp has accumulated
+    if (cs != kNoSlot) {
+      const uint32_t tt = __reduce_add_sync(FULL, cnt);
+      if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+      cnt = 0;
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        flush_agg(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, q.t_agg[fp.agg[a].index] + cs, part[a], lane);
+        part[a] = agg_identity(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0);
+      }
+    }
+    if (uni) {
+      cs = s0;
+      cnt = act ? 1u : 0u;
+#pragma unroll
+      for (int a = 0; a < NA; a++)
+        if (act) part[a] = agg_combine(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, part[a], lds64(acol[a] + uint32_t(s) * 256u));
+    } else {
+      cs = kNoSlot;
       mixed_rows(q.t_rows, slot, act, lane);
 #pragma unroll
-      for (int x = 0; x < kFastAggs; x++)
-        if (x < na) mixed_agg(uint8_t(afunc[x] & 0xff), (afunc[x] >> 8) != 0, q.t_agg[ai[x]], slot, act, act ? acol[x][idx] : 0, lane);
+      for (int a = 0; a < NA; a++)
+        mixed_agg(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, q.t_agg[fp.agg[a].index], slot, act, lds64(acol[a] + uint32_t(s) * 256u), lane);
     }
   }
   m.cnt[lane] = cnt;
 #pragma unroll
-  for (int x = 0; x < kFastAggs; x++)
-    if (x < na) m.acc[ai[x] * 32 + lane] = part[x];
+  for (int a = 0; a < NA; a++) m.acc[fp.agg[a].index * 32 + lane] = part[a];
   if (lane == 0) m.selected[0] += selected;
-  *cur_slot_io = cs;
-  return true;
+  return cs;
+}
+
+template <int NL, int NK>
+__device__ __forceinline__ uint32_t fast_dispatch_a(int na, const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t sa,
+                                                    const uint8_t* sm, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
+                                                    uint32_t cs) {
+  switch (na) {
+    case 0: return fast_pass<NL, NK, 0>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+    case 1: return fast_pass<NL, NK, 1>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+    default: return fast_pass<NL, NK, 2>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+  }
+}
+template <int NL>
+__device__ __forceinline__ uint32_t fast_dispatch_k(int nk, int na, const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t sa,
+                                                    const uint8_t* sm, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
+                                                    uint32_t cs) {
+  switch (nk) {
+    case 0: return fast_dispatch_a<NL, 0>(na, q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+    case 1: return fast_dispatch_a<NL, 1>(na, q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+    case 2: return fast_dispatch_a<NL, 2>(na, q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+    default: return fast_dispatch_a<NL, 3>(na, q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+  }
+}
+__device__ __forceinline__ uint32_t fast_dispatch(const VecCtx& v, const WarpMem& m, const FastPlan& fp, int lane, uint32_t cs) {
+  const QueryDesc& q = *v.q;
+  const uint32_t sa = smem_u32(v.slotmem);
+  const uint32_t n_in = min(uint32_t(q.vl), v.n_rows - v.r0);
+  switch (fp.nl) {
+    case 0: return fast_dispatch_k<0>(int(fp.nk), int(fp.na), q, m, fp, sa, v.slotmem, v.r0, v.chunk, n_in, v.steps, lane, cs);
+    case 1: return fast_dispatch_k<1>(int(fp.nk), int(fp.na), q, m, fp, sa, v.slotmem, v.r0, v.chunk, n_in, v.steps, lane, cs);
+    default: return fast_dispatch_k<2>(int(fp.nk), int(fp.na), q, m, fp, sa, v.slotmem, v.r0, v.chunk, n_in, v.steps, lane, cs);
+  }
 }
 
 __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
@@ -1327,6 +1398,10 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
       cached_rg = rg;
       cached_rows = __ldg(&q.rg_rows[rg]);
       __syncwarp();
+      if (q.fast_ok) {
+        if (lane == 0) build_fast_plan(q, m.cdesc, m.clrt, m.fplan);
+        __syncwarp();
+      }
     }
     if (lane == 0) {
       const uint32_t ahead = vec + uint32_t(D - 1) * GW;
@@ -1347,8 +1422,8 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
     v.steps = int((min(uint32_t(q.vl), v.n_rows - v.r0) + 31) / 32);
     mbar_wait(&m.full[rs], (it / uint32_t(D)) & 1u);
 
-    if (q.fast_ok && vec_fast(v, m, lane, &cur_slot)) {
-      // handled in one fused pass
+    if (q.fast_ok && m.fplan->ok) {
+      if (!m.fplan->none) cur_slot = fast_dispatch(v, m, *m.fplan, lane, cur_slot);  // one fused pass
     } else if (vec_selection(v, m, lane) != 0) {
       if (dense) vec_slots_dense(v, m, lane);
       else overflow |= vec_slots_hash(v, m, lane);
