@@ -626,14 +626,14 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   }
   if (prog.size() > size_t(kMaxProg)) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expressions too large");
   for (size_t p = 0; p < prog.size(); p++) qd.prog[p] = prog[p];
-  // the kernel evaluates aggregate expressions on an operand stack of two shared-memory vectors
+  // the kernel evaluates aggregate expressions on an operand stack of three shared-memory vectors
   for (size_t a = 0; a < q.aggs.size(); a++) {
     int depth = 0, maxd = 0;
     for (int p = qd.aggs[a].prog_off; p < qd.aggs[a].prog_off + qd.aggs[a].prog_len; p++) {
       depth += (prog[size_t(p)].op == PO_LOAD || prog[size_t(p)].op == PO_CONST) ? 1 : -1;
       maxd = std::max(maxd, depth);
     }
-    if (maxd > 2) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expression nests too deeply for the GPU path");
+    if (maxd > 3) return fail(FGPU_ERR_UNSUPPORTED, "aggregate expression nests too deeply for the GPU path");
   }
   qd.tile_rows = ctx->tile_rows;
   qd.n_rg = int32_t(c->rgs.size());
@@ -719,9 +719,9 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   // ---- scan kernel: vector length, ring depth and the per-warp shared-memory layout ----------------
   {
     auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-    int vl = envi("FROSTGPU_VL", 256);
+    int vl = envi("FROSTGPU_VL", 512);
     if (vl != 128 && vl != 256 && vl != 512) vl = 256;
-    int ring = envi("FROSTGPU_RING", 2);
+    int ring = envi("FROSTGPU_RING", 3);
     if (ring < 2) ring = 2;
     if (ring > 4) ring = 4;
     bool any_expr = false;
@@ -739,7 +739,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       qd.wr_slot = uint32_t(off); off = r128(off + size_t(vl) * 4);
       qd.wr_keyw = uint32_t(off); off = r128(off + (qd.table_mode == TM_HASH ? size_t(qd.key_words) * vl * 8 : 0));
       qd.wr_tmp1 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
-      qd.wr_tmp2 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
+      qd.wr_tmp2 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 16 : 0));
       qd.wr_acc = uint32_t(off); off = r128(off + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4 + 32 * 4);
       qd.wr_cdesc = uint32_t(off); off = r128(off + size_t(std::max(qd.n_slots, 1)) * sizeof(ChunkDesc));
       qd.wr_clrt = uint32_t(off); off = r128(off + size_t(std::max(qd.n_leaves, 1)) * sizeof(LeafRt));

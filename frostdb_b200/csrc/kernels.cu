@@ -898,8 +898,7 @@ __device__ __noinline__ uint32_t vec_selection(const VecCtx& v, const WarpMem& m
 // Evaluates an aggregate expression over the vector into out[] (raw 8-byte values, NULL slots 0).
 __device__ __noinline__ void vec_eval_expr(const VecCtx& v, const WarpMem& m, const AggDesc& a, int lane, long long* out) {
   const QueryDesc& q = *v.q;
-  long long* stack[3] = {out, m.tmp2, nullptr};
-  // operand i of the stack lives in: 0 -> out, 1 -> tmp2, 2 -> acc scratch is not available: depth 3 uses leafw+slot? (host limits depth to 2 here)
+  long long* stack[3] = {out, m.tmp2, m.tmp2 + q.vl};  // operand stack: depth <= 3 (checked by the host)
   int sp = 0;
   for (int p = a.prog_off; p < a.prog_off + a.prog_len; p++) {
     const ProgOp& o = q.prog[p];
