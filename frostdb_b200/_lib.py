@@ -34,6 +34,7 @@ AGG_SUM, AGG_MIN, AGG_MAX, AGG_COUNT, AGG_AVG, AGG_UNIQUE, AGG_AND = 1, 2, 3, 4,
 SCALAR_NULL, SCALAR_INT64, SCALAR_FLOAT64, SCALAR_STRING = 0, 1, 2, 3
 EXPR_COLUMN, EXPR_DYNCOLUMN, EXPR_LITERAL, EXPR_BINARY = 1, 2, 3, 4
 PLAN_AGGREGATE, PLAN_DISTINCT, PLAN_FILTER = 1, 2, 3
+PUT_DEFAULT, PUT_BORROW_PINNED = 0, 1
 
 
 class FrostGPUError(RuntimeError):
@@ -110,6 +111,8 @@ _SIGNATURES = {
     "fgpu_abi_version": ([], C.c_int32),
     "fgpu_part_put_parquet": ([C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32], C.c_int32),
     "fgpu_part_put_arrow": ([C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p], C.c_int32),
+    "fgpu_host_alloc": ([C.c_uint64, C.POINTER(C.c_void_p)], C.c_int32),
+    "fgpu_host_free": ([C.c_void_p], C.c_int32),
     "fgpu_part_drop": ([C.c_void_p, C.c_char_p, C.c_uint64], C.c_int32),
     "fgpu_table_drop": ([C.c_void_p, C.c_char_p], C.c_int32),
     "fgpu_query_prepare": ([C.c_void_p, C.POINTER(Plan), C.POINTER(C.c_void_p)], C.c_int32),

@@ -122,6 +122,7 @@ struct fgpu_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::map<std::string, Table> tables;
+  std::vector<ColumnImage*> pending_uploads;  // staging to release after the next stream sync
 };
 
 struct fgpu_query {
@@ -182,6 +183,50 @@ struct fgpu_result {
 };
 
 namespace {
+
+// Uploads one column of one part if it is not resident yet: the host-assembled meta region with one
+// copy, the PLAIN value regions straight from the source file (one async copy per contiguous extent),
+// all on the engine stream so that kernels queued behind need no extra synchronisation.
+int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::string& column, uint64_t* h2d_bytes) {
+  build_column(kIndexRows, table, part, column);
+  ColumnImage& img = part->images[column];
+  if (!img.error.empty()) return FGPU_OK;  // surfaces as an error only if a query projects the column
+  if (img.resident) return FGPU_OK;
+  void* dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, img.dev_bytes));
+  cudaError_t e = cudaMemcpyAsync(dev, img.meta.data(), img.meta.size(), cudaMemcpyHostToDevice, ctx->stream);
+  for (const Extent& x : img.extents) {
+    if (e != cudaSuccess) break;
+    e = cudaMemcpyAsync(static_cast<uint8_t*>(dev) + x.dst_off, x.src, x.len, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    cudaGetLastError();
+    return fail(FGPU_ERR_CUDA, std::string("column upload: ") + cudaGetErrorString(e));
+  }
+  img.dev = dev;
+  img.resident = true;
+  patch_column_pointers(part, column, static_cast<const uint8_t*>(dev));
+  uint64_t n = img.meta.size();
+  for (const Extent& x : img.extents) n += x.len;
+  if (h2d_bytes) *h2d_bytes += n;
+  ctx->pending_uploads.push_back(&img);
+  return FGPU_OK;
+}
+
+// After the stream has been synchronised the host staging of uploaded columns can go.
+void release_staging(fgpu_ctx* ctx) {
+  for (ColumnImage* img : ctx->pending_uploads) {
+    std::vector<uint8_t>().swap(img->meta);
+    std::vector<Extent>().swap(img->extents);
+  }
+  ctx->pending_uploads.clear();
+}
+
+void free_part(Part* p) {
+  for (auto& kv : p->images)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+}
 
 struct VisibleRG {
   Part* part;
@@ -267,6 +312,7 @@ struct Compiled {
   std::vector<uint32_t> dense_radix;
   uint64_t total_rows = 0;
   uint64_t group_bound = 0;
+  uint64_t h2d_bytes = 0;  // column uploads this query triggered
 };
 
 int32_t compile_filter(const fgpu_query& q, int node, Compiled* c, std::map<std::string, int>& slot_of) {
@@ -431,6 +477,22 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   qd.n_slots = int32_t(c->slot_names.size());
   for (int s = 0; s < qd.n_slots; s++) {
     qd.slot_type[s] = c->slot_types[size_t(s)];
+  }
+  // Lazy residency: the columns this query projects are built and uploaded now (parts put with
+  // FGPU_PUT_BORROW_PINNED upload nothing until a query needs it; optimize.go:36-73 physical projection).
+  {
+    Part* last = nullptr;
+    for (const VisibleRG& v : c->rgs) {
+      if (v.part == last) continue;
+      last = v.part;
+      for (const std::string& name : c->slot_names) {
+        if (std::find(v.part->columns.begin(), v.part->columns.end(), name) == v.part->columns.end()) continue;
+        int32_t rc = ensure_resident(ctx, &table, v.part, name, &c->h2d_bytes);
+        if (rc) return rc;
+        const ColumnImage& img = v.part->images[name];
+        if (!img.error.empty()) return fail(FGPU_ERR_UNSUPPORTED, "column " + name + ": " + img.error);
+      }
+    }
   }
   // shared-memory ring of the scan kernel: stage every numeric slot's PLAIN slice (up to kMaxStagePlain)
   // and the chunk seeds of every hybrid stream (up to kMaxStageSeeds); the rest is read from HBM directly
@@ -939,6 +1001,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   unsigned long long counters[8] = {0};
   CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));  // hostaux / counters stay valid until here
+  release_staging(ctx);
+  st.h2d_bytes += c.h2d_bytes;
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
   st.scan_kernel_ms = ms;
@@ -1210,8 +1274,7 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
   if (!ctx) return FGPU_OK;
   cudaSetDevice(ctx->device);
   for (auto& t : ctx->tables)
-    for (auto& p : t.second.parts)
-      if (p->dev) cudaFree(p->dev);
+    for (auto& p : t.second.parts) free_part(p.get());
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1222,7 +1285,7 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
 int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx, const uint8_t* file,
                               uint64_t len, int32_t flags) {
   if (!ctx || !table || !file) return fail(FGPU_ERR_INVALID, "null argument");
-  if (flags != FGPU_PUT_DEFAULT) return fail(FGPU_ERR_UNSUPPORTED, "put flags other than FGPU_PUT_DEFAULT are not implemented yet");
+  if (flags != FGPU_PUT_DEFAULT && flags != FGPU_PUT_BORROW_PINNED) return fail(FGPU_ERR_INVALID, "unknown put flags");
   std::lock_guard<std::mutex> lk(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
   Table& t = ctx->tables[table];
@@ -1231,20 +1294,26 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   auto part = std::make_unique<Part>();
   part->id = part_id;
   part->tx = tx;
+  part->borrowed = flags == FGPU_PUT_BORROW_PINNED;
   std::string err;
-  if (!build_part_image(file, len, kIndexRows, &t, part.get(), &err)) return fail(FGPU_ERR_PARQUET, err);
-  void* dev = nullptr;
-  CUDA_TRY(cudaMalloc(&dev, part->image.size()));
-  cudaError_t e = cudaMemcpyAsync(dev, part->image.data(), part->image.size(), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) {
-    cudaFree(dev);
-    return fail(FGPU_ERR_CUDA, std::string("part upload: ") + cudaGetErrorString(e));
+  if (!open_part(file, len, part.get(), &err)) return fail(FGPU_ERR_PARQUET, err);
+  if (!part->borrowed) {
+    // The caller may reuse the buffer on return: every column goes to the device now.
+    for (const std::string& col : part->columns) {
+      int32_t rc = ensure_resident(ctx, &t, part.get(), col, nullptr);
+      if (rc) {
+        free_part(part.get());
+        return rc;
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    release_staging(ctx);
+    if (e != cudaSuccess) {
+      free_part(part.get());
+      return fail(FGPU_ERR_CUDA, std::string("part upload: ") + cudaGetErrorString(e));
+    }
+    part->file = nullptr;
   }
-  part->dev = dev;
-  part->dev_bytes = part->image.size();
-  patch_part_pointers(part.get(), static_cast<const uint8_t*>(dev));
-  std::vector<uint8_t>().swap(part->image);
   t.parts.push_back(std::move(part));
   return FGPU_OK;
 }
@@ -1264,7 +1333,9 @@ int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {
   for (size_t i = 0; i < parts.size(); i++) {
     if (parts[i]->id == part_id) {
       cudaSetDevice(ctx->device);
-      if (parts[i]->dev) cudaFree(parts[i]->dev);
+      cudaStreamSynchronize(ctx->stream);
+      release_staging(ctx);
+      free_part(parts[i].get());
       parts.erase(parts.begin() + long(i));
       return FGPU_OK;
     }
@@ -1278,8 +1349,9 @@ int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
   auto it = ctx->tables.find(table);
   if (it == ctx->tables.end()) return FGPU_OK;
   cudaSetDevice(ctx->device);
-  for (auto& p : it->second.parts)
-    if (p->dev) cudaFree(p->dev);
+  cudaStreamSynchronize(ctx->stream);
+  release_staging(ctx);
+  for (auto& p : it->second.parts) free_part(p.get());
   ctx->tables.erase(it);
   return FGPU_OK;
 }
@@ -1428,6 +1500,23 @@ int32_t fgpu_result_free(fgpu_result* r) {
   return FGPU_OK;
 }
 
+int32_t fgpu_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return fail(FGPU_ERR_INVALID, "null argument");
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? FGPU_ERR_OOM : FGPU_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return FGPU_OK;
+}
+
+int32_t fgpu_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+  return FGPU_OK;
+}
+
 int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, uint8_t* buf, uint64_t cap,
                          uint64_t* out_len, uint32_t* out_count) {
   if (!ctx || !table || !column || !out_len || !out_count) return fail(FGPU_ERR_INVALID, "null argument");
@@ -1527,6 +1616,12 @@ int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_
   for (auto& p : it->second.parts)
     if (p->id == part_id) part = p.get();
   if (!part) return fail(FGPU_ERR_NOT_FOUND, "part not found");
+  {
+    int32_t rc = ensure_resident(ctx, &it->second, part, column, nullptr);
+    if (rc) return rc;
+    const ColumnImage& img = part->images[column];
+    if (!img.error.empty() && img.error != "column not in part") return fail(FGPU_ERR_UNSUPPORTED, std::string(column) + ": " + img.error);
+  }
   uint64_t total = 0;
   int phys = -1;
   for (auto& rg : part->rgs) {
@@ -1589,6 +1684,7 @@ int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_
     }
     if (col.null_count == 0) col.validity.clear();
   }
+  release_staging(ctx);
   export_column(std::move(col), out_schema, out_array);
   return FGPU_OK;
 }

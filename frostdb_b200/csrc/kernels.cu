@@ -1,10 +1,9 @@
 // sm_100a kernels of libfrostgpu.
 //
-//   k_scan<KW>   K1+K2+K4/K5 fused.  Every consumer warp streams one 128-row chunk of a row group at a time:
-//                it walks the stored Parquet encodings of the projected column chunks directly in HBM
-//                (PLAIN int64/double, RLE/bit-packed hybrid definition levels and dictionary indices)
-//                with per-lane run cursors seeded from a per-chunk seed, evaluates the predicate
-//                leaves into per-row bits, and folds the selected rows into the aggregate table.
+//   k_scan       K1+K2+K4/K5 fused.  Every warp walks the stored Parquet encodings of the projected column
+//                chunks (PLAIN int64/double, RLE/bit-packed hybrid definition levels and dictionary
+//                indices) with per-lane run cursors seeded from a per-128-row seed, evaluates the
+//                predicate leaves, and folds the selected rows into the aggregate table.
 //                Rows whose group does not change inside a warp (the common case for parts sorted in
 //                compaction order) are accumulated in registers and flushed with ONE warp-reduced
 //                atomic per aggregate when the group changes; mixed groups fall back to
@@ -19,11 +18,13 @@
 //                HashAggregate, synchronize.go:16-53, physicalplan.go:438-471).
 //   k_decode     K1 standalone: one column chunk -> dense buffers.
 //
-// HBM-bound integer / indexing work: no tensor cores.  In k_scan a dedicated producer warp keeps a
-// shared-memory ring of tiles full with cp.async.bulk (TMA bulk copies completing on mbarriers): the
-// PLAIN column slices of the tile and the 8 cursor seeds of every hybrid stream.  The 8 consumer warps
-// therefore never wait on an HBM round trip in the common case; what they still read from global
-// memory (run directory entries past the seed, bit-packed payload, LUTs) is small and L2 resident.
+// HBM-bound integer / indexing work: no tensor cores.  k_scan is a vectorized engine: every warp owns
+// vectors of 512 rows, prefetches the vector's PLAIN column slices and hybrid-stream seeds into a
+// private shared-memory ring with 16-byte cp.async (LDGSTS) groups two vectors ahead, and runs either
+// a fused register-only pass (conjunctive range filter + dense dictionary keys + Sum/Min/Max/Count) or
+// a general column-at-a-time path with per-row intermediates in shared memory.  (A cp.async.bulk/TMA
+// ring was measured first: 2 KB bulk copies cost ~0.37 us each per SM and cap the chip at ~0.8 TB/s,
+// so the bulk-copy engine is the wrong tool for per-warp vectors; see DESIGN.md.)
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -45,36 +46,7 @@ static_assert(STEPS == 4, "unrolled for 4 steps");
 constexpr uint32_t kNoSlot = 0xffffffffu;
 constexpr uint32_t FULL = 0xffffffffu;
 
-// ---- mbarrier / bulk-copy primitives (sm_90+ PTX) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA, non-tensor form); bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // ---- hybrid stream cursor ------------------------------------------------------------------------------
 struct HybCur {
@@ -383,47 +355,6 @@ __device__ __forceinline__ long long apply_arith(uint8_t op, bool is_float, long
       if (rb == 0) return 0;
       if (rb == -1) return (long long)(0ull - l);  // Go wraps INT64_MIN / -1
       return lb / rb;
-  }
-}
-
-// Values of aggregate `a` for the chunk's rows.  Evaluated column-at-a-time over a small operand stack
-// of 8-row vectors (depth <= 3; deeper expressions are rejected by the host).
-__device__ __forceinline__ void eval_agg_values(const TileCtx& t, const AggDesc& a, int lane, long long (&out)[STEPS]) {
-  const QueryDesc& q = *t.q;
-  long long s1[STEPS], s2[STEPS];
-  int sp = 0;
-  for (int p = a.prog_off; p < a.prog_off + a.prog_len; p++) {
-    const ProgOp& o = q.prog[p];
-    if (o.op == PO_LOAD || o.op == PO_CONST) {
-      long long v[STEPS];
-      if (o.op == PO_LOAD) {
-        uint32_t nm;
-        tile_num(t, o.slot, lane, v, nm);
-      } else {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) v[j] = o.imm;
-      }
-      if (sp == 0) {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) out[j] = v[j];
-      } else if (sp == 1) {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) s1[j] = v[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) s2[j] = v[j];
-      }
-      sp++;
-    } else {
-      if (sp == 2) {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) out[j] = apply_arith(o.op, a.is_float, out[j], s1[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < STEPS; j++) s1[j] = apply_arith(o.op, a.is_float, s1[j], s2[j]);
-      }
-      sp--;
-    }
   }
 }
 

@@ -10,9 +10,14 @@ namespace {
 constexpr size_t kAlign = 128;
 constexpr size_t kTailPad = 16;
 
+// Column image layout: [meta region: every section the host assembles][extent region: PLAIN value
+// bytes copied verbatim from the source file].  Section offsets of the extent region are recorded
+// relative to its start and rebased when the meta size is final.
 struct ImageWriter {
   std::vector<uint8_t>& buf;
-  explicit ImageWriter(std::vector<uint8_t>& b) : buf(b) {}
+  std::vector<Extent>& extents;
+  uint64_t ext_size = 0;
+  ImageWriter(std::vector<uint8_t>& b, std::vector<Extent>& e) : buf(b), extents(e) {}
   size_t begin() {
     size_t n = (buf.size() + kAlign - 1) / kAlign * kAlign;
     buf.resize(n, 0);
@@ -29,6 +34,20 @@ struct ImageWriter {
     end();
     return int64_t(off);
   }
+  // reserves an aligned hole in the extent region; returns its offset inside that region
+  uint64_t begin_extent() {
+    ext_size = (ext_size + kAlign - 1) / kAlign * kAlign;
+    return ext_size;
+  }
+  void add_extent(const uint8_t* src, uint64_t len) {
+    if (len == 0) return;
+    if (!extents.empty() && extents.back().src + extents.back().len == src && extents.back().dst_off + extents.back().len == ext_size)
+      extents.back().len += len;  // contiguous in the file too: one copy
+    else
+      extents.push_back({src, len, ext_size});
+    ext_size += len;
+  }
+  void end_extent() { ext_size += kTailPad; }
 };
 
 inline void or_bits(std::vector<uint64_t>& bm, uint64_t pos, uint64_t bits8) {
@@ -167,12 +186,10 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
     }
     out->desc.kind = (leaf.phys == PT_BYTE_ARRAY) ? CK_DICT_STR : CK_DICT64;
   } else {
-    vstream.reserve(size_t(n_values) * 8);
     for (size_t p = 0; p < cm.pages.size(); p++) {
       const PageInfo& pg = cm.pages[p];
       uint64_t need = uint64_t(page_nn[p]) * 8;
       if (need > pg.values_len) { out->error = "PLAIN page shorter than its value count"; return; }
-      vstream.insert(vstream.end(), pg.values, pg.values + need);
     }
     out->desc.kind = CK_PLAIN64;
   }
@@ -255,7 +272,19 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   out->desc.has_nulls = has_nulls ? 1 : 0;
   out->desc.n_values = n_values;
   out->desc.dict_size = dict_size;
-  out->off_values = w.section(vstream.data(), vstream.size());
+  uint64_t plain_bytes = 0;
+  if (out->desc.kind == CK_PLAIN64) {
+    // value regions go to the device straight from the file: negative offsets mark "extent region"
+    const uint64_t eoff = w.begin_extent();
+    for (size_t p = 0; p < cm.pages.size(); p++) {
+      w.add_extent(cm.pages[p].values, uint64_t(page_nn[p]) * 8);
+      plain_bytes += uint64_t(page_nn[p]) * 8;
+    }
+    w.end_extent();
+    out->off_values = -int64_t(eoff) - 1;
+  } else {
+    out->off_values = w.section(vstream.data(), vstream.size());
+  }
   if (out->desc.kind != CK_PLAIN64) {
     std::vector<Seed> seeds = make_seeds(vruns, n_values, false);
     out->desc.n_runs = uint32_t(vruns.size());
@@ -275,54 +304,82 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   }
   if (out->desc.kind == CK_DICT_STR) out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
   if (out->desc.kind == CK_DICT64) out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
+  (void)plain_bytes;
   const size_t payload = vstream.size() + (has_nulls ? defstream.size() : 0);
   out->meta_bytes = (w.buf.size() - before) - std::min(w.buf.size() - before, payload);
 }
 
 }  // namespace
 
-bool build_part_image(const uint8_t* file, uint64_t len, int tile_rows, Table* table, Part* part, std::string* err) {
-  ParsedFile pf;
-  if (!parse_parquet(file, len, &pf, err)) return false;
+bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) {
+  if (!parse_parquet(file, len, &part->pf, err)) return false;
+  part->file = file;
   part->file_bytes = len;
   part->columns.clear();
-  for (const SchemaLeaf& l : pf.leaves) part->columns.push_back(l.name);
-  part->image.clear();
-  part->image.reserve(size_t(len) + size_t(len) / 4 + 4096);
-  ImageWriter w(part->image);
-  for (const RowGroupMeta& rg : pf.row_groups) {
+  for (const SchemaLeaf& l : part->pf.leaves) part->columns.push_back(l.name);
+  for (const RowGroupMeta& rg : part->pf.row_groups) {
     if (rg.num_rows == 0) continue;
     if (rg.num_rows > 0x7fffffffll) { *err = "row group with more than 2^31 rows"; return false; }
     RowGroupHost h;
     h.n_rows = uint32_t(rg.num_rows);
     for (size_t c = 0; c < rg.chunks.size(); c++) {
-      const SchemaLeaf& leaf = pf.leaves[c];
-      GlobalDict* dict = (leaf.phys == PT_BYTE_ARRAY) ? &table->dicts[leaf.name] : nullptr;
-      ChunkHost ch;
-      build_chunk(rg.chunks[c], leaf, h.n_rows, tile_rows, dict, w, &ch);
-      h.cols.emplace(leaf.name, std::move(ch));
+      ChunkHost ch;  // skeleton: type and footer size are known before the column is built
+      ch.phys = part->pf.leaves[c].phys;
+      ch.stored_bytes = uint64_t(rg.chunks[c].total_compressed_size);
+      ch.desc.n_rows = h.n_rows;
+      h.cols.emplace(part->pf.leaves[c].name, std::move(ch));
     }
     part->rgs.push_back(std::move(h));
   }
-  if (part->image.empty()) part->image.resize(kAlign, 0);
   return true;
 }
 
-void patch_part_pointers(Part* part, const uint8_t* base) {
+void build_column(int index_rows, Table* table, Part* part, const std::string& column) {
+  ColumnImage& img = part->images[column];
+  if (img.built) return;
+  img.built = true;
+  size_t leaf = part->pf.leaves.size();
+  for (size_t c = 0; c < part->pf.leaves.size(); c++)
+    if (part->pf.leaves[c].name == column) leaf = c;
+  if (leaf == part->pf.leaves.size()) { img.error = "column not in part"; return; }
+  const SchemaLeaf& sl = part->pf.leaves[leaf];
+  GlobalDict* dict = (sl.phys == PT_BYTE_ARRAY) ? &table->dicts[column] : nullptr;
+  ImageWriter w(img.meta, img.extents);
+  size_t g = 0;
+  for (const RowGroupMeta& rg : part->pf.row_groups) {
+    if (rg.num_rows == 0) continue;
+    RowGroupHost& h = part->rgs[g++];
+    ChunkHost ch;
+    build_chunk(rg.chunks[leaf], sl, h.n_rows, index_rows, dict, w, &ch);
+    if (!ch.error.empty() && img.error.empty()) img.error = ch.error;
+    h.cols[column] = std::move(ch);
+  }
+  if (img.meta.empty()) img.meta.resize(kAlign, 0);
+  // rebase extent offsets behind the (128-aligned) meta region
+  const uint64_t meta_size = (img.meta.size() + kAlign - 1) / kAlign * kAlign;
+  for (Extent& e : img.extents) e.dst_off += meta_size;
+  for (RowGroupHost& h : part->rgs) {
+    ChunkHost& ch = h.cols[column];
+    if (ch.off_values < -0) ch.off_values = int64_t(meta_size) + (-ch.off_values - 1);
+  }
+  img.dev_bytes = meta_size + w.ext_size + kAlign;
+}
+
+void patch_column_pointers(Part* part, const std::string& column, const uint8_t* base) {
   for (RowGroupHost& rg : part->rgs) {
-    for (auto& kv : rg.cols) {
-      ChunkHost& c = kv.second;
-      if (!c.error.empty()) continue;
-      auto at = [&](int64_t off) -> const uint8_t* { return off < 0 ? nullptr : base + off; };
-      c.desc.values = at(c.off_values);
-      c.desc.runs = reinterpret_cast<const Run*>(at(c.off_runs));
-      c.desc.seeds = reinterpret_cast<const Seed*>(at(c.off_seeds));
-      c.desc.def = at(c.off_def);
-      c.desc.def_runs = reinterpret_cast<const Run*>(at(c.off_def_runs));
-      c.desc.def_seeds = reinterpret_cast<const Seed*>(at(c.off_def_seeds));
-      c.desc.lut = reinterpret_cast<const uint32_t*>(at(c.off_lut));
-      c.desc.dict64 = reinterpret_cast<const int64_t*>(at(c.off_dict64));
-    }
+    auto it = rg.cols.find(column);
+    if (it == rg.cols.end()) continue;
+    ChunkHost& c = it->second;
+    if (!c.error.empty()) continue;
+    auto at = [&](int64_t off) -> const uint8_t* { return off < 0 ? nullptr : base + off; };
+    c.desc.values = at(c.off_values);
+    c.desc.runs = reinterpret_cast<const Run*>(at(c.off_runs));
+    c.desc.seeds = reinterpret_cast<const Seed*>(at(c.off_seeds));
+    c.desc.def = at(c.off_def);
+    c.desc.def_runs = reinterpret_cast<const Run*>(at(c.off_def_runs));
+    c.desc.def_seeds = reinterpret_cast<const Seed*>(at(c.off_def_seeds));
+    c.desc.lut = reinterpret_cast<const uint32_t*>(at(c.off_lut));
+    c.desc.dict64 = reinterpret_cast<const int64_t*>(at(c.off_dict64));
   }
 }
 
@@ -345,11 +402,22 @@ void json_escape(std::ostringstream& o, const std::string& s) {
 std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows, std::string* err) {
   Table table;
   Part part;
-  if (!build_part_image(file, len, tile_rows, &table, &part, err)) return "";
-  patch_part_pointers(&part, part.image.data());  // pointers into the host image
+  if (!open_part(file, len, &part, err)) return "";
+  std::vector<std::vector<uint8_t>> host_images;  // one flat host copy per column (meta + extents)
+  uint64_t image_bytes = 0;
+  for (const std::string& name : part.columns) {
+    build_column(tile_rows, &table, &part, name);
+    ColumnImage& img = part.images[name];
+    std::vector<uint8_t> flat(size_t(img.dev_bytes), 0);
+    std::memcpy(flat.data(), img.meta.data(), img.meta.size());
+    for (const Extent& e : img.extents) std::memcpy(flat.data() + e.dst_off, e.src, size_t(e.len));
+    host_images.push_back(std::move(flat));
+    patch_column_pointers(&part, name, host_images.back().data());  // pointers into the host image
+    image_bytes += img.dev_bytes;
+  }
   const uint32_t T = uint32_t(tile_rows);
   std::ostringstream o;
-  o << "{\"image_bytes\":" << part.image.size() << ",\"file_bytes\":" << len << ",\"row_groups\":[";
+  o << "{\"image_bytes\":" << image_bytes << ",\"file_bytes\":" << len << ",\"row_groups\":[";
   for (size_t g = 0; g < part.rgs.size(); g++) {
     const RowGroupHost& rg = part.rgs[g];
     if (g) o << ',';

@@ -49,14 +49,35 @@ struct RowGroupHost {
   std::map<std::string, ChunkHost> cols;
 };
 
+// A byte range of the source Parquet file that is copied to the device as is (PLAIN value regions):
+// no host-side copy is made, the H2D copy reads straight from the (ideally pinned) source buffer.
+struct Extent {
+  const uint8_t* src;
+  uint64_t len;
+  uint64_t dst_off;  // offset inside the column image
+};
+
+// Device residency of one column of one part (all its row groups in one allocation).
+struct ColumnImage {
+  bool built = false;      // host side done (ChunkHosts filled, dictionary interned)
+  bool resident = false;   // bytes are on the device
+  void* dev = nullptr;
+  uint64_t dev_bytes = 0;
+  std::vector<uint8_t> meta;     // host staging of everything that is not an extent (kept until uploaded)
+  std::vector<Extent> extents;
+  std::string error;             // whole-column error (a chunk the engine cannot read)
+};
+
 struct Part {
   uint64_t id = 0, tx = 0;
+  const uint8_t* file = nullptr;    // source bytes: borrowed (caller keeps them alive) or `owned`
+  uint64_t file_bytes = 0;
+  std::vector<uint8_t> owned;
+  bool borrowed = false;
+  ParsedFile pf;
   std::vector<RowGroupHost> rgs;
   std::vector<std::string> columns;  // schema order
-  void* dev = nullptr;               // the part's single device allocation
-  uint64_t dev_bytes = 0;
-  uint64_t file_bytes = 0;
-  std::vector<uint8_t> image;        // host image (kept only until upload)
+  std::map<std::string, ColumnImage> images;
 };
 
 struct Table {
@@ -64,12 +85,16 @@ struct Table {
   std::map<std::string, GlobalDict> dicts;   // by column name
 };
 
-// Builds the host image of a part (no CUDA calls): sections for every readable column chunk,
-// run directories, tile indexes, dictionary LUTs.  Interns dictionary entries into `table`.
-bool build_part_image(const uint8_t* file, uint64_t len, int tile_rows, Table* table, Part* part, std::string* err);
+// Parses footer + page headers and prepares the row-group skeleton (no column is built yet).
+bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err);
 
-// Patches device pointers into every ChunkDesc once the image lives at `dev_base`.
-void patch_part_pointers(Part* part, const uint8_t* dev_base);
+// Builds the host side of one column of a part (no CUDA calls): run directories, seeds, dictionary
+// LUTs into `image.meta`, PLAIN value regions as extents.  Interns dictionary entries into `table`.
+// ChunkDesc pointers are offsets until patch_column_pointers() is called.
+void build_column(int index_rows, Table* table, Part* part, const std::string& column);
+
+// Patches device pointers into the column's ChunkDescs once the image lives at `dev_base`.
+void patch_column_pointers(Part* part, const std::string& column, const uint8_t* dev_base);
 
 // JSON description for fgpu_parquet_describe (host-only tests).
 std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows, std::string* err);

@@ -43,7 +43,7 @@ class GPUEngine:
         self.close()
 
     # ---- parts -------------------------------------------------------------------------------
-    def put_parquet(self, table: str, buf, tx: Optional[int] = None, part_id: Optional[int] = None) -> int:
+    def put_parquet(self, table: str, buf, tx: Optional[int] = None, part_id: Optional[int] = None, borrow: bool = False) -> int:
         lib = _lib.load()
         pid = self._next_part.get(table, 0) if part_id is None else part_id
         self._next_part[table] = max(self._next_part.get(table, 0), pid + 1)
@@ -54,7 +54,10 @@ class GPUEngine:
             addr, n = C.addressof(src), len(buf)
         else:  # numpy uint8 array: no copy
             addr, n = buf.ctypes.data, buf.nbytes
-        _lib.check(lib.fgpu_part_put_parquet(self.handle, table.encode(), pid, tx, addr, n, 0))
+        if borrow and isinstance(buf, (bytes, bytearray, memoryview)):
+            raise ValueError("borrowed parts must live in caller-owned (pinned) memory: pass a numpy array")
+        _lib.check(lib.fgpu_part_put_parquet(self.handle, table.encode(), pid, tx, addr, n,
+                                             _lib.PUT_BORROW_PINNED if borrow else _lib.PUT_DEFAULT))
         self._watermarks[table] = max(self._watermarks.get(table, 0), tx)
         return pid
 
@@ -166,3 +169,27 @@ class ColumnStore:
 
     def Close(self) -> None:
         self.engine.close()
+
+
+class PinnedBuffer:
+    """Page-locked host memory from fgpu_host_alloc, viewed as a numpy uint8 array (`.array`)."""
+
+    def __init__(self, nbytes: int):
+        import numpy as np
+        self._lib = _lib.load()
+        p = C.c_void_p()
+        _lib.check(self._lib.fgpu_host_alloc(nbytes, C.byref(p)))
+        self.ptr, self.nbytes = p, nbytes
+        self.array = np.frombuffer((C.c_uint8 * nbytes).from_address(p.value), dtype=np.uint8)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._lib.fgpu_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -191,9 +191,10 @@ enum {
                                 columns too, optimize.go:36-73)                                  */
 };
 
-/* Parses footer + page headers on the host, registers dictionary entries in the table's global
- * dictionaries, builds the run directories / tile indexes and (unless BORROW_PINNED) uploads the
- * page payloads to HBM.  The buffer is copied: the caller may free it on return.
+/* Parses footer + page headers on the host.  FGPU_PUT_DEFAULT then builds every column (run
+ * directories, chunk seeds, global dictionary ids) and uploads it, and the caller may free the
+ * buffer on return.  FGPU_PUT_BORROW_PINNED keeps the pointer instead: a column is built and
+ * uploaded by the first query that projects it, its PLAIN pages DMA'd straight from `file`.
  * `tx` is the part's transaction id (parts.Part.TX()). */
 int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx,
                               const uint8_t* file, uint64_t len, int32_t flags);
@@ -203,6 +204,11 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
  * dictionary<uint32|int32, binary|utf8>. */
 int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx,
                             struct ArrowSchema* schema, struct ArrowArray* array);
+
+/* Page-locked host memory for parts handed over with FGPU_PUT_BORROW_PINNED (the Go side would
+ * write the compacted part straight into such a buffer instead of a bytes.Buffer, table.go:1267). */
+int32_t fgpu_host_alloc(uint64_t bytes, void** out);
+int32_t fgpu_host_free(void* p);
 
 int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id);
 int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table);
