@@ -1,0 +1,117 @@
+"""CPU-only tests of the host half of libfrostgpu: the C-ABI surface, the Parquet parser / run
+directories / chunk seeds (checked against pyarrow's independent decode), error behaviour."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from frostdb_b200 import _lib
+from frostdb_b200 import dynparquet as dp
+from tests.util import make_columns
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "frostgpu.h")).read()
+    declared = set(re.findall(r"\b(fgpu_[a-z_0-9]+)\s*\(", hdr)) - {"fgpu_match_fn"}
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(built_lib, name), f"{name} is declared in include/frostgpu.h but not exported"
+        assert name in _lib._SIGNATURES, f"{name} has no ctypes signature in frostdb_b200/_lib.py"
+    assert built_lib.fgpu_abi_version() == _lib.ABI_VERSION
+
+
+def test_init_without_device_fails_loudly(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = _lib.Config(abi_version=_lib.ABI_VERSION, device=0, tile_rows=0, flags=0, staging_bytes=0)
+    h = C.c_void_p()
+    rc = built_lib.fgpu_init(C.byref(cfg), C.byref(h))
+    assert rc == _lib.FGPU_ERR_NO_DEVICE
+    assert b"no CUDA device" in built_lib.fgpu_last_error()
+    # and the Python mirror refuses to exist without the engine: there is no CPU fallback
+    from frostdb_b200.store import ColumnStore
+    with pytest.raises(_lib.FrostGPUError):
+        ColumnStore(0)
+
+
+def _check_against_pyarrow(buf):
+    d = _lib.describe_parquet(buf)
+    ref = dp.read_part(buf)
+    row = 0
+    for rg in d["row_groups"]:
+        for name, c in rg["columns"].items():
+            assert "error" not in c, (name, c)
+            assert c["tile_index_ok"], name
+            exp = ref.column(name).slice(row, rg["n_rows"])
+            if pa.types.is_dictionary(exp.type):
+                exp = exp.cast(pa.string())
+            assert c["decoded"] == exp.to_pylist(), name
+        row += rg["n_rows"]
+    return d
+
+
+@pytest.mark.parametrize("version", ["2.0", "1.0"])
+@pytest.mark.parametrize("sort", [True, False])
+@pytest.mark.parametrize("page_size", [256, 4096, 1 << 20])
+def test_run_directories_and_seeds_match_pyarrow(built_lib, version, sort, page_size):
+    cols = make_columns(9000, 5, {"a": (6, 0.0), "b": (500, 0.07), "c": (2, 0.95), "d": (40_000, 0.01)}, with_float=True,
+                        float_null_p=0.35)
+    buf = dp.write_part(dp.SampleDefinitionWithFloat(), cols, sort=sort, row_group_size=3100, data_page_size=page_size,
+                        data_page_version=version)
+    d = _check_against_pyarrow(buf)
+    kinds = {n: c["kind"] for n, c in d["row_groups"][0]["columns"].items()}
+    assert kinds["timestamp"] == 1 and kinds["labels.a"] == 2  # PLAIN64 / DICT_STR
+
+
+def test_edge_shapes(built_lib):
+    schema = dp.SampleDefinitionWithFloat()
+    # single row, all-NULL dynamic column, rows == chunk boundary +-1
+    for n in (1, 127, 128, 129, 2047, 2048, 2049):
+        cols = make_columns(n, n, {"a": (3, 0.0), "z": (2, 1.0)}, with_float=True, float_null_p=1.0 if n % 2 else 0.5)
+        _check_against_pyarrow(dp.write_part(schema, cols, row_group_size=max(1, n // 2 + 1)))
+
+
+def test_int64_dictionary_encoded_pages(built_lib):
+    """north_star: RLE-dictionary for int64 timestamp columns (pyarrow's default dictionary encoding)."""
+    import io
+    import pyarrow.parquet as pq
+    n = 5000
+    t = pa.table({"timestamp": pa.array(np.arange(n) // 7, type=pa.int64()),
+                  "value": pa.array((np.arange(n) * 31) % 11, type=pa.int64())})
+    t = t.cast(pa.schema([pa.field("timestamp", pa.int64(), nullable=False), pa.field("value", pa.int64(), nullable=True)]))
+    sink = io.BytesIO()
+    pq.write_table(t, sink, compression="NONE", use_dictionary=True, data_page_version="2.0", store_schema=False)
+    d = _check_against_pyarrow(sink.getvalue())
+    assert d["row_groups"][0]["columns"]["timestamp"]["kind"] == 3  # DICT64
+
+
+def test_rejects_what_it_cannot_read(built_lib):
+    with pytest.raises(_lib.FrostGPUError) as e:
+        _lib.describe_parquet(b"not a parquet file at all")
+    assert e.value.code == _lib.FGPU_ERR_PARQUET
+    # compressed chunks: parsed, but flagged per column so that only a query projecting them fails
+    import io
+    import pyarrow.parquet as pq
+    sink = io.BytesIO()
+    pq.write_table(pa.table({"value": pa.array([1, 2, 3], type=pa.int64())}), sink, compression="SNAPPY")
+    d = _lib.describe_parquet(sink.getvalue())
+    assert "compressed" in d["row_groups"][0]["columns"]["value"]["error"]
+    # truncated file
+    good = dp.write_part(dp.SampleDefinition(), make_columns(100, 1, {"a": (3, 0.0)}))
+    with pytest.raises(_lib.FrostGPUError):
+        _lib.describe_parquet(good[: len(good) // 2])
+
+
+def test_dictionary_values_of_a_file(built_lib):
+    cols = make_columns(3000, 9, {"a": (17, 0.2)})
+    buf = dp.write_part(dp.SampleDefinition(), cols, row_group_size=1000)
+    vals = _lib.parquet_dict_values(buf, "labels.a")
+    ref = set(x for x in dp.read_part(buf)["labels.a"].cast(pa.string()).to_pylist() if x is not None)
+    assert set(v.decode() for v in vals) == ref and len(vals) == len(ref)
+    assert _lib.parquet_dict_values(buf, "labels.nope") == []

@@ -1,0 +1,77 @@
+"""The CPU oracle pinned beyond the logictest files: its Parquet decode against pyarrow, and the
+engine-level expectations of the reference's Go tests (aggregate_test.go, db_test.go)."""
+import pyarrow as pa
+import pytest
+
+from frostdb_b200 import dynparquet as dp
+from frostdb_b200 import logicalplan as lp
+from oracle import oracle as orc
+from tests.oracle_scan import OracleEngine, OracleTableHandle, oracle_query
+from tests.util import make_columns, rows_of
+
+
+@pytest.mark.parametrize("version", ["2.0", "1.0"])
+def test_oracle_decode_matches_pyarrow(version):
+    cols = make_columns(7000, 3, {"a": (9, 0.0), "b": (700, 0.05), "c": (2, 0.9)}, with_float=True, float_null_p=0.4)
+    buf = dp.write_part(dp.SampleDefinitionWithFloat(), cols, row_group_size=2500, data_page_size=1024, data_page_version=version)
+    t = orc.OracleTable()
+    t.add_parquet(buf)
+    ref = dp.read_part(buf)
+    row = 0
+    for rg in range(3):
+        n = min(2500, 7000 - row)
+        for name in ("labels.a", "labels.b", "labels.c", "timestamp", "value", "floatvalue", "stacktrace"):
+            exp = ref[name].slice(row, n)
+            if pa.types.is_dictionary(exp.type):
+                exp = exp.cast(pa.string())
+            assert t.decode_column(0, rg, name) == exp.to_pylist(), (rg, name)
+        row += n
+    t.close()
+
+
+def _samples_inconsistent_schema(eng):
+    """aggregate_test.go:40-73: three single-row inserts with different dynamic label columns."""
+    t = OracleTableHandle(eng, "test", dp.SampleDefinition())
+    for labels, ts, v in (({"label1": "value1"}, 1, 1), ({"label2": "value2"}, 2, 2), ({"label2": "value2"}, 3, 3)):
+        cols = {"example_type": [""], "stacktrace": ["s"], "timestamp": [ts], "value": [v]}
+        for k, val in labels.items():
+            cols["labels." + k] = [val]
+        t.Insert(cols)
+
+
+@pytest.mark.parametrize("fn,alias,expected", [
+    (lp.Sum, "value_sum", [5, 1]), (lp.Min, "value_min", [2, 1]), (lp.Max, "value_max", [3, 1]),
+    (lp.Count, "value_count", [2, 1]), (lp.Avg, "value_avg", [2, 1])])
+def test_aggregate_inconsistent_schema(fn, alias, expected):
+    """TestAggregateInconsistentSchema, aggregate_test.go:23-148 (expected values :85-110)."""
+    eng = OracleEngine(threads=2)
+    try:
+        _samples_inconsistent_schema(eng)
+        out = []
+        oracle_query(eng, "test").Aggregate([fn(lp.Col("value"))], [lp.Col("labels.label2")]) \
+            .Project(fn(lp.Col("value")).Alias(alias)).Execute(None, lambda c, r: out.append(r))
+        assert len(out) == 1 and out[0].schema.names == [alias]
+        assert sorted(out[0].column(0).to_pylist(), reverse=True) == expected
+    finally:
+        eng.close()
+
+
+def test_aggregation_projection_union_of_dynamic_columns():
+    """TestAggregationProjection, aggregate_test.go:150-258: group by stacktrace + every label column;
+    the result is the union of the dynamic columns, NULL where a group never saw one (:246-257)."""
+    eng = OracleEngine(threads=3)
+    try:
+        t = OracleTableHandle(eng, "test", dp.SampleDefinition())
+        for labels, ts, v in (({"label1": "value1"}, 1, 1), ({"label2": "value2"}, 2, 2), ({"label2": "value2", "label3": "x"}, 3, 3)):
+            cols = {"example_type": [""], "stacktrace": ["s"], "timestamp": [ts], "value": [v]}
+            for k, val in labels.items():
+                cols["labels." + k] = [val]
+            t.Insert(cols)
+        out = []
+        oracle_query(eng, "test").Aggregate([lp.Sum(lp.Col("value")), lp.Max(lp.Col("value"))],
+                                            [lp.DynCol("labels"), lp.Col("stacktrace")]).Execute(None, lambda c, r: out.append(r))
+        names = ["labels.label1", "labels.label2", "labels.label3", "stacktrace", "sum(value)", "max(value)"]
+        assert rows_of(out, names) == sorted([("value1", None, None, "s", 1, 1), (None, "value2", None, "s", 2, 2),
+                                              (None, "value2", "x", "s", 3, 3)], key=lambda r: tuple((x is None, x) for x in r))
+    finally:
+        eng.close()
