@@ -1,0 +1,71 @@
+// Package frostgpu is the cgo binding of libfrostgpu (include/frostgpu.h).
+//
+// NOT BUILT IN THIS REPOSITORY'S CI: the build image has no Go toolchain (`go version` -> not
+// found).  The file documents, as compilable-looking Go, the exact calls a FrostDB maintainer adds;
+// the same C-ABI is exercised by frostdb_b200/_lib.py (ctypes) in the tests.
+package frostgpu
+
+/*
+#cgo LDFLAGS: -lfrostgpu
+#include "frostgpu.h"
+#include <stdlib.h>
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"unsafe"
+)
+
+// Engine owns one fgpu_ctx (one GPU).
+type Engine struct{ ctx *C.fgpu_ctx }
+
+var ErrUnsupported = errors.New("frostgpu: plan not covered by the GPU path")
+
+func lastError(rc C.int32_t) error {
+	msg := C.GoString(C.fgpu_last_error())
+	if rc == C.FGPU_ERR_UNSUPPORTED {
+		return fmt.Errorf("%w: %s", ErrUnsupported, msg)
+	}
+	return fmt.Errorf("frostgpu error %d: %s", int(rc), msg)
+}
+
+// New creates the engine for one device. FGPU_ERR_NO_DEVICE is returned as an error: the caller
+// keeps FrostDB's Go engine, the library never falls back to a CPU path on its own.
+func New(device int) (*Engine, error) {
+	cfg := C.fgpu_config{abi_version: C.FGPU_ABI_VERSION, device: C.int32_t(device)}
+	var ctx *C.fgpu_ctx
+	if rc := C.fgpu_init(&cfg, &ctx); rc != 0 {
+		return nil, lastError(rc)
+	}
+	return &Engine{ctx: ctx}, nil
+}
+
+func (e *Engine) Close() { C.fgpu_shutdown(e.ctx) }
+
+// PutPart registers one compacted Parquet part (table.go:1267 compactParts produces the bytes).
+// The library copies what it needs: the slice may be reused when PutPart returns.
+func (e *Engine) PutPart(table string, partID, tx uint64, parquet []byte) error {
+	ct := C.CString(table)
+	defer C.free(unsafe.Pointer(ct))
+	rc := C.fgpu_part_put_parquet(e.ctx, ct, C.uint64_t(partID), C.uint64_t(tx),
+		(*C.uint8_t)(unsafe.Pointer(&parquet[0])), C.uint64_t(len(parquet)), C.FGPU_PUT_DEFAULT)
+	if rc != 0 {
+		return lastError(rc)
+	}
+	return nil
+}
+
+// DropPart is called when the LSM releases the part (parts.Part.Release).
+func (e *Engine) DropPart(table string, partID uint64) error {
+	ct := C.CString(table)
+	defer C.free(unsafe.Pointer(ct))
+	if rc := C.fgpu_part_drop(e.ctx, ct, C.uint64_t(partID)); rc != 0 {
+		return lastError(rc)
+	}
+	return nil
+}
+
+// Handle exposes the raw context to the physicalplan shim in the same module.
+func (e *Engine) Handle() unsafe.Pointer { return unsafe.Pointer(e.ctx) }
