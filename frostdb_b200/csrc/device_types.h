@@ -55,6 +55,7 @@ struct ChunkDesc {
   uint8_t has_nulls;  // definition levels stored and at least one NULL
   uint8_t _pad[2];
   uint32_t n_rows;
+  uint32_t n_bp_runs; // bit-packed runs in the value directory (0: the chunk is run-length only)
   uint32_t n_values;  // non-null values
   uint32_t n_runs;    // value runs (excluding the sentinel)
   uint32_t n_defruns;

@@ -782,7 +782,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   {
     auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
     int vl = envi("FROSTGPU_VL", 512);
-    if (vl != 128 && vl != 256 && vl != 512) vl = 256;
+    if (vl != 128 && vl != 256 && vl != 512 && vl != 1024) vl = 512;
     int ring = envi("FROSTGPU_RING", 3);
     if (ring < 2) ring = 2;
     if (ring > 4) ring = 4;

@@ -1065,7 +1065,7 @@ struct FastAgg {
   uint32_t _pad;
 };
 struct FastPlan {
-  uint32_t ok, none, nl, nk, na, _pad;
+  uint32_t ok, none, nl, nk, na, tight;
   FastLeaf leaf[kFastLeaves];
   FastKey key[kFastKeys];
   FastAgg agg[kFastAggs];
@@ -1081,6 +1081,7 @@ __device__ __forceinline__ long long lds64(uint32_t a) {
 __device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc* chunks, const LeafRt* lrt, FastPlan* fp) {
   fp->ok = 0;
   fp->none = 0;
+  bool tight = true;
   uint32_t nl = 0, nk = 0, na = 0;
   for (int l = 0; l < q.n_leaves; l++) {
     const LeafDesc& ld = q.leaves[l];
@@ -1094,6 +1095,7 @@ __device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc
     f.col_off = uint32_t(p) * uint32_t(q.vl) * 8u;
     f.flags = (ld.cmp_float ? 1u : 0u) | (q.slot_type[ld.slot] == ST_F64 ? 2u : 0u) | (ld.neg ? 4u : 0u);
     f.lo_i = ld.lo_i; f.hi_i = ld.hi_i; f.lo_f = ld.lo_f; f.hi_f = ld.hi_f;
+    if (f.flags != 0) tight = false;
   }
   for (int k = 0; k < q.n_keys; k++) {
     const KeyDesc& kd = q.keys[k];
@@ -1105,6 +1107,7 @@ __device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc
     const int sv = q.slot_seed_stage[kd.slot][0];
     f.seed_off = sv >= 0 ? int32_t(uint32_t(q.n_stage_plain) * uint32_t(q.vl) * 8u + uint32_t(sv) * uint32_t(sizeof(Seed))) : -1;
     f.stride = kd.dense_stride;
+    if (c.n_bp_runs != 0) tight = false;
   }
   for (int a = 0; a < q.n_aggs; a++) {
     const AggDesc& ad = q.aggs[a];
@@ -1117,7 +1120,9 @@ __device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc
     f.col_off = uint32_t(p) * uint32_t(q.vl) * 8u;
     f.func = uint32_t(ad.func) | (uint32_t(ad.is_float) << 8);
     f.index = a;
+    if (f.func != 1u) tight = false;
   }
+  fp->tight = tight ? 1u : 0u;
   fp->nl = nl; fp->nk = nk; fp->na = na;
   fp->ok = 1;
 }
@@ -1152,6 +1157,50 @@ __device__ __forceinline__ uint32_t kc_get(KCur& c, const FastKey& fk, uint32_t 
   return __ldg(fk.lut + extract_bits(fk.stream, c.off, uint64_t(ord - c.start) * w, w));
 }
 
+// Cold part of the fused pass: the step's active lanes are not all in the running group `cs`.
+// Sorted parts produce exactly one shape here, a run boundary: the lanes still in `cs` join the running
+// accumulators, the warp flushes once, and the remaining lanes (one new group) start the next run.
+// Anything else (several new groups in one step) goes through the generic mixed path.
+template <int NA>
+__device__ __noinline__ void fast_cold_step(const QueryDesc& q, const FastPlan& fp, uint32_t slot, bool act, const long long (&val)[NA > 0 ? NA : 1],
+                                            int lane, uint32_t& cs, uint32_t& cnt, long long (&part)[NA > 0 ? NA : 1]) {
+  // 1. lanes that still belong to the running group
+  if (cs != kNoSlot) {
+    const bool old = act && slot == cs;
+    cnt += old ? 1u : 0u;
+#pragma unroll
+    for (int a = 0; a < NA; a++)
+      if (old) part[a] = agg_combine(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0, part[a], val[a]);
+    act = act && !old;
+    // 2. flush the running group
+    const uint32_t tt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+    cnt = 0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      flush_agg(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0, q.t_agg[fp.agg[a].index] + cs, part[a], lane);
+      part[a] = agg_identity(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0);
+    }
+    cs = kNoSlot;
+  }
+  // 3. what is left of the step
+  const unsigned rest = __ballot_sync(FULL, act);
+  if (rest == 0) return;
+  const uint32_t s1 = __shfl_sync(FULL, slot, __ffs(rest) - 1);
+  if (__all_sync(FULL, !act || slot == s1)) {  // one new group: it becomes the running group
+    cs = s1;
+    cnt = act ? 1u : 0u;
+#pragma unroll
+    for (int a = 0; a < NA; a++)
+      if (act) part[a] = agg_combine(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0, part[a], val[a]);
+    return;
+  }
+  mixed_rows(q.t_rows, slot, act, lane);
+#pragma unroll
+  for (int a = 0; a < NA; a++)
+    mixed_agg(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0, q.t_agg[fp.agg[a].index], slot, act, val[a], lane);
+}
+
 template <int NL, int NK, int NA>
 __device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t slot_saddr,
                                             const uint8_t* slotmem, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
@@ -1178,75 +1227,61 @@ __device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, const WarpMem& m,
     kc[k].k = a.x; kc[k].start = a.y; kc[k].end = a.z; kc[k].off = a.w; kc[k].val = b.x; kc[k].meta = b.y;
     kstride[k] = fk.stride;
   }
-  uint32_t acol[NA > 0 ? NA : 1], afunc[NA > 0 ? NA : 1];
+  uint32_t acol[NA > 0 ? NA : 1];
+  bool sum64[NA > 0 ? NA : 1];
   long long part[NA > 0 ? NA : 1];
 #pragma unroll
   for (int a = 0; a < NA; a++) {
     acol[a] = slot_saddr + fp.agg[a].col_off + uint32_t(lane) * 8u;
-    afunc[a] = fp.agg[a].func;
+    sum64[a] = fp.agg[a].func == 1u;  // Sum(int64): two adds in the hot loop
     part[a] = m.acc[fp.agg[a].index * 32 + lane];
   }
   uint32_t cs = cur_slot, cnt = m.cnt[lane], selected = 0;
-#pragma unroll 1
-  for (int s = 0; s < steps; s++) {
-    const uint32_t idx = uint32_t(s) * 32u + uint32_t(lane);
-    bool act = idx < n_in;
-#pragma unroll
-    for (int l = 0; l < NL; l++) {
-      const long long x = lds64(lcol[l] + uint32_t(s) * 256u);
-      bool in;
-      if (lflags[l] & 1u) {
-        const double d = (lflags[l] & 2u) ? __longlong_as_double(x) : double(x);
-        in = d >= __longlong_as_double(llo[l]) && d <= __longlong_as_double(lhi[l]);
-      } else {
-        in = x >= llo[l] && x <= lhi[l];
-      }
-      act = act && (in != ((lflags[l] & 4u) != 0));
-    }
-    const unsigned amask = __ballot_sync(FULL, act);
-    if (amask == 0) continue;
+  int s = 0;
+  while (s < steps) {
     uint32_t slot = 0;
-    const uint32_t r = r0 + idx;
+    bool act = false;
+    // ---- hot loop: no calls inside, leaves only when the step is not entirely in the running group ----
+#pragma unroll 1
+    for (; s < steps; s++) {
+      const uint32_t idx = uint32_t(s) * 32u + uint32_t(lane);
+      act = idx < n_in;
 #pragma unroll
-    for (int k = 0; k < NK; k++)
-      if (act) slot += (kc_get(kc[k], fp.key[k], r) + 1u) * kstride[k];
-    selected += __popc(amask);
-    const uint32_t s0 = __shfl_sync(FULL, slot, __ffs(amask) - 1);
-    const bool uni = __all_sync(FULL, !act || slot == s0);
-    if (uni && s0 == cs) {  // the common case: still in the running group
+      for (int l = 0; l < NL; l++) {
+        const long long x = lds64(lcol[l] + uint32_t(s) * 256u);
+        bool in;
+        if (lflags[l] & 1u) {
+          const double d = (lflags[l] & 2u) ? __longlong_as_double(x) : double(x);
+          in = d >= __longlong_as_double(llo[l]) && d <= __longlong_as_double(lhi[l]);
+        } else {
+          in = x >= llo[l] && x <= lhi[l];
+        }
+        act = act && (in != ((lflags[l] & 4u) != 0));
+      }
+      const unsigned amask = __ballot_sync(FULL, act);
+      if (amask == 0) continue;
+      slot = 0;
+      const uint32_t r = r0 + idx;
+#pragma unroll
+      for (int k = 0; k < NK; k++)
+        if (act) slot += (kc_get(kc[k], fp.key[k], r) + 1u) * kstride[k];
+      selected += __popc(amask);
+      if (!__all_sync(FULL, !act || slot == cs)) break;  // group change: leave the hot loop
       cnt += act ? 1u : 0u;
 #pragma unroll
       for (int a = 0; a < NA; a++) {
         const long long val = lds64(acol[a] + uint32_t(s) * 256u);
-        if (afunc[a] == 1u) part[a] = (long long)((unsigned long long)part[a] + (act ? (unsigned long long)val : 0ull));  // Sum(int64)
-        else if (act) part[a] = agg_combine(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, part[a], val);
-      }
-      continue;
-    }
-    // group change or mixed step: flush what the warp has accumulated
-    if (cs != kNoSlot) {
-      const uint32_t tt = __reduce_add_sync(FULL, cnt);
-      if (lane == 0 && tt) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
-      cnt = 0;
-#pragma unroll
-      for (int a = 0; a < NA; a++) {
-        flush_agg(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, q.t_agg[fp.agg[a].index] + cs, part[a], lane);
-        part[a] = agg_identity(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0);
+        if (sum64[a]) part[a] = (long long)((unsigned long long)part[a] + (act ? (unsigned long long)val : 0ull));
+        else if (act) part[a] = agg_combine(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0, part[a], val);
       }
     }
-    if (uni) {
-      cs = s0;
-      cnt = act ? 1u : 0u;
+    if (s >= steps) break;
+    // ---- cold: step s leaves the running group ----
+    long long val[NA > 0 ? NA : 1];
 #pragma unroll
-      for (int a = 0; a < NA; a++)
-        if (act) part[a] = agg_combine(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, part[a], lds64(acol[a] + uint32_t(s) * 256u));
-    } else {
-      cs = kNoSlot;
-      mixed_rows(q.t_rows, slot, act, lane);
-#pragma unroll
-      for (int a = 0; a < NA; a++)
-        mixed_agg(uint8_t(afunc[a] & 0xff), (afunc[a] >> 8) != 0, q.t_agg[fp.agg[a].index], slot, act, lds64(acol[a] + uint32_t(s) * 256u), lane);
-    }
+    for (int a = 0; a < NA; a++) val[a] = lds64(acol[a] + uint32_t(s) * 256u);
+    fast_cold_step<NA>(q, fp, slot, act, val, lane, cs, cnt, part);
+    s++;
   }
   m.cnt[lane] = cnt;
 #pragma unroll
@@ -1255,10 +1290,103 @@ __device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, const WarpMem& m,
   return cs;
 }
 
+// Tight variant of the fused pass, chosen per row group when every leaf is a plain (non-negated) int64
+// range, every key column chunk is run-length only (sorted parts) and every aggregate is Sum(int64):
+// the hot loop then carries a handful of registers and no calls.
+template <int NL, int NK, int NA>
+__device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t slot_saddr,
+                                                  const uint8_t* slotmem, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
+                                                  uint32_t cur_slot) {
+  long long lo[NL > 0 ? NL : 1], hi[NL > 0 ? NL : 1];
+  uint32_t lcol[NL > 0 ? NL : 1];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    lo[l] = fp.leaf[l].lo_i;
+    hi[l] = fp.leaf[l].hi_i;
+    lcol[l] = slot_saddr + fp.leaf[l].col_off + uint32_t(lane) * 8u;
+  }
+  uint32_t kk[NK > 0 ? NK : 1], kend[NK > 0 ? NK : 1], kadd[NK > 0 ? NK : 1];
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    const FastKey& fk = fp.key[k];
+    const Seed* sd = fk.seed_off >= 0 ? reinterpret_cast<const Seed*>(slotmem + fk.seed_off) : fk.seeds + chunk;
+    kk[k] = sd->k;
+    kend[k] = sd->end;
+    kadd[k] = (sd->val + 1u) * fk.stride;
+  }
+  uint32_t acol[NA > 0 ? NA : 1];
+  unsigned long long part[NA > 0 ? NA : 1];
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    acol[a] = slot_saddr + fp.agg[a].col_off + uint32_t(lane) * 8u;
+    part[a] = (unsigned long long)m.acc[fp.agg[a].index * 32 + lane];
+  }
+  uint32_t cs = cur_slot, cnt = m.cnt[lane], selected = 0;
+  int s = 0;
+  while (s < steps) {
+    uint32_t slot = 0;
+    bool act = false;
+#pragma unroll 1
+    for (; s < steps; s++) {
+      const uint32_t idx = uint32_t(s) * 32u + uint32_t(lane);
+      act = idx < n_in;
+#pragma unroll
+      for (int l = 0; l < NL; l++) {
+        const long long x = lds64(lcol[l] + uint32_t(s) * 256u);
+        act = act && x >= lo[l] && x <= hi[l];
+      }
+      const unsigned amask = __ballot_sync(FULL, act);
+      if (amask == 0) continue;
+      const uint32_t r = r0 + idx;
+      slot = 0;
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        if (act && r >= kend[k]) {  // this lane crossed into the next run(s)
+          const Run* runs = fp.key[k].runs;
+          do {
+            kk[k]++;
+            kend[k] = __ldg(&runs[kk[k] + 1].start);
+          } while (r >= kend[k]);
+          kadd[k] = (__ldg(&runs[kk[k]].val) + 1u) * fp.key[k].stride;
+        }
+        slot += kadd[k];
+      }
+      selected += __popc(amask);
+      if (!__all_sync(FULL, !act || slot == cs)) break;  // group change: leave the hot loop
+      cnt += act ? 1u : 0u;
+#pragma unroll
+      for (int a = 0; a < NA; a++) part[a] += act ? (unsigned long long)lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+    }
+    if (s >= steps) break;
+    long long val[NA > 0 ? NA : 1], p2[NA > 0 ? NA : 1];
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      val[a] = lds64(acol[a] + uint32_t(s) * 256u);
+      p2[a] = (long long)part[a];
+    }
+    fast_cold_step<NA>(q, fp, slot, act, val, lane, cs, cnt, p2);
+#pragma unroll
+    for (int a = 0; a < NA; a++) part[a] = (unsigned long long)p2[a];
+    s++;
+  }
+  m.cnt[lane] = cnt;
+#pragma unroll
+  for (int a = 0; a < NA; a++) m.acc[fp.agg[a].index * 32 + lane] = (long long)part[a];
+  if (lane == 0) m.selected[0] += selected;
+  return cs;
+}
+
 template <int NL, int NK>
 __device__ __forceinline__ uint32_t fast_dispatch_a(int na, const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t sa,
                                                     const uint8_t* sm, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
                                                     uint32_t cs) {
+  if (fp.tight) {
+    switch (na) {
+      case 0: return fast_pass_tight<NL, NK, 0>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+      case 1: return fast_pass_tight<NL, NK, 1>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+      default: return fast_pass_tight<NL, NK, 2>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
+    }
+  }
   switch (na) {
     case 0: return fast_pass<NL, NK, 0>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
     case 1: return fast_pass<NL, NK, 1>(q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
@@ -1287,7 +1415,7 @@ __device__ __forceinline__ uint32_t fast_dispatch(const VecCtx& v, const WarpMem
   }
 }
 
-__global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
+__global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __restrict__ qp) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ QueryDesc sq;
   __shared__ uint32_t s_first[kRgSmem + 1];

@@ -13,7 +13,7 @@ constexpr int kScanThreads = 256;
 constexpr int kRowsPerThread = 4;
 constexpr int kTileRows = kScanThreads * kRowsPerThread;  // 1024 rows per CTA iteration
 constexpr int kVecThreads = 128;  // scan kernel: 4 independent warps per CTA
-constexpr int kMaxVecRows = 512;  // rows per warp vector (multiple of kIndexRows)
+constexpr int kMaxVecRows = 1024;  // rows per warp vector (multiple of kIndexRows)
 constexpr int kIndexRows = 128;  // chunk index granularity (one warp): fixed when run directories are built
 
 cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st);

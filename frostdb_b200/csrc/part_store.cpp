@@ -288,6 +288,9 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   if (out->desc.kind != CK_PLAIN64) {
     std::vector<Seed> seeds = make_seeds(vruns, n_values, false);
     out->desc.n_runs = uint32_t(vruns.size());
+    uint32_t bp = 0;
+    for (const HostRun& r : vruns) bp += (r.meta & 1u);
+    out->desc.n_bp_runs = bp;
     HostRun sentinel{n_values, 0, 0, 0};
     vruns.push_back(sentinel);
     out->off_runs = w.section(vruns.data(), vruns.size() * sizeof(HostRun));
