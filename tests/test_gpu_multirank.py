@@ -1,0 +1,77 @@
+"""The N > 1 data path on one GPU: two engines (two fgpu_ctx, as two ranks would have) each own half of the
+parts, preload the same dictionary union, scan into partial tables, the tables are laid out back to back
+the way an all-gather leaves them, and one engine merges.  Must equal the single-engine result and the
+oracle."""
+import ctypes as C
+
+import pytest
+
+from frostdb_b200 import _lib
+from frostdb_b200 import dynparquet as dp
+from frostdb_b200 import logicalplan as lp
+from frostdb_b200.physicalplan import GPUScan
+from frostdb_b200.store import GPUEngine
+from tests.oracle_scan import OracleEngine, OracleTableHandle, oracle_query
+from tests.test_multirank_host import union_in_rank_order
+from tests.util import make_columns, rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("groups", [["labels.a", "labels.b"], ["labels.a", "labels.big", "labels.b"]])
+def test_partial_tables_merge_like_the_final_aggregate(built_lib, groups):
+    import torch
+    lib = built_lib
+    schema = dp.SampleDefinition()
+    bufs = []
+    for r in range(4):  # ranks see different label windows -> different local dictionaries
+        cols = make_columns(30_000, 70 + r, {"a": (5 + 3 * (r % 2), 0.1), "b": (40, 0.0), "big": (20000 + 500 * r, 0.02)}, t0=r * 30_000)
+        bufs.append(dp.write_part(schema, cols, row_group_size=12_000))
+    shards = [bufs[0::2], bufs[1::2]]
+    key_cols = groups
+    unions = {c: union_in_rank_order([[v for b in sh for v in _lib.parquet_dict_values(b, c)] for sh in shards]) for c in key_cols}
+    engines = [GPUEngine(0), GPUEngine(0)]
+    oe = OracleEngine(threads=2)
+    try:
+        ot = OracleTableHandle(oe, "t", schema)
+        for e, sh in zip(engines, shards):
+            for c in key_cols:
+                e.dict_preload("t", c, unions[c])
+            for b in sh:
+                e.put_parquet("t", b)
+        for b in bufs:
+            ot.InsertParquet(b)
+        aggs = [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value")), lp.Min(lp.Col("timestamp")), lp.Max(lp.Col("value"))]
+        gexprs = [lp.Col(c) for c in key_cols]
+        f = lp.Col("timestamp").GtEq(lp.Literal(10_000))
+        partials = []
+        for e in engines:
+            scan = GPUScan(e, "t", f, _lib.PLAN_AGGREGATE, gexprs, aggs)
+            q, keep = scan.prepare()
+            res, ptr, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
+            _lib.check(lib.fgpu_query_execute_partial(e.handle, q, e.table_watermark("t"), C.byref(res), C.byref(ptr), C.byref(nbytes)))
+            partials.append((e, q, keep, res, ptr.value, nbytes.value))
+        assert partials[0][5] == partials[1][5], "partial tables must have the same layout on every rank"
+        n8 = partials[0][5] // 8
+
+        class DevMem:
+            def __init__(self, p, n):
+                self.__cuda_array_interface__ = {"shape": (n // 8,), "typestr": "<i8", "data": (p, False), "version": 2}
+        gathered = torch.empty(2 * n8, dtype=torch.int64, device="cuda")
+        for i, (_, _, _, _, ptr, nb) in enumerate(partials):
+            gathered[i * n8:(i + 1) * n8].copy_(torch.as_tensor(DevMem(ptr, nb), device="cuda"))
+        torch.cuda.synchronize()
+        e0, q0, _, res0, _, nb = partials[0]
+        _lib.check(lib.fgpu_result_merge_partials(e0.handle, res0, gathered.data_ptr(), nb, 2))
+        got = list(e0.drain(res0))
+        exp = []
+        oracle_query(oe, "t").Filter(f).Aggregate(aggs, gexprs).Execute(None, lambda c, r: exp.append(r))
+        names = key_cols + [a.Name() for a in aggs]
+        assert rows_of(got, names) == rows_of(exp, names)
+        for e, q, _, res, _, _ in partials:
+            lib.fgpu_result_free(res)
+            lib.fgpu_query_free(q)
+    finally:
+        oe.close()
+        for e in engines:
+            e.close()
