@@ -696,13 +696,13 @@ __device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
 __device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_saddr), "l"(src) : "memory");
 }
-__device__ __forceinline__ void issue_vector(const QueryDesc& q, const WarpMem& m, uint32_t vec, int rs, uint32_t rg_first, uint32_t n_rows,
+__device__ __forceinline__ void issue_vector(const QueryDesc& q, uint8_t* ring, uint32_t vec, int rs, uint32_t rg_first, uint32_t n_rows,
                                              const ChunkDesc* chunks, int lane) {
   const uint32_t vec_in_rg = vec - rg_first;
   const uint32_t r0 = vec_in_rg * q.vl;
   const uint32_t n = min(uint32_t(q.vl), n_rows - r0);
   const uint32_t chunk = r0 / kIndexRows;
-  const uint32_t dst = smem_u32(m.ring + size_t(rs) * q.slot_bytes);
+  const uint32_t dst = smem_u32(ring + size_t(rs) * q.slot_bytes);
   const uint32_t plain_sz = (n * 8u + 15u) & ~15u;
   for (int p = 0; p < q.n_stage_plain; p++) {
     const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
@@ -729,7 +729,8 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // ---- selection -------------------------------------------------------------------------------------------
 // act[s] = ballot over the 32 rows of step s that pass the predicate.
-__device__ __noinline__ uint32_t vec_selection(const VecCtx& v, const WarpMem& m, int lane) {
+__device__ __noinline__ uint32_t vec_selection(const VecCtx& v, uint8_t* wb, int lane) {
+  const WarpMem m = warp_mem(*v.q, wb);
   const QueryDesc& q = *v.q;
   const int steps = v.steps;
   for (int s = lane; s < steps; s += 32) {
@@ -827,7 +828,8 @@ __device__ __noinline__ uint32_t vec_selection(const VecCtx& v, const WarpMem& m
 
 // ---- aggregate input vector -------------------------------------------------------------------------------
 // Evaluates an aggregate expression over the vector into out[] (raw 8-byte values, NULL slots 0).
-__device__ __noinline__ void vec_eval_expr(const VecCtx& v, const WarpMem& m, const AggDesc& a, int lane, long long* out) {
+__device__ __noinline__ void vec_eval_expr(const VecCtx& v, uint8_t* wb, const AggDesc& a, int lane, long long* out) {
+  const WarpMem m = warp_mem(*v.q, wb);
   const QueryDesc& q = *v.q;
   long long* stack[3] = {out, m.tmp2, m.tmp2 + q.vl};  // operand stack: depth <= 3 (checked by the host)
   int sp = 0;
@@ -859,7 +861,8 @@ __device__ __noinline__ void vec_eval_expr(const VecCtx& v, const WarpMem& m, co
 }
 
 // ---- table slot per row ----------------------------------------------------------------------------------
-__device__ __noinline__ void vec_slots_dense(const VecCtx& v, const WarpMem& m, int lane) {
+__device__ __noinline__ void vec_slots_dense(const VecCtx& v, uint8_t* wb, int lane) {
+  const WarpMem m = warp_mem(*v.q, wb);
   const QueryDesc& q = *v.q;
   bool first = true;
   for (int k = 0; k < q.n_keys; k++) {
@@ -882,7 +885,8 @@ __device__ __noinline__ void vec_slots_dense(const VecCtx& v, const WarpMem& m, 
 
 // Hash mode: packed key words per row in shared memory, then find-or-insert (with a per-lane
 // last-key cache in m.lastkw: sorted parts repeat the previous row's key most of the time).
-__device__ __noinline__ bool vec_slots_hash(const VecCtx& v, const WarpMem& m, int lane) {
+__device__ __noinline__ bool vec_slots_hash(const VecCtx& v, uint8_t* wb, int lane) {
+  const WarpMem m = warp_mem(*v.q, wb);
   const QueryDesc& q = *v.q;
   const int W = q.key_words;
   bool overflow = false;
@@ -942,7 +946,8 @@ __device__ __noinline__ bool vec_slots_hash(const VecCtx& v, const WarpMem& m, i
 
 // ---- rows-per-group counter (also every Count aggregate, aggregate.go:937-950) ------------------------------
 // Returns the running group after the vector; m.cnt[lane] carries this lane's pending row count.
-__device__ __noinline__ uint32_t vec_count_rows(const VecCtx& v, const WarpMem& m, int lane, uint32_t cur_slot) {
+__device__ __noinline__ uint32_t vec_count_rows(const VecCtx& v, uint8_t* wb, int lane, uint32_t cur_slot) {
+  const WarpMem m = warp_mem(*v.q, wb);
   const QueryDesc& q = *v.q;
   uint32_t cs = cur_slot;
   uint32_t cnt = m.cnt[lane];
@@ -982,7 +987,8 @@ __device__ __noinline__ uint32_t vec_count_rows(const VecCtx& v, const WarpMem& 
 }
 
 // ---- one aggregate over the vector: per-lane partial while the warp stays in one group ------------------------
-__device__ __noinline__ void vec_aggregate(const VecCtx& v, const WarpMem& m, int a, int lane, uint32_t cur_slot) {
+__device__ __noinline__ void vec_aggregate(const VecCtx& v, uint8_t* wb, int a, int lane, uint32_t cur_slot) {
+  const WarpMem m = warp_mem(*v.q, wb);
   const QueryDesc& q = *v.q;
   const AggDesc& ad = q.aggs[a];
   const uint8_t func = ad.func;
@@ -993,7 +999,7 @@ __device__ __noinline__ void vec_aggregate(const VecCtx& v, const WarpMem& m, in
   const bool simple = ad.prog_len == 1 && q.prog[ad.prog_off].op == PO_LOAD;
   NumReader rd;
   if (simple) rd.init(v, q.prog[ad.prog_off].slot, lane);
-  else vec_eval_expr(v, m, ad, lane, m.tmp1);
+  else vec_eval_expr(v, wb, ad, lane, m.tmp1);
   __syncwarp();
   uint32_t cs = cur_slot;
   long long part = m.acc[a * 32 + lane];
@@ -1202,9 +1208,10 @@ __device__ __noinline__ void fast_cold_step(const QueryDesc& q, const FastPlan& 
 }
 
 template <int NL, int NK, int NA>
-__device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t slot_saddr,
+__device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, uint8_t* wb, const FastPlan& fp, uint32_t slot_saddr,
                                             const uint8_t* slotmem, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
                                             uint32_t cur_slot) {
+  const WarpMem m = warp_mem(q, wb);
   // leaves: the active bound pair as raw 64-bit words
   long long llo[NL > 0 ? NL : 1], lhi[NL > 0 ? NL : 1];
   uint32_t lflags[NL > 0 ? NL : 1], lcol[NL > 0 ? NL : 1];
@@ -1294,9 +1301,10 @@ __device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, const WarpMem& m,
 // range, every key column chunk is run-length only (sorted parts) and every aggregate is Sum(int64):
 // the hot loop then carries a handful of registers and no calls.
 template <int NL, int NK, int NA>
-__device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t slot_saddr,
+__device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb, const FastPlan& fp, uint32_t slot_saddr,
                                                   const uint8_t* slotmem, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
                                                   uint32_t cur_slot) {
+  const WarpMem m = warp_mem(q, wb);
   long long lo[NL > 0 ? NL : 1], hi[NL > 0 ? NL : 1];
   uint32_t lcol[NL > 0 ? NL : 1];
 #pragma unroll
@@ -1377,7 +1385,7 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, const WarpM
 }
 
 template <int NL, int NK>
-__device__ __forceinline__ uint32_t fast_dispatch_a(int na, const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t sa,
+__device__ __forceinline__ uint32_t fast_dispatch_a(int na, const QueryDesc& q, uint8_t* m, const FastPlan& fp, uint32_t sa,
                                                     const uint8_t* sm, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
                                                     uint32_t cs) {
   if (fp.tight) {
@@ -1394,7 +1402,7 @@ __device__ __forceinline__ uint32_t fast_dispatch_a(int na, const QueryDesc& q, 
   }
 }
 template <int NL>
-__device__ __forceinline__ uint32_t fast_dispatch_k(int nk, int na, const QueryDesc& q, const WarpMem& m, const FastPlan& fp, uint32_t sa,
+__device__ __forceinline__ uint32_t fast_dispatch_k(int nk, int na, const QueryDesc& q, uint8_t* m, const FastPlan& fp, uint32_t sa,
                                                     const uint8_t* sm, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
                                                     uint32_t cs) {
   switch (nk) {
@@ -1404,7 +1412,7 @@ __device__ __forceinline__ uint32_t fast_dispatch_k(int nk, int na, const QueryD
     default: return fast_dispatch_a<NL, 3>(na, q, m, fp, sa, sm, r0, chunk, n_in, steps, lane, cs);
   }
 }
-__device__ __forceinline__ uint32_t fast_dispatch(const VecCtx& v, const WarpMem& m, const FastPlan& fp, int lane, uint32_t cs) {
+__device__ __forceinline__ uint32_t fast_dispatch(const VecCtx& v, uint8_t* m, const FastPlan& fp, int lane, uint32_t cs) {
   const QueryDesc& q = *v.q;
   const uint32_t sa = smem_u32(v.slotmem);
   const uint32_t n_in = min(uint32_t(q.vl), v.n_rows - v.r0);
@@ -1415,7 +1423,7 @@ __device__ __forceinline__ uint32_t fast_dispatch(const VecCtx& v, const WarpMem
   }
 }
 
-__global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __restrict__ qp) {
+__global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ QueryDesc sq;
   __shared__ uint32_t s_first[kRgSmem + 1];
@@ -1431,13 +1439,13 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
     for (int i = threadIdx.x; i <= q.n_rg; i += blockDim.x) s_first[i] = __ldg(&q.rg_first_tile[i]);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const WarpMem m = warp_mem(q, dyn + size_t(warp) * q.wr_bytes);
+  uint8_t* const wb = dyn + size_t(warp) * q.wr_bytes;  // this warp's shared-memory region (see WarpMem)
   const int D = q.n_ring;
   uint32_t cached_rows = 0;
-  if (lane == 0) m.selected[0] = 0;
-  m.cnt[lane] = 0;
-  m.lastslot[lane] = kNoSlot;
-  for (int a = 0; a < q.n_aggs; a++) m.acc[a * 32 + lane] = agg_identity(q.aggs[a].func, q.aggs[a].is_float);
+  if (lane == 0) reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8)[0] = 0;
+  reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4)[lane] = 0;
+  reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16)[lane] = kNoSlot;
+  for (int a = 0; a < q.n_aggs; a++) reinterpret_cast<long long*>(wb + q.wr_acc)[a * 32 + lane] = agg_identity(q.aggs[a].func, q.aggs[a].is_float);
   __syncwarp();
 
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;  // global warp id
@@ -1452,7 +1460,7 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
   auto first_tile = [&](int i) -> uint32_t { return rg_in_smem ? s_first[i] : __ldg(&q.rg_first_tile[i]); };
   int rg = 0, rg_a = 0;          // row group of the vector being processed / being prefetched
   int cached_rg = -1;
-  auto descs_of = [&](int g) -> const ChunkDesc* { return g == cached_rg ? m.cdesc : q.chunks + size_t(g) * q.n_slots; };
+  auto descs_of = [&](int g) -> const ChunkDesc* { return g == cached_rg ? reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc) : q.chunks + size_t(g) * q.n_slots; };
 
   // prologue: fill the ring (every iteration commits exactly one cp.async group, empty ones included,
   // so that "at most D-1 groups pending" always means "the current vector has landed")
@@ -1460,7 +1468,7 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
     const uint32_t vec = gw + uint32_t(d) * GW;
     if (vec < q.n_tiles) {
       while (vec >= first_tile(rg_a + 1)) rg_a++;
-      issue_vector(q, m, vec, d, first_tile(rg_a), __ldg(&q.rg_rows[rg_a]), q.chunks + size_t(rg_a) * q.n_slots, lane);
+      issue_vector(q, wb + q.wr_ring, vec, d, first_tile(rg_a), __ldg(&q.rg_rows[rg_a]), q.chunks + size_t(rg_a) * q.n_slots, lane);
     } else {
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -1471,16 +1479,16 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
     while (vec >= first_tile(rg + 1)) rg++;
     if (rg != cached_rg) {  // warp-uniform: copy this row group's descriptors into shared memory
       const uint32_t* src = reinterpret_cast<const uint32_t*>(q.chunks + size_t(rg) * q.n_slots);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(m.cdesc);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc));
       for (uint32_t i = lane; i < uint32_t(q.n_slots) * sizeof(ChunkDesc) / 4; i += 32) dst[i] = __ldg(src + i);
       src = reinterpret_cast<const uint32_t*>(q.leaf_rt + size_t(rg) * q.n_leaves);
-      dst = reinterpret_cast<uint32_t*>(m.clrt);
+      dst = reinterpret_cast<uint32_t*>(reinterpret_cast<LeafRt*>(wb + q.wr_clrt));
       for (uint32_t i = lane; i < uint32_t(q.n_leaves) * sizeof(LeafRt) / 4; i += 32) dst[i] = __ldg(src + i);
       cached_rg = rg;
       cached_rows = __ldg(&q.rg_rows[rg]);
       __syncwarp();
       if (q.fast_ok) {
-        if (lane == 0) build_fast_plan(q, m.cdesc, m.clrt, m.fplan);
+        if (lane == 0) build_fast_plan(q, reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc), reinterpret_cast<LeafRt*>(wb + q.wr_clrt), reinterpret_cast<FastPlan*>(wb + q.wr_fplan));
         __syncwarp();
       }
     }
@@ -1488,7 +1496,7 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
       const uint32_t ahead = vec + uint32_t(D - 1) * GW;
       if (ahead < q.n_tiles) {
         while (ahead >= first_tile(rg_a + 1)) rg_a++;
-        issue_vector(q, m, ahead, int((it + uint32_t(D) - 1) % uint32_t(D)), first_tile(rg_a),
+        issue_vector(q, wb + q.wr_ring, ahead, int((it + uint32_t(D) - 1) % uint32_t(D)), first_tile(rg_a),
                      rg_a == cached_rg ? cached_rows : __ldg(&q.rg_rows[rg_a]), descs_of(rg_a), lane);
       } else {
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1499,9 +1507,9 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
     v.n_rows = cached_rows;
     v.r0 = (vec - first_tile(rg)) * q.vl;
     v.chunk = v.r0 / kIndexRows;
-    v.chunks = m.cdesc;
-    v.lrt = m.clrt;
-    v.slotmem = m.ring + size_t(rs) * q.slot_bytes;
+    v.chunks = reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc);
+    v.lrt = reinterpret_cast<LeafRt*>(wb + q.wr_clrt);
+    v.slotmem = (wb + q.wr_ring) + size_t(rs) * q.slot_bytes;
     v.steps = int((min(uint32_t(q.vl), v.n_rows - v.r0) + 31) / 32);
     // the vector's copies are the oldest pending group of every lane
     if (D == 2) cp_async_wait<1>();
@@ -1509,28 +1517,28 @@ __global__ void __launch_bounds__(kVecThreads, 3) k_scan(const QueryDesc* __rest
     else cp_async_wait<3>();
     __syncwarp();
 
-    if (q.fast_ok && m.fplan->ok) {
-      if (!m.fplan->none) cur_slot = fast_dispatch(v, m, *m.fplan, lane, cur_slot);  // one fused pass
-    } else if (vec_selection(v, m, lane) != 0) {
-      if (dense) vec_slots_dense(v, m, lane);
-      else overflow |= vec_slots_hash(v, m, lane);
-      const uint32_t end_slot = vec_count_rows(v, m, lane, cur_slot);
+    if (q.fast_ok && reinterpret_cast<FastPlan*>(wb + q.wr_fplan)->ok) {
+      if (!reinterpret_cast<FastPlan*>(wb + q.wr_fplan)->none) cur_slot = fast_dispatch(v, wb, *reinterpret_cast<FastPlan*>(wb + q.wr_fplan), lane, cur_slot);  // one fused pass
+    } else if (vec_selection(v, wb, lane) != 0) {
+      if (dense) vec_slots_dense(v, wb, lane);
+      else overflow |= vec_slots_hash(v, wb, lane);
+      const uint32_t end_slot = vec_count_rows(v, wb, lane, cur_slot);
       for (int a = 0; a < q.n_aggs; a++)
-        if (q.aggs[a].func != 4 /*count*/) vec_aggregate(v, m, a, lane, cur_slot);
+        if (q.aggs[a].func != 4 /*count*/) vec_aggregate(v, wb, a, lane, cur_slot);
       cur_slot = end_slot;
     }
     __syncwarp();  // every lane is done with ring slot rs before lane 0 refills it next iteration
   }
   // ---- final flush ---------------------------------------------------------------------------------
   if (cur_slot != kNoSlot) {
-    const uint32_t tt = __reduce_add_sync(FULL, m.cnt[lane]);
+    const uint32_t tt = __reduce_add_sync(FULL, reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4)[lane]);
     if (lane == 0 && tt) atomicAdd(q.t_rows + cur_slot, (unsigned long long)tt);
     for (int a = 0; a < q.n_aggs; a++) {
       if (q.aggs[a].func == 4) continue;
-      flush_agg(q.aggs[a].func, q.aggs[a].is_float, q.t_agg[a] + cur_slot, m.acc[a * 32 + lane], lane);
+      flush_agg(q.aggs[a].func, q.aggs[a].is_float, q.t_agg[a] + cur_slot, reinterpret_cast<long long*>(wb + q.wr_acc)[a * 32 + lane], lane);
     }
   }
-  if (lane == 0 && m.selected[0]) atomicAdd(q.counters + 0, m.selected[0]);
+  if (lane == 0 && reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8)[0]) atomicAdd(q.counters + 0, reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8)[0]);
   if (overflow) atomicExch(q.counters + 1, 1ull);
 }
 
