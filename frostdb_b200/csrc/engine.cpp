@@ -781,7 +781,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   // ---- scan kernel: vector length, ring depth and the per-warp shared-memory layout ----------------
   {
     auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-    int vl = envi("FROSTGPU_VL", 512);
+    int vl = envi("FROSTGPU_VL", 256);
     if (vl != 128 && vl != 256 && vl != 512 && vl != 1024) vl = 512;
     int ring = envi("FROSTGPU_RING", 3);
     if (ring < 2) ring = 2;
