@@ -146,7 +146,7 @@ struct QueryDesc {
   int32_t n_ring;        // ring depth per warp
   uint32_t slot_bytes;   // bytes of one ring slot
   uint32_t wr_bytes;     // per-warp shared-memory region: size and section offsets
-  uint32_t wr_ring, wr_act, wr_leaf, wr_slot, wr_keyw, wr_tmp1, wr_tmp2, wr_acc, wr_cdesc, wr_clrt, wr_fplan;
+  uint32_t wr_ring, wr_act, wr_leaf, wr_slot, wr_keyw, wr_tmp1, wr_tmp2, wr_acc, wr_cdesc, wr_clrt, wr_fplan, wr_iplan;
   uint8_t stage_plain_slot[kMaxStagePlain];   // staged PLAIN buffer p holds this slot
   uint8_t stage_seed_slot[kMaxStageSeeds];    // staged seed block t belongs to this slot ...
   uint8_t stage_seed_is_def[kMaxStageSeeds];  // ... and is its definition-level stream (1) or value stream (0)

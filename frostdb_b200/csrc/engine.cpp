@@ -806,6 +806,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       qd.wr_cdesc = uint32_t(off); off = r128(off + size_t(std::max(qd.n_slots, 1)) * sizeof(ChunkDesc));
       qd.wr_clrt = uint32_t(off); off = r128(off + size_t(std::max(qd.n_leaves, 1)) * sizeof(LeafRt));
       qd.wr_fplan = uint32_t(off); off = r128(off + 512);
+      qd.wr_iplan = uint32_t(off); off = r128(off + 8 + 16 * size_t(kMaxStagePlain + kMaxStageSeeds));
       qd.wr_bytes = uint32_t(off);
       if (size_t(qd.wr_bytes) * (kVecThreads / 32) <= 200 * 1024 || vl == 128) break;
       vl /= 2;  // many staged columns / wide keys: shorter vectors

@@ -1048,7 +1048,8 @@ __device__ __noinline__ void vec_aggregate(const VecCtx& v, uint8_t* wb, int a, 
 // kinds) is resolved once per row group into a FastPlan kept in the warp's shared memory; a row group
 // that does not qualify sends its vectors down the general vectorized path.
 constexpr int kFastLeaves = 2, kFastKeys = 3, kFastAggs = 2;
-constexpr int kRgSmem = 2048;  // row groups whose prefix table fits the CTA's shared memory
+constexpr int kRgSmem = 2048;
+constexpr uint32_t kVecChunk = 8;  // consecutive vectors a warp takes per turn  // row groups whose prefix table fits the CTA's shared memory
 
 struct FastLeaf {
   uint32_t col_off;  // byte offset of the staged column inside a ring slot
@@ -1069,6 +1070,15 @@ struct FastAgg {
   uint32_t func;  // AggFunc | is_float << 8
   int32_t index;  // index into q.aggs / q.t_agg
   uint32_t _pad;
+};
+struct IssueItem {
+  const uint8_t* src;  // PLAIN: the chunk's value array; seed: the chunk's seed array
+  uint32_t dst_off;    // byte offset inside a ring slot
+  uint32_t is_seed;
+};
+struct IssuePlan {  // what to prefetch for a vector of the cached row group
+  uint32_t n, _pad;
+  IssueItem item[kMaxStagePlain + kMaxStageSeeds];
 };
 struct FastPlan {
   uint32_t ok, none, nl, nk, na, tight;
@@ -1113,7 +1123,6 @@ __device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc
     const int sv = q.slot_seed_stage[kd.slot][0];
     f.seed_off = sv >= 0 ? int32_t(uint32_t(q.n_stage_plain) * uint32_t(q.vl) * 8u + uint32_t(sv) * uint32_t(sizeof(Seed))) : -1;
     f.stride = kd.dense_stride;
-    if (c.n_bp_runs != 0) tight = false;
   }
   for (int a = 0; a < q.n_aggs; a++) {
     const AggDesc& ad = q.aggs[a];
@@ -1131,6 +1140,48 @@ __device__ __noinline__ void build_fast_plan(const QueryDesc& q, const ChunkDesc
   fp->tight = tight ? 1u : 0u;
   fp->nl = nl; fp->nk = nk; fp->na = na;
   fp->ok = 1;
+}
+
+__device__ __noinline__ void build_issue_plan(const QueryDesc& q, const ChunkDesc* chunks, IssuePlan* ip) {
+  uint32_t n = 0;
+  for (int p = 0; p < q.n_stage_plain; p++) {
+    const ChunkDesc& c = chunks[q.stage_plain_slot[p]];
+    if (c.kind != CK_PLAIN64 || c.has_nulls) continue;
+    ip->item[n].src = c.values;
+    ip->item[n].dst_off = uint32_t(p) * uint32_t(q.vl) * 8u;
+    ip->item[n].is_seed = 0;
+    n++;
+  }
+  const uint32_t seed_base = uint32_t(q.n_stage_plain) * uint32_t(q.vl) * 8u;
+  for (int t = 0; t < q.n_stage_seeds; t++) {
+    const ChunkDesc& c = chunks[q.stage_seed_slot[t]];
+    const bool is_def = q.stage_seed_is_def[t];
+    const bool present = is_def ? (c.kind != CK_ABSENT && c.has_nulls) : (c.kind == CK_DICT_STR || c.kind == CK_DICT64);
+    if (!present) continue;
+    ip->item[n].src = reinterpret_cast<const uint8_t*>(is_def ? c.def_seeds : c.seeds);
+    ip->item[n].dst_off = seed_base + uint32_t(t) * uint32_t(sizeof(Seed));
+    ip->item[n].is_seed = 1;
+    n++;
+  }
+  ip->n = n;
+}
+
+// Prefetch of a vector of the cached row group: everything resolved in the IssuePlan.
+__device__ __forceinline__ void issue_cached(const QueryDesc& q, const IssuePlan& ip, uint32_t ring_saddr, uint32_t slot_bytes, int rs,
+                                             uint32_t r0, uint32_t n_rows, int lane) {
+  const uint32_t n = min(uint32_t(q.vl), n_rows - r0);
+  const uint32_t plain_sz = (n * 8u + 15u) & ~15u;
+  const uint32_t dst = ring_saddr + uint32_t(rs) * slot_bytes;
+  for (uint32_t i = 0; i < ip.n; i++) {
+    const IssueItem it = ip.item[i];
+    if (it.is_seed) {
+      if (lane < 2) cp_async16(dst + it.dst_off + uint32_t(lane) * 16u, it.src + size_t(r0 / kIndexRows) * sizeof(Seed) + lane * 16);
+    } else {
+      const uint8_t* src = it.src + size_t(r0) * 8;
+      for (uint32_t o = uint32_t(lane) * 16u; o < plain_sz; o += 512u) cp_async16(dst + it.dst_off + o, src + o);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 __device__ __forceinline__ bool fast_leaf_test(const FastLeaf& f, long long x) {
@@ -1173,6 +1224,13 @@ __device__ __noinline__ void fast_cold_step(const QueryDesc& q, const FastPlan& 
   // 1. lanes that still belong to the running group
   if (cs != kNoSlot) {
     const bool old = act && slot == cs;
+    if (__ballot_sync(FULL, act && !old) == 0) {  // (bit-packed boundary group that did not change the group)
+      cnt += old ? 1u : 0u;
+#pragma unroll
+      for (int a = 0; a < NA; a++)
+        if (old) part[a] = agg_combine(uint8_t(fp.agg[a].func & 0xff), (fp.agg[a].func >> 8) != 0, part[a], val[a]);
+      return;
+    }
     cnt += old ? 1u : 0u;
 #pragma unroll
     for (int a = 0; a < NA; a++)
@@ -1314,6 +1372,7 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb
     lcol[l] = slot_saddr + fp.leaf[l].col_off + uint32_t(lane) * 8u;
   }
   uint32_t kk[NK > 0 ? NK : 1], kend[NK > 0 ? NK : 1], kadd[NK > 0 ? NK : 1];
+  uint32_t kbp = 0;  // bit k: this lane's current run of key k is bit-packed (kadd[k] is not valid)
 #pragma unroll
   for (int k = 0; k < NK; k++) {
     const FastKey& fk = fp.key[k];
@@ -1321,6 +1380,7 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb
     kk[k] = sd->k;
     kend[k] = sd->end;
     kadd[k] = (sd->val + 1u) * fk.stride;
+    kbp |= (sd->meta & 1u) << k;
   }
   uint32_t acol[NA > 0 ? NA : 1];
   unsigned long long part[NA > 0 ? NA : 1];
@@ -1355,17 +1415,35 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb
             kk[k]++;
             kend[k] = __ldg(&runs[kk[k] + 1].start);
           } while (r >= kend[k]);
-          kadd[k] = (__ldg(&runs[kk[k]].val) + 1u) * fp.key[k].stride;
+          const uint2 vm = __ldg(reinterpret_cast<const uint2*>(&runs[kk[k]].val));
+          kadd[k] = (vm.x + 1u) * fp.key[k].stride;
+          kbp = (kbp & ~(1u << k)) | ((vm.y & 1u) << k);
         }
         slot += kadd[k];
       }
       selected += __popc(amask);
-      if (!__all_sync(FULL, !act || slot == cs)) break;  // group change: leave the hot loop
+      // group change, or a lane sits in a bit-packed boundary group: leave the hot loop
+      if (!__all_sync(FULL, !act || (slot == cs && kbp == 0))) break;
       cnt += act ? 1u : 0u;
 #pragma unroll
       for (int a = 0; a < NA; a++) part[a] += act ? (unsigned long long)lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
     }
     if (s >= steps) break;
+    if (__any_sync(FULL, act && kbp != 0)) {  // general value of the lanes inside bit-packed runs
+      const uint32_t r = r0 + uint32_t(s) * 32u + uint32_t(lane);
+      slot = 0;
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        uint32_t add = kadd[k];
+        if (act && ((kbp >> k) & 1u)) {
+          const FastKey& fk = fp.key[k];
+          const uint4 run = __ldg(reinterpret_cast<const uint4*>(fk.runs + kk[k]));
+          const uint32_t w = (run.w >> 8) & 0xffu;
+          add = (__ldg(fk.lut + extract_bits(fk.stream, run.y, uint64_t(r - run.x) * w, w)) + 1u) * fk.stride;
+        }
+        slot += add;
+      }
+    }
     long long val[NA > 0 ? NA : 1], p2[NA > 0 ? NA : 1];
 #pragma unroll
     for (int a = 0; a < NA; a++) {
@@ -1456,26 +1534,35 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
 
   // Row-group lookup without pointer chasing: the prefix table sits in shared memory and every warp
   // walks it monotonically (its vectors only move forward); the descriptors of the row group a warp
-  // is in are cached in the warp's shared-memory region.
+  // is in are cached in the warp's shared-memory region, together with the resolved fast-path and
+  // prefetch plans.  Vectors are dealt in chunks of kVecChunk consecutive vectors (warp g takes chunks
+  // g, g + GW, ...), so a warp stays in one row group for a whole chunk while selective filters still
+  // spread evenly over the warps.
   auto first_tile = [&](int i) -> uint32_t { return rg_in_smem ? s_first[i] : __ldg(&q.rg_first_tile[i]); };
+  auto nth_vec = [&](uint32_t i) -> uint32_t { return ((i / kVecChunk) * GW + gw) * kVecChunk + (i % kVecChunk); };
   int rg = 0, rg_a = 0;          // row group of the vector being processed / being prefetched
   int cached_rg = -1;
-  auto descs_of = [&](int g) -> const ChunkDesc* { return g == cached_rg ? reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc) : q.chunks + size_t(g) * q.n_slots; };
+  const uint32_t ring_saddr = smem_u32(wb + q.wr_ring);
+  IssuePlan* const iplan = reinterpret_cast<IssuePlan*>(wb + q.wr_iplan);
+  auto issue = [&](uint32_t vec, int rs) {
+    if (vec >= q.n_tiles) {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
+    while (vec >= first_tile(rg_a + 1)) rg_a++;
+    if (rg_a == cached_rg)
+      issue_cached(q, *iplan, ring_saddr, q.slot_bytes, rs, (vec - first_tile(rg_a)) * q.vl, cached_rows, lane);
+    else
+      issue_vector(q, wb + q.wr_ring, vec, rs, first_tile(rg_a), __ldg(&q.rg_rows[rg_a]), q.chunks + size_t(rg_a) * q.n_slots, lane);
+  };
 
   // prologue: fill the ring (every iteration commits exactly one cp.async group, empty ones included,
   // so that "at most D-1 groups pending" always means "the current vector has landed")
-  for (int d = 0; d < D - 1; d++) {
-    const uint32_t vec = gw + uint32_t(d) * GW;
-    if (vec < q.n_tiles) {
-      while (vec >= first_tile(rg_a + 1)) rg_a++;
-      issue_vector(q, wb + q.wr_ring, vec, d, first_tile(rg_a), __ldg(&q.rg_rows[rg_a]), q.chunks + size_t(rg_a) * q.n_slots, lane);
-    } else {
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-  }
-  uint32_t it = 0;
-  for (uint32_t vec = gw; vec < q.n_tiles; vec += GW, it++) {
-    const int rs = int(it % uint32_t(D));
+  for (int d = 0; d < D - 1; d++) issue(nth_vec(uint32_t(d)), d);
+  int rs = 0, rs_ahead = D - 1;
+  for (uint32_t it = 0;; it++) {
+    const uint32_t vec = nth_vec(it);
+    if (vec >= q.n_tiles) break;
     while (vec >= first_tile(rg + 1)) rg++;
     if (rg != cached_rg) {  // warp-uniform: copy this row group's descriptors into shared memory
       const uint32_t* src = reinterpret_cast<const uint32_t*>(q.chunks + size_t(rg) * q.n_slots);
@@ -1487,21 +1574,15 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
       cached_rg = rg;
       cached_rows = __ldg(&q.rg_rows[rg]);
       __syncwarp();
-      if (q.fast_ok) {
-        if (lane == 0) build_fast_plan(q, reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc), reinterpret_cast<LeafRt*>(wb + q.wr_clrt), reinterpret_cast<FastPlan*>(wb + q.wr_fplan));
-        __syncwarp();
+      if (lane == 0) {
+        build_issue_plan(q, reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc), iplan);
+        if (q.fast_ok)
+          build_fast_plan(q, reinterpret_cast<ChunkDesc*>(wb + q.wr_cdesc), reinterpret_cast<LeafRt*>(wb + q.wr_clrt), reinterpret_cast<FastPlan*>(wb + q.wr_fplan));
       }
+      __syncwarp();
     }
-    {
-      const uint32_t ahead = vec + uint32_t(D - 1) * GW;
-      if (ahead < q.n_tiles) {
-        while (ahead >= first_tile(rg_a + 1)) rg_a++;
-        issue_vector(q, wb + q.wr_ring, ahead, int((it + uint32_t(D) - 1) % uint32_t(D)), first_tile(rg_a),
-                     rg_a == cached_rg ? cached_rows : __ldg(&q.rg_rows[rg_a]), descs_of(rg_a), lane);
-      } else {
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-    }
+    issue(nth_vec(it + uint32_t(D) - 1), rs_ahead);
+    rs_ahead = (rs_ahead + 1 == D) ? 0 : rs_ahead + 1;
     VecCtx v;
     v.q = &q;
     v.n_rows = cached_rows;
@@ -1527,7 +1608,8 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
         if (q.aggs[a].func != 4 /*count*/) vec_aggregate(v, wb, a, lane, cur_slot);
       cur_slot = end_slot;
     }
-    __syncwarp();  // every lane is done with ring slot rs before lane 0 refills it next iteration
+    __syncwarp();  // every lane is done with ring slot rs before it is refilled
+    rs = (rs + 1 == D) ? 0 : rs + 1;
   }
   // ---- final flush ---------------------------------------------------------------------------------
   if (cur_slot != kNoSlot) {
