@@ -46,22 +46,26 @@ int32_t fail(int32_t code, const std::string& msg) {
     }                                                                                          \
   } while (0)
 
+// Stream-ordered device allocation (cudaMallocAsync on the engine stream, pool kept warm): a query's
+// scratch and a streamed part's columns cost microseconds to allocate instead of a cudaMalloc each.
 struct DevBuf {
   void* p = nullptr;
   size_t n = 0;
+  cudaStream_t st = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { reset(); }
   void reset() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
     p = nullptr;
     n = 0;
   }
-  cudaError_t alloc(size_t bytes) {
+  cudaError_t alloc(size_t bytes, cudaStream_t stream) {
     reset();
+    st = stream;
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMalloc(&p, bytes);
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
     if (e == cudaSuccess) n = bytes;
     else p = nullptr;
     return e;
@@ -193,14 +197,14 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
   if (!img.error.empty()) return FGPU_OK;  // surfaces as an error only if a query projects the column
   if (img.resident) return FGPU_OK;
   void* dev = nullptr;
-  CUDA_TRY(cudaMalloc(&dev, img.dev_bytes));
+  CUDA_TRY(cudaMallocAsync(&dev, img.dev_bytes, ctx->stream));
   cudaError_t e = cudaMemcpyAsync(dev, img.meta.data(), img.meta.size(), cudaMemcpyHostToDevice, ctx->stream);
   for (const Extent& x : img.extents) {
     if (e != cudaSuccess) break;
     e = cudaMemcpyAsync(static_cast<uint8_t*>(dev) + x.dst_off, x.src, x.len, cudaMemcpyHostToDevice, ctx->stream);
   }
   if (e != cudaSuccess) {
-    cudaFree(dev);
+    cudaFreeAsync(dev, ctx->stream);
     cudaGetLastError();
     return fail(FGPU_ERR_CUDA, std::string("column upload: ") + cudaGetErrorString(e));
   }
@@ -223,9 +227,9 @@ void release_staging(fgpu_ctx* ctx) {
   ctx->pending_uploads.clear();
 }
 
-void free_part(Part* p) {
+void free_part(fgpu_ctx* ctx, Part* p) {
   for (auto& kv : p->images)
-    if (kv.second.dev) cudaFree(kv.second.dev);
+    if (kv.second.dev) cudaFreeAsync(kv.second.dev, ctx->stream);
 }
 
 struct VisibleRG {
@@ -932,7 +936,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   if (!rows_plan) {
     size_t off_aggs, off_tags, off_keys;
     size_t tbytes = table_layout(qd, &off_aggs, &off_tags, &off_keys);
-    CUDA_TRY(res->table.alloc(tbytes));
+    CUDA_TRY(res->table.alloc(tbytes, ctx->stream));
     res->table_bytes = tbytes;
     bind_table(&qd, static_cast<uint8_t*>(res->table.p));
   }
@@ -950,7 +954,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     }
     state_off = out_bytes;
     out_bytes = al(out_bytes + size_t(tiles) * 8);
-    CUDA_TRY(res->table.alloc(out_bytes));
+    CUDA_TRY(res->table.alloc(out_bytes, ctx->stream));
     uint8_t* ob = static_cast<uint8_t*>(res->table.p);
     for (int o = 0; o < qd.n_out; o++) {
       qd.out_data[o] = ob + out_off[size_t(o)];
@@ -967,7 +971,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   size_t o_lut = align16(o_rows + rg_rows.size() * 4);
   size_t o_cnt = align16(o_lut + lutbytes.size());
   size_t aux_bytes = o_cnt + 64;
-  CUDA_TRY(res->aux.alloc(aux_bytes));
+  CUDA_TRY(res->aux.alloc(aux_bytes, ctx->stream));
   uint8_t* aux = static_cast<uint8_t*>(res->aux.p);
   for (auto& fx : lut_fix) lrt[fx.first].lut = aux + o_lut + fx.second;
   std::vector<uint8_t> hostaux(aux_bytes, 0);
@@ -981,7 +985,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   qd.rg_first_tile = reinterpret_cast<const uint32_t*>(aux + o_first);
   qd.rg_rows = reinterpret_cast<const uint32_t*>(aux + o_rows);
   qd.counters = reinterpret_cast<unsigned long long*>(aux + o_cnt);
-  CUDA_TRY(res->qdesc_dev.alloc(sizeof(QueryDesc)));
+  CUDA_TRY(res->qdesc_dev.alloc(sizeof(QueryDesc), ctx->stream));
 
   cudaStream_t s = ctx->stream;
   CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
@@ -1132,7 +1136,7 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   // Upper bound of result rows: every slot could be occupied; count first to size the output.
   // (k_finalize with max_out == 0 only counts.)
   DevBuf cnt;
-  CUDA_TRY(cnt.alloc(16));
+  CUDA_TRY(cnt.alloc(16, ctx->stream));
   CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
   fd.out_count = static_cast<unsigned int*>(cnt.p);
   fd.max_out = 0;
@@ -1151,7 +1155,7 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   if (G > 0) {
     DevBuf out;
     size_t bytes = (size_t(nk) + size_t(na) + 1) * G * 8;
-    CUDA_TRY(out.alloc(bytes));
+    CUDA_TRY(out.alloc(bytes, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
     fd.max_out = n_groups;
     fd.out_keys = static_cast<long long*>(out.p);
@@ -1266,6 +1270,12 @@ int32_t fgpu_init(const fgpu_config* cfg, fgpu_ctx** out) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   ctx->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+    uint64_t keep = ~0ull;  // freed blocks stay in the pool: allocation is a pointer bump afterwards
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
   *out = ctx.release();
   return FGPU_OK;
@@ -1275,7 +1285,7 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
   if (!ctx) return FGPU_OK;
   cudaSetDevice(ctx->device);
   for (auto& t : ctx->tables)
-    for (auto& p : t.second.parts) free_part(p.get());
+    for (auto& p : t.second.parts) free_part(ctx, p.get());
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1303,14 +1313,14 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
     for (const std::string& col : part->columns) {
       int32_t rc = ensure_resident(ctx, &t, part.get(), col, nullptr);
       if (rc) {
-        free_part(part.get());
+        free_part(ctx, part.get());
         return rc;
       }
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     release_staging(ctx);
     if (e != cudaSuccess) {
-      free_part(part.get());
+      free_part(ctx, part.get());
       return fail(FGPU_ERR_CUDA, std::string("part upload: ") + cudaGetErrorString(e));
     }
     part->file = nullptr;
@@ -1336,7 +1346,7 @@ int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {
       cudaSetDevice(ctx->device);
       cudaStreamSynchronize(ctx->stream);
       release_staging(ctx);
-      free_part(parts[i].get());
+      free_part(ctx, parts[i].get());
       parts.erase(parts.begin() + long(i));
       return FGPU_OK;
     }
@@ -1352,7 +1362,7 @@ int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   release_staging(ctx);
-  for (auto& p : it->second.parts) free_part(p.get());
+  for (auto& p : it->second.parts) free_part(ctx, p.get());
   ctx->tables.erase(it);
   return FGPU_OK;
 }
@@ -1455,7 +1465,7 @@ int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* ga
     if (nbytes != r->table_bytes) return fail(FGPU_ERR_INVALID, "partial table size differs between ranks (dictionaries not preloaded identically?)");
     // Start from an empty table and fold every rank's partial in, this rank's own included.
     DevBuf merged;
-    CUDA_TRY(merged.alloc(r->table_bytes));
+    CUDA_TRY(merged.alloc(r->table_bytes, ctx->stream));
     QueryDesc qd = r->qd;
     bind_table(&qd, static_cast<uint8_t*>(merged.p));
     CUDA_TRY(launch_table_init(qd, ctx->stream));
@@ -1634,8 +1644,8 @@ int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_
   }
   const bool is_str = phys == PT_BYTE_ARRAY;
   DevBuf d_vals, d_valid;
-  CUDA_TRY(d_vals.alloc(total * (is_str ? 4 : 8)));
-  if (!is_str) CUDA_TRY(d_valid.alloc(total));
+  CUDA_TRY(d_vals.alloc(total * (is_str ? 4 : 8), ctx->stream));
+  if (!is_str) CUDA_TRY(d_valid.alloc(total, ctx->stream));
   uint64_t row = 0;
   for (auto& rg : part->rgs) {
     const ChunkDesc& cd = rg.cols.at(column).desc;
