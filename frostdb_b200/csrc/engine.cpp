@@ -1286,6 +1286,7 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& t : ctx->tables)
     for (auto& p : t.second.parts) free_part(ctx, p.get());
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
