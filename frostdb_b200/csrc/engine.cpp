@@ -806,7 +806,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       qd.wr_keyw = uint32_t(off); off = r128(off + (qd.table_mode == TM_HASH ? size_t(qd.key_words) * vl * 8 : 0));
       qd.wr_tmp1 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 8 : 0));
       qd.wr_tmp2 = uint32_t(off); off = r128(off + (any_expr ? size_t(vl) * 16 : 0));
-      qd.wr_acc = uint32_t(off); off = r128(off + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4 + 32 * 4);
+      qd.wr_acc = uint32_t(off); off = r128(off + size_t(qd.n_aggs) * 32 * 8 + 16 + 32 * 4 + 32 * 4 + (qd.table_mode == TM_HASH ? size_t(qd.key_words) * 32 * 8 : 0));
       qd.wr_cdesc = uint32_t(off); off = r128(off + size_t(std::max(qd.n_slots, 1)) * sizeof(ChunkDesc));
       qd.wr_clrt = uint32_t(off); off = r128(off + size_t(std::max(qd.n_leaves, 1)) * sizeof(LeafRt));
       qd.wr_fplan = uint32_t(off); off = r128(off + 512);

@@ -680,10 +680,10 @@ __device__ __forceinline__ WarpMem warp_mem(const QueryDesc& q, uint8_t* base) {
   m.tmp1 = reinterpret_cast<long long*>(base + q.wr_tmp1);
   m.tmp2 = reinterpret_cast<long long*>(base + q.wr_tmp2);
   m.acc = reinterpret_cast<long long*>(base + q.wr_acc);
-  m.lastkw = reinterpret_cast<unsigned long long*>(base + q.wr_acc + size_t(kMaxAggs) * 32 * 8);
-  m.selected = m.lastkw + size_t(kMaxKeyWords) * 32;
-  m.lastslot = reinterpret_cast<uint32_t*>(m.selected + 2);
-  m.cnt = m.lastslot + 32;
+  m.selected = reinterpret_cast<unsigned long long*>(base + q.wr_acc + size_t(q.n_aggs) * 32 * 8);
+  m.cnt = reinterpret_cast<uint32_t*>(m.selected + 2);
+  m.lastslot = m.cnt + 32;
+  m.lastkw = reinterpret_cast<unsigned long long*>(m.lastslot + 32);  // [key_words][32], hash mode only
   m.cdesc = reinterpret_cast<ChunkDesc*>(base + q.wr_cdesc);
   m.clrt = reinterpret_cast<LeafRt*>(base + q.wr_clrt);
   m.fplan = reinterpret_cast<struct FastPlan*>(base + q.wr_fplan);
@@ -1177,8 +1177,15 @@ __device__ __forceinline__ void issue_cached(const QueryDesc& q, const IssuePlan
     if (it.is_seed) {
       if (lane < 2) cp_async16(dst + it.dst_off + uint32_t(lane) * 16u, it.src + size_t(r0 / kIndexRows) * sizeof(Seed) + lane * 16);
     } else {
-      const uint8_t* src = it.src + size_t(r0) * 8;
-      for (uint32_t o = uint32_t(lane) * 16u; o < plain_sz; o += 512u) cp_async16(dst + it.dst_off + o, src + o);
+      const uint8_t* src = it.src + size_t(r0) * 8 + uint32_t(lane) * 16u;
+      const uint32_t d = dst + it.dst_off + uint32_t(lane) * 16u;
+      if (n == uint32_t(q.vl)) {  // full vector: fixed trip count
+        const uint32_t iters = uint32_t(q.vl) / 64u;
+#pragma unroll 4
+        for (uint32_t j = 0; j < iters; j++) cp_async16(d + j * 512u, src + j * 512u);
+      } else {
+        for (uint32_t o = uint32_t(lane) * 16u; o < plain_sz; o += 512u) cp_async16(d - uint32_t(lane) * 16u + o, src - uint32_t(lane) * 16u + o);
+      }
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1504,7 +1511,6 @@ __device__ __forceinline__ uint32_t fast_dispatch(const VecCtx& v, uint8_t* m, c
 __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __restrict__ qp) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ QueryDesc sq;
-  __shared__ uint32_t s_first[kRgSmem + 1];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(qp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
@@ -1513,6 +1519,7 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
   __syncthreads();
   const QueryDesc& q = sq;
   const bool rg_in_smem = q.n_rg <= kRgSmem;
+  uint32_t* const s_first = reinterpret_cast<uint32_t*>(dyn + size_t(blockDim.x >> 5) * q.wr_bytes);  // after the warp regions
   if (rg_in_smem)
     for (int i = threadIdx.x; i <= q.n_rg; i += blockDim.x) s_first[i] = __ldg(&q.rg_first_tile[i]);
   __syncthreads();
@@ -1520,9 +1527,9 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
   uint8_t* const wb = dyn + size_t(warp) * q.wr_bytes;  // this warp's shared-memory region (see WarpMem)
   const int D = q.n_ring;
   uint32_t cached_rows = 0;
-  if (lane == 0) reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8)[0] = 0;
-  reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4)[lane] = 0;
-  reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16)[lane] = kNoSlot;
+  if (lane == 0) reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(q.n_aggs) * 32 * 8)[0] = 0;
+  reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(q.n_aggs) * 32 * 8 + 16)[lane] = 0;
+  reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(q.n_aggs) * 32 * 8 + 16 + 32 * 4)[lane] = kNoSlot;
   for (int a = 0; a < q.n_aggs; a++) reinterpret_cast<long long*>(wb + q.wr_acc)[a * 32 + lane] = agg_identity(q.aggs[a].func, q.aggs[a].is_float);
   __syncwarp();
 
@@ -1613,14 +1620,14 @@ __global__ void __launch_bounds__(kVecThreads, 4) k_scan(const QueryDesc* __rest
   }
   // ---- final flush ---------------------------------------------------------------------------------
   if (cur_slot != kNoSlot) {
-    const uint32_t tt = __reduce_add_sync(FULL, reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8 + 16 + 32 * 4)[lane]);
+    const uint32_t tt = __reduce_add_sync(FULL, reinterpret_cast<uint32_t*>(wb + q.wr_acc + size_t(q.n_aggs) * 32 * 8 + 16)[lane]);
     if (lane == 0 && tt) atomicAdd(q.t_rows + cur_slot, (unsigned long long)tt);
     for (int a = 0; a < q.n_aggs; a++) {
       if (q.aggs[a].func == 4) continue;
       flush_agg(q.aggs[a].func, q.aggs[a].is_float, q.t_agg[a] + cur_slot, reinterpret_cast<long long*>(wb + q.wr_acc)[a * 32 + lane], lane);
     }
   }
-  if (lane == 0 && reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8)[0]) atomicAdd(q.counters + 0, reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(kMaxAggs) * 32 * 8 + size_t(kMaxKeyWords) * 32 * 8)[0]);
+  if (lane == 0 && reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(q.n_aggs) * 32 * 8)[0]) atomicAdd(q.counters + 0, reinterpret_cast<unsigned long long*>(wb + q.wr_acc + size_t(q.n_aggs) * 32 * 8)[0]);
   if (overflow) atomicExch(q.counters + 1, 1ull);
 }
 
@@ -1870,7 +1877,7 @@ cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st) {
 cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st) {
   if (q.n_tiles == 0) return cudaSuccess;
   const int warps = kVecThreads / 32;
-  const size_t smem = size_t(q.wr_bytes) * warps;
+  const size_t smem = size_t(q.wr_bytes) * warps + (q.n_rg <= 2048 ? (size_t(q.n_rg) + 1) * 4 + 16 : 0);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
