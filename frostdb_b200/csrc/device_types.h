@@ -178,6 +178,36 @@ struct QueryDesc {
 };
 
 // Dense/hash table -> compacted result rows.
+// ---- sorted-run scan (k_runs): the plan shape of compacted parts ---------------------------------------
+// Row groups whose filter columns and aggregate inputs are PLAIN non-null int64 and whose group-key
+// columns are run-length only (sorted parts) are scanned by a dedicated kernel that walks the key run
+// directories with warp-uniform cursors.  The host lists those row groups here; the rest of the table
+// goes through the general scan kernel into the same aggregate table.
+constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 2, kRunsCols = kRunsLeaves + kRunsAggs;
+
+struct RunsRg {
+  uint32_t n_rows;
+  uint32_t _pad;
+  long long lo[kRunsLeaves], hi[kRunsLeaves];  // inclusive bounds of the (fused) range leaves for this row group
+  const uint8_t* col[kRunsCols];               // the staged PLAIN columns (distinct leaf and aggregate inputs)
+  const Run* runs[kRunsKeys];                  // run directory of every group-key column (dictionary ids premapped)
+  const Seed* seeds[kRunsKeys];                // cursor seeds, one per kIndexRows rows
+};
+
+struct RunsDesc {
+  uint32_t n_rg, n_spans;
+  uint32_t block_rows;   // rows per prefetch block (multiple of 128)
+  uint32_t span_blocks;  // blocks per span: a span is the contiguous piece of a row group one warp takes per turn
+  uint32_t n_ring, n_cols;
+  uint32_t leaf_col[kRunsLeaves], agg_col[kRunsAggs];  // index into RunsRg::col
+  uint32_t stride[kRunsKeys];                           // dense-table stride of every key
+  const RunsRg* rgs;
+  const uint32_t* rg_first_span;  // [n_rg + 1]
+  unsigned long long* t_rows;
+  long long* t_agg[kRunsAggs];
+  unsigned long long* counters;
+};
+
 struct FinalizeDesc {
   int32_t table_mode, key_words, n_keys, n_aggs;
   uint32_t table_slots;

@@ -885,11 +885,44 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   std::vector<std::pair<size_t, size_t>> lut_fix;  // (index into lrt, offset into lutbytes)
   uint32_t tiles = 0;
   const uint32_t tile_len = q.kind == FGPU_PLAN_FILTER ? uint32_t(kTileRows) : uint32_t(qd.vl);  // rows plan: CTA tiles; scan: warp vectors
-  for (int g = 0; g < n_rg; g++) {
-    RowGroupHost& rg = *c.rgs[size_t(g)].rg;
-    first_tile[size_t(g)] = tiles;
-    rg_rows[size_t(g)] = rg.n_rows;
-    tiles += (rg.n_rows + tile_len - 1) / tile_len;
+  // ---- sorted-run scan: query-level eligibility (see runs_scan.cu) --------------------------------
+  RunsDesc rd{};
+  std::vector<RunsRg> runs_rgs;
+  int runs_nl = 0, runs_nk = 0, runs_na = 0;
+  int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
+  bool runs_q = q.kind != FGPU_PLAN_FILTER && qd.fast_ok && !getenv("FROSTGPU_NO_RUNS");
+  if (runs_q) {
+    for (int l = 0; l < n_leaves && runs_q; l++) {
+      const LeafDesc& ld = qd.leaves[l];
+      if (ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || runs_nl >= kRunsLeaves) runs_q = false;
+      else runs_leaf_slot[runs_nl++] = ld.slot;
+    }
+    for (int a = 0; a < qd.n_aggs && runs_q; a++) {
+      if (qd.aggs[a].func == FGPU_AGG_COUNT) continue;
+      if (qd.aggs[a].func != FGPU_AGG_SUM || qd.aggs[a].is_float || runs_na >= kRunsAggs) { runs_q = false; break; }
+      runs_agg_slot[runs_na] = qd.prog[qd.aggs[a].prog_off].slot;
+      runs_agg_index[runs_na++] = a;
+    }
+    if (qd.n_keys > kRunsKeys) runs_q = false;
+    runs_nk = qd.n_keys;
+  }
+  int runs_col_slot[kRunsCols] = {0};
+  if (runs_q) {  // distinct staged columns
+    auto col_of = [&](int slot) {
+      for (uint32_t i = 0; i < rd.n_cols; i++)
+        if (runs_col_slot[i] == slot) return i;
+      runs_col_slot[rd.n_cols] = slot;
+      return rd.n_cols++;
+    };
+    for (int l = 0; l < runs_nl; l++) rd.leaf_col[l] = col_of(runs_leaf_slot[l]);
+    for (int a = 0; a < runs_na; a++) rd.agg_col[a] = col_of(runs_agg_slot[a]);
+    for (int k = 0; k < runs_nk; k++) rd.stride[k] = qd.keys[k].dense_stride;
+  }
+  std::vector<uint32_t> runs_rows;
+  int gi = 0;  // row groups that stay with the general scan kernel
+  for (int g0 = 0; g0 < n_rg; g0++) {
+    RowGroupHost& rg = *c.rgs[size_t(g0)].rg;
+    const int g = gi;
     for (int s = 0; s < n_slots; s++) {
       ChunkDesc d{};
       d.kind = CK_ABSENT;
@@ -927,9 +960,73 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       }
       lrt[size_t(g) * n_leaves + l] = rt;
     }
+    // ---- does this row group qualify for the sorted-run kernel? ----
+    bool runs_ok = runs_q && rg.n_rows > 0;
+    RunsRg rr{};
+    if (runs_ok) {
+      rr.n_rows = rg.n_rows;
+      for (int l = 0; l < runs_nl && runs_ok; l++) {
+        if (lrt[size_t(g) * n_leaves + l].mode != LM_EVAL) runs_ok = false;
+        rr.lo[l] = qd.leaves[l].lo_i;
+        rr.hi[l] = qd.leaves[l].hi_i;
+      }
+      for (uint32_t i = 0; i < rd.n_cols && runs_ok; i++) {
+        const ChunkDesc& d = chunks[size_t(g) * n_slots + runs_col_slot[i]];
+        if (d.kind != CK_PLAIN64 || d.has_nulls) runs_ok = false;
+        rr.col[i] = d.values;
+      }
+      for (int k = 0; k < runs_nk && runs_ok; k++) {
+        const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.keys[k].slot];
+        // run-length only, and runs long enough that a 32-row step rarely holds two run ends
+        if (d.kind != CK_DICT_STR || d.has_nulls || d.n_bp_runs != 0 || uint64_t(d.n_runs) * 32 > uint64_t(rg.n_rows) + 1024) runs_ok = false;
+        rr.runs[k] = d.runs;
+        rr.seeds[k] = d.seeds;
+      }
+    }
+    if (runs_ok) {
+      runs_rgs.push_back(rr);
+      runs_rows.push_back(rg.n_rows);
+      lut_fix.erase(std::remove_if(lut_fix.begin(), lut_fix.end(), [&](const std::pair<size_t, size_t>& f) { return f.first >= size_t(g) * n_leaves; }), lut_fix.end());
+      continue;  // slot g of the general tables is reused by the next row group
+    }
+    first_tile[size_t(g)] = tiles;
+    rg_rows[size_t(g)] = rg.n_rows;
+    tiles += (rg.n_rows + tile_len - 1) / tile_len;
+    gi++;
   }
-  first_tile[size_t(n_rg)] = tiles;
+  first_tile[size_t(gi)] = tiles;
+  qd.n_rg = gi;
   qd.n_tiles = tiles;
+  // spans of the sorted-run kernel: sized so that every warp of the grid gets several
+  std::vector<uint32_t> runs_first_span;
+  if (!runs_rgs.empty()) {
+    auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    int br = envi("FROSTGPU_RUNS_BR", 256);
+    if (br != 128 && br != 256 && br != 512) br = 256;
+    int ring = envi("FROSTGPU_RUNS_RING", 3);
+    ring = std::min(4, std::max(2, ring));
+    if (rd.n_cols == 0) { br = 128; ring = 2; }  // nothing is staged (count(*) per group): the ring is idle
+    rd.block_rows = uint32_t(br);
+    rd.n_ring = uint32_t(ring);
+    rd.n_rg = uint32_t(runs_rgs.size());
+    int per_sm = 1;
+    CUDA_TRY(runs_blocks_per_sm(rd, runs_nl, runs_nk, runs_na, &per_sm));
+    const uint64_t warps = uint64_t(ctx->sm_count) * uint64_t(std::max(per_sm, 1)) * (kRunsThreads / 32);
+    uint64_t total = 0;
+    for (uint32_t r : runs_rows) total += r;
+    uint64_t span_blocks = total / (warps * 8 * uint64_t(br));
+    span_blocks = std::min<uint64_t>(64, std::max<uint64_t>(4, span_blocks));
+    if (const char* e = getenv("FROSTGPU_RUNS_SPAN")) span_blocks = std::max(1, atoi(e));
+    rd.span_blocks = uint32_t(span_blocks);
+    const uint64_t span_rows = span_blocks * uint64_t(br);
+    uint32_t spans = 0;
+    for (uint32_t r : runs_rows) {
+      runs_first_span.push_back(spans);
+      spans += uint32_t((uint64_t(r) + span_rows - 1) / span_rows);
+    }
+    runs_first_span.push_back(spans);
+    rd.n_spans = spans;
+  }
 
   // ---- device memory -----------------------------------------------------------------------
   const bool rows_plan = q.kind == FGPU_PLAN_FILTER;
@@ -969,7 +1066,9 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   size_t o_first = align16(o_lrt + lrt.size() * sizeof(LeafRt));
   size_t o_rows = align16(o_first + first_tile.size() * 4);
   size_t o_lut = align16(o_rows + rg_rows.size() * 4);
-  size_t o_cnt = align16(o_lut + lutbytes.size());
+  size_t o_rrg = align16(o_lut + lutbytes.size());
+  size_t o_rspan = align16(o_rrg + runs_rgs.size() * sizeof(RunsRg));
+  size_t o_cnt = align16(o_rspan + runs_first_span.size() * 4);
   size_t aux_bytes = o_cnt + 64;
   CUDA_TRY(res->aux.alloc(aux_bytes, ctx->stream));
   uint8_t* aux = static_cast<uint8_t*>(res->aux.p);
@@ -980,6 +1079,10 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   std::memcpy(hostaux.data() + o_first, first_tile.data(), first_tile.size() * 4);
   std::memcpy(hostaux.data() + o_rows, rg_rows.data(), rg_rows.size() * 4);
   if (!lutbytes.empty()) std::memcpy(hostaux.data() + o_lut, lutbytes.data(), lutbytes.size());
+  if (!runs_rgs.empty()) {
+    std::memcpy(hostaux.data() + o_rrg, runs_rgs.data(), runs_rgs.size() * sizeof(RunsRg));
+    std::memcpy(hostaux.data() + o_rspan, runs_first_span.data(), runs_first_span.size() * 4);
+  }
   qd.chunks = reinterpret_cast<const ChunkDesc*>(aux + o_chunks);
   qd.leaf_rt = reinterpret_cast<const LeafRt*>(aux + o_lrt);
   qd.rg_first_tile = reinterpret_cast<const uint32_t*>(aux + o_first);
@@ -998,10 +1101,18 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   } else {
     CUDA_TRY(launch_table_init(qd, s));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
+    if (!runs_rgs.empty()) {
+      rd.rgs = reinterpret_cast<const RunsRg*>(aux + o_rrg);
+      rd.rg_first_span = reinterpret_cast<const uint32_t*>(aux + o_rspan);
+      rd.t_rows = qd.t_rows;
+      for (int a = 0; a < runs_na; a++) rd.t_agg[a] = qd.t_agg[runs_agg_index[a]];
+      rd.counters = qd.counters;
+      CUDA_TRY(launch_runs(rd, runs_nl, runs_nk, runs_na, ctx->sm_count, s));
+    }
     CUDA_TRY(launch_scan(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
   }
   CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
-  st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0);
+  st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0) + (runs_rgs.empty() ? 0 : 1);
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
   unsigned long long counters[8] = {0};
   CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));

@@ -1363,8 +1363,12 @@ __device__ __noinline__ uint32_t fast_pass(const QueryDesc& q, uint8_t* wb, cons
 }
 
 // Tight variant of the fused pass, chosen per row group when every leaf is a plain (non-negated) int64
-// range, every key column chunk is run-length only (sorted parts) and every aggregate is Sum(int64):
-// the hot loop then carries a handful of registers and no calls.
+// range and every aggregate is Sum(int64).  The key cursors are WARP-UNIFORM: they sit on the runs that
+// hold the first row of the current step, so the distance to the nearest run end says how many whole
+// 32-row steps lie inside one group.  Those steps run in an inner loop with no vote, no shuffle and no
+// branch (two loads, a range test, two adds).  A step that straddles one run end is split by lane index
+// (lanes below the boundary close the running group, the others open the next one); only steps with a
+// second boundary or a bit-packed run compute a slot per lane and go through fast_cold_step.
 template <int NL, int NK, int NA>
 __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb, const FastPlan& fp, uint32_t slot_saddr,
                                                   const uint8_t* slotmem, uint32_t r0, uint32_t chunk, uint32_t n_in, int steps, int lane,
@@ -1379,7 +1383,7 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb
     lcol[l] = slot_saddr + fp.leaf[l].col_off + uint32_t(lane) * 8u;
   }
   uint32_t kk[NK > 0 ? NK : 1], kend[NK > 0 ? NK : 1], kadd[NK > 0 ? NK : 1];
-  uint32_t kbp = 0;  // bit k: this lane's current run of key k is bit-packed (kadd[k] is not valid)
+  uint32_t kbp = 0;  // bit k: the current run of key k is bit-packed (kadd[k] is not valid)
 #pragma unroll
   for (int k = 0; k < NK; k++) {
     const FastKey& fk = fp.key[k];
@@ -1396,61 +1400,72 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb
     acol[a] = slot_saddr + fp.agg[a].col_off + uint32_t(lane) * 8u;
     part[a] = (unsigned long long)m.acc[fp.agg[a].index * 32 + lane];
   }
-  uint32_t cs = cur_slot, cnt = m.cnt[lane], selected = 0;
-  int s = 0;
-  while (s < steps) {
+  uint32_t cs = cur_slot, cnt = m.cnt[lane], sel = 0;
+  const uint32_t rend = r0 + n_in;
+
+  // moves the cursors onto the runs that hold `row` (same row in every lane: the loads broadcast)
+  auto advance = [&](uint32_t row) {
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      if (row >= kend[k]) {
+        const Run* runs = fp.key[k].runs;
+        uint32_t i = kk[k], e;
+        do {
+          i++;
+          e = __ldg(&runs[i + 1].start);
+        } while (row >= e);
+        kk[k] = i;
+        kend[k] = e;
+        const uint2 vm = __ldg(reinterpret_cast<const uint2*>(&runs[i].val));
+        kadd[k] = (vm.x + 1u) * fp.key[k].stride;
+        kbp = (kbp & ~(1u << k)) | ((vm.y & 1u) << k);
+      }
+    }
+  };
+  // the running group leaves the registers (Sum only: a group without rows has nothing to add)
+  auto flush = [&]() {
+    const uint32_t tt = __reduce_add_sync(FULL, cnt);
+    if (tt == 0) return;
+    if (lane == 0) atomicAdd(q.t_rows + cs, (unsigned long long)tt);
+    cnt = 0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      unsigned long long v = part[a];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(q.t_agg[fp.agg[a].index] + cs), v);
+      part[a] = 0;
+    }
+  };
+  auto passes = [&](int s) -> bool {
+    bool act = true;
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const long long x = lds64(lcol[l] + uint32_t(s) * 256u);
+      act = act && x >= lo[l] && x <= hi[l];
+    }
+    return act;
+  };
+  // slot of row r from the cursors (which sit on a row <= r); unpacks bit-packed runs
+  auto lane_slot = [&](uint32_t r) -> uint32_t {
     uint32_t slot = 0;
-    bool act = false;
-#pragma unroll 1
-    for (; s < steps; s++) {
-      const uint32_t idx = uint32_t(s) * 32u + uint32_t(lane);
-      act = idx < n_in;
 #pragma unroll
-      for (int l = 0; l < NL; l++) {
-        const long long x = lds64(lcol[l] + uint32_t(s) * 256u);
-        act = act && x >= lo[l] && x <= hi[l];
+    for (int k = 0; k < NK; k++) {
+      const FastKey& fk = fp.key[k];
+      uint32_t i = kk[k];
+      while (r >= __ldg(&fk.runs[i + 1].start)) i++;
+      const uint4 run = __ldg(reinterpret_cast<const uint4*>(fk.runs + i));
+      uint32_t v = run.z;
+      if (run.w & 1u) {
+        const uint32_t w = (run.w >> 8) & 0xffu;
+        v = __ldg(fk.lut + extract_bits(fk.stream, run.y, uint64_t(r - run.x) * w, w));
       }
-      const unsigned amask = __ballot_sync(FULL, act);
-      if (amask == 0) continue;
-      const uint32_t r = r0 + idx;
-      slot = 0;
-#pragma unroll
-      for (int k = 0; k < NK; k++) {
-        if (act && r >= kend[k]) {  // this lane crossed into the next run(s)
-          const Run* runs = fp.key[k].runs;
-          do {
-            kk[k]++;
-            kend[k] = __ldg(&runs[kk[k] + 1].start);
-          } while (r >= kend[k]);
-          const uint2 vm = __ldg(reinterpret_cast<const uint2*>(&runs[kk[k]].val));
-          kadd[k] = (vm.x + 1u) * fp.key[k].stride;
-          kbp = (kbp & ~(1u << k)) | ((vm.y & 1u) << k);
-        }
-        slot += kadd[k];
-      }
-      selected += __popc(amask);
-      // group change, or a lane sits in a bit-packed boundary group: leave the hot loop
-      if (!__all_sync(FULL, !act || (slot == cs && kbp == 0))) break;
-      cnt += act ? 1u : 0u;
-#pragma unroll
-      for (int a = 0; a < NA; a++) part[a] += act ? (unsigned long long)lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+      slot += (v + 1u) * fk.stride;
     }
-    if (s >= steps) break;
-    if (__any_sync(FULL, act && kbp != 0)) {  // general value of the lanes inside bit-packed runs
-      const uint32_t r = r0 + uint32_t(s) * 32u + uint32_t(lane);
-      slot = 0;
-#pragma unroll
-      for (int k = 0; k < NK; k++) {
-        uint32_t add = kadd[k];
-        if (act && ((kbp >> k) & 1u)) {
-          const FastKey& fk = fp.key[k];
-          const uint4 run = __ldg(reinterpret_cast<const uint4*>(fk.runs + kk[k]));
-          const uint32_t w = (run.w >> 8) & 0xffu;
-          add = (__ldg(fk.lut + extract_bits(fk.stream, run.y, uint64_t(r - run.x) * w, w)) + 1u) * fk.stride;
-        }
-        slot += add;
-      }
-    }
+    return slot;
+  };
+  auto general_step = [&](int s, uint32_t r, bool act) {
+    const uint32_t slot = act ? lane_slot(r) : 0u;
     long long val[NA > 0 ? NA : 1], p2[NA > 0 ? NA : 1];
 #pragma unroll
     for (int a = 0; a < NA; a++) {
@@ -1460,12 +1475,78 @@ __device__ __noinline__ uint32_t fast_pass_tight(const QueryDesc& q, uint8_t* wb
     fast_cold_step<NA>(q, fp, slot, act, val, lane, cs, cnt, p2);
 #pragma unroll
     for (int a = 0; a < NA; a++) part[a] = (unsigned long long)p2[a];
+  };
+
+  int s = 0;
+  while (s < steps) {
+    uint32_t rs = r0 + uint32_t(s) * 32u;
+    advance(rs);
+    if (kbp != 0) {  // a long bit-packed run (unsorted key column): one slot per lane
+      const uint32_t r = rs + uint32_t(lane);
+      const bool act = r < rend && passes(s);
+      sel += act ? 1u : 0u;
+      general_step(s, r, act);
+      s++;
+      continue;
+    }
+    uint32_t safe = rend, us = 0;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      safe = min(safe, kend[k]);
+      us += kadd[k];
+    }
+    if (us != cs) {
+      if (cs != kNoSlot) flush();
+      cs = us;
+    }
+    // ---- whole steps inside the running group ----
+    const int e = s + int((safe - rs) >> 5);
+#pragma unroll 2
+    for (; s < e; s++) {
+      const bool act = passes(s);
+      cnt += act ? 1u : 0u;
+      sel += act ? 1u : 0u;
+#pragma unroll
+      for (int a = 0; a < NA; a++) part[a] += act ? (unsigned long long)lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+    }
+    if (s >= steps) break;
+    // ---- the step that holds row `safe`: lanes below it still belong to the running group ----
+    rs = r0 + uint32_t(s) * 32u;
+    const uint32_t r = rs + uint32_t(lane);
+    const bool act = r < rend && passes(s);
+    const bool old = act && r < safe;
+    sel += act ? 1u : 0u;
+    cnt += old ? 1u : 0u;
+#pragma unroll
+    for (int a = 0; a < NA; a++) part[a] += old ? (unsigned long long)lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+    if (safe < rend) {
+      advance(safe);
+      uint32_t safe2 = rend, us2 = 0;
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        safe2 = min(safe2, kend[k]);
+        us2 += kadd[k];
+      }
+      const bool fresh = act && !old;
+      if (kbp == 0 && safe2 >= min(rs + 32u, rend)) {  // one boundary in this step: the rest is one group
+        if (us2 != cs) {
+          flush();
+          cs = us2;
+        }
+        cnt += fresh ? 1u : 0u;
+#pragma unroll
+        for (int a = 0; a < NA; a++) part[a] += fresh ? (unsigned long long)lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+      } else {
+        general_step(s, r, fresh);
+      }
+    }
     s++;
   }
   m.cnt[lane] = cnt;
 #pragma unroll
   for (int a = 0; a < NA; a++) m.acc[fp.agg[a].index * 32 + lane] = (long long)part[a];
-  if (lane == 0) m.selected[0] += selected;
+  sel = __reduce_add_sync(FULL, sel);
+  if (lane == 0) m.selected[0] += sel;
   return cs;
 }
 

@@ -18,6 +18,10 @@ constexpr int kIndexRows = 128;  // chunk index granularity (one warp): fixed wh
 
 cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st);
 cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
+// sorted-run scan (runs_scan.cu): nl range leaves, nk run-length keys, na Sum(int64) aggregates
+constexpr int kRunsThreads = 128;
+cudaError_t launch_runs(const RunsDesc& d, int nl, int nk, int na, int sm_count, cudaStream_t st);
+cudaError_t runs_blocks_per_sm(const RunsDesc& d, int nl, int nk, int na, int* per_sm);  // resident CTAs per SM for this shape
 cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st);
 cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t st);

@@ -496,6 +496,19 @@ bool walk_hybrid(const uint8_t* data, uint32_t len, int w, uint32_t count, uint3
   const uint8_t* end = data + len;
   uint32_t produced = 0;
   const uint32_t vbytes = uint32_t((w + 7) / 8);
+  constexpr uint32_t kShortLiteral = 64;
+  // appends a run-length entry, merging with a preceding one of the same value (also the last run of
+  // the previous page of the chunk: `runs` is per column chunk and its runs are contiguous, the
+  // previous run ends where this one starts)
+  auto push_rle = [&](uint32_t start, uint32_t v) {
+    if (!runs->empty() && (runs->back().meta & 1u) == 0 && runs->back().val == v) return;
+    HostRun r;
+    r.start = start;
+    r.off = 0;
+    r.val = v;
+    r.meta = 0u | (uint32_t(w) << 8);
+    runs->push_back(r);
+  };
   while (produced < count) {
     // ULEB128 run header
     uint64_t h = 0;
@@ -521,7 +534,20 @@ bool walk_hybrid(const uint8_t* data, uint32_t len, int w, uint32_t count, uint3
         nbytes = avail;
       }
       uint32_t take = uint32_t(nvals < uint64_t(count - produced) ? nvals : uint64_t(count - produced));
-      if (take > 0) {
+      if (take > 0 && take <= kShortLiteral) {
+        // Writers close a repeated run on a multiple of 8 values and spill the boundary into one or two
+        // literal groups ("aaaaabbb").  Such short literal runs are unpacked here into run-length
+        // entries, so the directory of a sorted column holds no bit-packed run at all and the scan
+        // kernel's run cursor never has to unpack bits at a group boundary.
+        for (uint32_t i = 0; i < take; i++) {
+          uint64_t bit = uint64_t(i) * uint64_t(w);
+          uint64_t word = 0;
+          const uint8_t* q = p + (bit >> 3);
+          for (int b = 0; b < 8 && q + b < end; b++) word |= uint64_t(q[b]) << (8 * b);
+          uint32_t v = w == 0 ? 0u : uint32_t((word >> (bit & 7)) & ((w >= 32 ? 0xffffffffull : ((1ull << w) - 1))));
+          push_rle(start0 + produced + i, v);
+        }
+      } else if (take > 0) {
         HostRun r;
         r.start = start0 + produced;
         r.off = off0 + uint32_t(p - data);
@@ -538,20 +564,7 @@ bool walk_hybrid(const uint8_t* data, uint32_t len, int w, uint32_t count, uint3
       for (uint32_t i = 0; i < vbytes; i++) v |= uint32_t(p[i]) << (8 * i);
       p += vbytes;
       uint32_t take = uint32_t(n < uint64_t(count - produced) ? n : uint64_t(count - produced));
-      if (take > 0) {
-        HostRun r;
-        r.start = start0 + produced;
-        r.off = 0;
-        r.val = v;
-        r.meta = 0u | (uint32_t(w) << 8);
-        // merge with a preceding RLE run of the same value (keeps the directory minimal)
-        if (!runs->empty() && (runs->back().meta & 1u) == 0 && runs->back().val == v &&
-            runs->back().start >= start0 && ((runs->back().meta >> 8) & 0xff) == uint32_t(w)) {
-          // contiguous by construction: the previous run ends where this one starts
-        } else {
-          runs->push_back(r);
-        }
-      }
+      if (take > 0) push_rle(start0 + produced, v);
       produced += take;
       if (n == 0) { *err = "zero-length RLE run"; return false; }
     }

@@ -70,7 +70,7 @@ print("\n-- by function: inst%  samples%")
 for name, v in byfn_i.most_common(22):
     print(f"{v / ti * 100:5.1f} {byfn_s[name] / ts * 100:5.1f}  {name}")
 print("\n-- by line: inst%  samples%")
-for k, v in inst.most_common(40):
+for k, v in inst.most_common(int(os.environ.get("NCU_LINES_TOP", 40))):
     if not k:
         continue
     text = src[k[1] - 1].strip()[:100] if k[0] == "kernels.cu" else k[0]
