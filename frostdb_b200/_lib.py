@@ -77,7 +77,8 @@ class Stats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("metadata_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("row_groups", C.c_uint32),
                 ("scan_kernel_ms", C.c_float), ("total_device_ms", C.c_float), ("h2d_ms", C.c_float),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("row_groups_pruned", C.c_uint32), ("row_groups_runs", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

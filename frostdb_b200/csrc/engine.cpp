@@ -235,6 +235,8 @@ void free_part(fgpu_ctx* ctx, Part* p) {
 struct VisibleRG {
   Part* part;
   RowGroupHost* rg;
+  uint64_t skip_slots = 0;               // bit s: slot s is not read in this row group (its leaf is decided by statistics)
+  uint8_t leaf_mode[kMaxLeaves] = {0};   // LeafMode per leaf decided from the chunk statistics (LM_EVAL: undecided)
 };
 
 int bit_width_u32(uint64_t max_value) {
@@ -308,6 +310,7 @@ struct Compiled {
   std::vector<VisibleRG> rgs;
   std::vector<std::string> slot_names;
   std::vector<uint8_t> slot_types;
+  std::vector<uint8_t> slot_needed;  // 0: only named by Count(), whose result does not depend on the values
   std::vector<LeafHost> leaves;
   std::vector<uint8_t> filter_prog;
   std::vector<KeyOut> keys;
@@ -317,6 +320,7 @@ struct Compiled {
   uint64_t total_rows = 0;
   uint64_t group_bound = 0;
   uint64_t h2d_bytes = 0;  // column uploads this query triggered
+  uint32_t pruned_row_groups = 0;
 };
 
 int32_t compile_filter(const fgpu_query& q, int node, Compiled* c, std::map<std::string, int>& slot_of) {
@@ -482,51 +486,17 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   for (int s = 0; s < qd.n_slots; s++) {
     qd.slot_type[s] = c->slot_types[size_t(s)];
   }
-  // Lazy residency: the columns this query projects are built and uploaded now (parts put with
-  // FGPU_PUT_BORROW_PINNED upload nothing until a query needs it; optimize.go:36-73 physical projection).
+  // Count(col) counts rows, NULLs included (aggregate.go:929-950): its input column is never read,
+  // so it is neither uploaded nor staged unless something else in the query needs it.
   {
-    Part* last = nullptr;
-    for (const VisibleRG& v : c->rgs) {
-      if (v.part == last) continue;
-      last = v.part;
-      for (const std::string& name : c->slot_names) {
-        if (std::find(v.part->columns.begin(), v.part->columns.end(), name) == v.part->columns.end()) continue;
-        int32_t rc = ensure_resident(ctx, &table, v.part, name, &c->h2d_bytes);
-        if (rc) return rc;
-        const ColumnImage& img = v.part->images[name];
-        if (!img.error.empty()) return fail(FGPU_ERR_UNSUPPORTED, "column " + name + ": " + img.error);
-      }
-    }
-  }
-  // shared-memory ring of the scan kernel: stage every numeric slot's PLAIN slice (up to kMaxStagePlain)
-  // and the chunk seeds of every hybrid stream (up to kMaxStageSeeds); the rest is read from HBM directly
-  for (int s = 0; s < kMaxSlots; s++) {
-    qd.slot_plain_stage[s] = -1;
-    qd.slot_seed_stage[s][0] = qd.slot_seed_stage[s][1] = -1;
-  }
-  for (int s = 0; s < qd.n_slots; s++) {
-    bool any_plain = false, any_vals = false, any_def = false;
-    for (const VisibleRG& v : c->rgs) {
-      auto it = v.rg->cols.find(c->slot_names[size_t(s)]);
-      if (it == v.rg->cols.end()) continue;
-      const ChunkDesc& d = it->second.desc;
-      if (d.kind == CK_PLAIN64 && !d.has_nulls) any_plain = true;
-      if (d.kind == CK_DICT_STR || d.kind == CK_DICT64) any_vals = true;
-      if (d.has_nulls) any_def = true;
-    }
-    if (any_plain && qd.n_stage_plain < kMaxStagePlain) {
-      qd.slot_plain_stage[s] = int8_t(qd.n_stage_plain);
-      qd.stage_plain_slot[qd.n_stage_plain++] = uint8_t(s);
-    }
-    if (any_vals && qd.n_stage_seeds < kMaxStageSeeds) {
-      qd.slot_seed_stage[s][0] = int8_t(qd.n_stage_seeds);
-      qd.stage_seed_slot[qd.n_stage_seeds] = uint8_t(s);
-      qd.stage_seed_is_def[qd.n_stage_seeds++] = 0;
-    }
-    if (any_def && qd.n_stage_seeds < kMaxStageSeeds) {
-      qd.slot_seed_stage[s][1] = int8_t(qd.n_stage_seeds);
-      qd.stage_seed_slot[qd.n_stage_seeds] = uint8_t(s);
-      qd.stage_seed_is_def[qd.n_stage_seeds++] = 1;
+    std::vector<std::string> need = key_names;
+    collect_columns(q, q.filter, &need);
+    for (const fgpu_agg& a : q.aggs)
+      if (a.func != FGPU_AGG_COUNT) collect_columns(q, a.expr, &need);
+    c->slot_needed.assign(c->slot_names.size(), q.kind == FGPU_PLAN_AGGREGATE ? 0 : 1);
+    for (auto& n : need) {
+      auto it = slot_of.find(n);
+      if (it != slot_of.end()) c->slot_needed[size_t(it->second)] = 1;
     }
   }
   // filter
@@ -656,6 +626,121 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     ld.neg = lh.neg;
     ld.lo_i = lh.lo_i; ld.hi_i = lh.hi_i;
     ld.lo_f = lh.lo_f; ld.hi_f = lh.hi_f;
+  }
+  // ---- row-group pruning by chunk statistics ----------------------------------------------------------
+  // LSM.Scan asks the filter's TrueNegativeFilter whether a row group may hold matching rows before it
+  // hands the row group to the plan (index/lsm.go:401-454; expr/binaryscalarexpr.go:41-190 compares the
+  // literal with the chunk's min/max).  Same decision here, from the footer statistics, before anything
+  // is uploaded: an int64 range leaf whose chunk bounds miss the range selects nothing in that row group
+  // (under a conjunction the row group is dropped: never uploaded, never scanned); bounds inside the
+  // range of a chunk without NULLs select every row, and the leaf's column is then not read there.
+  {
+    const bool conj = qd.n_filter_prog > 0 && qd.filter_kind == FK_AND;
+    const bool may_skip = q.kind != FGPU_PLAN_FILTER;
+    std::vector<uint8_t> base(c->slot_names.size(), may_skip ? 0 : 1);  // needed regardless of the filter
+    if (may_skip) {
+      std::vector<std::string> need = key_names;
+      for (const fgpu_agg& a : q.aggs)
+        if (a.func != FGPU_AGG_COUNT) collect_columns(q, a.expr, &need);
+      for (auto& n : need) {
+        auto it = slot_of.find(n);
+        if (it != slot_of.end()) base[size_t(it->second)] = 1;
+      }
+    }
+    std::vector<VisibleRG> kept;
+    const bool prune_on = !getenv("FROSTGPU_NO_PRUNE");
+    for (VisibleRG& v : c->rgs) {
+      bool drop = false;
+      for (size_t l = 0; l < c->leaves.size() && prune_on; l++) {
+        const LeafHost& lh = c->leaves[l];
+        uint8_t mode = LM_EVAL;
+        auto it = lh.slot < 0 ? v.rg->cols.end() : v.rg->cols.find(lh.column);
+        if (it == v.rg->cols.end()) {
+          mode = lh.missing_mode;  // the missing-column rules are the row-group filter's own (:47-73)
+        } else if (lh.numeric && !lh.cmp_float && !lh.null_literal && c->slot_types[size_t(lh.slot)] == ST_I64 && it->second.has_minmax) {
+          const int64_t mn = it->second.min_bits, mx = it->second.max_bits;
+          const bool disjoint = mx < lh.lo_i || mn > lh.hi_i;
+          const bool inside = mn >= lh.lo_i && mx <= lh.hi_i;
+          const bool no_nulls = it->second.null_count == 0;
+          if (!lh.neg) mode = disjoint ? LM_NONE : ((inside && no_nulls) ? LM_ALL : LM_EVAL);
+          else mode = inside ? LM_NONE : ((disjoint && no_nulls) ? LM_ALL : LM_EVAL);
+        }
+        v.leaf_mode[l] = mode;
+        if (conj && mode == LM_NONE) drop = true;
+      }
+      if (drop) continue;
+      for (size_t s = 0; s < c->slot_names.size(); s++) {
+        bool needed = base[s] != 0;
+        for (size_t l = 0; l < c->leaves.size() && !needed; l++)
+          if (c->leaves[l].slot == int(s) && v.leaf_mode[l] == LM_EVAL) needed = true;
+        if (!needed || !c->slot_needed[s]) v.skip_slots |= 1ull << s;
+      }
+      kept.push_back(v);
+    }
+    c->pruned_row_groups = uint32_t(c->rgs.size() - kept.size());
+    c->rgs.swap(kept);
+    if (c->rgs.empty()) {  // every row group was ruled out: same as scanning an empty table
+      c->qd = QueryDesc{};
+      c->qd.table_mode = TM_DENSE;
+      c->qd.key_words = 1;
+      c->qd.table_slots = 1;
+      c->qd.tile_rows = ctx->tile_rows;
+      c->keys.clear();
+      return FGPU_OK;
+    }
+  }
+  // Lazy residency: the columns this query projects are built and uploaded now (parts put with
+  // FGPU_PUT_BORROW_PINNED upload nothing until a query needs it; optimize.go:36-73 physical projection).
+  {
+    Part* last = nullptr;
+    for (const VisibleRG& v : c->rgs) {
+      if (v.part == last) continue;
+      last = v.part;
+      for (size_t si = 0; si < c->slot_names.size(); si++) {
+        const std::string& name = c->slot_names[si];
+        bool read = false;
+        for (const VisibleRG& w : c->rgs)
+          if (w.part == v.part && !((w.skip_slots >> si) & 1)) { read = true; break; }
+        if (!read) continue;
+        if (std::find(v.part->columns.begin(), v.part->columns.end(), name) == v.part->columns.end()) continue;
+        int32_t rc = ensure_resident(ctx, &table, v.part, name, &c->h2d_bytes);
+        if (rc) return rc;
+        const ColumnImage& img = v.part->images[name];
+        if (!img.error.empty()) return fail(FGPU_ERR_UNSUPPORTED, "column " + name + ": " + img.error);
+      }
+    }
+  }
+  // shared-memory ring of the scan kernel: stage every numeric slot's PLAIN slice (up to kMaxStagePlain)
+  // and the chunk seeds of every hybrid stream (up to kMaxStageSeeds); the rest is read from HBM directly
+  for (int s = 0; s < kMaxSlots; s++) {
+    qd.slot_plain_stage[s] = -1;
+    qd.slot_seed_stage[s][0] = qd.slot_seed_stage[s][1] = -1;
+  }
+  for (int s = 0; s < qd.n_slots; s++) {
+    bool any_plain = false, any_vals = false, any_def = false;
+    if (!c->slot_needed[size_t(s)]) continue;
+    for (const VisibleRG& v : c->rgs) {
+      auto it = v.rg->cols.find(c->slot_names[size_t(s)]);
+      if (it == v.rg->cols.end() || ((v.skip_slots >> s) & 1)) continue;
+      const ChunkDesc& d = it->second.desc;
+      if (d.kind == CK_PLAIN64 && !d.has_nulls) any_plain = true;
+      if (d.kind == CK_DICT_STR || d.kind == CK_DICT64) any_vals = true;
+      if (d.has_nulls) any_def = true;
+    }
+    if (any_plain && qd.n_stage_plain < kMaxStagePlain) {
+      qd.slot_plain_stage[s] = int8_t(qd.n_stage_plain);
+      qd.stage_plain_slot[qd.n_stage_plain++] = uint8_t(s);
+    }
+    if (any_vals && qd.n_stage_seeds < kMaxStageSeeds) {
+      qd.slot_seed_stage[s][0] = int8_t(qd.n_stage_seeds);
+      qd.stage_seed_slot[qd.n_stage_seeds] = uint8_t(s);
+      qd.stage_seed_is_def[qd.n_stage_seeds++] = 0;
+    }
+    if (any_def && qd.n_stage_seeds < kMaxStageSeeds) {
+      qd.slot_seed_stage[s][1] = int8_t(qd.n_stage_seeds);
+      qd.stage_seed_slot[qd.n_stage_seeds] = uint8_t(s);
+      qd.stage_seed_is_def[qd.n_stage_seeds++] = 1;
+    }
   }
   // aggregates
   if (q.aggs.size() > size_t(kMaxAggs)) return fail(FGPU_ERR_UNSUPPORTED, "too many aggregates");
@@ -876,6 +961,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   fgpu_stats& st = res->stats;
   st.rows_scanned = c.total_rows;
   st.row_groups = uint32_t(n_rg);
+  st.row_groups_pruned = c.pruned_row_groups;
 
   // ---- per row group tables: chunk descriptors, leaf runtime, leaf LUTs, tile prefix -----------
   std::vector<ChunkDesc> chunks(size_t(n_rg) * std::max(n_slots, 1));
@@ -886,15 +972,24 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   uint32_t tiles = 0;
   const uint32_t tile_len = q.kind == FGPU_PLAN_FILTER ? uint32_t(kTileRows) : uint32_t(qd.vl);  // rows plan: CTA tiles; scan: warp vectors
   // ---- sorted-run scan: query-level eligibility (see runs_scan.cu) --------------------------------
-  RunsDesc rd{};
-  std::vector<RunsRg> runs_rgs;
+  // Two batches of row groups, each its own launch: [0] evaluates the range leaves, [1] holds the row
+  // groups whose statistics already decided every leaf (all rows pass: the leaf columns are not read).
+  struct RunsBatch {
+    RunsDesc rd{};
+    int nl = 0;
+    int col_slot[kRunsCols] = {0};
+    std::vector<RunsRg> rgs;
+    std::vector<uint32_t> rows, first_span;
+    size_t o_rg = 0, o_span = 0;
+  };
+  RunsBatch batches[2];
   int runs_nl = 0, runs_nk = 0, runs_na = 0;
   int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
   bool runs_q = q.kind != FGPU_PLAN_FILTER && qd.fast_ok && !getenv("FROSTGPU_NO_RUNS");
   if (runs_q) {
     for (int l = 0; l < n_leaves && runs_q; l++) {
       const LeafDesc& ld = qd.leaves[l];
-      if (ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || runs_nl >= kRunsLeaves) runs_q = false;
+      if (ld.slot == 0xff || ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || runs_nl >= kRunsLeaves) runs_q = false;
       else runs_leaf_slot[runs_nl++] = ld.slot;
     }
     for (int a = 0; a < qd.n_aggs && runs_q; a++) {
@@ -906,19 +1001,21 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     if (qd.n_keys > kRunsKeys) runs_q = false;
     runs_nk = qd.n_keys;
   }
-  int runs_col_slot[kRunsCols] = {0};
-  if (runs_q) {  // distinct staged columns
-    auto col_of = [&](int slot) {
-      for (uint32_t i = 0; i < rd.n_cols; i++)
-        if (runs_col_slot[i] == slot) return i;
-      runs_col_slot[rd.n_cols] = slot;
-      return rd.n_cols++;
-    };
-    for (int l = 0; l < runs_nl; l++) rd.leaf_col[l] = col_of(runs_leaf_slot[l]);
-    for (int a = 0; a < runs_na; a++) rd.agg_col[a] = col_of(runs_agg_slot[a]);
-    for (int k = 0; k < runs_nk; k++) rd.stride[k] = qd.keys[k].dense_stride;
+  if (runs_q) {  // distinct staged columns of each batch
+    for (int bi = 0; bi < 2; bi++) {
+      RunsBatch& B = batches[bi];
+      auto col_of = [&](int slot) {
+        for (uint32_t i = 0; i < B.rd.n_cols; i++)
+          if (B.col_slot[i] == slot) return i;
+        B.col_slot[B.rd.n_cols] = slot;
+        return B.rd.n_cols++;
+      };
+      B.nl = bi == 0 ? runs_nl : 0;
+      for (int l = 0; l < B.nl; l++) B.rd.leaf_col[l] = col_of(runs_leaf_slot[l]);
+      for (int a = 0; a < runs_na; a++) B.rd.agg_col[a] = col_of(runs_agg_slot[a]);
+      for (int k = 0; k < runs_nk; k++) B.rd.stride[k] = qd.keys[k].dense_stride;
+    }
   }
-  std::vector<uint32_t> runs_rows;
   int gi = 0;  // row groups that stay with the general scan kernel
   for (int g0 = 0; g0 < n_rg; g0++) {
     RowGroupHost& rg = *c.rgs[size_t(g0)].rg;
@@ -927,7 +1024,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       ChunkDesc d{};
       d.kind = CK_ABSENT;
       d.n_rows = rg.n_rows;
-      auto it = rg.cols.find(c.slot_names[size_t(s)]);
+      auto it = ((c.rgs[size_t(g0)].skip_slots >> s) & 1) ? rg.cols.end() : rg.cols.find(c.slot_names[size_t(s)]);
       if (it != rg.cols.end()) {
         ChunkHost& ch = it->second;
         if (!ch.error.empty())
@@ -958,22 +1055,43 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       } else {
         rt.mode = lh.null_literal ? LM_NONE : LM_EVAL;
       }
+      if (c.rgs[size_t(g0)].leaf_mode[l] != LM_EVAL) rt.mode = c.rgs[size_t(g0)].leaf_mode[l];
       lrt[size_t(g) * n_leaves + l] = rt;
     }
     // ---- does this row group qualify for the sorted-run kernel? ----
     bool runs_ok = runs_q && rg.n_rows > 0;
+    int bi = 0;
+    if (runs_ok) {
+      bool all_all = runs_nl > 0;
+      for (int l = 0; l < runs_nl; l++) {
+        const uint8_t m = lrt[size_t(g) * n_leaves + l].mode;
+        if (m != LM_ALL) all_all = false;
+        if (m == LM_NONE) runs_ok = false;  // (only with pruning switched off)
+      }
+      bi = all_all ? 1 : 0;
+    }
     RunsRg rr{};
     if (runs_ok) {
+      RunsBatch& B = batches[bi];
       rr.n_rows = rg.n_rows;
-      for (int l = 0; l < runs_nl && runs_ok; l++) {
-        if (lrt[size_t(g) * n_leaves + l].mode != LM_EVAL) runs_ok = false;
-        rr.lo[l] = qd.leaves[l].lo_i;
-        rr.hi[l] = qd.leaves[l].hi_i;
+      for (int l = 0; l < B.nl; l++) {
+        const bool all = lrt[size_t(g) * n_leaves + l].mode == LM_ALL;
+        rr.lo[l] = all ? std::numeric_limits<int64_t>::min() : qd.leaves[l].lo_i;
+        rr.hi[l] = all ? std::numeric_limits<int64_t>::max() : qd.leaves[l].hi_i;
       }
-      for (uint32_t i = 0; i < rd.n_cols && runs_ok; i++) {
-        const ChunkDesc& d = chunks[size_t(g) * n_slots + runs_col_slot[i]];
+      const uint8_t* any_col = nullptr;
+      for (uint32_t i = 0; i < B.rd.n_cols && runs_ok; i++) {
+        const ChunkDesc& d = chunks[size_t(g) * n_slots + B.col_slot[i]];
+        rr.col[i] = nullptr;
+        if ((c.rgs[size_t(g0)].skip_slots >> B.col_slot[i]) & 1) continue;  // decided leaf: any column stands in
         if (d.kind != CK_PLAIN64 || d.has_nulls) runs_ok = false;
         rr.col[i] = d.values;
+        any_col = d.values;
+      }
+      for (uint32_t i = 0; i < B.rd.n_cols && runs_ok; i++) {
+        if (rr.col[i]) continue;
+        if (!any_col) runs_ok = false;
+        rr.col[i] = any_col;
       }
       for (int k = 0; k < runs_nk && runs_ok; k++) {
         const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.keys[k].slot];
@@ -984,8 +1102,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       }
     }
     if (runs_ok) {
-      runs_rgs.push_back(rr);
-      runs_rows.push_back(rg.n_rows);
+      batches[bi].rgs.push_back(rr);
+      batches[bi].rows.push_back(rg.n_rows);
       lut_fix.erase(std::remove_if(lut_fix.begin(), lut_fix.end(), [&](const std::pair<size_t, size_t>& f) { return f.first >= size_t(g) * n_leaves; }), lut_fix.end());
       continue;  // slot g of the general tables is reused by the next row group
     }
@@ -998,33 +1116,34 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   qd.n_rg = gi;
   qd.n_tiles = tiles;
   // spans of the sorted-run kernel: sized so that every warp of the grid gets several
-  std::vector<uint32_t> runs_first_span;
-  if (!runs_rgs.empty()) {
+  for (RunsBatch& B : batches) {
+    if (B.rgs.empty()) continue;
+    RunsDesc& rd = B.rd;
     auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
     int br = envi("FROSTGPU_RUNS_BR", 256);
     if (br != 128 && br != 256 && br != 512) br = 256;
-    int ring = envi("FROSTGPU_RUNS_RING", 3);
+    int ring = envi("FROSTGPU_RUNS_RING", 2);
     ring = std::min(4, std::max(2, ring));
-    if (rd.n_cols == 0) { br = 128; ring = 2; }  // nothing is staged (count(*) per group): the ring is idle
+    if (rd.n_cols == 0) { br = 128; ring = 2; }  // nothing is staged (count per group): the ring is idle
     rd.block_rows = uint32_t(br);
     rd.n_ring = uint32_t(ring);
-    rd.n_rg = uint32_t(runs_rgs.size());
+    rd.n_rg = uint32_t(B.rgs.size());
     int per_sm = 1;
-    CUDA_TRY(runs_blocks_per_sm(rd, runs_nl, runs_nk, runs_na, &per_sm));
+    CUDA_TRY(runs_blocks_per_sm(rd, B.nl, runs_nk, runs_na, &per_sm));
     const uint64_t warps = uint64_t(ctx->sm_count) * uint64_t(std::max(per_sm, 1)) * (kRunsThreads / 32);
     uint64_t total = 0;
-    for (uint32_t r : runs_rows) total += r;
+    for (uint32_t r : B.rows) total += r;
     uint64_t span_blocks = total / (warps * 8 * uint64_t(br));
     span_blocks = std::min<uint64_t>(64, std::max<uint64_t>(4, span_blocks));
-    if (const char* e = getenv("FROSTGPU_RUNS_SPAN")) span_blocks = std::max(1, atoi(e));
+    if (const char* e = getenv("FROSTGPU_RUNS_SPAN")) span_blocks = uint64_t(std::max(1, atoi(e)));
     rd.span_blocks = uint32_t(span_blocks);
     const uint64_t span_rows = span_blocks * uint64_t(br);
     uint32_t spans = 0;
-    for (uint32_t r : runs_rows) {
-      runs_first_span.push_back(spans);
+    for (uint32_t r : B.rows) {
+      B.first_span.push_back(spans);
       spans += uint32_t((uint64_t(r) + span_rows - 1) / span_rows);
     }
-    runs_first_span.push_back(spans);
+    B.first_span.push_back(spans);
     rd.n_spans = spans;
   }
 
@@ -1066,9 +1185,12 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   size_t o_first = align16(o_lrt + lrt.size() * sizeof(LeafRt));
   size_t o_rows = align16(o_first + first_tile.size() * 4);
   size_t o_lut = align16(o_rows + rg_rows.size() * 4);
-  size_t o_rrg = align16(o_lut + lutbytes.size());
-  size_t o_rspan = align16(o_rrg + runs_rgs.size() * sizeof(RunsRg));
-  size_t o_cnt = align16(o_rspan + runs_first_span.size() * 4);
+  size_t o_cnt = align16(o_lut + lutbytes.size());
+  for (RunsBatch& B : batches) {
+    B.o_rg = o_cnt;
+    B.o_span = align16(B.o_rg + B.rgs.size() * sizeof(RunsRg));
+    o_cnt = align16(B.o_span + B.first_span.size() * 4);
+  }
   size_t aux_bytes = o_cnt + 64;
   CUDA_TRY(res->aux.alloc(aux_bytes, ctx->stream));
   uint8_t* aux = static_cast<uint8_t*>(res->aux.p);
@@ -1079,9 +1201,10 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   std::memcpy(hostaux.data() + o_first, first_tile.data(), first_tile.size() * 4);
   std::memcpy(hostaux.data() + o_rows, rg_rows.data(), rg_rows.size() * 4);
   if (!lutbytes.empty()) std::memcpy(hostaux.data() + o_lut, lutbytes.data(), lutbytes.size());
-  if (!runs_rgs.empty()) {
-    std::memcpy(hostaux.data() + o_rrg, runs_rgs.data(), runs_rgs.size() * sizeof(RunsRg));
-    std::memcpy(hostaux.data() + o_rspan, runs_first_span.data(), runs_first_span.size() * 4);
+  for (RunsBatch& B : batches) {
+    if (B.rgs.empty()) continue;
+    std::memcpy(hostaux.data() + B.o_rg, B.rgs.data(), B.rgs.size() * sizeof(RunsRg));
+    std::memcpy(hostaux.data() + B.o_span, B.first_span.data(), B.first_span.size() * 4);
   }
   qd.chunks = reinterpret_cast<const ChunkDesc*>(aux + o_chunks);
   qd.leaf_rt = reinterpret_cast<const LeafRt*>(aux + o_lrt);
@@ -1101,18 +1224,22 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   } else {
     CUDA_TRY(launch_table_init(qd, s));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
-    if (!runs_rgs.empty()) {
-      rd.rgs = reinterpret_cast<const RunsRg*>(aux + o_rrg);
-      rd.rg_first_span = reinterpret_cast<const uint32_t*>(aux + o_rspan);
+    for (RunsBatch& B : batches) {
+      if (B.rgs.empty()) continue;
+      RunsDesc& rd = B.rd;
+      rd.rgs = reinterpret_cast<const RunsRg*>(aux + B.o_rg);
+      rd.rg_first_span = reinterpret_cast<const uint32_t*>(aux + B.o_span);
       rd.t_rows = qd.t_rows;
       for (int a = 0; a < runs_na; a++) rd.t_agg[a] = qd.t_agg[runs_agg_index[a]];
       rd.counters = qd.counters;
-      CUDA_TRY(launch_runs(rd, runs_nl, runs_nk, runs_na, ctx->sm_count, s));
+      CUDA_TRY(launch_runs(rd, B.nl, runs_nk, runs_na, ctx->sm_count, s));
+      st.kernel_launches++;
+      st.row_groups_runs += uint32_t(B.rgs.size());
     }
     CUDA_TRY(launch_scan(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
   }
   CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
-  st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0) + (runs_rgs.empty() ? 0 : 1);
+  st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0);
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
   unsigned long long counters[8] = {0};
   CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));

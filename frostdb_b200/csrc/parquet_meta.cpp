@@ -151,18 +151,28 @@ struct RawColumnMeta {
   int32_t type = -1, codec = 0;
   int64_t num_values = 0, total_compressed = 0, data_page_offset = -1, dict_page_offset = -1;
   int64_t null_count = -1;
+  std::string stat_min, stat_max;  // raw PLAIN-encoded bounds, empty = not written
   std::vector<std::string> path;
 };
 
-int64_t read_statistics_null_count(TReader& r) {
+void read_statistics(TReader& r, RawColumnMeta* m) {
   // Statistics {1: max, 2: min, 3: i64 null_count, 4: distinct_count, 5: max_value, 6: min_value, ...}
-  int64_t nc = -1;
+  // The deprecated pair (1, 2) is ordered by signed comparison, which is the right order for the
+  // INT64 / DOUBLE columns the bounds are used on; the new pair wins when both are present.
+  std::string old_min, old_max;
   int16_t last = 0, id; int t;
   while (r.field(&last, &id, &t)) {
-    if (id == 3) nc = r.zigzag();
+    if (id == 3) m->null_count = r.zigzag();
+    else if (id == 1 && t == 8) old_max = r.binary();
+    else if (id == 2 && t == 8) old_min = r.binary();
+    else if (id == 5 && t == 8) m->stat_max = r.binary();
+    else if (id == 6 && t == 8) m->stat_min = r.binary();
     else r.skip(t);
   }
-  return nc;
+  if (m->stat_min.empty() || m->stat_max.empty()) {
+    m->stat_min = old_min;
+    m->stat_max = old_max;
+  }
 }
 
 RawColumnMeta read_column_meta(TReader& r) {
@@ -182,7 +192,7 @@ RawColumnMeta read_column_meta(TReader& r) {
       case 7: m.total_compressed = r.zigzag(); break;
       case 9: m.data_page_offset = r.zigzag(); break;
       case 11: m.dict_page_offset = r.zigzag(); break;
-      case 12: m.null_count = read_statistics_null_count(r); break;
+      case 12: read_statistics(r, &m); break;
       default: r.skip(t);
     }
   }
@@ -265,6 +275,11 @@ void walk_chunk(const uint8_t* file, uint64_t len, const RawColumnMeta& cm, cons
   out->num_values = cm.num_values;
   out->total_compressed_size = cm.total_compressed;
   out->null_count = cm.null_count;
+  if ((leaf.phys == PT_INT64 || leaf.phys == PT_DOUBLE) && cm.stat_min.size() == 8 && cm.stat_max.size() == 8) {
+    out->has_minmax = true;
+    std::memcpy(&out->min_bits, cm.stat_min.data(), 8);
+    std::memcpy(&out->max_bits, cm.stat_max.data(), 8);
+  }
   if (cm.codec != 0) {
     out->error = "compressed column chunk (codec " + std::to_string(cm.codec) + ") is not supported";
     return;

@@ -46,6 +46,8 @@ struct ChunkMeta {
   int64_t num_values = 0;
   int64_t total_compressed_size = 0;  // footer figure: the algorithmic bytes of this chunk
   int64_t null_count = -1;            // from chunk statistics when present
+  bool has_minmax = false;            // INT64 / DOUBLE chunks: footer statistics carry both bounds
+  int64_t min_bits = 0, max_bits = 0; // raw 8-byte bounds of the non-null values
   const uint8_t* dict = nullptr;      // dictionary page payload (PLAIN)
   uint32_t dict_len = 0;
   uint32_t dict_num_values = 0;

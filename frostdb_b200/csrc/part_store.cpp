@@ -329,6 +329,11 @@ bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) 
       ChunkHost ch;  // skeleton: type and footer size are known before the column is built
       ch.phys = part->pf.leaves[c].phys;
       ch.stored_bytes = uint64_t(rg.chunks[c].total_compressed_size);
+      ch.has_minmax = rg.chunks[c].has_minmax;
+      ch.min_bits = rg.chunks[c].min_bits;
+      ch.max_bits = rg.chunks[c].max_bits;
+      ch.null_count = rg.chunks[c].null_count;
+      if (ch.null_count < 0 && part->pf.leaves[c].max_def == 0) ch.null_count = 0;  // required column
       ch.desc.n_rows = h.n_rows;
       h.cols.emplace(part->pf.leaves[c].name, std::move(ch));
     }

@@ -38,6 +38,9 @@ struct ChunkHost {
   uint64_t stored_bytes = 0;   // footer total_compressed_size (algorithmic bytes)
   uint64_t meta_bytes = 0;     // directories / indexes / LUTs
   std::string error;           // non-empty: unreadable; an error only if a query projects it
+  bool has_minmax = false;     // footer statistics of an INT64 / DOUBLE chunk (known before the column is built)
+  int64_t min_bits = 0, max_bits = 0;
+  int64_t null_count = -1;     // -1: not recorded
   std::vector<uint32_t> lut_host;  // CK_DICT_STR: chunk dictionary index -> *local* global id
   // section offsets inside the part image (patched into desc after upload)
   int64_t off_values = -1, off_runs = -1, off_seeds = -1, off_def = -1, off_def_runs = -1, off_def_seeds = -1, off_lut = -1,

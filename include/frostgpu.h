@@ -167,6 +167,8 @@ typedef struct fgpu_stats {
   float h2d_ms;               /* uploads performed inside this Execute (streamed parts)           */
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;
+  uint32_t row_groups_pruned; /* ruled out by chunk statistics before upload (index/lsm.go:437)      */
+  uint32_t row_groups_runs;   /* scanned by the sorted-run kernel (the rest: general scan kernel)   */
 } fgpu_stats;
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */

@@ -1,0 +1,168 @@
+"""Sorted-run kernel (k_runs) and statistics pruning against the oracle, and against the general scan
+kernel with both switched off (FROSTGPU_NO_RUNS / FROSTGPU_NO_PRUNE): the three ways to run a query must
+give identical records."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from frostdb_b200 import _lib
+from frostdb_b200 import dynparquet as dp
+from frostdb_b200 import logicalplan as lp
+from frostdb_b200.physicalplan import GPUScan
+from tests.test_gpu_parity import Pair, assert_same
+from tests.util import label_values, rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+def sorted_columns(n, seed, *, t0=0, cards=(5, 23), run_scale=1.0, third=None):
+    """Non-null label columns a, b (and optionally c) whose sort leaves runs of very different lengths."""
+    rng = np.random.default_rng(seed)
+    cols = {
+        "example_type": (np.zeros(n, np.int32), ["cpu"]),
+        "stacktrace": (rng.integers(0, 11, n).astype(np.int32), [f"stack{i:02d}" for i in range(11)]),
+        "timestamp": t0 + np.arange(n, dtype=np.int64),
+        "value": rng.integers(-500, 1000, n).astype(np.int64),
+    }
+    # skewed group sizes: some (a, b) groups hold a handful of rows, others thousands
+    w = rng.random(cards[0] * cards[1]) ** (4.0 * run_scale)
+    g = rng.choice(cards[0] * cards[1], size=n, p=w / w.sum())
+    cols["labels.a"] = ((g // cards[1]).astype(np.int32), label_values(cards[0]))
+    cols["labels.b"] = ((g % cards[1]).astype(np.int32), label_values(cards[1]))
+    if third:
+        cols["labels.c"] = (rng.integers(0, third, n).astype(np.int32), label_values(third))
+    return cols
+
+
+@pytest.fixture()
+def pair(store):
+    made = []
+
+    def make(name, schema=None):
+        p = Pair(store, name, schema or dp.SampleDefinition())
+        made.append(p)
+        return p
+    yield make
+    for p in made:
+        p.close()
+    for k in ("FROSTGPU_NO_RUNS", "FROSTGPU_NO_PRUNE"):
+        os.environ.pop(k, None)
+
+
+def run3(p, build, float_cols=()):
+    """default path, no sorted-run kernel, no pruning: all equal to the oracle"""
+    got, exp = p.run(build)
+    assert_same(got, exp, float_cols)
+    for env in ({"FROSTGPU_NO_RUNS": "1"}, {"FROSTGPU_NO_PRUNE": "1"}, {"FROSTGPU_NO_RUNS": "1", "FROSTGPU_NO_PRUNE": "1"}):
+        os.environ.update(env)
+        try:
+            got2, _ = p.run(build)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+        assert_same(got2, exp, float_cols)
+    return got
+
+
+def scan_stats(p, filt, aggs, groups):
+    eng = p.store.engine
+    scan = GPUScan(eng, p.name, filt, _lib.PLAN_AGGREGATE, groups, aggs)
+    q, keep = scan.prepare()
+    lib = _lib.load()
+    res = C.c_void_p()
+    _lib.check(lib.fgpu_query_execute(eng.handle, q, eng.table_watermark(p.name), C.byref(res)))
+    st = eng.stats(res)
+    lib.fgpu_result_free(res)
+    lib.fgpu_query_free(q)
+    return st
+
+
+AGGS = [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value"))]
+KEYS = [lp.Col("labels.a"), lp.Col("labels.b")]
+
+
+@pytest.mark.parametrize("rows,rg", [(100_000, 32_768), (33_333, 10_007), (4_099, 4_099)])
+def test_sorted_parts_group_by_two_keys(pair, rows, rg):
+    p = pair("runs2")
+    for i in range(3):
+        p.insert(sorted_columns(rows, 100 + i, t0=i * rows), row_group_size=rg, data_page_size=16_384)
+    run3(p, lambda q: q.Aggregate(AGGS, KEYS))
+    st = scan_stats(p, None, AGGS, KEYS)
+    assert st["row_groups_runs"] == st["row_groups"] > 0  # every row group of a sorted part takes the run kernel
+    run3(p, lambda q: q.Aggregate([lp.Count(lp.Col("value"))], KEYS))
+    run3(p, lambda q: q.Aggregate([lp.Sum(lp.Col("value")), lp.Sum(lp.Col("timestamp"))], [lp.Col("labels.a")]))
+    run3(p, lambda q: q.Aggregate(AGGS, []))
+
+
+def test_time_range_filters_prune_and_split(pair):
+    p = pair("runs_prune")
+    n = 50_000
+    for i in range(6):
+        p.insert(sorted_columns(n, 200 + i, t0=i * n), row_group_size=20_000)
+    ts = lp.Col("timestamp")
+    cases = [
+        lp.And(ts.GtEq(lp.Literal(n + 17)), ts.Lt(lp.Literal(4 * n + 5))),   # parts 0 and 5 out, 2 and 3 fully inside
+        lp.And(ts.GtEq(lp.Literal(2 * n)), ts.Lt(lp.Literal(4 * n))),        # exact part boundaries
+        ts.Lt(lp.Literal(10)),                                               # ten rows of the first part
+        ts.Gt(lp.Literal(10 * n)),                                           # nothing
+        ts.GtEq(lp.Literal(0)),                                              # everything, decided by statistics alone
+        lp.And(ts.GtEq(lp.Literal(n // 2)), lp.Col("value").Gt(lp.Literal(250))),  # two leaves, two columns
+        lp.And(ts.LtEq(lp.Literal(5 * n)), lp.Col("value").GtEq(lp.Literal(-500))),  # second leaf always true
+        lp.And(lp.Col("value").Gt(lp.Literal(100)), lp.Col("value").LtEq(lp.Literal(700))),  # filter column == aggregate input
+        ts.NotEq(lp.Literal(3 * n)),                                         # negated range: general kernel, statistics still apply
+        lp.Or(ts.Lt(lp.Literal(n)), ts.GtEq(lp.Literal(5 * n))),             # disjunction: no row group is dropped
+    ]
+    for f in cases:
+        try:
+            run3(p, lambda q: q.Filter(f).Aggregate(AGGS, KEYS))
+            run3(p, lambda q: q.Filter(f).Aggregate([lp.Count(lp.Col("value"))], [lp.Col("labels.a")]))
+        except AssertionError as e:
+            raise AssertionError(f"filter {f.Name()}: {e}") from e
+    st = scan_stats(p, cases[0], AGGS, KEYS)
+    assert st["row_groups_pruned"] > 0 and st["row_groups_runs"] > 0
+    assert st["row_groups_pruned"] + st["row_groups"] == 6 * 3
+    st = scan_stats(p, cases[3], AGGS, KEYS)
+    assert st["row_groups"] == 0 and st["rows_selected"] == 0
+    # rows plans keep their order when row groups are dropped
+    got, exp = p.run(lambda q: q.Filter(cases[0]).Project(lp.Col("timestamp"), lp.Col("value"), lp.Col("labels.b")))
+    assert rows_of(got) == rows_of(exp)
+
+
+def test_short_runs_and_three_keys(pair):
+    p = pair("runs_short")
+    # third sort key with a few values: runs of labels.c are often shorter than a warp
+    p.insert(sorted_columns(60_000, 301, cards=(3, 7), third=4), row_group_size=25_000)
+    p.insert(sorted_columns(60_000, 302, cards=(3, 7), third=40, run_scale=0.2, t0=60_000), row_group_size=25_000)
+    keys3 = KEYS + [lp.Col("labels.c")]
+    run3(p, lambda q: q.Aggregate(AGGS, keys3))
+    f = lp.And(lp.Col("timestamp").GtEq(lp.Literal(1000)), lp.Col("timestamp").Lt(lp.Literal(100_000)))
+    run3(p, lambda q: q.Filter(f).Aggregate(AGGS, keys3))
+    run3(p, lambda q: q.Filter(f).Aggregate(AGGS, [lp.Col("labels.c")]))  # not a sort prefix: long bit-packed runs
+
+
+def test_unsorted_and_nullable_parts_fall_back(pair):
+    p = pair("runs_mixed")
+    p.insert(sorted_columns(40_000, 401), row_group_size=16_000)
+    cols = sorted_columns(40_000, 402, t0=40_000)
+    p.insert(cols, sort=False, row_group_size=16_000)                # arrival order: bit-packed key columns
+    cols = sorted_columns(40_000, 403, t0=80_000)
+    idx = cols["labels.b"][0].copy()
+    idx[::7] = -1                                                    # NULL keys
+    cols["labels.b"] = (idx, cols["labels.b"][1])
+    p.insert(cols, row_group_size=16_000)
+    f = lp.Col("timestamp").GtEq(lp.Literal(20_000))
+    run3(p, lambda q: q.Filter(f).Aggregate(AGGS, KEYS))
+    st = scan_stats(p, f, AGGS, KEYS)
+    assert 0 < st["row_groups_runs"] < st["row_groups"]
+
+
+def test_without_statistics_nothing_is_pruned(pair):
+    p = pair("runs_nostats")
+    for i in range(2):
+        p.insert(sorted_columns(30_000, 500 + i, t0=i * 30_000), row_group_size=10_000, write_statistics=False)
+    f = lp.Col("timestamp").Lt(lp.Literal(15_000))
+    run3(p, lambda q: q.Filter(f).Aggregate(AGGS, KEYS))
+    st = scan_stats(p, f, AGGS, KEYS)
+    assert st["row_groups_pruned"] == 0
