@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -127,6 +128,25 @@ struct fgpu_ctx {
   std::mutex mu;
   std::map<std::string, Table> tables;
   std::vector<ColumnImage*> pending_uploads;  // staging to release after the next stream sync
+};
+
+// FROSTGPU_PROFILE=1: host-side phase times of every Execute on stderr (development aid).
+struct PhaseClock {
+  bool on = getenv("FROSTGPU_PROFILE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  std::string line;
+  void mark(const char* what) {
+    if (!on) return;
+    auto t = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s=%.0fus", what, std::chrono::duration<double, std::micro>(t - t0).count());
+    line += buf;
+    t0 = t;
+  }
+  void flush(const char* tag) {
+    if (on && !line.empty()) fprintf(stderr, "[frostgpu %s]%s\n", tag, line.c_str());
+    line.clear();
+  }
 };
 
 struct fgpu_query {
@@ -953,9 +973,11 @@ void bind_table(QueryDesc* qd, uint8_t* base) {
 
 // Runs init + scan.  On success the result owns the device table.
 int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* res) {
+  PhaseClock pc;
   Compiled c;
   int32_t rc = compile(ctx, q, tx, &c);
   if (rc) return rc;
+  pc.mark("compile");
   QueryDesc& qd = c.qd;
   const int n_rg = qd.n_rg, n_slots = qd.n_slots, n_leaves = qd.n_leaves;
   fgpu_stats& st = res->stats;
@@ -1214,6 +1236,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   CUDA_TRY(res->qdesc_dev.alloc(sizeof(QueryDesc), ctx->stream));
 
   cudaStream_t s = ctx->stream;
+  pc.mark("describe");
   CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
   CUDA_TRY(cudaMemcpyAsync(aux, hostaux.data(), aux_bytes, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(res->qdesc_dev.p, &qd, sizeof(QueryDesc), cudaMemcpyHostToDevice, s));
@@ -1243,7 +1266,9 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
   unsigned long long counters[8] = {0};
   CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));
+  pc.mark("launch");
   CUDA_TRY(cudaStreamSynchronize(s));  // hostaux / counters stay valid until here
+  pc.mark("sync");
   release_staging(ctx);
   st.h2d_bytes += c.h2d_bytes;
   float ms = 0;
@@ -1285,6 +1310,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   for (int a = 0; a < kMaxAggs; a++) fd.t_agg[a] = qd.t_agg[a];
   fd.t_tag = qd.t_tag;
   fd.t_keys = qd.t_keys;
+  pc.mark("keep");
+  pc.flush("scan");
   return FGPU_OK;
 }
 
@@ -1369,6 +1396,7 @@ int32_t finalize_rows(fgpu_ctx* ctx, fgpu_result* res) {
 
 int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   if (res->rows_plan) return finalize_rows(ctx, res);
+  PhaseClock pc;
   FinalizeDesc& fd = res->fd;
   cudaStream_t s = ctx->stream;
   // Upper bound of result rows: every slot could be occupied; count first to size the output.
@@ -1411,6 +1439,7 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
   res->stats.total_device_ms = ms;
+  pc.mark("finalize_device");
 
   // ---- build Arrow columns (aggregate.go:551-625: group columns first, then aggregates) --------
   std::vector<OwnedColumn> cols;
@@ -1477,6 +1506,8 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   res->table.reset();
   res->aux.reset();
   res->qdesc_dev.reset();
+  pc.mark("arrow");
+  pc.flush("finalize");
   return FGPU_OK;
 }
 

@@ -89,6 +89,10 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
                  ImageWriter& w, ChunkHost* out) {
   out->phys = leaf.phys;
   out->stored_bytes = uint64_t(cm.total_compressed_size);
+  out->has_minmax = cm.has_minmax;
+  out->min_bits = cm.min_bits;
+  out->max_bits = cm.max_bits;
+  out->null_count = (cm.null_count < 0 && leaf.max_def == 0) ? 0 : cm.null_count;
   out->desc.n_rows = n_rows;
   if (!cm.error.empty()) { out->error = cm.error; return; }
   if (leaf.phys != PT_INT64 && leaf.phys != PT_DOUBLE && leaf.phys != PT_BYTE_ARRAY) {
@@ -446,7 +450,8 @@ std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows,
       const ChunkDesc& d = c.desc;
       o << "\"kind\":" << int(d.kind) << ",\"has_nulls\":" << int(d.has_nulls) << ",\"n_values\":" << d.n_values
         << ",\"n_runs\":" << d.n_runs << ",\"n_defruns\":" << d.n_defruns << ",\"dict_size\":" << d.dict_size
-        << ",\"stored_bytes\":" << c.stored_bytes << ",\"meta_bytes\":" << c.meta_bytes;
+        << ",\"stored_bytes\":" << c.stored_bytes << ",\"meta_bytes\":" << c.meta_bytes << ",\"null_count\":" << c.null_count;
+      if (c.has_minmax && c.phys == PT_INT64) o << ",\"min\":" << c.min_bits << ",\"max\":" << c.max_bits;
       // Decode through the same directories / tile indexes the kernel uses (small inputs only).
       if (rg.n_rows <= 65536) {
         std::vector<HostRun> vruns, druns;

@@ -140,6 +140,10 @@ typedef struct {
 typedef struct {
   int phys, codec;
   int64_t num_values, total_compressed, data_off, dict_off;
+  /* chunk statistics (the bounds and null count the reference reads through the ColumnIndex) */
+  int64_t null_count;                  /* -1: not recorded */
+  const uint8_t *smin, *smax;          /* PLAIN-encoded bounds inside the footer, NULL: not recorded */
+  uint32_t smin_len, smax_len;
 } o_chunk;
 
 typedef struct { int64_t num_rows; o_chunk* chunks; } o_rg;
@@ -189,7 +193,7 @@ static int parse_footer(o_part* part, char* err) {
             int et2; uint32_t nc; t_list(&r, &et2, &nc);
             rg->chunks = xcalloc(nc, sizeof(o_chunk));
             for (uint32_t c = 0; c < nc; c++) {
-              o_chunk* ch = &rg->chunks[c]; ch->data_off = -1; ch->dict_off = -1;
+              o_chunk* ch = &rg->chunks[c]; ch->data_off = -1; ch->dict_off = -1; ch->null_count = -1;
               int l3 = 0, id3, t3;
               while (t_field(&r, &l3, &id3, &t3)) {
                 if (id3 == 3) {
@@ -201,6 +205,21 @@ static int parse_footer(o_part* part, char* err) {
                     else if (id4 == 7) ch->total_compressed = t_zz(&r);
                     else if (id4 == 9) ch->data_off = t_zz(&r);
                     else if (id4 == 11) ch->dict_off = t_zz(&r);
+                    else if (id4 == 12) { /* Statistics: 5/6 max_value/min_value, 1/2 the deprecated pair, 3 null_count */
+                      const uint8_t *omin = NULL, *omax = NULL; uint32_t ominl = 0, omaxl = 0;
+                      int l5 = 0, id5, t5;
+                      while (t_field(&r, &l5, &id5, &t5)) {
+                        if (id5 == 3) ch->null_count = t_zz(&r);
+                        else if ((id5 == 1 || id5 == 2 || id5 == 5 || id5 == 6) && t5 == 8) {
+                          uint64_t bl = t_uvar(&r); const uint8_t* bp = r.p; t_skipn(&r, bl);
+                          if (id5 == 5) { ch->smax = bp; ch->smax_len = (uint32_t)bl; }
+                          else if (id5 == 6) { ch->smin = bp; ch->smin_len = (uint32_t)bl; }
+                          else if (id5 == 1) { omax = bp; omaxl = (uint32_t)bl; }
+                          else { omin = bp; ominl = (uint32_t)bl; }
+                        } else t_skip(&r, t5, 0);
+                      }
+                      if (!ch->smin || !ch->smax) { ch->smin = omin; ch->smin_len = ominl; ch->smax = omax; ch->smax_len = omaxl; }
+                    }
                     else t_skip(&r, t4, 0);
                   }
                 } else t_skip(&r, t3, 0);
@@ -819,6 +838,67 @@ static void collect_proj(const fgpu_plan* plan, int node, qctx* q) {
 
 static void record_free(record* rec) { for (int i = 0; i < rec->n_cols; i++) if (rec->cols[i].present) col_free(&rec->cols[i].col); free(rec->cols); rec->cols = NULL; }
 
+/* ---- row-group filter: LSM.Scan asks the plan's TrueNegativeFilter before a row group reaches the plan
+   (index/lsm.go:401-454).  BooleanExpr (expr/filter.go:251-268) turns And/Or into AndExpr/OrExpr
+   (:208-250), comparisons into BinaryScalarExpr, everything else into AlwaysTrueFilter (:129-131);
+   BinaryScalarExpr.Eval / BinaryScalarOperation (expr/binaryscalarexpr.go:41-190) answer "may this
+   column chunk hold a matching value" from the null count and the min/max of the chunk.  The
+   reference reads them through the ColumnIndex of parquet-go files; here they come from the chunk
+   statistics of the footer (the min/max over the pages).  Without recorded bounds the answer is
+   "maybe", as for a NULL bound (:141-146). ---- */
+static int stat_cmp(int phys, const uint8_t* a, uint32_t al, const fgpu_scalar* lit, int* ok) {
+  /* compare(v1, v2) switches on the chunk value's kind (:296-311); only like-typed literals are decided here */
+  *ok = 0;
+  if (phys == PQ_INT64 && lit->type == FGPU_SCALAR_INT64 && al == 8) { int64_t v; memcpy(&v, a, 8); *ok = 1; return v < lit->i64 ? -1 : (v > lit->i64 ? 1 : 0); }
+  if (phys == PQ_DOUBLE && lit->type == FGPU_SCALAR_FLOAT64 && al == 8) { double v; memcpy(&v, a, 8); *ok = 1; return v < lit->f64 ? -1 : (v > lit->f64 ? 1 : 0); }
+  if (phys == PQ_BYTE_ARRAY && lit->type == FGPU_SCALAR_STRING) {
+    uint64_t m = al < lit->len ? al : lit->len; int c = m ? memcmp(a, lit->bytes, (size_t)m) : 0; *ok = 1;
+    return c ? (c < 0 ? -1 : 1) : (al < lit->len ? -1 : (al > lit->len ? 1 : 0));
+  }
+  return 0;
+}
+
+static int rg_may_match(const fgpu_plan* plan, int node, const o_part* part, const o_rg* rg) {
+  if (node < 0) return 1;
+  const fgpu_expr* e = &plan->exprs[node];
+  if (e->kind != FGPU_EXPR_BINARY) return 1;
+  if (e->op == FGPU_OP_AND) return rg_may_match(plan, e->left, part, rg) && rg_may_match(plan, e->right, part, rg);
+  if (e->op == FGPU_OP_OR) return rg_may_match(plan, e->left, part, rg) || rg_may_match(plan, e->right, part, rg);
+  if (e->op < FGPU_OP_EQ || e->op > FGPU_OP_GT_EQ) return 1; /* AlwaysTrueFilter */
+  const fgpu_expr* l = &plan->exprs[e->left];
+  const fgpu_expr* rt = &plan->exprs[e->right];
+  if (l->kind != FGPU_EXPR_COLUMN || rt->kind != FGPU_EXPR_LITERAL) return 1;
+  const fgpu_scalar* lit = &rt->literal;
+  int ci = -1;
+  for (int c = 0; c < part->n_leaves; c++) if (strcmp(part->leaves[c].name, l->name) == 0) { ci = c; break; }
+  if (ci < 0) { /* column not in this row group (:47-73) */
+    if (lit->type == FGPU_SCALAR_NULL) { if (e->op == FGPU_OP_EQ) return 1; if (e->op == FGPU_OP_NOT_EQ) return 0; }
+    if (lit->type == FGPU_SCALAR_STRING) { if (e->op == FGPU_OP_EQ && lit->len == 0) return 1; if (e->op == FGPU_OP_NOT_EQ && lit->len != 0) return 1; }
+    return 0;
+  }
+  const o_chunk* ch = &rg->chunks[ci];
+  int64_t nulls = ch->null_count >= 0 ? ch->null_count : (part->leaves[ci].optional ? -1 : 0);
+  int full_of_nulls = nulls >= 0 && nulls == rg->num_rows;
+  int ok;
+  if (e->op == FGPU_OP_EQ) {
+    if (lit->type == FGPU_SCALAR_NULL) return nulls != 0; /* unknown count: maybe */
+    if (full_of_nulls) return 0;
+    if (!ch->smin || !ch->smax) return 1;
+    int cmax = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); if (!ok) return 1;
+    int cmin = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); if (!ok) return 1;
+    return cmax >= 0 && cmin <= 0; /* compare(right, Max) <= 0 && compare(right, Min) >= 0 */
+  }
+  if (lit->type == FGPU_SCALAR_NULL) return 1;
+  if (full_of_nulls) return 0;
+  switch (e->op) {
+    case FGPU_OP_LT_EQ: if (!ch->smin) return 1; { int c = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); return !ok || c <= 0; }
+    case FGPU_OP_LT:    if (!ch->smin) return 1; { int c = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); return !ok || c < 0; }
+    case FGPU_OP_GT:    if (!ch->smax) return 1; { int c = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); return !ok || c > 0; }
+    case FGPU_OP_GT_EQ: if (!ch->smax) return 1; { int c = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); return !ok || c >= 0; }
+    default: return 1; /* != : delegated to the execution engine */
+  }
+}
+
 static void* worker_main(void* arg) {
   worker* w = arg; qctx* q = w->q;
   for (;;) {
@@ -901,8 +981,13 @@ int oracle_execute(oracle_table* t, const fgpu_plan* plan, uint64_t tx_watermark
   q.table = t; q.plan = plan; q.max_rows = max_rows;
   for (int p = 0; p < t->n_parts; p++) if (t->parts[p]->tx <= tx_watermark) q.n_queue += t->parts[p]->n_rgs;
   q.queue = xcalloc((size_t)q.n_queue + 1, sizeof(rg_ref));
+  const int no_prune = getenv("FROST_ORACLE_NO_PRUNE") != NULL; /* tests: the filter never changes a result */
   int qi = 0;
-  for (int p = 0; p < t->n_parts; p++) if (t->parts[p]->tx <= tx_watermark) for (int g = 0; g < t->parts[p]->n_rgs; g++) if (t->parts[p]->rgs[g].num_rows > 0) { q.queue[qi].part = t->parts[p]; q.queue[qi].rg = g; qi++; }
+  int64_t pruned_rows = 0; /* row groups the filter rules out still count as scanned rows of the table */
+  for (int p = 0; p < t->n_parts; p++) if (t->parts[p]->tx <= tx_watermark) for (int g = 0; g < t->parts[p]->n_rgs; g++) if (t->parts[p]->rgs[g].num_rows > 0) {
+    if (!no_prune && !rg_may_match(plan, plan->filter, t->parts[p], &t->parts[p]->rgs[g])) { pruned_rows += t->parts[p]->rgs[g].num_rows; continue; }
+    q.queue[qi].part = t->parts[p]; q.queue[qi].rg = g; qi++;
+  }
   q.n_queue = qi;
   collect_proj(plan, plan->filter, &q);
   for (int g = 0; g < plan->n_group_by; g++) collect_proj(plan, plan->group_by[g], &q);
@@ -924,6 +1009,7 @@ int oracle_execute(oracle_table* t, const fgpu_plan* plan, uint64_t tx_watermark
   if (!rc) for (int i = 0; i < n_threads; i++) { ha_merge(&r->fin, &r->workers[i].agg, plan, aif); r->rows_scanned += r->workers[i].rows_scanned; r->rows_selected += r->workers[i].rows_selected; }
   free(q.queue); free(q.proj); free(q.proj_dyn);
   if (rc) { oracle_result_free(r); return -1; }
+  r->rows_scanned += pruned_rows;
   if (plan->kind == FGPU_PLAN_FILTER) {
     /* Filter -> Projection(columns): the compacted rows themselves, in scan order. */
     int total_recs = 0; for (int i = 0; i < n_threads; i++) total_recs += r->workers[i].n_kept;

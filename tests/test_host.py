@@ -115,3 +115,23 @@ def test_dictionary_values_of_a_file(built_lib):
     ref = set(x for x in dp.read_part(buf)["labels.a"].cast(pa.string()).to_pylist() if x is not None)
     assert set(v.decode() for v in vals) == ref and len(vals) == len(ref)
     assert _lib.parquet_dict_values(buf, "labels.nope") == []
+
+
+def test_footer_statistics_and_run_length_directories_of_sorted_parts(built_lib):
+    """What row-group pruning and the sorted-run kernel rely on: the int64 bounds and null counts of the
+    footer survive into the column description, and a sorted dictionary column's directory holds one
+    run per distinct value (the writer's literal groups at run boundaries are unpacked on the host)."""
+    n = 20_000
+    cols = make_columns(n, 77, {"a": (5, 0.0), "b": (37, 0.0), "n": (3, 0.25)}, t0=-500)
+    buf = dp.write_part(dp.SampleDefinition(), cols, sort=True, row_group_size=n, data_page_size=2048)
+    d = _check_against_pyarrow(buf)
+    c = d["row_groups"][0]["columns"]
+    assert (c["timestamp"]["min"], c["timestamp"]["max"], c["timestamp"]["null_count"]) == (-500, n - 501, 0)
+    v = np.asarray(cols["value"])
+    assert (c["value"]["min"], c["value"]["max"]) == (int(v.min()), int(v.max()))
+    assert c["labels.n"]["null_count"] == int((np.asarray(cols["labels.n"][0]) < 0).sum())
+    assert c["labels.a"]["n_runs"] == 5              # first sort key: one run per value, across all pages
+    assert c["labels.b"]["n_runs"] <= 5 * 37         # second key: one run per (a, b) group
+    buf = dp.write_part(dp.SampleDefinition(), cols, sort=True, row_group_size=n, write_statistics=False)
+    c = _lib.describe_parquet(buf)["row_groups"][0]["columns"]
+    assert "min" not in c["timestamp"]

@@ -75,3 +75,41 @@ def test_aggregation_projection_union_of_dynamic_columns():
                                               (None, "value2", "x", "s", 3, 3)], key=lambda r: tuple((x is None, x) for x in r))
     finally:
         eng.close()
+
+
+def test_row_group_filter_never_changes_a_result(monkeypatch):
+    """The oracle's port of LSM.Scan's TrueNegativeFilter (index/lsm.go:401-454, expr/binaryscalarexpr.go)
+    drops row groups by their chunk statistics; the records must be those of a scan of every row group."""
+    eng = OracleEngine(threads=2)
+    try:
+        t = OracleTableHandle(eng, "t", dp.SampleDefinitionWithFloat())
+        n = 5_000
+        for i in range(4):
+            t.Insert(make_columns(n, 900 + i, {"a": (4, 0.2), "b": (9, 0.0)}, with_float=True, float_null_p=0.3, t0=i * n),
+                     row_group_size=2_000)
+        ts, v, f = lp.Col("timestamp"), lp.Col("value"), lp.Col("floatvalue")
+        filters = [
+            lp.And(ts.GtEq(lp.Literal(n + 3)), ts.Lt(lp.Literal(3 * n - 1))), ts.Eq(lp.Literal(2 * n)), ts.Eq(lp.Literal(40 * n)),
+            ts.NotEq(lp.Literal(7)), ts.LtEq(lp.Literal(-1)), ts.Gt(lp.Literal(4 * n - 2)), v.Gt(lp.Literal(998)), v.Lt(lp.Literal(0)),
+            f.GtEq(lp.Literal(999.5)), f.Lt(lp.Literal(250.25)), v.Lt(lp.Literal(10.5)),
+            lp.Or(ts.Lt(lp.Literal(10)), ts.GtEq(lp.Literal(4 * n - 10))), lp.And(ts.Lt(lp.Literal(n)), lp.Col("labels.a").Eq(lp.Literal("v000001"))),
+            lp.Col("labels.a").Eq(lp.Literal("zzz")), lp.Col("labels.a").Eq(lp.Literal(None)), lp.Col("labels.zz").NotEq(lp.Literal(None)),
+            lp.Col("nope").Lt(lp.Literal(4)),
+        ]
+        scanned = []
+        for flt in filters:
+            outs = []
+            for off in (False, True):
+                if off:
+                    monkeypatch.setenv("FROST_ORACLE_NO_PRUNE", "1")
+                else:
+                    monkeypatch.delenv("FROST_ORACLE_NO_PRUNE", raising=False)
+                out = []
+                oracle_query(eng, "t").Filter(flt).Aggregate([lp.Sum(v), lp.Count(v), lp.Max(f)], [lp.Col("labels.b")]) \
+                    .Execute(None, lambda c, r: out.append(r))
+                outs.append(rows_of(out))
+            assert outs[0] == outs[1], flt.Name()
+            scanned.append(len(outs[0]))
+        assert scanned[2] == 0 and scanned[0] > 0
+    finally:
+        eng.close()
