@@ -370,7 +370,7 @@ def main():
             "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(rows_per_gpu, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fgpu::k_scan", "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes),
+                         "traffic": None, "kernel": "fgpu::k_runs (sorted-run scan; fgpu::k_scan takes unsorted / nullable-key row groups)", "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes),
                          "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "groups": int(st["groups"]), "rows_selected_per_gpu": int(st["rows_selected"]),
