@@ -128,6 +128,19 @@ struct fgpu_ctx {
   std::mutex mu;
   std::map<std::string, Table> tables;
   std::vector<ColumnImage*> pending_uploads;  // staging to release after the next stream sync
+  // page-locked scratch for the per-query descriptor upload and the counters read-back (guarded by mu)
+  uint8_t* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  cudaError_t ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_bytes) return cudaSuccess;
+    if (scratch) cudaFreeHost(scratch);
+    scratch = nullptr;
+    scratch_bytes = 0;
+    size_t want = std::max<size_t>(bytes * 2, 1 << 20);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&scratch), want, cudaHostAllocDefault);
+    if (e == cudaSuccess) scratch_bytes = want;
+    return e;
+  }
 };
 
 // FROSTGPU_PROFILE=1: host-side phase times of every Execute on stderr (development aid).
@@ -193,8 +206,11 @@ struct fgpu_result {
   // compiled state kept for partial/merge
   QueryDesc qd{};
   FinalizeDesc fd{};
-  DevBuf table, qdesc_dev, aux;
+  DevBuf table, aux, cnt;
   size_t table_bytes = 0;
+  unsigned int* cnt_ptr = nullptr;  // group counter inside `aux` when the scan counted the result rows
+  bool groups_known = false;  // the scan's own stream already counted the result rows
+  unsigned int n_groups = 0;
   std::vector<KeyOut> keys;
   std::vector<std::string> agg_names;
   std::vector<uint8_t> agg_is_float;
@@ -972,7 +988,7 @@ void bind_table(QueryDesc* qd, uint8_t* base) {
 }
 
 // Runs init + scan.  On success the result owns the device table.
-int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* res) {
+int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* res, bool count_groups = false) {
   PhaseClock pc;
   Compiled c;
   int32_t rc = compile(ctx, q, tx, &c);
@@ -1213,11 +1229,17 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     B.o_span = align16(B.o_rg + B.rgs.size() * sizeof(RunsRg));
     o_cnt = align16(B.o_span + B.first_span.size() * 4);
   }
-  size_t aux_bytes = o_cnt + 64;
+  // device block: [tables | counters 64 B | group counter 16 B | QueryDesc]; the host image of it lives in
+  // page-locked scratch so that one asynchronous copy uploads everything
+  const size_t o_qd = align16(o_cnt + 64 + 16);
+  const size_t aux_bytes = o_qd + sizeof(QueryDesc);
+  const size_t o_ret = align16(aux_bytes);  // scratch only: counters + group count read back
   CUDA_TRY(res->aux.alloc(aux_bytes, ctx->stream));
   uint8_t* aux = static_cast<uint8_t*>(res->aux.p);
   for (auto& fx : lut_fix) lrt[fx.first].lut = aux + o_lut + fx.second;
-  std::vector<uint8_t> hostaux(aux_bytes, 0);
+  CUDA_TRY(ctx->ensure_scratch(o_ret + 128));
+  struct { uint8_t* p; uint8_t* data() { return p; } } hostaux{ctx->scratch};
+  std::memset(hostaux.data(), 0, o_ret + 128);
   std::memcpy(hostaux.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
   std::memcpy(hostaux.data() + o_lrt, lrt.data(), lrt.size() * sizeof(LeafRt));
   std::memcpy(hostaux.data() + o_first, first_tile.data(), first_tile.size() * 4);
@@ -1233,17 +1255,32 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   qd.rg_first_tile = reinterpret_cast<const uint32_t*>(aux + o_first);
   qd.rg_rows = reinterpret_cast<const uint32_t*>(aux + o_rows);
   qd.counters = reinterpret_cast<unsigned long long*>(aux + o_cnt);
-  CUDA_TRY(res->qdesc_dev.alloc(sizeof(QueryDesc), ctx->stream));
+  const QueryDesc* qdesc_dev = reinterpret_cast<const QueryDesc*>(aux + o_qd);
 
+  FinalizeDesc& fd = res->fd;
+  fd = FinalizeDesc{};
+  fd.table_mode = qd.table_mode;
+  fd.key_words = qd.key_words;
+  fd.n_keys = qd.n_keys;
+  fd.n_aggs = qd.n_aggs;
+  fd.table_slots = qd.table_slots;
+  for (int k = 0; k < qd.n_keys; k++) {
+    fd.keys[k] = qd.keys[k];
+    fd.dense_radix[k] = c.dense_radix[size_t(k)] ? c.dense_radix[size_t(k)] : 1;
+  }
+  fd.t_rows = qd.t_rows;
+  for (int a = 0; a < kMaxAggs; a++) fd.t_agg[a] = qd.t_agg[a];
+  fd.t_tag = qd.t_tag;
+  fd.t_keys = qd.t_keys;
   cudaStream_t s = ctx->stream;
   pc.mark("describe");
   CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
+  std::memcpy(hostaux.data() + o_qd, &qd, sizeof(QueryDesc));
   CUDA_TRY(cudaMemcpyAsync(aux, hostaux.data(), aux_bytes, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(res->qdesc_dev.p, &qd, sizeof(QueryDesc), cudaMemcpyHostToDevice, s));
   if (rows_plan) {
     CUDA_TRY(cudaMemsetAsync(qd.tile_state, 0, size_t(tiles) * 8, s));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
-    CUDA_TRY(launch_rows(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
+    CUDA_TRY(launch_rows(qdesc_dev, qd, ctx->sm_count, s));
   } else {
     CUDA_TRY(launch_table_init(qd, s));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
@@ -1259,13 +1296,24 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       st.kernel_launches++;
       st.row_groups_runs += uint32_t(B.rgs.size());
     }
-    CUDA_TRY(launch_scan(static_cast<const QueryDesc*>(res->qdesc_dev.p), qd, ctx->sm_count, s));
+    CUDA_TRY(launch_scan(qdesc_dev, qd, ctx->sm_count, s));
   }
   CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
   st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0);
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
-  unsigned long long counters[8] = {0};
-  CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, s));
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(hostaux.data() + o_ret);
+  if (count_groups && !rows_plan) {  // count the result rows behind the scan: one host round trip less
+    res->cnt_ptr = reinterpret_cast<unsigned int*>(aux + o_cnt + 64);
+    fd.out_count = res->cnt_ptr;
+    fd.max_out = 0;
+    fd.out_keys = nullptr;
+    fd.out_aggs = nullptr;
+    fd.out_rows = nullptr;
+    CUDA_TRY(launch_finalize(fd, s));
+    st.kernel_launches++;
+    res->groups_known = true;
+  }
+  CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64 + 16, cudaMemcpyDeviceToHost, s));
   pc.mark("launch");
   CUDA_TRY(cudaStreamSynchronize(s));  // hostaux / counters stay valid until here
   pc.mark("sync");
@@ -1275,6 +1323,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
   st.scan_kernel_ms = ms;
   st.rows_selected = counters[0];
+  if (res->groups_known) res->n_groups = static_cast<unsigned int>(counters[8] & 0xffffffffull);
   st.d2h_bytes += 64;
   if (counters[1]) return fail(FGPU_ERR_UNSUPPORTED, "aggregate hash table overflow (more groups than the sized capacity)");
 
@@ -1295,21 +1344,6 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     // Count yields int64; Sum/Min/Max keep the input type (aggregate.go:734-950)
     res->agg_is_float.push_back(qd.aggs[a].func != FGPU_AGG_COUNT && qd.aggs[a].is_float);
   }
-  FinalizeDesc& fd = res->fd;
-  fd = FinalizeDesc{};
-  fd.table_mode = qd.table_mode;
-  fd.key_words = qd.key_words;
-  fd.n_keys = qd.n_keys;
-  fd.n_aggs = qd.n_aggs;
-  fd.table_slots = qd.table_slots;
-  for (int k = 0; k < qd.n_keys; k++) {
-    fd.keys[k] = qd.keys[k];
-    fd.dense_radix[k] = c.dense_radix[size_t(k)] ? c.dense_radix[size_t(k)] : 1;
-  }
-  fd.t_rows = qd.t_rows;
-  for (int a = 0; a < kMaxAggs; a++) fd.t_agg[a] = qd.t_agg[a];
-  fd.t_tag = qd.t_tag;
-  fd.t_keys = qd.t_keys;
   pc.mark("keep");
   pc.flush("scan");
   return FGPU_OK;
@@ -1390,7 +1424,6 @@ int32_t finalize_rows(fgpu_ctx* ctx, fgpu_result* res) {
   res->finalized = true;
   res->table.reset();
   res->aux.reset();
-  res->qdesc_dev.reset();
   return FGPU_OK;
 }
 
@@ -1401,36 +1434,43 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   cudaStream_t s = ctx->stream;
   // Upper bound of result rows: every slot could be occupied; count first to size the output.
   // (k_finalize with max_out == 0 only counts.)
-  DevBuf cnt;
-  CUDA_TRY(cnt.alloc(16, ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
-  fd.out_count = static_cast<unsigned int*>(cnt.p);
-  fd.max_out = 0;
-  fd.out_keys = nullptr;
-  fd.out_aggs = nullptr;
-  fd.out_rows = nullptr;
-  CUDA_TRY(launch_finalize(fd, s));
-  unsigned int n_groups = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n_groups, cnt.p, 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  res->stats.kernel_launches += 1;
+  DevBuf& cnt = res->cnt;
+  unsigned int n_groups = res->n_groups;
+  if (!res->groups_known) {
+    CUDA_TRY(cnt.alloc(16, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
+    res->cnt_ptr = static_cast<unsigned int*>(cnt.p);
+    fd.out_count = static_cast<unsigned int*>(cnt.p);
+    fd.max_out = 0;
+    fd.out_keys = nullptr;
+    fd.out_aggs = nullptr;
+    fd.out_rows = nullptr;
+    CUDA_TRY(launch_finalize(fd, s));
+    CUDA_TRY(cudaMemcpyAsync(&n_groups, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    res->stats.kernel_launches += 1;
+  }
   res->stats.groups = n_groups;
   const size_t G = n_groups;
   const int nk = fd.n_keys, na = fd.n_aggs;
-  std::vector<long long> h_keys(size_t(nk) * G), h_aggs(size_t(na) * G);
+  // the result columns land in page-locked scratch (keys first, then aggregates)
+  CUDA_TRY(ctx->ensure_scratch((size_t(nk) + size_t(na)) * G * 8 + 64));
+  struct HostCols { const long long* p; const long long* data() const { return p; } };
+  const HostCols h_keys{reinterpret_cast<const long long*>(ctx->scratch)};
+  const HostCols h_aggs{reinterpret_cast<const long long*>(ctx->scratch) + size_t(nk) * G};
   if (G > 0) {
     DevBuf out;
     size_t bytes = (size_t(nk) + size_t(na) + 1) * G * 8;
     CUDA_TRY(out.alloc(bytes, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 16, s));
+    CUDA_TRY(cudaMemsetAsync(res->cnt_ptr, 0, 16, s));
+    fd.out_count = res->cnt_ptr;
     fd.max_out = n_groups;
     fd.out_keys = static_cast<long long*>(out.p);
     fd.out_aggs = fd.out_keys + size_t(nk) * G;
     fd.out_rows = reinterpret_cast<unsigned long long*>(fd.out_aggs + size_t(na) * G);
     CUDA_TRY(launch_finalize(fd, s));
     res->stats.kernel_launches += 1;
-    if (nk) CUDA_TRY(cudaMemcpyAsync(h_keys.data(), fd.out_keys, size_t(nk) * G * 8, cudaMemcpyDeviceToHost, s));
-    if (na) CUDA_TRY(cudaMemcpyAsync(h_aggs.data(), fd.out_aggs, size_t(na) * G * 8, cudaMemcpyDeviceToHost, s));
+    if (nk + na) CUDA_TRY(cudaMemcpyAsync(ctx->scratch, fd.out_keys, (size_t(nk) + size_t(na)) * G * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     res->stats.d2h_bytes += (size_t(nk) + size_t(na)) * G * 8;
   }
@@ -1459,18 +1499,21 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
       col.validity.assign((G + 7) / 8, 0);
       col.data.resize(G * 4);
       uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
-      std::vector<uint32_t> used;
-      used.reserve(G);
+      // used dictionary ids in increasing order -> dense indices (O(groups + cardinality))
+      std::vector<uint32_t> remap(ko.dict_snapshot.size(), 0xffffffffu), used;
       for (size_t i = 0; i < G; i++)
-        if (codes[i] != 0) used.push_back(uint32_t(codes[i] - 1));
-      std::sort(used.begin(), used.end());
-      used.erase(std::unique(used.begin(), used.end()), used.end());
+        if (codes[i] != 0) remap[size_t(codes[i] - 1)] = 0;
+      for (size_t g = 0; g < remap.size(); g++)
+        if (remap[g] == 0) {
+          remap[g] = uint32_t(used.size());
+          used.push_back(uint32_t(g));
+        }
       for (size_t i = 0; i < G; i++) {
         if (codes[i] == 0) {
           idx[i] = 0;
           col.null_count++;
         } else {
-          idx[i] = uint32_t(std::lower_bound(used.begin(), used.end(), uint32_t(codes[i] - 1)) - used.begin());
+          idx[i] = remap[size_t(codes[i] - 1)];
           set_bit(col.validity, int64_t(i));
         }
       }
@@ -1505,7 +1548,7 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   res->finalized = true;
   res->table.reset();
   res->aux.reset();
-  res->qdesc_dev.reset();
+  res->cnt.reset();
   pc.mark("arrow");
   pc.flush("finalize");
   return FGPU_OK;
@@ -1559,6 +1602,7 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->scratch) cudaFreeHost(ctx->scratch);
   delete ctx;
   return FGPU_OK;
 }
@@ -1701,7 +1745,7 @@ int32_t fgpu_query_execute(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, 
   CUDA_TRY(cudaSetDevice(ctx->device));
   auto res = std::make_unique<fgpu_result>();
   res->ctx = ctx;
-  int32_t rc = run_scan(ctx, *q, tx_watermark, res.get());
+  int32_t rc = run_scan(ctx, *q, tx_watermark, res.get(), /*count_groups=*/true);
   if (rc) return rc;
   rc = finalize_result(ctx, res.get());
   if (rc) return rc;

@@ -1965,10 +1965,14 @@ cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, 
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan, kVecThreads, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
+  static size_t occ_smem = ~size_t(0);
+  static int per_sm = 0;
+  if (occ_smem != smem) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan, kVecThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    occ_smem = smem;
+  }
   uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
   const uint32_t need = (q.n_tiles + warps - 1) / warps;
   if (grid > need) grid = need;

@@ -281,10 +281,21 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
 template <int NL, int NK>
 cudaError_t launch_na(const RunsDesc& d, int na, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
   auto go = [&](auto kern) -> cudaError_t {
-    if (query_only) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      if (e != cudaSuccess) return e;
-      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, kRunsThreads, smem);
+    if (query_only) {  // per kernel instance: attribute and occupancy are looked up once per shared-memory size
+      static size_t cfg_smem = 0, occ_smem = ~size_t(0);
+      static int occ = 0;
+      if (smem > cfg_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        cfg_smem = smem;
+      }
+      if (occ_smem != smem) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRunsThreads, smem);
+        if (e != cudaSuccess) return e;
+        occ_smem = smem;
+      }
+      *per_sm = occ;
+      return cudaSuccess;
     }
     kern<<<grid, kRunsThreads, smem, st>>>(d);
     return cudaGetLastError();

@@ -127,7 +127,8 @@ def test_time_range_filters_prune_and_split(pair):
     assert st["row_groups"] == 0 and st["rows_selected"] == 0
     # rows plans keep their order when row groups are dropped
     got, exp = p.run(lambda q: q.Filter(cases[0]).Project(lp.Col("timestamp"), lp.Col("value"), lp.Col("labels.b")))
-    assert rows_of(got) == rows_of(exp)
+    names = ["timestamp", "value", "labels.b"]
+    assert rows_of(got, names) == rows_of(exp, names) and len(rows_of(got, names)) > 0
 
 
 def test_short_runs_and_three_keys(pair):
