@@ -187,7 +187,7 @@ constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 2, kRunsCols = kRunsLe
 
 struct RunsRg {
   uint32_t n_rows;
-  uint32_t _pad;
+  uint32_t all_pass;  // 1: the chunk statistics decided every leaf (all rows pass); the leaf columns are not staged
   long long lo[kRunsLeaves], hi[kRunsLeaves];  // inclusive bounds of the (fused) range leaves for this row group
   const uint8_t* col[kRunsCols];               // the staged PLAIN columns (distinct leaf and aggregate inputs)
   const Run* runs[kRunsKeys];                  // run directory of every group-key column (dictionary ids premapped)

@@ -227,8 +227,16 @@ namespace {
 // Uploads one column of one part if it is not resident yet: the host-assembled meta region with one
 // copy, the PLAIN value regions straight from the source file (one async copy per contiguous extent),
 // all on the engine stream so that kernels queued behind need no extra synchronisation.
-int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::string& column, uint64_t* h2d_bytes) {
+int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::string& column, uint64_t* h2d_bytes,
+                        double* build_us = nullptr, double* upload_us = nullptr) {
+  auto t0 = std::chrono::steady_clock::now();
   build_column(kIndexRows, table, part, column);
+  auto t1 = std::chrono::steady_clock::now();
+  if (build_us) *build_us += std::chrono::duration<double, std::micro>(t1 - t0).count();
+  struct Tail {
+    double* out; std::chrono::steady_clock::time_point t;
+    ~Tail() { if (out) *out += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t).count(); }
+  } tail{upload_us, t1};
   ColumnImage& img = part->images[column];
   if (!img.error.empty()) return FGPU_OK;  // surfaces as an error only if a query projects the column
   if (img.resident) return FGPU_OK;
@@ -728,6 +736,8 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   // Lazy residency: the columns this query projects are built and uploaded now (parts put with
   // FGPU_PUT_BORROW_PINNED upload nothing until a query needs it; optimize.go:36-73 physical projection).
   {
+    PhaseClock pc;
+    double build_us = 0, upload_us = 0;
     Part* last = nullptr;
     for (const VisibleRG& v : c->rgs) {
       if (v.part == last) continue;
@@ -739,11 +749,17 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
           if (w.part == v.part && !((w.skip_slots >> si) & 1)) { read = true; break; }
         if (!read) continue;
         if (std::find(v.part->columns.begin(), v.part->columns.end(), name) == v.part->columns.end()) continue;
-        int32_t rc = ensure_resident(ctx, &table, v.part, name, &c->h2d_bytes);
+        int32_t rc = ensure_resident(ctx, &table, v.part, name, &c->h2d_bytes, pc.on ? &build_us : nullptr, pc.on ? &upload_us : nullptr);
         if (rc) return rc;
         const ColumnImage& img = v.part->images[name];
         if (!img.error.empty()) return fail(FGPU_ERR_UNSUPPORTED, "column " + name + ": " + img.error);
       }
+    }
+    if (pc.on && c->h2d_bytes) {
+      char buf[128];
+      snprintf(buf, sizeof buf, " build=%.0fus enqueue=%.0fus bytes=%llu", build_us, upload_us, (unsigned long long)c->h2d_bytes);
+      pc.line = buf;
+      pc.flush("residency");
     }
   }
   // shared-memory ring of the scan kernel: stage every numeric slot's PLAIN slice (up to kMaxStagePlain)
@@ -1010,8 +1026,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   uint32_t tiles = 0;
   const uint32_t tile_len = q.kind == FGPU_PLAN_FILTER ? uint32_t(kTileRows) : uint32_t(qd.vl);  // rows plan: CTA tiles; scan: warp vectors
   // ---- sorted-run scan: query-level eligibility (see runs_scan.cu) --------------------------------
-  // Two batches of row groups, each its own launch: [0] evaluates the range leaves, [1] holds the row
-  // groups whose statistics already decided every leaf (all rows pass: the leaf columns are not read).
+  // One launch over the qualifying row groups; a row group whose statistics already decided every
+  // leaf is flagged all_pass (its leaf columns are neither uploaded nor staged).
   struct RunsBatch {
     RunsDesc rd{};
     int nl = 0;
@@ -1020,7 +1036,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     std::vector<uint32_t> rows, first_span;
     size_t o_rg = 0, o_span = 0;
   };
-  RunsBatch batches[2];
+  RunsBatch batches[1];
   int runs_nl = 0, runs_nk = 0, runs_na = 0;
   int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
   bool runs_q = q.kind != FGPU_PLAN_FILTER && qd.fast_ok && !getenv("FROSTGPU_NO_RUNS");
@@ -1040,7 +1056,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     runs_nk = qd.n_keys;
   }
   if (runs_q) {  // distinct staged columns of each batch
-    for (int bi = 0; bi < 2; bi++) {
+    for (int bi = 0; bi < 1; bi++) {
       RunsBatch& B = batches[bi];
       auto col_of = [&](int slot) {
         for (uint32_t i = 0; i < B.rd.n_cols; i++)
@@ -1048,7 +1064,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         B.col_slot[B.rd.n_cols] = slot;
         return B.rd.n_cols++;
       };
-      B.nl = bi == 0 ? runs_nl : 0;
+      B.nl = runs_nl;
       for (int l = 0; l < B.nl; l++) B.rd.leaf_col[l] = col_of(runs_leaf_slot[l]);
       for (int a = 0; a < runs_na; a++) B.rd.agg_col[a] = col_of(runs_agg_slot[a]);
       for (int k = 0; k < runs_nk; k++) B.rd.stride[k] = qd.keys[k].dense_stride;
@@ -1098,7 +1114,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     }
     // ---- does this row group qualify for the sorted-run kernel? ----
     bool runs_ok = runs_q && rg.n_rows > 0;
-    int bi = 0;
+    const int bi = 0;
+    bool all_pass = false;
     if (runs_ok) {
       bool all_all = runs_nl > 0;
       for (int l = 0; l < runs_nl; l++) {
@@ -1106,7 +1123,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         if (m != LM_ALL) all_all = false;
         if (m == LM_NONE) runs_ok = false;  // (only with pruning switched off)
       }
-      bi = all_all ? 1 : 0;
+      all_pass = all_all;
     }
     RunsRg rr{};
     if (runs_ok) {
@@ -1117,20 +1134,26 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         rr.lo[l] = all ? std::numeric_limits<int64_t>::min() : qd.leaves[l].lo_i;
         rr.hi[l] = all ? std::numeric_limits<int64_t>::max() : qd.leaves[l].hi_i;
       }
+      rr.all_pass = all_pass ? 1 : 0;
       const uint8_t* any_col = nullptr;
       for (uint32_t i = 0; i < B.rd.n_cols && runs_ok; i++) {
         const ChunkDesc& d = chunks[size_t(g) * n_slots + B.col_slot[i]];
         rr.col[i] = nullptr;
-        if ((c.rgs[size_t(g0)].skip_slots >> B.col_slot[i]) & 1) continue;  // decided leaf: any column stands in
+        if ((c.rgs[size_t(g0)].skip_slots >> B.col_slot[i]) & 1) continue;  // a decided leaf's own column
         if (d.kind != CK_PLAIN64 || d.has_nulls) runs_ok = false;
         rr.col[i] = d.values;
         any_col = d.values;
       }
-      for (uint32_t i = 0; i < B.rd.n_cols && runs_ok; i++) {
+      // all_pass: the leaf columns stay null (not staged).  Otherwise a decided leaf still runs its
+      // (widened) range test: any staged column stands in for the one that was not uploaded.
+      for (uint32_t i = 0; i < B.rd.n_cols && runs_ok && !all_pass; i++) {
         if (rr.col[i]) continue;
         if (!any_col) runs_ok = false;
         rr.col[i] = any_col;
       }
+      if (all_pass)  // aggregate inputs must be there
+        for (int a = 0; a < runs_na && runs_ok; a++)
+          if (!rr.col[B.rd.agg_col[a]]) runs_ok = false;
       for (int k = 0; k < runs_nk && runs_ok; k++) {
         const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.keys[k].slot];
         // run-length only, and runs long enough that a 32-row step rarely holds two run ends
@@ -1612,6 +1635,8 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   if (!ctx || !table || !file) return fail(FGPU_ERR_INVALID, "null argument");
   if (flags != FGPU_PUT_DEFAULT && flags != FGPU_PUT_BORROW_PINNED) return fail(FGPU_ERR_INVALID, "unknown put flags");
   std::lock_guard<std::mutex> lk(ctx->mu);
+  PhaseClock pc;
+  struct PutTail { PhaseClock& pc; ~PutTail() { pc.mark("put"); pc.flush("put"); } } put_tail{pc};
   CUDA_TRY(cudaSetDevice(ctx->device));
   Table& t = ctx->tables[table];
   for (auto& p : t.parts)
@@ -1673,11 +1698,14 @@ int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->tables.find(table);
   if (it == ctx->tables.end()) return FGPU_OK;
+  PhaseClock pc;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   release_staging(ctx);
   for (auto& p : it->second.parts) free_part(ctx, p.get());
   ctx->tables.erase(it);
+  pc.mark("drop");
+  pc.flush("drop");
   return FGPU_OK;
 }
 

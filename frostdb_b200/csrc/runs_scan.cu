@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
       const uint32_t dst = ring_s + rs * slot_bytes + uint32_t(lane) * 16u;
 #pragma unroll
       for (int c = 0; c < NC; c++) {
-        if (uint32_t(c) < n_cols) {
+        if (uint32_t(c) < n_cols && i_col[c] != nullptr) {  // (null: a leaf column this row group does not need)
           const uint8_t* src = i_col[c] + size_t(i_row) * 8u + uint32_t(lane) * 16u;
           const uint32_t dc = dst + uint32_t(c) * col_bytes;
           if (n == BR) {
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
       lo[l] = __ldg(&R->lo[l]);
       hi[l] = __ldg(&R->hi[l]);
     }
+    const bool all_pass = NL == 0 || __ldg(&R->all_pass) != 0;  // warp-uniform: statistics decided the filter
     // key cursors: the run that holds the span's first row (seed of its 128-row chunk)
     const Run* runs[NK > 0 ? NK : 1];
     uint32_t kk[NK > 0 ? NK : 1], kend[NK > 0 ? NK : 1], kadd[NK > 0 ? NK : 1];
@@ -213,18 +214,27 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
         }
         // ---- whole steps inside the running group ----
         const int e = s + int((safe - row) >> 5);
-#pragma unroll 2
-        for (; s < e; s++) {
-          const bool act = passes(s);
-          cnt += act ? 1u : 0u;
+        if (all_pass) {
+          cnt += uint32_t(e - s);
+#pragma unroll 4
+          for (; s < e; s++) {
 #pragma unroll
-          for (int a = 0; a < NA; a++) part[a] += act ? lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+            for (int a = 0; a < NA; a++) part[a] += lds64(acol[a] + uint32_t(s) * 256u);
+          }
+        } else {
+#pragma unroll 2
+          for (; s < e; s++) {
+            const bool act = passes(s);
+            cnt += act ? 1u : 0u;
+#pragma unroll
+            for (int a = 0; a < NA; a++) part[a] += act ? lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
+          }
         }
         if (s >= steps) break;
         // ---- the step that holds row `safe`: lanes below it still belong to the running group ----
         row = r0 + uint32_t(s) * 32u;
         const uint32_t r = row + uint32_t(lane);
-        const bool act = r < rend && passes(s);
+        const bool act = r < rend && (all_pass || passes(s));
         const bool old = act && r < safe;
         unsigned long long v[NA > 0 ? NA : 1];
 #pragma unroll

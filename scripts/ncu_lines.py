@@ -1,6 +1,7 @@
 """Per-source-line instruction / stall profile of one kernel from an ncu report.
 
   python scripts/ncu_lines.py gpurun_out/prof.ncu-rep [kernel-symbol-substring] [rows]
+  (NCU_LINES_UNIT=runs_scan picks frostdb_b200/csrc/runs_scan.cu / build/runs_scan.o instead of kernels)
 
 Joins `ncu --page source --csv` (per-SASS-instruction counters, in program order) with
 `nvdisasm -g` of the cubin inside frostdb_b200/csrc/build/kernels.o (line markers, same order)."""
@@ -11,8 +12,9 @@ sym = sys.argv[2] if len(sys.argv) > 2 else "k_scan"
 rows_scanned = float(sys.argv[3]) if len(sys.argv) > 3 else 0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csrc = os.path.join(root, "frostdb_b200", "csrc")
-subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.join(csrc, "build", "kernels.o")], cwd="/tmp", stdout=subprocess.DEVNULL)
-dis = subprocess.run(["nvdisasm", "-g", "-c", "/tmp/kernels.sm_100a.cubin"], capture_output=True, text=True).stdout
+unit = os.environ.get("NCU_LINES_UNIT", "kernels")
+subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.join(csrc, "build", unit + ".o")], cwd="/tmp", stdout=subprocess.DEVNULL)
+dis = subprocess.run(["nvdisasm", "-g", "-c", f"/tmp/{unit}.sm_100a.cubin"], capture_output=True, text=True).stdout
 cur_fn, cur_line, seq = None, None, []
 for ln in dis.split("\n"):
     if ln.startswith("\t.section") and ".text." in ln:
@@ -52,7 +54,7 @@ ti, ts = sum(inst.values()), sum(samp.values())
 print(f"warp instructions {ti:.0f}" + (f"  = {ti / (rows_scanned / 32):.1f} per 32-row step" if rows_scanned else ""))
 ss = sum(stall.values())
 print("stalls:", ", ".join(f"{k[6:]} {v / ss * 100:.0f}%" for k, v in stall.most_common(7)))
-src = open(os.path.join(csrc, "kernels.cu")).read().split("\n")
+src = open(os.path.join(csrc, unit + ".cu")).read().split("\n")
 # per function (source ranges between "__device__"/"__global__" definitions)
 starts = [i + 1 for i, l in enumerate(src) if re.match(r"^(template .*)?(__device__|__global__)", l) or (l.startswith("__device__") or l.startswith("__global__"))]
 def fn_of(line):
@@ -63,7 +65,7 @@ def fn_of(line):
     return src[best - 1].strip()[:90] if best else "?"
 byfn_i, byfn_s = collections.Counter(), collections.Counter()
 for k, v in inst.items():
-    name = fn_of(k[1]) if k and k[0] == "kernels.cu" else (k[0] if k else "?")
+    name = fn_of(k[1]) if k and k[0] == unit + ".cu" else (k[0] if k else "?")
     byfn_i[name] += v
     byfn_s[name] += samp[k]
 print("\n-- by function: inst%  samples%")
@@ -73,5 +75,5 @@ print("\n-- by line: inst%  samples%")
 for k, v in inst.most_common(int(os.environ.get("NCU_LINES_TOP", 40))):
     if not k:
         continue
-    text = src[k[1] - 1].strip()[:100] if k[0] == "kernels.cu" else k[0]
+    text = src[k[1] - 1].strip()[:100] if k[0] == unit + ".cu" else k[0]
     print(f"{k[1]:5d} {v / ti * 100:5.1f} {samp[k] / ts * 100:5.1f}  {text}")
