@@ -178,6 +178,17 @@ struct QueryDesc {
 };
 
 // Dense/hash table -> compacted result rows.
+// One cursor-seed array to derive on the device from an uploaded run directory (k_make_seeds): the
+// seeds are 32 bytes per 128 rows, far more than the directory of a sorted column, so they are computed
+// where they are used instead of being built and copied by the host.  Offsets are relative to the
+// column image.
+struct SeedJob {
+  uint64_t runs_off;   // Run[n_runs + 1] (sentinel included)
+  uint64_t seeds_off;  // Seed[n_chunks] to fill
+  uint64_t val0_off;   // uint32[n_chunks]: values before each 128-row chunk (nullable columns); ~0: chunk * 128
+  uint32_t n_runs, total, n_chunks, is_def;
+};
+
 // ---- sorted-run scan (k_runs): the plan shape of compacted parts ---------------------------------------
 // Row groups whose filter columns and aggregate inputs are PLAIN non-null int64 and whose group-key
 // columns are run-length only (sorted parts) are scanned by a dedicated kernel that walks the key run

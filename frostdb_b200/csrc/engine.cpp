@@ -230,7 +230,7 @@ namespace {
 int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::string& column, uint64_t* h2d_bytes,
                         double* build_us = nullptr, double* upload_us = nullptr) {
   auto t0 = std::chrono::steady_clock::now();
-  build_column(kIndexRows, table, part, column);
+  build_column(kIndexRows, table, part, column, /*device_seeds=*/true);
   auto t1 = std::chrono::steady_clock::now();
   if (build_us) *build_us += std::chrono::duration<double, std::micro>(t1 - t0).count();
   struct Tail {
@@ -247,6 +247,7 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
     if (e != cudaSuccess) break;
     e = cudaMemcpyAsync(static_cast<uint8_t*>(dev) + x.dst_off, x.src, x.len, cudaMemcpyHostToDevice, ctx->stream);
   }
+  if (e == cudaSuccess) e = launch_make_seeds(dev, img.seed_jobs_off, img.n_seed_jobs, img.max_seed_chunks, ctx->stream);
   if (e != cudaSuccess) {
     cudaFreeAsync(dev, ctx->stream);
     cudaGetLastError();

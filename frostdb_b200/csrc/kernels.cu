@@ -2002,6 +2002,47 @@ cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t s
   return cudaGetLastError();
 }
 
+// ---- cursor seeds from an uploaded run directory (one thread per 128-row chunk, binary search) ----
+// Same result as the host's make_seeds (part_store.cpp): the run that holds the chunk's first value.
+__global__ void k_make_seeds(uint8_t* base, const SeedJob* jobs) {
+  const SeedJob j = jobs[blockIdx.y];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= j.n_chunks) return;
+  const Run* runs = reinterpret_cast<const Run*>(base + j.runs_off);
+  const uint32_t* val0 = j.val0_off == ~0ull ? nullptr : reinterpret_cast<const uint32_t*>(base + j.val0_off);
+  const uint32_t v0 = val0 ? val0[t] : t * uint32_t(kIndexRows);
+  const uint32_t first = j.is_def ? t * uint32_t(kIndexRows) : v0;
+  Seed sd{};
+  sd.val0 = v0;
+  if (j.n_runs == 0 || first >= j.total) {  // nothing left to decode from this chunk on
+    sd.k = j.n_runs;
+    sd.start = j.total;
+    sd.end = 0xffffffffu;
+  } else {
+    uint32_t lo = 0, hi = j.n_runs;  // last run with start <= first
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (runs[mid].start <= first) lo = mid;
+      else hi = mid;
+    }
+    const Run r = runs[lo];
+    sd.k = lo;
+    sd.start = r.start;
+    sd.end = runs[lo + 1].start;  // the sentinel's start is the total
+    sd.off = r.off;
+    sd.val = r.val;
+    sd.meta = r.meta;
+  }
+  reinterpret_cast<Seed*>(base + j.seeds_off)[t] = sd;
+}
+
+cudaError_t launch_make_seeds(void* image, uint64_t jobs_off, uint32_t n_jobs, uint32_t max_chunks, cudaStream_t st) {
+  if (n_jobs == 0 || max_chunks == 0) return cudaSuccess;
+  dim3 grid((max_chunks + 255) / 256, n_jobs);
+  k_make_seeds<<<grid, 256, 0, st>>>(static_cast<uint8_t*>(image), reinterpret_cast<const SeedJob*>(static_cast<uint8_t*>(image) + jobs_off));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const ChunkDesc& c, int32_t* out_i32, long long* out_i64, uint8_t* out_valid, int sm_count,
                           cudaStream_t st) {
   uint32_t n_chunks = (c.n_rows + kIndexRows - 1) / kIndexRows;

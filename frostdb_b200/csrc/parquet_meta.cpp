@@ -262,15 +262,10 @@ RawPageHeader read_page_header(TReader& r) {
   return h;
 }
 
-int bit_width_for(int max_level) {
-  int w = 0;
-  while ((1 << w) <= max_level) w++;
-  return w;
-}
-
-// Walks the pages of one column chunk.
-void walk_chunk(const uint8_t* file, uint64_t len, const RawColumnMeta& cm, const SchemaLeaf& leaf,
-                int64_t rg_rows, ChunkMeta* out) {
+// Footer facts of one column chunk (no page is touched).
+void init_chunk(const RawColumnMeta& cm, const SchemaLeaf& leaf, ChunkMeta* out) {
+  out->data_page_offset = cm.data_page_offset;
+  out->dict_page_offset = cm.dict_page_offset;
   out->codec = cm.codec;
   out->num_values = cm.num_values;
   out->total_compressed_size = cm.total_compressed;
@@ -288,6 +283,16 @@ void walk_chunk(const uint8_t* file, uint64_t len, const RawColumnMeta& cm, cons
     out->error = "repeated (nested) columns are not supported";
     return;
   }
+}
+
+}  // namespace
+
+void walk_chunk_pages(const uint8_t* file, uint64_t len, const SchemaLeaf& leaf, int64_t rg_rows, ChunkMeta* out) {
+  if (out->pages_walked) return;
+  out->pages_walked = true;
+  if (!out->error.empty()) return;
+  struct { int64_t data_page_offset, dict_page_offset, total_compressed, num_values; } cm{out->data_page_offset, out->dict_page_offset,
+                                                                                          out->total_compressed_size, out->num_values};
   int64_t start = cm.data_page_offset;
   if (cm.dict_page_offset > 0 && cm.dict_page_offset < start) start = cm.dict_page_offset;
   if (start < 4 || uint64_t(start) >= len) {
@@ -372,12 +377,9 @@ void walk_chunk(const uint8_t* file, uint64_t len, const RawColumnMeta& cm, cons
     out->error = "flat column with num_values != row group rows";
     return;
   }
-  (void)bit_width_for;
 }
 
-}  // namespace
-
-bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::string* err) {
+bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::string* err, bool walk_pages) {
   *out = ParsedFile{};
   if (len < 12 || std::memcmp(file, "PAR1", 4) != 0 || std::memcmp(file + len - 4, "PAR1", 4) != 0) {
     *err = "not a Parquet file (missing PAR1 magic)";
@@ -498,7 +500,8 @@ bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::stri
     m.chunks.resize(rg.cols.size());
     for (size_t c = 0; c < rg.cols.size(); c++) {
       m.chunks[c].leaf = int32_t(c);
-      walk_chunk(file, len, rg.cols[c], out->leaves[c], rg.num_rows, &m.chunks[c]);
+      init_chunk(rg.cols[c], out->leaves[c], &m.chunks[c]);
+      if (walk_pages) walk_chunk_pages(file, len, out->leaves[c], rg.num_rows, &m.chunks[c]);
     }
     out->row_groups.push_back(std::move(m));
   }

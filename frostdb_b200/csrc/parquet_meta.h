@@ -53,6 +53,9 @@ struct ChunkMeta {
   uint32_t dict_num_values = 0;
   std::vector<PageInfo> pages;
   std::string error;  // non-empty: chunk is unreadable by this engine (reason); only an error if projected
+  // page walk state: footers are parsed eagerly, page headers only for the chunks a query touches
+  int64_t data_page_offset = -1, dict_page_offset = -1;
+  bool pages_walked = false;
 };
 
 struct RowGroupMeta {
@@ -70,7 +73,11 @@ struct ParsedFile {
 
 // Parses footer and walks every page header.  Pointers in the result alias `file`.
 // Returns false and sets err on malformed input.
-bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::string* err);
+// With walk_pages == false only the footer is read; walk_chunk_pages() then fills a chunk on demand.
+bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::string* err, bool walk_pages = true);
+
+// Walks the page headers of one column chunk (idempotent): fills pages / dict, or sets error.
+void walk_chunk_pages(const uint8_t* file, uint64_t len, const SchemaLeaf& leaf, int64_t rg_rows, ChunkMeta* cm);
 
 // One run of an RLE/bit-packed hybrid stream (Parquet "RLE" encoding).
 struct HostRun {

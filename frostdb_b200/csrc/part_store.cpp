@@ -17,7 +17,16 @@ struct ImageWriter {
   std::vector<uint8_t>& buf;
   std::vector<Extent>& extents;
   uint64_t ext_size = 0;
+  uint64_t dev_size = 0;            // device-only region behind the extents (seeds derived on the device)
+  bool device_seeds = false;
+  std::vector<SeedJob> jobs;
   ImageWriter(std::vector<uint8_t>& b, std::vector<Extent>& e) : buf(b), extents(e) {}
+  uint64_t reserve_dev(uint64_t n) {
+    dev_size = (dev_size + kAlign - 1) / kAlign * kAlign;
+    uint64_t off = dev_size;
+    dev_size += n + kTailPad;
+    return off;
+  }
   size_t begin() {
     size_t n = (buf.size() + kAlign - 1) / kAlign * kAlign;
     buf.resize(n, 0);
@@ -289,37 +298,57 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   } else {
     out->off_values = w.section(vstream.data(), vstream.size());
   }
+  uint64_t val0_off = ~0ull;
+  if (w.device_seeds && has_nulls) val0_off = uint64_t(w.section(chunk_val0.data(), chunk_val0.size() * 4));
+  auto seed_job = [&](int64_t runs_off, uint32_t n_runs, uint32_t total, bool is_def) {
+    SeedJob j{};
+    j.runs_off = uint64_t(runs_off);
+    j.seeds_off = w.reserve_dev(uint64_t(n_chunks) * sizeof(Seed));
+    j.val0_off = val0_off;
+    j.n_runs = n_runs;
+    j.total = total;
+    j.n_chunks = n_chunks;
+    j.is_def = is_def ? 1 : 0;
+    w.jobs.push_back(j);
+    return int64_t(j.seeds_off);
+  };
   if (out->desc.kind != CK_PLAIN64) {
-    std::vector<Seed> seeds = make_seeds(vruns, n_values, false);
     out->desc.n_runs = uint32_t(vruns.size());
     uint32_t bp = 0;
     for (const HostRun& r : vruns) bp += (r.meta & 1u);
     out->desc.n_bp_runs = bp;
+    std::vector<Seed> seeds;
+    if (!w.device_seeds) seeds = make_seeds(vruns, n_values, false);
     HostRun sentinel{n_values, 0, 0, 0};
     vruns.push_back(sentinel);
     out->off_runs = w.section(vruns.data(), vruns.size() * sizeof(HostRun));
-    out->off_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
+    if (w.device_seeds) out->dev_seeds = seed_job(out->off_runs, out->desc.n_runs, n_values, false);
+    else out->off_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
   }
   if (has_nulls) {
-    std::vector<Seed> seeds = make_seeds(defruns, n_rows, true);
     out->desc.n_defruns = uint32_t(defruns.size());
+    std::vector<Seed> seeds;
+    if (!w.device_seeds) seeds = make_seeds(defruns, n_rows, true);
     HostRun sentinel{n_rows, 0, 0, 0};
     defruns.push_back(sentinel);
     out->off_def = w.section(defstream.data(), defstream.size());
     out->off_def_runs = w.section(defruns.data(), defruns.size() * sizeof(HostRun));
-    out->off_def_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
+    if (w.device_seeds) out->dev_def_seeds = seed_job(out->off_def_runs, out->desc.n_defruns, n_rows, true);
+    else out->off_def_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
   }
   if (out->desc.kind == CK_DICT_STR) out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
   if (out->desc.kind == CK_DICT64) out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
   (void)plain_bytes;
   const size_t payload = vstream.size() + (has_nulls ? defstream.size() : 0);
   out->meta_bytes = (w.buf.size() - before) - std::min(w.buf.size() - before, payload);
+  if (out->dev_seeds >= 0) out->meta_bytes += uint64_t(n_chunks) * sizeof(Seed);
+  if (out->dev_def_seeds >= 0) out->meta_bytes += uint64_t(n_chunks) * sizeof(Seed);
 }
 
 }  // namespace
 
 bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) {
-  if (!parse_parquet(file, len, &part->pf, err)) return false;
+  if (!parse_parquet(file, len, &part->pf, err, /*walk_pages=*/false)) return false;  // page headers: on demand, per column
   part->file = file;
   part->file_bytes = len;
   part->columns.clear();
@@ -346,7 +375,7 @@ bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) 
   return true;
 }
 
-void build_column(int index_rows, Table* table, Part* part, const std::string& column) {
+void build_column(int index_rows, Table* table, Part* part, const std::string& column, bool device_seeds) {
   ColumnImage& img = part->images[column];
   if (img.built) return;
   img.built = true;
@@ -357,24 +386,38 @@ void build_column(int index_rows, Table* table, Part* part, const std::string& c
   const SchemaLeaf& sl = part->pf.leaves[leaf];
   GlobalDict* dict = (sl.phys == PT_BYTE_ARRAY) ? &table->dicts[column] : nullptr;
   ImageWriter w(img.meta, img.extents);
+  w.device_seeds = device_seeds;
   size_t g = 0;
-  for (const RowGroupMeta& rg : part->pf.row_groups) {
+  for (RowGroupMeta& rg : part->pf.row_groups) {
     if (rg.num_rows == 0) continue;
     RowGroupHost& h = part->rgs[g++];
     ChunkHost ch;
+    walk_chunk_pages(part->file, part->file_bytes, sl, rg.num_rows, &rg.chunks[leaf]);  // first touch of this chunk
     build_chunk(rg.chunks[leaf], sl, h.n_rows, index_rows, dict, w, &ch);
     if (!ch.error.empty() && img.error.empty()) img.error = ch.error;
     h.cols[column] = std::move(ch);
   }
+  if (!w.jobs.empty()) {
+    img.seed_jobs_off = uint64_t(w.section(w.jobs.data(), w.jobs.size() * sizeof(SeedJob)));
+    img.n_seed_jobs = uint32_t(w.jobs.size());
+    for (const SeedJob& j : w.jobs) img.max_seed_chunks = std::max(img.max_seed_chunks, j.n_chunks);
+  }
   if (img.meta.empty()) img.meta.resize(kAlign, 0);
-  // rebase extent offsets behind the (128-aligned) meta region
+  // rebase extent offsets behind the (128-aligned) meta region, the device-only region behind the extents
   const uint64_t meta_size = (img.meta.size() + kAlign - 1) / kAlign * kAlign;
+  const uint64_t dev_base = (meta_size + w.ext_size + kAlign - 1) / kAlign * kAlign;
   for (Extent& e : img.extents) e.dst_off += meta_size;
   for (RowGroupHost& h : part->rgs) {
     ChunkHost& ch = h.cols[column];
     if (ch.off_values < -0) ch.off_values = int64_t(meta_size) + (-ch.off_values - 1);
+    if (ch.dev_seeds >= 0) ch.off_seeds = int64_t(dev_base) + ch.dev_seeds;
+    if (ch.dev_def_seeds >= 0) ch.off_def_seeds = int64_t(dev_base) + ch.dev_def_seeds;
   }
-  img.dev_bytes = meta_size + w.ext_size + kAlign;
+  for (uint32_t i = 0; i < img.n_seed_jobs; i++) {
+    SeedJob* j = reinterpret_cast<SeedJob*>(img.meta.data() + img.seed_jobs_off) + i;
+    j->seeds_off += dev_base;
+  }
+  img.dev_bytes = dev_base + w.dev_size + kAlign;
 }
 
 void patch_column_pointers(Part* part, const std::string& column, const uint8_t* base) {

@@ -45,6 +45,7 @@ struct ChunkHost {
   // section offsets inside the part image (patched into desc after upload)
   int64_t off_values = -1, off_runs = -1, off_seeds = -1, off_def = -1, off_def_runs = -1, off_def_seeds = -1, off_lut = -1,
           off_dict64 = -1;
+  int64_t dev_seeds = -1, dev_def_seeds = -1;  // seeds derived on the device: offsets inside the image's device-only region
 };
 
 struct RowGroupHost {
@@ -68,6 +69,8 @@ struct ColumnImage {
   uint64_t dev_bytes = 0;
   std::vector<uint8_t> meta;     // host staging of everything that is not an extent (kept until uploaded)
   std::vector<Extent> extents;
+  uint64_t seed_jobs_off = 0;    // SeedJob[n_seed_jobs] inside the meta region (device-derived seeds)
+  uint32_t n_seed_jobs = 0, max_seed_chunks = 0;
   std::string error;             // whole-column error (a chunk the engine cannot read)
 };
 
@@ -94,7 +97,8 @@ bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err);
 // Builds the host side of one column of a part (no CUDA calls): run directories, seeds, dictionary
 // LUTs into `image.meta`, PLAIN value regions as extents.  Interns dictionary entries into `table`.
 // ChunkDesc pointers are offsets until patch_column_pointers() is called.
-void build_column(int index_rows, Table* table, Part* part, const std::string& column);
+// device_seeds: leave the cursor seeds to k_make_seeds (ColumnImage::seed_jobs_*) instead of building them here.
+void build_column(int index_rows, Table* table, Part* part, const std::string& column, bool device_seeds = false);
 
 // Patches device pointers into the column's ChunkDescs once the image lives at `dev_base`.
 void patch_column_pointers(Part* part, const std::string& column, const uint8_t* dev_base);
