@@ -178,6 +178,14 @@ struct QueryDesc {
 };
 
 // Dense/hash table -> compacted result rows.
+// One PLAIN page payload to move from the raw chunk bytes (copied from the host in ONE transfer per column
+// chunk, page headers and level bytes included) to its place in the dense value array (k_gather_pages).
+struct PageCopy {
+  uint64_t src_off;  // byte offset inside the staging buffer (any alignment)
+  uint64_t dst_off;  // byte offset inside the column image (8-byte aligned)
+  uint64_t len;      // multiple of 8
+};
+
 // One cursor-seed array to derive on the device from an uploaded run directory (k_make_seeds): the
 // seeds are 32 bytes per 128 rows, far more than the directory of a sorted column, so they are computed
 // where they are used instead of being built and copied by the host.  Offsets are relative to the

@@ -243,9 +243,48 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
   void* dev = nullptr;
   CUDA_TRY(cudaMallocAsync(&dev, img.dev_bytes, ctx->stream));
   cudaError_t e = cudaMemcpyAsync(dev, img.meta.data(), img.meta.size(), cudaMemcpyHostToDevice, ctx->stream);
-  for (const Extent& x : img.extents) {
-    if (e != cudaSuccess) break;
-    e = cudaMemcpyAsync(static_cast<uint8_t*>(dev) + x.dst_off, x.src, x.len, cudaMemcpyHostToDevice, ctx->stream);
+  // PLAIN pages: neighbouring page payloads (separated by a page header) travel as ONE transfer of the
+  // raw bytes into a staging buffer and are gathered into the dense value array on the device; a payload
+  // without neighbours goes straight to its place.
+  uint64_t copied = img.meta.size();
+  {
+    struct Span { const uint8_t* src; uint64_t len, stage_off; size_t first, n; };
+    std::vector<Span> spans;
+    constexpr uint64_t kGap = 4096;
+    for (size_t i = 0; i < img.extents.size(); i++) {
+      const Extent& x = img.extents[i];
+      if (!spans.empty() && x.src >= spans.back().src + spans.back().len && uint64_t(x.src - (spans.back().src + spans.back().len)) <= kGap) {
+        spans.back().len = uint64_t(x.src - spans.back().src) + x.len;
+        spans.back().n++;
+      } else {
+        spans.push_back({x.src, x.len, 0, i, 1});
+      }
+    }
+    uint64_t stage_bytes = 0;
+    std::vector<PageCopy> copies;
+    for (Span& sp : spans) {
+      if (sp.n == 1) continue;
+      sp.stage_off = stage_bytes;
+      stage_bytes += ((sp.len + 15) & ~uint64_t(15)) + 16;
+      for (size_t i = sp.first; i < sp.first + sp.n; i++)
+        copies.push_back({sp.stage_off + uint64_t(img.extents[i].src - sp.src), img.extents[i].dst_off, img.extents[i].len});
+    }
+    DevBuf stage;
+    const uint64_t table_off = stage_bytes;
+    if (!copies.empty() && e == cudaSuccess) {
+      e = stage.alloc(stage_bytes + copies.size() * sizeof(PageCopy), ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(static_cast<uint8_t*>(stage.p) + table_off, copies.data(), copies.size() * sizeof(PageCopy), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    for (const Span& sp : spans) {
+      if (e != cudaSuccess) break;
+      copied += sp.len;
+      if (sp.n == 1) e = cudaMemcpyAsync(static_cast<uint8_t*>(dev) + img.extents[sp.first].dst_off, sp.src, sp.len, cudaMemcpyHostToDevice, ctx->stream);
+      else e = cudaMemcpyAsync(static_cast<uint8_t*>(stage.p) + sp.stage_off, sp.src, sp.len, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess && !copies.empty())
+      e = launch_gather_pages(stage.p, dev, reinterpret_cast<const PageCopy*>(static_cast<uint8_t*>(stage.p) + table_off), uint32_t(copies.size()), ctx->stream);
+    // `stage` is released in stream order when it goes out of scope
   }
   if (e == cudaSuccess) e = launch_make_seeds(dev, img.seed_jobs_off, img.n_seed_jobs, img.max_seed_chunks, ctx->stream);
   if (e != cudaSuccess) {
@@ -256,9 +295,7 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
   img.dev = dev;
   img.resident = true;
   patch_column_pointers(part, column, static_cast<const uint8_t*>(dev));
-  uint64_t n = img.meta.size();
-  for (const Extent& x : img.extents) n += x.len;
-  if (h2d_bytes) *h2d_bytes += n;
+  if (h2d_bytes) *h2d_bytes += copied;
   ctx->pending_uploads.push_back(&img);
   return FGPU_OK;
 }
@@ -739,12 +776,16 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
   {
     PhaseClock pc;
     double build_us = 0, upload_us = 0;
+    // numeric columns first: their bytes are the bulk of the transfer, which then runs while the host
+    // assembles the dictionary columns' run directories
+    for (int pass = 0; pass < 2; pass++) {
     Part* last = nullptr;
     for (const VisibleRG& v : c->rgs) {
       if (v.part == last) continue;
       last = v.part;
       for (size_t si = 0; si < c->slot_names.size(); si++) {
         const std::string& name = c->slot_names[si];
+        if ((c->slot_types[si] == ST_DICT) != (pass == 1)) continue;
         bool read = false;
         for (const VisibleRG& w : c->rgs)
           if (w.part == v.part && !((w.skip_slots >> si) & 1)) { read = true; break; }
@@ -755,6 +796,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
         const ColumnImage& img = v.part->images[name];
         if (!img.error.empty()) return fail(FGPU_ERR_UNSUPPORTED, "column " + name + ": " + img.error);
       }
+    }
     }
     if (pc.on && c->h2d_bytes) {
       char buf[128];

@@ -2002,6 +2002,28 @@ cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t s
   return cudaGetLastError();
 }
 
+// ---- PLAIN pages: raw chunk bytes -> dense value array (one CTA per page, unaligned source) ----
+__global__ void k_gather_pages(const uint8_t* __restrict__ stage, uint8_t* __restrict__ image, const PageCopy* __restrict__ table) {
+  const PageCopy c = table[blockIdx.x];
+  const uint8_t* src = stage + c.src_off;
+  const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(src) & 7u);
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(src - a);
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(image + c.dst_off);
+  const uint64_t n = c.len >> 3;
+  if (a == 0) {
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = w[i];
+  } else {
+    const uint32_t sh = a * 8u;
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = (w[i] >> sh) | (w[i + 1] << (64u - sh));  // (the span has 16 bytes of slack)
+  }
+}
+
+cudaError_t launch_gather_pages(const void* stage, void* image, const PageCopy* table, uint32_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_gather_pages<<<n, 256, 0, st>>>(static_cast<const uint8_t*>(stage), static_cast<uint8_t*>(image), table);
+  return cudaGetLastError();
+}
+
 // ---- cursor seeds from an uploaded run directory (one thread per 128-row chunk, binary search) ----
 // Same result as the host's make_seeds (part_store.cpp): the run that holds the chunk's first value.
 __global__ void k_make_seeds(uint8_t* base, const SeedJob* jobs) {

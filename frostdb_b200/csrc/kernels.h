@@ -25,6 +25,7 @@ cudaError_t runs_blocks_per_sm(const RunsDesc& d, int nl, int nk, int na, int* p
 cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st);
 cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t st);
+cudaError_t launch_gather_pages(const void* stage, void* image, const PageCopy* table, uint32_t n, cudaStream_t st);
 cudaError_t launch_make_seeds(void* image, uint64_t jobs_off, uint32_t n_jobs, uint32_t max_chunks, cudaStream_t st);
 cudaError_t launch_decode(const ChunkDesc& c, int32_t* out_i32, long long* out_i64, uint8_t* out_valid, int sm_count,
                           cudaStream_t st);

@@ -561,7 +561,8 @@ bool walk_hybrid(const uint8_t* data, uint32_t len, int w, uint32_t count, uint3
           uint64_t bit = uint64_t(i) * uint64_t(w);
           uint64_t word = 0;
           const uint8_t* q = p + (bit >> 3);
-          for (int b = 0; b < 8 && q + b < end; b++) word |= uint64_t(q[b]) << (8 * b);
+          if (end - q >= 8) std::memcpy(&word, q, 8);
+          else for (int b = 0; b < 8 && q + b < end; b++) word |= uint64_t(q[b]) << (8 * b);
           uint32_t v = w == 0 ? 0u : uint32_t((word >> (bit & 7)) & ((w >= 32 ? 0xffffffffull : ((1ull << w) - 1))));
           push_rle(start0 + produced + i, v);
         }

@@ -128,8 +128,8 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   std::vector<uint64_t> valid;  // bitset, only when max_def == 1
   std::vector<uint32_t> page_nn(cm.pages.size());
   uint32_t n_values = n_rows;
+  bool all_present = false;  // optional column whose definition levels are one run of 1s per page: no bitset needed
   if (leaf.max_def == 1) {
-    valid.assign((size_t(n_rows) + 63) / 64 + 1, 0);
     uint32_t row = 0;
     for (size_t p = 0; p < cm.pages.size(); p++) {
       const PageInfo& pg = cm.pages[p];
@@ -146,6 +146,16 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
       (void)page_start;
     }
     if (row != n_rows) { out->error = "definition levels do not cover the row group"; return; }
+    all_present = defruns.size() == 1 && (defruns[0].meta & 1u) == 0 && defruns[0].val == 1;
+    for (size_t p = 0; p < cm.pages.size() && all_present; p++)
+      if (cm.pages[p].num_nulls > 0) {
+        out->error = "page num_nulls disagrees with its definition levels";
+        return;
+      }
+  }
+  if (leaf.max_def == 1 && !all_present) {
+    valid.assign((size_t(n_rows) + 63) / 64 + 1, 0);
+    uint32_t row = 0;
     for (size_t k = 0; k < defruns.size(); k++) {
       const HostRun& r = defruns[k];
       uint32_t end = (k + 1 < defruns.size()) ? defruns[k + 1].start : n_rows;
@@ -243,8 +253,10 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
 
   // ---- chunk seeds ------------------------------------------------------------------------------
   const uint32_t n_chunks = n_tiles;  // `tile_rows` is the seed granularity (kIndexRows)
-  std::vector<uint32_t> chunk_val0(n_chunks);
-  if (has_nulls) {
+  std::vector<uint32_t> chunk_val0((has_nulls || !w.device_seeds) ? n_chunks : 0);
+  if (!has_nulls && w.device_seeds) {
+    // k_make_seeds derives chunk * 128 itself
+  } else if (has_nulls) {
     uint64_t acc = 0;
     for (uint32_t t = 0; t < n_chunks; t++) {
       chunk_val0[t] = uint32_t(acc);
