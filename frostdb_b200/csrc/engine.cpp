@@ -128,6 +128,25 @@ struct fgpu_ctx {
   std::mutex mu;
   std::map<std::string, Table> tables;
   std::vector<ColumnImage*> pending_uploads;  // staging to release after the next stream sync
+  // page-locked arena for column metadata on its way to the device: a pageable source would make every
+  // cudaMemcpyAsync wait for the transfers queued before it.  Reset by release_staging() after a sync.
+  uint8_t* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
+  void* arena_take(size_t n) {
+    if (!arena) {
+      size_t want = size_t(64) << 20;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&arena), want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        arena = nullptr;
+        return nullptr;
+      }
+      arena_cap = want;
+    }
+    size_t off = (arena_used + 63) & ~size_t(63);
+    if (off + n > arena_cap) return nullptr;  // caller falls back to the pageable source
+    arena_used = off + n;
+    return arena + off;
+  }
   // page-locked scratch for the per-query descriptor upload and the counters read-back (guarded by mu)
   uint8_t* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -242,7 +261,12 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
   if (img.resident) return FGPU_OK;
   void* dev = nullptr;
   CUDA_TRY(cudaMallocAsync(&dev, img.dev_bytes, ctx->stream));
-  cudaError_t e = cudaMemcpyAsync(dev, img.meta.data(), img.meta.size(), cudaMemcpyHostToDevice, ctx->stream);
+  const void* meta_src = img.meta.data();
+  if (void* pin = ctx->arena_take(img.meta.size())) {
+    std::memcpy(pin, img.meta.data(), img.meta.size());
+    meta_src = pin;
+  }
+  cudaError_t e = cudaMemcpyAsync(dev, meta_src, img.meta.size(), cudaMemcpyHostToDevice, ctx->stream);
   // PLAIN pages: neighbouring page payloads (separated by a page header) travel as ONE transfer of the
   // raw bytes into a staging buffer and are gathered into the dense value array on the device; a payload
   // without neighbours goes straight to its place.
@@ -273,8 +297,14 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
     const uint64_t table_off = stage_bytes;
     if (!copies.empty() && e == cudaSuccess) {
       e = stage.alloc(stage_bytes + copies.size() * sizeof(PageCopy), ctx->stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(static_cast<uint8_t*>(stage.p) + table_off, copies.data(), copies.size() * sizeof(PageCopy), cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) {
+        const void* tsrc = copies.data();
+        if (void* pin = ctx->arena_take(copies.size() * sizeof(PageCopy))) {
+          std::memcpy(pin, copies.data(), copies.size() * sizeof(PageCopy));
+          tsrc = pin;
+        }
+        e = cudaMemcpyAsync(static_cast<uint8_t*>(stage.p) + table_off, tsrc, copies.size() * sizeof(PageCopy), cudaMemcpyHostToDevice, ctx->stream);
+      }
     }
     for (const Span& sp : spans) {
       if (e != cudaSuccess) break;
@@ -302,6 +332,7 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
 
 // After the stream has been synchronised the host staging of uploaded columns can go.
 void release_staging(fgpu_ctx* ctx) {
+  ctx->arena_used = 0;
   for (ColumnImage* img : ctx->pending_uploads) {
     std::vector<uint8_t>().swap(img->meta);
     std::vector<Extent>().swap(img->extents);
@@ -1669,6 +1700,7 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->scratch) cudaFreeHost(ctx->scratch);
+  if (ctx->arena) cudaFreeHost(ctx->arena);
   delete ctx;
   return FGPU_OK;
 }
