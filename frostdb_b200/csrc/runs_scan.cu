@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
 
   // ---- prefetch iterator: walks the warp's spans block by block, D - 1 blocks ahead of the consumer ----
   uint32_t i_span = gw, i_rg = 0, i_row = 0, i_end = 0;
-  const uint8_t* i_col[NC];
+  const uint8_t* i_src[NC];  // this lane's next 16-byte piece of every staged column (null: not staged here)
   auto issue_open = [&]() {  // i_span < n_spans: position on the first block of the span
     while (i_span >= __ldg(d.rg_first_span + i_rg + 1)) i_rg++;
     const RunsRg* R = d.rgs + i_rg;
@@ -65,24 +65,35 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
     i_row = (i_span - __ldg(d.rg_first_span + i_rg)) * span_rows;
     i_end = min(n_rows, i_row + span_rows);
 #pragma unroll
-    for (int c = 0; c < NC; c++) i_col[c] = (uint32_t(c) < n_cols) ? reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->col[c]))) : nullptr;
+    for (int c = 0; c < NC; c++) {
+      const uint8_t* col = (uint32_t(c) < n_cols) ? reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->col[c]))) : nullptr;
+      i_src[c] = col ? col + size_t(i_row) * 8u + uint32_t(lane) * 16u : nullptr;
+    }
   };
   auto issue_block = [&](uint32_t rs) {
     if (i_span < d.n_spans) {
-      const uint32_t n = min(BR, i_end - i_row);
+      const uint32_t n = i_end - i_row;  // rows left in the span
       const uint32_t dst = ring_s + rs * slot_bytes + uint32_t(lane) * 16u;
 #pragma unroll
       for (int c = 0; c < NC; c++) {
-        if (uint32_t(c) < n_cols && i_col[c] != nullptr) {  // (null: a leaf column this row group does not need)
-          const uint8_t* src = i_col[c] + size_t(i_row) * 8u + uint32_t(lane) * 16u;
+        if (i_src[c] != nullptr) {
+          const uint8_t* src = i_src[c];
           const uint32_t dc = dst + uint32_t(c) * col_bytes;
-          if (n == BR) {
-            const uint32_t iters = BR >> 6;
-#pragma unroll 4
-            for (uint32_t j = 0; j < iters; j++) cp_async16(dc + j * 512u, src + j * 512u);
+          if (n >= BR) {
+            if (BR == 256u) {
+              cp_async16(dc, src);
+              cp_async16(dc + 512u, src + 512);
+              cp_async16(dc + 1024u, src + 1024);
+              cp_async16(dc + 1536u, src + 1536);
+            } else {
+              const uint32_t iters = BR >> 6;
+#pragma unroll 2
+              for (uint32_t j = 0; j < iters; j++) cp_async16(dc + j * 512u, src + j * 512u);
+            }
           } else {
             for (uint32_t o = uint32_t(lane) * 16u; o < n * 8u; o += 512u) cp_async16(dc + o - uint32_t(lane) * 16u, src + o - uint32_t(lane) * 16u);
           }
+          i_src[c] = src + size_t(BR) * 8u;
         }
       }
       i_row += BR;
@@ -160,18 +171,6 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
         }
       }
     };
-    // dense slot of row r, walking from the cursors (which sit on a row <= r)
-    auto lane_slot = [&](uint32_t r) -> uint32_t {
-      uint32_t slot = 0;
-#pragma unroll
-      for (int k = 0; k < NK; k++) {
-        uint32_t i = kk[k];
-        while (r >= __ldg(&runs[k][i + 1].start)) i++;
-        slot += (__ldg(&runs[k][i].val) + 1u) * d.stride[k];
-      }
-      return slot;
-    };
-
     for (uint32_t r0 = row0; r0 < span_end; r0 += BR) {
       issue_block(rs_ahead);
       rs_ahead = (rs_ahead + 1 == D) ? 0 : rs_ahead + 1;
@@ -196,89 +195,57 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
         }
         return act;
       };
+      // The block is consumed segment by segment: a segment is the stretch of rows up to the nearest run
+      // end of any key column (or the block end), i.e. rows of ONE group.  Its whole 32-row steps run
+      // unmasked; the partial steps at its two ends are masked by row index.  A step that holds several
+      // run ends is simply visited once per segment.
       const uint32_t rend = min(span_end, r0 + BR);
-      const int steps = int((rend - r0 + 31u) >> 5);
-      int s = 0;
-      while (s < steps) {
-        uint32_t row = r0 + uint32_t(s) * 32u;
+      const uint32_t idx0 = uint32_t(lane);
+      uint32_t row = r0;
+      while (row < rend) {
         advance(row);
-        uint32_t safe = rend, us = 0;
+        uint32_t seg_end = rend, us = 0;
 #pragma unroll
         for (int k = 0; k < NK; k++) {
-          safe = min(safe, kend[k]);
+          seg_end = min(seg_end, kend[k]);
           us += kadd[k];
         }
         if (us != cs) {
           if (cs != kNoSlot) flush();
           cs = us;
         }
-        // ---- whole steps inside the running group ----
-        const int e = s + int((safe - row) >> 5);
-        if (all_pass) {
-          cnt += uint32_t(e - s);
-#pragma unroll 4
-          for (; s < e; s++) {
+        const uint32_t a = row - r0, b = seg_end - r0;  // block-relative rows [a, b)
+        const uint32_t sa = (a + 31u) >> 5, sb = b >> 5;  // whole steps [sa, sb)
+        auto masked_step = [&](uint32_t s) {
+          const bool in = (s * 32u + idx0 - a) < (b - a);
+          const bool act = in && (all_pass || passes(int(s)));
+          cnt += act ? 1u : 0u;
 #pragma unroll
-            for (int a = 0; a < NA; a++) part[a] += lds64(acol[a] + uint32_t(s) * 256u);
-          }
+          for (int q = 0; q < NA; q++) part[q] += act ? lds64(acol[q] + s * 256u) : 0ull;
+        };
+        if (sa > sb) {
+          masked_step(a >> 5);  // the segment lies inside one step
         } else {
-#pragma unroll 2
-          for (; s < e; s++) {
-            const bool act = passes(s);
-            cnt += act ? 1u : 0u;
+          if (a & 31u) masked_step(a >> 5);
+          if (all_pass) {
+            cnt += sb - sa;
+#pragma unroll 4
+            for (uint32_t s = sa; s < sb; s++) {
 #pragma unroll
-            for (int a = 0; a < NA; a++) part[a] += act ? lds64(acol[a] + uint32_t(s) * 256u) : 0ull;
-          }
-        }
-        if (s >= steps) break;
-        // ---- the step that holds row `safe`: lanes below it still belong to the running group ----
-        row = r0 + uint32_t(s) * 32u;
-        const uint32_t r = row + uint32_t(lane);
-        const bool act = r < rend && (all_pass || passes(s));
-        const bool old = act && r < safe;
-        unsigned long long v[NA > 0 ? NA : 1];
-#pragma unroll
-        for (int a = 0; a < NA; a++) v[a] = lds64(acol[a] + uint32_t(s) * 256u);
-        cnt += old ? 1u : 0u;
-#pragma unroll
-        for (int a = 0; a < NA; a++) part[a] += old ? v[a] : 0ull;
-        if (safe < rend) {
-          advance(safe);
-          uint32_t safe2 = rend, us2 = 0;
-#pragma unroll
-          for (int k = 0; k < NK; k++) {
-            safe2 = min(safe2, kend[k]);
-            us2 += kadd[k];
-          }
-          const bool fresh = act && !old;
-          if (safe2 >= min(row + 32u, rend)) {  // one boundary in this step: the rest is one group
-            if (us2 != cs) {
-              flush();
-              cs = us2;
+              for (int q = 0; q < NA; q++) part[q] += lds64(acol[q] + s * 256u);
             }
-            cnt += fresh ? 1u : 0u;
-#pragma unroll
-            for (int a = 0; a < NA; a++) part[a] += fresh ? v[a] : 0ull;
           } else {
-            // several run ends inside one step (runs shorter than a warp): one slot per lane, the
-            // groups become the running group one after the other
-            const uint32_t slot = fresh ? lane_slot(r) : 0u;
-            unsigned rem = __ballot_sync(FULL, fresh);
-            while (rem) {
-              const uint32_t s0 = __shfl_sync(FULL, slot, __ffs(rem) - 1);
-              const bool mine = fresh && slot == s0;
-              if (s0 != cs) {
-                flush();
-                cs = s0;
-              }
-              cnt += mine ? 1u : 0u;
+#pragma unroll 2
+            for (uint32_t s = sa; s < sb; s++) {
+              const bool act = passes(int(s));
+              cnt += act ? 1u : 0u;
 #pragma unroll
-              for (int a = 0; a < NA; a++) part[a] += mine ? v[a] : 0ull;
-              rem &= ~__ballot_sync(FULL, mine);
+              for (int q = 0; q < NA; q++) part[q] += act ? lds64(acol[q] + s * 256u) : 0ull;
             }
           }
+          if (b & 31u) masked_step(sb);
         }
-        s++;
+        row = seg_end;
       }
       __syncwarp();  // every lane is done with ring slot rs before it is refilled
       rs = (rs + 1 == D) ? 0 : rs + 1;
