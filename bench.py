@@ -365,12 +365,22 @@ def main():
         peak, peak_src = measured_peak()
         avg_scan_ms = float(np.mean(scan_ms))
         achieved = alg_bytes / (avg_scan_ms * 1e-3) / 1e9 if avg_scan_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this same
+        # workload (profiles/r1_traffic.json), only when the launch processes the same bytes
+        traffic = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)
+            if tr["workload_rows_per_gpu"] == rows_per_gpu and abs(tr["algorithmic_bytes"] - alg_bytes) <= 0.01 * alg_bytes:
+                traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(rows_per_gpu, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fgpu::k_runs (sorted-run scan; fgpu::k_scan takes unsorted / nullable-key row groups)", "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes),
+                         "traffic": traffic, "kernel": "fgpu::k_runs (sorted-run scan; fgpu::k_scan takes unsorted / nullable-key row groups)", "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes),
                          "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "groups": int(st["groups"]), "rows_selected_per_gpu": int(st["rows_selected"]),
