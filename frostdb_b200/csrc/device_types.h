@@ -220,6 +220,7 @@ struct RunsDesc {
   uint32_t n_ring, n_cols;
   uint32_t leaf_col[kRunsLeaves], agg_col[kRunsAggs];  // index into RunsRg::col
   uint32_t stride[kRunsKeys];                           // dense-table stride of every key
+  uint32_t agg_func[kRunsAggs];                         // AggFunc | is_float << 8 (general-reducer instances)
   const RunsRg* rgs;
   const uint32_t* rg_first_span;  // [n_rg + 1]
   unsigned long long* t_rows;

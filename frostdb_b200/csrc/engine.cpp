@@ -1113,6 +1113,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   RunsBatch batches[1];
   int runs_nl = 0, runs_nk = 0, runs_na = 0;
   int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
+  uint32_t runs_agg_func[kRunsAggs] = {0};
   bool runs_q = q.kind != FGPU_PLAN_FILTER && qd.fast_ok && !getenv("FROSTGPU_NO_RUNS");
   if (runs_q) {
     for (int l = 0; l < n_leaves && runs_q; l++) {
@@ -1122,8 +1123,9 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     }
     for (int a = 0; a < qd.n_aggs && runs_q; a++) {
       if (qd.aggs[a].func == FGPU_AGG_COUNT) continue;
-      if (qd.aggs[a].func != FGPU_AGG_SUM || qd.aggs[a].is_float || runs_na >= kRunsAggs) { runs_q = false; break; }
+      if ((qd.aggs[a].func != FGPU_AGG_SUM && qd.aggs[a].func != FGPU_AGG_MIN && qd.aggs[a].func != FGPU_AGG_MAX) || runs_na >= kRunsAggs) { runs_q = false; break; }
       runs_agg_slot[runs_na] = qd.prog[qd.aggs[a].prog_off].slot;
+      runs_agg_func[runs_na] = uint32_t(qd.aggs[a].func) | (qd.aggs[a].is_float ? 0x100u : 0u);
       runs_agg_index[runs_na++] = a;
     }
     if (qd.n_keys > kRunsKeys) runs_q = false;
@@ -1140,7 +1142,10 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       };
       B.nl = runs_nl;
       for (int l = 0; l < B.nl; l++) B.rd.leaf_col[l] = col_of(runs_leaf_slot[l]);
-      for (int a = 0; a < runs_na; a++) B.rd.agg_col[a] = col_of(runs_agg_slot[a]);
+      for (int a = 0; a < runs_na; a++) {
+        B.rd.agg_col[a] = col_of(runs_agg_slot[a]);
+        B.rd.agg_func[a] = runs_agg_func[a];
+      }
       for (int k = 0; k < runs_nk; k++) B.rd.stride[k] = qd.keys[k].dense_stride;
     }
   }

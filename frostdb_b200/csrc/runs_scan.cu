@@ -21,6 +21,7 @@
 
 #include "device_types.h"
 #include "kernels.h"
+#include "agg_ops.cuh"
 
 namespace fgpu {
 namespace {
@@ -44,7 +45,9 @@ __device__ __forceinline__ unsigned long long lds64(uint32_t a) {
   return v;
 }
 
-template <int NL, int NK, int NA>
+// GEN = false: every stored aggregate is Sum(int64) (plain 64-bit adds, the headline shape).
+// GEN = true: Sum / Min / Max over int64 or float64 through the shared reducers (agg_ops.cuh).
+template <int NL, int NK, int NA, bool GEN>
 __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant__ RunsDesc d) {
   extern __shared__ __align__(128) uint8_t dyn[];
   constexpr int NC = (NL + NA) > 0 ? (NL + NA) : 1;
@@ -111,21 +114,43 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
   // ---- running group (warp-uniform slot, per-lane partials) ----
   uint32_t cs = kNoSlot, cnt = 0, sel = 0;
   unsigned long long part[NA > 0 ? NA : 1];
+  uint32_t afunc[NA > 0 ? NA : 1];
+  bool aflt[NA > 0 ? NA : 1];
 #pragma unroll
-  for (int a = 0; a < NA; a++) part[a] = 0;
+  for (int a = 0; a < NA; a++) {
+    afunc[a] = GEN ? (d.agg_func[a] & 0xffu) : 1u;
+    aflt[a] = GEN && (d.agg_func[a] >> 8) != 0;
+    part[a] = GEN ? (unsigned long long)agg_identity(uint8_t(afunc[a]), aflt[a]) : 0ull;
+  }
+  // folds value bits v into the partial of aggregate q when act
+  auto fold = [&](int q, bool act, unsigned long long v) {
+    if constexpr (GEN) {
+      if (act) part[q] = (unsigned long long)agg_combine(uint8_t(afunc[q]), aflt[q], (long long)part[q], (long long)v);
+    } else {
+      part[q] += act ? v : 0ull;
+    }
+  };
   auto flush = [&]() {
     const uint32_t tt = __reduce_add_sync(FULL, cnt);
-    if (tt == 0) return;  // Sum only: a group that received no row has nothing to add
+    if (tt == 0) return;  // a group that received no row leaves the table untouched
     if (lane == 0) atomicAdd(d.t_rows + cs, (unsigned long long)tt);
     sel += tt;
     cnt = 0;
 #pragma unroll
     for (int a = 0; a < NA; a++) {
       unsigned long long v = part[a];
+      if constexpr (GEN) {
 #pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(d.t_agg[a] + cs), v);
-      part[a] = 0;
+        for (int o = 16; o; o >>= 1)
+          v = (unsigned long long)agg_combine(uint8_t(afunc[a]), aflt[a], (long long)v, (long long)__shfl_xor_sync(FULL, v, o));
+        if (lane == 0) apply_agg(uint8_t(afunc[a]), aflt[a], d.t_agg[a] + cs, (long long)v);
+        part[a] = (unsigned long long)agg_identity(uint8_t(afunc[a]), aflt[a]);
+      } else {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(d.t_agg[a] + cs), v);
+        part[a] = 0;
+      }
     }
   };
 
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
           const bool act = in && (all_pass || passes(int(s)));
           cnt += act ? 1u : 0u;
 #pragma unroll
-          for (int q = 0; q < NA; q++) part[q] += act ? lds64(acol[q] + s * 256u) : 0ull;
+          for (int q = 0; q < NA; q++) fold(q, act, lds64(acol[q] + s * 256u));
         };
         if (sa > sb) {
           masked_step(a >> 5);  // the segment lies inside one step
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
 #pragma unroll 4
             for (uint32_t s = sa; s < sb; s++) {
 #pragma unroll
-              for (int q = 0; q < NA; q++) part[q] += lds64(acol[q] + s * 256u);
+              for (int q = 0; q < NA; q++) fold(q, true, lds64(acol[q] + s * 256u));
             }
           } else {
 #pragma unroll 2
@@ -240,7 +265,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
               const bool act = passes(int(s));
               cnt += act ? 1u : 0u;
 #pragma unroll
-              for (int q = 0; q < NA; q++) part[q] += act ? lds64(acol[q] + s * 256u) : 0ull;
+              for (int q = 0; q < NA; q++) fold(q, act, lds64(acol[q] + s * 256u));
             }
           }
           if (b & 31u) masked_step(sb);
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
 }
 
 template <int NL, int NK>
-cudaError_t launch_na(const RunsDesc& d, int na, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
+cudaError_t launch_na(const RunsDesc& d, int na, bool gen, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
   auto go = [&](auto kern) -> cudaError_t {
     if (query_only) {  // per kernel instance: attribute and occupancy are looked up once per shared-memory size
       static size_t cfg_smem = 0, occ_smem = ~size_t(0);
@@ -277,26 +302,29 @@ cudaError_t launch_na(const RunsDesc& d, int na, dim3 grid, size_t smem, cudaStr
     kern<<<grid, kRunsThreads, smem, st>>>(d);
     return cudaGetLastError();
   };
+  if (gen && na > 0) return na == 1 ? go(k_runs<NL, NK, 1, true>) : go(k_runs<NL, NK, 2, true>);
   switch (na) {
-    case 0: return go(k_runs<NL, NK, 0>);
-    case 1: return go(k_runs<NL, NK, 1>);
-    default: return go(k_runs<NL, NK, 2>);
+    case 0: return go(k_runs<NL, NK, 0, false>);
+    case 1: return go(k_runs<NL, NK, 1, false>);
+    default: return go(k_runs<NL, NK, 2, false>);
   }
 }
 template <int NL>
-cudaError_t launch_nk(const RunsDesc& d, int nk, int na, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
+cudaError_t launch_nk(const RunsDesc& d, int nk, int na, bool gen, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
   switch (nk) {
-    case 0: return launch_na<NL, 0>(d, na, grid, smem, st, query_only, per_sm);
-    case 1: return launch_na<NL, 1>(d, na, grid, smem, st, query_only, per_sm);
-    case 2: return launch_na<NL, 2>(d, na, grid, smem, st, query_only, per_sm);
-    default: return launch_na<NL, 3>(d, na, grid, smem, st, query_only, per_sm);
+    case 0: return launch_na<NL, 0>(d, na, gen, grid, smem, st, query_only, per_sm);
+    case 1: return launch_na<NL, 1>(d, na, gen, grid, smem, st, query_only, per_sm);
+    case 2: return launch_na<NL, 2>(d, na, gen, grid, smem, st, query_only, per_sm);
+    default: return launch_na<NL, 3>(d, na, gen, grid, smem, st, query_only, per_sm);
   }
 }
 cudaError_t launch_nl(const RunsDesc& d, int nl, int nk, int na, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
+  bool gen = false;  // any reducer other than Sum(int64)
+  for (int a = 0; a < na; a++) gen = gen || d.agg_func[a] != 1u;
   switch (nl) {
-    case 0: return launch_nk<0>(d, nk, na, grid, smem, st, query_only, per_sm);
-    case 1: return launch_nk<1>(d, nk, na, grid, smem, st, query_only, per_sm);
-    default: return launch_nk<2>(d, nk, na, grid, smem, st, query_only, per_sm);
+    case 0: return launch_nk<0>(d, nk, na, gen, grid, smem, st, query_only, per_sm);
+    case 1: return launch_nk<1>(d, nk, na, gen, grid, smem, st, query_only, per_sm);
+    default: return launch_nk<2>(d, nk, na, gen, grid, smem, st, query_only, per_sm);
   }
 }
 

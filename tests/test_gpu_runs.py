@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pyarrow as pa
 import pytest
 
 from frostdb_b200 import _lib
@@ -17,7 +18,7 @@ from tests.util import label_values, rows_of
 pytestmark = pytest.mark.gpu
 
 
-def sorted_columns(n, seed, *, t0=0, cards=(5, 23), run_scale=1.0, third=None):
+def sorted_columns(n, seed, *, t0=0, cards=(5, 23), run_scale=1.0, third=None, with_float=False):
     """Non-null label columns a, b (and optionally c) whose sort leaves runs of very different lengths."""
     rng = np.random.default_rng(seed)
     cols = {
@@ -33,6 +34,8 @@ def sorted_columns(n, seed, *, t0=0, cards=(5, 23), run_scale=1.0, third=None):
     cols["labels.b"] = ((g % cards[1]).astype(np.int32), label_values(cards[1]))
     if third:
         cols["labels.c"] = (rng.integers(0, third, n).astype(np.int32), label_values(third))
+    if with_float:
+        cols["floatvalue"] = pa.array((rng.integers(-10**6, 10**6, n).astype(np.float64)) / 997.0)
     return cols
 
 
@@ -167,3 +170,25 @@ def test_without_statistics_nothing_is_pruned(pair):
     run3(p, lambda q: q.Filter(f).Aggregate(AGGS, KEYS))
     st = scan_stats(p, f, AGGS, KEYS)
     assert st["row_groups_pruned"] == 0
+
+
+def test_min_max_and_float_aggregates_on_sorted_parts(pair):
+    p = pair("runs_minmax", dp.SampleDefinitionWithFloat())
+    n = 70_001
+    for i in range(3):
+        p.insert(sorted_columns(n, 600 + i, t0=i * n, with_float=True), row_group_size=30_000)
+    v, fv, ts = lp.Col("value"), lp.Col("floatvalue"), lp.Col("timestamp")
+    f = lp.And(ts.GtEq(lp.Literal(n // 3)), ts.Lt(lp.Literal(2 * n + 11)))
+    cases = [
+        ([lp.Sum(v), lp.Min(v)], ()), ([lp.Max(v), lp.Min(v), lp.Count(v)], ()), ([lp.Min(ts), lp.Max(ts)], ()),
+        ([lp.Sum(fv), lp.Max(v)], ("sum(floatvalue)",)), ([lp.Min(fv), lp.Max(fv)], ()), ([lp.Sum(fv), lp.Sum(v)], ("sum(floatvalue)",)),
+    ]
+    for aggs, fcols in cases:
+        for flt in (None, f):
+            build = (lambda q: q.Filter(flt).Aggregate(aggs, KEYS)) if flt is not None else (lambda q: q.Aggregate(aggs, KEYS))
+            try:
+                run3(p, build, fcols)
+            except AssertionError as e:
+                raise AssertionError(f"{[a.Name() for a in aggs]} filter={flt is not None}: {e}") from e
+    st = scan_stats(p, f, [lp.Min(fv), lp.Sum(v)], KEYS)
+    assert st["row_groups_runs"] == st["row_groups"] > 0
