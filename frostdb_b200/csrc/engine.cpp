@@ -1748,10 +1748,43 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   return FGPU_OK;
 }
 
-int32_t fgpu_part_put_arrow(fgpu_ctx*, const char*, uint64_t, uint64_t, struct ArrowSchema* schema, struct ArrowArray* array) {
-  if (schema && schema->release) schema->release(schema);
-  if (array && array->release) array->release(array);
-  return fail(FGPU_ERR_UNSUPPORTED, "L0 Arrow-record parts are not implemented yet (SURVEY.md 8f N1)");
+int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx, struct ArrowSchema* schema,
+                            struct ArrowArray* array) {
+  // the library owns both structs from here on, whatever happens
+  struct Release {
+    ArrowSchema* s; ArrowArray* a;
+    ~Release() {
+      if (s && s->release) s->release(s);
+      if (a && a->release) a->release(a);
+    }
+  } rel{schema, array};
+  if (!ctx || !table || !schema || !array) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Table& t = ctx->tables[table];
+  for (auto& p : t.parts)
+    if (p->id == part_id) return fail(FGPU_ERR_INVALID, "part id already registered");
+  auto part = std::make_unique<Part>();
+  part->id = part_id;
+  part->tx = tx;
+  std::string err;
+  if (!build_arrow_part(&t, part.get(), schema, array, &err)) return fail(FGPU_ERR_UNSUPPORTED, "Arrow part: " + err);
+  // the record's buffers go away on return: every column image is uploaded now
+  for (const std::string& col : part->columns) {
+    int32_t rc = ensure_resident(ctx, &t, part.get(), col, nullptr);
+    if (rc) {
+      free_part(ctx, part.get());
+      return rc;
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  release_staging(ctx);
+  if (e != cudaSuccess) {
+    free_part(ctx, part.get());
+    return fail(FGPU_ERR_CUDA, std::string("part upload: ") + cudaGetErrorString(e));
+  }
+  t.parts.push_back(std::move(part));
+  return FGPU_OK;
 }
 
 int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstring>
 #include <sstream>
+#include <unordered_map>
 
 namespace fgpu {
 namespace {
@@ -357,6 +358,32 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   if (out->dev_def_seeds >= 0) out->meta_bytes += uint64_t(n_chunks) * sizeof(Seed);
 }
 
+// Closes a column image: seed jobs table, final offsets of the extent and device-only regions.
+void finish_image(ImageWriter& w, ColumnImage& img, Part* part, const std::string& column) {
+  if (!w.jobs.empty()) {
+    img.seed_jobs_off = uint64_t(w.section(w.jobs.data(), w.jobs.size() * sizeof(SeedJob)));
+    img.n_seed_jobs = uint32_t(w.jobs.size());
+    for (const SeedJob& j : w.jobs) img.max_seed_chunks = std::max(img.max_seed_chunks, j.n_chunks);
+  }
+  if (img.meta.empty()) img.meta.resize(kAlign, 0);
+  // rebase extent offsets behind the (128-aligned) meta region, the device-only region behind the extents
+  const uint64_t meta_size = (img.meta.size() + kAlign - 1) / kAlign * kAlign;
+  const uint64_t dev_base = (meta_size + w.ext_size + kAlign - 1) / kAlign * kAlign;
+  for (Extent& e : img.extents) e.dst_off += meta_size;
+  for (RowGroupHost& h : part->rgs) {
+    ChunkHost& ch = h.cols[column];
+    if (ch.off_values < -0) ch.off_values = int64_t(meta_size) + (-ch.off_values - 1);
+    if (ch.dev_seeds >= 0) ch.off_seeds = int64_t(dev_base) + ch.dev_seeds;
+    if (ch.dev_def_seeds >= 0) ch.off_def_seeds = int64_t(dev_base) + ch.dev_def_seeds;
+  }
+  for (uint32_t i = 0; i < img.n_seed_jobs; i++) {
+    SeedJob* j = reinterpret_cast<SeedJob*>(img.meta.data() + img.seed_jobs_off) + i;
+    j->seeds_off += dev_base;
+  }
+  img.dev_bytes = dev_base + w.dev_size + kAlign;
+}
+
+
 }  // namespace
 
 bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) {
@@ -409,27 +436,191 @@ void build_column(int index_rows, Table* table, Part* part, const std::string& c
     if (!ch.error.empty() && img.error.empty()) img.error = ch.error;
     h.cols[column] = std::move(ch);
   }
-  if (!w.jobs.empty()) {
-    img.seed_jobs_off = uint64_t(w.section(w.jobs.data(), w.jobs.size() * sizeof(SeedJob)));
-    img.n_seed_jobs = uint32_t(w.jobs.size());
-    for (const SeedJob& j : w.jobs) img.max_seed_chunks = std::max(img.max_seed_chunks, j.n_chunks);
+  finish_image(w, img, part, column);
+}
+
+namespace {
+
+inline bool bit_at(const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+// Integer view of an Arrow index buffer element.
+inline int64_t arrow_index(const void* buf, char fmt, int64_t i) {
+  switch (fmt) {
+    case 'c': return static_cast<const int8_t*>(buf)[i];
+    case 'C': return static_cast<const uint8_t*>(buf)[i];
+    case 's': return static_cast<const int16_t*>(buf)[i];
+    case 'S': return static_cast<const uint16_t*>(buf)[i];
+    case 'i': return static_cast<const int32_t*>(buf)[i];
+    case 'I': return static_cast<const uint32_t*>(buf)[i];
+    case 'l': return static_cast<const int64_t*>(buf)[i];
+    default: return int64_t(static_cast<const uint64_t*>(buf)[i]);
   }
-  if (img.meta.empty()) img.meta.resize(kAlign, 0);
-  // rebase extent offsets behind the (128-aligned) meta region, the device-only region behind the extents
-  const uint64_t meta_size = (img.meta.size() + kAlign - 1) / kAlign * kAlign;
-  const uint64_t dev_base = (meta_size + w.ext_size + kAlign - 1) / kAlign * kAlign;
-  for (Extent& e : img.extents) e.dst_off += meta_size;
-  for (RowGroupHost& h : part->rgs) {
-    ChunkHost& ch = h.cols[column];
-    if (ch.off_values < -0) ch.off_values = int64_t(meta_size) + (-ch.off_values - 1);
-    if (ch.dev_seeds >= 0) ch.off_seeds = int64_t(dev_base) + ch.dev_seeds;
-    if (ch.dev_def_seeds >= 0) ch.off_def_seeds = int64_t(dev_base) + ch.dev_def_seeds;
+}
+
+// One Arrow column -> one column image (one chunk).
+bool build_arrow_column(Table* table, Part* part, const std::string& name, const ::ArrowSchema* cs, const ::ArrowArray* ca,
+                        uint32_t n_rows, std::string* err) {
+  const std::string fmt = cs->format ? cs->format : "";
+  const bool is_dict = cs->dictionary != nullptr;
+  const bool is_i64 = !is_dict && fmt == "l";
+  const bool is_f64 = !is_dict && fmt == "g";
+  const bool is_str = !is_dict && (fmt == "u" || fmt == "z");
+  if (!is_dict && !is_i64 && !is_f64 && !is_str) { *err = "column " + name + ": unsupported Arrow type '" + fmt + "'"; return false; }
+  if (is_dict && (fmt.size() != 1 || std::string("cCsSiIlL").find(fmt[0]) == std::string::npos)) {
+    *err = "column " + name + ": unsupported dictionary index type '" + fmt + "'";
+    return false;
   }
-  for (uint32_t i = 0; i < img.n_seed_jobs; i++) {
-    SeedJob* j = reinterpret_cast<SeedJob*>(img.meta.data() + img.seed_jobs_off) + i;
-    j->seeds_off += dev_base;
+  if (uint64_t(ca->length) != n_rows) { *err = "column " + name + ": length differs from the record"; return false; }
+  const int64_t off = ca->offset;
+  const uint8_t* validity = (ca->n_buffers > 0 && ca->null_count != 0) ? static_cast<const uint8_t*>(ca->buffers[0]) : nullptr;
+  auto valid_at = [&](int64_t i) { return !validity || bit_at(validity, off + i); };
+
+  ColumnImage& img = part->images[name];
+  img.built = true;
+  ImageWriter w(img.meta, img.extents);
+  w.device_seeds = true;
+  ChunkHost ch;
+  ch.desc.n_rows = n_rows;
+  const uint32_t T = 128;  // seed granularity (kIndexRows)
+  const uint32_t n_chunks = (n_rows + T - 1) / T;
+
+  // ---- validity -> definition levels (the Arrow bitmap is the bit-packed level stream, LSB first) ----
+  uint32_t n_values = 0;
+  std::vector<uint8_t> defbits((size_t(n_rows) + 7) / 8 + 8, 0);
+  std::vector<uint32_t> val0(n_chunks);
+  for (uint32_t i = 0; i < n_rows; i++) {
+    if (i % T == 0) val0[i / T] = n_values;
+    if (valid_at(i)) {
+      defbits[i >> 3] |= uint8_t(1u << (i & 7));
+      n_values++;
+    }
   }
-  img.dev_bytes = dev_base + w.dev_size + kAlign;
+  const bool has_nulls = n_values != n_rows;
+  ch.null_count = int64_t(n_rows) - int64_t(n_values);
+  ch.desc.has_nulls = has_nulls ? 1 : 0;
+  ch.desc.n_values = n_values;
+
+  uint64_t val0_off = ~0ull;
+  if (has_nulls) val0_off = uint64_t(w.section(val0.data(), val0.size() * 4));
+  auto seed_job = [&](int64_t runs_off, uint32_t n_runs, uint32_t total, bool is_def) {
+    SeedJob j{};
+    j.runs_off = uint64_t(runs_off);
+    j.seeds_off = w.reserve_dev(uint64_t(n_chunks) * sizeof(Seed));
+    j.val0_off = val0_off;
+    j.n_runs = n_runs;
+    j.total = total;
+    j.n_chunks = n_chunks;
+    j.is_def = is_def ? 1 : 0;
+    w.jobs.push_back(j);
+    return int64_t(j.seeds_off);
+  };
+
+  if (is_i64 || is_f64) {
+    ch.phys = is_i64 ? PT_INT64 : PT_DOUBLE;
+    ch.desc.kind = CK_PLAIN64;
+    const int64_t* src = static_cast<const int64_t*>(ca->buffers[1]) + off;
+    std::vector<int64_t> packed;
+    const int64_t* vals = src;
+    if (has_nulls) {
+      packed.reserve(n_values);
+      for (uint32_t i = 0; i < n_rows; i++)
+        if (valid_at(i)) packed.push_back(src[i]);
+      vals = packed.data();
+    }
+    if (is_i64 && n_values > 0) {  // bounds for row-group pruning, as a Parquet writer would record them
+      int64_t mn = vals[0], mx = vals[0];
+      for (uint32_t i = 1; i < n_values; i++) { mn = std::min(mn, vals[i]); mx = std::max(mx, vals[i]); }
+      ch.has_minmax = true;
+      ch.min_bits = mn;
+      ch.max_bits = mx;
+    }
+    ch.off_values = w.section(vals, size_t(n_values) * 8);
+    ch.stored_bytes = uint64_t(n_values) * 8 + (has_nulls ? (n_rows + 7) / 8 : 0);
+  } else {
+    ch.phys = PT_BYTE_ARRAY;
+    ch.desc.kind = CK_DICT_STR;
+    GlobalDict* gd = &table->dicts[name];
+    std::vector<uint32_t> idx;  // chunk-local index of every non-null row
+    idx.reserve(n_values);
+    if (is_dict) {
+      const ::ArrowArray* da = ca->dictionary;
+      const std::string dfmt = cs->dictionary->format ? cs->dictionary->format : "";
+      if (dfmt != "u" && dfmt != "z") { *err = "column " + name + ": dictionary values must be binary/utf8, got '" + dfmt + "'"; return false; }
+      const int32_t* doff = static_cast<const int32_t*>(da->buffers[1]) + da->offset;
+      const char* dbytes = static_cast<const char*>(da->buffers[2]);
+      ch.lut_host.reserve(size_t(da->length));
+      for (int64_t i = 0; i < da->length; i++) ch.lut_host.push_back(gd->intern(dbytes ? dbytes + doff[i] : "", size_t(doff[i + 1] - doff[i])));
+      for (uint32_t i = 0; i < n_rows; i++) {
+        if (!valid_at(i)) continue;
+        int64_t v = arrow_index(ca->buffers[1], fmt[0], off + i);
+        if (v < 0 || v >= da->length) { *err = "column " + name + ": dictionary index out of range"; return false; }
+        idx.push_back(uint32_t(v));
+      }
+    } else {
+      const int32_t* soff = static_cast<const int32_t*>(ca->buffers[1]) + off;
+      const char* sbytes = static_cast<const char*>(ca->buffers[2]);
+      std::unordered_map<std::string, uint32_t> local;
+      for (uint32_t i = 0; i < n_rows; i++) {
+        if (!valid_at(i)) continue;
+        std::string v(sbytes ? sbytes + soff[i] : "", size_t(soff[i + 1] - soff[i]));
+        auto it = local.find(v);
+        if (it == local.end()) {
+          it = local.emplace(v, uint32_t(ch.lut_host.size())).first;
+          ch.lut_host.push_back(gd->intern(v.data(), v.size()));
+        }
+        idx.push_back(it->second);
+      }
+    }
+    ch.desc.dict_size = uint32_t(ch.lut_host.size());
+    // index stream: raw 32-bit indices = one bit-packed run of width 32
+    std::vector<HostRun> vruns;
+    if (n_values > 0) vruns.push_back(HostRun{0, 0, 0, 1u | (32u << 8)});
+    ch.desc.n_runs = uint32_t(vruns.size());
+    ch.desc.n_bp_runs = uint32_t(vruns.size());
+    vruns.push_back(HostRun{n_values, 0, 0, 0});
+    ch.off_values = w.section(idx.data(), idx.size() * 4);
+    ch.off_runs = w.section(vruns.data(), vruns.size() * sizeof(HostRun));
+    ch.dev_seeds = seed_job(ch.off_runs, ch.desc.n_runs, n_values, false);
+    ch.off_lut = w.section(ch.lut_host.data(), ch.lut_host.size() * 4);
+    ch.stored_bytes = uint64_t(n_values) * 4 + (has_nulls ? (n_rows + 7) / 8 : 0);
+  }
+  if (has_nulls) {
+    std::vector<HostRun> druns;
+    druns.push_back(HostRun{0, 0, 0, 1u | (1u << 8)});
+    ch.desc.n_defruns = 1;
+    druns.push_back(HostRun{n_rows, 0, 0, 0});
+    ch.off_def = w.section(defbits.data(), defbits.size());
+    ch.off_def_runs = w.section(druns.data(), druns.size() * sizeof(HostRun));
+    ch.dev_def_seeds = seed_job(ch.off_def_runs, 1, n_rows, true);
+  }
+  ch.meta_bytes = uint64_t(n_chunks) * sizeof(Seed) * ((ch.dev_seeds >= 0) + (ch.dev_def_seeds >= 0));
+  part->rgs[0].cols[name] = std::move(ch);
+  finish_image(w, img, part, name);
+  return true;
+}
+
+}  // namespace
+
+bool build_arrow_part(Table* table, Part* part, const ::ArrowSchema* schema, const ::ArrowArray* array, std::string* err) {
+  if (!schema || !array || !schema->format || std::string(schema->format) != "+s") { *err = "Arrow part must be a struct array (record batch)"; return false; }
+  if (schema->n_children != array->n_children) { *err = "Arrow schema / array children differ"; return false; }
+  if (array->length < 0 || array->length > 0x7fffffffll) { *err = "record with more than 2^31 rows"; return false; }
+  if (array->offset != 0 || array->null_count > 0) { *err = "sliced or nullable record structs are not supported"; return false; }
+  const uint32_t n_rows = uint32_t(array->length);
+  part->columns.clear();
+  part->rgs.clear();
+  if (n_rows == 0) return true;  // an empty record scans nothing
+  RowGroupHost h;
+  h.n_rows = n_rows;
+  part->rgs.push_back(std::move(h));
+  for (int64_t c = 0; c < schema->n_children; c++) {
+    const ::ArrowSchema* cs = schema->children[c];
+    const std::string name = cs->name ? cs->name : "";
+    if (name.empty()) { *err = "unnamed column in Arrow part"; return false; }
+    part->columns.push_back(name);
+    if (!build_arrow_column(table, part, name, cs, array->children[c], n_rows, err)) return false;
+  }
+  return true;
 }
 
 void patch_column_pointers(Part* part, const std::string& column, const uint8_t* base) {

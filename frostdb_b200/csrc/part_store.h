@@ -11,6 +11,7 @@
 
 #include "device_types.h"
 #include "parquet_meta.h"
+#include "../../include/frostgpu.h"
 
 namespace fgpu {
 
@@ -99,6 +100,13 @@ bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err);
 // ChunkDesc pointers are offsets until patch_column_pointers() is called.
 // device_seeds: leave the cursor seeds to k_make_seeds (ColumnImage::seed_jobs_*) instead of building them here.
 void build_column(int index_rows, Table* table, Part* part, const std::string& column, bool device_seeds = false);
+
+// L0 Arrow-record part (parts/arrow.go:14-55): one row group holding the record's rows.  Every column image
+// is built here (the record is released by the caller afterwards): int64 / float64 arrays become PLAIN
+// chunks (non-null values packed, the validity bitmap IS the bit-packed definition-level stream),
+// dictionary<int, binary|utf8> and plain binary/utf8 arrays become dictionary chunks whose index stream is
+// one 32-bit "bit-packed" run.  Returns false and sets err for unsupported layouts.
+bool build_arrow_part(Table* table, Part* part, const ::ArrowSchema* schema, const ::ArrowArray* array, std::string* err);
 
 // Patches device pointers into the column's ChunkDescs once the image lives at `dev_base`.
 void patch_column_pointers(Part* part, const std::string& column, const uint8_t* dev_base);

@@ -61,6 +61,19 @@ class GPUEngine:
         self._watermarks[table] = max(self._watermarks.get(table, 0), tx)
         return pid
 
+    def put_arrow(self, table: str, record: pa.RecordBatch, tx: Optional[int] = None, part_id: Optional[int] = None) -> int:
+        """An L0 part: the Arrow record itself (parts/arrow.go:14-55), handed over through the C Data Interface."""
+        lib = _lib.load()
+        pid = self._next_part.get(table, 0) if part_id is None else part_id
+        self._next_part[table] = max(self._next_part.get(table, 0), pid + 1)
+        if tx is None:
+            tx = self._watermarks.get(table, 0) + 1
+        schema, array = _lib.ArrowSchema(), _lib.ArrowArray()
+        record._export_to_c(C.addressof(array), C.addressof(schema))
+        _lib.check(lib.fgpu_part_put_arrow(self.handle, table.encode(), pid, tx, C.addressof(schema), C.addressof(array)))
+        self._watermarks[table] = max(self._watermarks.get(table, 0), tx)
+        return pid
+
     def drop_part(self, table: str, part_id: int) -> None:
         _lib.check(_lib.load().fgpu_part_drop(self.handle, table.encode(), part_id))
 
@@ -129,6 +142,10 @@ class Table:
 
     def InsertParquet(self, buf: bytes) -> int:
         return self.db.engine.put_parquet(self.name, buf)
+
+    def InsertRecord(self, record: pa.RecordBatch) -> int:
+        """Table.InsertRecord (table.go:505-560): the record becomes an L0 part as it is (no sort, no Parquet)."""
+        return self.db.engine.put_arrow(self.name, record)
 
 
 class DB:
