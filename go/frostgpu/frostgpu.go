@@ -16,6 +16,9 @@ import (
 	"errors"
 	"fmt"
 	"unsafe"
+
+	"github.com/apache/arrow-go/v18/arrow"
+	"github.com/apache/arrow-go/v18/arrow/cdata"
 )
 
 // Engine owns one fgpu_ctx (one GPU).
@@ -51,6 +54,23 @@ func (e *Engine) PutPart(table string, partID, tx uint64, parquet []byte) error 
 	defer C.free(unsafe.Pointer(ct))
 	rc := C.fgpu_part_put_parquet(e.ctx, ct, C.uint64_t(partID), C.uint64_t(tx),
 		(*C.uint8_t)(unsafe.Pointer(&parquet[0])), C.uint64_t(len(parquet)), C.FGPU_PUT_DEFAULT)
+	if rc != 0 {
+		return lastError(rc)
+	}
+	return nil
+}
+
+// PutRecord registers an L0 part: the Arrow record Table.InsertRecord appended (parts/arrow.go:14-55,
+// table.go:505-560), exported through the Arrow C Data Interface.  The library builds its column images
+// from the record's buffers and releases both structs before returning.
+func (e *Engine) PutRecord(table string, partID, tx uint64, rec arrow.Record) error {
+	ct := C.CString(table)
+	defer C.free(unsafe.Pointer(ct))
+	var cs cdata.CArrowSchema
+	var ca cdata.CArrowArray
+	cdata.ExportArrowRecordBatch(rec, &ca, &cs)
+	rc := C.fgpu_part_put_arrow(e.ctx, ct, C.uint64_t(partID), C.uint64_t(tx),
+		(*C.struct_ArrowSchema)(unsafe.Pointer(&cs)), (*C.struct_ArrowArray)(unsafe.Pointer(&ca)))
 	if rc != 0 {
 		return lastError(rc)
 	}
