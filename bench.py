@@ -160,7 +160,7 @@ def run_reference(args, rows_per_gpu):
 
 def workload_config(rows_per_gpu, n_gpus):
     return {"workload": f"cfg3+filter: {rows_per_gpu} rows per GPU x {n_gpus} GPU(s), Parca SampleDefinition with {N_LABELS} dynamic "
-                        "label columns, Filter(timestamp in middle 50%) + Sum(value),Count(value) GROUP BY labels.l00,labels.l01 "
+                        "label columns, Filter(timestamp in the middle 50% of the rank's own time range) + Sum(value),Count(value) GROUP BY labels.l00,labels.l01 "
                         "(<=16705 groups); parts of 4Mi rows sorted in compaction order, 1Mi-row row groups, uncompressed, DataPageV2",
             "rows_per_gpu": rows_per_gpu, "label_columns": N_LABELS, "part_rows": bd.PART_ROWS, "row_group_rows": bd.RG_ROWS,
             "l2": "inputs (>=1.6 GB projected per step per GPU) exceed the 126 MB L2; no explicit flush",
@@ -206,6 +206,7 @@ def main():
     # cross-rank dictionary ids: union of every rank's dictionary entries, in rank order, preloaded
     # before the parts are put (one-time, at upload)
     key_cols = ["labels.l00", "labels.l01"]
+    unions = {}
     if world > 1:
         for col in key_cols:
             seen, mine = set(), []
@@ -222,6 +223,7 @@ def main():
                     if v not in seen:
                         seen.add(v)
                         union.append(v)
+            unions[col] = union
             eng.dict_preload(TABLE, col, union)
     t_up = time.perf_counter()
     for b in bufs:
@@ -232,6 +234,7 @@ def main():
     scan = GPUScan(eng, TABLE, filt, _lib.PLAN_AGGREGATE, groups, aggs)
     q, keep = scan.prepare()
     tx = eng.table_watermark(TABLE)
+    q_main, tx_main = q, tx
 
     def step_single():
         res = C.c_void_p()
@@ -243,7 +246,9 @@ def main():
 
     gathered = {}
 
-    def step_multi():
+    def step_multi(q=None, tx=None):
+        q = q_main if q is None else q
+        tx = tx_main if tx is None else tx
         res, ptr, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
         _lib.check(lib.fgpu_query_execute_partial(eng.handle, q, tx, C.byref(res), C.byref(ptr), C.byref(nbytes)))
         n8 = nbytes.value // 8
@@ -299,7 +304,7 @@ def main():
     # the projected columns, PLAIN pages DMA'd straight from the host buffers — reads the result
     # record back and drops the parts again.
     e2e = None
-    if world == 1 and not os.environ.get("FROSTGPU_SKIP_E2E"):
+    if not os.environ.get("FROSTGPU_SKIP_E2E"):
         from frostdb_b200.store import PinnedBuffer
         e2e_steps = max(1, min(args.steps, env_int("FROSTGPU_E2E_STEPS", 3)))
         E2E = "bench_e2e"
@@ -312,13 +317,22 @@ def main():
         h2d = {"bytes": 0}
 
         def e2e_step():
+            for col, union in unions.items():  # (multi-rank) same dictionary ids on every rank
+                eng.dict_preload(E2E, col, union)
             for pb in pinned:
                 eng.put_parquet(E2E, pb.array, borrow=True)
-            out = []
-            scan_e.SetNext(_Collect(out))
-            scan_e.Execute(None)
-            h2d["bytes"] = scan_e.last_stats["h2d_bytes"]
-            d2h = sum(x.nbytes for x in out)
+            if world == 1:
+                out = []
+                scan_e.SetNext(_Collect(out))
+                scan_e.Execute(None)
+                h2d["bytes"] = scan_e.last_stats["h2d_bytes"]
+                d2h = sum(x.nbytes for x in out)
+            else:  # partial table per rank -> all-gather -> merge, as in the resident run
+                qe, keep_e = scan_e.prepare()
+                st_e, batches_e = step_multi(qe, eng.table_watermark(E2E))
+                lib.fgpu_query_free(qe)
+                h2d["bytes"] = st_e["h2d_bytes"]
+                d2h = sum(x.nbytes for x in batches_e)
             eng.drop_table(E2E)
             return d2h
 
@@ -330,7 +344,13 @@ def main():
             d2h = e2e_step()
         sync_all()
         de = time.perf_counter() - t0
-        e2e = {"value": rows_per_gpu * e2e_steps / de, "unit": "rows/s", "h2d_bytes_per_step": int(h2d["bytes"]),
+        tde = torch.tensor([de], dtype=torch.float64, device="cuda")
+        tb = torch.tensor([float(h2d["bytes"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tde, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        de, h2d["bytes"] = float(tde.item()), int(tb.item())
+        e2e = {"value": rows_per_gpu * world * e2e_steps / de, "unit": "rows/s", "h2d_bytes_per_step": int(h2d["bytes"]),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1000.0 * de / e2e_steps,
                "note": "every step: fgpu_part_put_parquet(BORROW_PINNED) of all parts from page-locked host memory (footer/page "
                        "parse), fgpu_query_execute (builds + uploads the projected columns, then the scan), result record read "

@@ -228,6 +228,26 @@ struct RunsDesc {
   unsigned long long* counters;
 };
 
+// ---- filter-only plans over PLAIN columns (k_take_*, take_rows.cu) -----------------------------------
+constexpr int kTakeLeaves = 2, kTakeOut = 4;
+
+struct TakeRg {
+  uint32_t n_rows;
+  uint32_t all_pass;  // 1: statistics decided every leaf (all rows pass): the span is a plain copy
+  long long lo[kTakeLeaves], hi[kTakeLeaves];
+  const uint8_t* leaf_col[kTakeLeaves];  // PLAIN int64 values of every leaf's column
+  const uint8_t* out_col[kTakeOut];      // PLAIN 8-byte values of every projected column
+};
+
+struct TakeDesc {
+  uint32_t n_rg, n_spans, span_blocks, nl, n_out, _pad;
+  const TakeRg* rgs;
+  const uint32_t* rg_first_span;      // [n_rg + 1]
+  unsigned long long* span_count;     // [n_spans + 1]: passing rows per span, then their exclusive prefix
+  unsigned long long* total;          // rows that passed (the query's counters[0])
+  long long* out_data[kTakeOut];
+};
+
 struct FinalizeDesc {
   int32_t table_mode, key_words, n_keys, n_aggs;
   uint32_t table_slots;

@@ -239,6 +239,7 @@ struct fgpu_result {
   size_t next = 0;
   bool finalized = false;
   bool rows_plan = false;
+  bool rows_no_nulls = false;  // rows plan produced by the take kernels: no projected value is NULL
 };
 
 namespace {
@@ -1287,6 +1288,69 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     rd.n_spans = spans;
   }
 
+  // ---- filter-only plans over PLAIN columns: ordered take (take_rows.cu) instead of k_rows ------------
+  TakeDesc td{};
+  std::vector<TakeRg> take_rgs;
+  std::vector<uint32_t> take_first_span;
+  bool take_q = q.kind == FGPU_PLAN_FILTER && qd.n_out >= 1 && qd.n_out <= kTakeOut && n_leaves <= kTakeLeaves &&
+                (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) && gi > 0 && !getenv("FROSTGPU_NO_TAKE");
+  for (int l = 0; l < n_leaves && take_q; l++) {
+    const LeafDesc& ld = qd.leaves[l];
+    if (ld.slot == 0xff || ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || c.leaves[size_t(l)].null_literal) take_q = false;
+  }
+  for (int o = 0; o < qd.n_out && take_q; o++)
+    if (qd.slot_type[qd.out_slot[o]] == ST_DICT) take_q = false;
+  for (int g = 0; g < gi && take_q; g++) {
+    TakeRg tr{};
+    tr.n_rows = rg_rows[size_t(g)];
+    bool all = n_leaves > 0;
+    for (int l = 0; l < n_leaves && take_q; l++) {
+      const uint8_t m = lrt[size_t(g) * n_leaves + l].mode;
+      if (m == LM_NONE) take_q = false;  // (only with pruning switched off)
+      if (m != LM_ALL) all = false;
+    }
+    tr.all_pass = all ? 1 : 0;
+    for (int l = 0; l < n_leaves && take_q; l++) {
+      const bool decided = lrt[size_t(g) * n_leaves + l].mode == LM_ALL;
+      tr.lo[l] = decided ? std::numeric_limits<int64_t>::min() : qd.leaves[l].lo_i;
+      tr.hi[l] = decided ? std::numeric_limits<int64_t>::max() : qd.leaves[l].hi_i;
+      const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.leaves[l].slot];
+      if (all) continue;  // the leaf columns are not read at all
+      if (decided) {  // its column may not even be uploaded: any evaluated leaf's column stands in below
+        tr.leaf_col[l] = nullptr;
+        continue;
+      }
+      if (d.kind != CK_PLAIN64 || d.has_nulls) take_q = false;
+      tr.leaf_col[l] = d.values;
+    }
+    for (int l = 0; l < n_leaves && take_q && !all; l++)
+      if (!tr.leaf_col[l]) tr.leaf_col[l] = tr.leaf_col[l == 0 ? 1 : 0];
+    for (int o = 0; o < qd.n_out && take_q; o++) {
+      const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.out_slot[o]];
+      if (d.kind != CK_PLAIN64 || d.has_nulls) take_q = false;
+      tr.out_col[o] = d.values;
+    }
+    take_rgs.push_back(tr);
+  }
+  if (take_q) {
+    const uint64_t warps = uint64_t(take_resident_warps(ctx->sm_count));
+    uint64_t total = 0;
+    for (const TakeRg& r : take_rgs) total += r.n_rows;
+    uint64_t span_blocks = std::min<uint64_t>(64, std::max<uint64_t>(4, total / (warps * 4 * 256)));
+    td.span_blocks = uint32_t(span_blocks);
+    const uint64_t span_rows = span_blocks * 256;
+    uint32_t spans = 0;
+    for (const TakeRg& r : take_rgs) {
+      take_first_span.push_back(spans);
+      spans += uint32_t((uint64_t(r.n_rows) + span_rows - 1) / span_rows);
+    }
+    take_first_span.push_back(spans);
+    td.n_spans = spans;
+    td.n_rg = uint32_t(take_rgs.size());
+    td.nl = uint32_t(n_leaves);
+    td.n_out = uint32_t(qd.n_out);
+  }
+
   // ---- device memory -----------------------------------------------------------------------
   const bool rows_plan = q.kind == FGPU_PLAN_FILTER;
   if (!rows_plan) {
@@ -1331,6 +1395,13 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     B.o_span = align16(B.o_rg + B.rgs.size() * sizeof(RunsRg));
     o_cnt = align16(B.o_span + B.first_span.size() * 4);
   }
+  size_t o_take_rg = 0, o_take_span = 0, o_take_count = 0;
+  if (take_q) {
+    o_take_rg = o_cnt;
+    o_take_span = align16(o_take_rg + take_rgs.size() * sizeof(TakeRg));
+    o_take_count = align16(o_take_span + take_first_span.size() * 4);
+    o_cnt = align16(o_take_count + (size_t(td.n_spans) + 1) * 8);
+  }
   // device block: [tables | counters 64 B | group counter 16 B | QueryDesc]; the host image of it lives in
   // page-locked scratch so that one asynchronous copy uploads everything
   const size_t o_qd = align16(o_cnt + 64 + 16);
@@ -1351,6 +1422,10 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     if (B.rgs.empty()) continue;
     std::memcpy(hostaux.data() + B.o_rg, B.rgs.data(), B.rgs.size() * sizeof(RunsRg));
     std::memcpy(hostaux.data() + B.o_span, B.first_span.data(), B.first_span.size() * 4);
+  }
+  if (take_q) {
+    std::memcpy(hostaux.data() + o_take_rg, take_rgs.data(), take_rgs.size() * sizeof(TakeRg));
+    std::memcpy(hostaux.data() + o_take_span, take_first_span.data(), take_first_span.size() * 4);
   }
   qd.chunks = reinterpret_cast<const ChunkDesc*>(aux + o_chunks);
   qd.leaf_rt = reinterpret_cast<const LeafRt*>(aux + o_lrt);
@@ -1382,7 +1457,18 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   if (rows_plan) {
     CUDA_TRY(cudaMemsetAsync(qd.tile_state, 0, size_t(tiles) * 8, s));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
-    CUDA_TRY(launch_rows(qdesc_dev, qd, ctx->sm_count, s));
+    if (take_q) {
+      td.rgs = reinterpret_cast<const TakeRg*>(aux + o_take_rg);
+      td.rg_first_span = reinterpret_cast<const uint32_t*>(aux + o_take_span);
+      td.span_count = reinterpret_cast<unsigned long long*>(aux + o_take_count);
+      td.total = qd.counters;
+      for (int o = 0; o < qd.n_out; o++) td.out_data[o] = static_cast<long long*>(qd.out_data[o]);
+      CUDA_TRY(launch_take(td, ctx->sm_count, s));
+      st.kernel_launches += 2;
+      res->rows_no_nulls = true;
+    } else {
+      CUDA_TRY(launch_rows(qdesc_dev, qd, ctx->sm_count, s));
+    }
   } else {
     CUDA_TRY(launch_table_init(qd, s));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
@@ -1497,6 +1583,14 @@ int32_t finalize_rows(fgpu_ctx* ctx, fgpu_result* res) {
     } else {
       col.format = ko.is_float ? "g" : "l";
       col.data.resize(R * 8);
+      if (res->rows_no_nulls) {
+        if (R) CUDA_TRY(cudaMemcpyAsync(col.data.data(), qd.out_data[o], R * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        res->stats.d2h_bytes += R * 8;
+        res->stats.algorithmic_bytes += R * 8;
+        cols.push_back(std::move(col));
+        continue;
+      }
       std::vector<uint8_t> valid(R);
       if (R) {
         CUDA_TRY(cudaMemcpyAsync(col.data.data(), qd.out_data[o], R * 8, cudaMemcpyDeviceToHost, s));

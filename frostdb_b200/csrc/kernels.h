@@ -22,6 +22,9 @@ cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, 
 constexpr int kRunsThreads = 128;
 cudaError_t launch_runs(const RunsDesc& d, int nl, int nk, int na, int sm_count, cudaStream_t st);
 cudaError_t runs_blocks_per_sm(const RunsDesc& d, int nl, int nk, int na, int* per_sm);  // resident CTAs per SM for this shape
+// filter-only plans over PLAIN columns (take_rows.cu): count per span, scan, ordered write
+cudaError_t launch_take(const TakeDesc& d, int sm_count, cudaStream_t st);
+int take_resident_warps(int sm_count);
 cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st);
 cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t st);

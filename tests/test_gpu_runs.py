@@ -192,3 +192,36 @@ def test_min_max_and_float_aggregates_on_sorted_parts(pair):
                 raise AssertionError(f"{[a.Name() for a in aggs]} filter={flt is not None}: {e}") from e
     st = scan_stats(p, f, [lp.Min(fv), lp.Sum(v)], KEYS)
     assert st["row_groups_runs"] == st["row_groups"] > 0
+
+
+def test_filter_only_plans_take_path(pair):
+    """TableScan -> Filter -> Projection(PLAIN columns): the ordered take kernels against the oracle and
+    against k_rows (FROSTGPU_NO_TAKE), over selectivities from nothing to everything."""
+    p = pair("take", dp.SampleDefinitionWithFloat())
+    n = 41_003
+    for i in range(4):
+        p.insert(sorted_columns(n, 800 + i, t0=i * n, with_float=True), row_group_size=15_000)
+    ts, v, fv = lp.Col("timestamp"), lp.Col("value"), lp.Col("floatvalue")
+    filters = [
+        ts.Lt(lp.Literal(int(0.001 * 4 * n))), ts.Lt(lp.Literal(2 * n + 7)), ts.GtEq(lp.Literal(0)), ts.Gt(lp.Literal(9 * n)),
+        v.Lt(lp.Literal(-499)), v.Lt(lp.Literal(250)), v.GtEq(lp.Literal(-500)),
+        lp.And(lp.And(ts.GtEq(lp.Literal(n // 2)), ts.Lt(lp.Literal(3 * n))), v.Gt(lp.Literal(900))),
+        lp.And(ts.LtEq(lp.Literal(10 * n)), v.Eq(lp.Literal(77))),
+    ]
+    names = ["timestamp", "value", "floatvalue"]
+    for f in filters:
+        for proj in ([ts, v], [v], [fv, ts, v]):
+            cols = [e.Name() for e in proj]
+            got, exp = p.run(lambda q: q.Filter(f).Project(*proj))
+            os.environ["FROSTGPU_NO_TAKE"] = "1"
+            try:
+                got2, _ = p.run(lambda q: q.Filter(f).Project(*proj))
+            finally:
+                os.environ.pop("FROSTGPU_NO_TAKE")
+            # order-preserving: compare WITHOUT sorting
+            def flat(batches):
+                out = []
+                for b in batches:
+                    out.extend(zip(*[b.column(b.schema.get_field_index(c)).to_pylist() for c in cols]))
+                return out
+            assert flat(got) == flat(exp) == flat(got2), f"{f.Name()} -> {cols}"
