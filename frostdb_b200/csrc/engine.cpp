@@ -779,6 +779,13 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
           if (!lh.neg) mode = disjoint ? LM_NONE : ((inside && no_nulls) ? LM_ALL : LM_EVAL);
           else mode = inside ? LM_NONE : ((disjoint && no_nulls) ? LM_ALL : LM_EVAL);
         }
+        else if (it != v.rg->cols.end() && c->slot_types[size_t(lh.slot)] == ST_DICT && lh.op == FGPU_OP_EQ &&
+                 lh.lit->lit_type == FGPU_SCALAR_STRING && it->second.has_minmax_str) {
+          // string equality against the chunk's bounding strings (binaryscalarexpr.go:98-104; bounds may be
+          // truncated by the writer, they still bound): outside them no value can be equal
+          const std::string& lit = lh.lit->lit_bytes;
+          if (lit < it->second.min_str || lit > it->second.max_str) mode = LM_NONE;
+        }
         v.leaf_mode[l] = mode;
         if (conj && mode == LM_NONE) drop = true;
       }

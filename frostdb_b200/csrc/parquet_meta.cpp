@@ -275,6 +275,11 @@ void init_chunk(const RawColumnMeta& cm, const SchemaLeaf& leaf, ChunkMeta* out)
     std::memcpy(&out->min_bits, cm.stat_min.data(), 8);
     std::memcpy(&out->max_bits, cm.stat_max.data(), 8);
   }
+  if (leaf.phys == PT_BYTE_ARRAY && !cm.stat_min.empty() && !cm.stat_max.empty()) {
+    out->has_minmax_str = true;
+    out->min_str = cm.stat_min;
+    out->max_str = cm.stat_max;
+  }
   if (cm.codec != 0) {
     out->error = "compressed column chunk (codec " + std::to_string(cm.codec) + ") is not supported";
     return;

@@ -48,6 +48,8 @@ struct ChunkMeta {
   int64_t null_count = -1;            // from chunk statistics when present
   bool has_minmax = false;            // INT64 / DOUBLE chunks: footer statistics carry both bounds
   int64_t min_bits = 0, max_bits = 0; // raw 8-byte bounds of the non-null values
+  bool has_minmax_str = false;        // BYTE_ARRAY chunks: both (possibly truncated, still bounding) strings recorded
+  std::string min_str, max_str;
   const uint8_t* dict = nullptr;      // dictionary page payload (PLAIN)
   uint32_t dict_len = 0;
   uint32_t dict_num_values = 0;

@@ -103,6 +103,9 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   out->min_bits = cm.min_bits;
   out->max_bits = cm.max_bits;
   out->null_count = (cm.null_count < 0 && leaf.max_def == 0) ? 0 : cm.null_count;
+  out->has_minmax_str = cm.has_minmax_str;
+  out->min_str = cm.min_str;
+  out->max_str = cm.max_str;
   out->desc.n_rows = n_rows;
   if (!cm.error.empty()) { out->error = cm.error; return; }
   if (leaf.phys != PT_INT64 && leaf.phys != PT_DOUBLE && leaf.phys != PT_BYTE_ARRAY) {
@@ -406,6 +409,9 @@ bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) 
       ch.max_bits = rg.chunks[c].max_bits;
       ch.null_count = rg.chunks[c].null_count;
       if (ch.null_count < 0 && part->pf.leaves[c].max_def == 0) ch.null_count = 0;  // required column
+      ch.has_minmax_str = rg.chunks[c].has_minmax_str;
+      ch.min_str = rg.chunks[c].min_str;
+      ch.max_str = rg.chunks[c].max_str;
       ch.desc.n_rows = h.n_rows;
       h.cols.emplace(part->pf.leaves[c].name, std::move(ch));
     }

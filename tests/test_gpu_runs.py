@@ -227,3 +227,22 @@ def test_filter_only_plans_take_path(pair):
                     out.extend(zip(*[b.column(b.schema.get_field_index(c)).to_pylist() for c in cols]))
                 return out
             assert flat(got) == flat(exp) == flat(got2), f"{f.Name()} -> {cols}"
+
+
+def test_string_equality_prunes_row_groups_by_bounds(pair):
+    p = pair("runs_strprune")
+    n = 60_000
+    for i in range(3):
+        p.insert(sorted_columns(n, 900 + i, t0=i * n, cards=(6, 9)), row_group_size=7_000)
+    a, b = lp.Col("labels.a"), lp.Col("labels.b")
+    for f in (a.Eq(lp.Literal("v000002")), a.Eq(lp.Literal("v000009")), a.Eq(lp.Literal("")), a.NotEq(lp.Literal("v000002")),
+              lp.And(a.Eq(lp.Literal("v000004")), lp.Col("timestamp").Lt(lp.Literal(2 * n))),
+              lp.Or(a.Eq(lp.Literal("v000000")), b.Eq(lp.Literal("v000003")))):
+        try:
+            run3(p, lambda q: q.Filter(f).Aggregate(AGGS, KEYS))
+        except AssertionError as e:
+            raise AssertionError(f"filter {f.Name()}: {e}") from e
+    st = scan_stats(p, a.Eq(lp.Literal("v000002")), AGGS, KEYS)
+    assert 0 < st["row_groups_pruned"] < 27 and st["rows_selected"] > 0
+    st = scan_stats(p, a.Eq(lp.Literal("v000009")), AGGS, KEYS)   # beyond every chunk's maximum
+    assert st["row_groups"] == 0
