@@ -202,7 +202,7 @@ struct SeedJob {
 // columns are run-length only (sorted parts) are scanned by a dedicated kernel that walks the key run
 // directories with warp-uniform cursors.  The host lists those row groups here; the rest of the table
 // goes through the general scan kernel into the same aggregate table.
-constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 2, kRunsCols = kRunsLeaves + kRunsAggs;
+constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 3, kRunsCols = kRunsLeaves + kRunsAggs;
 
 struct RunsRg {
   uint32_t n_rows;

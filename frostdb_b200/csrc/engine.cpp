@@ -435,6 +435,7 @@ struct Compiled {
   uint64_t group_bound = 0;
   uint64_t h2d_bytes = 0;  // column uploads this query triggered
   uint32_t pruned_row_groups = 0;
+  bool runs_shape = false;  // dense keys, conjunction of numeric leaves, plain aggregate inputs (any number of them)
 };
 
 int32_t compile_filter(const fgpu_query& q, int node, Compiled* c, std::map<std::string, int>& slot_of) {
@@ -1050,6 +1051,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       stored++;
       if (!(qd.aggs[a].prog_len == 1 && qd.prog[qd.aggs[a].prog_off].op == PO_LOAD)) fast = false;
     }
+    c->runs_shape = fast && !getenv("FROSTGPU_NO_FAST") ? true : false;  // the sorted-run kernel takes up to kRunsAggs reducers
     if (stored > 2) fast = false;
     qd.fast_ok = fast ? 1 : 0;
   }
@@ -1122,7 +1124,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   int runs_nl = 0, runs_nk = 0, runs_na = 0;
   int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
   uint32_t runs_agg_func[kRunsAggs] = {0};
-  bool runs_q = q.kind != FGPU_PLAN_FILTER && qd.fast_ok && !getenv("FROSTGPU_NO_RUNS");
+  bool runs_q = q.kind != FGPU_PLAN_FILTER && c.runs_shape && !getenv("FROSTGPU_NO_RUNS");
   if (runs_q) {
     for (int l = 0; l < n_leaves && runs_q; l++) {
       const LeafDesc& ld = qd.leaves[l];

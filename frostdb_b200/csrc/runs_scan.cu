@@ -302,11 +302,12 @@ cudaError_t launch_na(const RunsDesc& d, int na, bool gen, dim3 grid, size_t sme
     kern<<<grid, kRunsThreads, smem, st>>>(d);
     return cudaGetLastError();
   };
-  if (gen && na > 0) return na == 1 ? go(k_runs<NL, NK, 1, true>) : go(k_runs<NL, NK, 2, true>);
+  if (gen && na > 0) return na == 1 ? go(k_runs<NL, NK, 1, true>) : (na == 2 ? go(k_runs<NL, NK, 2, true>) : go(k_runs<NL, NK, 3, true>));
   switch (na) {
     case 0: return go(k_runs<NL, NK, 0, false>);
     case 1: return go(k_runs<NL, NK, 1, false>);
-    default: return go(k_runs<NL, NK, 2, false>);
+    case 2: return go(k_runs<NL, NK, 2, false>);
+    default: return go(k_runs<NL, NK, 3, false>);
   }
 }
 template <int NL>

@@ -182,6 +182,7 @@ def test_min_max_and_float_aggregates_on_sorted_parts(pair):
     cases = [
         ([lp.Sum(v), lp.Min(v)], ()), ([lp.Max(v), lp.Min(v), lp.Count(v)], ()), ([lp.Min(ts), lp.Max(ts)], ()),
         ([lp.Sum(fv), lp.Max(v)], ("sum(floatvalue)",)), ([lp.Min(fv), lp.Max(fv)], ()), ([lp.Sum(fv), lp.Sum(v)], ("sum(floatvalue)",)),
+        ([lp.Sum(v), lp.Min(v), lp.Max(v), lp.Count(v)], ()), ([lp.Sum(fv), lp.Min(ts), lp.Max(v)], ("sum(floatvalue)",)),
     ]
     for aggs, fcols in cases:
         for flt in (None, f):
