@@ -69,6 +69,13 @@ struct ChunkDesc {
   const Seed* def_seeds;   // has_nulls: one per 128-row chunk (val0 = non-null values before the chunk)
   const uint32_t* lut;     // CK_DICT_STR: chunk dictionary index -> global dictionary id (bit-packed runs)
   const int64_t* dict64;   // CK_DICT64: chunk dictionary values (raw 8 bytes each)
+  // CK_DICT_STR whose value AND definition-level streams are run-length only (sorted parts): one directory in
+  // ROW space, val = global dictionary id or 0xffffffff for NULL (+1 sentinel with start == n_rows), with
+  // its per-128-row seeds.  A column without NULLs aliases runs / seeds.  Null: not available.
+  const Run* row_runs;
+  const Seed* row_seeds;
+  uint32_t n_row_runs;
+  uint32_t _pad_rr;
 };
 
 enum SlotType : uint8_t { ST_I64 = 0, ST_F64 = 1, ST_DICT = 2 };

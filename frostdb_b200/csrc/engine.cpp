@@ -1246,9 +1246,10 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       for (int k = 0; k < runs_nk && runs_ok; k++) {
         const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.keys[k].slot];
         // run-length only, and runs long enough that a 32-row step rarely holds two run ends
-        if (d.kind != CK_DICT_STR || d.has_nulls || d.n_bp_runs != 0 || uint64_t(d.n_runs) * 32 > uint64_t(rg.n_rows) + 1024) runs_ok = false;
-        rr.runs[k] = d.runs;
-        rr.seeds[k] = d.seeds;
+        // (row_runs: the directory in row space; it exists when the column chunk is run-length only, NULLs included)
+        if (d.kind != CK_DICT_STR || d.row_runs == nullptr || uint64_t(d.n_row_runs) * 32 > uint64_t(rg.n_rows) + 1024) runs_ok = false;
+        rr.runs[k] = d.row_runs;
+        rr.seeds[k] = d.row_seeds;
       }
     }
     if (runs_ok) {

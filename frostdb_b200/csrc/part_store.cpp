@@ -316,11 +316,11 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
   }
   uint64_t val0_off = ~0ull;
   if (w.device_seeds && has_nulls) val0_off = uint64_t(w.section(chunk_val0.data(), chunk_val0.size() * 4));
-  auto seed_job = [&](int64_t runs_off, uint32_t n_runs, uint32_t total, bool is_def) {
+  auto seed_job = [&](int64_t runs_off, uint32_t n_runs, uint32_t total, bool is_def, bool use_val0 = true) {
     SeedJob j{};
     j.runs_off = uint64_t(runs_off);
     j.seeds_off = w.reserve_dev(uint64_t(n_chunks) * sizeof(Seed));
-    j.val0_off = val0_off;
+    j.val0_off = use_val0 ? val0_off : ~0ull;
     j.n_runs = n_runs;
     j.total = total;
     j.n_chunks = n_chunks;
@@ -328,6 +328,36 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
     w.jobs.push_back(j);
     return int64_t(j.seeds_off);
   };
+  // ---- row-space directory of a nullable dictionary column whose two streams are run-length only ----
+  // (what a sorted part leaves: NULLs first, then one run per value).  The sorted-run kernel walks it like
+  // the directory of a column without NULLs; 0xffffffff stands for NULL (contributes 0 to the dense slot).
+  std::vector<HostRun> row_runs;
+  if (out->desc.kind == CK_DICT_STR && has_nulls) {
+    bool rle_only = true;
+    for (const HostRun& r : vruns) rle_only = rle_only && (r.meta & 1u) == 0;
+    for (const HostRun& r : defruns) rle_only = rle_only && (r.meta & 1u) == 0;
+    if (rle_only) {
+      auto push = [&](uint32_t start, uint32_t val) {
+        if (!row_runs.empty() && row_runs.back().val == val) return;
+        row_runs.push_back(HostRun{start, 0, val, 0});
+      };
+      size_t vk = 0;
+      uint32_t vord = 0;  // ordinal of the next non-null value
+      for (size_t k = 0; k < defruns.size(); k++) {
+        const uint32_t s0 = defruns[k].start, e0 = (k + 1 < defruns.size()) ? defruns[k + 1].start : n_rows;
+        if (defruns[k].val == 0) { push(s0, 0xffffffffu); continue; }
+        uint32_t row = s0;
+        while (row < e0) {
+          while (vk + 1 < vruns.size() && vruns[vk + 1].start <= vord) vk++;
+          const uint32_t vend = (vk + 1 < vruns.size()) ? vruns[vk + 1].start : n_values;
+          const uint32_t take = std::min(e0 - row, vend - vord);
+          push(row, vruns[vk].val);
+          row += take;
+          vord += take;
+        }
+      }
+    }
+  }
   if (out->desc.kind != CK_PLAIN64) {
     out->desc.n_runs = uint32_t(vruns.size());
     uint32_t bp = 0;
@@ -351,6 +381,15 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
     out->off_def_runs = w.section(defruns.data(), defruns.size() * sizeof(HostRun));
     if (w.device_seeds) out->dev_def_seeds = seed_job(out->off_def_runs, out->desc.n_defruns, n_rows, true);
     else out->off_def_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
+  }
+  if (!row_runs.empty()) {
+    out->desc.n_row_runs = uint32_t(row_runs.size());
+    std::vector<Seed> seeds;
+    if (!w.device_seeds) seeds = make_seeds(row_runs, n_rows, true);
+    row_runs.push_back(HostRun{n_rows, 0, 0, 0});
+    out->off_row_runs = w.section(row_runs.data(), row_runs.size() * sizeof(HostRun));
+    if (w.device_seeds) out->dev_row_seeds = seed_job(out->off_row_runs, out->desc.n_row_runs, n_rows, true, /*use_val0=*/false);
+    else out->off_row_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
   }
   if (out->desc.kind == CK_DICT_STR) out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
   if (out->desc.kind == CK_DICT64) out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
@@ -378,6 +417,7 @@ void finish_image(ImageWriter& w, ColumnImage& img, Part* part, const std::strin
     if (ch.off_values < -0) ch.off_values = int64_t(meta_size) + (-ch.off_values - 1);
     if (ch.dev_seeds >= 0) ch.off_seeds = int64_t(dev_base) + ch.dev_seeds;
     if (ch.dev_def_seeds >= 0) ch.off_def_seeds = int64_t(dev_base) + ch.dev_def_seeds;
+    if (ch.dev_row_seeds >= 0) ch.off_row_seeds = int64_t(dev_base) + ch.dev_row_seeds;
   }
   for (uint32_t i = 0; i < img.n_seed_jobs; i++) {
     SeedJob* j = reinterpret_cast<SeedJob*>(img.meta.data() + img.seed_jobs_off) + i;
@@ -644,6 +684,17 @@ void patch_column_pointers(Part* part, const std::string& column, const uint8_t*
     c.desc.def_seeds = reinterpret_cast<const Seed*>(at(c.off_def_seeds));
     c.desc.lut = reinterpret_cast<const uint32_t*>(at(c.off_lut));
     c.desc.dict64 = reinterpret_cast<const int64_t*>(at(c.off_dict64));
+    if (c.off_row_runs >= 0) {
+      c.desc.row_runs = reinterpret_cast<const Run*>(at(c.off_row_runs));
+      c.desc.row_seeds = reinterpret_cast<const Seed*>(at(c.off_row_seeds));
+    } else if (c.desc.kind == CK_DICT_STR && !c.desc.has_nulls && c.desc.n_bp_runs == 0) {
+      c.desc.row_runs = c.desc.runs;  // no NULLs: value ordinals are rows
+      c.desc.row_seeds = c.desc.seeds;
+      c.desc.n_row_runs = c.desc.n_runs;
+    } else {
+      c.desc.row_runs = nullptr;
+      c.desc.row_seeds = nullptr;
+    }
   }
 }
 
@@ -761,6 +812,25 @@ std::string describe_part_json(const uint8_t* file, uint64_t len, int tile_rows,
           vord++;
         }
         o << "],\"tile_index_ok\":" << (tiles_ok ? "true" : "false");
+        // the row-space directory (sorted-run kernel) must say the same as the two streams it was merged from
+        if (d.row_runs) {
+          std::vector<HostRun> rr(reinterpret_cast<const HostRun*>(d.row_runs), reinterpret_cast<const HostRun*>(d.row_runs) + d.n_row_runs + 1);
+          bool ok = rr.back().start == rg.n_rows;
+          uint32_t vo = 0;
+          for (uint32_t r = 0; r < rg.n_rows && ok; r++) {
+            const uint32_t got = hybrid_value_at(nullptr, rr, r);
+            const bool valid = !d.has_nulls || hybrid_value_at(d.def, druns, r) != 0;
+            if (!valid) { ok = got == 0xffffffffu; continue; }
+            bool was_rle = false;
+            uint32_t idx = hybrid_value_at(d.values, vruns, vo++, &was_rle);
+            ok = got == (was_rle ? idx : d.lut[idx]);
+            if (r % T == 0) {
+              const Seed& sd = d.row_seeds[r / T];
+              ok = ok && sd.k < rr.size() - 1 && rr[sd.k].start <= r && rr[sd.k + 1].start > r && sd.end == rr[sd.k + 1].start && sd.val == rr[sd.k].val;
+            }
+          }
+          o << ",\"n_row_runs\":" << d.n_row_runs << ",\"row_runs_ok\":" << (ok ? "true" : "false");
+        }
       }
       o << '}';
     }

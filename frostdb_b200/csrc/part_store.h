@@ -49,6 +49,7 @@ struct ChunkHost {
   int64_t off_values = -1, off_runs = -1, off_seeds = -1, off_def = -1, off_def_runs = -1, off_def_seeds = -1, off_lut = -1,
           off_dict64 = -1;
   int64_t dev_seeds = -1, dev_def_seeds = -1;  // seeds derived on the device: offsets inside the image's device-only region
+  int64_t off_row_runs = -1, off_row_seeds = -1, dev_row_seeds = -1;  // row-space directory of a nullable run-length column
 };
 
 struct RowGroupHost {

@@ -247,3 +247,26 @@ def test_string_equality_prunes_row_groups_by_bounds(pair):
     assert 0 < st["row_groups_pruned"] < 27 and st["rows_selected"] > 0
     st = scan_stats(p, a.Eq(lp.Literal("v000009")), AGGS, KEYS)   # beyond every chunk's maximum
     assert st["row_groups"] == 0
+
+
+def test_nullable_sorted_keys_take_the_run_kernel(pair):
+    """NULL keys sort first (compaction order): levels and indices are both run-length, the host merges them
+    into one directory in row space and the row groups stay with k_runs."""
+    p = pair("runs_nullkeys")
+    n = 50_000
+    for i in range(3):
+        cols = sorted_columns(n, 950 + i, t0=i * n, cards=(4, 17))
+        rng = np.random.default_rng(i)
+        for name, pnull in (("labels.a", 0.15), ("labels.b", 0.3)):
+            idx = cols[name][0].copy()
+            idx[rng.random(n) < pnull] = -1
+            cols[name] = (idx, cols[name][1])
+        p.insert(cols, row_group_size=21_000)
+    f = lp.And(lp.Col("timestamp").GtEq(lp.Literal(n // 4)), lp.Col("timestamp").Lt(lp.Literal(2 * n + 5)))
+    for flt in (None, f):
+        build = (lambda q: q.Filter(flt).Aggregate(AGGS, KEYS)) if flt is not None else (lambda q: q.Aggregate(AGGS, KEYS))
+        run3(p, build)
+        build1 = (lambda q: q.Filter(flt).Aggregate(AGGS, [lp.Col("labels.a")])) if flt is not None else (lambda q: q.Aggregate(AGGS, [lp.Col("labels.a")]))
+        run3(p, build1)
+    st = scan_stats(p, None, AGGS, KEYS)
+    assert st["row_groups_runs"] == st["row_groups"] > 0

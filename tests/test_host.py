@@ -135,3 +135,13 @@ def test_footer_statistics_and_run_length_directories_of_sorted_parts(built_lib)
     buf = dp.write_part(dp.SampleDefinition(), cols, sort=True, row_group_size=n, write_statistics=False)
     c = _lib.describe_parquet(buf)["row_groups"][0]["columns"]
     assert "min" not in c["timestamp"]
+    # nullable sort keys: the two run-length streams (levels, indices) merge into one directory in row space
+    cols = make_columns(n, 78, {"a": (5, 0.2), "b": (37, 0.3), "z": (2, 1.0)}, t0=0)
+    d = _check_against_pyarrow(dp.write_part(dp.SampleDefinition(), cols, sort=True, row_group_size=7_001, data_page_size=2048))
+    seen = 0
+    for rg in d["row_groups"]:
+        for name in ("labels.a", "labels.b"):
+            c = rg["columns"][name]
+            assert c["row_runs_ok"] and c["n_row_runs"] <= c["n_runs"] + 2 * c["n_defruns"] + 1, (name, c["n_row_runs"])
+            seen += c["has_nulls"]
+    assert seen > 0
