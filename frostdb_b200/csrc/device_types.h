@@ -210,6 +210,7 @@ struct SeedJob {
 // directories with warp-uniform cursors.  The host lists those row groups here; the rest of the table
 // goes through the general scan kernel into the same aggregate table.
 constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 3, kRunsCols = kRunsLeaves + kRunsAggs;
+constexpr int kRunsPreds = 2;  // dictionary-column leaves evaluated once per run (result byte per dictionary id)
 
 struct RunsRg {
   uint32_t n_rows;
@@ -218,6 +219,11 @@ struct RunsRg {
   const uint8_t* col[kRunsCols];               // the staged PLAIN columns (distinct leaf and aggregate inputs)
   const Run* runs[kRunsKeys];                  // run directory of every group-key column (dictionary ids premapped)
   const Seed* seeds[kRunsKeys];                // cursor seeds, one per kIndexRows rows
+  // dictionary leaves (== / != / contains / regex on a run-length column): row-space directory + seeds of the
+  // leaf's column and the leaf's result per GLOBAL dictionary id; runs == null: decided for this row group (passes)
+  const Run* pred_runs[kRunsPreds];
+  const Seed* pred_seeds[kRunsPreds];
+  const uint8_t* pred_lut[kRunsPreds];
 };
 
 struct RunsDesc {
@@ -228,6 +234,8 @@ struct RunsDesc {
   uint32_t leaf_col[kRunsLeaves], agg_col[kRunsAggs];  // index into RunsRg::col
   uint32_t stride[kRunsKeys];                           // dense-table stride of every key
   uint32_t agg_func[kRunsAggs];                         // AggFunc | is_float << 8 (general-reducer instances)
+  uint32_t n_pred;                                      // dictionary leaves (conjunction with the range leaves)
+  uint32_t pred_null[kRunsPreds];                       // their result for NULL rows (== NULL selects NULLs)
   const RunsRg* rgs;
   const uint32_t* rg_first_span;  // [n_rg + 1]
   unsigned long long* t_rows;

@@ -1051,7 +1051,15 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       stored++;
       if (!(qd.aggs[a].prog_len == 1 && qd.prog[qd.aggs[a].prog_off].op == PO_LOAD)) fast = false;
     }
-    c->runs_shape = fast && !getenv("FROSTGPU_NO_FAST") ? true : false;  // the sorted-run kernel takes up to kRunsAggs reducers
+    {  // the sorted-run kernel: up to kRunsAggs reducers, and dictionary leaves evaluated once per run
+      bool rs = qd.table_mode == TM_DENSE && (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) && qd.n_keys <= kRunsKeys &&
+                qd.n_leaves <= kRunsLeaves + kRunsPreds && !getenv("FROSTGPU_NO_FAST");
+      for (int l = 0; l < qd.n_leaves && rs; l++)
+        if (c->leaves[size_t(l)].slot >= 0 && c->leaves[size_t(l)].numeric && c->leaves[size_t(l)].null_literal) rs = false;
+      for (int a = 0; a < qd.n_aggs && rs; a++)
+        if (qd.aggs[a].func != FGPU_AGG_COUNT && !(qd.aggs[a].prog_len == 1 && qd.prog[qd.aggs[a].prog_off].op == PO_LOAD)) rs = false;
+      c->runs_shape = rs;
+    }
     if (stored > 2) fast = false;
     qd.fast_ok = fast ? 1 : 0;
   }
@@ -1121,15 +1129,26 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     size_t o_rg = 0, o_span = 0;
   };
   RunsBatch batches[1];
-  int runs_nl = 0, runs_nk = 0, runs_na = 0;
+  int runs_nl = 0, runs_nk = 0, runs_na = 0, runs_np = 0;
+  int runs_leaf_index[kRunsLeaves] = {0}, runs_pred_leaf[kRunsPreds] = {0};  // query leaf behind every range / dictionary leaf
   int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
   uint32_t runs_agg_func[kRunsAggs] = {0};
   bool runs_q = q.kind != FGPU_PLAN_FILTER && c.runs_shape && !getenv("FROSTGPU_NO_RUNS");
   if (runs_q) {
     for (int l = 0; l < n_leaves && runs_q; l++) {
       const LeafDesc& ld = qd.leaves[l];
-      if (ld.slot == 0xff || ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || runs_nl >= kRunsLeaves) runs_q = false;
-      else runs_leaf_slot[runs_nl++] = ld.slot;
+      if (ld.slot != 0xff && qd.slot_type[ld.slot] == ST_DICT) {  // dictionary leaf: evaluated once per run
+        if (runs_np >= kRunsPreds) runs_q = false;
+        else runs_pred_leaf[runs_np++] = l;
+      } else if (ld.slot == 0xff) {  // column absent from every row group: ALL / NONE everywhere, nothing to evaluate
+        if (runs_np >= kRunsPreds) runs_q = false;
+        else runs_pred_leaf[runs_np++] = l;
+      } else if (ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || runs_nl >= kRunsLeaves) {
+        runs_q = false;
+      } else {
+        runs_leaf_index[runs_nl] = l;
+        runs_leaf_slot[runs_nl++] = ld.slot;
+      }
     }
     for (int a = 0; a < qd.n_aggs && runs_q; a++) {
       if (qd.aggs[a].func == FGPU_AGG_COUNT) continue;
@@ -1157,6 +1176,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         B.rd.agg_func[a] = runs_agg_func[a];
       }
       for (int k = 0; k < runs_nk; k++) B.rd.stride[k] = qd.keys[k].dense_stride;
+      B.rd.n_pred = uint32_t(runs_np);
     }
   }
   int gi = 0;  // row groups that stay with the general scan kernel
@@ -1208,7 +1228,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     if (runs_ok) {
       bool all_all = runs_nl > 0;
       for (int l = 0; l < runs_nl; l++) {
-        const uint8_t m = lrt[size_t(g) * n_leaves + l].mode;
+        const uint8_t m = lrt[size_t(g) * n_leaves + runs_leaf_index[l]].mode;
         if (m != LM_ALL) all_all = false;
         if (m == LM_NONE) runs_ok = false;  // (only with pruning switched off)
       }
@@ -1219,9 +1239,23 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       RunsBatch& B = batches[bi];
       rr.n_rows = rg.n_rows;
       for (int l = 0; l < B.nl; l++) {
-        const bool all = lrt[size_t(g) * n_leaves + l].mode == LM_ALL;
-        rr.lo[l] = all ? std::numeric_limits<int64_t>::min() : qd.leaves[l].lo_i;
-        rr.hi[l] = all ? std::numeric_limits<int64_t>::max() : qd.leaves[l].hi_i;
+        const int ql = runs_leaf_index[l];
+        const bool all = lrt[size_t(g) * n_leaves + ql].mode == LM_ALL;
+        rr.lo[l] = all ? std::numeric_limits<int64_t>::min() : qd.leaves[ql].lo_i;
+        rr.hi[l] = all ? std::numeric_limits<int64_t>::max() : qd.leaves[ql].hi_i;
+      }
+      for (int i = 0; i < runs_np && runs_ok; i++) {  // dictionary leaves: one result per run
+        const int ql = runs_pred_leaf[i];
+        const LeafRt& rt = lrt[size_t(g) * n_leaves + ql];
+        rr.pred_runs[i] = nullptr;
+        if (rt.mode == LM_ALL) continue;                      // decided: passes everywhere in this row group
+        if (rt.mode == LM_NONE) { runs_ok = false; break; }   // (only with pruning switched off)
+        const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.leaves[ql].slot];
+        if (d.kind != CK_DICT_STR || d.row_runs == nullptr) { runs_ok = false; break; }
+        rr.pred_runs[i] = d.row_runs;
+        rr.pred_seeds[i] = d.row_seeds;
+        rr.pred_lut[i] = reinterpret_cast<const uint8_t*>(uintptr_t(c.leaves[size_t(ql)].lut_off));  // offset, rebased below
+        B.rd.pred_null[i] = rt.null_result;
       }
       rr.all_pass = all_pass ? 1 : 0;
       const uint8_t* any_col = nullptr;
@@ -1430,6 +1464,9 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   if (!lutbytes.empty()) std::memcpy(hostaux.data() + o_lut, lutbytes.data(), lutbytes.size());
   for (RunsBatch& B : batches) {
     if (B.rgs.empty()) continue;
+    for (RunsRg& r : B.rgs)
+      for (int i = 0; i < runs_np; i++)
+        if (r.pred_runs[i]) r.pred_lut[i] = aux + o_lut + size_t(uintptr_t(r.pred_lut[i]));
     std::memcpy(hostaux.data() + B.o_rg, B.rgs.data(), B.rgs.size() * sizeof(RunsRg));
     std::memcpy(hostaux.data() + B.o_span, B.first_span.data(), B.first_span.size() * 4);
   }

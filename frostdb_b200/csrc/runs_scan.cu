@@ -180,6 +180,48 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
       kend[k] = s4.z;
       kadd[k] = (sv + 1u) * d.stride[k];
     }
+    // dictionary leaves: one more cursor per leaf, its run says whether the rows of the run pass
+    const uint32_t n_pred = d.n_pred;
+    const Run* pruns[kRunsPreds];
+    const uint8_t* plut[kRunsPreds];
+    uint32_t pk[kRunsPreds], pend[kRunsPreds];
+    bool ppass[kRunsPreds];
+#pragma unroll
+    for (int i = 0; i < kRunsPreds; i++) {
+      pruns[i] = nullptr;
+      plut[i] = nullptr;
+      pk[i] = 0;
+      pend[i] = 0xffffffffu;
+      ppass[i] = true;
+      if (uint32_t(i) < n_pred) {
+        pruns[i] = reinterpret_cast<const Run*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->pred_runs[i])));
+        if (pruns[i] != nullptr) {
+          plut[i] = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->pred_lut[i])));
+          const Seed* sd = reinterpret_cast<const Seed*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->pred_seeds[i]))) + row0 / uint32_t(kIndexRows);
+          const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sd));
+          const uint32_t sv = __ldg(reinterpret_cast<const uint32_t*>(sd) + 4);
+          pk[i] = s4.x;
+          pend[i] = s4.z;
+          ppass[i] = (sv == 0xffffffffu) ? (d.pred_null[i] != 0) : (__ldg(plut[i] + sv) != 0);
+        }
+      }
+    }
+    auto advance_preds = [&](uint32_t row) {
+#pragma unroll
+      for (int i = 0; i < kRunsPreds; i++) {
+        if (row >= pend[i]) {  // (pend == 0xffffffff: no such leaf here)
+          uint32_t k = pk[i], e;
+          do {
+            k++;
+            e = __ldg(&pruns[i][k + 1].start);
+          } while (row >= e);
+          pk[i] = k;
+          pend[i] = e;
+          const uint32_t v = __ldg(&pruns[i][k].val);
+          ppass[i] = (v == 0xffffffffu) ? (d.pred_null[i] != 0) : (__ldg(plut[i] + v) != 0);
+        }
+      }
+    };
     // moves the cursors onto the runs that hold `row` (same row in every lane: the loads broadcast)
     auto advance = [&](uint32_t row) {
 #pragma unroll
@@ -228,8 +270,15 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
       const uint32_t idx0 = uint32_t(lane);
       uint32_t row = r0;
       while (row < rend) {
+        if (n_pred) {  // rows of a run that fails a dictionary leaf are skipped as a whole
+          advance_preds(row);
+          if (!(ppass[0] && ppass[1])) {
+            row = min(rend, (!ppass[0] && !ppass[1]) ? max(pend[0], pend[1]) : (!ppass[0] ? pend[0] : pend[1]));
+            continue;
+          }
+        }
         advance(row);
-        uint32_t seg_end = rend, us = 0;
+        uint32_t seg_end = min(rend, min(pend[0], pend[1])), us = 0;
 #pragma unroll
         for (int k = 0; k < NK; k++) {
           seg_end = min(seg_end, kend[k]);

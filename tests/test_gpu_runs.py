@@ -270,3 +270,36 @@ def test_nullable_sorted_keys_take_the_run_kernel(pair):
         run3(p, build1)
     st = scan_stats(p, None, AGGS, KEYS)
     assert st["row_groups_runs"] == st["row_groups"] > 0
+
+
+def test_dictionary_leaves_evaluated_once_per_run(pair):
+    """label == / != / regex / contains / == NULL on run-length columns run inside k_runs (one result per run)."""
+    p = pair("runs_dictleaf")
+    n = 45_000
+    for i in range(3):
+        cols = sorted_columns(n, 970 + i, t0=i * n, cards=(6, 19), third=5)
+        idx = cols["labels.b"][0].copy()
+        idx[np.random.default_rng(i).random(n) < 0.2] = -1          # nullable second key
+        cols["labels.b"] = (idx, cols["labels.b"][1])
+        p.insert(cols, row_group_size=16_000)
+    a, b, cc, ts = lp.Col("labels.a"), lp.Col("labels.b"), lp.Col("labels.c"), lp.Col("timestamp")
+    rng = lp.And(ts.GtEq(lp.Literal(n // 3)), ts.Lt(lp.Literal(2 * n + 9)))
+    filters = [
+        a.Eq(lp.Literal("v000003")), a.NotEq(lp.Literal("v000003")), b.Eq(lp.Literal(None)), b.NotEq(lp.Literal(None)),
+        b.RegexMatch("v00000[2-5]$"), b.Contains("01"), lp.And(a.Eq(lp.Literal("v000001")), b.NotEq(lp.Literal("v000004"))),
+        lp.And(rng, a.Eq(lp.Literal("v000002"))), lp.And(lp.And(rng, b.RegexNotMatch("v00001")), lp.Col("value").Gt(lp.Literal(0))),
+        lp.And(a.Eq(lp.Literal("v000004")), lp.Col("labels.zz").Eq(lp.Literal(""))),   # absent column: decided everywhere
+        lp.And(a.Eq(lp.Literal("v000000")), cc.Eq(lp.Literal("v000001"))),             # labels.c is not run-length: general kernel
+    ]
+    for f in filters:
+        try:
+            run3(p, lambda q: q.Filter(f).Aggregate(AGGS, KEYS))
+            run3(p, lambda q: q.Filter(f).Aggregate([lp.Max(lp.Col("value")), lp.Count(lp.Col("value"))], [b]))
+        except AssertionError as e:
+            raise AssertionError(f"filter {f.Name()}: {e}") from e
+    st = scan_stats(p, filters[7], AGGS, KEYS)
+    assert st["row_groups_runs"] == st["row_groups"] > 0 and st["rows_selected"] > 0
+    st = scan_stats(p, filters[4], AGGS, KEYS)
+    assert st["row_groups_runs"] == st["row_groups"] > 0
+    st = scan_stats(p, filters[-1], AGGS, KEYS)
+    assert st["row_groups_runs"] == 0
