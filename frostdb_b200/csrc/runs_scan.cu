@@ -19,6 +19,8 @@
 // Algorithmic bytes per row: 8 per distinct staged column (the run directories are O(groups)).
 #include <cuda_runtime.h>
 
+#include <unordered_map>
+
 #include "device_types.h"
 #include "kernels.h"
 #include "agg_ops.cuh"
@@ -333,19 +335,20 @@ template <int NL, int NK>
 cudaError_t launch_na(const RunsDesc& d, int na, bool gen, dim3 grid, size_t smem, cudaStream_t st, bool query_only, int* per_sm) {
   auto go = [&](auto kern) -> cudaError_t {
     if (query_only) {  // per kernel instance: attribute and occupancy are looked up once per shared-memory size
-      static size_t cfg_smem = 0, occ_smem = ~size_t(0);
-      static int occ = 0;
-      if (smem > cfg_smem) {
+      struct Cache { size_t cfg_smem = 0, occ_smem = ~size_t(0); int occ = 0; };
+      static std::unordered_map<const void*, Cache> cache;  // (every instance has the same function type: key by address)
+      Cache& c = cache[reinterpret_cast<const void*>(kern)];
+      if (smem > c.cfg_smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
-        cfg_smem = smem;
+        c.cfg_smem = smem;
       }
-      if (occ_smem != smem) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRunsThreads, smem);
+      if (c.occ_smem != smem) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.occ, kern, kRunsThreads, smem);
         if (e != cudaSuccess) return e;
-        occ_smem = smem;
+        c.occ_smem = smem;
       }
-      *per_sm = occ;
+      *per_sm = c.occ;
       return cudaSuccess;
     }
     kern<<<grid, kRunsThreads, smem, st>>>(d);

@@ -19,6 +19,8 @@
 // selected row 8 read + 8 written per projected column.
 #include <cuda_runtime.h>
 
+#include <unordered_map>
+
 #include "device_types.h"
 #include "kernels.h"
 
@@ -180,7 +182,8 @@ __global__ void __launch_bounds__(kTakeThreads) k_take_write(const __grid_consta
 
 template <typename K>
 cudaError_t run(K kern, const TakeDesc& d, int sm_count, cudaStream_t st) {
-  static int per_sm = 0;
+  static std::unordered_map<const void*, int> occ;  // (instances share one function type: key by address)
+  int& per_sm = occ[reinterpret_cast<const void*>(kern)];
   if (per_sm == 0) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTakeThreads, 0);
     if (e != cudaSuccess) return e;
