@@ -164,7 +164,7 @@ def workload_config(rows_per_gpu, n_gpus):
                         "(<=16705 groups); parts of 4Mi rows sorted in compaction order, 1Mi-row row groups, uncompressed, DataPageV2",
             "rows_per_gpu": rows_per_gpu, "label_columns": N_LABELS, "part_rows": bd.PART_ROWS, "row_group_rows": bd.RG_ROWS,
             "l2": "inputs (>=1.6 GB projected per step per GPU) exceed the 126 MB L2; no explicit flush",
-            "parallelism": f"parts sharded one range per GPU x{n_gpus}, one all-gather of partial aggregate tables"}
+            "parallelism": f"parts sharded one range per GPU x{n_gpus}, one NCCL all-reduce (SUM) of the dense partial aggregate tables"}
 
 
 def main():
@@ -252,13 +252,21 @@ def main():
         res, ptr, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
         _lib.check(lib.fgpu_query_execute_partial(eng.handle, q, tx, C.byref(res), C.byref(ptr), C.byref(nbytes)))
         n8 = nbytes.value // 8
-        if "buf" not in gathered or gathered["buf"].numel() != n8 * world:
-            gathered["buf"] = torch.empty(n8 * world, dtype=torch.int64, device="cuda")
         # zero-copy view of the library's partial table (the scan has completed on its stream)
         mine = torch.as_tensor(_DevMem(ptr.value, nbytes.value), device="cuda")
-        dist.all_gather_into_tensor(gathered["buf"], mine)
-        torch.cuda.current_stream().synchronize()
-        _lib.check(lib.fgpu_result_merge_partials(eng.handle, res, gathered["buf"].data_ptr(), nbytes.value, world))
+        additive = C.c_int32(0)
+        _lib.check(lib.fgpu_result_partial_is_additive(res, C.byref(additive)))
+        if additive.value and not os.environ.get("FROSTGPU_BENCH_GATHER"):
+            # dense table of counts and integer sums: the partial -> final step is one in-place all-reduce
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().synchronize()
+            _lib.check(lib.fgpu_result_merge_partials(eng.handle, res, None, 0, 0))
+        else:
+            if "buf" not in gathered or gathered["buf"].numel() != n8 * world:
+                gathered["buf"] = torch.empty(n8 * world, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(gathered["buf"], mine)
+            torch.cuda.current_stream().synchronize()
+            _lib.check(lib.fgpu_result_merge_partials(eng.handle, res, gathered["buf"].data_ptr(), nbytes.value, world))
         st = eng.stats(res)
         batches = list(eng.drain(res))
         lib.fgpu_result_free(res)

@@ -2084,6 +2084,15 @@ int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* ga
   return finalize_result(ctx, r);
 }
 
+int32_t fgpu_result_partial_is_additive(const fgpu_result* r, int32_t* out) {
+  if (!r || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  bool add = !r->rows_plan && r->qd.table_mode == TM_DENSE;
+  for (int a = 0; a < r->qd.n_aggs && add; a++)
+    if (r->qd.aggs[a].func != FGPU_AGG_COUNT && !(r->qd.aggs[a].func == FGPU_AGG_SUM && !r->qd.aggs[a].is_float)) add = false;
+  *out = add ? 1 : 0;
+  return FGPU_OK;
+}
+
 int32_t fgpu_result_next(fgpu_result* r, struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
   if (!r || !out_schema || !out_array) return fail(FGPU_ERR_INVALID, "null argument");
   if (!r->finalized) return fail(FGPU_ERR_INVALID, "partial result: call fgpu_result_merge_partials first");

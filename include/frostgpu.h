@@ -261,6 +261,11 @@ int32_t fgpu_query_execute_partial(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_wat
  * long, e.g. the output of an all-gather) into `r` and finalises it. */
 int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* gathered,
                                    uint64_t nbytes, int32_t n);
+/* `*out` = 1 when the partial table of `r` merges by element-wise int64 addition (dense table, every
+ * aggregate a Count or an integer Sum): the ranks may then all-reduce (SUM) the tables in place over
+ * nbytes / 8 int64 words and call fgpu_result_merge_partials(ctx, r, NULL, 0, 0) instead of gathering
+ * them — the dense-table reduction of the partial -> final aggregate step (physicalplan.go:438-471). */
+int32_t fgpu_result_partial_is_additive(const fgpu_result* r, int32_t* out);
 
 /* ---- standalone K1: decode one column of one part to Arrow buffers on the device and return
  * them on the host (replaces ParquetConverter.Convert, pqarrow/arrow.go:264-373, for tests and

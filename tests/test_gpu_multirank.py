@@ -75,3 +75,69 @@ def test_partial_tables_merge_like_the_final_aggregate(built_lib, groups):
         oe.close()
         for e in engines:
             e.close()
+
+
+def test_additive_partial_tables_reduce_in_place(built_lib):
+    """Dense table of counts and integer sums: adding the ranks' tables element-wise (what an NCCL all-reduce
+    does) and finalising without a gather equals the oracle; Min/Max or float sums must say "not additive"."""
+    import torch
+    lib = built_lib
+    schema = dp.SampleDefinition()
+    bufs = [dp.write_part(schema, make_columns(25_000, 80 + r, {"a": (6, 0.1), "b": (30, 0.0)}, t0=r * 25_000), row_group_size=9_000)
+            for r in range(4)]
+    shards = [bufs[0::2], bufs[1::2]]
+    key_cols = ["labels.a", "labels.b"]
+    unions = {c: union_in_rank_order([[v for b in sh for v in _lib.parquet_dict_values(b, c)] for sh in shards]) for c in key_cols}
+    engines = [GPUEngine(0), GPUEngine(0)]
+    oe = OracleEngine(threads=2)
+    try:
+        ot = OracleTableHandle(oe, "t", schema)
+        for e, sh in zip(engines, shards):
+            for c in key_cols:
+                e.dict_preload("t", c, unions[c])
+            for b in sh:
+                e.put_parquet("t", b)
+        for b in bufs:
+            ot.InsertParquet(b)
+        gexprs = [lp.Col(c) for c in key_cols]
+        f = lp.Col("timestamp").Lt(lp.Literal(80_000))
+
+        class DevMem:
+            def __init__(self, p, n):
+                self.__cuda_array_interface__ = {"shape": (n // 8,), "typestr": "<i8", "data": (p, False), "version": 2}
+
+        def partials(aggs):
+            out = []
+            for e in engines:
+                q, keep = GPUScan(e, "t", f, _lib.PLAN_AGGREGATE, gexprs, aggs).prepare()
+                res, ptr, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
+                _lib.check(lib.fgpu_query_execute_partial(e.handle, q, e.table_watermark("t"), C.byref(res), C.byref(ptr), C.byref(nbytes)))
+                add = C.c_int32(-1)
+                _lib.check(lib.fgpu_result_partial_is_additive(res, C.byref(add)))
+                out.append((e, q, keep, res, ptr.value, nbytes.value, add.value))
+            return out
+
+        aggs = [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value")), lp.Sum(lp.Col("timestamp"))]
+        ps = partials(aggs)
+        assert [p[6] for p in ps] == [1, 1] and ps[0][5] == ps[1][5]
+        t0 = torch.as_tensor(DevMem(ps[0][4], ps[0][5]), device="cuda")
+        t0 += torch.as_tensor(DevMem(ps[1][4], ps[1][5]), device="cuda")   # the all-reduce, with two "ranks" on one GPU
+        torch.cuda.synchronize()
+        _lib.check(lib.fgpu_result_merge_partials(ps[0][0].handle, ps[0][3], None, 0, 0))
+        got = list(ps[0][0].drain(ps[0][3]))
+        exp = []
+        oracle_query(oe, "t").Filter(f).Aggregate(aggs, gexprs).Execute(None, lambda c, r: exp.append(r))
+        names = key_cols + [a.Name() for a in aggs]
+        assert rows_of(got, names) == rows_of(exp, names)
+        for p in ps:
+            lib.fgpu_result_free(p[3])
+            lib.fgpu_query_free(p[1])
+        ps = partials([lp.Sum(lp.Col("value")), lp.Max(lp.Col("value"))])
+        assert [p[6] for p in ps] == [0, 0]
+        for p in ps:
+            lib.fgpu_result_free(p[3])
+            lib.fgpu_query_free(p[1])
+    finally:
+        oe.close()
+        for e in engines:
+            e.close()
