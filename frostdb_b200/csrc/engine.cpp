@@ -128,6 +128,7 @@ struct fgpu_ctx {
   std::mutex mu;
   std::map<std::string, Table> tables;
   std::vector<ColumnImage*> pending_uploads;  // staging to release after the next stream sync
+  uint64_t epoch_counter = 0;                 // source of Table::epoch stamps
   // page-locked arena for column metadata on its way to the device: a pageable source would make every
   // cudaMemcpyAsync wait for the transfers queued before it.  Reset by release_staging() after a sync.
   uint8_t* arena = nullptr;
@@ -182,6 +183,10 @@ struct PhaseClock {
 };
 
 struct fgpu_query {
+  // the compiled plan of the last Execute, reused while the table (its parts, its dictionaries) and the read
+  // transaction are the same: a prepared query re-executed on an unchanged table skips plan compilation
+  mutable std::shared_ptr<void> plan_cache;  // Compiled
+  mutable uint64_t cache_epoch = 0, cache_tx = 0;
   fgpu_ctx* ctx = nullptr;
   std::string table;
   int32_t kind = 0;
@@ -1098,11 +1103,25 @@ void bind_table(QueryDesc* qd, uint8_t* base) {
 // Runs init + scan.  On success the result owns the device table.
 int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* res, bool count_groups = false) {
   PhaseClock pc;
-  Compiled c;
-  int32_t rc = compile(ctx, q, tx, &c);
-  if (rc) return rc;
+  Table& plan_table = ctx->tables[q.table];
+  if (plan_table.epoch == 0) plan_table.epoch = ++ctx->epoch_counter;
+  if (!q.plan_cache || q.cache_epoch != plan_table.epoch || q.cache_tx != tx || getenv("FROSTGPU_NO_PLAN_CACHE")) {
+    std::shared_ptr<void> fresh(new Compiled(), [](void* p) { delete static_cast<Compiled*>(p); });
+    int32_t rc0 = compile(ctx, q, tx, static_cast<Compiled*>(fresh.get()));
+    q.plan_cache.reset();
+    if (rc0) return rc0;
+    q.plan_cache = std::move(fresh);
+    q.cache_epoch = plan_table.epoch;
+    q.cache_tx = tx;
+  } else {
+    static_cast<Compiled*>(q.plan_cache.get())->h2d_bytes = 0;  // nothing is uploaded by a cached plan
+  }
+  Compiled& c = *static_cast<Compiled*>(q.plan_cache.get());
+  for (LeafHost& lh : c.leaves) lh.lut_off = size_t(-1);  // per-Execute state of the plan
+  int32_t rc = FGPU_OK;
+  (void)rc;
   pc.mark("compile");
-  QueryDesc& qd = c.qd;
+  QueryDesc qd = c.qd;  // a copy: the plan in `c` may be reused by the next Execute
   const int n_rg = qd.n_rg, n_slots = qd.n_slots, n_leaves = qd.n_leaves;
   fgpu_stats& st = res->stats;
   st.rows_scanned = c.total_rows;
@@ -1537,8 +1556,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0);
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(hostaux.data() + o_ret);
+  res->cnt_ptr = reinterpret_cast<unsigned int*>(aux + o_cnt + 64);  // 16 bytes behind the counters, zeroed by the upload
   if (count_groups && !rows_plan) {  // count the result rows behind the scan: one host round trip less
-    res->cnt_ptr = reinterpret_cast<unsigned int*>(aux + o_cnt + 64);
     fd.out_count = res->cnt_ptr;
     fd.max_out = 0;
     fd.out_keys = nullptr;
@@ -1564,7 +1583,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
 
   // keep what finalize / merge need
   res->qd = qd;
-  res->keys = std::move(c.keys);
+  res->keys = c.keys;  // (the plan may be reused by the next Execute)
   for (KeyOut& k : res->keys) {
     if (k.dict) {
       uint32_t card = k.dict->cardinality();
@@ -1886,6 +1905,7 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
     part->file = nullptr;
   }
   t.parts.push_back(std::move(part));
+  t.epoch = ++ctx->epoch_counter;
   return FGPU_OK;
 }
 
@@ -1925,6 +1945,7 @@ int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, 
     return fail(FGPU_ERR_CUDA, std::string("part upload: ") + cudaGetErrorString(e));
   }
   t.parts.push_back(std::move(part));
+  t.epoch = ++ctx->epoch_counter;
   return FGPU_OK;
 }
 
@@ -1941,6 +1962,7 @@ int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {
       release_staging(ctx);
       free_part(ctx, parts[i].get());
       parts.erase(parts.begin() + long(i));
+      it->second.epoch = ++ctx->epoch_counter;
       return FGPU_OK;
     }
   }
@@ -2069,17 +2091,35 @@ int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* ga
       CUDA_TRY(launch_merge(qd, static_cast<const uint8_t*>(gathered) + size_t(i) * nbytes, ctx->stream));
       r->stats.kernel_launches++;
     }
-    unsigned long long counters[8] = {0};
-    CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    // the result now lives in the merged table; its groups are counted right behind the merges so that
+    // finalisation needs one host round trip less
+    FinalizeDesc& fd = r->fd;
+    fd.t_rows = qd.t_rows;
+    for (int a = 0; a < kMaxAggs; a++) fd.t_agg[a] = qd.t_agg[a];
+    fd.t_tag = qd.t_tag;
+    fd.t_keys = qd.t_keys;
+    if (r->cnt_ptr) {
+      CUDA_TRY(cudaMemsetAsync(r->cnt_ptr, 0, 16, ctx->stream));
+      fd.out_count = r->cnt_ptr;
+      fd.max_out = 0;
+      fd.out_keys = nullptr;
+      fd.out_aggs = nullptr;
+      fd.out_rows = nullptr;
+      CUDA_TRY(launch_finalize(fd, ctx->stream));
+      r->stats.kernel_launches++;
+    }
+    CUDA_TRY(ctx->ensure_scratch(128));
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->scratch);
+    CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64 + 16, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (counters[1]) return fail(FGPU_ERR_UNSUPPORTED, "aggregate hash table overflow while merging partials");
+    if (r->cnt_ptr) {
+      r->n_groups = static_cast<unsigned int>(counters[8] & 0xffffffffull);
+      r->groups_known = true;
+    }
     std::swap(r->table.p, merged.p);
     std::swap(r->table.n, merged.n);
     r->qd = qd;
-    r->fd.t_rows = qd.t_rows;
-    for (int a = 0; a < kMaxAggs; a++) r->fd.t_agg[a] = qd.t_agg[a];
-    r->fd.t_tag = qd.t_tag;
-    r->fd.t_keys = qd.t_keys;
   }
   return finalize_result(ctx, r);
 }
@@ -2176,6 +2216,7 @@ int32_t fgpu_dict_preload(fgpu_ctx* ctx, const char* table, const char* column, 
     d.intern(reinterpret_cast<const char*>(p), l);
     p += l;
   }
+  ctx->tables[table].epoch = ++ctx->epoch_counter;
   return FGPU_OK;
 }
 

@@ -91,6 +91,7 @@ struct Part {
 };
 
 struct Table {
+  uint64_t epoch = 0;  // changes whenever the set of parts or a dictionary does (0: not stamped yet); plans cache against it
   std::vector<std::unique_ptr<Part>> parts;  // insertion order
   std::map<std::string, GlobalDict> dicts;   // by column name
 };
