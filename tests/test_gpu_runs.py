@@ -301,3 +301,45 @@ def test_dictionary_leaves_evaluated_once_per_run(pair):
     assert st["row_groups_runs"] == st["row_groups"] > 0 and st["rows_selected"] > 0
     st = scan_stats(p, filters[4], AGGS, KEYS)
     assert st["row_groups_runs"] == st["row_groups"] > 0
+
+
+def test_prepared_query_reexecuted_and_invalidated(pair):
+    """A prepared query keeps its compiled plan while the table is unchanged; a new part, a dropped part or a new
+    read transaction must recompile.  Every execution equals a freshly prepared one."""
+    p = pair("plan_cache")
+    n = 30_000
+    eng, lib = p.store.engine, _lib.load()
+    f = lp.And(lp.Col("timestamp").GtEq(lp.Literal(n // 2)), lp.Col("labels.a").NotEq(lp.Literal("v000001")))
+    names = ["labels.a", "labels.b", "sum(value)", "count(value)"]
+
+    def execute(q):
+        res = C.c_void_p()
+        _lib.check(lib.fgpu_query_execute(eng.handle, q, eng.table_watermark(p.name), C.byref(res)))
+        out = list(eng.drain(res))
+        lib.fgpu_result_free(res)
+        return rows_of(out, names)
+
+    def fresh():
+        q, keep = GPUScan(eng, p.name, f, _lib.PLAN_AGGREGATE, KEYS, AGGS).prepare()
+        try:
+            return execute(q)
+        finally:
+            lib.fgpu_query_free(q)
+
+    p.insert(sorted_columns(n, 990, t0=0), row_group_size=11_000)
+    p.insert(sorted_columns(n, 991, t0=n), sort=False)
+    q, keep = GPUScan(eng, p.name, f, _lib.PLAN_AGGREGATE, KEYS, AGGS).prepare()
+    try:
+        first = execute(q)
+        assert first == execute(q) == execute(q) == fresh() and len(first) > 0
+        got, exp = p.run(lambda b: b.Filter(f).Aggregate(AGGS, KEYS))
+        assert rows_of(got, names) == rows_of(exp, names) == first
+        p.insert(sorted_columns(n, 992, t0=2 * n, cards=(7, 29)), row_group_size=9_000)   # new part, new dictionary entries
+        second = execute(q)
+        assert second == execute(q) == fresh() and second != first
+        got, exp = p.run(lambda b: b.Filter(f).Aggregate(AGGS, KEYS))
+        assert rows_of(got, names) == rows_of(exp, names) == second
+        eng.drop_part(p.name, 2)
+        assert execute(q) == first
+    finally:
+        lib.fgpu_query_free(q)
