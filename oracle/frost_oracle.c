@@ -12,6 +12,9 @@
  * format specification.  Semantics with no reference test behind them are marked UNPINNED.
  *
  * The code follows the reference's algorithm shape on purpose (it is also the CPU baseline):
+ *   scan       -> visible parts, row groups ruled out by the filter's  index/lsm.go:401-454
+ *                 TrueNegativeFilter over the chunk statistics        query/expr/{filter,binaryscalarexpr}.go
+ *                 (UNPINNED: no reference test fixes which row groups are skipped; it never changes a result)
  *   row group  -> decode projected columns to Arrow-like arrays    pqarrow/arrow.go:264-373,711-823
  *                 dictionary columns: one memo-table insert per row pqarrow/writer/writer.go:381-405
  *   filter     -> leaf bitmaps, AND/OR, compaction of all columns   query/physicalplan/filter.go:167-323
