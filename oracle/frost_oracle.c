@@ -14,7 +14,8 @@
  * The code follows the reference's algorithm shape on purpose (it is also the CPU baseline):
  *   scan       -> visible parts, row groups ruled out by the filter's  index/lsm.go:401-454
  *                 TrueNegativeFilter over the chunk statistics        query/expr/{filter,binaryscalarexpr}.go
- *                 (UNPINNED: no reference test fixes which row groups are skipped; it never changes a result)
+ *                 (pinned by TestBinaryScalarOperation, expr/binaryscalarexpr_test.go:56-212 ->
+ *                 tests/golden/rowgroup_filter_cases.py; it never changes a result)
  *   row group  -> decode projected columns to Arrow-like arrays    pqarrow/arrow.go:264-373,711-823
  *                 dictionary columns: one memo-table insert per row pqarrow/writer/writer.go:381-405
  *   filter     -> leaf bitmaps, AND/OR, compaction of all columns   query/physicalplan/filter.go:167-323
@@ -861,6 +862,29 @@ static int stat_cmp(int phys, const uint8_t* a, uint32_t al, const fgpu_scalar* 
   return 0;
 }
 
+/* BinaryScalarOperation (expr/binaryscalarexpr.go:84-190) over one chunk's statistics.  nulls < 0: unknown. */
+static int chunk_may_match(const o_chunk* ch, int64_t nulls, int64_t num_rows, int op, const fgpu_scalar* lit) {
+  int full_of_nulls = nulls >= 0 && nulls == num_rows;
+  int ok;
+  if (op == FGPU_OP_EQ) {
+    if (lit->type == FGPU_SCALAR_NULL) return nulls != 0; /* unknown count: maybe */
+    if (full_of_nulls) return 0;
+    if (!ch->smin || !ch->smax) return 1;
+    int cmax = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); if (!ok) return 1;
+    int cmin = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); if (!ok) return 1;
+    return cmax >= 0 && cmin <= 0; /* compare(right, Max) <= 0 && compare(right, Min) >= 0 */
+  }
+  if (lit->type == FGPU_SCALAR_NULL) return 1;
+  if (full_of_nulls) return 0;
+  switch (op) {
+    case FGPU_OP_LT_EQ: if (!ch->smin) return 1; { int c = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); return !ok || c <= 0; }
+    case FGPU_OP_LT:    if (!ch->smin) return 1; { int c = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); return !ok || c < 0; }
+    case FGPU_OP_GT:    if (!ch->smax) return 1; { int c = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); return !ok || c > 0; }
+    case FGPU_OP_GT_EQ: if (!ch->smax) return 1; { int c = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); return !ok || c >= 0; }
+    default: return 1; /* != : delegated to the execution engine */
+  }
+}
+
 static int rg_may_match(const fgpu_plan* plan, int node, const o_part* part, const o_rg* rg) {
   if (node < 0) return 1;
   const fgpu_expr* e = &plan->exprs[node];
@@ -881,25 +905,18 @@ static int rg_may_match(const fgpu_plan* plan, int node, const o_part* part, con
   }
   const o_chunk* ch = &rg->chunks[ci];
   int64_t nulls = ch->null_count >= 0 ? ch->null_count : (part->leaves[ci].optional ? -1 : 0);
-  int full_of_nulls = nulls >= 0 && nulls == rg->num_rows;
-  int ok;
-  if (e->op == FGPU_OP_EQ) {
-    if (lit->type == FGPU_SCALAR_NULL) return nulls != 0; /* unknown count: maybe */
-    if (full_of_nulls) return 0;
-    if (!ch->smin || !ch->smax) return 1;
-    int cmax = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); if (!ok) return 1;
-    int cmin = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); if (!ok) return 1;
-    return cmax >= 0 && cmin <= 0; /* compare(right, Max) <= 0 && compare(right, Min) >= 0 */
-  }
-  if (lit->type == FGPU_SCALAR_NULL) return 1;
-  if (full_of_nulls) return 0;
-  switch (e->op) {
-    case FGPU_OP_LT_EQ: if (!ch->smin) return 1; { int c = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); return !ok || c <= 0; }
-    case FGPU_OP_LT:    if (!ch->smin) return 1; { int c = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); return !ok || c < 0; }
-    case FGPU_OP_GT:    if (!ch->smax) return 1; { int c = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); return !ok || c > 0; }
-    case FGPU_OP_GT_EQ: if (!ch->smax) return 1; { int c = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); return !ok || c >= 0; }
-    default: return 1; /* != : delegated to the execution engine */
-  }
+  return chunk_may_match(ch, nulls, rg->num_rows, e->op, lit);
+}
+
+/* Test hook: BinaryScalarOperation on an int64 chunk described by its statistics alone, so that the cases of
+   the reference's TestBinaryScalarOperation (expr/binaryscalarexpr_test.go:56-212) can be replayed. */
+int oracle_chunk_may_match_i64(int has_minmax, int64_t mn, int64_t mx, int64_t null_count, int64_t num_values, int op, int lit_is_null, int64_t lit) {
+  o_chunk ch; memset(&ch, 0, sizeof ch);
+  ch.phys = PQ_INT64; ch.null_count = null_count;
+  if (has_minmax) { ch.smin = (const uint8_t*)&mn; ch.smin_len = 8; ch.smax = (const uint8_t*)&mx; ch.smax_len = 8; }
+  fgpu_scalar s; memset(&s, 0, sizeof s);
+  s.type = lit_is_null ? FGPU_SCALAR_NULL : FGPU_SCALAR_INT64; s.i64 = lit;
+  return chunk_may_match(&ch, null_count, num_values, op, &s);
 }
 
 static void* worker_main(void* arg) {

@@ -45,6 +45,8 @@ def load() -> C.CDLL:
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                          C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.oracle_free.argtypes = [C.c_void_p]
+    lib.oracle_chunk_may_match_i64.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64]
+    lib.oracle_chunk_may_match_i64.restype = C.c_int
     _lib = lib
     return lib
 
@@ -156,3 +158,8 @@ class OracleResult:
         if self.h:
             self.lib.oracle_result_free(self.h)
             self.h = None
+
+
+def chunk_may_match_i64(has_minmax: bool, mn: int, mx: int, null_count: int, num_values: int, op: int, literal) -> bool:
+    """BinaryScalarOperation of the row-group filter on an int64 chunk given by its statistics (literal None = NULL)."""
+    return bool(load().oracle_chunk_may_match_i64(int(has_minmax), mn, mx, null_count, num_values, op, int(literal is None), literal or 0))

@@ -21,3 +21,13 @@ def test_oracle_reproduces_reference_goldens(case, threads):
         assert n > 0
     finally:
         eng.close()
+
+
+def test_row_group_filter_against_reference_vectors():
+    """TestBinaryScalarOperation (query/expr/binaryscalarexpr_test.go:56-212): the oracle's port of the row-group
+    filter gives the reference's own expected answers."""
+    from oracle import oracle as orc
+    from tests.golden import rowgroup_filter_cases as g
+    for name, mn, mx, right, nulls, op, expect in g.CASES:
+        has_bounds = nulls != g.NUM_VALUES  # upstream: all-NULL chunks carry NULL bounds
+        assert orc.chunk_may_match_i64(has_bounds, mn, mx, nulls, g.NUM_VALUES, op, right) == expect, name
