@@ -128,6 +128,7 @@ _SIGNATURES = {
     "fgpu_query_execute_partial": ([C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)], C.c_int32),
     "fgpu_result_merge_partials": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32], C.c_int32),
     "fgpu_result_partial_is_additive": ([C.c_void_p, C.POINTER(C.c_int32)], C.c_int32),
+    "fgpu_rowgroup_leaf_mode": ([C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int32)], C.c_int32),
     "fgpu_part_decode_column": ([C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_void_p], C.c_int32),
     "fgpu_parquet_describe": ([C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int32),
 }

@@ -425,6 +425,31 @@ bool dict_leaf_value(const LeafHost& l, const std::string& v) {
   return false;
 }
 
+// "column op literal" on an int64 column as an inclusive range, optionally negated (see LeafDesc).
+void canonical_int_range(int op, int64_t v, int64_t* lo, int64_t* hi, bool* neg) {
+  const int64_t kMin = std::numeric_limits<int64_t>::min(), kMax = std::numeric_limits<int64_t>::max();
+  *lo = kMax; *hi = kMin;  // empty
+  *neg = false;
+  switch (op) {
+    case FGPU_OP_EQ: *lo = *hi = v; break;
+    case FGPU_OP_NOT_EQ: *lo = *hi = v; *neg = true; break;
+    case FGPU_OP_LT: if (v != kMin) { *lo = kMin; *hi = v - 1; } break;
+    case FGPU_OP_LT_EQ: *lo = kMin; *hi = v; break;
+    case FGPU_OP_GT: if (v != kMax) { *lo = v + 1; *hi = kMax; } break;
+    default: *lo = v; *hi = kMax; break;
+  }
+}
+
+// What the chunk statistics [mn, mx] (bounds of the non-null values) decide about an int64 range leaf for a
+// whole row group: LM_NONE no row can pass, LM_ALL every row passes (needs a chunk without NULLs), LM_EVAL
+// undecided.  The row-group filter of the reference (expr/binaryscalarexpr.go:84-190) answers the first question.
+uint8_t stats_leaf_mode(int64_t lo, int64_t hi, bool neg, int64_t mn, int64_t mx, bool no_nulls) {
+  const bool disjoint = mx < lo || mn > hi;
+  const bool inside = mn >= lo && mx <= hi;
+  if (!neg) return disjoint ? LM_NONE : ((inside && no_nulls) ? LM_ALL : LM_EVAL);
+  return inside ? LM_NONE : ((disjoint && no_nulls) ? LM_ALL : LM_EVAL);
+}
+
 struct Compiled {
   std::vector<VisibleRG> rgs;
   std::vector<std::string> slot_names;
@@ -668,7 +693,6 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       lh.numeric = true;
       lh.null_literal = lit.lit_type == FGPU_SCALAR_NULL;  // arrow compute against NULL: nothing selected (:143-150)
       lh.cmp_float = (st == ST_F64) || lit.lit_type == FGPU_SCALAR_FLOAT64;
-      const int64_t kMin = std::numeric_limits<int64_t>::min(), kMax = std::numeric_limits<int64_t>::max();
       const double kInf = std::numeric_limits<double>::infinity();
       if (lh.cmp_float) {
         const double v = lit.lit_type == FGPU_SCALAR_FLOAT64 ? lit.lit_f : double(lit.lit_i);
@@ -688,16 +712,9 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
           lh.neg = true;  // x != NaN holds for every non-NULL x
         }
       } else {
-        const int64_t v = lit.lit_i;
-        lh.lo_i = kMax; lh.hi_i = kMin;  // empty
-        switch (lh.op) {
-          case FGPU_OP_EQ: lh.lo_i = lh.hi_i = v; break;
-          case FGPU_OP_NOT_EQ: lh.lo_i = lh.hi_i = v; lh.neg = true; break;
-          case FGPU_OP_LT: if (v != kMin) { lh.lo_i = kMin; lh.hi_i = v - 1; } break;
-          case FGPU_OP_LT_EQ: lh.lo_i = kMin; lh.hi_i = v; break;
-          case FGPU_OP_GT: if (v != kMax) { lh.lo_i = v + 1; lh.hi_i = kMax; } break;
-          default: lh.lo_i = v; lh.hi_i = kMax; break;
-        }
+        bool neg = false;
+        canonical_int_range(lh.op, lit.lit_i, &lh.lo_i, &lh.hi_i, &neg);
+        lh.neg = neg;
       }
     }
   }
@@ -778,12 +795,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
         if (it == v.rg->cols.end()) {
           mode = lh.missing_mode;  // the missing-column rules are the row-group filter's own (:47-73)
         } else if (lh.numeric && !lh.cmp_float && !lh.null_literal && c->slot_types[size_t(lh.slot)] == ST_I64 && it->second.has_minmax) {
-          const int64_t mn = it->second.min_bits, mx = it->second.max_bits;
-          const bool disjoint = mx < lh.lo_i || mn > lh.hi_i;
-          const bool inside = mn >= lh.lo_i && mx <= lh.hi_i;
-          const bool no_nulls = it->second.null_count == 0;
-          if (!lh.neg) mode = disjoint ? LM_NONE : ((inside && no_nulls) ? LM_ALL : LM_EVAL);
-          else mode = inside ? LM_NONE : ((disjoint && no_nulls) ? LM_ALL : LM_EVAL);
+          mode = stats_leaf_mode(lh.lo_i, lh.hi_i, lh.neg, it->second.min_bits, it->second.max_bits, it->second.null_count == 0);
         }
         else if (it != v.rg->cols.end() && c->slot_types[size_t(lh.slot)] == ST_DICT && lh.op == FGPU_OP_EQ &&
                  lh.lit->lit_type == FGPU_SCALAR_STRING && it->second.has_minmax_str) {
@@ -2130,6 +2142,18 @@ int32_t fgpu_result_partial_is_additive(const fgpu_result* r, int32_t* out) {
   for (int a = 0; a < r->qd.n_aggs && add; a++)
     if (r->qd.aggs[a].func != FGPU_AGG_COUNT && !(r->qd.aggs[a].func == FGPU_AGG_SUM && !r->qd.aggs[a].is_float)) add = false;
   *out = add ? 1 : 0;
+  return FGPU_OK;
+}
+
+int32_t fgpu_rowgroup_leaf_mode(int32_t op, int64_t literal, int32_t has_bounds, int64_t min_value, int64_t max_value, int64_t null_count,
+                                int64_t num_values, int32_t* out_mode) {
+  if (!out_mode) return fail(FGPU_ERR_INVALID, "null argument");
+  if (op < FGPU_OP_EQ || op > FGPU_OP_GT_EQ) return fail(FGPU_ERR_INVALID, "not a comparison operator");
+  int64_t lo, hi;
+  bool neg;
+  canonical_int_range(op, literal, &lo, &hi, &neg);
+  // an all-NULL chunk has no bounds: nothing is decided from statistics (the kernels find no passing row)
+  *out_mode = (has_bounds && null_count != num_values) ? stats_leaf_mode(lo, hi, neg, min_value, max_value, null_count == 0) : LM_EVAL;
   return FGPU_OK;
 }
 

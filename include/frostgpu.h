@@ -276,6 +276,13 @@ int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_
 
 /* ---- host-only introspection (works without a GPU; used by the CPU test-suite) --------------- */
 
+/* What the engine decides for a whole row group about the leaf "int64 column <op> literal" from the chunk
+ * statistics alone (the decision LSM.Scan's TrueNegativeFilter makes, index/lsm.go:437,
+ * expr/binaryscalarexpr.go:84-190): *out_mode = 0 undecided (the kernels evaluate the leaf), 1 every row
+ * passes, 2 no row can pass (under a conjunction the row group is skipped). */
+int32_t fgpu_rowgroup_leaf_mode(int32_t op, int64_t literal, int32_t has_bounds, int64_t min_value, int64_t max_value,
+                                int64_t null_count, int64_t num_values, int32_t* out_mode);
+
 /* Parses a Parquet file exactly as fgpu_part_put_parquet does (footer, page walk, run
  * directories) and writes a JSON description into buf.  Call with buf == NULL to size. */
 int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_rows, char* buf,

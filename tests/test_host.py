@@ -145,3 +145,36 @@ def test_footer_statistics_and_run_length_directories_of_sorted_parts(built_lib)
             assert c["row_runs_ok"] and c["n_row_runs"] <= c["n_runs"] + 2 * c["n_defruns"] + 1, (name, c["n_row_runs"])
             seen += c["has_nulls"]
     assert seen > 0
+
+
+def test_row_group_pruning_decisions_against_reference_vectors(built_lib):
+    """The engine's own statistics decision (fgpu_rowgroup_leaf_mode, the function compile() uses) replayed on
+    TestBinaryScalarOperation (query/expr/binaryscalarexpr_test.go:56-212): it must never rule out a row group
+    the reference keeps, it must rule out every bounded chunk the reference rules out, and "every row passes" needs
+    bounds inside the range and no NULLs."""
+    from tests.golden import rowgroup_filter_cases as g
+    ruled_out = 0
+    for name, mn, mx, right, nulls, op, expect in g.CASES:
+        if right is None:
+            continue  # numeric comparison with the NULL literal is decided at row level (nothing is selected)
+        mode = C.c_int32(-1)
+        has_bounds = nulls != g.NUM_VALUES
+        assert built_lib.fgpu_rowgroup_leaf_mode(op, right, int(has_bounds), mn, mx, nulls, g.NUM_VALUES, C.byref(mode)) == 0
+        if mode.value == 2:
+            assert not expect, name
+            ruled_out += 1
+        if not expect and has_bounds:
+            assert mode.value == 2, name
+        if mode.value == 1:
+            assert expect and nulls == 0, name
+    assert ruled_out >= 4
+    # ranges: <, <=, >=, != against [5, 9]
+    cases = [(3, 5, 2), (3, 6, 0), (3, 10, 1), (4, 4, 2), (4, 5, 0), (4, 9, 1), (6, 10, 2), (6, 9, 0), (6, 5, 1), (2, 7, 0), (2, 4, 1)]
+    for op, lit, want in cases:  # logicalplan.Op: 2 !=, 3 <, 4 <=, 5 >, 6 >=
+        mode = C.c_int32(-1)
+        assert built_lib.fgpu_rowgroup_leaf_mode(op, lit, 1, 5, 9, 0, 10, C.byref(mode)) == 0
+        assert mode.value == want, (op, lit, mode.value)
+        if want == 1:  # NULLs in the chunk: "every row passes" is off the table
+            assert built_lib.fgpu_rowgroup_leaf_mode(op, lit, 1, 5, 9, 3, 10, C.byref(mode)) == 0 and mode.value == 0
+    mode = C.c_int32(-1)
+    assert built_lib.fgpu_rowgroup_leaf_mode(2, 7, 1, 7, 7, 2, 10, C.byref(mode)) == 0 and mode.value == 2   # != 7 on a chunk of 7s and NULLs
