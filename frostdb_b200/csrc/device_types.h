@@ -263,6 +263,68 @@ struct TakeDesc {
   long long* out_data[kTakeOut];
 };
 
+// ---- tile aggregate (k_tile_agg, tile_agg.cu): unsorted / short-run / nullable keys -------------------------
+// Row groups the sorted-run kernel cannot take (bit-packed or short-run key columns, NULLs in the keys, fresh
+// L0 records) are scanned CTA-cooperatively: one producer warp stages TILES of every projected column into a
+// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier), the consumer warps aggregate the tile
+// into a CTA-private shared-memory table with 32-bit shared atomics and the table is folded into the global
+// one once per CTA.  Dictionary columns are read as FLAT CODE arrays: fixed-width codes (global dictionary
+// id, or id + 1 with 0 = NULL) derived once per column chunk on the device from the stored hybrid streams
+// (k_flatten), so that a tile of any column is one contiguous, 128-byte aligned byte range.
+constexpr int kTaPlain = 4;   // staged PLAIN columns (distinct leaf + aggregate inputs)
+constexpr int kTaCodes = 6;   // staged flat-code columns (keys + dictionary-leaf columns)
+constexpr int kTaLeaves = 3;  // range leaves (conjunction)
+constexpr int kTaPreds = 3;   // dictionary leaves (conjunction)
+constexpr int kTaKeys = 4;
+constexpr int kTaAggs = 4;
+constexpr int kTaConsumerWarps = 16;
+constexpr int kTaThreads = (kTaConsumerWarps + 1) * 32;  // + one producer warp
+
+struct TileAggRg {
+  uint32_t n_rows;
+  uint32_t _pad;
+  long long lo[kTaLeaves], hi[kTaLeaves];  // inclusive bounds (bits of a double when the leaf compares as float)
+  const uint8_t* plain[kTaPlain];          // PLAIN value arrays (null: the column is not read in this row group)
+  const uint8_t* codes[kTaCodes];          // flat code arrays (null: column absent, every row NULL)
+  const uint8_t* pred_lut[kTaPreds];       // result byte per GLOBAL dictionary id (null: the leaf is decided, passes)
+  uint8_t code_w[kTaCodes];                // bits per code
+  uint8_t code_bias[kTaCodes];             // 1: chunk without NULLs, code = id; 0: code = id + 1, 0 = NULL
+  uint8_t leaf_skip[kTaLeaves];            // 1: decided by statistics / missing-column rules (passes)
+  uint8_t _pad2[8 - (2 * kTaCodes + kTaLeaves) % 8];
+};
+static_assert(sizeof(TileAggRg) % 8 == 0, "copied word-wise into the stage header");
+
+struct TileAggDesc {
+  uint32_t n_rg, n_tiles, tile_rows, n_stages, slot_bytes;
+  uint32_t n_plain, n_codes;
+  uint32_t plain_off[kTaPlain], code_off[kTaCodes];  // byte offsets inside a ring slot
+  uint32_t nl, leaf_plain[kTaLeaves], leaf_flags[kTaLeaves];  // flags: 1 compare as double, 2 column is double, 4 negate
+  uint32_t np, pred_code[kTaPreds], pred_null[kTaPreds];
+  uint32_t nk, key_code[kTaKeys], key_stride[kTaKeys];
+  uint32_t na, agg_plain[kTaAggs], agg_func[kTaAggs];  // AggFunc | is_float << 8
+  uint32_t table_slots;
+  uint32_t rep_log2;             // shared-memory table: every slot has 1 << rep_log2 replicas (lane & (R - 1))
+  uint32_t smem_table;           // 0: atomics go to the global table directly
+  uint32_t cell_off[kTaAggs];    // shared-memory table: byte offset of the aggregate's cell array (behind the counts)
+  uint32_t cell64[kTaAggs];      // 1: 64-bit cells (Min / Max / float64), 0: low word of an int64 Sum
+  uint32_t table_bytes;          // shared-memory table bytes
+  uint32_t chunk_tiles;          // consecutive tiles a CTA takes per turn
+  const TileAggRg* rgs;
+  const uint32_t* rg_first_tile;  // [n_rg + 1]
+  unsigned long long* t_rows;
+  long long* t_agg[kTaAggs];
+  unsigned long long* counters;
+};
+
+// One column chunk to turn into a flat code array (k_flatten).
+struct FlatJob {
+  ChunkDesc chunk;     // resident hybrid image
+  uint8_t* out;        // flat codes, 128-byte aligned, padded
+  uint32_t w, bias;
+  uint32_t first_block;  // prefix over the jobs of one launch: 128-row blocks before this job
+  uint32_t _pad;
+};
+
 struct FinalizeDesc {
   int32_t table_mode, key_words, n_keys, n_aggs;
   uint32_t table_slots;

@@ -336,6 +336,69 @@ int32_t ensure_resident(fgpu_ctx* ctx, Table* table, Part* part, const std::stri
   return FGPU_OK;
 }
 
+int bit_width_u32(uint64_t max_value) {
+  int w = 0;
+  while (w < 64 && (max_value >> w) != 0) w++;
+  return w;
+}
+
+// Flat code arrays of one dictionary column of a part (every row group, one allocation), derived on the device
+// from the resident hybrid image the first time the tile-aggregate kernel needs the column (k_flatten).
+int32_t ensure_flat(fgpu_ctx* ctx, Part* part, const std::string& column) {
+  ColumnImage& img = part->images[column];
+  if (img.flat_dev) return FGPU_OK;
+  if (!img.resident) return fail(FGPU_ERR_INVALID, "flat codes requested for a column that is not resident: " + column);
+  std::vector<FlatJob> jobs;
+  std::vector<ChunkHost*> chs;
+  std::vector<uint64_t> offs;
+  uint64_t bytes = 0;
+  uint32_t blocks = 0;
+  for (RowGroupHost& rg : part->rgs) {
+    auto it = rg.cols.find(column);
+    if (it == rg.cols.end()) continue;
+    ChunkHost& ch = it->second;
+    if (!ch.error.empty() || ch.desc.kind != CK_DICT_STR) continue;
+    uint32_t max_gid = 0;
+    for (uint32_t g : ch.lut_host) max_gid = std::max(max_gid, g);
+    FlatJob j{};
+    j.chunk = ch.desc;
+    j.bias = ch.desc.has_nulls ? 0u : 1u;
+    const int bits = bit_width_u32(uint64_t(max_gid) + 1u - j.bias);
+    j.w = bits <= 8 ? 8u : (bits <= 16 ? 16u : 32u);  // byte-aligned codes: one shared-memory load per row and column
+    j.first_block = blocks;
+    const uint32_t nb = (rg.n_rows + uint32_t(kIndexRows) - 1) / uint32_t(kIndexRows);
+    blocks += nb;
+    offs.push_back(bytes);
+    bytes += (uint64_t(nb) * (kIndexRows / 8) * j.w + 64 + 127) & ~uint64_t(127);
+    jobs.push_back(j);
+    chs.push_back(&ch);
+  }
+  if (jobs.empty()) return FGPU_OK;
+  void* dev = nullptr;
+  CUDA_TRY(cudaMallocAsync(&dev, bytes + jobs.size() * sizeof(FlatJob), ctx->stream));
+  for (size_t i = 0; i < jobs.size(); i++) jobs[i].out = static_cast<uint8_t*>(dev) + offs[i];
+  const void* src = jobs.data();
+  if (void* pin = ctx->arena_take(jobs.size() * sizeof(FlatJob))) {
+    std::memcpy(pin, jobs.data(), jobs.size() * sizeof(FlatJob));
+    src = pin;
+  }
+  FlatJob* d_jobs = reinterpret_cast<FlatJob*>(static_cast<uint8_t*>(dev) + bytes);
+  cudaError_t e = cudaMemcpyAsync(d_jobs, src, jobs.size() * sizeof(FlatJob), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_flatten(d_jobs, uint32_t(jobs.size()), blocks, ctx->sm_count, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(dev, ctx->stream);
+    cudaGetLastError();
+    return fail(FGPU_ERR_CUDA, std::string("flat codes: ") + cudaGetErrorString(e));
+  }
+  img.flat_dev = dev;
+  for (size_t i = 0; i < jobs.size(); i++) {
+    chs[i]->flat = jobs[i].out;
+    chs[i]->flat_w = uint8_t(jobs[i].w);
+    chs[i]->flat_bias = uint8_t(jobs[i].bias);
+  }
+  return FGPU_OK;
+}
+
 // After the stream has been synchronised the host staging of uploaded columns can go.
 void release_staging(fgpu_ctx* ctx) {
   ctx->arena_used = 0;
@@ -347,8 +410,10 @@ void release_staging(fgpu_ctx* ctx) {
 }
 
 void free_part(fgpu_ctx* ctx, Part* p) {
-  for (auto& kv : p->images)
+  for (auto& kv : p->images) {
     if (kv.second.dev) cudaFreeAsync(kv.second.dev, ctx->stream);
+    if (kv.second.flat_dev) cudaFreeAsync(kv.second.flat_dev, ctx->stream);
+  }
 }
 
 struct VisibleRG {
@@ -358,11 +423,6 @@ struct VisibleRG {
   uint8_t leaf_mode[kMaxLeaves] = {0};   // LeafMode per leaf decided from the chunk statistics (LM_EVAL: undecided)
 };
 
-int bit_width_u32(uint64_t max_value) {
-  int w = 0;
-  while (w < 64 && (max_value >> w) != 0) w++;
-  return w;
-}
 
 // One predicate leaf on the host.
 struct LeafHost {
@@ -1210,6 +1270,72 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       B.rd.n_pred = uint32_t(runs_np);
     }
   }
+  // ---- tile aggregate: query-level eligibility (see tile_agg.cu) -------------------------------------
+  // Row groups the sorted-run kernel does not take (bit-packed / short-run / nullable keys, L0 records) go to
+  // the tile-aggregate kernel when the plan is a conjunction of range + dictionary leaves over a dense table
+  // with plain aggregate inputs; what is left after that stays with the general scan kernel.
+  struct TaBatch {
+    TileAggDesc td{};
+    std::vector<TileAggRg> rgs;
+    std::vector<uint32_t> rows, first_tile;
+    size_t o_rg = 0, o_tile = 0;
+    int plain_slot[kTaPlain] = {0}, code_slot[kTaCodes] = {0};
+    uint32_t code_wmax[kTaCodes] = {0};
+    int leaf_q[kTaLeaves] = {0}, pred_q[kTaPreds] = {0}, agg_index[kTaAggs] = {0};
+  } TA;
+  bool ta_q = q.kind != FGPU_PLAN_FILTER && qd.table_mode == TM_DENSE && (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) &&
+              qd.n_keys <= kTaKeys && !getenv("FROSTGPU_NO_TILE");
+  {
+    TileAggDesc& td = TA.td;
+    auto plain_of = [&](int slot) -> int {
+      for (uint32_t i = 0; i < td.n_plain; i++)
+        if (TA.plain_slot[i] == slot) return int(i);
+      if (td.n_plain >= uint32_t(kTaPlain)) return -1;
+      TA.plain_slot[td.n_plain] = slot;
+      return int(td.n_plain++);
+    };
+    auto code_of = [&](int slot) -> int {
+      for (uint32_t i = 0; i < td.n_codes; i++)
+        if (TA.code_slot[i] == slot) return int(i);
+      if (td.n_codes >= uint32_t(kTaCodes)) return -1;
+      TA.code_slot[td.n_codes] = slot;
+      return int(td.n_codes++);
+    };
+    for (int l = 0; l < n_leaves && ta_q; l++) {
+      const LeafDesc& ld = qd.leaves[l];
+      if (ld.slot == 0xff) continue;  // column absent from every row group: ALL / NONE per row group, nothing to evaluate
+      if (qd.slot_type[ld.slot] == ST_DICT) {
+        const int cc = code_of(ld.slot);
+        if (td.np >= uint32_t(kTaPreds) || cc < 0) { ta_q = false; break; }
+        TA.pred_q[td.np] = l;
+        td.pred_code[td.np++] = uint32_t(cc);
+      } else {
+        const int pp = plain_of(ld.slot);
+        if (c.leaves[size_t(l)].null_literal || td.nl >= uint32_t(kTaLeaves) || pp < 0) { ta_q = false; break; }
+        TA.leaf_q[td.nl] = l;
+        td.leaf_plain[td.nl] = uint32_t(pp);
+        td.leaf_flags[td.nl++] = (ld.cmp_float ? 1u : 0u) | (qd.slot_type[ld.slot] == ST_F64 ? 2u : 0u) | (ld.neg ? 4u : 0u);
+      }
+    }
+    for (int k = 0; k < qd.n_keys && ta_q; k++) {
+      const int cc = code_of(qd.keys[k].slot);
+      if (qd.keys[k].is_int64 || cc < 0) { ta_q = false; break; }
+      td.key_code[td.nk] = uint32_t(cc);
+      td.key_stride[td.nk++] = qd.keys[k].dense_stride;
+    }
+    for (int a = 0; a < qd.n_aggs && ta_q; a++) {
+      const AggDesc& ad = qd.aggs[a];
+      if (ad.func == FGPU_AGG_COUNT) continue;
+      const bool simple = ad.prog_len == 1 && qd.prog[ad.prog_off].op == PO_LOAD;
+      const int pp = simple ? plain_of(qd.prog[ad.prog_off].slot) : -1;
+      if ((ad.func != FGPU_AGG_SUM && ad.func != FGPU_AGG_MIN && ad.func != FGPU_AGG_MAX) || td.na >= uint32_t(kTaAggs) || pp < 0) { ta_q = false; break; }
+      TA.agg_index[td.na] = a;
+      td.agg_plain[td.na] = uint32_t(pp);
+      td.cell64[td.na] = (ad.func == FGPU_AGG_SUM && !ad.is_float) ? 0u : 1u;
+      td.agg_func[td.na++] = uint32_t(ad.func) | (ad.is_float ? 0x100u : 0u);
+    }
+  }
+  uint32_t ta_empty_rgs = 0;
   int gi = 0;  // row groups that stay with the general scan kernel
   for (int g0 = 0; g0 < n_rg; g0++) {
     RowGroupHost& rg = *c.rgs[size_t(g0)].rg;
@@ -1323,6 +1449,65 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       lut_fix.erase(std::remove_if(lut_fix.begin(), lut_fix.end(), [&](const std::pair<size_t, size_t>& f) { return f.first >= size_t(g) * n_leaves; }), lut_fix.end());
       continue;  // slot g of the general tables is reused by the next row group
     }
+    // ---- does this row group go to the tile-aggregate kernel? ----
+    if (ta_q && rg.n_rows > 0) {
+      const TileAggDesc& td = TA.td;
+      bool ok = true, none = false;
+      for (int l = 0; l < n_leaves; l++)
+        if (lrt[size_t(g) * n_leaves + l].mode == LM_NONE) none = true;  // conjunction: no row of this row group passes
+      TileAggRg tr{};
+      tr.n_rows = rg.n_rows;
+      bool plain_needed[kTaPlain] = {false};
+      for (uint32_t i = 0; i < td.nl && ok; i++) {
+        const int ql = TA.leaf_q[i];
+        const LeafDesc& ld = qd.leaves[ql];
+        if (lrt[size_t(g) * n_leaves + ql].mode == LM_ALL) { tr.leaf_skip[i] = 1; continue; }
+        plain_needed[td.leaf_plain[i]] = true;
+        if (ld.cmp_float) { std::memcpy(&tr.lo[i], &ld.lo_f, 8); std::memcpy(&tr.hi[i], &ld.hi_f, 8); }
+        else { tr.lo[i] = ld.lo_i; tr.hi[i] = ld.hi_i; }
+      }
+      for (uint32_t i = 0; i < td.na; i++) plain_needed[td.agg_plain[i]] = true;
+      for (uint32_t i = 0; i < td.n_plain && ok && !none; i++) {
+        const ChunkDesc& d = chunks[size_t(g) * n_slots + TA.plain_slot[i]];
+        tr.plain[i] = nullptr;
+        if (!plain_needed[i]) continue;
+        if (d.kind != CK_PLAIN64 || d.has_nulls) { ok = false; break; }
+        tr.plain[i] = d.values;
+      }
+      bool code_needed[kTaCodes] = {false};
+      for (uint32_t i = 0; i < td.np && ok; i++) {
+        const int ql = TA.pred_q[i];
+        const LeafRt& rt = lrt[size_t(g) * n_leaves + ql];
+        tr.pred_lut[i] = nullptr;
+        if (rt.mode != LM_EVAL) continue;  // decided: passes (a NONE row group is dropped as a whole)
+        code_needed[td.pred_code[i]] = true;
+        tr.pred_lut[i] = reinterpret_cast<const uint8_t*>(uintptr_t(c.leaves[size_t(ql)].lut_off) + 1);  // offset + 1, rebased below
+        TA.td.pred_null[i] = rt.null_result;
+      }
+      for (uint32_t i = 0; i < td.nk; i++) code_needed[td.key_code[i]] = true;
+      for (uint32_t i = 0; i < td.n_codes && ok && !none; i++) {
+        const ChunkDesc& d = chunks[size_t(g) * n_slots + TA.code_slot[i]];
+        tr.codes[i] = nullptr;
+        if (!code_needed[i] || d.kind == CK_ABSENT) continue;  // absent column: NULL for every row
+        if (d.kind != CK_DICT_STR) { ok = false; break; }
+        const std::string& name = c.slot_names[size_t(TA.code_slot[i])];
+        int32_t frc = ensure_flat(ctx, c.rgs[size_t(g0)].part, name);
+        if (frc) return frc;
+        const ChunkHost& ch = rg.cols.at(name);
+        if (!ch.flat) { ok = false; break; }
+        tr.codes[i] = ch.flat;
+        tr.code_w[i] = ch.flat_w;
+        tr.code_bias[i] = ch.flat_bias;
+        TA.code_wmax[i] = std::max<uint32_t>(TA.code_wmax[i], ch.flat_w);
+      }
+      if (ok) {
+        lut_fix.erase(std::remove_if(lut_fix.begin(), lut_fix.end(), [&](const std::pair<size_t, size_t>& f) { return f.first >= size_t(g) * n_leaves; }), lut_fix.end());
+        if (none) { ta_empty_rgs++; continue; }
+        TA.rgs.push_back(tr);
+        TA.rows.push_back(rg.n_rows);
+        continue;  // slot g of the general tables is reused by the next row group
+      }
+    }
     first_tile[size_t(g)] = tiles;
     rg_rows[size_t(g)] = rg.n_rows;
     tiles += (rg.n_rows + tile_len - 1) / tile_len;
@@ -1361,6 +1546,62 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     }
     B.first_span.push_back(spans);
     rd.n_spans = spans;
+  }
+
+  // ---- tile aggregate: tile size, ring depth and the shared-memory table -------------------------------
+  if (!TA.rgs.empty()) {
+    TileAggDesc& td = TA.td;
+    auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    td.n_rg = uint32_t(TA.rgs.size());
+    td.table_slots = qd.table_slots;
+    // replicas of small tables: same-address CAS on 64-bit cells serialises, 32 lanes on 17 slots
+    uint32_t rl = 0;
+    while (rl < 5 && (uint64_t(qd.table_slots) << (rl + 1)) <= 2048) rl++;
+    td.rep_log2 = rl;
+    const uint64_t cells = uint64_t(qd.table_slots) << rl;
+    uint64_t tb = (cells * 4 + 7) & ~uint64_t(7);
+    for (uint32_t a = 0; a < td.na; a++) {
+      td.cell_off[a] = uint32_t(tb);
+      tb += (cells * (td.cell64[a] ? 8 : 4) + 7) & ~uint64_t(7);
+    }
+    const uint64_t kSmemMax = 227 * 1024;
+    const int cand[7][2] = {{4096, 3}, {2048, 4}, {4096, 2}, {2048, 3}, {2048, 2}, {1024, 3}, {1024, 2}};
+    auto slot_bytes_for = [&](uint32_t T) {
+      uint64_t off = 0;
+      for (uint32_t i = 0; i < td.n_plain; i++) { td.plain_off[i] = uint32_t(off); off += uint64_t(T) * 8; }
+      for (uint32_t i = 0; i < td.n_codes; i++) {
+        td.code_off[i] = uint32_t(off);
+        off += (uint64_t(T) * std::max<uint32_t>(TA.code_wmax[i], 8) / 8 + 127) & ~uint64_t(127);
+      }
+      return std::max<uint64_t>(off, 128);
+    };
+    bool fits = false;
+    const int force_t = envi("FROSTGPU_TA_TILE", 0), force_s = envi("FROSTGPU_TA_STAGES", 0);
+    for (int smem_table = tb < kSmemMax && !getenv("FROSTGPU_TA_GLOBAL") ? 1 : 0; smem_table >= 0 && !fits; smem_table--) {
+      for (const auto& cs : cand) {
+        if ((force_t && cs[0] != force_t) || (force_s && cs[1] != force_s)) continue;
+        const uint64_t sb = slot_bytes_for(uint32_t(cs[0]));
+        const uint64_t total = 128 + uint64_t(cs[1]) * (256 + sb) + (smem_table ? tb : 0);
+        if (total > kSmemMax) continue;
+        td.tile_rows = uint32_t(cs[0]);
+        td.n_stages = uint32_t(cs[1]);
+        td.slot_bytes = uint32_t(sb);
+        td.smem_table = uint32_t(smem_table);
+        fits = true;
+        break;
+      }
+    }
+    if (!fits) return fail(FGPU_ERR_UNSUPPORTED, "tile aggregate: the projected columns do not fit the shared-memory ring");
+    td.table_bytes = uint32_t(td.smem_table ? tb : 0);
+    uint32_t t = 0;
+    for (uint32_t r : TA.rows) {
+      TA.first_tile.push_back(t);
+      t += (r + td.tile_rows - 1) / td.tile_rows;
+    }
+    TA.first_tile.push_back(t);
+    td.n_tiles = t;
+    td.chunk_tiles = std::max<uint32_t>(1, t / (uint32_t(ctx->sm_count) * 4));  // ~4 turns per CTA: a CTA stays inside one row group for a whole chunk
+    if (const char* e = getenv("FROSTGPU_TA_CHUNK")) td.chunk_tiles = uint32_t(std::max(1, atoi(e)));
   }
 
   // ---- filter-only plans over PLAIN columns: ordered take (take_rows.cu) instead of k_rows ------------
@@ -1470,6 +1711,11 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     B.o_span = align16(B.o_rg + B.rgs.size() * sizeof(RunsRg));
     o_cnt = align16(B.o_span + B.first_span.size() * 4);
   }
+  if (!TA.rgs.empty()) {
+    TA.o_rg = o_cnt;
+    TA.o_tile = align16(TA.o_rg + TA.rgs.size() * sizeof(TileAggRg));
+    o_cnt = align16(TA.o_tile + TA.first_tile.size() * 4);
+  }
   size_t o_take_rg = 0, o_take_span = 0, o_take_count = 0;
   if (take_q) {
     o_take_rg = o_cnt;
@@ -1500,6 +1746,13 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         if (r.pred_runs[i]) r.pred_lut[i] = aux + o_lut + size_t(uintptr_t(r.pred_lut[i]));
     std::memcpy(hostaux.data() + B.o_rg, B.rgs.data(), B.rgs.size() * sizeof(RunsRg));
     std::memcpy(hostaux.data() + B.o_span, B.first_span.data(), B.first_span.size() * 4);
+  }
+  if (!TA.rgs.empty()) {
+    for (TileAggRg& r : TA.rgs)
+      for (int i = 0; i < kTaPreds; i++)
+        if (r.pred_lut[i]) r.pred_lut[i] = aux + o_lut + (size_t(uintptr_t(r.pred_lut[i])) - 1);
+    std::memcpy(hostaux.data() + TA.o_rg, TA.rgs.data(), TA.rgs.size() * sizeof(TileAggRg));
+    std::memcpy(hostaux.data() + TA.o_tile, TA.first_tile.data(), TA.first_tile.size() * 4);
   }
   if (take_q) {
     std::memcpy(hostaux.data() + o_take_rg, take_rgs.data(), take_rgs.size() * sizeof(TakeRg));
@@ -1561,6 +1814,17 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       CUDA_TRY(launch_runs(rd, B.nl, runs_nk, runs_na, ctx->sm_count, s));
       st.kernel_launches++;
       st.row_groups_runs += uint32_t(B.rgs.size());
+    }
+    if (!TA.rgs.empty()) {
+      TileAggDesc& td = TA.td;
+      td.rgs = reinterpret_cast<const TileAggRg*>(aux + TA.o_rg);
+      td.rg_first_tile = reinterpret_cast<const uint32_t*>(aux + TA.o_tile);
+      td.t_rows = qd.t_rows;
+      for (uint32_t a = 0; a < td.na; a++) td.t_agg[a] = qd.t_agg[TA.agg_index[a]];
+      td.counters = qd.counters;
+      CUDA_TRY(launch_tile_agg(td, ctx->sm_count, s));
+      st.kernel_launches++;
+      st.row_groups_tiles += uint32_t(TA.rgs.size());
     }
     CUDA_TRY(launch_scan(qdesc_dev, qd, ctx->sm_count, s));
   }

@@ -2014,6 +2014,43 @@ cudaError_t launch_make_seeds(void* image, uint64_t jobs_off, uint32_t n_jobs, u
   return cudaGetLastError();
 }
 
+// ======================================================================================================
+// k_flatten: dictionary column chunk -> flat code array (one warp per 128-row block).
+//   code = global dictionary id (+ 1 when the chunk has NULLs, 0 = NULL), w = 8, 16 or 32 bits per row.
+// Runs once per (part, column) on the device, from the resident hybrid image; the tile-aggregate kernel
+// then stages any tile of the column with ONE bulk copy (tile_agg.cu).
+// ======================================================================================================
+__global__ void __launch_bounds__(NT) k_flatten(const FlatJob* __restrict__ jobs, uint32_t n_jobs, uint32_t total_blocks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t blk = blockIdx.x * NWARP + warp; blk < total_blocks; blk += gridDim.x * NWARP) {
+    uint32_t lo = 0, hi = n_jobs;  // last job with first_block <= blk
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&jobs[mid].first_block) <= blk) lo = mid; else hi = mid;
+    }
+    const FlatJob& J = jobs[lo];
+    const uint32_t chunk = blk - J.first_block, c0 = chunk * kIndexRows, w = J.w;
+    uint32_t gid[STEPS];
+    decode_dict_chunk(J.chunk, global_seeds(J.chunk, chunk), c0, J.chunk.n_rows, lane, gid);
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+      const uint32_t code = (gid[j] == kNullIdx) ? 0u : gid[j] + 1u - J.bias;  // rows past the end: 0 (padding)
+      const uint32_t r = c0 + j * 32 + lane;
+      if (w == 8) J.out[r] = uint8_t(code);
+      else if (w == 16) reinterpret_cast<uint16_t*>(J.out)[r] = uint16_t(code);
+      else reinterpret_cast<uint32_t*>(J.out)[r] = code;
+    }
+  }
+}
+
+cudaError_t launch_flatten(const FlatJob* d_jobs, uint32_t n_jobs, uint32_t total_blocks, int sm_count, cudaStream_t st) {
+  if (n_jobs == 0 || total_blocks == 0) return cudaSuccess;
+  uint32_t grid = (total_blocks + NWARP - 1) / NWARP;
+  if (grid > uint32_t(sm_count) * 8) grid = uint32_t(sm_count) * 8;
+  k_flatten<<<grid, NT, 0, st>>>(d_jobs, n_jobs, total_blocks);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const ChunkDesc& c, int32_t* out_i32, long long* out_i64, uint8_t* out_valid, int sm_count,
                           cudaStream_t st) {
   uint32_t n_chunks = (c.n_rows + kIndexRows - 1) / kIndexRows;

@@ -25,6 +25,11 @@ cudaError_t runs_blocks_per_sm(const RunsDesc& d, int nl, int nk, int na, int* p
 // filter-only plans over PLAIN columns (take_rows.cu): count per span, scan, ordered write
 cudaError_t launch_take(const TakeDesc& d, int sm_count, cudaStream_t st);
 int take_resident_warps(int sm_count);
+// tile aggregate (tile_agg.cu): TMA-staged column tiles, CTA-private shared-memory table
+cudaError_t launch_tile_agg(const TileAggDesc& d, int sm_count, cudaStream_t st);
+size_t tile_agg_smem_bytes(const TileAggDesc& d);
+// dictionary column chunks -> flat code arrays (kernels.cu)
+cudaError_t launch_flatten(const FlatJob* d_jobs, uint32_t n_jobs, uint32_t total_blocks, int sm_count, cudaStream_t st);
 cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st);
 cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t st);

@@ -50,6 +50,9 @@ struct ChunkHost {
           off_dict64 = -1;
   int64_t dev_seeds = -1, dev_def_seeds = -1;  // seeds derived on the device: offsets inside the image's device-only region
   int64_t off_row_runs = -1, off_row_seeds = -1, dev_row_seeds = -1;  // row-space directory of a nullable run-length column
+  // flat code array of a CK_DICT_STR chunk (device pointer; derived on first use by k_flatten, see tile_agg.cu)
+  const uint8_t* flat = nullptr;
+  uint8_t flat_w = 0, flat_bias = 0;
 };
 
 struct RowGroupHost {
@@ -76,6 +79,7 @@ struct ColumnImage {
   uint64_t seed_jobs_off = 0;    // SeedJob[n_seed_jobs] inside the meta region (device-derived seeds)
   uint32_t n_seed_jobs = 0, max_seed_chunks = 0;
   std::string error;             // whole-column error (a chunk the engine cannot read)
+  void* flat_dev = nullptr;      // flat code arrays of every row group of this column (one allocation) + the job table
 };
 
 struct Part {

@@ -168,7 +168,9 @@ typedef struct fgpu_stats {
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;
   uint32_t row_groups_pruned; /* ruled out by chunk statistics before upload (index/lsm.go:437)      */
-  uint32_t row_groups_runs;   /* scanned by the sorted-run kernel (the rest: general scan kernel)   */
+  uint32_t row_groups_runs;   /* scanned by the sorted-run kernel                                   */
+  uint32_t row_groups_tiles;  /* scanned by the tile-aggregate kernel (the rest: general scan kernel) */
+  uint32_t _reserved;
 } fgpu_stats;
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */
