@@ -10,7 +10,13 @@ One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE).  A step is o
 
 over this rank's parts: 100M rows per GPU (weak scaling), 16 dynamic label columns, parts of 4Mi
 rows sorted the way compaction leaves them, row groups of 1Mi rows.  N > 1 adds the one exchange
-step the path has: an all-gather of the per-rank partial aggregate tables and the merge kernel.
+step the path has, inside the library (fgpu_query_execute_collective): every rank's partial table is
+stored into every rank's peer-mapped mailbox over NVLink and merged behind a flag wait.
+
+The line also carries `parity` (the timed result compared bit-exact with the oracle on the same rows;
+a mismatch fails the run) and `extra` (the other BASELINE.json configurations: cfg 2 latency, cfg 3
+without filter and on unsorted parts, the cfg 5 selectivity sweep), each with kernel time, algorithmic
+bytes and roofline fraction.
 
 `value`  parts resident in HBM before the timed region (fgpu_query_execute only).
 `e2e`    the same query through the public C-ABI from HOST Parquet buffers: every step puts the
@@ -52,6 +58,60 @@ def headline_query_exprs(total_first_row: int, rows: int):
     aggs = [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value"))]
     groups = [lp.Col("labels.l00"), lp.Col("labels.l01")]
     return filt, aggs, groups
+
+
+
+def result_rows(batches):
+    """Result records -> {key tuple: aggregate tuple} (dictionary key columns decoded; aggregates are the trailing
+    columns named func(expr))."""
+    import pyarrow as pa
+    out = {}
+    for b in batches:
+        names = b.schema.names
+        cols = []
+        for i, n in enumerate(names):
+            a = b.column(i)
+            if pa.types.is_dictionary(a.type):
+                a = a.dictionary_decode()
+            vals = a.to_pylist()
+            cols.append([v.decode() if isinstance(v, (bytes, bytearray)) else v for v in vals])
+        nk = sum(1 for n in names if not (n.endswith(")") and "(" in n))
+        order = sorted(range(nk), key=lambda i: names[i])  # key columns by name: both engines may order them differently
+        for r in range(b.num_rows):
+            key = tuple((names[i], cols[i][r]) for i in order)
+            out[key] = tuple(cols[i][r] for i in range(nk, len(names)))
+    return out
+
+
+def parity_of(gpu_rows: dict, ref_rows: dict) -> dict:
+    """Bit-exact comparison of two results (integer aggregates)."""
+    mism = 0
+    for k, v in ref_rows.items():
+        if gpu_rows.get(k) != v:
+            mism += 1
+    mism += sum(1 for k in gpu_rows if k not in ref_rows)
+    return {"checked": True, "groups": len(ref_rows), "gpu_groups": len(gpu_rows), "mismatches": mism}
+
+
+def oracle_rows(bufs, plan_scan, agg_names, threads, sample_rows=0, reps=1):
+    """Runs the oracle over the given Parquet buffers; returns (result rows, best seconds, rows scanned)."""
+    from oracle import oracle as orc
+    table = orc.OracleTable()
+    for b in bufs:
+        table.add_pinned(b.ctypes.data, b.nbytes, b)
+    plan, keep = plan_scan._plan()
+    best, scanned, rows = None, 0, {}
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = table.execute(plan, threads=threads, max_rows=sample_rows)
+        d = time.perf_counter() - t0
+        scanned = r.rows_scanned
+        if not rows:
+            rows = result_rows([r.to_batch(agg_names)])
+        r.close()
+        best = d if best is None else min(best, d)
+    table.close()
+    return rows, best, scanned
 
 
 def load_files(paths):
@@ -163,8 +223,92 @@ def workload_config(rows_per_gpu, n_gpus):
                         "label columns, Filter(timestamp in the middle 50% of the rank's own time range) + Sum(value),Count(value) GROUP BY labels.l00,labels.l01 "
                         "(<=16705 groups); parts of 4Mi rows sorted in compaction order, 1Mi-row row groups, uncompressed, DataPageV2",
             "rows_per_gpu": rows_per_gpu, "label_columns": N_LABELS, "part_rows": bd.PART_ROWS, "row_group_rows": bd.RG_ROWS,
-            "l2": "inputs (>=1.6 GB projected per step per GPU) exceed the 126 MB L2; no explicit flush",
-            "parallelism": f"parts sharded one range per GPU x{n_gpus}, one NCCL all-gather of the partial aggregate tables + k_merge"}
+            "l2": "inputs (>=0.5 GB read per step per GPU) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"parts sharded one range per GPU x{n_gpus}; the partial -> final aggregate step runs inside the library "
+                           "(fgpu_query_execute_collective: NVLink stores into peer-mapped mailboxes, flag wait, merge kernel)"}
+
+
+def run_case(eng, lib, table, rows, kind, filt, groups, aggs, peak, reps=5, env=None, note=None):
+    """One query on resident parts: kernel time (CUDA events around the scan launches), Execute wall time, bytes."""
+    import ctypes as C
+    from frostdb_b200 import _lib
+    from frostdb_b200.physicalplan import GPUScan
+    env = env or {}
+    os.environ.update(env)
+    try:
+        scan = GPUScan(eng, table, filt, kind, groups, aggs)
+        q, keep = scan.prepare()
+        ks, ws, st = [], [], None
+        for i in range(reps + 1):
+            res = C.c_void_p()
+            t0 = time.perf_counter()
+            _lib.check(lib.fgpu_query_execute(eng.handle, q, eng.table_watermark(table), C.byref(res)))
+            w = (time.perf_counter() - t0) * 1e3
+            st = eng.stats(res)
+            lib.fgpu_result_free(res)
+            if i:
+                ks.append(st["scan_kernel_ms"])
+                ws.append(w)
+        lib.fgpu_query_free(q)
+    finally:
+        for k in env:
+            os.environ.pop(k)
+    k = float(np.median(ks))
+    out = {"rows": int(rows), "kernel_ms": round(k, 4), "exec_ms": round(float(np.median(ws)), 4),
+           "algorithmic_bytes": int(st["algorithmic_bytes"]), "GBps": round(st["algorithmic_bytes"] / k / 1e6, 1) if k > 0 else None,
+           "frac": round(st["algorithmic_bytes"] / k / 1e6 / peak, 4) if k > 0 else None, "rows_selected": int(st["rows_selected"]),
+           "result_rows": int(st["groups"]), "row_groups": int(st["row_groups"]), "row_groups_pruned": int(st["row_groups_pruned"]),
+           "row_groups_runs": int(st["row_groups_runs"]), "row_groups_tiles": int(st["row_groups_tiles"])}
+    if note:
+        out["note"] = note
+    return out
+
+
+def extra_configs(eng, lib, rows_per_gpu, peak):
+    """The other BASELINE.json configurations, measured on one GPU next to the headline (N == 1 only)."""
+    from frostdb_b200 import _lib
+    AGG, FILT = _lib.PLAN_AGGREGATE, _lib.PLAN_FILTER
+    ts, val = lp.Col("timestamp"), lp.Col("value")
+    K01 = [lp.Col("labels.l00"), lp.Col("labels.l01")]
+    SC = [lp.Sum(val), lp.Count(val)]
+    out = {}
+    # cfg 3 as BASELINE.json states it: no filter, Sum + Count by two dictionary keys, all 100M rows
+    out["cfg3_sorted_nofilter"] = run_case(eng, lib, TABLE, rows_per_gpu, AGG, None, K01, SC, peak)
+    # cfg 5: filter-only compaction (timestamp, value of the passing rows) and filter + Sum, int64 and dictionary predicates
+    sweep = {}
+    for sel in (0.001, 0.01, 0.1, 0.5, 0.9):
+        f = ts.Lt(lp.Literal(bd.T0 + int(sel * rows_per_gpu)))
+        sweep[f"rows_ts_lt_{sel}"] = run_case(eng, lib, TABLE, rows_per_gpu, FILT, f, [ts, val], [], peak, reps=2)
+        sweep[f"sum_ts_lt_{sel}"] = run_case(eng, lib, TABLE, rows_per_gpu, AGG, f, [], [lp.Sum(val)], peak, reps=3)
+    for sel in (0.001, 0.1, 0.5):  # spread over every row group: no pruning possible
+        f = val.Lt(lp.Literal(int(sel * 1000)))
+        sweep[f"rows_value_lt_{int(sel * 1000)}"] = run_case(eng, lib, TABLE, rows_per_gpu, FILT, f, [ts, val], [], peak, reps=2)
+    fd = lp.Col("labels.l02").Eq(lp.Literal("v000003"))
+    sweep["rows_l02_eq"] = run_case(eng, lib, TABLE, rows_per_gpu, FILT, fd, [ts, val], [], peak, reps=2)
+    sweep["sum_l02_eq"] = run_case(eng, lib, TABLE, rows_per_gpu, AGG, fd, [], [lp.Sum(val)], peak, reps=3)
+    out["cfg5_selectivity_sweep_sorted_100M"] = sweep
+    out["cfg3_sorted_sum_by_l02_short_runs"] = run_case(eng, lib, TABLE, rows_per_gpu, AGG, None, [lp.Col("labels.l02")], [lp.Sum(val)], peak)
+    # cfg 3 on UNSORTED parts (arrival order, table.go:1410-1426): bit-packed keys, the tile-aggregate kernel
+    n_un = min(rows_per_gpu, env_int("FROSTGPU_BENCH_UNSORTED_ROWS", 32 * 1024 * 1024))
+    paths = bd.generate_parts(n_un, N_LABELS, sort=False)
+    for pth in paths:
+        eng.put_parquet("bench_unsorted", np.fromfile(pth, dtype=np.uint8))
+    lo, hi = bd.T0 + n_un // 4, bd.T0 + (3 * n_un) // 4
+    f50 = lp.And(ts.GtEq(lp.Literal(lo)), ts.Lt(lp.Literal(hi)))
+    out["cfg3_unsorted_nofilter"] = run_case(eng, lib, "bench_unsorted", n_un, AGG, None, K01, SC, peak)
+    out["cfg3_unsorted_filter50"] = run_case(eng, lib, "bench_unsorted", n_un, AGG, f50, K01, SC, peak)
+    out["cfg3_unsorted_general_kernel"] = run_case(eng, lib, "bench_unsorted", n_un, AGG, None, K01, SC, peak, reps=2, env={"FROSTGPU_NO_TILE": "1"},
+                                                  note="the same query with the tile-aggregate kernel switched off (k_scan)")
+    eng.drop_table("bench_unsorted")
+    # cfg 2: 1M rows, 4 label columns, Filter(timestamp range 50%) + Sum(value) GROUP BY labels.l00 (C = 64): latency
+    n2 = 1_000_000
+    for pth in bd.generate_parts(n2, 4, part_rows=n2, rg_rows=bd.RG_ROWS):
+        eng.put_parquet("bench_cfg2", np.fromfile(pth, dtype=np.uint8))
+    f2 = lp.And(ts.Gt(lp.Literal(bd.T0 + n2 // 4)), ts.Lt(lp.Literal(bd.T0 + (3 * n2) // 4)))
+    out["cfg2_1M_rows_latency"] = run_case(eng, lib, "bench_cfg2", n2, AGG, f2, [lp.Col("labels.l00")], [lp.Sum(val)], peak, reps=20,
+                                           note="launch / latency bound: exec_ms is the number")
+    eng.drop_table("bench_cfg2")
+    return out
 
 
 def main():
@@ -225,55 +369,32 @@ def main():
                         union.append(v)
             unions[col] = union
             eng.dict_preload(TABLE, col, union)
+
+        def exchange(handle):  # the mailbox handles travel once, at setup
+            allh = [None] * world
+            dist.all_gather_object(allh, handle)
+            return allh
+        eng.comm_open(rank, world, exchange, slot_bytes=8 << 20)
     t_up = time.perf_counter()
     for b in bufs:
         eng.put_parquet(TABLE, b)
     t_up = time.perf_counter() - t_up
 
     filt, aggs, groups = headline_query_exprs(first_row, rows_per_gpu)
+    agg_names = [a.Name() for a in aggs]
     scan = GPUScan(eng, TABLE, filt, _lib.PLAN_AGGREGATE, groups, aggs)
     q, keep = scan.prepare()
     tx = eng.table_watermark(TABLE)
-    q_main, tx_main = q, tx
+    execute = lib.fgpu_query_execute_collective if world > 1 else lib.fgpu_query_execute
 
-    def step_single():
+    def step(q_=None, tx_=None):
+        """ONE C call per step: scan (+ at N > 1 the exchange and the merge, inside the library) -> result record."""
         res = C.c_void_p()
-        _lib.check(lib.fgpu_query_execute(eng.handle, q, tx, C.byref(res)))
+        _lib.check(execute(eng.handle, q if q_ is None else q_, tx if tx_ is None else tx_, C.byref(res)))
         st = eng.stats(res)
         batches = list(eng.drain(res))
         lib.fgpu_result_free(res)
         return st, batches
-
-    gathered = {}
-
-    def step_multi(q=None, tx=None):
-        q = q_main if q is None else q
-        tx = tx_main if tx is None else tx
-        res, ptr, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
-        _lib.check(lib.fgpu_query_execute_partial(eng.handle, q, tx, C.byref(res), C.byref(ptr), C.byref(nbytes)))
-        n8 = nbytes.value // 8
-        # zero-copy view of the library's partial table (the scan has completed on its stream)
-        mine = torch.as_tensor(_DevMem(ptr.value, nbytes.value), device="cuda")
-        additive = C.c_int32(0)
-        _lib.check(lib.fgpu_result_partial_is_additive(res, C.byref(additive)))
-        if additive.value and os.environ.get("FROSTGPU_BENCH_ALLREDUCE"):
-            # dense table of counts and integer sums: the partial -> final step can be one in-place all-reduce
-            # (measured at N=2: 0.74 ms/step against 0.63 for all-gather + k_merge, so the gather stays the default)
-            dist.all_reduce(mine, op=dist.ReduceOp.SUM)
-            torch.cuda.current_stream().synchronize()
-            _lib.check(lib.fgpu_result_merge_partials(eng.handle, res, None, 0, 0))
-        else:
-            if "buf" not in gathered or gathered["buf"].numel() != n8 * world:
-                gathered["buf"] = torch.empty(n8 * world, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(gathered["buf"], mine)
-            torch.cuda.current_stream().synchronize()
-            _lib.check(lib.fgpu_result_merge_partials(eng.handle, res, gathered["buf"].data_ptr(), nbytes.value, world))
-        st = eng.stats(res)
-        batches = list(eng.drain(res))
-        lib.fgpu_result_free(res)
-        return st, batches
-
-    step = step_multi if world > 1 else step_single
 
     def sync_all():
         torch.cuda.synchronize()
@@ -306,6 +427,7 @@ def main():
     dt = float(tmax.item())
     total_rows = rows_per_gpu * world
     value = total_rows * args.steps / dt
+    gpu_rows = result_rows(batches)  # the last timed step's record (at N > 1: the merged result, on every rank)
 
     # ---- e2e: host Parquet buffers -> result record, every step --------------------------------------
     # The parts sit in page-locked host memory (where the Go side would have written them); a step
@@ -330,18 +452,11 @@ def main():
                 eng.dict_preload(E2E, col, union)
             for pb in pinned:
                 eng.put_parquet(E2E, pb.array, borrow=True)
-            if world == 1:
-                out = []
-                scan_e.SetNext(_Collect(out))
-                scan_e.Execute(None)
-                h2d["bytes"] = scan_e.last_stats["h2d_bytes"]
-                d2h = sum(x.nbytes for x in out)
-            else:  # partial table per rank -> all-gather -> merge, as in the resident run
-                qe, keep_e = scan_e.prepare()
-                st_e, batches_e = step_multi(qe, eng.table_watermark(E2E))
-                lib.fgpu_query_free(qe)
-                h2d["bytes"] = st_e["h2d_bytes"]
-                d2h = sum(x.nbytes for x in batches_e)
+            qe, keep_e = scan_e.prepare()  # the shim prepares per Execute; equal plans share their compiled state
+            st_e, batches_e = step(qe, eng.table_watermark(E2E))
+            lib.fgpu_query_free(qe)
+            h2d["bytes"] = st_e["h2d_bytes"]
+            d2h = sum(x.nbytes for x in batches_e)
             eng.drop_table(E2E)
             return d2h
 
@@ -362,82 +477,86 @@ def main():
         e2e = {"value": rows_per_gpu * world * e2e_steps / de, "unit": "rows/s", "h2d_bytes_per_step": int(h2d["bytes"]),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1000.0 * de / e2e_steps,
                "note": "every step: fgpu_part_put_parquet(BORROW_PINNED) of all parts from page-locked host memory (footer/page "
-                       "parse), fgpu_query_execute (builds + uploads the projected columns, then the scan), result record read "
+                       "parse), fgpu_query_prepare + execute (builds + uploads the projected columns, then the scan), result record read "
                        "back, fgpu_table_drop"}
         for pb in pinned:
             pb.close()
 
-    # ---- CPU baseline (rank 0, N == 1) ------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not os.environ.get("FROSTGPU_SKIP_CPU"):
-        from oracle import oracle as orc
+    # ---- parity of the timed result + CPU baseline -------------------------------------------------------
+    # Every rank runs the oracle (test infrastructure, oracle/) over ITS OWN 100M rows with the same plan; the
+    # per-rank oracle results are added up (Sum and Count are additive) and compared bit for bit with the record the
+    # last timed step returned.  At N == 1 the same oracle runs are the cpu_baseline (best of 3).
+    cpu, parity = None, {"checked": False}
+    if not os.environ.get("FROSTGPU_SKIP_CPU"):
         cores = os.cpu_count() or 1
-        sample_rows = min(rows_per_gpu, env_int("FROSTGPU_REF_SAMPLE_ROWS", 128 * bd.RG_ROWS))
-        need_parts = (sample_rows + bd.PART_ROWS - 1) // bd.PART_ROWS
-        table = orc.OracleTable()
-        for b in bufs[:need_parts]:
-            table.add_pinned(b.ctypes.data, b.nbytes, b)
-        plan, keep2 = scan._plan()
-        best, scanned = None, 0
-        for _ in range(3):
-            t0 = time.perf_counter()
-            r = table.execute(plan, threads=cores, max_rows=sample_rows)
-            d = time.perf_counter() - t0
-            scanned = r.rows_scanned
-            r.close()
-            best = d if best is None else min(best, d)
-        table.close()
-        cpu = {"value": scanned / best, "unit": "rows/s", "cores": cores, "kind": "port",
-               "sample": f"{scanned} rows of the same parts, best of 3, C port of the reference chain (oracle/frost_oracle.c)"}
+        threads = max(1, cores // world)
+        ref_rows, best, scanned = oracle_rows(bufs, scan, agg_names, threads, sample_rows=0, reps=3 if world == 1 else 1)
+        if world > 1:
+            allr = [None] * world
+            dist.all_gather_object(allr, ref_rows)
+            merged = {}
+            for rr in allr:
+                for k_, v_ in rr.items():
+                    merged[k_] = tuple(a + b_ for a, b_ in zip(merged[k_], v_)) if k_ in merged else v_
+            ref_rows = merged
+        parity = parity_of(gpu_rows, ref_rows)
+        parity["rows"] = int(total_rows)
+        parity["how"] = ("oracle (oracle/frost_oracle.c) over the same %d rows per rank, per-rank results added; compared bit-exact with the "
+                         "record of the last timed step" % rows_per_gpu)
+        if world == 1:
+            cpu = {"value": scanned / best, "unit": "rows/s", "cores": threads, "kind": "port",
+                   "sample": f"{scanned} rows of the same parts, best of 3, C port of the reference chain (oracle/frost_oracle.c)"}
 
+    extra = None
+    if rank == 0 and world == 1 and not os.environ.get("FROSTGPU_SKIP_EXTRA"):
+        extra = extra_configs(eng, lib, rows_per_gpu, measured_peak()[0])
+
+    rc = 0
     if rank == 0:
         peak, peak_src = measured_peak()
         avg_scan_ms = float(np.mean(scan_ms))
         achieved = alg_bytes / (avg_scan_ms * 1e-3) / 1e9 if avg_scan_ms > 0 else 0.0
         # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this same
-        # workload (profiles/r1_traffic.json), only when the launch processes the same bytes
-        traffic = None
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
-                tr = json.load(f)
-            if tr["workload_rows_per_gpu"] == rows_per_gpu and abs(tr["algorithmic_bytes"] - alg_bytes) <= 0.01 * alg_bytes:
-                traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
-        except (OSError, KeyError, ValueError):
-            pass
+        # workload (profiles/*_traffic.json), only when the launch processes the same bytes
+        traffic, traffic_src = None, None
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tr = json.load(f)
+                if tr["workload_rows_per_gpu"] == rows_per_gpu and abs(tr["algorithmic_bytes"] - alg_bytes) <= 0.01 * alg_bytes:
+                    traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+                    traffic_src = f"profiles/{name} (ncu --set full capture of this workload's scan launch; not re-measured in this run)"
+                    break
+            except (OSError, KeyError, ValueError):
+                pass
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(rows_per_gpu, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fgpu::k_runs (sorted-run scan; fgpu::k_scan takes unsorted / nullable-key row groups)", "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes),
-                         "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "fgpu::k_runs (sorted-run scan); unsorted / short-run / nullable keys: fgpu::k_tile_agg, see extra",
+                         "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "groups": int(st["groups"]), "rows_selected_per_gpu": int(st["rows_selected"]),
+            "parity": parity, "groups": int(st["groups"]), "rows_selected_per_gpu": int(st["rows_selected"]),
+            "rows_touched_per_gpu": int(rows_per_gpu - st["row_groups_pruned"] * bd.RG_ROWS) if rows_per_gpu % bd.RG_ROWS == 0 else None,
+            "row_groups": {"scanned": int(st["row_groups"]), "pruned": int(st["row_groups_pruned"])},
             "setup": {"generate_s": round(t_gen, 2), "upload_s": round(t_up, 2), "parquet_bytes_per_gpu": int(file_bytes)},
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
+        if parity.get("checked") and parity["mismatches"]:
+            print(f"bench.py: PARITY FAILURE: {parity['mismatches']} of {parity['groups']} groups differ from the oracle", file=sys.stderr)
+            rc = 3
     lib.fgpu_query_free(q)
+    if world > 1:
+        sync_all()
+        eng.comm_close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-class _Collect:
-    def __init__(self, out):
-        self.out = out
-
-    def Callback(self, ctx, r):
-        self.out.append(r)
-
-    def Finish(self, ctx):
-        return None
-
-
-class _DevMem:
-    """__cuda_array_interface__ wrapper so torch can view library-owned device memory without a copy."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+    if rc:
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

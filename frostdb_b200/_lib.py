@@ -35,6 +35,7 @@ SCALAR_NULL, SCALAR_INT64, SCALAR_FLOAT64, SCALAR_STRING = 0, 1, 2, 3
 EXPR_COLUMN, EXPR_DYNCOLUMN, EXPR_LITERAL, EXPR_BINARY = 1, 2, 3, 4
 PLAN_AGGREGATE, PLAN_DISTINCT, PLAN_FILTER = 1, 2, 3
 PUT_DEFAULT, PUT_BORROW_PINNED = 0, 1
+COMM_HANDLE_BYTES = 128
 
 
 class FrostGPUError(RuntimeError):
@@ -129,6 +130,12 @@ _SIGNATURES = {
     "fgpu_query_execute_partial": ([C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)], C.c_int32),
     "fgpu_result_merge_partials": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32], C.c_int32),
     "fgpu_result_partial_is_additive": ([C.c_void_p, C.POINTER(C.c_int32)], C.c_int32),
+    "fgpu_comm_export": ([C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p], C.c_int32),
+    "fgpu_comm_open": ([C.c_void_p, C.c_void_p], C.c_int32),
+    "fgpu_comm_close": ([C.c_void_p], C.c_int32),
+    "fgpu_query_execute_collective": ([C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int32),
+    "fgpu_query_execute_collective_begin": ([C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int32),
+    "fgpu_query_execute_collective_end": ([C.c_void_p, C.c_void_p], C.c_int32),
     "fgpu_rowgroup_leaf_mode": ([C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int32)], C.c_int32),
     "fgpu_part_decode_column": ([C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_void_p], C.c_int32),
     "fgpu_parquet_describe": ([C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int32),

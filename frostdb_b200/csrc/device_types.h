@@ -277,7 +277,7 @@ constexpr int kTaLeaves = 3;  // range leaves (conjunction)
 constexpr int kTaPreds = 3;   // dictionary leaves (conjunction)
 constexpr int kTaKeys = 4;
 constexpr int kTaAggs = 4;
-constexpr int kTaConsumerWarps = 16;
+constexpr int kTaConsumerWarps = 24;
 constexpr int kTaThreads = (kTaConsumerWarps + 1) * 32;  // + one producer warp
 
 struct TileAggRg {
@@ -323,6 +323,38 @@ struct FlatJob {
   uint32_t w, bias;
   uint32_t first_block;  // prefix over the jobs of one launch: 128-row blocks before this job
   uint32_t _pad;
+};
+
+// Dense table -> compacted result columns for the cached Execute path (k_finalize_dense): dictionary indices as
+// uint32 (0xffffffff = NULL), aggregates as raw 8 bytes, so that the host only copies columns.
+struct DenseOut {
+  uint32_t table_slots, max_out, n_keys, n_aggs;
+  uint32_t stride[kMaxKeys], radix[kMaxKeys];
+  const unsigned long long* t_rows;
+  const long long* t_agg[kMaxAggs];  // null: Count (the row count)
+  const unsigned long long* counters;  // the query's counters: [0..3] travel in the header
+  uint8_t* out;  // [header 256 B: count u32 @0, counters u64 x4 @32, any_null u32 per key @64][n_keys x max_out u32 (8-byte aligned)][n_aggs x max_out i64]
+};
+
+// ---- partial-table exchange between the GPUs of one node (comm.cu) ---------------------------------------
+constexpr int kMaxRanks = 16;
+struct CommPush {
+  const uint8_t* src;                  // this rank's partial table
+  unsigned long long bytes;            // multiple of 16
+  unsigned long long seq;
+  int32_t n, _pad;
+  uint8_t* dst[kMaxRanks];             // slot [my rank] of the current set in every rank's mailbox
+  unsigned long long* flag[kMaxRanks]; // flag pair {seq, bytes} [my rank] of the current set in every rank's mailbox
+};
+struct CommWait {
+  const unsigned long long* flags;     // this rank's flags of the current set: {seq, bytes} per rank
+  unsigned long long seq, bytes, timeout_ns;
+  unsigned long long* counters;        // the query's counters: [3] = 1 timeout, 2 table shapes differ
+  int32_t n, _pad;
+};
+struct CommMerge {
+  const uint8_t* src[kMaxRanks];       // the slots of the current set in this rank's mailbox
+  int32_t n, _pad;
 };
 
 struct FinalizeDesc {

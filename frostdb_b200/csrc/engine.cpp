@@ -4,6 +4,7 @@
 // There is deliberately no CPU execution path in this file: without a CUDA device fgpu_init fails
 // with FGPU_ERR_NO_DEVICE and nothing else can run.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -15,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <set>
 #include <sstream>
 #include <string>
@@ -119,7 +121,31 @@ const char* agg_string(int f) {  // logicalplan.AggFunc.String(), expr.go:731-75
 
 }  // namespace
 
+// Mailbox communicator of one rank (see comm.cu).
+struct CommHandle {  // what travels between the ranks (FGPU_COMM_HANDLE_BYTES)
+  uint32_t magic;
+  int32_t device;
+  uint64_t pid, ptr, total, slot_bytes;
+  int32_t n, rank;
+  cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(CommHandle) <= FGPU_COMM_HANDLE_BYTES, "handle fits its blob");
+constexpr uint32_t kCommMagic = 0x46474d42u;  // "FGMB"
+constexpr size_t kCommDataOff = 4096;        // flags live in front of the slots
+
+struct Comm {
+  int rank = -1, n = 0;
+  uint64_t slot_bytes = 0, total = 0, seq = 0;
+  uint8_t* mailbox = nullptr;  // [flags: 2 sets x kMaxRanks x {seq, bytes}] ... [2 sets x n slots]
+  bool open = false;
+  uint8_t* peer[kMaxRanks] = {nullptr};
+  bool peer_ipc[kMaxRanks] = {false};
+  size_t flag_off(uint64_t set, int r) const { return (size_t(set) * kMaxRanks + size_t(r)) * 16; }
+  size_t data_off(uint64_t set, int r) const { return kCommDataOff + (size_t(set) * size_t(n) + size_t(r)) * slot_bytes; }
+};
+
 struct fgpu_ctx {
+  Comm comm;
   int device = 0;
   int sm_count = 148;
   int tile_rows = kTileRows;
@@ -129,6 +155,7 @@ struct fgpu_ctx {
   std::map<std::string, Table> tables;
   std::vector<ColumnImage*> pending_uploads;  // staging to release after the next stream sync
   uint64_t epoch_counter = 0;                 // source of Table::epoch stamps
+  std::map<std::string, std::shared_ptr<struct QueryPlan>> plans;  // by plan signature (bounded, see fgpu_query_prepare)
   // page-locked arena for column metadata on its way to the device: a pageable source would make every
   // cudaMemcpyAsync wait for the transfers queued before it.  Reset by release_staging() after a sync.
   uint8_t* arena = nullptr;
@@ -148,6 +175,28 @@ struct fgpu_ctx {
     arena_used = off + n;
     return arena + off;
   }
+  // page-locked blocks handed to compiled plans (result images): recycled, only released at shutdown — freeing
+  // page-locked memory synchronises the device, which must not happen while a peer's exchange kernel waits for us
+  std::multimap<size_t, uint8_t*> pinned_free;
+  uint8_t* pinned_take(size_t bytes, size_t* cap) {
+    size_t want = 4096;
+    while (want < bytes) want <<= 1;
+    auto it = pinned_free.lower_bound(want);
+    if (it != pinned_free.end() && it->first <= want * 2) {
+      uint8_t* p = it->second;
+      *cap = it->first;
+      pinned_free.erase(it);
+      return p;
+    }
+    uint8_t* p = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    *cap = want;
+    return p;
+  }
+  void pinned_give(uint8_t* p, size_t cap) { pinned_free.emplace(cap, p); }
   // page-locked scratch for the per-query descriptor upload and the counters read-back (guarded by mu)
   uint8_t* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -182,11 +231,14 @@ struct PhaseClock {
   }
 };
 
-struct fgpu_query {
+// A prepared plan.  Prepared queries with the same plan text share ONE of these through the context's plan table,
+// so that the shim's prepare-per-Execute still reuses the compiled plan and its device state.
+struct QueryPlan {
   // the compiled plan of the last Execute, reused while the table (its parts, its dictionaries) and the read
   // transaction are the same: a prepared query re-executed on an unchanged table skips plan compilation
   mutable std::shared_ptr<void> plan_cache;  // Compiled
   mutable uint64_t cache_epoch = 0, cache_tx = 0;
+  mutable std::string cache_env;  // the FROSTGPU_* development switches the plan was compiled under
   fgpu_ctx* ctx = nullptr;
   std::string table;
   int32_t kind = 0;
@@ -214,6 +266,11 @@ struct fgpu_query {
     }
     return "?";
   }
+};
+
+struct fgpu_query {
+  fgpu_ctx* ctx = nullptr;
+  std::shared_ptr<QueryPlan> plan;
 };
 
 struct KeyOut {
@@ -245,6 +302,11 @@ struct fgpu_result {
   bool finalized = false;
   bool rows_plan = false;
   bool rows_no_nulls = false;  // rows plan produced by the take kernels: no projected value is NULL
+  // collective Execute between its two halves: the partial table is pushed, the merge is still to come
+  bool pending = false;
+  void* pending_cached = nullptr;              // ExecCache: the plan-owned device state holds the table (else `table`)
+  std::shared_ptr<void> plan_keep;             // keeps that plan alive
+  uint64_t pending_seq = 0, pending_bytes = 0;
 };
 
 namespace {
@@ -510,7 +572,45 @@ uint8_t stats_leaf_mode(int64_t lo, int64_t hi, bool neg, int64_t mn, int64_t mx
   return inside ? LM_NONE : ((disjoint && no_nulls) ? LM_ALL : LM_EVAL);
 }
 
+// The decision compile() takes for an int64 range leaf on one chunk, also behind the host-only test hook
+// fgpu_rowgroup_leaf_mode: an all-NULL chunk has no usable bounds (nothing is decided from statistics).
+uint8_t chunk_leaf_mode(int64_t lo, int64_t hi, bool neg, bool has_bounds, int64_t mn, int64_t mx, int64_t null_count, int64_t num_values) {
+  if (!has_bounds || (null_count >= 0 && null_count == num_values)) return LM_EVAL;
+  return stats_leaf_mode(lo, hi, neg, mn, mx, null_count == 0);
+}
+
+// Device and page-locked state of a compiled plan that every Execute of a prepared query reuses while the plan is
+// valid (same table epoch, same read transaction): the descriptor block is uploaded once, the aggregate table and
+// its counters are one persistent allocation, and the table comes back to page-locked memory with ONE copy and ONE
+// stream synchronisation per Execute; dense tables of this size are compacted into the result record on the host.
+struct ExecCache {
+  DevBuf aux, table, out;         // descriptors; [aggregate table | counters 128 B]; compacted result image
+  DenseOut dout{};
+  size_t out_bytes = 0;
+  std::vector<std::unique_ptr<OwnedColumn>> dict_template;  // per key: the whole dictionary, ready to copy (small dictionaries)
+  fgpu_ctx* ctx = nullptr;
+  uint8_t* pinned = nullptr;      // host image of the compacted result (from the context's page-locked pool)
+  size_t pinned_cap = 0;
+  size_t table_bytes = 0;
+  bool ready = false;
+  QueryDesc qd{};
+  const QueryDesc* qdesc_dev = nullptr;
+  bool has_runs = false, has_ta = false;
+  RunsDesc rd{};
+  int runs_nl = 0, runs_nk = 0, runs_na = 0;
+  TileAggDesc td{};
+  fgpu_stats stats{};             // everything about the scan that does not change between Executes
+  std::vector<KeyOut> keys;       // with the dictionary snapshots
+  std::vector<uint32_t> dense_radix;
+  std::vector<std::string> agg_names;
+  std::vector<uint8_t> agg_is_float;
+  ~ExecCache() {
+    if (pinned && ctx) ctx->pinned_give(pinned, pinned_cap);
+  }
+};
+
 struct Compiled {
+  std::unique_ptr<ExecCache> exec;
   std::vector<VisibleRG> rgs;
   std::vector<std::string> slot_names;
   std::vector<uint8_t> slot_types;
@@ -528,7 +628,7 @@ struct Compiled {
   bool runs_shape = false;  // dense keys, conjunction of numeric leaves, plain aggregate inputs (any number of them)
 };
 
-int32_t compile_filter(const fgpu_query& q, int node, Compiled* c, std::map<std::string, int>& slot_of) {
+int32_t compile_filter(const QueryPlan& q, int node, Compiled* c, std::map<std::string, int>& slot_of) {
   const ExprNode& e = q.exprs[size_t(node)];
   if (e.kind != FGPU_EXPR_BINARY) return fail(FGPU_ERR_UNSUPPORTED, "unsupported boolean expression");
   if (e.op == FGPU_OP_AND || e.op == FGPU_OP_OR) {
@@ -565,7 +665,7 @@ int32_t compile_filter(const fgpu_query& q, int node, Compiled* c, std::map<std:
   return FGPU_OK;
 }
 
-int32_t compile_agg_expr(const fgpu_query& q, int node, std::map<std::string, int>& slot_of, const Compiled& c,
+int32_t compile_agg_expr(const QueryPlan& q, int node, std::map<std::string, int>& slot_of, const Compiled& c,
                          std::vector<ProgOp>* prog, bool* any_float, bool* any_int_col) {
   const ExprNode& e = q.exprs[size_t(node)];
   if (e.kind == FGPU_EXPR_COLUMN) {
@@ -602,7 +702,7 @@ int32_t compile_agg_expr(const fgpu_query& q, int node, std::map<std::string, in
   return fail(FGPU_ERR_UNSUPPORTED, "unsupported aggregate expression");
 }
 
-void collect_columns(const fgpu_query& q, int node, std::vector<std::string>* out) {
+void collect_columns(const QueryPlan& q, int node, std::vector<std::string>* out) {
   if (node < 0) return;
   const ExprNode& e = q.exprs[size_t(node)];
   if (e.kind == FGPU_EXPR_COLUMN) out->push_back(e.name);
@@ -612,9 +712,83 @@ void collect_columns(const fgpu_query& q, int node, std::vector<std::string>* ou
   }
 }
 
+// The row-group filter LSM.Scan applies to the row groups of Parquet parts before they reach the plan
+// (index/lsm.go:437; expr/filter.go:208-268 builds And / Or / BinaryScalarExpr, everything else is AlwaysTrue;
+// expr/binaryscalarexpr.go:42-190 answers "may this chunk hold a matching value" from the null count and the
+// bounds).  Its rules for a column that is MISSING from the row group (:47-73) differ from the physical plan's
+// (physicalplan/binaryscalarexpr.go:47-73): `missing == 5`, `missing != 5`, `missing != ""` and every ordering
+// comparison drop the row group here, so its rows never reach the plan.
+int stat_compare(const ChunkHost& ch, bool use_max, const ExprNode& lit, bool* ok) {
+  *ok = false;
+  if (ch.phys == PT_INT64 && lit.lit_type == FGPU_SCALAR_INT64 && ch.has_minmax) {
+    const int64_t v = use_max ? ch.max_bits : ch.min_bits;
+    *ok = true;
+    return v < lit.lit_i ? -1 : (v > lit.lit_i ? 1 : 0);
+  }
+  if (ch.phys == PT_DOUBLE && lit.lit_type == FGPU_SCALAR_FLOAT64 && ch.has_minmax) {
+    double v;
+    std::memcpy(&v, use_max ? &ch.max_bits : &ch.min_bits, 8);
+    *ok = true;
+    return v < lit.lit_f ? -1 : (v > lit.lit_f ? 1 : 0);
+  }
+  if (ch.phys == PT_BYTE_ARRAY && lit.lit_type == FGPU_SCALAR_STRING && ch.has_minmax_str) {
+    const std::string& v = use_max ? ch.max_str : ch.min_str;
+    *ok = true;
+    const int c = v.compare(lit.lit_bytes);
+    return c < 0 ? -1 : (c > 0 ? 1 : 0);
+  }
+  return 0;
+}
+
+bool rg_may_match(const QueryPlan& q, int node, const RowGroupHost& rg) {
+  if (node < 0) return true;
+  const ExprNode& e = q.exprs[size_t(node)];
+  if (e.kind != FGPU_EXPR_BINARY) return true;
+  if (e.op == FGPU_OP_AND) return rg_may_match(q, e.left, rg) && rg_may_match(q, e.right, rg);
+  if (e.op == FGPU_OP_OR) return rg_may_match(q, e.left, rg) || rg_may_match(q, e.right, rg);
+  if (e.op < FGPU_OP_EQ || e.op > FGPU_OP_GT_EQ) return true;  // AlwaysTrueFilter
+  const ExprNode& l = q.exprs[size_t(e.left)];
+  const ExprNode& lit = q.exprs[size_t(e.right)];
+  if (l.kind != FGPU_EXPR_COLUMN || lit.kind != FGPU_EXPR_LITERAL) return true;
+  auto it = rg.cols.find(l.name);
+  if (it == rg.cols.end()) {  // :47-73
+    if (lit.lit_type == FGPU_SCALAR_NULL) {
+      if (e.op == FGPU_OP_EQ) return true;
+      if (e.op == FGPU_OP_NOT_EQ) return false;
+    }
+    if (lit.lit_type == FGPU_SCALAR_STRING) {
+      if (e.op == FGPU_OP_EQ && lit.lit_bytes.empty()) return true;
+      if (e.op == FGPU_OP_NOT_EQ && !lit.lit_bytes.empty()) return true;
+    }
+    return false;
+  }
+  const ChunkHost& ch = it->second;
+  const int64_t nulls = ch.null_count;  // -1: not recorded
+  const bool full_of_nulls = nulls >= 0 && uint64_t(nulls) == rg.n_rows;
+  bool ok;
+  if (e.op == FGPU_OP_EQ) {
+    if (lit.lit_type == FGPU_SCALAR_NULL) return nulls != 0;
+    if (full_of_nulls) return false;
+    const int cmax = stat_compare(ch, true, lit, &ok);
+    if (!ok) return true;
+    const int cmin = stat_compare(ch, false, lit, &ok);
+    if (!ok) return true;
+    return cmax >= 0 && cmin <= 0;
+  }
+  if (lit.lit_type == FGPU_SCALAR_NULL) return true;
+  if (full_of_nulls) return false;
+  switch (e.op) {
+    case FGPU_OP_LT_EQ: { const int c = stat_compare(ch, false, lit, &ok); return !ok || c <= 0; }
+    case FGPU_OP_LT: { const int c = stat_compare(ch, false, lit, &ok); return !ok || c < 0; }
+    case FGPU_OP_GT: { const int c = stat_compare(ch, true, lit, &ok); return !ok || c > 0; }
+    case FGPU_OP_GT_EQ: { const int c = stat_compare(ch, true, lit, &ok); return !ok || c >= 0; }
+    default: return true;  // != : left to the execution engine
+  }
+}
+
 // Resolves the plan against the visible row groups and fills everything of QueryDesc that does
 // not need device memory.
-int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
+int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
   Table& table = ctx->tables[q.table];  // a table without parts scans nothing (empty LSM)
   for (auto& p : table.parts) {
     if (p->tx > tx) continue;  // index/lsm.go:416
@@ -641,6 +815,11 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       else if (it->second != t) return fail(FGPU_ERR_UNSUPPORTED, "column " + kv.first + " changes type between parts");
     }
   }
+  // string columns whose dictionaries were preloaded (identically on every rank of a multi-GPU run) count
+  // as present even when no local row group holds them: the key set, and with it the shape of the partial
+  // aggregate table, must not depend on which parts a rank happens to own
+  for (auto& kv : table.dicts)
+    if (kv.second.preloaded && !present.count(kv.first)) present.emplace(kv.first, uint8_t(ST_DICT));
   std::map<std::string, int> slot_of;
   auto want = [&](const std::string& name) -> int32_t {
     if (slot_of.count(name)) return FGPU_OK;
@@ -847,15 +1026,17 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     std::vector<VisibleRG> kept;
     const bool prune_on = !getenv("FROSTGPU_NO_PRUNE");
     for (VisibleRG& v : c->rgs) {
+      // Parquet parts: the reference's own row-group filter first (L0 Arrow records are never filtered, lsm.go:420-427)
+      if (prune_on && !v.part->arrow && q.filter >= 0 && !rg_may_match(q, q.filter, *v.rg)) continue;
       bool drop = false;
       for (size_t l = 0; l < c->leaves.size() && prune_on; l++) {
         const LeafHost& lh = c->leaves[l];
         uint8_t mode = LM_EVAL;
         auto it = lh.slot < 0 ? v.rg->cols.end() : v.rg->cols.find(lh.column);
         if (it == v.rg->cols.end()) {
-          mode = lh.missing_mode;  // the missing-column rules are the row-group filter's own (:47-73)
+          mode = lh.missing_mode;  // the physical plan's rule for the rows of a row group that got this far (physicalplan/binaryscalarexpr.go:47-73)
         } else if (lh.numeric && !lh.cmp_float && !lh.null_literal && c->slot_types[size_t(lh.slot)] == ST_I64 && it->second.has_minmax) {
-          mode = stats_leaf_mode(lh.lo_i, lh.hi_i, lh.neg, it->second.min_bits, it->second.max_bits, it->second.null_count == 0);
+          mode = chunk_leaf_mode(lh.lo_i, lh.hi_i, lh.neg, true, it->second.min_bits, it->second.max_bits, it->second.null_count, int64_t(v.rg->n_rows));
         }
         else if (it != v.rg->cols.end() && c->slot_types[size_t(lh.slot)] == ST_DICT && lh.op == FGPU_OP_EQ &&
                  lh.lit->lit_type == FGPU_SCALAR_STRING && it->second.has_minmax_str) {
@@ -878,15 +1059,8 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
     }
     c->pruned_row_groups = uint32_t(c->rgs.size() - kept.size());
     c->rgs.swap(kept);
-    if (c->rgs.empty()) {  // every row group was ruled out: same as scanning an empty table
-      c->qd = QueryDesc{};
-      c->qd.table_mode = TM_DENSE;
-      c->qd.key_words = 1;
-      c->qd.table_slots = 1;
-      c->qd.tile_rows = ctx->tile_rows;
-      c->keys.clear();
-      return FGPU_OK;
-    }
+    // Every row group ruled out: nothing is scanned, but the plan keeps its full shape (keys, aggregates, table
+    // slots): a rank whose time range misses the filter must still produce a partial table its peers can merge.
   }
   // Lazy residency: the columns this query projects are built and uploaded now (parts put with
   // FGPU_PUT_BORROW_PINNED upload nothing until a query needs it; optimize.go:36-73 physical projection).
@@ -1011,7 +1185,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       ko.name = key_names[k];
       ko.is_int64 = c->slot_types[size_t(slot)] != ST_DICT;
       ko.is_float = c->slot_types[size_t(slot)] == ST_F64;
-      if (!ko.is_int64) ko.dict = &table.dicts.at(key_names[k]);
+      if (!ko.is_int64) ko.dict = &table.dicts[key_names[k]];  // (a column whose every row group was pruned was never built: empty dictionary)
       c->keys.push_back(std::move(ko));
       c->key_slots.push_back(slot);
     }
@@ -1032,7 +1206,7 @@ int32_t compile(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, Compiled* c) {
       all_dict = false;
       product *= 1e18L;
     } else {
-      ko.dict = &table.dicts.at(key_names[k]);
+      ko.dict = &table.dicts[key_names[k]];
       uint32_t card = ko.dict->cardinality();
       c->dense_radix[k] = card + 1;
       product *= (long double)(card + 1);
@@ -1173,11 +1347,138 @@ void bind_table(QueryDesc* qd, uint8_t* base) {
 }
 
 // Runs init + scan.  On success the result owns the device table.
-int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* res, bool count_groups = false) {
+// The development / test switches that change how a plan is compiled or launched: a cached plan is only reused
+// under the switches it was built with.
+std::string env_switches() {
+  static const char* const kNames[] = {"FROSTGPU_NO_TILE", "FROSTGPU_NO_RUNS", "FROSTGPU_NO_PRUNE", "FROSTGPU_NO_FAST", "FROSTGPU_NO_FUSE",
+                                       "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK",
+                                       "FROSTGPU_VL", "FROSTGPU_RING", "FROSTGPU_RUNS_BR", "FROSTGPU_RUNS_RING", "FROSTGPU_RUNS_SPAN",
+                                       "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE"};
+  std::string out;
+  for (const char* n : kNames) {
+    const char* v = getenv(n);
+    if (v) { out += n; out += '='; out += v; out += ';'; }
+  }
+  return out;
+}
+
+int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, const ExecCache& x);
+void bind_table(QueryDesc* qd, uint8_t* base);
+
+// First half of the exchange, enqueued behind the scan: this rank's partial table goes into slot [rank] of every
+// rank's mailbox, then the flags are raised (comm.cu).
+int32_t comm_push(fgpu_ctx* ctx, const void* table, size_t table_bytes, uint64_t* out_seq, uint64_t* out_bytes) {
+  Comm& cm = ctx->comm;
+  if (!cm.open) return fail(FGPU_ERR_INVALID, "collective Execute without an open communicator (fgpu_comm_open)");
+  const size_t bytes = (table_bytes + 15) & ~size_t(15);
+  if (bytes > cm.slot_bytes) return fail(FGPU_ERR_UNSUPPORTED, "partial table (" + std::to_string(bytes) + " bytes) larger than the exchange slot");
+  const uint64_t seq = ++cm.seq, set = seq & 1u;
+  CommPush p{};
+  p.src = static_cast<const uint8_t*>(table);
+  p.bytes = bytes;
+  p.seq = seq;
+  p.n = cm.n;
+  for (int r = 0; r < cm.n; r++) {
+    p.dst[r] = cm.peer[r] + cm.data_off(set, cm.rank);
+    p.flag[r] = reinterpret_cast<unsigned long long*>(cm.peer[r] + cm.flag_off(set, cm.rank));
+  }
+  CUDA_TRY(launch_comm_push(p, ctx->sm_count, ctx->stream));
+  *out_seq = seq;
+  *out_bytes = bytes;
+  return FGPU_OK;
+}
+
+// Second half: wait for every rank's flag; dense tables are then folded from the n mailbox slots into `table`
+// itself (it holds the FINAL table afterwards).  Hash tables: the caller merges the slots with k_merge.
+int32_t comm_wait_merge(fgpu_ctx* ctx, const QueryDesc& qd, void* table, uint64_t seq, uint64_t bytes) {
+  Comm& cm = ctx->comm;
+  const uint64_t set = seq & 1u;
+  CommWait w{};
+  w.flags = reinterpret_cast<const unsigned long long*>(cm.mailbox + cm.flag_off(set, 0));
+  w.seq = seq;
+  w.bytes = bytes;
+  const char* to = getenv("FROSTGPU_COMM_TIMEOUT_MS");
+  w.timeout_ns = uint64_t(to ? std::max(1, atoi(to)) : 10000) * 1000000ull;
+  w.counters = qd.counters;
+  w.n = cm.n;
+  CUDA_TRY(launch_comm_wait(w, ctx->stream));
+  if (qd.table_mode == TM_DENSE) {
+    CommMerge m{};
+    m.n = cm.n;
+    for (int r = 0; r < cm.n; r++) m.src[r] = cm.mailbox + cm.data_off(set, r);
+    QueryDesc q2 = qd;
+    bind_table(&q2, static_cast<uint8_t*>(table));
+    CUDA_TRY(launch_merge_dense(q2, m, ctx->stream));
+  }
+  return FGPU_OK;
+}
+
+int32_t comm_check(unsigned long long code) {
+  if (code == 1) return fail(FGPU_ERR_CUDA, "collective Execute: a peer did not deliver its partial table within the timeout");
+  if (code == 2) return fail(FGPU_ERR_UNSUPPORTED, "collective Execute: partial table shapes differ between ranks (dictionaries not preloaded identically?)");
+  return FGPU_OK;
+}
+
+// Re-issues the launches of a cached plan (see ExecCache): table init, scans, one copy back, one synchronisation.
+// Tail of a cached Execute: compact the (final) dense table into result columns on the device and bring them back.
+int32_t cached_tail(fgpu_ctx* ctx, ExecCache& x) {
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(cudaMemsetAsync(x.out.p, 0, 256, s));
+  CUDA_TRY(launch_finalize_dense(x.dout, s));
+  CUDA_TRY(cudaMemcpyAsync(x.pinned, x.out.p, x.out_bytes, cudaMemcpyDeviceToHost, s));
+  return FGPU_OK;
+}
+
+// collective: 0 no exchange, 1 push + wait + merge in one go, 2 push only (fgpu_query_execute_collective_begin)
+int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective) {
+  cudaStream_t s = ctx->stream;
+  res->stats = x.stats;
+  fgpu_stats& st = res->stats;
+  CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
+  CUDA_TRY(launch_table_init(x.qd, s));
+  CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
+  if (x.has_runs) CUDA_TRY(launch_runs(x.rd, x.runs_nl, x.runs_nk, x.runs_na, ctx->sm_count, s));
+  if (x.has_ta) CUDA_TRY(launch_tile_agg(x.td, ctx->sm_count, s));
+  CUDA_TRY(launch_scan(x.qdesc_dev, x.qd, ctx->sm_count, s));
+  CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
+  if (collective) {
+    uint64_t seq = 0, bytes = 0;
+    int32_t rc = comm_push(ctx, x.table.p, x.table_bytes, &seq, &bytes);
+    if (rc) return rc;
+    if (collective == 2) {  // the merge half follows in fgpu_query_execute_collective_end
+      res->pending = true;
+      res->pending_cached = &x;
+      res->pending_seq = seq;
+      res->pending_bytes = bytes;
+      return FGPU_OK;
+    }
+    rc = comm_wait_merge(ctx, x.qd, x.table.p, seq, bytes);
+    if (rc) return rc;
+  }
+  if (int32_t rc = cached_tail(ctx, x)) return rc;
+  CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+  st.scan_kernel_ms = ms;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+  st.total_device_ms = ms;
+  const unsigned long long* counters = reinterpret_cast<const unsigned long long*>(x.pinned + 32);
+  st.rows_selected = counters[0];
+  st.d2h_bytes += x.out_bytes;
+  if (int32_t rc = comm_check(counters[3])) return rc;
+  return finalize_dense_host(ctx, res, x);
+}
+
+// collective: 0 no exchange; 1 / 2: the first run of a plan pushes its partial table and leaves the result pending
+// (the merge half is collective_end); a cached plan does what run_cached does for the mode.
+int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* res, bool count_groups = false, bool cacheable = false,
+                 int collective = 0) {
   PhaseClock pc;
   Table& plan_table = ctx->tables[q.table];
   if (plan_table.epoch == 0) plan_table.epoch = ++ctx->epoch_counter;
-  if (!q.plan_cache || q.cache_epoch != plan_table.epoch || q.cache_tx != tx || getenv("FROSTGPU_NO_PLAN_CACHE")) {
+  const std::string env_now = env_switches();
+  if (!q.plan_cache || q.cache_epoch != plan_table.epoch || q.cache_tx != tx || q.cache_env != env_now || getenv("FROSTGPU_NO_PLAN_CACHE")) {
     std::shared_ptr<void> fresh(new Compiled(), [](void* p) { delete static_cast<Compiled*>(p); });
     int32_t rc0 = compile(ctx, q, tx, static_cast<Compiled*>(fresh.get()));
     q.plan_cache.reset();
@@ -1185,10 +1486,13 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     q.plan_cache = std::move(fresh);
     q.cache_epoch = plan_table.epoch;
     q.cache_tx = tx;
+    q.cache_env = env_now;
   } else {
     static_cast<Compiled*>(q.plan_cache.get())->h2d_bytes = 0;  // nothing is uploaded by a cached plan
   }
   Compiled& c = *static_cast<Compiled*>(q.plan_cache.get());
+  if (cacheable && c.exec && c.exec->ready && !getenv("FROSTGPU_NO_EXEC_CACHE")) return run_cached(ctx, *c.exec, res, collective);
+  c.exec.reset();
   for (LeafHost& lh : c.leaves) lh.lut_off = size_t(-1);  // per-Execute state of the plan
   int32_t rc = FGPU_OK;
   (void)rc;
@@ -1366,7 +1670,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
         rt.null_result = (lh.op == FGPU_OP_EQ && lh.lit->lit_type == FGPU_SCALAR_NULL) ? 1 : 0;
         if (lh.lut_off == size_t(-1)) {
           // one result byte per GLOBAL dictionary id, evaluated once per distinct dictionary entry
-          const GlobalDict& gd = ctx->tables.at(q.table).dicts.at(lh.column);
+          const GlobalDict& gd = ctx->tables[q.table].dicts[lh.column];
           lh.lut_off = lutbytes.size();
           lutbytes.resize(lh.lut_off + gd.values.size() + 1);
           for (size_t g = 0; g < gd.values.size(); g++) lutbytes[lh.lut_off + g] = dict_leaf_value(lh, gd.values[g]) ? 1 : 0;
@@ -1565,7 +1869,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
       tb += (cells * (td.cell64[a] ? 8 : 4) + 7) & ~uint64_t(7);
     }
     const uint64_t kSmemMax = 227 * 1024;
-    const int cand[7][2] = {{4096, 3}, {2048, 4}, {4096, 2}, {2048, 3}, {2048, 2}, {1024, 3}, {1024, 2}};
+    // tile rows: multiples of the rows the consumer threads take per turn (kTaConsumerWarps * 32 lanes * 4 rows)
+    const int cand[10][2] = {{6144, 3}, {3072, 4}, {3072, 3}, {6144, 2}, {3072, 2}, {1536, 4}, {1536, 3}, {1536, 2}, {768, 3}, {768, 2}};
     auto slot_bytes_for = [&](uint32_t T) {
       uint64_t off = 0;
       for (uint32_t i = 0; i < td.n_plain; i++) { td.plain_off[i] = uint32_t(off); off += uint64_t(T) * 8; }
@@ -1669,12 +1974,18 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
 
   // ---- device memory -----------------------------------------------------------------------
   const bool rows_plan = q.kind == FGPU_PLAN_FILTER;
+  // small dense tables of a re-executable query: persistent device state owned by the plan (ExecCache)
+  const bool cache_mode = cacheable && !rows_plan && qd.table_mode == TM_DENSE && qd.table_slots <= 65536 && !getenv("FROSTGPU_NO_EXEC_CACHE");
+  if (cache_mode) c.exec.reset(new ExecCache());
+  DevBuf& tbuf = cache_mode ? c.exec->table : res->table;
+  DevBuf& abuf = cache_mode ? c.exec->aux : res->aux;
+  size_t tbytes = 0;
   if (!rows_plan) {
     size_t off_aggs, off_tags, off_keys;
-    size_t tbytes = table_layout(qd, &off_aggs, &off_tags, &off_keys);
-    CUDA_TRY(res->table.alloc(tbytes, ctx->stream));
+    tbytes = table_layout(qd, &off_aggs, &off_tags, &off_keys);
+    CUDA_TRY(tbuf.alloc(tbytes + 128, ctx->stream));  // (+ counters in cache mode; slack for the 16-byte exchange copies)
     res->table_bytes = tbytes;
-    bind_table(&qd, static_cast<uint8_t*>(res->table.p));
+    bind_table(&qd, static_cast<uint8_t*>(tbuf.p));
   }
   // rows plan: one output array per projected column (worst case every row is selected) + look-back state
   std::vector<size_t> out_off(size_t(qd.n_out)), valid_off(size_t(qd.n_out));
@@ -1690,8 +2001,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
     }
     state_off = out_bytes;
     out_bytes = al(out_bytes + size_t(tiles) * 8);
-    CUDA_TRY(res->table.alloc(out_bytes, ctx->stream));
-    uint8_t* ob = static_cast<uint8_t*>(res->table.p);
+    CUDA_TRY(tbuf.alloc(out_bytes, ctx->stream));
+    uint8_t* ob = static_cast<uint8_t*>(tbuf.p);
     for (int o = 0; o < qd.n_out; o++) {
       qd.out_data[o] = ob + out_off[size_t(o)];
       qd.out_valid[o] = ob + valid_off[size_t(o)];
@@ -1728,8 +2039,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   const size_t o_qd = align16(o_cnt + 64 + 16);
   const size_t aux_bytes = o_qd + sizeof(QueryDesc);
   const size_t o_ret = align16(aux_bytes);  // scratch only: counters + group count read back
-  CUDA_TRY(res->aux.alloc(aux_bytes, ctx->stream));
-  uint8_t* aux = static_cast<uint8_t*>(res->aux.p);
+  CUDA_TRY(abuf.alloc(aux_bytes, ctx->stream));
+  uint8_t* aux = static_cast<uint8_t*>(abuf.p);
   for (auto& fx : lut_fix) lrt[fx.first].lut = aux + o_lut + fx.second;
   CUDA_TRY(ctx->ensure_scratch(o_ret + 128));
   struct { uint8_t* p; uint8_t* data() { return p; } } hostaux{ctx->scratch};
@@ -1762,7 +2073,8 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   qd.leaf_rt = reinterpret_cast<const LeafRt*>(aux + o_lrt);
   qd.rg_first_tile = reinterpret_cast<const uint32_t*>(aux + o_first);
   qd.rg_rows = reinterpret_cast<const uint32_t*>(aux + o_rows);
-  qd.counters = reinterpret_cast<unsigned long long*>(aux + o_cnt);
+  qd.counters = cache_mode ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(tbuf.p) + tbytes)  // behind the table: one copy brings both back
+                           : reinterpret_cast<unsigned long long*>(aux + o_cnt);
   const QueryDesc* qdesc_dev = reinterpret_cast<const QueryDesc*>(aux + o_qd);
 
   FinalizeDesc& fd = res->fd;
@@ -1832,7 +2144,109 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   st.kernel_launches += (rows_plan ? 0 : 1) + (tiles ? 1 : 0);
   st.h2d_bytes += aux_bytes + sizeof(QueryDesc);
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(hostaux.data() + o_ret);
-  res->cnt_ptr = reinterpret_cast<unsigned int*>(aux + o_cnt + 64);  // 16 bytes behind the counters, zeroed by the upload
+  res->cnt_ptr = reinterpret_cast<unsigned int*>(qd.counters + 8);  // 16 bytes behind the counters, zeroed by the upload / the table init
+  if (collective) {
+    if (rows_plan) return fail(FGPU_ERR_INVALID, "rows plans have no partial table: execute them per rank");
+    int32_t rcx = comm_push(ctx, tbuf.p, tbytes, &res->pending_seq, &res->pending_bytes);
+    if (rcx) return rcx;
+    res->pending = true;
+    res->plan_keep = q.plan_cache;
+    count_groups = false;  // the table is not final yet
+  }
+  if (cache_mode) {
+    // ---- the plan keeps this device state; the table comes back with one copy and is compacted on the host ----
+    ExecCache& x = *c.exec;
+    x.table_bytes = tbytes;
+    x.ctx = ctx;
+    {
+      DenseOut& f = x.dout;
+      f.table_slots = qd.table_slots;
+      f.max_out = qd.table_slots;
+      f.n_keys = uint32_t(qd.n_keys);
+      f.n_aggs = uint32_t(qd.n_aggs);
+      for (int k = 0; k < qd.n_keys; k++) {
+        f.stride[k] = qd.keys[k].dense_stride;
+        f.radix[k] = c.dense_radix[size_t(k)] ? c.dense_radix[size_t(k)] : 1;
+      }
+      f.t_rows = qd.t_rows;
+      for (int a = 0; a < kMaxAggs; a++) f.t_agg[a] = qd.t_agg[a];
+      f.counters = qd.counters;
+      x.out_bytes = 256 + size_t(qd.n_keys) * ((size_t(f.max_out) * 4 + 7) & ~size_t(7)) + size_t(qd.n_aggs) * f.max_out * 8;
+      CUDA_TRY(x.out.alloc(x.out_bytes, s));
+      f.out = static_cast<uint8_t*>(x.out.p);
+    }
+    x.pinned = ctx->pinned_take(x.out_bytes, &x.pinned_cap);
+    if (!x.pinned) return fail(FGPU_ERR_OOM, "page-locked memory for the result image");
+    if (!res->pending) {
+      if (int32_t rct = cached_tail(ctx, x)) return rct;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(x.pinned + 32, qd.counters, 32, cudaMemcpyDeviceToHost, s));  // (rows selected by this rank's scan)
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
+    pc.mark("launch");
+    CUDA_TRY(cudaStreamSynchronize(s));  // hostaux stays valid until here
+    pc.mark("sync");
+    release_staging(ctx);
+    st.h2d_bytes += c.h2d_bytes;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+    st.scan_kernel_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+    st.total_device_ms = ms;
+    const unsigned long long* cnts = reinterpret_cast<const unsigned long long*>(x.pinned + 32);
+    st.rows_selected = cnts[0];
+    x.qd = qd;
+    x.qdesc_dev = qdesc_dev;
+    x.has_runs = !batches[0].rgs.empty();
+    x.rd = batches[0].rd;
+    x.runs_nl = batches[0].nl;
+    x.runs_nk = runs_nk;
+    x.runs_na = runs_na;
+    x.has_ta = !TA.rgs.empty();
+    x.td = TA.td;
+    x.keys = c.keys;
+    for (KeyOut& k : x.keys) {
+      if (k.dict) {
+        const uint32_t card = k.dict->cardinality();
+        k.dict_snapshot.reserve(card);
+        for (uint32_t i = 0; i < card; i++) k.dict_snapshot.push_back(k.dict->value(i));
+        k.dict = nullptr;
+      }
+    }
+    x.dense_radix = c.dense_radix;
+    for (const KeyOut& k : x.keys) {  // small dictionaries are exported whole: the host then only copies index columns
+      std::unique_ptr<OwnedColumn> d;
+      if (k.dict_snapshot.size() <= 4096) {
+        d = std::make_unique<OwnedColumn>();
+        d->format = "z";
+        d->length = int64_t(k.dict_snapshot.size());
+        d->offsets.push_back(0);
+        for (const std::string& v : k.dict_snapshot) {
+          d->data.insert(d->data.end(), v.begin(), v.end());
+          d->offsets.push_back(int32_t(d->data.size()));
+        }
+      }
+      x.dict_template.push_back(std::move(d));
+    }
+    for (size_t a = 0; a < q.aggs.size(); a++) {
+      x.agg_names.push_back(std::string(agg_string(q.aggs[a].func)) + "(" + q.expr_name(q.aggs[a].expr) + ")");
+      x.agg_is_float.push_back(qd.aggs[a].func != FGPU_AGG_COUNT && qd.aggs[a].is_float);
+    }
+    x.stats = st;  // what a cached Execute reports: no uploads, no compile
+    x.stats.h2d_bytes = 0;
+    x.stats.d2h_bytes = 0;
+    x.stats.rows_selected = 0;
+    x.ready = true;
+    st.d2h_bytes += x.out_bytes;
+    res->qd = qd;
+    pc.mark("keep");
+    pc.flush("scan");
+    if (res->pending) {
+      res->pending_cached = &x;
+      return FGPU_OK;
+    }
+    return finalize_dense_host(ctx, res, x);
+  }
   if (count_groups && !rows_plan) {  // count the result rows behind the scan: one host round trip less
     fd.out_count = res->cnt_ptr;
     fd.max_out = 0;
@@ -1856,6 +2270,7 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   if (res->groups_known) res->n_groups = static_cast<unsigned int>(counters[8] & 0xffffffffull);
   st.d2h_bytes += 64;
   if (counters[1]) return fail(FGPU_ERR_UNSUPPORTED, "aggregate hash table overflow (more groups than the sized capacity)");
+  if (int32_t rcc = comm_check(counters[3])) return rcc;
 
   // keep what finalize / merge need
   res->qd = qd;
@@ -1876,6 +2291,92 @@ int32_t run_scan(fgpu_ctx* ctx, const fgpu_query& q, uint64_t tx, fgpu_result* r
   }
   pc.mark("keep");
   pc.flush("scan");
+  return FGPU_OK;
+}
+
+// Compacted result image in page-locked memory -> one Arrow record (finishAggregate, aggregate.go:543-633): the
+// device already produced dictionary indices and aggregate values per result row (k_finalize_dense); the host copies.
+int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, const ExecCache& x) {
+  (void)ctx;
+  PhaseClock pc;
+  const QueryDesc& qd = x.qd;
+  const uint32_t* hdr = reinterpret_cast<const uint32_t*>(x.pinned);
+  const size_t G = std::min<size_t>(hdr[0], x.dout.max_out);
+  res->stats.groups = G;
+  const int nk = qd.n_keys, na = qd.n_aggs;
+  const size_t key_bytes = (size_t(x.dout.max_out) * 4 + 7) & ~size_t(7);
+  std::vector<OwnedColumn> cols;
+  cols.reserve(size_t(nk + na));
+  for (int k = 0; k < nk; k++) {
+    const KeyOut& ko = x.keys[size_t(k)];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x.pinned + 256 + size_t(k) * key_bytes);
+    OwnedColumn col;
+    col.name = ko.name;
+    col.length = int64_t(G);
+    col.format = "I";  // dictionary<uint32, binary>
+    col.data.resize(G * 4);
+    uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
+    std::memcpy(idx, src, G * 4);
+    if (hdr[16 + k]) {  // NULL keys: validity bitmap, index 0 in the NULL slots
+      col.validity.assign((G + 7) / 8, 0);
+      for (size_t i = 0; i < G; i++) {
+        if (idx[i] == 0xffffffffu) {
+          idx[i] = 0;
+          col.null_count++;
+        } else {
+          set_bit(col.validity, int64_t(i));
+        }
+      }
+    }
+    auto dict = std::make_unique<OwnedColumn>();
+    if (const OwnedColumn* t = x.dict_template[size_t(k)].get()) {
+      dict->format = t->format;
+      dict->length = t->length;
+      dict->data = t->data;
+      dict->offsets = t->offsets;
+    } else {  // large dictionary: only the values this result uses
+      std::vector<uint32_t> remap(ko.dict_snapshot.size(), 0xffffffffu), used;
+      const std::vector<uint8_t>& val = col.validity;
+      auto is_valid = [&](size_t i) { return val.empty() || ((val[i >> 3] >> (i & 7)) & 1); };
+      for (size_t i = 0; i < G; i++)
+        if (is_valid(i)) remap[idx[i]] = 0;
+      for (size_t g = 0; g < remap.size(); g++)
+        if (remap[g] == 0) {
+          remap[g] = uint32_t(used.size());
+          used.push_back(uint32_t(g));
+        }
+      for (size_t i = 0; i < G; i++)
+        if (is_valid(i)) idx[i] = remap[idx[i]];
+      dict->format = "z";
+      dict->length = int64_t(used.size());
+      dict->offsets.push_back(0);
+      for (uint32_t gid : used) {
+        const std::string& v = ko.dict_snapshot[gid];
+        dict->data.insert(dict->data.end(), v.begin(), v.end());
+        dict->offsets.push_back(int32_t(dict->data.size()));
+      }
+    }
+    col.dictionary = std::move(dict);
+    cols.push_back(std::move(col));
+  }
+  const uint8_t* aggs = x.pinned + 256 + size_t(nk) * key_bytes;
+  for (int a = 0; a < na; a++) {
+    OwnedColumn col;
+    col.name = x.agg_names[size_t(a)];
+    col.format = x.agg_is_float[size_t(a)] ? "g" : "l";
+    col.length = int64_t(G);
+    col.data.resize(G * 8);
+    std::memcpy(col.data.data(), aggs + size_t(a) * x.dout.max_out * 8, G * 8);
+    cols.push_back(std::move(col));
+  }
+  res->stats.algorithmic_bytes += (size_t(nk) + size_t(na)) * G * 8;
+  if (G > 0) {  // finishAggregate skips empty aggregates (aggregate.go:547-549)
+    res->records.push_back(std::move(cols));
+    res->record_rows.push_back(int64_t(G));
+  }
+  res->finalized = true;
+  pc.mark("arrow");
+  pc.flush("finalize-host");
   return FGPU_OK;
 }
 
@@ -2092,17 +2593,84 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   return FGPU_OK;
 }
 
+
+// Second half of a collective Execute: wait for the peers, merge, bring the final result to the host.
+int32_t collective_end(fgpu_ctx* ctx, fgpu_result* res) {
+  if (!res->pending) return fail(FGPU_ERR_INVALID, "no collective Execute pending on this result");
+  res->pending = false;
+  cudaStream_t s = ctx->stream;
+  if (ExecCache* x = static_cast<ExecCache*>(res->pending_cached)) {
+    int32_t rc = comm_wait_merge(ctx, x->qd, x->table.p, res->pending_seq, res->pending_bytes);
+    if (rc) return rc;
+    if (int32_t rct = cached_tail(ctx, *x)) return rct;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const unsigned long long* counters = reinterpret_cast<const unsigned long long*>(x->pinned + 32);
+    res->stats.d2h_bytes += x->out_bytes;
+    if (int32_t rcc = comm_check(counters[3])) return rcc;
+    return finalize_dense_host(ctx, res, *x);
+  }
+  QueryDesc& qd = res->qd;
+  int32_t rc = comm_wait_merge(ctx, qd, res->table.p, res->pending_seq, res->pending_bytes);
+  if (rc) return rc;
+  FinalizeDesc& fd = res->fd;
+  if (qd.table_mode != TM_DENSE) {  // hash tables: fold every rank's slot into a fresh table
+    DevBuf merged;
+    CUDA_TRY(merged.alloc(res->table_bytes + 128, s));
+    QueryDesc q2 = qd;
+    bind_table(&q2, static_cast<uint8_t*>(merged.p));
+    CUDA_TRY(launch_table_init(q2, s, /*zero_counters=*/false));
+    for (int r = 0; r < ctx->comm.n; r++) CUDA_TRY(launch_merge(q2, ctx->comm.mailbox + ctx->comm.data_off(res->pending_seq & 1u, r), s));
+    std::swap(res->table.p, merged.p);
+    std::swap(res->table.n, merged.n);
+    qd = q2;
+    fd.t_rows = qd.t_rows;
+    for (int a = 0; a < kMaxAggs; a++) fd.t_agg[a] = qd.t_agg[a];
+    fd.t_tag = qd.t_tag;
+    fd.t_keys = qd.t_keys;
+  }
+  if (res->cnt_ptr) {  // count the groups of the final table behind the merge
+    CUDA_TRY(cudaMemsetAsync(res->cnt_ptr, 0, 16, s));
+    fd.out_count = res->cnt_ptr;
+    fd.max_out = 0;
+    fd.out_keys = nullptr;
+    fd.out_aggs = nullptr;
+    fd.out_rows = nullptr;
+    CUDA_TRY(launch_finalize(fd, s));
+    res->stats.kernel_launches++;
+  }
+  CUDA_TRY(ctx->ensure_scratch(128));
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->scratch);
+  CUDA_TRY(cudaMemcpyAsync(counters, qd.counters, 64 + 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (counters[1]) return fail(FGPU_ERR_UNSUPPORTED, "aggregate hash table overflow while merging partials");
+  if (int32_t rcc = comm_check(counters[3])) return rcc;
+  if (res->cnt_ptr) {
+    res->n_groups = static_cast<unsigned int>(counters[8] & 0xffffffffull);
+    res->groups_known = true;
+  }
+  return finalize_result(ctx, res);
+}
+
 }  // namespace
 
 // =====================================================================================================
 // extern "C"
 // =====================================================================================================
+// No C++ exception crosses the C ABI: every entry point that returns a status runs inside this guard.
+#define API_TRY try {
+#define API_CATCH                                                                      \
+  }                                                                                    \
+  catch (const std::bad_alloc&) { return fail(FGPU_ERR_OOM, "out of host memory"); }   \
+  catch (const std::exception& ex) { return fail(FGPU_ERR_INVALID, std::string("internal error: ") + ex.what()); } \
+  catch (...) { return fail(FGPU_ERR_INVALID, "internal error"); }
+
 extern "C" {
 
 const char* fgpu_last_error(void) { return g_err.c_str(); }
 int32_t fgpu_abi_version(void) { return FGPU_ABI_VERSION; }
 
 int32_t fgpu_init(const fgpu_config* cfg, fgpu_ctx** out) {
+  API_TRY
   if (!cfg || !out) return fail(FGPU_ERR_INVALID, "null argument");
   if (cfg->abi_version != FGPU_ABI_VERSION) return fail(FGPU_ERR_INVALID, "ABI version mismatch");
   if (cfg->tile_rows != 0 && cfg->tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 (default)");
@@ -2129,25 +2697,38 @@ int32_t fgpu_init(const fgpu_config* cfg, fgpu_ctx** out) {
   for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
   *out = ctx.release();
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_shutdown(fgpu_ctx* ctx) {
+  API_TRY
   if (!ctx) return FGPU_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->comm.mailbox) {
+    for (int r = 0; r < ctx->comm.n; r++)
+      if (ctx->comm.peer_ipc[r] && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
+    cudaFree(ctx->comm.mailbox);
+    ctx->comm = Comm{};
+  }
+  for (auto& kv : ctx->plans) kv.second->plan_cache.reset();  // device state of compiled plans (queries still held by the caller stay valid handles)
+  ctx->plans.clear();
   for (auto& t : ctx->tables)
     for (auto& p : t.second.parts) free_part(ctx, p.get());
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto& kv : ctx->pinned_free) cudaFreeHost(kv.second);
   if (ctx->scratch) cudaFreeHost(ctx->scratch);
   if (ctx->arena) cudaFreeHost(ctx->arena);
   delete ctx;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx, const uint8_t* file,
                               uint64_t len, int32_t flags) {
+  API_TRY
   if (!ctx || !table || !file) return fail(FGPU_ERR_INVALID, "null argument");
   if (flags != FGPU_PUT_DEFAULT && flags != FGPU_PUT_BORROW_PINNED) return fail(FGPU_ERR_INVALID, "unknown put flags");
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -2183,10 +2764,12 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   t.parts.push_back(std::move(part));
   t.epoch = ++ctx->epoch_counter;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, uint64_t tx, struct ArrowSchema* schema,
                             struct ArrowArray* array) {
+  API_TRY
   // the library owns both structs from here on, whatever happens
   struct Release {
     ArrowSchema* s; ArrowArray* a;
@@ -2205,6 +2788,7 @@ int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, 
   part->id = part_id;
   part->tx = tx;
   std::string err;
+  part->arrow = true;
   if (!build_arrow_part(&t, part.get(), schema, array, &err)) return fail(FGPU_ERR_UNSUPPORTED, "Arrow part: " + err);
   // the record's buffers go away on return: every column image is uploaded now
   for (const std::string& col : part->columns) {
@@ -2223,9 +2807,11 @@ int32_t fgpu_part_put_arrow(fgpu_ctx* ctx, const char* table, uint64_t part_id, 
   t.parts.push_back(std::move(part));
   t.epoch = ++ctx->epoch_counter;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {
+  API_TRY
   if (!ctx || !table) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->tables.find(table);
@@ -2243,9 +2829,11 @@ int32_t fgpu_part_drop(fgpu_ctx* ctx, const char* table, uint64_t part_id) {
     }
   }
   return fail(FGPU_ERR_NOT_FOUND, "part not found");
+  API_CATCH
 }
 
 int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
+  API_TRY
   if (!ctx || !table) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->tables.find(table);
@@ -2259,17 +2847,26 @@ int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table) {
   pc.mark("drop");
   pc.flush("drop");
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** out) {
+  API_TRY
   if (!ctx || !plan || !out || !plan->table) return fail(FGPU_ERR_INVALID, "null argument");
   if (plan->kind != FGPU_PLAN_AGGREGATE && plan->kind != FGPU_PLAN_DISTINCT && plan->kind != FGPU_PLAN_FILTER)
     return fail(FGPU_ERR_INVALID, "unknown plan kind");
-  auto q = std::make_unique<fgpu_query>();
+  auto q = std::make_shared<QueryPlan>();
   q->ctx = ctx;
   q->table = plan->table;
   q->kind = plan->kind;
   q->filter = plan->filter;
+  // the plan's text: two prepared queries with the same signature share one QueryPlan (and its compiled state)
+  std::string sig;
+  auto put = [&](const void* p, size_t n) { sig.append(static_cast<const char*>(p), n); };
+  auto put_str = [&](const std::string& v) { const uint64_t n = v.size(); put(&n, 8); sig += v; };
+  put_str(q->table);
+  put(&plan->kind, 4);
+  put(&plan->filter, 4);
   auto check = [&](int32_t i) { return i >= 0 && i < plan->n_exprs; };
   for (int32_t i = 0; i < plan->n_exprs; i++) {
     const fgpu_expr& e = plan->exprs[i];
@@ -2278,9 +2875,11 @@ int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** ou
     n.op = e.op;
     n.left = e.left;
     n.right = e.right;
+    put(&e.kind, 4); put(&e.op, 4); put(&e.left, 4); put(&e.right, 4);
     if (e.kind == FGPU_EXPR_COLUMN || e.kind == FGPU_EXPR_DYNCOLUMN) {
       if (!e.name) return fail(FGPU_ERR_INVALID, "column expression without a name");
       n.name = e.name;
+      put_str(n.name);
     } else if (e.kind == FGPU_EXPR_LITERAL) {
       n.lit_type = e.literal.type;
       n.lit_i = e.literal.i64;
@@ -2289,11 +2888,15 @@ int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** ou
         if (e.literal.len && !e.literal.bytes) return fail(FGPU_ERR_INVALID, "string literal without bytes");
         n.lit_bytes.assign(reinterpret_cast<const char*>(e.literal.bytes), size_t(e.literal.len));
       }
+      put(&n.lit_type, 4); put(&n.lit_i, 8); put(&n.lit_f, 8);
+      put_str(n.lit_bytes);
     } else if (e.kind == FGPU_EXPR_BINARY) {
       if (!check(e.left) || !check(e.right) || e.left >= i || e.right >= i)
         return fail(FGPU_ERR_INVALID, "binary expression children must precede their parent");
       n.match = e.match;
       n.match_user = e.match_user;
+      const void* fn = reinterpret_cast<const void*>(e.match);
+      put(&fn, sizeof fn); put(&e.match_user, sizeof e.match_user);  // a different matcher is a different plan
     } else {
       return fail(FGPU_ERR_INVALID, "unknown expression kind");
     }
@@ -2303,53 +2906,86 @@ int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** ou
   for (int32_t i = 0; i < plan->n_group_by; i++) {
     if (!check(plan->group_by[i])) return fail(FGPU_ERR_INVALID, "group-by index out of range");
     q->group_by.push_back(plan->group_by[i]);
+    put(&plan->group_by[i], 4);
   }
   if (plan->kind != FGPU_PLAN_AGGREGATE && plan->n_aggs != 0) return fail(FGPU_ERR_INVALID, "DISTINCT / FILTER plan with aggregates");
   if (plan->kind == FGPU_PLAN_AGGREGATE && plan->n_aggs == 0) return fail(FGPU_ERR_INVALID, "AGGREGATE plan without aggregates");
+  sig += "|";
   for (int32_t i = 0; i < plan->n_aggs; i++) {
     if (!check(plan->aggs[i].expr)) return fail(FGPU_ERR_INVALID, "aggregate expression index out of range");
     q->aggs.push_back(plan->aggs[i]);
+    put(&plan->aggs[i].func, 4); put(&plan->aggs[i].expr, 4);
   }
-  *out = q.release();
+  auto handle = std::make_unique<fgpu_query>();
+  handle->ctx = ctx;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->plans.find(sig);
+    if (it != ctx->plans.end()) {
+      handle->plan = it->second;
+    } else {
+      if (ctx->plans.size() >= 256) {  // bounded: forget the plans nobody holds any more, then everything
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        for (auto p = ctx->plans.begin(); p != ctx->plans.end();) p = p->second.use_count() == 1 ? ctx->plans.erase(p) : std::next(p);
+        if (ctx->plans.size() >= 256) ctx->plans.clear();
+      }
+      ctx->plans.emplace(std::move(sig), q);
+      handle->plan = std::move(q);
+    }
+  }
+  *out = handle.release();
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_query_free(fgpu_query* q) {
+  API_TRY
+  if (q && q->ctx) {  // the last reference to a plan may own device state
+    std::lock_guard<std::mutex> lk(q->ctx->mu);
+    cudaSetDevice(q->ctx->device);
+    q->plan.reset();
+  }
   delete q;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_query_execute(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out) {
+  API_TRY
   if (!ctx || !q || !out) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
   auto res = std::make_unique<fgpu_result>();
   res->ctx = ctx;
-  int32_t rc = run_scan(ctx, *q, tx_watermark, res.get(), /*count_groups=*/true);
+  int32_t rc = run_scan(ctx, *q->plan, tx_watermark, res.get(), /*count_groups=*/true, /*cacheable=*/true);
   if (rc) return rc;
-  rc = finalize_result(ctx, res.get());
+  if (!res->finalized) rc = finalize_result(ctx, res.get());
   if (rc) return rc;
   *out = res.release();
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_query_execute_partial(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out, void** dev_ptr,
                                    uint64_t* nbytes) {
+  API_TRY
   if (!ctx || !q || !out || !dev_ptr || !nbytes) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
   auto res = std::make_unique<fgpu_result>();
   res->ctx = ctx;
-  if (q->kind == FGPU_PLAN_FILTER) return fail(FGPU_ERR_INVALID, "rows plans have no partial table: execute them per rank");
-  int32_t rc = run_scan(ctx, *q, tx_watermark, res.get());
+  if (q->plan->kind == FGPU_PLAN_FILTER) return fail(FGPU_ERR_INVALID, "rows plans have no partial table: execute them per rank");
+  int32_t rc = run_scan(ctx, *q->plan, tx_watermark, res.get());
   if (rc) return rc;
   *dev_ptr = res->table.p;
   *nbytes = res->table_bytes;
   *out = res.release();
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* gathered, uint64_t nbytes, int32_t n) {
+  API_TRY
   if (!ctx || !r) return fail(FGPU_ERR_INVALID, "null argument");
   if (r->finalized) return fail(FGPU_ERR_INVALID, "result already finalised");
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -2398,53 +3034,195 @@ int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* ga
     r->qd = qd;
   }
   return finalize_result(ctx, r);
+  API_CATCH
+}
+
+int32_t fgpu_comm_export(fgpu_ctx* ctx, int32_t rank, int32_t n_ranks, uint64_t slot_bytes, uint8_t* handle) {
+  API_TRY
+  if (!ctx || !handle) return fail(FGPU_ERR_INVALID, "null argument");
+  if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(FGPU_ERR_INVALID, "rank / n_ranks out of range");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Comm& cm = ctx->comm;
+  if (cm.mailbox) return fail(FGPU_ERR_INVALID, "communicator already exported: fgpu_comm_close first");
+  cm.rank = rank;
+  cm.n = n_ranks;
+  cm.slot_bytes = (std::max<uint64_t>(slot_bytes, 4096) + 255) & ~uint64_t(255);
+  cm.total = kCommDataOff + 2 * uint64_t(n_ranks) * cm.slot_bytes;
+  cm.seq = 0;
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, cm.total));  // (cudaMalloc, not the stream-ordered pool: the allocation is exported through CUDA IPC)
+  cm.mailbox = static_cast<uint8_t*>(p);
+  CUDA_TRY(cudaMemset(cm.mailbox, 0, kCommDataOff));
+  CommHandle h{};
+  h.magic = kCommMagic;
+  h.device = ctx->device;
+  h.pid = uint64_t(getpid());
+  h.ptr = uint64_t(reinterpret_cast<uintptr_t>(cm.mailbox));
+  h.total = cm.total;
+  h.slot_bytes = cm.slot_bytes;
+  h.n = n_ranks;
+  h.rank = rank;
+  CUDA_TRY(cudaIpcGetMemHandle(&h.ipc, cm.mailbox));
+  std::memset(handle, 0, FGPU_COMM_HANDLE_BYTES);
+  std::memcpy(handle, &h, sizeof h);
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_comm_open(fgpu_ctx* ctx, const uint8_t* all_handles) {
+  API_TRY
+  if (!ctx || !all_handles) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Comm& cm = ctx->comm;
+  if (!cm.mailbox) return fail(FGPU_ERR_INVALID, "fgpu_comm_export first");
+  if (cm.open) return fail(FGPU_ERR_INVALID, "communicator already open");
+  for (int r = 0; r < cm.n; r++) {
+    CommHandle h;
+    std::memcpy(&h, all_handles + size_t(r) * FGPU_COMM_HANDLE_BYTES, sizeof h);
+    if (h.magic != kCommMagic || h.rank != r || h.n != cm.n || h.slot_bytes != cm.slot_bytes)
+      return fail(FGPU_ERR_INVALID, "handle " + std::to_string(r) + " does not belong to this communicator (rank order, n_ranks and slot_bytes must agree)");
+    if (r == cm.rank) {
+      cm.peer[r] = cm.mailbox;
+      cm.peer_ipc[r] = false;
+    } else if (h.pid == uint64_t(getpid())) {  // another context of this process: plain peer access
+      if (h.device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          return fail(FGPU_ERR_CUDA, std::string("peer access to device ") + std::to_string(h.device) + ": " + cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+      }
+      cm.peer[r] = reinterpret_cast<uint8_t*>(uintptr_t(h.ptr));
+      cm.peer_ipc[r] = false;
+    } else {
+      void* p = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+      cm.peer[r] = static_cast<uint8_t*>(p);
+      cm.peer_ipc[r] = true;
+    }
+  }
+  cm.open = true;
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_comm_close(fgpu_ctx* ctx) {
+  API_TRY
+  if (!ctx) return FGPU_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Comm& cm = ctx->comm;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < cm.n; r++)
+    if (cm.peer_ipc[r] && cm.peer[r]) cudaIpcCloseMemHandle(cm.peer[r]);
+  if (cm.mailbox) cudaFree(cm.mailbox);
+  cudaGetLastError();
+  cm = Comm{};
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_query_execute_collective(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out) {
+  API_TRY
+  if (!ctx || !q || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto res = std::make_unique<fgpu_result>();
+  res->ctx = ctx;
+  // a cached plan: scan -> push -> wait -> merge -> one copy back, one synchronisation; the first run of a plan
+  // pushes, synchronises once more for its own bookkeeping and then runs the merge half
+  int32_t rc = run_scan(ctx, *q->plan, tx_watermark, res.get(), /*count_groups=*/false, /*cacheable=*/true, /*collective=*/1);
+  if (rc) return rc;
+  if (res->pending) rc = collective_end(ctx, res.get());
+  if (rc) return rc;
+  *out = res.release();
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_query_execute_collective_begin(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out) {
+  API_TRY
+  if (!ctx || !q || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto res = std::make_unique<fgpu_result>();
+  res->ctx = ctx;
+  int32_t rc = run_scan(ctx, *q->plan, tx_watermark, res.get(), /*count_groups=*/false, /*cacheable=*/true, /*collective=*/2);
+  if (rc) return rc;
+  res->plan_keep = q->plan->plan_cache;
+  *out = res.release();
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_query_execute_collective_end(fgpu_ctx* ctx, fgpu_result* r) {
+  API_TRY
+  if (!ctx || !r) return fail(FGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return collective_end(ctx, r);
+  API_CATCH
 }
 
 int32_t fgpu_result_partial_is_additive(const fgpu_result* r, int32_t* out) {
+  API_TRY
   if (!r || !out) return fail(FGPU_ERR_INVALID, "null argument");
   bool add = !r->rows_plan && r->qd.table_mode == TM_DENSE;
   for (int a = 0; a < r->qd.n_aggs && add; a++)
     if (r->qd.aggs[a].func != FGPU_AGG_COUNT && !(r->qd.aggs[a].func == FGPU_AGG_SUM && !r->qd.aggs[a].is_float)) add = false;
   *out = add ? 1 : 0;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_rowgroup_leaf_mode(int32_t op, int64_t literal, int32_t has_bounds, int64_t min_value, int64_t max_value, int64_t null_count,
                                 int64_t num_values, int32_t* out_mode) {
+  API_TRY
   if (!out_mode) return fail(FGPU_ERR_INVALID, "null argument");
   if (op < FGPU_OP_EQ || op > FGPU_OP_GT_EQ) return fail(FGPU_ERR_INVALID, "not a comparison operator");
   int64_t lo, hi;
   bool neg;
   canonical_int_range(op, literal, &lo, &hi, &neg);
-  // an all-NULL chunk has no bounds: nothing is decided from statistics (the kernels find no passing row)
-  *out_mode = (has_bounds && null_count != num_values) ? stats_leaf_mode(lo, hi, neg, min_value, max_value, null_count == 0) : LM_EVAL;
+  *out_mode = chunk_leaf_mode(lo, hi, neg, has_bounds != 0, min_value, max_value, null_count, num_values);
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_result_next(fgpu_result* r, struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  API_TRY
   if (!r || !out_schema || !out_array) return fail(FGPU_ERR_INVALID, "null argument");
-  if (!r->finalized) return fail(FGPU_ERR_INVALID, "partial result: call fgpu_result_merge_partials first");
+  if (!r->finalized) return fail(FGPU_ERR_INVALID, r->pending ? "collective Execute pending: call fgpu_query_execute_collective_end first"
+                                                               : "partial result: call fgpu_result_merge_partials first");
   if (r->next >= r->records.size()) return fail(FGPU_ERR_END, "no more records");
   export_record(std::move(r->records[r->next]), r->record_rows[r->next], out_schema, out_array);
   r->next++;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_result_stats(const fgpu_result* r, fgpu_stats* out) {
+  API_TRY
   if (!r || !out) return fail(FGPU_ERR_INVALID, "null argument");
   *out = r->stats;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_result_free(fgpu_result* r) {
+  API_TRY
   if (r) {
     if (r->ctx) cudaSetDevice(r->ctx->device);
     delete r;
   }
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_host_alloc(uint64_t bytes, void** out) {
+  API_TRY
   if (!out) return fail(FGPU_ERR_INVALID, "null argument");
   void* p = nullptr;
   cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
@@ -2454,15 +3232,19 @@ int32_t fgpu_host_alloc(uint64_t bytes, void** out) {
   }
   *out = p;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_host_free(void* p) {
+  API_TRY
   if (p) cudaFreeHost(p);
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, uint8_t* buf, uint64_t cap,
                          uint64_t* out_len, uint32_t* out_count) {
+  API_TRY
   if (!ctx || !table || !column || !out_len || !out_count) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->tables.find(table);
@@ -2487,12 +3269,15 @@ int32_t fgpu_dict_export(fgpu_ctx* ctx, const char* table, const char* column, u
     p += v.size();
   }
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_dict_preload(fgpu_ctx* ctx, const char* table, const char* column, const uint8_t* blob, uint64_t len, uint32_t count) {
+  API_TRY
   if (!ctx || !table || !column || (!blob && len)) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   GlobalDict& d = ctx->tables[table].dicts[column];
+  d.preloaded = true;
   const uint8_t* p = blob;
   const uint8_t* end = blob + len;
   for (uint32_t i = 0; i < count; i++) {
@@ -2506,10 +3291,12 @@ int32_t fgpu_dict_preload(fgpu_ctx* ctx, const char* table, const char* column, 
   }
   ctx->tables[table].epoch = ++ctx->epoch_counter;
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_parquet_dict_values(const uint8_t* file, uint64_t len, const char* column, uint8_t* buf, uint64_t cap, uint64_t* out_len,
                                  uint32_t* out_count) {
+  API_TRY
   if (!file || !column || !out_len || !out_count) return fail(FGPU_ERR_INVALID, "null argument");
   ParsedFile pf;
   std::string err;
@@ -2548,10 +3335,12 @@ int32_t fgpu_parquet_dict_values(const uint8_t* file, uint64_t len, const char* 
     o += v.size();
   }
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_id, const char* column,
                                 struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  API_TRY
   if (!ctx || !table || !column || !out_schema || !out_array) return fail(FGPU_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -2632,10 +3421,12 @@ int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_
   release_staging(ctx);
   export_column(std::move(col), out_schema, out_array);
   return FGPU_OK;
+  API_CATCH
 }
 
 int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_rows, char* buf, uint64_t cap,
                               uint64_t* out_len) {
+  API_TRY
   if (!file || !out_len) return fail(FGPU_ERR_INVALID, "null argument");
   if (tile_rows == 0) tile_rows = kTileRows;
   if (tile_rows != kTileRows) return fail(FGPU_ERR_INVALID, "tile_rows must be 0 (default)");
@@ -2647,6 +3438,7 @@ int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_ro
   if (cap < js.size()) return fail(FGPU_ERR_INVALID, "buffer too small");
   std::memcpy(buf, js.data(), js.size());
   return FGPU_OK;
+  API_CATCH
 }
 
 }  // extern "C"

@@ -1777,7 +1777,8 @@ __global__ void __launch_bounds__(NT) k_rows(const QueryDesc* __restrict__ qp) {
 // ======================================================================================================
 // k_table_init: rows = 0, sum = 0, min = +max, max = -max (int64) / +-inf (double), tags = 0
 // ======================================================================================================
-__global__ void k_table_init(QueryDesc q) {
+__global__ void k_table_init(QueryDesc q, bool zero_counters) {
+  if (zero_counters && blockIdx.x == 0 && threadIdx.x < 10) q.counters[threadIdx.x] = 0;  // counters + the group counter behind them
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x; s < q.table_slots; s += stride) {
     q.t_rows[s] = 0;
@@ -1899,8 +1900,8 @@ int grid_for(size_t n) {
 }
 }  // namespace
 
-cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st) {
-  k_table_init<<<grid_for(q.table_slots), 256, 0, st>>>(q);
+cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st, bool zero_counters) {
+  k_table_init<<<grid_for(q.table_slots), 256, 0, st>>>(q, zero_counters);
   return cudaGetLastError();
 }
 
@@ -1943,6 +1944,41 @@ cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, 
 
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st) {
   k_finalize<<<grid_for(f.table_slots), 256, 0, st>>>(f);
+  return cudaGetLastError();
+}
+
+// ======================================================================================================
+// k_finalize_dense: occupied slots of a dense table -> compacted columns (one warp-aggregated atomic per warp)
+// ======================================================================================================
+__global__ void __launch_bounds__(256) k_finalize_dense(DenseOut f) {
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(f.out);
+  if (blockIdx.x == 0 && threadIdx.x < 4) reinterpret_cast<unsigned long long*>(f.out + 32)[threadIdx.x] = f.counters[threadIdx.x];
+  const size_t key_bytes = (size_t(f.max_out) * 4 + 7) & ~size_t(7);
+  const int lane = threadIdx.x & 31;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t S = f.table_slots, S_pad = (S + 31) & ~size_t(31);
+  for (size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x; s < S_pad; s += stride) {
+    const unsigned long long rows = s < S ? f.t_rows[s] : 0ull;
+    const unsigned m = __ballot_sync(FULL, rows != 0);
+    if (m == 0) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(hdr, uint32_t(__popc(m)));
+    base = __shfl_sync(FULL, base, 0);
+    if (rows == 0) continue;
+    const uint32_t o = base + __popc(m & ((1u << lane) - 1u));
+    if (o >= f.max_out) continue;
+    for (uint32_t k = 0; k < f.n_keys; k++) {
+      const uint32_t code = (uint32_t(s) / f.stride[k]) % f.radix[k];
+      reinterpret_cast<uint32_t*>(f.out + 256 + size_t(k) * key_bytes)[o] = code ? code - 1u : 0xffffffffu;
+      if (!code) hdr[16 + k] = 1u;
+    }
+    long long* aggs = reinterpret_cast<long long*>(f.out + 256 + size_t(f.n_keys) * key_bytes);
+    for (uint32_t a = 0; a < f.n_aggs; a++) aggs[size_t(a) * f.max_out + o] = f.t_agg[a] ? f.t_agg[a][s] : (long long)rows;
+  }
+}
+
+cudaError_t launch_finalize_dense(const DenseOut& f, cudaStream_t st) {
+  k_finalize_dense<<<grid_for(f.table_slots), 256, 0, st>>>(f);
   return cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ constexpr int kVecThreads = 128;  // scan kernel: 4 independent warps per CTA
 constexpr int kMaxVecRows = 1024;  // rows per warp vector (multiple of kIndexRows)
 constexpr int kIndexRows = 128;  // chunk index granularity (one warp): fixed when run directories are built
 
-cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st);
+cudaError_t launch_table_init(const QueryDesc& q, cudaStream_t st, bool zero_counters = true);
 cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
 // sorted-run scan (runs_scan.cu): nl range leaves, nk run-length keys, na Sum(int64) aggregates
 constexpr int kRunsThreads = 128;
@@ -30,9 +30,14 @@ cudaError_t launch_tile_agg(const TileAggDesc& d, int sm_count, cudaStream_t st)
 size_t tile_agg_smem_bytes(const TileAggDesc& d);
 // dictionary column chunks -> flat code arrays (kernels.cu)
 cudaError_t launch_flatten(const FlatJob* d_jobs, uint32_t n_jobs, uint32_t total_blocks, int sm_count, cudaStream_t st);
+// partial-table exchange over peer-mapped mailboxes (comm.cu)
+cudaError_t launch_comm_push(const CommPush& p, int sm_count, cudaStream_t st);
+cudaError_t launch_comm_wait(const CommWait& w, cudaStream_t st);
+cudaError_t launch_merge_dense(const QueryDesc& q, const CommMerge& m, cudaStream_t st);
 cudaError_t launch_rows(const QueryDesc* d_q, const QueryDesc& q, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st);
 cudaError_t launch_merge(const QueryDesc& q, const void* partial, cudaStream_t st);
+cudaError_t launch_finalize_dense(const DenseOut& f, cudaStream_t st);
 cudaError_t launch_gather_pages(const void* stage, void* image, const PageCopy* table, uint32_t n, cudaStream_t st);
 cudaError_t launch_make_seeds(void* image, uint64_t jobs_off, uint32_t n_jobs, uint32_t max_chunks, cudaStream_t st);
 cudaError_t launch_decode(const ChunkDesc& c, int32_t* out_i32, long long* out_i64, uint8_t* out_valid, int sm_count,

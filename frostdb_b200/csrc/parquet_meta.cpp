@@ -152,6 +152,7 @@ struct RawColumnMeta {
   int64_t num_values = 0, total_compressed = 0, data_page_offset = -1, dict_page_offset = -1;
   int64_t null_count = -1;
   std::string stat_min, stat_max;  // raw PLAIN-encoded bounds, empty = not written
+  bool stat_deprecated = false;    // the bounds come from the deprecated min / max fields (signed byte order for BYTE_ARRAY)
   std::vector<std::string> path;
 };
 
@@ -172,6 +173,7 @@ void read_statistics(TReader& r, RawColumnMeta* m) {
   if (m->stat_min.empty() || m->stat_max.empty()) {
     m->stat_min = old_min;
     m->stat_max = old_max;
+    m->stat_deprecated = true;
   }
 }
 
@@ -275,7 +277,8 @@ void init_chunk(const RawColumnMeta& cm, const SchemaLeaf& leaf, ChunkMeta* out)
     std::memcpy(&out->min_bits, cm.stat_min.data(), 8);
     std::memcpy(&out->max_bits, cm.stat_max.data(), 8);
   }
-  if (leaf.phys == PT_BYTE_ARRAY && !cm.stat_min.empty() && !cm.stat_max.empty()) {
+  // string bounds: min_value / max_value only (legacy writers order the deprecated pair by signed bytes)
+  if (leaf.phys == PT_BYTE_ARRAY && !cm.stat_deprecated && !cm.stat_min.empty() && !cm.stat_max.empty()) {
     out->has_minmax_str = true;
     out->min_str = cm.stat_min;
     out->max_str = cm.stat_max;

@@ -20,6 +20,7 @@ namespace fgpu {
 struct GlobalDict {
   std::vector<std::string> values;
   std::unordered_map<std::string, uint32_t> index;
+  bool preloaded = false;  // fgpu_dict_preload named this column: it exists on some rank of a multi-GPU run
   uint32_t intern(const char* p, size_t n) {
     std::string s(p, n);
     auto it = index.find(s);
@@ -88,6 +89,7 @@ struct Part {
   uint64_t file_bytes = 0;
   std::vector<uint8_t> owned;
   bool borrowed = false;
+  bool arrow = false;               // L0 Arrow record: LSM.Scan hands it to the plan unfiltered (index/lsm.go:420-427)
   ParsedFile pf;
   std::vector<RowGroupHost> rgs;
   std::vector<std::string> columns;  // schema order

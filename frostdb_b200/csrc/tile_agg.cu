@@ -30,6 +30,8 @@
 // Algorithmic bytes per row: 8 per staged PLAIN column + w / 8 per staged code column.
 #include <cuda_runtime.h>
 
+#include <unordered_map>
+
 #include "agg_ops.cuh"
 #include "device_types.h"
 #include "kernels.h"
@@ -92,6 +94,31 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
   return v;
 }
 
+// Predicated shared-memory atomics (PTX-level predicates keep the row loop free of divergence regions).
+__device__ __forceinline__ void red_add_shared_if(uint32_t addr, uint32_t v, bool p) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %2, 0;\n"
+      "@q red.shared.add.u32 [%0], %1;\n"
+      "}\n" ::"r"(addr),
+      "r"(v), "r"(uint32_t(p))
+      : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_shared_if(uint32_t addr, uint32_t v, bool p) {
+  uint32_t old = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %3, 0;\n"
+      "@q atom.shared.add.u32 %0, [%1], %2;\n"
+      "}\n"
+      : "+r"(old)
+      : "r"(addr), "r"(v), "r"(uint32_t(p))
+      : "memory");
+  return old;
+}
+
 // 64-bit cell in shared memory (Min / Max / float64 Sum): compare-and-swap loop, Go's `<` / `>` NaN behaviour
 __device__ __forceinline__ void smem_apply64(uint32_t func, bool is_float, unsigned long long* cell, long long v) {
   unsigned long long old = *cell;
@@ -116,7 +143,8 @@ constexpr int RB = 4;  // rows a consumer thread works on at a time (independent
 
 // SMEM: CTA-private table in shared memory (else atomics on the global table).
 // SIMPLE: every range leaf is a plain int64 range, no dictionary leaves, every stored aggregate is Sum(int64).
-template <bool SMEM, bool SIMPLE>
+// NK / NA: number of key columns / stored aggregates when the instance is specialised for them (-1: read from the descriptor).
+template <bool SMEM, bool SIMPLE, int NK, int NA>
 __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constant__ TileAggDesc d) {
   extern __shared__ __align__(128) uint8_t dyn[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -218,9 +246,11 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
     }
   } else {
     // ================================ consumer warps ================================
+    constexpr bool RTK = NK < 0, RTA = NA < 0;  // key / aggregate counts known at run time only
     uint32_t sel = 0;
-    uint32_t* const t_cnt = reinterpret_cast<uint32_t*>(table);
+    const uint32_t table_s = smem_u32(table);
     const uint32_t rep = uint32_t(lane) & (R - 1u);
+    const uint32_t nk = RTK ? d.nk : uint32_t(NK), na = RTA ? d.na : uint32_t(NA);
     // constants of the row group the tiles come from (refreshed when the header names another row group)
     uint32_t cur_rg = 0xffffffffu;
     long long lo[kTaLeaves], hi[kTaLeaves];
@@ -230,17 +260,17 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
     const uint8_t* plut[kTaPreds];
     bool peval[kTaPreds];
     bool tile_pass = true;
+    // a key column that is absent from the row group (every row NULL) reads any staged byte with stride 0
     uint32_t koff[kTaKeys], ksh[kTaKeys], kbias[kTaKeys], kstride[kTaKeys];
-    bool kon[kTaKeys];
 #pragma unroll
     for (int l = 0; l < kTaLeaves; l++) { lo[l] = hi[l] = 0; loff[l] = 0; leval[l] = false; }
 #pragma unroll
     for (int p = 0; p < kTaPreds; p++) { poff[p] = psh[p] = pbias[p] = 0; plut[p] = nullptr; peval[p] = false; }
 #pragma unroll
-    for (int k = 0; k < kTaKeys; k++) { koff[k] = ksh[k] = kbias[k] = kstride[k] = 0; kon[k] = false; }
+    for (int k = 0; k < kTaKeys; k++) { koff[k] = ksh[k] = kbias[k] = kstride[k] = 0; }
     uint32_t aoff[kTaAggs];
 #pragma unroll
-    for (int a = 0; a < kTaAggs; a++) aoff[a] = uint32_t(a) < d.na ? d.plain_off[d.agg_plain[a]] : 0u;
+    for (int a = 0; a < kTaAggs; a++) aoff[a] = uint32_t(a) < na ? d.plain_off[d.agg_plain[a]] : 0u;
 
     for (uint32_t it = 0;; it++) {
       const uint32_t tile = nth_tile(it);
@@ -280,25 +310,26 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
         }
 #pragma unroll
         for (int k = 0; k < kTaKeys; k++) {
-          kon[k] = uint32_t(k) < d.nk && h->rg.codes[d.key_code[k]] != nullptr;
-          if (kon[k]) {
+          if (uint32_t(k) < nk) {
             const uint32_t c = d.key_code[k];
-            koff[k] = d.code_off[c];
-            ksh[k] = uint32_t(h->rg.code_w[c]) >> 4;
-            kbias[k] = h->rg.code_bias[c];
-            kstride[k] = d.key_stride[k];
+            const bool on = h->rg.codes[c] != nullptr;
+            koff[k] = on ? d.code_off[c] : 0u;
+            ksh[k] = on ? uint32_t(h->rg.code_w[c]) >> 4 : 0u;
+            kbias[k] = on ? uint32_t(h->rg.code_bias[c]) : 0u;
+            kstride[k] = on ? d.key_stride[k] : 0u;
           }
         }
       }
 
       if (tile_pass) {
         for (uint32_t base = uint32_t(tid); base < n; base += RB * NC) {
-          uint32_t r[RB];
+          uint32_t r[RB];  // row inside the tile (clamped: loads of rows past the end stay inside the staged tile)
           bool act[RB];
 #pragma unroll
           for (int j = 0; j < RB; j++) {
-            r[j] = base + uint32_t(j) * NC;
-            act[j] = r[j] < n;
+            const uint32_t rj = base + uint32_t(j) * NC;
+            act[j] = rj < n;
+            r[j] = act[j] ? rj : base;
           }
           // ---- range leaves ----
 #pragma unroll
@@ -308,14 +339,14 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
               if (SIMPLE) {
 #pragma unroll
                 for (int j = 0; j < RB; j++) {
-                  const long long x = act[j] ? (long long)lds64(cb + r[j] * 8u) : 0;
+                  const long long x = (long long)lds64(cb + r[j] * 8u);
                   act[j] = act[j] && x >= lo[l] && x <= hi[l];
                 }
               } else {
                 const uint32_t f = d.leaf_flags[l];
 #pragma unroll
                 for (int j = 0; j < RB; j++) {
-                  const long long x = act[j] ? (long long)lds64(cb + r[j] * 8u) : 0;
+                  const long long x = (long long)lds64(cb + r[j] * 8u);
                   bool in;
                   if (f & 1u) {
                     const double xd = (f & 2u) ? __longlong_as_double(x) : double(x);
@@ -336,11 +367,11 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
                 const uint32_t cb = slot_s + poff[p];
 #pragma unroll
                 for (int j = 0; j < RB; j++) {
-                  if (act[j]) {
-                    const uint32_t code = psh[p] == 0 ? lds_u8(cb + r[j]) : (psh[p] == 1 ? lds_u16(cb + r[j] * 2u) : lds32(cb + r[j] * 4u));
-                    const bool isnull = pbias[p] == 0u && code == 0u;
-                    act[j] = isnull ? (d.pred_null[p] != 0) : (__ldg(plut[p] + (code + pbias[p] - 1u)) != 0);
-                  }
+                  const uint32_t code = psh[p] == 0 ? lds_u8(cb + r[j]) : (psh[p] == 1 ? lds_u16(cb + r[j] * 2u) : lds32(cb + r[j] * 4u));
+                  const bool isnull = pbias[p] == 0u && code == 0u;
+                  const uint32_t id = isnull ? 0u : code + pbias[p] - 1u;
+                  const bool pass = isnull ? (d.pred_null[p] != 0) : (__ldg(plut[p] + id) != 0);
+                  act[j] = act[j] && pass;
                 }
               }
             }
@@ -354,20 +385,17 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
           }
 #pragma unroll
           for (int k = 0; k < kTaKeys; k++) {
-            if (kon[k]) {
+            if (uint32_t(k) < nk) {
               const uint32_t cb = slot_s + koff[k];
               if (ksh[k] == 0) {
 #pragma unroll
-                for (int j = 0; j < RB; j++)
-                  if (act[j]) slot[j] += (lds_u8(cb + r[j]) + kbias[k]) * kstride[k];
+                for (int j = 0; j < RB; j++) slot[j] += (lds_u8(cb + r[j]) + kbias[k]) * kstride[k];
               } else if (ksh[k] == 1) {
 #pragma unroll
-                for (int j = 0; j < RB; j++)
-                  if (act[j]) slot[j] += (lds_u16(cb + r[j] * 2u) + kbias[k]) * kstride[k];
+                for (int j = 0; j < RB; j++) slot[j] += (lds_u16(cb + r[j] * 2u) + kbias[k]) * kstride[k];
               } else {
 #pragma unroll
-                for (int j = 0; j < RB; j++)
-                  if (act[j]) slot[j] += (lds32(cb + r[j] * 4u) + kbias[k]) * kstride[k];
+                for (int j = 0; j < RB; j++) slot[j] += (lds32(cb + r[j] * 4u) + kbias[k]) * kstride[k];
               }
             }
           }
@@ -376,23 +404,27 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
 #pragma unroll
             for (int j = 0; j < RB; j++) {
               slot[j] = (slot[j] << d.rep_log2) + rep;  // cell index (global slot = cell >> rep_log2)
-              if (act[j]) atomicAdd(t_cnt + slot[j], 1u);
+              red_add_shared_if(table_s + slot[j] * 4u, 1u, act[j]);
             }
 #pragma unroll
             for (int a = 0; a < kTaAggs; a++) {
-              if (uint32_t(a) < d.na) {
+              if (uint32_t(a) < na) {
                 const uint32_t cb = slot_s + aoff[a];
                 if (SIMPLE || !d.cell64[a]) {
-                  uint32_t* cells = reinterpret_cast<uint32_t*>(table + d.cell_off[a]);
+                  const uint32_t cells_s = table_s + d.cell_off[a];
+                  uint32_t up[RB], any_up = 0;
 #pragma unroll
                   for (int j = 0; j < RB; j++) {
-                    if (act[j]) {
-                      const unsigned long long v = lds64(cb + r[j] * 8u);
-                      const uint32_t vlo = uint32_t(v);
-                      const uint32_t old = atomicAdd(cells + slot[j], vlo);
-                      const uint32_t up = uint32_t(v >> 32) + ((old + vlo < old) ? 1u : 0u);  // high word + carry out of the low word
-                      if (up) atomicAdd(reinterpret_cast<unsigned long long*>(d.t_agg[a] + (slot[j] >> d.rep_log2)), (unsigned long long)up << 32);
-                    }
+                    const unsigned long long v = lds64(cb + r[j] * 8u);
+                    const uint32_t vlo = uint32_t(v);
+                    const uint32_t old = atom_add_shared_if(cells_s + slot[j] * 4u, vlo, act[j]);
+                    up[j] = act[j] ? uint32_t(v >> 32) + ((old + vlo < old) ? 1u : 0u) : 0u;  // high word + carry out of the low word
+                    any_up |= up[j];
+                  }
+                  if (any_up) {  // values beyond 32 bits / a low word that wrapped: the global cell takes the rest
+#pragma unroll
+                    for (int j = 0; j < RB; j++)
+                      if (up[j]) atomicAdd(reinterpret_cast<unsigned long long*>(d.t_agg[a] + (slot[j] >> d.rep_log2)), (unsigned long long)up[j] << 32);
                   }
                 } else {
                   unsigned long long* cells = reinterpret_cast<unsigned long long*>(table + d.cell_off[a]);
@@ -410,7 +442,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
               if (act[j]) atomicAdd(d.t_rows + slot[j], 1ull);
 #pragma unroll
             for (int a = 0; a < kTaAggs; a++) {
-              if (uint32_t(a) < d.na) {
+              if (uint32_t(a) < na) {
                 const uint32_t cb = slot_s + aoff[a];
                 const uint8_t func = SIMPLE ? uint8_t(1) : uint8_t(d.agg_func[a] & 0xffu);
                 const bool isf = SIMPLE ? false : (d.agg_func[a] >> 8) != 0;
@@ -462,25 +494,52 @@ size_t tile_agg_smem_bytes(const TileAggDesc& d) {
   return 128 + size_t(d.n_stages) * kHdrBytes + size_t(d.n_stages) * d.slot_bytes + (d.smem_table ? d.table_bytes : 0);
 }
 
+namespace {
+using TaKern = void (*)(const TileAggDesc);
+template <int NK>
+TaKern simple_smem_na(int na) {
+  switch (na) {
+    case 0: return k_tile_agg<true, true, NK, 0>;
+    case 1: return k_tile_agg<true, true, NK, 1>;
+    case 2: return k_tile_agg<true, true, NK, 2>;
+    default: return nullptr;
+  }
+}
+TaKern simple_smem(int nk, int na) {
+  switch (nk) {
+    case 0: return simple_smem_na<0>(na);
+    case 1: return simple_smem_na<1>(na);
+    case 2: return simple_smem_na<2>(na);
+    case 3: return simple_smem_na<3>(na);
+    case 4: return simple_smem_na<4>(na);
+    default: return nullptr;
+  }
+}
+}  // namespace
+
 cudaError_t launch_tile_agg(const TileAggDesc& d, int sm_count, cudaStream_t st) {
   if (d.n_tiles == 0) return cudaSuccess;
   const size_t smem = tile_agg_smem_bytes(d);
   bool simple = d.np == 0;
   for (uint32_t l = 0; l < d.nl; l++) simple = simple && d.leaf_flags[l] == 0;
   for (uint32_t a = 0; a < d.na; a++) simple = simple && d.cell64[a] == 0;
-  static size_t configured[4] = {0, 0, 0, 0};
-  const int which = (d.smem_table ? 2 : 0) + (simple ? 1 : 0);
-  using Kern = void (*)(const TileAggDesc);
-  const Kern kerns[4] = {k_tile_agg<false, false>, k_tile_agg<false, true>, k_tile_agg<true, false>, k_tile_agg<true, true>};
-  if (smem > configured[which]) {
-    cudaError_t e = cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  TaKern kern = nullptr;
+  if (simple && d.smem_table) kern = simple_smem(int(d.nk), int(d.na));
+  if (!kern) {
+    if (d.smem_table) kern = simple ? k_tile_agg<true, true, -1, -1> : k_tile_agg<true, false, -1, -1>;
+    else kern = simple ? k_tile_agg<false, true, -1, -1> : k_tile_agg<false, false, -1, -1>;
+  }
+  static std::unordered_map<const void*, size_t> configured;  // (guarded by the engine's mutex)
+  size_t& cfg = configured[reinterpret_cast<const void*>(kern)];
+  if (smem > cfg) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    configured[which] = smem;
+    cfg = smem;
   }
   uint32_t grid = uint32_t(sm_count);
   const uint32_t need = (d.n_tiles + d.chunk_tiles - 1) / d.chunk_tiles;
   if (grid > need) grid = need;
-  kerns[which]<<<grid, kTaThreads, smem, st>>>(d);
+  kern<<<grid, kTaThreads, smem, st>>>(d);
   return cudaGetLastError();
 }
 

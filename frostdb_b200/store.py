@@ -108,6 +108,33 @@ class GPUEngine:
                                                        C.addressof(schema), C.addressof(array)))
         return pa.Array._import_from_c(C.addressof(array), C.addressof(schema))
 
+    # ---- multi-GPU exchange inside the library (fgpu_comm_*) -------------------------------------------
+    def comm_open(self, rank: int, n_ranks: int, exchange, slot_bytes: int = 64 << 20) -> None:
+        """One process per GPU: exports this rank's mailbox, lets `exchange(handle_bytes) -> [handle_bytes] * n`
+        move the handles (any transport), opens the peers."""
+        lib = _lib.load()
+        h = (C.c_uint8 * _lib.COMM_HANDLE_BYTES)()
+        _lib.check(lib.fgpu_comm_export(self.handle, rank, n_ranks, slot_bytes, h))
+        handles = exchange(bytes(h))
+        assert len(handles) == n_ranks
+        _lib.check(lib.fgpu_comm_open(self.handle, b"".join(handles)))
+
+    def comm_close(self) -> None:
+        _lib.check(_lib.load().fgpu_comm_close(self.handle))
+
+    def execute_collective(self, query, tx: int) -> C.c_void_p:
+        res = C.c_void_p()
+        _lib.check(_lib.load().fgpu_query_execute_collective(self.handle, query, tx, C.byref(res)))
+        return res
+
+    def execute_collective_begin(self, query, tx: int) -> C.c_void_p:
+        res = C.c_void_p()
+        _lib.check(_lib.load().fgpu_query_execute_collective_begin(self.handle, query, tx, C.byref(res)))
+        return res
+
+    def execute_collective_end(self, res: C.c_void_p) -> None:
+        _lib.check(_lib.load().fgpu_query_execute_collective_end(self.handle, res))
+
     # ---- cross-rank dictionaries ------------------------------------------------------------------
     def dict_export(self, table: str, column: str) -> List[bytes]:
         lib = _lib.load()
@@ -127,6 +154,26 @@ class GPUEngine:
         blob = b"".join(len(v).to_bytes(4, "little") + v for v in values)
         src = (C.c_char * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
         _lib.check(_lib.load().fgpu_dict_preload(self.handle, table.encode(), column.encode(), C.addressof(src), len(blob), len(values)))
+
+
+def comm_setup(engines: "List[GPUEngine]", slot_bytes: int = 64 << 20, exchange=None) -> None:
+    """Opens the mailbox communicator (fgpu_comm_*) over `engines`.
+
+    In-process ranks: pass every rank's engine.  One process per GPU: pass `[engine]` plus `exchange`, a
+    function `(rank_handle: bytes) -> List[bytes]` that returns all ranks' handles in rank order (e.g. built on
+    torch.distributed.all_gather_object); rank and world size then come from the returned list."""
+    lib = _lib.load()
+    if exchange is None:
+        handles = []
+        for r, e in enumerate(engines):
+            h = (C.c_uint8 * _lib.COMM_HANDLE_BYTES)()
+            _lib.check(lib.fgpu_comm_export(e.handle, r, len(engines), slot_bytes, h))
+            handles.append(bytes(h))
+        blob = b"".join(handles)
+        for e in engines:
+            _lib.check(lib.fgpu_comm_open(e.handle, blob))
+        return
+    raise ValueError("multi-process setup: use GPUEngine.comm_open(rank, n, exchange)")
 
 
 class Table:

@@ -269,6 +269,36 @@ int32_t fgpu_result_merge_partials(fgpu_ctx* ctx, fgpu_result* r, const void* ga
  * them — the dense-table reduction of the partial -> final aggregate step (physicalplan.go:438-471). */
 int32_t fgpu_result_partial_is_additive(const fgpu_result* r, int32_t* out);
 
+/* ---- the exchange inside the library: peer-mapped mailboxes over NVLink -------------------------
+ * The Synchronizer + final HashAggregate of physicalplan.go:438-471 / synchronize.go:16-53 as ONE call per
+ * rank: scan -> push the partial table into every rank's mailbox (NVLink stores) -> wait for every rank's
+ * flag -> merge -> result, all on the library's stream with a single host synchronisation.  Ranks are
+ * contexts: one process per GPU (mailboxes mapped through CUDA IPC) or several contexts in one process
+ * (plain peer access); both may be mixed.
+ *
+ *   1. every rank:  fgpu_comm_export(ctx, rank, n, slot_bytes, handle)      -- allocates this rank's mailbox
+ *   2. the caller exchanges the n 128-byte handles (any transport: gloo, a channel, a file)
+ *   3. every rank:  fgpu_comm_open(ctx, all_handles)                        -- maps the peers' mailboxes
+ *   4. every rank, in the same order: fgpu_query_execute_collective(...)    -- every rank gets the merged result
+ *   5. after a barrier of the caller: fgpu_comm_close(ctx)
+ * Dictionaries must have been unified with fgpu_dict_preload before the parts were put, exactly as for
+ * fgpu_query_execute_partial.  `slot_bytes` bounds the partial table of one query (dense tables:
+ * slots * 8 * (1 + stored aggregates)); a larger table fails with FGPU_ERR_UNSUPPORTED. */
+#define FGPU_COMM_HANDLE_BYTES 128
+int32_t fgpu_comm_export(fgpu_ctx* ctx, int32_t rank, int32_t n_ranks, uint64_t slot_bytes,
+                         uint8_t handle[FGPU_COMM_HANDLE_BYTES]);
+int32_t fgpu_comm_open(fgpu_ctx* ctx, const uint8_t* all_handles /* n_ranks * FGPU_COMM_HANDLE_BYTES, rank order */);
+int32_t fgpu_comm_close(fgpu_ctx* ctx);
+/* Collective Execute: every rank of the communicator calls it with the same plan; `*out` holds the merged
+ * result on every rank.  A peer that does not arrive within the timeout (FROSTGPU_COMM_TIMEOUT_MS, default
+ * 10000) fails the call with FGPU_ERR_CUDA instead of hanging the GPU. */
+int32_t fgpu_query_execute_collective(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out);
+/* The same in two halves, for callers that overlap other work with the exchange (and for ranks that share one
+ * device, where a rank's flag wait must not be enqueued before its peers have pushed): `begin` scans and pushes
+ * this rank's partial table, `end` waits for the peers, merges and finalises `r`. */
+int32_t fgpu_query_execute_collective_begin(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out);
+int32_t fgpu_query_execute_collective_end(fgpu_ctx* ctx, fgpu_result* r);
+
 /* ---- standalone K1: decode one column of one part to Arrow buffers on the device and return
  * them on the host (replaces ParquetConverter.Convert, pqarrow/arrow.go:264-373, for tests and
  * for Filter-only consumers). ------------------------------------------------------------------ */

@@ -54,7 +54,7 @@ K01 = [lp.Col("labels.l00"), lp.Col("labels.l01")]
 AGG = _lib.PLAN_AGGREGATE
 load("u", False)
 run("u", "unsorted: sum by l00,l01", AGG, None, K01, [lp.Sum(val)])
-for t, s in ((4096, 3), (4096, 2), (2048, 4), (2048, 3), (2048, 2), (1024, 3)):
+for t, s in ((3072, 4), (3072, 3), (3072, 2), (6144, 2)):
     run("u", "unsorted: sum by l00,l01", AGG, None, K01, [lp.Sum(val)], {"FROSTGPU_TA_TILE": str(t), "FROSTGPU_TA_STAGES": str(s)})
 run("u", "unsorted: sum by l00,l01", AGG, None, K01, [lp.Sum(val)], {"FROSTGPU_TA_GLOBAL": "1"})
 run("u", "unsorted: sum by l00,l01", AGG, None, K01, [lp.Sum(val)], {"FROSTGPU_NO_TILE": "1"})

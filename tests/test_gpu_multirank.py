@@ -141,3 +141,62 @@ def test_additive_partial_tables_reduce_in_place(built_lib):
         oe.close()
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("n_ranks,key_cols", [(2, ["labels.a", "labels.b"]), (3, ["labels.a", "labels.b"]), (2, ["labels.a", "labels.big", "labels.b"])])
+def test_collective_execute_exchanges_inside_the_library(built_lib, n_ranks, key_cols):
+    """The exchange inside the library: scan -> push into every rank's mailbox -> wait -> merge, per rank, no host
+    collective.  Ranks are contexts on one GPU; every rank must end with the result of the union of all parts
+    (= the oracle), also when the filter leaves a rank nothing to scan, and when the same prepared query runs
+    again (cached plan, alternating mailbox sets)."""
+    from frostdb_b200.store import comm_setup
+    lib = built_lib
+    schema = dp.SampleDefinition()
+    per = 30_000
+    bufs = []
+    for r in range(2 * n_ranks):
+        cols = make_columns(per, 170 + r, {"a": (5 + 3 * (r % 2), 0.1), "b": (40, 0.0), "big": (20000 + 500 * (r % 2), 0.02)}, t0=r * per)
+        bufs.append(dp.write_part(schema, cols, row_group_size=12_000))
+    shards = [bufs[2 * r:2 * r + 2] for r in range(n_ranks)]  # contiguous time ranges per rank
+    unions = {c: union_in_rank_order([[v for b in sh for v in _lib.parquet_dict_values(b, c)] for sh in shards]) for c in key_cols}
+    engines = [GPUEngine(0) for _ in range(n_ranks)]
+    oe = OracleEngine(threads=2)
+    try:
+        ot = OracleTableHandle(oe, "t", schema)
+        for e, sh in zip(engines, shards):
+            for c in key_cols:
+                e.dict_preload("t", c, unions[c])
+            for b in sh:
+                e.put_parquet("t", b)
+        for b in bufs:
+            ot.InsertParquet(b)
+        comm_setup(engines, slot_bytes=32 << 20)
+        aggs = [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value")), lp.Min(lp.Col("timestamp")), lp.Max(lp.Col("value"))]
+        gexprs = [lp.Col(c) for c in key_cols]
+        names = key_cols + [a.Name() for a in aggs]
+        hash_mode = "labels.big" in key_cols
+        filters = [None, lp.Col("timestamp").GtEq(lp.Literal(10_000))]
+        if not hash_mode:  # rank 0's parts all fall outside the range: its partial table must still have the common shape
+            filters.append(lp.Col("timestamp").GtEq(lp.Literal(2 * per + 5)))
+        for f in filters:
+            exp = []
+            oracle_query(oe, "t").Filter(f).Aggregate(aggs, gexprs).Execute(None, lambda c, r: exp.append(r))
+            prepared = [GPUScan(e, "t", f, _lib.PLAN_AGGREGATE, gexprs, aggs).prepare() for e in engines]
+            # The ranks of this test share ONE device, where a rank's flag wait would keep its peers' kernels from
+            # running: the two halves of the collective are issued separately, every push before the first wait.  (One
+            # GPU per rank runs the fused fgpu_query_execute_collective; bench.py --gpus N does.)
+            for rep in range(3):  # first run: plan compiled; later runs: cached plan, alternating mailbox sets
+                pend = [engines[r].execute_collective_begin(prepared[r][0], engines[r].table_watermark("t")) for r in range(n_ranks)]
+                for r in range(n_ranks):
+                    engines[r].execute_collective_end(pend[r])
+                    got = list(engines[r].drain(pend[r]))
+                    lib.fgpu_result_free(pend[r])
+                    assert rows_of(got, names) == rows_of(exp, names), (r, rep)
+            for q, keep in prepared:
+                lib.fgpu_query_free(q)
+        for e in engines:
+            e.comm_close()
+    finally:
+        oe.close()
+        for e in engines:
+            e.close()

@@ -188,3 +188,52 @@ def test_empty_and_ragged_inputs(pair):
     # filter that selects nothing
     got, exp = p.run(lambda q: q.Filter(lp.Col("timestamp").Lt(lp.Literal(-1))).Aggregate([lp.Sum(lp.Col("value"))], [lp.Col("labels.a")]))
     assert rows_of(got) == rows_of(exp) == []
+
+
+def test_missing_column_leaves_follow_the_row_group_filter(pair):
+    """Parquet parts pass LSM.Scan's row-group filter first, whose rules for a column that is missing from the row
+    group (query/expr/binaryscalarexpr.go:47-73) differ from the physical plan's (physicalplan/binaryscalarexpr.go:47-73):
+    `missing == 5`, `missing != 5`, `missing != ""` drop the row group."""
+    p = pair("missing_rules")
+    n = 20_000
+    p.insert(make_columns(n, 1, {"a": (5, 0.0), "b": (4, 0.2)}, t0=0))
+    p.insert(make_columns(n, 2, {"a": (5, 0.1)}, t0=n))              # labels.b missing in this part
+    m, ts = lp.Col("labels.b"), lp.Col("timestamp")
+    zz = lp.Col("labels.zz")                                           # missing everywhere
+    filters = [m.NotEq(lp.Literal("")), m.Eq(lp.Literal("")), zz.Eq(lp.Literal(5)), zz.NotEq(lp.Literal(5)),
+               zz.NotEq(lp.Literal("")), zz.Eq(lp.Literal("")), zz.Eq(lp.Literal(None)), zz.NotEq(lp.Literal(None)), zz.Lt(lp.Literal(3)),
+               m.NotEq(lp.Literal("v000001")), m.Eq(lp.Literal(None)), m.NotEq(lp.Literal(None)),
+               lp.Or(zz.Eq(lp.Literal(5)), ts.Lt(lp.Literal(100))), lp.Or(m.NotEq(lp.Literal("")), ts.GtEq(lp.Literal(2 * n - 10))),
+               lp.And(zz.NotEq(lp.Literal("x")), ts.Lt(lp.Literal(n + 50)))]
+    for f in filters:
+        try:
+            got, exp = p.run(lambda q: q.Filter(f).Aggregate([lp.Sum(lp.Col("value")), lp.Count(lp.Col("value"))], [lp.Col("labels.a")]))
+            assert_same(got, exp)
+        except AssertionError as e:
+            raise AssertionError(f"filter {f.Name()}: {e}") from e
+
+
+def test_key_column_only_in_pruned_parts(store):
+    """A dynamic key column that exists only in row groups the filter rules out (lazily built parts): no dictionary was
+    ever built for it; the query must neither fail nor name the column."""
+    import numpy as np
+    eng = store.engine
+    name = "pruned_keys"
+    eng.drop_table(name)
+    n = 10_000
+    bufs = [np.frombuffer(dp.write_part(dp.SampleDefinition(), make_columns(n, 7, {"a": (3, 0.0)}, t0=0)), dtype=np.uint8),
+            np.frombuffer(dp.write_part(dp.SampleDefinition(), make_columns(n, 8, {"a": (3, 0.0), "x": (4, 0.0)}, t0=10 * n)), dtype=np.uint8)]
+    try:
+        for b in bufs:
+            eng.put_parquet(name, b, borrow=True)
+        got = []
+
+        class _P:
+            def gpu_engine(self):
+                return eng
+        q = query.NewEngine(None, _P()).ScanTable(name)
+        q.Filter(lp.Col("timestamp").Lt(lp.Literal(n))).Aggregate([lp.Count(lp.Col("value"))], [lp.DynCol("labels")]).Execute(None, lambda c, r: got.append(r))
+        rows = rows_of(got)
+        assert sum(r[-1] for r in rows) == n
+    finally:
+        eng.drop_table(name)

@@ -74,7 +74,7 @@ def test_unsorted_two_keys(pair, rows, rg, page):
     assert st["row_groups_tiles"] == st["row_groups"] > 0  # every row group of an unsorted part takes the tile kernel
     assert st["rows_selected"] == 3 * rows
     # ring shapes and the global-table variant give the same records
-    for env in ({"FROSTGPU_TA_TILE": "1024", "FROSTGPU_TA_STAGES": "2"}, {"FROSTGPU_TA_TILE": "2048", "FROSTGPU_TA_STAGES": "4"},
+    for env in ({"FROSTGPU_TA_TILE": "3072", "FROSTGPU_TA_STAGES": "2"}, {"FROSTGPU_TA_TILE": "6144", "FROSTGPU_TA_STAGES": "3"},
                 {"FROSTGPU_TA_GLOBAL": "1"}, {"FROSTGPU_TA_CHUNK": "3"}):
         os.environ.update(env)
         try:
