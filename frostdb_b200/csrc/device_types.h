@@ -112,7 +112,8 @@ struct KeyDesc {
   uint8_t shift;     // packed mode: bit offset inside the word
   uint32_t bits;     // packed mode: field width
   uint32_t dense_stride;  // dense mode: multiplier of (gid + 1)
-  uint32_t _pad;
+  uint8_t prog_off, prog_len;  // computed int64 key ((timestamp / 1000) * 1000): its program in QueryDesc::prog (prog_len > 0)
+  uint16_t _pad;
 };
 
 enum ProgOpCode : uint8_t { PO_LOAD = 0, PO_CONST = 1, PO_ADD = 2, PO_SUB = 3, PO_MUL = 4, PO_DIV = 5 };

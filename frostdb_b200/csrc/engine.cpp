@@ -832,8 +832,10 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
     c->slot_types.push_back(it->second);
     return FGPU_OK;
   };
-  // group-by / distinct columns
+  // group-by / distinct columns; a computed key (arithmetic over int64 columns, the sqlparse pre-projection
+  // `(timestamp / 1000) * 1000 as bucket`) is named after its expression and carries the expression's node
   std::vector<std::string> key_names;
+  std::map<std::string, int32_t> key_expr;  // computed keys: name -> expression node
   for (int32_t g : q.group_by) {
     const ExprNode& e = q.exprs[size_t(g)];
     if (e.kind == FGPU_EXPR_COLUMN) {
@@ -842,8 +844,13 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
       std::string prefix = e.name + ".";  // DynamicColumn.MatchColumn, expr.go:564
       for (auto& kv : present)
         if (kv.first.compare(0, prefix.size(), prefix) == 0) key_names.push_back(kv.first);
+    } else if (e.kind == FGPU_EXPR_BINARY && e.op >= FGPU_OP_ADD && e.op <= FGPU_OP_DIV && q.kind == FGPU_PLAN_AGGREGATE) {
+      const std::string name = q.expr_name(g);
+      if (present.count(name)) return fail(FGPU_ERR_UNSUPPORTED, "computed group key shadows a column: " + name);
+      key_names.push_back(name);
+      key_expr[name] = g;
     } else {
-      return fail(FGPU_ERR_UNSUPPORTED, "computed group-by expressions are not supported on the GPU path");
+      return fail(FGPU_ERR_UNSUPPORTED, "this group-by expression is not supported on the GPU path");
     }
   }
   {
@@ -854,11 +861,13 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
   }
   if (key_names.size() > size_t(kMaxKeys)) return fail(FGPU_ERR_UNSUPPORTED, "too many group-by columns");
   for (auto& n : key_names) {
+    if (key_expr.count(n)) continue;
     int32_t rc = want(n);
     if (rc) return rc;
   }
-  // filter + aggregate input columns
+  // filter + aggregate + computed-key input columns
   std::vector<std::string> cols;
+  for (auto& kv : key_expr) collect_columns(q, kv.second, &cols);
   collect_columns(q, q.filter, &cols);
   for (const fgpu_agg& a : q.aggs) collect_columns(q, a.expr, &cols);
   for (auto& n : cols) {
@@ -874,6 +883,7 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
   // so it is neither uploaded nor staged unless something else in the query needs it.
   {
     std::vector<std::string> need = key_names;
+    for (auto& kv : key_expr) collect_columns(q, kv.second, &need);
     collect_columns(q, q.filter, &need);
     for (const fgpu_agg& a : q.aggs)
       if (a.func != FGPU_AGG_COUNT) collect_columns(q, a.expr, &need);
@@ -1016,6 +1026,7 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
     std::vector<uint8_t> base(c->slot_names.size(), may_skip ? 0 : 1);  // needed regardless of the filter
     if (may_skip) {
       std::vector<std::string> need = key_names;
+      for (auto& kv : key_expr) collect_columns(q, kv.second, &need);
       for (const fgpu_agg& a : q.aggs)
         if (a.func != FGPU_AGG_COUNT) collect_columns(q, a.expr, &need);
       for (auto& n : need) {
@@ -1197,6 +1208,39 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
   long double product = 1;
   c->dense_radix.assign(key_names.size(), 0);
   for (size_t k = 0; k < key_names.size(); k++) {
+    const auto kx = key_expr.find(key_names[k]);
+    if (kx != key_expr.end()) {  // computed int64 key: its program sits behind the aggregates' in qd.prog
+      bool any_float = false, any_int_col = false;
+      const size_t off = prog.size();
+      int32_t rc = compile_agg_expr(q, kx->second, slot_of, *c, &prog, &any_float, &any_int_col);
+      if (rc) return rc;
+      if (any_float) return fail(FGPU_ERR_UNSUPPORTED, "float64 group-by expressions are not supported");
+      if (prog.size() > size_t(kMaxProg) || prog.size() - off > 255) return fail(FGPU_ERR_UNSUPPORTED, "group-by expression too large");
+      int depth = 0, maxd = 0;
+      for (size_t p = off; p < prog.size(); p++) {
+        depth += (prog[p].op == PO_LOAD || prog[p].op == PO_CONST) ? 1 : -1;
+        maxd = std::max(maxd, depth);
+      }
+      if (maxd > 3) return fail(FGPU_ERR_UNSUPPORTED, "group-by expression nests too deeply for the GPU path");
+      for (size_t p = off; p < prog.size(); p++) qd.prog[p] = prog[p];
+      std::vector<std::string> kcols;
+      collect_columns(q, kx->second, &kcols);
+      for (const VisibleRG& v : c->rgs)
+        for (auto& n : kcols)
+          if (!v.rg->cols.count(n)) return fail(FGPU_ERR_NOT_FOUND, "group-by expression column not found: " + n);
+      KeyOut ko;
+      ko.name = key_names[k];
+      ko.is_int64 = true;
+      all_dict = false;
+      product *= 1e18L;
+      c->keys.push_back(std::move(ko));
+      c->key_slots.push_back(-1);
+      qd.keys[k].slot = 0xff;
+      qd.keys[k].is_int64 = 1;
+      qd.keys[k].prog_off = uint8_t(off);
+      qd.keys[k].prog_len = uint8_t(prog.size() - off);
+      continue;
+    }
     int slot = slot_of.at(key_names[k]);
     KeyOut ko;
     ko.name = key_names[k];
@@ -1262,6 +1306,8 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
     if (ring < 2) ring = 2;
     if (ring > 4) ring = 4;
     bool any_expr = false;
+    for (int k = 0; k < qd.n_keys; k++)
+      if (qd.keys[k].prog_len) any_expr = true;
     for (int a = 0; a < qd.n_aggs; a++)
       if (qd.aggs[a].func != FGPU_AGG_COUNT && !(qd.aggs[a].prog_len == 1 && qd.prog[qd.aggs[a].prog_off].op == PO_LOAD)) any_expr = true;
     auto r128 = [](size_t x) { return (x + 127) & ~size_t(127); };

@@ -844,7 +844,17 @@ __device__ __noinline__ bool vec_slots_hash(const VecCtx& v, uint8_t* wb, int la
   for (int k = 0; k < q.n_keys; k++) {
     const KeyDesc& kd = q.keys[k];
     unsigned long long* kwp = m.keyw + size_t(kd.word) * q.vl;
-    if (kd.is_int64) {
+    if (kd.is_int64 && kd.prog_len) {
+      // computed key (the sqlparse pre-projection `(timestamp / 1000) * 1000 as bucket`, project.go:58-167): the
+      // expression is evaluated into the warp's temporaries; Div by zero yields 0, which groups like NULL
+      AggDesc kx{};
+      kx.prog_off = kd.prog_off;
+      kx.prog_len = kd.prog_len;
+      vec_eval_expr(v, wb, kx, lane, m.tmp1);
+      __syncwarp();
+#pragma unroll 1
+      for (int s = 0; s < v.steps; s++) kwp[s * 32 + lane] = (unsigned long long)m.tmp1[s * 32 + lane];
+    } else if (kd.is_int64) {
       NumReader rd;
       rd.init(v, kd.slot, lane);
 #pragma unroll 1

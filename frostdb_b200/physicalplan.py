@@ -141,8 +141,16 @@ class GPUScan:
         self.agg_exprs = list(agg_exprs)
         self.next: Optional[PhysicalPlan] = None
         self.last_stats: Optional[dict] = None
+        # computed group keys arrive as AliasExpr (sqlparse pre-projection: `(timestamp/1000)*1000 as bucket`); the
+        # library names the result column after the expression, the record is renamed to the alias here
+        self.rename = {g.Expr.Name(): g.AliasName for g in self.group_exprs if isinstance(g, lp.AliasExpr)}
 
     def SetNext(self, nxt): self.next = nxt
+
+    def renamed(self, rec: pa.RecordBatch) -> pa.RecordBatch:
+        if not self.rename:
+            return rec
+        return pa.RecordBatch.from_arrays(rec.columns, names=[self.rename.get(n, n) for n in rec.schema.names])
 
     def Draw(self) -> Diagram:
         what = ("distinct " if self.kind == _lib.PLAN_DISTINCT else "") + ",".join(a.Name() for a in self.agg_exprs)
@@ -186,7 +194,7 @@ class GPUScan:
             _lib.check(lib.fgpu_query_execute(self.engine.handle, q, tx, C.byref(res)))
             try:
                 for rec in self.engine.drain(res):
-                    self.next.Callback(ctx, rec)
+                    self.next.Callback(ctx, self.renamed(rec))
                 self.last_stats = self.engine.stats(res)
             finally:
                 lib.fgpu_result_free(res)
@@ -294,8 +302,8 @@ def Build(engine, plan: lp.LogicalPlan, scan_factory=None) -> OutputPlan:
         # Projection feeding the aggregate (sqlparse pre-projection): plain / dynamic columns and the
         # arithmetic the aggregate expressions repeat; the fused scan reads what it needs itself.
         def ok(e):
-            if isinstance(e, lp.AliasExpr):
-                return False
+            if isinstance(e, lp.AliasExpr):  # `(timestamp / 1000) * 1000 as timestamp_bucket`: a computed group key
+                return isinstance(e.Expr, lp.BinaryExpr) and ok(e.Expr)
             if isinstance(e, (lp.Column, lp.DynamicColumn)):
                 return True
             return isinstance(e, lp.BinaryExpr) and lp.OpAdd <= e.Op <= lp.OpDiv and ok_operand(e.Left) and ok_operand(e.Right)
@@ -304,13 +312,17 @@ def Build(engine, plan: lp.LogicalPlan, scan_factory=None) -> OutputPlan:
             return isinstance(e, (lp.Column, lp.LiteralExpr)) or ok(e)
         return all(ok(e) for e in proj.Exprs)
 
+    aliases = {}
     if (i + 1 < len(nodes) and nodes[i].Projection is not None and nodes[i + 1].Aggregation is not None
             and passthrough(nodes[i].Projection)):
+        aliases = {e.AliasName: e for e in nodes[i].Projection.Exprs if isinstance(e, lp.AliasExpr)}
         i += 1
     gpu: Optional[GPUScan] = None
     if i < len(nodes) and nodes[i].Aggregation is not None:
         a = nodes[i].Aggregation
-        gpu = scan_factory(engine, scan.TableName, filter_expr, _lib.PLAN_AGGREGATE, a.GroupExprs, a.AggExprs)
+        # a group column that names an aliased pre-projection is that expression (computed group key)
+        group_exprs = [aliases.get(g.ColumnName, g) if isinstance(g, lp.Column) else g for g in a.GroupExprs]
+        gpu = scan_factory(engine, scan.TableName, filter_expr, _lib.PLAN_AGGREGATE, group_exprs, a.AggExprs)
         i += 1
     elif i + 1 < len(nodes) and nodes[i].Projection is not None and nodes[i + 1].Distinct is not None:
         d = nodes[i + 1].Distinct

@@ -673,6 +673,24 @@ static int eval_arith(const fgpu_plan* plan, int node, record* rec, int as_float
 
 typedef struct { const char* name; o_col* col; int kc; uint64_t* hashes; } keyref;
 
+/* Expr.Name() of an arithmetic expression (expr.go:181,326,623): "left op right", literals printed plainly. */
+static void expr_name(const fgpu_plan* plan, int node, char* out, size_t cap) {
+  const fgpu_expr* e = &plan->exprs[node];
+  size_t n = strlen(out);
+  if (e->kind == FGPU_EXPR_COLUMN || e->kind == FGPU_EXPR_DYNCOLUMN) { snprintf(out + n, cap - n, "%s", e->name); return; }
+  if (e->kind == FGPU_EXPR_LITERAL) {
+    if (e->literal.type == FGPU_SCALAR_INT64) snprintf(out + n, cap - n, "%lld", (long long)e->literal.i64);
+    else if (e->literal.type == FGPU_SCALAR_FLOAT64) snprintf(out + n, cap - n, "%g", e->literal.f64);
+    else snprintf(out + n, cap - n, "null");
+    return;
+  }
+  static const char* const ops[] = {"?", "==", "!=", "<", "<=", ">", ">=", "=~", "!~", "&&", "||", "+", "-", "*", "/", "contains", "not contains"};
+  expr_name(plan, e->left, out, cap);
+  n = strlen(out);
+  snprintf(out + n, cap - n, " %s ", (e->op >= 0 && e->op <= 16) ? ops[e->op] : "?");
+  expr_name(plan, e->right, out, cap);
+}
+
 /* HashAggregate.Callback (aggregate.go:263-490) for one record. */
 static int ha_callback(hashagg* a, const fgpu_plan* plan, record* rec, uint8_t* agg_is_float, char* err) {
   int64_t n = rec->n;
@@ -687,7 +705,7 @@ static int ha_callback(hashagg* a, const fgpu_plan* plan, record* rec, uint8_t* 
       int match = 0;
       if (ge->kind == FGPU_EXPR_COLUMN) match = strcmp(ge->name, fname) == 0;
       else if (ge->kind == FGPU_EXPR_DYNCOLUMN) { size_t pl = strlen(ge->name); match = strncmp(ge->name, fname, pl) == 0 && fname[pl] == '.'; }
-      else { free(keys); snprintf(err, 512, "computed group-by expressions unsupported"); return -1; }
+      else continue; /* computed key: the pre-projection's column, appended behind the physical ones below */
       if (match) {
         int dup = 0; for (int k = 0; k < nk; k++) if (keys[k].col == &rec->cols[ci].col) dup = 1;
         if (dup) continue;
@@ -697,6 +715,24 @@ static int ha_callback(hashagg* a, const fgpu_plan* plan, record* rec, uint8_t* 
         nk++;
       }
     }
+  }
+  /* computed group keys: the sqlparse pre-projection evaluates `(timestamp / 1000) * 1000 as bucket` into an int64
+     column of the record (binaryExprProjection, project.go:58-167; Div by zero -> NULL, which hashes like 0);
+     the aggregate then matches it by name like any other column. */
+  o_col* computed = xcalloc((size_t)plan->n_group_by + 1, sizeof(o_col)); char** cnames = xcalloc((size_t)plan->n_group_by + 1, sizeof(char*)); int n_comp = 0;
+  keys = xrealloc(keys, (size_t)(rec->n_cols + plan->n_group_by + 1) * sizeof(keyref));
+  for (int g = 0; g < plan->n_group_by; g++) {
+    const fgpu_expr* ge = &plan->exprs[plan->group_by[g]];
+    if (ge->kind != FGPU_EXPR_BINARY) continue;
+    int has_int = 0;
+    if (expr_is_float(plan, plan->group_by[g], rec, &has_int)) { snprintf(err, 512, "float64 group-by unsupported"); for (int i = 0; i < n_comp; i++) { free(computed[i].i64); free(cnames[i]); } free(computed); free(cnames); free(keys); return -1; }
+    o_col* c = &computed[n_comp];
+    c->type = C_I64; c->i64 = xmalloc((size_t)n * 8); c->valid = NULL;
+    if (eval_arith(plan, plan->group_by[g], rec, 0, c->i64, err)) { for (int i = 0; i <= n_comp; i++) free(computed[i].i64); for (int i = 0; i < n_comp; i++) free(cnames[i]); free(computed); free(cnames); free(keys); return -1; }
+    char* nm = xcalloc(1, 512); expr_name(plan, plan->group_by[g], nm, 512);
+    cnames[n_comp] = nm;
+    keys[nk].name = nm; keys[nk].col = c; keys[nk].kc = ha_keycol(a, nm, 1); keys[nk].hashes = NULL;
+    nk++; n_comp++;
   }
   /* per-column hashes: HashArray (hashed.go:86-105) — per ROW, as the reference does */
   for (int k = 0; k < nk; k++) {
@@ -742,6 +778,8 @@ static int ha_callback(hashagg* a, const fgpu_plan* plan, record* rec, uint8_t* 
   }
   for (int k = 0; k < nk; k++) free(keys[k].hashes);
   for (int j = 0; j < na; j++) free(vals[j]);
+  for (int i = 0; i < n_comp; i++) { free(computed[i].i64); free(cnames[i]); }
+  free(computed); free(cnames);
   free(vals); free(keys);
   return rc;
 }

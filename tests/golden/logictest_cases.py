@@ -318,3 +318,46 @@ _d(67, "select distinct(labels)", [DynCol("labels")],
    ["value1 value1 null null value1", "value2 value2 value3 null value1", "value3 value1 null value4 value1"])
 _d(75, "select distinct(labels.label1) where labels.label2 = 'value1' and labels.label4 = 'value4'", _c("labels.label1"), ["value3"],
    where=And(Col("labels.label2").Eq(Literal("value1")), Col("labels.label4").Eq(Literal("value4"))))
+
+
+# ---------------------------------------------------------------------------------------------------
+# exec/aggregate/window: group by a computed bucket, `(timestamp / k) * k as timestamp_bucket`.  sqlparse
+# (visitor.go:62-130) plans Project(pre: aggregate inputs + the aliased bucket) -> Aggregate(by Col(alias)) ->
+# Project(post); plan/aggregate/window shows the same chain.
+# ---------------------------------------------------------------------------------------------------
+_win = case("logictest/testdata/exec/aggregate/window")
+insert(_win, ["labels.label1", "stacktrace", "timestamp", "value"],
+       ["value1 stack1 120000 1", "value2 stack1 121000 2", "value3 stack1 122000 3", "value4 stack1 123000 4"])
+
+
+def _bucket(k):
+    return Mul(Div(Col("timestamp"), Literal(k)), Literal(k)).Alias("timestamp_bucket")
+
+
+def _win_sum(line, k, expected):
+    exec_(_win, line, f"select sum(value) as value_sum, (timestamp/{k})*{k} as timestamp_bucket group by timestamp_bucket",
+          lambda q, k=k: q.Project(Col("value"), _bucket(k)).Aggregate([Sum(Col("value"))], _c("timestamp_bucket"))
+          .Project(Sum(Col("value")).Alias("value_sum"), Col("timestamp_bucket")),
+          expected, unordered=True)
+
+
+_win_sum(14, 1000, ["1 120000", "2 121000", "3 122000", "4 123000"])
+_win_sum(22, 2000, ["3 120000", "7 122000"])
+_win_sum(28, 3000, ["6 120000", "4 123000"])
+exec_(_win, 34, "select sum(value) as value_sum, count(value) as value_count, (timestamp/3000)*3000 as timestamp_bucket group by timestamp_bucket",
+      lambda q: q.Project(Col("value"), _bucket(3000)).Aggregate([Sum(Col("value")), Count(Col("value"))], _c("timestamp_bucket"))
+      .Project(Sum(Col("value")).Alias("value_sum"), Count(Col("value")).Alias("value_count"), Col("timestamp_bucket")),
+      ["6 3 120000", "4 1 123000"], unordered=True)
+_win_sum(40, 4000, ["10 120000"])
+exec_(_win, 45, "select labels.label1, (timestamp/5000)*5000 as timestamp_bucket, sum(value) as value_sum group by labels.label1, timestamp_bucket",
+      lambda q: q.Project(Col("labels.label1"), _bucket(5000), Col("value")).Aggregate([Sum(Col("value"))], _c("labels.label1", "timestamp_bucket"))
+      .Project(Col("labels.label1"), Col("timestamp_bucket"), Sum(Col("value")).Alias("value_sum")),
+      ["value1 120000 1", "value2 120000 2", "value3 120000 3", "value4 120000 4"], unordered=True)
+exec_(_win, 54, "select (timestamp/2000)*2000 as timestamp_bucket, sum(value) as value_sum, count(timestamp) as timestamp_count group by timestamp_bucket",
+      lambda q: q.Project(_bucket(2000), Col("value"), Col("timestamp")).Aggregate([Sum(Col("value")), Count(Col("timestamp"))], _c("timestamp_bucket"))
+      .Project(Col("timestamp_bucket"), Sum(Col("value")).Alias("value_sum"), Count(Col("timestamp")).Alias("timestamp_count")),
+      ["120000 3 2", "122000 7 2"], unordered=True)
+exec_(_win, 60, "select (timestamp/3000)*3000 as timestamp_bucket, count(timestamp) as timestamp_count group by timestamp_bucket",
+      lambda q: q.Project(_bucket(3000), Col("timestamp")).Aggregate([Count(Col("timestamp"))], _c("timestamp_bucket"))
+      .Project(Col("timestamp_bucket"), Count(Col("timestamp")).Alias("timestamp_count")),
+      ["120000 3", "123000 1"], unordered=True)

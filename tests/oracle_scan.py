@@ -30,7 +30,7 @@ class OracleScan(pp.GPUScan):
         finally:
             res.close()
         del keep
-        self.next.Callback(ctx, batch)
+        self.next.Callback(ctx, self.renamed(batch))
         self.next.Finish(ctx)
 
 

@@ -237,3 +237,25 @@ def test_key_column_only_in_pruned_parts(store):
         assert sum(r[-1] for r in rows) == n
     finally:
         eng.drop_table(name)
+
+
+def test_computed_group_keys_time_buckets(pair):
+    """The Parca "Range" query shape (bench_test.go:325-349; logictest exec/aggregate/window): group by a bucket
+    computed from the timestamp, alone and next to a dictionary key, with a filter in front."""
+    p = pair("buckets", dp.SampleDefinition())
+    n = 60_000
+    for i in range(3):
+        p.insert(make_columns(n, 400 + i, {"a": (6, 0.1), "b": (30, 0.0)}, t0=1_000_000 + i * n), sort=(i != 1), row_group_size=25_000)
+    ts, v = lp.Col("timestamp"), lp.Col("value")
+
+    def bucket(k):
+        return lp.Mul(lp.Div(ts, lp.Literal(k)), lp.Literal(k)).Alias("timestamp_bucket")
+    aggs = [lp.Sum(v), lp.Count(v), lp.Max(v)]
+    for k in (1000, 7, 1_000_000_000):
+        got, exp = p.run(lambda q: q.Project(v, bucket(k)).Aggregate(aggs, [lp.Col("timestamp_bucket")]))
+        assert_same(got, exp)
+    got, exp = p.run(lambda q: q.Filter(ts.GtEq(lp.Literal(1_030_000))).Project(v, lp.Col("labels.a"), bucket(5000))
+                     .Aggregate(aggs, [lp.Col("labels.a"), lp.Col("timestamp_bucket")]))
+    assert_same(got, exp)
+    got, exp = p.run(lambda q: q.Project(v, lp.Sub(ts, v).Alias("d")).Aggregate([lp.Count(v)], [lp.Col("d"), lp.Col("labels.b")]))
+    assert_same(got, exp)
