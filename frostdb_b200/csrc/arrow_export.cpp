@@ -80,7 +80,7 @@ void fill_array(OwnedColumn&& col, ArrowArray* a) {
     p->buffers = {validity, c.offsets.empty() ? static_cast<const void*>(kEmpty) : c.offsets.data(),
                   c.data.empty() ? static_cast<const void*>(kEmpty) : c.data.data()};
   } else {
-    p->buffers = {validity, c.data.empty() ? static_cast<const void*>(kEmpty) : c.data.data()};
+    p->buffers = {validity, c.ext ? static_cast<const void*>(c.ext) : (c.data.empty() ? static_cast<const void*>(kEmpty) : c.data.data())};
   }
   if (c.dictionary) {
     p->dictionary = new ArrowArray;

@@ -18,6 +18,10 @@ struct OwnedColumn {
   int64_t null_count = 0;
   std::vector<uint8_t> validity;  // bitmap, empty = no nulls
   std::vector<uint8_t> data;      // fixed width values, or binary value bytes
+  // fixed width values living in memory the column does not own as a vector (page-locked result blocks that go
+  // back to their pool when the consumer releases the array): `ext` wins over `data` when set
+  const uint8_t* ext = nullptr;
+  std::shared_ptr<void> ext_keep;
   std::vector<int32_t> offsets;   // binary: length + 1 offsets
   std::unique_ptr<OwnedColumn> dictionary;  // for dictionary-encoded columns: the values
 };

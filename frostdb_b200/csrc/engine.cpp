@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -20,6 +21,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/frostgpu.h"
@@ -121,6 +123,46 @@ const char* agg_string(int f) {  // logicalplan.AggFunc.String(), expr.go:731-75
 
 }  // namespace
 
+// Page-locked host blocks, recycled: result images of cached plans and the columns of large results (which the
+// Arrow consumer holds until it releases the array, possibly after the context is gone: the pool is shared-owned).
+// Freeing page-locked memory synchronises the device, so blocks are only released when the pool itself dies.
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, uint8_t*> free_blocks;
+  size_t free_bytes = 0;
+  ~PinnedPool() {
+    for (auto& kv : free_blocks) cudaFreeHost(kv.second);
+  }
+  uint8_t* take(size_t bytes, size_t* cap) {
+    size_t want = 4096;
+    while (want < bytes) want <<= 1;
+    if (bytes > (size_t(1) << 24)) want = (bytes + (size_t(1) << 22) - 1) & ~((size_t(1) << 22) - 1);  // large blocks: 4 MiB granules
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = free_blocks.lower_bound(want);
+      if (it != free_blocks.end() && it->first <= want * 2) {
+        uint8_t* p = it->second;
+        *cap = it->first;
+        free_bytes -= it->first;
+        free_blocks.erase(it);
+        return p;
+      }
+    }
+    uint8_t* p = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    *cap = want;
+    return p;
+  }
+  void give(uint8_t* p, size_t cap) {
+    std::lock_guard<std::mutex> lk(mu);
+    free_blocks.emplace(cap, p);
+    free_bytes += cap;
+  }
+};
+
 // Mailbox communicator of one rank (see comm.cu).
 struct CommHandle {  // what travels between the ranks (FGPU_COMM_HANDLE_BYTES)
   uint32_t magic;
@@ -175,28 +217,9 @@ struct fgpu_ctx {
     arena_used = off + n;
     return arena + off;
   }
-  // page-locked blocks handed to compiled plans (result images): recycled, only released at shutdown — freeing
-  // page-locked memory synchronises the device, which must not happen while a peer's exchange kernel waits for us
-  std::multimap<size_t, uint8_t*> pinned_free;
-  uint8_t* pinned_take(size_t bytes, size_t* cap) {
-    size_t want = 4096;
-    while (want < bytes) want <<= 1;
-    auto it = pinned_free.lower_bound(want);
-    if (it != pinned_free.end() && it->first <= want * 2) {
-      uint8_t* p = it->second;
-      *cap = it->first;
-      pinned_free.erase(it);
-      return p;
-    }
-    uint8_t* p = nullptr;
-    if (cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault) != cudaSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    *cap = want;
-    return p;
-  }
-  void pinned_give(uint8_t* p, size_t cap) { pinned_free.emplace(cap, p); }
+  std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
+  uint8_t* pinned_take(size_t bytes, size_t* cap) { return pinned->take(bytes, cap); }
+  void pinned_give(uint8_t* p, size_t cap) { pinned->give(p, cap); }
   // page-locked scratch for the per-query descriptor upload and the counters read-back (guarded by mu)
   uint8_t* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -404,6 +427,34 @@ int bit_width_u32(uint64_t max_value) {
   return w;
 }
 
+// Host side of several columns of one part in parallel (page walk, run directories, dictionary interning): the
+// columns are independent — every column has its own dictionary, image and chunk records, all created here
+// before the workers start so that no container is resized concurrently.
+void prebuild_columns(Table* table, Part* part, const std::vector<std::string>& columns) {
+  std::vector<const std::string*> todo;
+  for (const std::string& c : columns) {
+    ColumnImage& img = part->images[c];  // creates the entry
+    if (img.built) continue;
+    for (const SchemaLeaf& l : part->pf.leaves)
+      if (l.name == c && l.phys == PT_BYTE_ARRAY) (void)table->dicts[c];
+    todo.push_back(&c);
+  }
+  if (todo.size() < 2) return;  // a single column is built by its caller
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t n_threads = std::min<size_t>(todo.size(), std::min<size_t>(hw ? hw : 4, 16));
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> workers;
+  for (size_t t = 0; t < n_threads; t++)
+    workers.emplace_back([&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= todo.size()) break;
+        build_column(kIndexRows, table, part, *todo[i], /*device_seeds=*/true);
+      }
+    });
+  for (std::thread& w : workers) w.join();
+}
+
 // Flat code arrays of one dictionary column of a part (every row group, one allocation), derived on the device
 // from the resident hybrid image the first time the tile-aggregate kernel needs the column (k_flatten).
 int32_t ensure_flat(fgpu_ctx* ctx, Part* part, const std::string& column) {
@@ -604,8 +655,9 @@ struct ExecCache {
   std::vector<uint32_t> dense_radix;
   std::vector<std::string> agg_names;
   std::vector<uint8_t> agg_is_float;
+  std::shared_ptr<PinnedPool> pool;
   ~ExecCache() {
-    if (pinned && ctx) ctx->pinned_give(pinned, pinned_cap);
+    if (pinned && pool) pool->give(pinned, pinned_cap);
   }
 };
 
@@ -2221,6 +2273,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       CUDA_TRY(x.out.alloc(x.out_bytes, s));
       f.out = static_cast<uint8_t*>(x.out.p);
     }
+    x.pool = ctx->pinned;
     x.pinned = ctx->pinned_take(x.out_bytes, &x.pinned_cap);
     if (!x.pinned) return fail(FGPU_ERR_OOM, "page-locked memory for the result image");
     if (!res->pending) {
@@ -2433,24 +2486,53 @@ int32_t finalize_rows(fgpu_ctx* ctx, fgpu_result* res) {
   const QueryDesc& qd = res->qd;
   const size_t R = size_t(res->stats.rows_selected);
   res->stats.groups = R;
+  // Every projected column comes back into a page-locked block of the context's pool with ONE copy each and ONE
+  // synchronisation for all of them; the block itself becomes the Arrow buffer (it returns to the pool when the
+  // consumer releases the array), so a large selection costs its PCIe transfer and nothing else.
+  struct Block { uint8_t* p = nullptr; size_t cap = 0; };
+  std::shared_ptr<PinnedPool> pool = ctx->pinned;
+  auto keep_of = [pool](Block b) { return std::shared_ptr<void>(b.p, [pool, b](void*) { pool->give(b.p, b.cap); }); };
+  std::vector<Block> data(size_t(qd.n_out)), valid(size_t(qd.n_out));
+  for (int o = 0; o < qd.n_out && R; o++) {
+    const bool dict = !res->keys[size_t(o)].is_int64;
+    const size_t bytes = R * (dict ? 4 : 8);
+    data[size_t(o)].p = pool->take(bytes, &data[size_t(o)].cap);
+    if (!data[size_t(o)].p) return fail(FGPU_ERR_OOM, "page-locked memory for the result rows");
+    CUDA_TRY(cudaMemcpyAsync(data[size_t(o)].p, qd.out_data[o], bytes, cudaMemcpyDeviceToHost, s));
+    res->stats.d2h_bytes += bytes;
+    if (!dict && !res->rows_no_nulls) {
+      valid[size_t(o)].p = pool->take(R, &valid[size_t(o)].cap);
+      if (!valid[size_t(o)].p) return fail(FGPU_ERR_OOM, "page-locked memory for the result rows");
+      CUDA_TRY(cudaMemcpyAsync(valid[size_t(o)].p, qd.out_valid[o], R, cudaMemcpyDeviceToHost, s));
+      res->stats.d2h_bytes += R;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+  res->stats.total_device_ms = ms;
   std::vector<OwnedColumn> cols;
   for (int o = 0; o < qd.n_out; o++) {
     const KeyOut& ko = res->keys[size_t(o)];
     OwnedColumn col;
     col.name = ko.name;
     col.length = int64_t(R);
+    if (R) {
+      col.ext = data[size_t(o)].p;
+      col.ext_keep = keep_of(data[size_t(o)]);
+    }
     if (!ko.is_int64) {
-      std::vector<int32_t> ids(R);
-      if (R) CUDA_TRY(cudaMemcpyAsync(ids.data(), qd.out_data[o], R * 4, cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(cudaStreamSynchronize(s));
-      res->stats.d2h_bytes += R * 4;
+      // dictionary ids (-1 = NULL): indices into a dictionary of the values this result uses
       col.format = "I";
-      col.validity.assign((R + 7) / 8, 0);
-      col.data.resize(R * 4);
-      uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
+      int32_t* ids = reinterpret_cast<int32_t*>(data[size_t(o)].p);
+      uint32_t* idx = reinterpret_cast<uint32_t*>(data[size_t(o)].p);
       std::vector<int32_t> remap(ko.dict_snapshot.size(), -1);
-      for (size_t i = 0; i < R; i++)
+      bool any_null = false;
+      for (size_t i = 0; i < R; i++) {
         if (ids[i] >= 0) remap[size_t(ids[i])] = 0;
+        else any_null = true;
+      }
       auto dict = std::make_unique<OwnedColumn>();
       dict->format = "z";
       dict->offsets.push_back(0);
@@ -2463,45 +2545,30 @@ int32_t finalize_rows(fgpu_ctx* ctx, fgpu_result* res) {
         dict->offsets.push_back(int32_t(dict->data.size()));
       }
       dict->length = next;
+      if (any_null) col.validity.assign((R + 7) / 8, 0);
       for (size_t i = 0; i < R; i++) {
         if (ids[i] < 0) { idx[i] = 0; col.null_count++; }
-        else { idx[i] = uint32_t(remap[size_t(ids[i])]); set_bit(col.validity, int64_t(i)); }
+        else { idx[i] = uint32_t(remap[size_t(ids[i])]); if (any_null) set_bit(col.validity, int64_t(i)); }
       }
-      if (col.null_count == 0) col.validity.clear();
       col.dictionary = std::move(dict);
     } else {
       col.format = ko.is_float ? "g" : "l";
-      col.data.resize(R * 8);
-      if (res->rows_no_nulls) {
-        if (R) CUDA_TRY(cudaMemcpyAsync(col.data.data(), qd.out_data[o], R * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        res->stats.d2h_bytes += R * 8;
-        res->stats.algorithmic_bytes += R * 8;
-        cols.push_back(std::move(col));
-        continue;
+      if (valid[size_t(o)].p) {
+        const uint8_t* v = valid[size_t(o)].p;
+        size_t nulls = 0;
+        for (size_t i = 0; i < R; i++) nulls += v[i] ? 0 : 1;
+        if (nulls) {
+          col.validity.assign((R + 7) / 8, 0);
+          for (size_t i = 0; i < R; i++)
+            if (v[i]) set_bit(col.validity, int64_t(i));
+          col.null_count = int64_t(nulls);
+        }
+        pool->give(valid[size_t(o)].p, valid[size_t(o)].cap);
       }
-      std::vector<uint8_t> valid(R);
-      if (R) {
-        CUDA_TRY(cudaMemcpyAsync(col.data.data(), qd.out_data[o], R * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(valid.data(), qd.out_valid[o], R, cudaMemcpyDeviceToHost, s));
-      }
-      CUDA_TRY(cudaStreamSynchronize(s));
-      res->stats.d2h_bytes += R * 9;
-      col.validity.assign((R + 7) / 8, 0);
-      for (size_t i = 0; i < R; i++) {
-        if (valid[i]) set_bit(col.validity, int64_t(i));
-        else col.null_count++;
-      }
-      if (col.null_count == 0) col.validity.clear();
     }
     res->stats.algorithmic_bytes += R * (ko.is_int64 ? 8 : 4);
     cols.push_back(std::move(col));
   }
-  CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
-  CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
-  res->stats.total_device_ms = ms;
   if (R > 0) {  // an empty selection emits no record (filter.go:264-266)
     res->records.push_back(std::move(cols));
     res->record_rows.push_back(int64_t(R));
@@ -2538,11 +2605,12 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
   res->stats.groups = n_groups;
   const size_t G = n_groups;
   const int nk = fd.n_keys, na = fd.n_aggs;
-  // the result columns land in page-locked scratch (keys first, then aggregates)
-  CUDA_TRY(ctx->ensure_scratch((size_t(nk) + size_t(na)) * G * 8 + 64));
-  struct HostCols { const long long* p; const long long* data() const { return p; } };
-  const HostCols h_keys{reinterpret_cast<const long long*>(ctx->scratch)};
-  const HostCols h_aggs{reinterpret_cast<const long long*>(ctx->scratch) + size_t(nk) * G};
+  // every result column lands in its own page-locked block of the context's pool; int64 keys and aggregates hand
+  // that block to the Arrow consumer as it is (returned to the pool on release), dictionary keys are re-indexed
+  struct Block { uint8_t* p = nullptr; size_t cap = 0; };
+  std::shared_ptr<PinnedPool> pool = ctx->pinned;
+  auto keep_of = [pool](Block b) { return std::shared_ptr<void>(b.p, [pool, b](void*) { pool->give(b.p, b.cap); }); };
+  std::vector<Block> blocks(size_t(nk + na));
   if (G > 0) {
     DevBuf out;
     size_t bytes = (size_t(nk) + size_t(na) + 1) * G * 8;
@@ -2555,7 +2623,11 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
     fd.out_rows = reinterpret_cast<unsigned long long*>(fd.out_aggs + size_t(na) * G);
     CUDA_TRY(launch_finalize(fd, s));
     res->stats.kernel_launches += 1;
-    if (nk + na) CUDA_TRY(cudaMemcpyAsync(ctx->scratch, fd.out_keys, (size_t(nk) + size_t(na)) * G * 8, cudaMemcpyDeviceToHost, s));
+    for (int c = 0; c < nk + na; c++) {
+      blocks[size_t(c)].p = pool->take(G * 8, &blocks[size_t(c)].cap);
+      if (!blocks[size_t(c)].p) return fail(FGPU_ERR_OOM, "page-locked memory for the result columns");
+      CUDA_TRY(cudaMemcpyAsync(blocks[size_t(c)].p, fd.out_keys + size_t(c) * G, G * 8, cudaMemcpyDeviceToHost, s));
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
     res->stats.d2h_bytes += (size_t(nk) + size_t(na)) * G * 8;
   }
@@ -2573,11 +2645,13 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
     OwnedColumn col;
     col.name = ko.name;
     col.length = int64_t(G);
-    const long long* codes = h_keys.data() + size_t(k) * G;
+    const long long* codes = reinterpret_cast<const long long*>(blocks[size_t(k)].p);
     if (ko.is_int64) {
       col.format = "l";
-      col.data.resize(G * 8);
-      std::memcpy(col.data.data(), codes, G * 8);
+      if (G) {
+        col.ext = blocks[size_t(k)].p;
+        col.ext_keep = keep_of(blocks[size_t(k)]);
+      }
     } else {
       // dictionary<uint32, binary> holding only the values this result uses
       col.format = "I";
@@ -2613,6 +2687,7 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
         dict->offsets.push_back(int32_t(dict->data.size()));
       }
       col.dictionary = std::move(dict);
+      if (G) pool->give(blocks[size_t(k)].p, blocks[size_t(k)].cap);  // the codes are re-indexed into col.data
     }
     cols.push_back(std::move(col));
   }
@@ -2621,8 +2696,10 @@ int32_t finalize_result(fgpu_ctx* ctx, fgpu_result* res) {
     col.name = res->agg_names[size_t(a)];
     col.format = res->agg_is_float[size_t(a)] ? "g" : "l";
     col.length = int64_t(G);
-    col.data.resize(G * 8);
-    std::memcpy(col.data.data(), h_aggs.data() + size_t(a) * G, G * 8);
+    if (G) {
+      col.ext = blocks[size_t(nk + a)].p;
+      col.ext_keep = keep_of(blocks[size_t(nk + a)]);
+    }
     cols.push_back(std::move(col));
   }
   res->stats.algorithmic_bytes += (size_t(nk) + size_t(na)) * G * 8;
@@ -2764,7 +2841,6 @@ int32_t fgpu_shutdown(fgpu_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  for (auto& kv : ctx->pinned_free) cudaFreeHost(kv.second);
   if (ctx->scratch) cudaFreeHost(ctx->scratch);
   if (ctx->arena) cudaFreeHost(ctx->arena);
   delete ctx;
@@ -2791,7 +2867,9 @@ int32_t fgpu_part_put_parquet(fgpu_ctx* ctx, const char* table, uint64_t part_id
   std::string err;
   if (!open_part(file, len, part.get(), &err)) return fail(FGPU_ERR_PARQUET, err);
   if (!part->borrowed) {
-    // The caller may reuse the buffer on return: every column goes to the device now.
+    // The caller may reuse the buffer on return: every column goes to the device now (host images built in
+    // parallel, one worker per column).
+    prebuild_columns(&t, part.get(), part->columns);
     for (const std::string& col : part->columns) {
       int32_t rc = ensure_resident(ctx, &t, part.get(), col, nullptr);
       if (rc) {

@@ -148,8 +148,11 @@ __global__ void __launch_bounds__(kRunsThreads, 5) k_runs(const __grid_constant_
         if (lane == 0) apply_agg(uint8_t(afunc[a]), aflt[a], d.t_agg[a] + cs, (long long)v);
         part[a] = (unsigned long long)agg_identity(uint8_t(afunc[a]), aflt[a]);
       } else {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        // 64-bit warp sum from three 32-bit REDUX sums over 22-bit pieces (32 x 2^22 fits): no shuffle chain
+        const uint32_t s0 = __reduce_add_sync(FULL, uint32_t(v) & 0x3fffffu);
+        const uint32_t s1 = __reduce_add_sync(FULL, uint32_t(v >> 22) & 0x3fffffu);
+        const uint32_t s2 = __reduce_add_sync(FULL, uint32_t(v >> 44));
+        v = (unsigned long long)s0 + ((unsigned long long)s1 << 22) + ((unsigned long long)s2 << 44);
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(d.t_agg[a] + cs), v);
         part[a] = 0;
       }
