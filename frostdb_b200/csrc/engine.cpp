@@ -1088,7 +1088,37 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
     }
     std::vector<VisibleRG> kept;
     const bool prune_on = !getenv("FROSTGPU_NO_PRUNE");
+    // AggFuncPushDown (logicalplan/optimize.go:166-193) + MaxAgg (expr/filter.go:156-207): a global Max(column)
+    // directly above the scan, without filter, turns into a row-group filter that memoises the largest chunk
+    // maximum seen so far, in scan order, and only lets row groups through that exceed it.
+    bool max_agg = prune_on && q.kind == FGPU_PLAN_AGGREGATE && q.group_by.empty() && q.aggs.size() == 1 && q.aggs[0].func == FGPU_AGG_MAX &&
+                   q.filter < 0 && q.exprs[size_t(q.aggs[0].expr)].kind == FGPU_EXPR_COLUMN;
+    const std::string max_col = max_agg ? q.exprs[size_t(q.aggs[0].expr)].name : std::string();
+    bool have_max = false;
+    int64_t max_i = 0;
+    double max_f = 0;
     for (VisibleRG& v : c->rgs) {
+      if (max_agg && !v.part->arrow) {
+        auto it = v.rg->cols.find(max_col);
+        if (it == v.rg->cols.end()) continue;  // no such field in this row group: nothing to contribute
+        const ChunkHost& ch = it->second;
+        const bool all_null = ch.null_count >= 0 && uint64_t(ch.null_count) == v.rg->n_rows;
+        if (all_null) continue;
+        if (ch.has_minmax && (ch.phys == PT_INT64 || ch.phys == PT_DOUBLE)) {
+          bool greater;
+          if (ch.phys == PT_INT64) {
+            greater = !have_max || ch.max_bits > max_i;
+            if (greater) max_i = ch.max_bits;
+          } else {
+            double mx;
+            std::memcpy(&mx, &ch.max_bits, 8);
+            greater = !have_max || mx > max_f;
+            if (greater) max_f = mx;
+          }
+          if (!greater) continue;
+          have_max = true;
+        }
+      }
       // Parquet parts: the reference's own row-group filter first (L0 Arrow records are never filtered, lsm.go:420-427)
       if (prune_on && !v.part->arrow && q.filter >= 0 && !rg_may_match(q, q.filter, *v.rg)) continue;
       bool drop = false;

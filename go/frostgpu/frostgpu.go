@@ -89,3 +89,56 @@ func (e *Engine) DropPart(table string, partID uint64) error {
 
 // Handle exposes the raw context to the physicalplan shim in the same module.
 func (e *Engine) Handle() unsafe.Pointer { return unsafe.Pointer(e.ctx) }
+
+// ---- multi-GPU: the exchange inside the library (fgpu_comm_*) -----------------------------------------------------
+// One Engine per GPU (several in one process, or one process per GPU).  The caller moves the 128-byte handles between
+// the ranks with whatever transport it has; every rank then opens the communicator with all of them in rank order.
+
+const CommHandleBytes = C.FGPU_COMM_HANDLE_BYTES
+
+// CommExport allocates this rank's mailbox and returns its handle.
+func (e *Engine) CommExport(rank, nRanks int, slotBytes uint64) ([]byte, error) {
+	h := make([]byte, CommHandleBytes)
+	rc := C.fgpu_comm_export(e.ctx, C.int32_t(rank), C.int32_t(nRanks), C.uint64_t(slotBytes), (*C.uint8_t)(unsafe.Pointer(&h[0])))
+	if rc != 0 {
+		return nil, lastError(rc)
+	}
+	return h, nil
+}
+
+// CommOpen maps every rank's mailbox (handles concatenated in rank order).
+func (e *Engine) CommOpen(allHandles []byte) error {
+	if rc := C.fgpu_comm_open(e.ctx, (*C.uint8_t)(unsafe.Pointer(&allHandles[0]))); rc != 0 {
+		return lastError(rc)
+	}
+	return nil
+}
+
+// CommClose releases the mailbox; call it after a barrier of the ranks.
+func (e *Engine) CommClose() { C.fgpu_comm_close(e.ctx) }
+
+// NewInProcess opens one Engine per device of this process and connects them: FrostDB is a single process, so this
+// is the deployment SURVEY.md §8(b) sketches (parts are then assigned to the engine with the fewest resident bytes
+// by the caller, and every engine runs the same plan through fgpu_query_execute_collective from its own goroutine).
+func NewInProcess(devices []int, slotBytes uint64) ([]*Engine, error) {
+	engines := make([]*Engine, 0, len(devices))
+	all := make([]byte, 0, len(devices)*CommHandleBytes)
+	for r, d := range devices {
+		e, err := New(d)
+		if err != nil {
+			return nil, err
+		}
+		engines = append(engines, e)
+		h, err := e.CommExport(r, len(devices), slotBytes)
+		if err != nil {
+			return nil, err
+		}
+		all = append(all, h...)
+	}
+	for _, e := range engines {
+		if err := e.CommOpen(all); err != nil {
+			return nil, err
+		}
+	}
+	return engines, nil
+}

@@ -259,3 +259,72 @@ def test_computed_group_keys_time_buckets(pair):
     assert_same(got, exp)
     got, exp = p.run(lambda q: q.Project(v, lp.Sub(ts, v).Alias("d")).Aggregate([lp.Count(v)], [lp.Col("d"), lp.Col("labels.b")]))
     assert_same(got, exp)
+
+
+def test_read_transaction_hides_later_parts(pair):
+    """Table.View -> LSM.Scan skips parts whose tx is above the read transaction (index/lsm.go:416): a query with an
+    older watermark must not see them, in the engine and in the oracle alike; the compiled plan is per watermark."""
+    import ctypes as C
+    from frostdb_b200 import _lib
+    from frostdb_b200.physicalplan import GPUScan
+    p = pair("watermark", dp.SampleDefinition())
+    bufs = [dp.write_part(p.schema, make_columns(10_000, 600 + i, {"a": (4, 0.0)}, t0=i * 10_000)) for i in range(3)]
+    eng = p.store.engine
+    for i, b in enumerate(bufs):
+        eng.put_parquet(p.name, b, tx=10 * (i + 1))
+        p.oe.put_parquet(p.name, b, tx=10 * (i + 1))
+    aggs, keys = [lp.Sum(lp.Col("value")), lp.Count(lp.Col("value"))], [lp.Col("labels.a")]
+    lib = _lib.load()
+    scan = GPUScan(eng, p.name, None, _lib.PLAN_AGGREGATE, keys, aggs)
+    q, keep = scan.prepare()
+    plan, keep2 = scan._plan()
+    names = ["labels.a", "sum(value)", "count(value)"]
+    for tx, n_parts in ((5, 0), (10, 1), (25, 2), (30, 3), (10, 1), (1000, 3)):
+        res = C.c_void_p()
+        _lib.check(lib.fgpu_query_execute(eng.handle, q, tx, C.byref(res)))
+        got = list(eng.drain(res))
+        lib.fgpu_result_free(res)
+        ores = p.oe.tables[p.name].execute(plan, tx=tx, threads=2)
+        exp = [ores.to_batch([a.Name() for a in aggs])] if ores.n_groups else []
+        ores.close()
+        assert rows_of(got, names) == rows_of(exp, names), tx
+        assert sum(r[2] for r in rows_of(got, names)) == 10_000 * n_parts
+    lib.fgpu_query_free(q)
+
+
+def test_concurrent_executes_on_one_context(store):
+    """Several host threads on one fgpu_ctx (the Go shim calls from many goroutines): calls are serialised inside
+    the library, every thread gets its own complete result."""
+    import threading
+    p = Pair(store, "concurrent", dp.SampleDefinition())
+    try:
+        for i in range(2):
+            p.insert(make_columns(30_000, 650 + i, {"a": (5, 0.0), "b": (7, 0.1)}, t0=i * 30_000), sort=bool(i))
+        plans = [lambda q: q.Aggregate([lp.Sum(lp.Col("value"))], [lp.Col("labels.a")]),
+                 lambda q: q.Filter(lp.Col("value").Lt(lp.Literal(500))).Aggregate([lp.Count(lp.Col("value"))], [lp.Col("labels.b")]),
+                 lambda q: q.Distinct(lp.Col("labels.a"), lp.Col("labels.b"))]
+        expected = []
+        for b in plans:
+            exp = []
+            b(oracle_query(p.oe, p.name)).Execute(None, lambda c, r: exp.append(r))
+            expected.append(rows_of(exp))
+        errors = []
+
+        def worker(k):
+            try:
+                for it in range(20):
+                    j = (k + it) % len(plans)
+                    got = []
+                    plans[j](query.NewEngine(None, p.db.TableProvider()).ScanTable(p.name)).Execute(None, lambda c, r: got.append(r))
+                    if rows_of(got) != expected[j]:
+                        errors.append((k, it, j))
+            except Exception as ex:  # noqa: BLE001
+                errors.append((k, repr(ex)))
+        ths = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errors, errors[:3]
+    finally:
+        p.close()

@@ -343,3 +343,17 @@ def test_prepared_query_reexecuted_and_invalidated(pair):
         assert execute(q) == first
     finally:
         lib.fgpu_query_free(q)
+
+
+def test_global_max_skips_row_groups_below_the_running_maximum(pair):
+    """AggFuncPushDown + MaxAgg (logicalplan/optimize.go:166-193, expr/filter.go:156-207): Max(column) without group-by
+    and filter only reads the row groups whose chunk maximum exceeds the largest one seen before them."""
+    p = pair("maxagg")
+    n = 40_000
+    for i in range(4):
+        p.insert(sorted_columns(n, 300 + i, t0=(3 - i) * n), row_group_size=10_000)   # later parts hold EARLIER timestamps
+    run3(p, lambda q: q.Aggregate([lp.Max(lp.Col("timestamp"))], []))
+    st = scan_stats(p, None, [lp.Max(lp.Col("timestamp"))], [])
+    assert st["row_groups_pruned"] >= 12 and st["row_groups"] <= 4   # only the first part's row groups raise the maximum
+    run3(p, lambda q: q.Aggregate([lp.Max(lp.Col("value"))], []))
+    run3(p, lambda q: q.Aggregate([lp.Min(lp.Col("timestamp"))], []))    # no push-down for Min
