@@ -310,6 +310,8 @@ struct TileAggDesc {
   uint32_t cell64[kTaAggs];      // 1: 64-bit cells (Min / Max / float64), 0: low word of an int64 Sum
   uint32_t table_bytes;          // shared-memory table bytes
   uint32_t chunk_tiles;          // consecutive tiles a CTA takes per turn
+  uint32_t keys8;                // every key code column of this launch is 8 bits wide
+  uint32_t sums_fit32;           // chunk statistics prove that no int64 Sum leaves 32 bits inside one CTA
   const TileAggRg* rgs;
   const uint32_t* rg_first_tile;  // [n_rg + 1]
   unsigned long long* t_rows;

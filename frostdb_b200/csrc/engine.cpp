@@ -1479,7 +1479,7 @@ void bind_table(QueryDesc* qd, uint8_t* base) {
 // under the switches it was built with.
 std::string env_switches() {
   static const char* const kNames[] = {"FROSTGPU_NO_TILE", "FROSTGPU_NO_RUNS", "FROSTGPU_NO_PRUNE", "FROSTGPU_NO_FAST", "FROSTGPU_NO_FUSE",
-                                       "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK",
+                                       "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK", "FROSTGPU_TA_CARRY",
                                        "FROSTGPU_VL", "FROSTGPU_RING", "FROSTGPU_RUNS_BR", "FROSTGPU_RUNS_RING", "FROSTGPU_RUNS_SPAN",
                                        "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE"};
   std::string out;
@@ -1714,6 +1714,8 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     int plain_slot[kTaPlain] = {0}, code_slot[kTaCodes] = {0};
     uint32_t code_wmax[kTaCodes] = {0};
     int leaf_q[kTaLeaves] = {0}, pred_q[kTaPreds] = {0}, agg_index[kTaAggs] = {0};
+    bool agg_bounded = true;          // every int64 Sum input of every row group has statistics inside [0, 2^32)
+    uint64_t agg_max = 0;             // the largest of those chunk maxima
   } TA;
   bool ta_q = q.kind != FGPU_PLAN_FILTER && qd.table_mode == TM_DENSE && (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) &&
               qd.n_keys <= kTaKeys && !getenv("FROSTGPU_NO_TILE");
@@ -1935,6 +1937,12 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       if (ok) {
         lut_fix.erase(std::remove_if(lut_fix.begin(), lut_fix.end(), [&](const std::pair<size_t, size_t>& f) { return f.first >= size_t(g) * n_leaves; }), lut_fix.end());
         if (none) { ta_empty_rgs++; continue; }
+        for (uint32_t i = 0; i < td.na; i++) {  // bounds of the int64 Sum inputs (see TileAggDesc::sums_fit32)
+          if (td.cell64[i]) continue;
+          const ChunkHost& ch = rg.cols.at(c.slot_names[size_t(TA.plain_slot[td.agg_plain[i]])]);
+          if (!ch.has_minmax || ch.phys != PT_INT64 || ch.min_bits < 0 || ch.max_bits > 0xffffffffll) TA.agg_bounded = false;
+          else TA.agg_max = std::max<uint64_t>(TA.agg_max, uint64_t(ch.max_bits));
+        }
         TA.rgs.push_back(tr);
         TA.rows.push_back(rg.n_rows);
         continue;  // slot g of the general tables is reused by the next row group
@@ -2034,6 +2042,14 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     TA.first_tile.push_back(t);
     td.n_tiles = t;
     td.chunk_tiles = std::max<uint32_t>(1, t / (uint32_t(ctx->sm_count) * 4));  // ~4 turns per CTA: a CTA stays inside one row group for a whole chunk
+    td.keys8 = 1;
+    for (uint32_t i = 0; i < td.nk; i++)
+      if (TA.code_wmax[td.key_code[i]] > 8) td.keys8 = 0;
+    {  // can a Sum leave 32 bits inside one CTA?  rows per CTA <= its share of the tiles (+ one chunk), all in one slot
+      const uint64_t grid = uint64_t(std::max(1, ctx->sm_count));
+      const uint64_t rows_per_cta = (uint64_t(t) / grid + 2 * uint64_t(td.chunk_tiles) + 1) * td.tile_rows;
+      td.sums_fit32 = (TA.agg_bounded && !getenv("FROSTGPU_TA_CARRY") && TA.agg_max * rows_per_cta < (1ull << 32)) ? 1u : 0u;
+    }
     if (const char* e = getenv("FROSTGPU_TA_CHUNK")) td.chunk_tiles = uint32_t(std::max(1, atoi(e)));
   }
 

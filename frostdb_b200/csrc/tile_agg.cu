@@ -144,7 +144,10 @@ constexpr int RB = 4;  // rows a consumer thread works on at a time (independent
 // SMEM: CTA-private table in shared memory (else atomics on the global table).
 // SIMPLE: every range leaf is a plain int64 range, no dictionary leaves, every stored aggregate is Sum(int64).
 // NK / NA: number of key columns / stored aggregates when the instance is specialised for them (-1: read from the descriptor).
-template <bool SMEM, bool SIMPLE, int NK, int NA>
+// K8: every key code column of the launch is 8 bits wide.  NOCARRY: the host proved from the chunk statistics that no
+// int64 Sum can leave 32 bits inside one CTA (values in [0, 2^32) and rows per CTA x max value < 2^32): plain
+// fire-and-forget shared-memory adds, no carry bookkeeping.
+template <bool SMEM, bool SIMPLE, int NK, int NA, bool K8, bool NOCARRY>
 __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constant__ TileAggDesc d) {
   extern __shared__ __align__(128) uint8_t dyn[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -181,17 +184,32 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
   __syncthreads();
 
   const uint32_t CH = d.chunk_tiles, G = gridDim.x, b = blockIdx.x;
-  auto nth_tile = [&](uint32_t it) -> uint32_t { return ((it / CH) * G + b) * CH + (it % CH); };
+  // a CTA takes chunks of CH consecutive tiles, chunk b, b + G, ...; tile, ring stage and phase advance by
+  // additions only (no division per tile and thread)
+  struct TileIter {
+    uint32_t tile, within, st, ph;
+  };
+  auto iter_begin = [&]() { return TileIter{b * CH, 0u, 0u, 0u}; };
+  auto iter_next = [&](TileIter& t) {
+    t.tile++;
+    if (++t.within == CH) {
+      t.within = 0;
+      t.tile += (G - 1u) * CH;
+    }
+    if (++t.st == S) {
+      t.st = 0;
+      t.ph ^= 1u;
+    }
+  };
 
   if (warp == kTaConsumerWarps) {
     // ================================ producer warp ================================
     uint32_t rg = 0, rg_lo = 0, rg_hi = 0, n_rows = 0, rg_cached = 0xffffffffu;
     unsigned long long w0 = 0, w1 = 0;  // this lane's two words of the current row group's descriptor
     static_assert(sizeof(TileAggRg) / 8 <= 64, "descriptor fits two words per lane");
-    for (uint32_t it = 0;; it++) {
-      const uint32_t tile = nth_tile(it);
-      if (tile >= d.n_tiles) break;
-      const uint32_t st = it % S, ph = (it / S) & 1u;
+    uint32_t it = 0;
+    for (TileIter ti = iter_begin(); ti.tile < d.n_tiles; iter_next(ti), it++) {
+      const uint32_t tile = ti.tile, st = ti.st, ph = ti.ph;
       if (tile >= rg_hi) {
         while (tile >= __ldg(d.rg_first_tile + rg + 1)) rg++;
         rg_lo = __ldg(d.rg_first_tile + rg);
@@ -272,10 +290,8 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
 #pragma unroll
     for (int a = 0; a < kTaAggs; a++) aoff[a] = uint32_t(a) < na ? d.plain_off[d.agg_plain[a]] : 0u;
 
-    for (uint32_t it = 0;; it++) {
-      const uint32_t tile = nth_tile(it);
-      if (tile >= d.n_tiles) break;
-      const uint32_t st = it % S, ph = (it / S) & 1u;
+    for (TileIter ti = iter_begin(); ti.tile < d.n_tiles; iter_next(ti)) {
+      const uint32_t st = ti.st, ph = ti.ph;
       mbar_wait(bars + st * 8, ph);
       const TileHdr* h = reinterpret_cast<const TileHdr*>(hdrs + st * kHdrBytes);
       const uint32_t slot_s = ring_s + st * d.slot_bytes;
@@ -387,7 +403,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
           for (int k = 0; k < kTaKeys; k++) {
             if (uint32_t(k) < nk) {
               const uint32_t cb = slot_s + koff[k];
-              if (ksh[k] == 0) {
+              if (K8 || ksh[k] == 0) {
 #pragma unroll
                 for (int j = 0; j < RB; j++) slot[j] += (lds_u8(cb + r[j]) + kbias[k]) * kstride[k];
               } else if (ksh[k] == 1) {
@@ -412,6 +428,11 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
                 const uint32_t cb = slot_s + aoff[a];
                 if (SIMPLE || !d.cell64[a]) {
                   const uint32_t cells_s = table_s + d.cell_off[a];
+                  if (NOCARRY) {
+#pragma unroll
+                    for (int j = 0; j < RB; j++) red_add_shared_if(cells_s + slot[j] * 4u, uint32_t(lds64(cb + r[j] * 8u)), act[j]);
+                    continue;
+                  }
                   uint32_t up[RB], any_up = 0;
 #pragma unroll
                   for (int j = 0; j < RB; j++) {
@@ -496,24 +517,29 @@ size_t tile_agg_smem_bytes(const TileAggDesc& d) {
 
 namespace {
 using TaKern = void (*)(const TileAggDesc);
-template <int NK>
+template <int NK, bool K8, bool NOCARRY>
 TaKern simple_smem_na(int na) {
   switch (na) {
-    case 0: return k_tile_agg<true, true, NK, 0>;
-    case 1: return k_tile_agg<true, true, NK, 1>;
-    case 2: return k_tile_agg<true, true, NK, 2>;
+    case 0: return k_tile_agg<true, true, NK, 0, K8, NOCARRY>;
+    case 1: return k_tile_agg<true, true, NK, 1, K8, NOCARRY>;
+    case 2: return k_tile_agg<true, true, NK, 2, K8, NOCARRY>;
     default: return nullptr;
   }
 }
-TaKern simple_smem(int nk, int na) {
+template <bool K8, bool NOCARRY>
+TaKern simple_smem_nk(int nk, int na) {
   switch (nk) {
-    case 0: return simple_smem_na<0>(na);
-    case 1: return simple_smem_na<1>(na);
-    case 2: return simple_smem_na<2>(na);
-    case 3: return simple_smem_na<3>(na);
-    case 4: return simple_smem_na<4>(na);
+    case 0: return simple_smem_na<0, K8, NOCARRY>(na);
+    case 1: return simple_smem_na<1, K8, NOCARRY>(na);
+    case 2: return simple_smem_na<2, K8, NOCARRY>(na);
+    case 3: return simple_smem_na<3, K8, NOCARRY>(na);
+    case 4: return simple_smem_na<4, K8, NOCARRY>(na);
     default: return nullptr;
   }
+}
+TaKern simple_smem(int nk, int na, bool k8, bool nocarry) {
+  if (k8) return nocarry ? simple_smem_nk<true, true>(nk, na) : simple_smem_nk<true, false>(nk, na);
+  return nocarry ? simple_smem_nk<false, true>(nk, na) : simple_smem_nk<false, false>(nk, na);
 }
 }  // namespace
 
@@ -524,10 +550,10 @@ cudaError_t launch_tile_agg(const TileAggDesc& d, int sm_count, cudaStream_t st)
   for (uint32_t l = 0; l < d.nl; l++) simple = simple && d.leaf_flags[l] == 0;
   for (uint32_t a = 0; a < d.na; a++) simple = simple && d.cell64[a] == 0;
   TaKern kern = nullptr;
-  if (simple && d.smem_table) kern = simple_smem(int(d.nk), int(d.na));
+  if (simple && d.smem_table) kern = simple_smem(int(d.nk), int(d.na), d.keys8 != 0, d.sums_fit32 != 0);
   if (!kern) {
-    if (d.smem_table) kern = simple ? k_tile_agg<true, true, -1, -1> : k_tile_agg<true, false, -1, -1>;
-    else kern = simple ? k_tile_agg<false, true, -1, -1> : k_tile_agg<false, false, -1, -1>;
+    if (d.smem_table) kern = simple ? k_tile_agg<true, true, -1, -1, false, false> : k_tile_agg<true, false, -1, -1, false, false>;
+    else kern = simple ? k_tile_agg<false, true, -1, -1, false, false> : k_tile_agg<false, false, -1, -1, false, false>;
   }
   static std::unordered_map<const void*, size_t> configured;  // (guarded by the engine's mutex)
   size_t& cfg = configured[reinterpret_cast<const void*>(kern)];

@@ -30,7 +30,7 @@ def pair(store):
     yield make
     for p in made:
         p.close()
-    for k in ("FROSTGPU_NO_TILE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK"):
+    for k in ("FROSTGPU_NO_TILE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK", "FROSTGPU_TA_CARRY"):
         os.environ.pop(k, None)
 
 
@@ -75,7 +75,7 @@ def test_unsorted_two_keys(pair, rows, rg, page):
     assert st["rows_selected"] == 3 * rows
     # ring shapes and the global-table variant give the same records
     for env in ({"FROSTGPU_TA_TILE": "3072", "FROSTGPU_TA_STAGES": "2"}, {"FROSTGPU_TA_TILE": "6144", "FROSTGPU_TA_STAGES": "3"},
-                {"FROSTGPU_TA_GLOBAL": "1"}, {"FROSTGPU_TA_CHUNK": "3"}):
+                {"FROSTGPU_TA_GLOBAL": "1"}, {"FROSTGPU_TA_CHUNK": "3"}, {"FROSTGPU_TA_CARRY": "1"}):
         os.environ.update(env)
         try:
             got, exp = p.run(lambda q: q.Aggregate(SUMCOUNT, keys))
