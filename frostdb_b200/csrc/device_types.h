@@ -212,6 +212,9 @@ struct SeedJob {
 // goes through the general scan kernel into the same aggregate table.
 constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 3, kRunsCols = kRunsLeaves + kRunsAggs;
 constexpr int kRunsPreds = 2;  // dictionary-column leaves evaluated once per run (result byte per dictionary id)
+constexpr int kRtConsumerWarps = 8;                         // k_runs_tma: consumer warps per CTA (default; 4 / 8 / 16)
+constexpr int kRtMaxThreads = (16 + 1) * 32;                // + one producer warp
+constexpr int kRtDirMax = 128;                              // most directory entries staged per cursor column and tile
 
 struct RunsRg {
   uint32_t n_rows;
@@ -225,7 +228,12 @@ struct RunsRg {
   const Run* pred_runs[kRunsPreds];
   const Seed* pred_seeds[kRunsPreds];
   const uint8_t* pred_lut[kRunsPreds];
+  uint32_t n_runs[kRunsKeys];                  // entries of every key directory (the sentinel not counted)
+  uint32_t pred_n_runs[kRunsPreds];
+  uint32_t tile_rows;                          // k_runs_tma: rows per tile in this row group (fewer when more columns are staged)
+  uint8_t col_pos[8];                          // k_runs_tma: place of col[c] among the row group's staged (non-null) columns
 };
+static_assert(kRunsCols <= 8 && (kRunsKeys + kRunsPreds + 1) % 2 == 0, "RunsRg layout");
 
 struct RunsDesc {
   uint32_t n_rg, n_spans;
@@ -237,6 +245,11 @@ struct RunsDesc {
   uint32_t agg_func[kRunsAggs];                         // AggFunc | is_float << 8 (general-reducer instances)
   uint32_t n_pred;                                      // dictionary leaves (conjunction with the range leaves)
   uint32_t pred_null[kRunsPreds];                       // their result for NULL rows (== NULL selects NULLs)
+  // k_runs_tma (runs_tma.cu): block_rows = rows per tile, span_blocks = tiles per span, n_ring = ring stages
+  uint32_t dir_entries;                                 // directory entries staged per cursor column and tile
+  uint32_t stage_bytes, col_off;                        // bytes of one ring stage; offset of the staged columns inside it
+  uint32_t n_consumers, consumers_log2;                 // consumer warps per CTA
+  uint32_t _pad_rt;
   const RunsRg* rgs;
   const uint32_t* rg_first_span;  // [n_rg + 1]
   unsigned long long* t_rows;

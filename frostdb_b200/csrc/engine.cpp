@@ -646,7 +646,7 @@ struct ExecCache {
   bool ready = false;
   QueryDesc qd{};
   const QueryDesc* qdesc_dev = nullptr;
-  bool has_runs = false, has_ta = false;
+  bool has_runs = false, has_ta = false, runs_v1 = false;
   RunsDesc rd{};
   int runs_nl = 0, runs_nk = 0, runs_na = 0;
   TileAggDesc td{};
@@ -1481,6 +1481,7 @@ std::string env_switches() {
   static const char* const kNames[] = {"FROSTGPU_NO_TILE", "FROSTGPU_NO_RUNS", "FROSTGPU_NO_PRUNE", "FROSTGPU_NO_FAST", "FROSTGPU_NO_FUSE",
                                        "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK", "FROSTGPU_TA_CARRY",
                                        "FROSTGPU_VL", "FROSTGPU_RING", "FROSTGPU_RUNS_BR", "FROSTGPU_RUNS_RING", "FROSTGPU_RUNS_SPAN",
+                                       "FROSTGPU_RUNS_V1", "FROSTGPU_RT_TILE", "FROSTGPU_RT_STAGES", "FROSTGPU_RT_SPAN", "FROSTGPU_RT_WARPS",
                                        "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE"};
   std::string out;
   for (const char* n : kNames) {
@@ -1565,7 +1566,10 @@ int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective
   CUDA_TRY(cudaEventRecord(ctx->ev[0], s));
   CUDA_TRY(launch_table_init(x.qd, s));
   CUDA_TRY(cudaEventRecord(ctx->ev[1], s));
-  if (x.has_runs) CUDA_TRY(launch_runs(x.rd, x.runs_nl, x.runs_nk, x.runs_na, ctx->sm_count, s));
+  if (x.has_runs) {
+    if (x.runs_v1) CUDA_TRY(launch_runs(x.rd, x.runs_nl, x.runs_nk, x.runs_na, ctx->sm_count, s));
+    else CUDA_TRY(launch_runs_tma(x.rd, x.runs_nl, x.runs_nk, x.runs_na, ctx->sm_count, s));
+  }
   if (x.has_ta) CUDA_TRY(launch_tile_agg(x.td, ctx->sm_count, s));
   CUDA_TRY(launch_scan(x.qdesc_dev, x.qd, ctx->sm_count, s));
   CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
@@ -1657,6 +1661,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
   int runs_leaf_slot[kRunsLeaves] = {0}, runs_agg_slot[kRunsAggs] = {0}, runs_agg_index[kRunsAggs] = {0};
   uint32_t runs_agg_func[kRunsAggs] = {0};
   bool runs_q = q.kind != FGPU_PLAN_FILTER && c.runs_shape && !getenv("FROSTGPU_NO_RUNS");
+  const bool runs_v1 = getenv("FROSTGPU_RUNS_V1") != nullptr;  // the warp-private cp.async kernel (runs_scan.cu), kept for A/B measurements
   if (runs_q) {
     for (int l = 0; l < n_leaves && runs_q; l++) {
       const LeafDesc& ld = qd.leaves[l];
@@ -1845,6 +1850,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
         if (d.kind != CK_DICT_STR || d.row_runs == nullptr) { runs_ok = false; break; }
         rr.pred_runs[i] = d.row_runs;
         rr.pred_seeds[i] = d.row_seeds;
+        rr.pred_n_runs[i] = d.n_row_runs;
         rr.pred_lut[i] = reinterpret_cast<const uint8_t*>(uintptr_t(c.leaves[size_t(ql)].lut_off));  // offset, rebased below
         B.rd.pred_null[i] = rt.null_result;
       }
@@ -1875,6 +1881,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
         if (d.kind != CK_DICT_STR || d.row_runs == nullptr || uint64_t(d.n_row_runs) * 32 > uint64_t(rg.n_rows) + 1024) runs_ok = false;
         rr.runs[k] = d.row_runs;
         rr.seeds[k] = d.row_seeds;
+        rr.n_runs[k] = d.n_row_runs;
       }
     }
     if (runs_ok) {
@@ -1961,22 +1968,52 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     if (B.rgs.empty()) continue;
     RunsDesc& rd = B.rd;
     auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-    int br = envi("FROSTGPU_RUNS_BR", 256);
-    if (br != 128 && br != 256 && br != 512) br = 256;
-    int ring = envi("FROSTGPU_RUNS_RING", 2);
-    ring = std::min(4, std::max(2, ring));
-    if (rd.n_cols == 0) { br = 128; ring = 2; }  // nothing is staged (count per group): the ring is idle
-    rd.block_rows = uint32_t(br);
-    rd.n_ring = uint32_t(ring);
     rd.n_rg = uint32_t(B.rgs.size());
-    int per_sm = 1;
-    CUDA_TRY(runs_blocks_per_sm(rd, B.nl, runs_nk, runs_na, &per_sm));
-    const uint64_t warps = uint64_t(ctx->sm_count) * uint64_t(std::max(per_sm, 1)) * (kRunsThreads / 32);
     uint64_t total = 0;
     for (uint32_t r : B.rows) total += r;
-    uint64_t span_blocks = total / (warps * 8 * uint64_t(br));
-    span_blocks = std::min<uint64_t>(64, std::max<uint64_t>(4, span_blocks));
-    if (const char* e = getenv("FROSTGPU_RUNS_SPAN")) span_blocks = uint64_t(std::max(1, atoi(e)));
+    int br = 0;
+    uint64_t span_blocks = 0;
+    if (!runs_v1) {
+      // CTA-cooperative kernel (runs_tma.cu): tiles of br rows, spans of span_blocks tiles dealt to the CTAs in turn
+      // CTA-cooperative kernel (runs_tma.cu): every row group is cut into tiles of about 32 KB of column data; the
+      // launch's tile table {row group, first row} is dealt to the CTAs in chunks of consecutive entries
+      uint32_t base_tile = 4096;
+      { const int f = envi("FROSTGPU_RT_TILE", 0); if (f == 1024 || f == 2048 || f == 4096 || f == 8192) base_tile = uint32_t(f); }
+      uint32_t tiles_rt = 0, gidx = 0, col_region = 0;
+      for (RunsRg& r : B.rgs) {
+        uint32_t nc = 0;
+        for (uint32_t i = 0; i < rd.n_cols; i++) {
+          r.col_pos[i] = uint8_t(nc);
+          if (r.col[i]) nc++;
+        }
+        r.tile_rows = runs_tma_tile_rows(base_tile, nc);
+        col_region = std::max(col_region, nc * r.tile_rows * 8u);
+        for (uint32_t r0 = 0; r0 < r.n_rows; r0 += r.tile_rows) {
+          B.first_span.push_back(gidx);
+          B.first_span.push_back(r0);
+          tiles_rt++;
+        }
+        gidx++;
+      }
+      runs_tma_plan(rd, runs_nk + runs_np, base_tile, col_region, envi("FROSTGPU_RT_STAGES", 0), envi("FROSTGPU_RT_WARPS", 0), envi("FROSTGPU_RT_SPAN", 0));
+      rd.n_spans = tiles_rt;
+      (void)br; (void)span_blocks;
+      continue;
+    } else {
+      br = envi("FROSTGPU_RUNS_BR", 256);
+      if (br != 128 && br != 256 && br != 512) br = 256;
+      int ring = envi("FROSTGPU_RUNS_RING", 2);
+      ring = std::min(4, std::max(2, ring));
+      if (rd.n_cols == 0) { br = 128; ring = 2; }  // nothing is staged (count per group): the ring is idle
+      rd.block_rows = uint32_t(br);
+      rd.n_ring = uint32_t(ring);
+      int per_sm = 1;
+      CUDA_TRY(runs_blocks_per_sm(rd, B.nl, runs_nk, runs_na, &per_sm));
+      const uint64_t warps = uint64_t(ctx->sm_count) * uint64_t(std::max(per_sm, 1)) * (kRunsThreads / 32);
+      span_blocks = total / (warps * 8 * uint64_t(br));
+      span_blocks = std::min<uint64_t>(64, std::max<uint64_t>(4, span_blocks));
+      if (const char* e = getenv("FROSTGPU_RUNS_SPAN")) span_blocks = uint64_t(std::max(1, atoi(e)));
+    }
     rd.span_blocks = uint32_t(span_blocks);
     const uint64_t span_rows = span_blocks * uint64_t(br);
     uint32_t spans = 0;
@@ -2267,7 +2304,8 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       rd.t_rows = qd.t_rows;
       for (int a = 0; a < runs_na; a++) rd.t_agg[a] = qd.t_agg[runs_agg_index[a]];
       rd.counters = qd.counters;
-      CUDA_TRY(launch_runs(rd, B.nl, runs_nk, runs_na, ctx->sm_count, s));
+      if (runs_v1) CUDA_TRY(launch_runs(rd, B.nl, runs_nk, runs_na, ctx->sm_count, s));
+      else CUDA_TRY(launch_runs_tma(rd, B.nl, runs_nk, runs_na, ctx->sm_count, s));
       st.kernel_launches++;
       st.row_groups_runs += uint32_t(B.rgs.size());
     }
@@ -2343,6 +2381,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     x.qd = qd;
     x.qdesc_dev = qdesc_dev;
     x.has_runs = !batches[0].rgs.empty();
+    x.runs_v1 = runs_v1;
     x.rd = batches[0].rd;
     x.runs_nl = batches[0].nl;
     x.runs_nk = runs_nk;

@@ -22,6 +22,12 @@ cudaError_t launch_scan(const QueryDesc* d_q, const QueryDesc& q, int sm_count, 
 constexpr int kRunsThreads = 128;
 cudaError_t launch_runs(const RunsDesc& d, int nl, int nk, int na, int sm_count, cudaStream_t st);
 cudaError_t runs_blocks_per_sm(const RunsDesc& d, int nl, int nk, int na, int* per_sm);  // resident CTAs per SM for this shape
+// sorted-run scan, CTA-cooperative with TMA-staged column tiles (runs_tma.cu): same descriptors as launch_runs
+uint32_t runs_tma_tile_rows(uint32_t base, uint32_t nc);  // rows per tile of a row group that stages nc columns
+void runs_tma_plan(RunsDesc& d, int nq, uint32_t base_tile, uint32_t col_region, int force_stages, int force_warps, int force_chunk);  // tile rows, ring depth, stage layout
+size_t runs_tma_smem_bytes(const RunsDesc& d);
+int runs_tma_ctas_per_sm(const RunsDesc& d);
+cudaError_t launch_runs_tma(const RunsDesc& d, int nl, int nk, int na, int sm_count, cudaStream_t st);
 // filter-only plans over PLAIN columns (take_rows.cu): count per span, scan, ordered write
 cudaError_t launch_take(const TakeDesc& d, int sm_count, cudaStream_t st);
 int take_resident_warps(int sm_count);
