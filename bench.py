@@ -535,7 +535,7 @@ def main():
             "dtype": "int64", "data": "synthetic", "config": workload_config(rows_per_gpu, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "fgpu::k_runs (sorted-run scan); unsorted / short-run / nullable keys: fgpu::k_tile_agg, see extra",
+                         "kernel": "fgpu::k_runs_tma (sorted-run scan, TMA-staged tiles); unsorted / short-run / nullable keys: fgpu::k_tile_agg, see extra",
                          "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "parity": parity, "groups": int(st["groups"]), "rows_selected_per_gpu": int(st["rows_selected"]),

@@ -212,8 +212,8 @@ struct SeedJob {
 // goes through the general scan kernel into the same aggregate table.
 constexpr int kRunsLeaves = 2, kRunsKeys = 3, kRunsAggs = 3, kRunsCols = kRunsLeaves + kRunsAggs;
 constexpr int kRunsPreds = 2;  // dictionary-column leaves evaluated once per run (result byte per dictionary id)
-constexpr int kRtConsumerWarps = 8;                         // k_runs_tma: consumer warps per CTA (default; 4 / 8 / 16)
-constexpr int kRtMaxThreads = (16 + 1) * 32;                // + one producer warp
+constexpr int kRtConsumerWarps = 8;                         // k_runs_tma: consumer warps per CTA (most; 4 / 8)
+constexpr int kRtMaxThreads = (kRtConsumerWarps + 1) * 32;  // + one producer warp
 constexpr int kRtDirMax = 128;                              // most directory entries staged per cursor column and tile
 
 struct RunsRg {
@@ -349,7 +349,8 @@ struct DenseOut {
   const unsigned long long* t_rows;
   const long long* t_agg[kMaxAggs];  // null: Count (the row count)
   const unsigned long long* counters;  // the query's counters: [0..3] travel in the header
-  uint8_t* out;  // [header 256 B: count u32 @0, counters u64 x4 @32, any_null u32 per key @64][n_keys x max_out u32 (8-byte aligned)][n_aggs x max_out i64]
+  uint32_t* hdr;  // 256 bytes of device memory, zero between launches (see k_finalize_dense)
+  uint8_t* out;   // device or page-locked host memory: [header 256 B: count u32 @0, counters u64 x4 @32, any_null u32 per key @64][n_keys x max_out u32 (8-byte aligned)][n_aggs x max_out i64]
 };
 
 // ---- partial-table exchange between the GPUs of one node (comm.cu) ---------------------------------------

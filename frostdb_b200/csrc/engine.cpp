@@ -236,8 +236,33 @@ struct fgpu_ctx {
 };
 
 // FROSTGPU_PROFILE=1: host-side phase times of every Execute on stderr (development aid).
+extern "C" char** environ;
+// The FROSTGPU_* development switches as one string.  Called per Execute: the scan of the environment is skipped
+// while the environment block looks unchanged (same array, same entry pointers: setenv / putenv replace an entry).
+const std::string& env_switches() {
+  static const char* const kNames[] = {"FROSTGPU_NO_TILE", "FROSTGPU_NO_RUNS", "FROSTGPU_NO_PRUNE", "FROSTGPU_NO_FAST", "FROSTGPU_NO_FUSE",
+                                       "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK", "FROSTGPU_TA_CARRY",
+                                       "FROSTGPU_VL", "FROSTGPU_RING", "FROSTGPU_RUNS_BR", "FROSTGPU_RUNS_RING", "FROSTGPU_RUNS_SPAN",
+                                       "FROSTGPU_RUNS_V1", "FROSTGPU_RT_TILE", "FROSTGPU_RT_STAGES", "FROSTGPU_RT_SPAN", "FROSTGPU_RT_WARPS",
+                                       "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE", "FROSTGPU_PROFILE"};
+  static std::mutex mu;
+  static std::string cached;
+  static uint64_t cached_sig = 0;
+  uint64_t sig = 0x9e3779b97f4a7c15ull ^ uint64_t(reinterpret_cast<uintptr_t>(environ));
+  for (char** e = environ; e && *e; e++) sig = (sig ^ uint64_t(reinterpret_cast<uintptr_t>(*e))) * 0x100000001b3ull;
+  std::lock_guard<std::mutex> lk(mu);
+  if (sig != cached_sig || cached_sig == 0) {
+    cached.clear();
+    for (const char* n : kNames) {
+      const char* v = getenv(n);
+      if (v) { cached += n; cached += '='; cached += v; cached += ';'; }
+    }
+    cached_sig = sig;
+  }
+  return cached;
+}
 struct PhaseClock {
-  bool on = getenv("FROSTGPU_PROFILE") != nullptr;
+  bool on = env_switches().find("FROSTGPU_PROFILE") != std::string::npos;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   std::string line;
   void mark(const char* what) {
@@ -1477,21 +1502,9 @@ void bind_table(QueryDesc* qd, uint8_t* base) {
 // Runs init + scan.  On success the result owns the device table.
 // The development / test switches that change how a plan is compiled or launched: a cached plan is only reused
 // under the switches it was built with.
-std::string env_switches() {
-  static const char* const kNames[] = {"FROSTGPU_NO_TILE", "FROSTGPU_NO_RUNS", "FROSTGPU_NO_PRUNE", "FROSTGPU_NO_FAST", "FROSTGPU_NO_FUSE",
-                                       "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK", "FROSTGPU_TA_CARRY",
-                                       "FROSTGPU_VL", "FROSTGPU_RING", "FROSTGPU_RUNS_BR", "FROSTGPU_RUNS_RING", "FROSTGPU_RUNS_SPAN",
-                                       "FROSTGPU_RUNS_V1", "FROSTGPU_RT_TILE", "FROSTGPU_RT_STAGES", "FROSTGPU_RT_SPAN", "FROSTGPU_RT_WARPS",
-                                       "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE"};
-  std::string out;
-  for (const char* n : kNames) {
-    const char* v = getenv(n);
-    if (v) { out += n; out += '='; out += v; out += ';'; }
-  }
-  return out;
-}
+inline bool env_has(const std::string& env, const char* name) { return env.find(name) != std::string::npos; }
 
-int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, const ExecCache& x);
+int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, ExecCache& x);
 void bind_table(QueryDesc* qd, uint8_t* base);
 
 // First half of the exchange, enqueued behind the scan: this rank's partial table goes into slot [rank] of every
@@ -1550,16 +1563,24 @@ int32_t comm_check(unsigned long long code) {
 
 // Re-issues the launches of a cached plan (see ExecCache): table init, scans, one copy back, one synchronisation.
 // Tail of a cached Execute: compact the (final) dense table into result columns on the device and bring them back.
+// The result image is written by the kernel straight into a page-locked block of the context's pool (host memory the
+// device addresses directly): no copy operation, and the block later travels to the Arrow consumer as it is.
 int32_t cached_tail(fgpu_ctx* ctx, ExecCache& x) {
   cudaStream_t s = ctx->stream;
-  CUDA_TRY(cudaMemsetAsync(x.out.p, 0, 256, s));
+  if (!x.pinned) {
+    x.pinned = ctx->pinned_take(x.out_bytes, &x.pinned_cap);
+    if (!x.pinned) return fail(FGPU_ERR_OOM, "page-locked memory for the result image");
+  }
+  x.dout.hdr = static_cast<uint32_t*>(x.out.p);
+  x.dout.out = x.pinned;
   CUDA_TRY(launch_finalize_dense(x.dout, s));
-  CUDA_TRY(cudaMemcpyAsync(x.pinned, x.out.p, x.out_bytes, cudaMemcpyDeviceToHost, s));
   return FGPU_OK;
 }
 
 // collective: 0 no exchange, 1 push + wait + merge in one go, 2 push only (fgpu_query_execute_collective_begin)
 int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective) {
+  PhaseClock pc;
+  struct Tail { PhaseClock& pc; ~Tail() { pc.flush("cached"); } } tail{pc};
   cudaStream_t s = ctx->stream;
   res->stats = x.stats;
   fgpu_stats& st = res->stats;
@@ -1589,7 +1610,9 @@ int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective
   }
   if (int32_t rc = cached_tail(ctx, x)) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
+  pc.mark("launch");
   CUDA_TRY(cudaStreamSynchronize(s));
+  pc.mark("sync");
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
   st.scan_kernel_ms = ms;
@@ -1599,7 +1622,9 @@ int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective
   st.rows_selected = counters[0];
   st.d2h_bytes += x.out_bytes;
   if (int32_t rc = comm_check(counters[3])) return rc;
-  return finalize_dense_host(ctx, res, x);
+  const int32_t rc = finalize_dense_host(ctx, res, x);
+  pc.mark("export");
+  return rc;
 }
 
 // collective: 0 no exchange; 1 / 2: the first run of a plan pushes its partial table and leaves the result pending
@@ -1610,7 +1635,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
   Table& plan_table = ctx->tables[q.table];
   if (plan_table.epoch == 0) plan_table.epoch = ++ctx->epoch_counter;
   const std::string env_now = env_switches();
-  if (!q.plan_cache || q.cache_epoch != plan_table.epoch || q.cache_tx != tx || q.cache_env != env_now || getenv("FROSTGPU_NO_PLAN_CACHE")) {
+  if (!q.plan_cache || q.cache_epoch != plan_table.epoch || q.cache_tx != tx || q.cache_env != env_now || env_has(env_now, "FROSTGPU_NO_PLAN_CACHE")) {
     std::shared_ptr<void> fresh(new Compiled(), [](void* p) { delete static_cast<Compiled*>(p); });
     int32_t rc0 = compile(ctx, q, tx, static_cast<Compiled*>(fresh.get()));
     q.plan_cache.reset();
@@ -1623,7 +1648,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     static_cast<Compiled*>(q.plan_cache.get())->h2d_bytes = 0;  // nothing is uploaded by a cached plan
   }
   Compiled& c = *static_cast<Compiled*>(q.plan_cache.get());
-  if (cacheable && c.exec && c.exec->ready && !getenv("FROSTGPU_NO_EXEC_CACHE")) return run_cached(ctx, *c.exec, res, collective);
+  if (cacheable && c.exec && c.exec->ready && !env_has(env_now, "FROSTGPU_NO_EXEC_CACHE")) return run_cached(ctx, *c.exec, res, collective);
   c.exec.reset();
   for (LeafHost& lh : c.leaves) lh.lut_off = size_t(-1);  // per-Execute state of the plan
   int32_t rc = FGPU_OK;
@@ -2354,8 +2379,10 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       for (int a = 0; a < kMaxAggs; a++) f.t_agg[a] = qd.t_agg[a];
       f.counters = qd.counters;
       x.out_bytes = 256 + size_t(qd.n_keys) * ((size_t(f.max_out) * 4 + 7) & ~size_t(7)) + size_t(qd.n_aggs) * f.max_out * 8;
-      CUDA_TRY(x.out.alloc(x.out_bytes, s));
-      f.out = static_cast<uint8_t*>(x.out.p);
+      CUDA_TRY(x.out.alloc(256, s));  // the device half of the header (k_finalize_dense leaves it zero)
+      CUDA_TRY(cudaMemsetAsync(x.out.p, 0, 256, s));
+      f.hdr = static_cast<uint32_t*>(x.out.p);
+      f.out = nullptr;  // a page-locked block per Execute (cached_tail)
     }
     x.pool = ctx->pinned;
     x.pinned = ctx->pinned_take(x.out_bytes, &x.pinned_cap);
@@ -2480,7 +2507,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
 
 // Compacted result image in page-locked memory -> one Arrow record (finishAggregate, aggregate.go:543-633): the
 // device already produced dictionary indices and aggregate values per result row (k_finalize_dense); the host copies.
-int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, const ExecCache& x) {
+int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, ExecCache& x) {
   (void)ctx;
   PhaseClock pc;
   const QueryDesc& qd = x.qd;
@@ -2491,16 +2518,26 @@ int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, const ExecCache& x)
   const size_t key_bytes = (size_t(x.dout.max_out) * 4 + 7) & ~size_t(7);
   std::vector<OwnedColumn> cols;
   cols.reserve(size_t(nk + na));
+  // the columns of the record are slices of the page-locked block the kernel wrote; it goes back to the pool when the
+  // consumer has released every array
+  std::shared_ptr<void> keep;
+  if (G > 0) {
+    std::shared_ptr<PinnedPool> pool = x.pool;
+    uint8_t* blk = x.pinned;
+    const size_t cap = x.pinned_cap;
+    keep = std::shared_ptr<void>(blk, [pool, blk, cap](void*) { pool->give(blk, cap); });
+  }
   for (int k = 0; k < nk; k++) {
     const KeyOut& ko = x.keys[size_t(k)];
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(x.pinned + 256 + size_t(k) * key_bytes);
+    uint32_t* idx = reinterpret_cast<uint32_t*>(x.pinned + 256 + size_t(k) * key_bytes);
     OwnedColumn col;
     col.name = ko.name;
     col.length = int64_t(G);
     col.format = "I";  // dictionary<uint32, binary>
-    col.data.resize(G * 4);
-    uint32_t* idx = reinterpret_cast<uint32_t*>(col.data.data());
-    std::memcpy(idx, src, G * 4);
+    if (G > 0) {
+      col.ext = reinterpret_cast<const uint8_t*>(idx);
+      col.ext_keep = keep;
+    }
     if (hdr[16 + k]) {  // NULL keys: validity bitmap, index 0 in the NULL slots
       col.validity.assign((G + 7) / 8, 0);
       for (size_t i = 0; i < G; i++) {
@@ -2549,14 +2586,18 @@ int32_t finalize_dense_host(fgpu_ctx* ctx, fgpu_result* res, const ExecCache& x)
     col.name = x.agg_names[size_t(a)];
     col.format = x.agg_is_float[size_t(a)] ? "g" : "l";
     col.length = int64_t(G);
-    col.data.resize(G * 8);
-    std::memcpy(col.data.data(), aggs + size_t(a) * x.dout.max_out * 8, G * 8);
+    if (G > 0) {
+      col.ext = aggs + size_t(a) * x.dout.max_out * 8;
+      col.ext_keep = keep;
+    }
     cols.push_back(std::move(col));
   }
   res->stats.algorithmic_bytes += (size_t(nk) + size_t(na)) * G * 8;
   if (G > 0) {  // finishAggregate skips empty aggregates (aggregate.go:547-549)
     res->records.push_back(std::move(cols));
     res->record_rows.push_back(int64_t(G));
+    x.pinned = nullptr;  // the block now belongs to the record; the next Execute takes another one
+    x.pinned_cap = 0;
   }
   res->finalized = true;
   pc.mark("arrow");

@@ -1961,8 +1961,10 @@ cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st) {
 // k_finalize_dense: occupied slots of a dense table -> compacted columns (one warp-aggregated atomic per warp)
 // ======================================================================================================
 __global__ void __launch_bounds__(256) k_finalize_dense(DenseOut f) {
-  uint32_t* hdr = reinterpret_cast<uint32_t*>(f.out);
-  if (blockIdx.x == 0 && threadIdx.x < 4) reinterpret_cast<unsigned long long*>(f.out + 32)[threadIdx.x] = f.counters[threadIdx.x];
+  // f.hdr: 256-byte header in DEVICE memory (zero on entry, left zero on exit): [0] rows written, [16 + k] key k has a
+  // NULL, [62] CTAs done.  f.out may be page-locked HOST memory (the columns are written over PCIe while the scan's
+  // tail still runs elsewhere; no copy operation follows): the last CTA to finish publishes the header there.
+  uint32_t* hdr = f.hdr;
   const size_t key_bytes = (size_t(f.max_out) * 4 + 7) & ~size_t(7);
   const int lane = threadIdx.x & 31;
   const size_t stride = size_t(gridDim.x) * blockDim.x;
@@ -1984,6 +1986,18 @@ __global__ void __launch_bounds__(256) k_finalize_dense(DenseOut f) {
     }
     long long* aggs = reinterpret_cast<long long*>(f.out + 256 + size_t(f.n_keys) * key_bytes);
     for (uint32_t a = 0; a < f.n_aggs; a++) aggs[size_t(a) * f.max_out + o] = f.t_agg[a] ? f.t_agg[a][s] : (long long)rows;
+  }
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(hdr + 62, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x < 64) {
+    __threadfence();
+    uint32_t v = threadIdx.x == 62 ? 0u : atomicAdd(hdr + threadIdx.x, 0u);
+    if (threadIdx.x >= 8 && threadIdx.x < 16) v = reinterpret_cast<const uint32_t*>(f.counters)[threadIdx.x - 8];  // counters [0..3] at byte 32
+    reinterpret_cast<uint32_t*>(f.out)[threadIdx.x] = v;
+    hdr[threadIdx.x] = 0;
   }
 }
 

@@ -151,7 +151,7 @@ constexpr uint32_t kHdrR0 = 40, kHdrN = 44, kHdrRg = 48, kHdrT = 52;  // first r
 // GEN = false: every stored aggregate is Sum(int64).  GEN = true: Sum / Min / Max over int64 or float64 (agg_ops.cuh).
 // HP: the launch has dictionary leaves (cursor columns behind the keys).
 template <int NL, int NK, int NA, bool GEN, bool HP>
-__global__ void __launch_bounds__(kRtMaxThreads, 1) k_runs_tma(const __grid_constant__ RunsDesc d) {
+__global__ void __launch_bounds__(kRtMaxThreads, 3) k_runs_tma(const __grid_constant__ RunsDesc d) {
   extern __shared__ __align__(128) uint8_t dyn[];
   constexpr int NQ = HP ? kNQ : NK;  // cursor columns the code is unrolled for
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -617,10 +617,10 @@ uint32_t runs_tma_tile_rows(uint32_t base, uint32_t nc) {
 // Ring depth, consumer warps and stage layout for a launch with nq cursor columns whose largest tile holds
 // col_region bytes of column data (fills the descriptor; block_rows = the tile rows of a one-column row group).
 void runs_tma_plan(RunsDesc& d, int nq, uint32_t base_tile, uint32_t col_region, int force_stages, int force_warps, int force_chunk) {
-  uint32_t S = 3;
+  uint32_t S = 2;  // two stages of 32 KB leave room for three CTAs per SM: measured faster than deeper rings under two
   if (force_stages >= 2 && force_stages <= 8) S = uint32_t(force_stages);
   uint32_t W = uint32_t(kRtConsumerWarps);
-  if (force_warps == 4 || force_warps == 8 || force_warps == 16) W = uint32_t(force_warps);
+  if (force_warps == 4 || force_warps == 8) W = uint32_t(force_warps);
   d.block_rows = base_tile;
   d.span_blocks = force_chunk >= 1 && force_chunk <= 64 ? uint32_t(force_chunk) : 4u;
   d.n_ring = S;
@@ -642,7 +642,7 @@ size_t runs_tma_smem_bytes(const RunsDesc& d) { return 128 + size_t(d.n_ring) * 
 int runs_tma_ctas_per_sm(const RunsDesc& d) {
   const size_t per_cta = runs_tma_smem_bytes(d) + 1024;
   int n = int((228u * 1024u) / per_cta);
-  const int by_threads = 2048 / int((d.n_consumers + 1) * 32), by_regs = 65536 / int((d.n_consumers + 1) * 32 * 104);
+  const int by_threads = 2048 / int((d.n_consumers + 1) * 32), by_regs = 65536 / int((d.n_consumers + 1) * 32 * 72);
   n = std::min(n, std::min(by_threads, by_regs));
   return std::max(1, std::min(n, 4));
 }

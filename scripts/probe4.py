@@ -101,8 +101,8 @@ def sweep(ci, combos):
         run("s", cases[ci][0], AGG, cases[ci][1], cases[ci][2], cases[ci][3], env)
 
 
-sweep(0, ((4096, 2, 8), (4096, 4, 8), (2048, 3, 8), (2048, 4, 8), (2048, 6, 8), (2048, 4, 4), (1024, 6, 4), (8192, 3, 16), (8192, 2, 16), (4096, 5, 16), (4096, 3, 16), (4096, 3, 4)))
-sweep(1, ((2048, 3, 8), (2048, 4, 8), (4096, 3, 8), (4096, 4, 16), (2048, 6, 8), (8192, 3, 16)))
-sweep(2, ((4096, 3, 8), (2048, 4, 8), (2048, 6, 8), (4096, 4, 16)))
-for sp in (1, 4, 16):
-    run("s", cases[0][0], AGG, cases[0][1], cases[0][2], cases[0][3], {"FROSTGPU_RT_SPAN": str(sp)})
+for ci in (0, 1, 2, 4, 6):
+    sweep(ci, ((4096, 2, 8), (4096, 3, 8), (2048, 3, 8), (2048, 4, 4), (4096, 2, 4)))
+for ci in (0, 6):
+    for sp in (1, 2, 8, 16):
+        run("s", cases[ci][0], AGG, cases[ci][1], cases[ci][2], cases[ci][3], {"FROSTGPU_RT_SPAN": str(sp)})
