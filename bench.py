@@ -539,7 +539,7 @@ def main():
                          "kernel_ms": avg_scan_ms, "algorithmic_bytes": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "parity": parity, "groups": int(st["groups"]), "rows_selected_per_gpu": int(st["rows_selected"]),
-            "rows_touched_per_gpu": int(rows_per_gpu - st["row_groups_pruned"] * bd.RG_ROWS) if rows_per_gpu % bd.RG_ROWS == 0 else None,
+            "rows_touched_per_gpu": int(st["rows_touched"]),
             "row_groups": {"scanned": int(st["row_groups"]), "pruned": int(st["row_groups_pruned"])},
             "setup": {"generate_s": round(t_gen, 2), "upload_s": round(t_up, 2), "parquet_bytes_per_gpu": int(file_bytes)},
             "extra": extra,

@@ -1962,8 +1962,9 @@ cudaError_t launch_finalize(const FinalizeDesc& f, cudaStream_t st) {
 // ======================================================================================================
 __global__ void __launch_bounds__(256) k_finalize_dense(DenseOut f) {
   // f.hdr: 256-byte header in DEVICE memory (zero on entry, left zero on exit): [0] rows written, [16 + k] key k has a
-  // NULL, [62] CTAs done.  f.out may be page-locked HOST memory (the columns are written over PCIe while the scan's
-  // tail still runs elsewhere; no copy operation follows): the last CTA to finish publishes the header there.
+  // NULL, [62] CTAs done.  f.out may be page-locked HOST memory (the columns then cross PCIe as they are produced and
+  // no copy operation follows the kernel).  The last CTA to finish publishes the header in front of the columns and
+  // clears the working copy, so no memset precedes the next launch.
   uint32_t* hdr = f.hdr;
   const size_t key_bytes = (size_t(f.max_out) * 4 + 7) & ~size_t(7);
   const int lane = threadIdx.x & 31;

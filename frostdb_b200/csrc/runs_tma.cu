@@ -536,19 +536,35 @@ __global__ void __launch_bounds__(kRtMaxThreads, 3) k_runs_tma(const __grid_cons
               }
             } else if (NL > 0) {
               counted = true;
-              const uint32_t steps = whole + (rem ? 1u : 0u);
+              // whole steps: no row mask; the tail step re-reads the segment's first row in the lanes behind its end
+              uint32_t so = off;
 #pragma unroll 2
-              for (uint32_t s = 0; s < steps; s++) {
-                bool act = s < whole || uint32_t(lane) < rem;
-                const uint32_t so = act ? off + s * 256u : off - uint32_t(lane) * 8u;  // lanes behind the segment re-read its first row (masked out)
+              for (uint32_t s = 0; s < whole; s++, so += 256u) {
+                bool in = true;
 #pragma unroll
                 for (int l = 0; l < NL; l++) {
                   const long long x = (long long)lds64(lcol[l] + so);
-                  act = act && x >= lo[l] && x <= hi[l];
+                  in = in && x >= lo[l] && x <= hi[l];
                 }
-                cnt += act ? 1u : 0u;
+                if (in) cnt++;
 #pragma unroll
-                for (int q = 0; q < NA; q++) fold(q, act, lds64(acol[q] + so));
+                for (int q = 0; q < NA; q++) {
+                  const unsigned long long v = lds64(acol[q] + so);
+                  if constexpr (GEN) fold(q, in, v);
+                  else if (in) part[q] += v;
+                }
+              }
+              if (rem) {
+                bool in = uint32_t(lane) < rem;
+                if (!in) so = off - uint32_t(lane) * 8u;
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                  const long long x = (long long)lds64(lcol[l] + so);
+                  in = in && x >= lo[l] && x <= hi[l];
+                }
+                if (in) cnt++;
+#pragma unroll
+                for (int q = 0; q < NA; q++) fold(q, in, lds64(acol[q] + so));
               }
             }
           }

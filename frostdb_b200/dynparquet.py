@@ -85,6 +85,26 @@ def SampleDefinition() -> Schema:
     )
 
 
+def BytesDefinition() -> Schema:
+    """The logictest "bytes" schema (logictest/logic_test.go:110-142): dynamic labels, timestamp, and a non-dynamic
+    string column `value`.  Upstream stores `timestamp` as UINT64 and `value` as DELTA_LENGTH_BYTE_ARRAY + LZ4_RAW;
+    this mirror writes int64 and RLE_DICTIONARY (the engine takes neither compressed pages nor non-dictionary strings
+    in Parquet parts) — the logical column types, which is what the queries see, are the same."""
+    return Schema(
+        name="test",
+        columns=[
+            ColumnDefinition("labels", TYPE_STRING, nullable=True, dynamic=True, rle_dictionary=True),
+            ColumnDefinition("timestamp", TYPE_INT64),
+            ColumnDefinition("value", TYPE_STRING, rle_dictionary=True),
+        ],
+        sorting_columns=[
+            SortingColumn("labels", nulls_first=True),
+            SortingColumn("timestamp"),
+            SortingColumn("value"),
+        ],
+    )
+
+
 def SampleDefinitionWithFloat() -> Schema:
     """samples/example.go:215-226."""
     s = SampleDefinition()

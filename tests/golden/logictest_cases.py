@@ -264,6 +264,17 @@ for _ln, _sql, _e, _exp in (
     exec_(_filter, _ln, "select stacktrace, value where " + _sql,
           lambda q, _e=_e: q.Filter(_e).Project(Col("stacktrace"), Col("value")), _exp, kind="filter")
 
+# exec/filter/filter_contains: LIKE / NOT LIKE on a non-dynamic string column (schema=bytes)
+_fcont = case("logictest/testdata/exec/filter/filter_contains", schema="bytes")
+insert(_fcont, ["labels.label1", "labels.label2", "labels.label3", "labels.label4", "timestamp", "value"],
+       ["value1 value2 null null 1 foo", "value2 value2 value3 null 2 bar", "value3 value2 null value4 3 baz"])
+for _ln, _sql, _e, _exp in (
+        (10, "timestamp = 2", Col("timestamp").Eq(Literal(2)), ["value2 value2 value3 null 2 bar"]),
+        (15, "value LIKE 'a'", Col("value").Contains("a"), ["value2 value2 value3 null 2 bar", "value3 value2 null value4 3 baz"]),
+        (21, "value NOT LIKE 'a'", Col("value").ContainsNot("a"), ["value1 value2 null null 1 foo"])):
+    exec_(_fcont, _ln, "select labels, timestamp, value where " + _sql,
+          lambda q, _e=_e: q.Filter(_e).Project(DynCol("labels"), Col("timestamp"), Col("value")), _exp, kind="filter")
+
 # exec/filter/filter_projection
 _fproj = case("logictest/testdata/exec/filter/filter_projection")
 insert(_fproj, ["labels.label1", "labels.label2", "labels.label3", "labels.label4", "stacktrace", "timestamp", "value"],

@@ -8,7 +8,7 @@ import pyarrow as pa
 
 from frostdb_b200 import dynparquet as dp
 
-SCHEMAS = {"default": dp.SampleDefinitionWithFloat}
+SCHEMAS = {"default": dp.SampleDefinitionWithFloat, "bytes": dp.BytesDefinition}
 
 
 def format_rows(batches: List[pa.RecordBatch]) -> List[List[str]]:

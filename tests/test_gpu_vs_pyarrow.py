@@ -8,6 +8,7 @@ import pytest
 from frostdb_b200 import dynparquet as dp
 from frostdb_b200 import logicalplan as lp
 from frostdb_b200 import query
+from frostdb_b200 import _lib
 from tests.util import make_columns, rows_of
 
 pytestmark = pytest.mark.gpu
@@ -136,3 +137,55 @@ def test_int64_dictionary_pages_on_the_gpu(store):
         assert rows == exp
     finally:
         eng.drop_table(name)
+
+
+def test_converted_parts_give_the_reference_dictionaries_and_indices(store):
+    """pqarrow/arrow_test.go:17-145 (TestDifferentSchemasToArrow): five one-row buffers whose dynamic label columns
+    differ, converted one after the other.  The reference's record holds, per label column, ONE dictionary in
+    first-seen order and the indices [0 1 2 0 0] / [0 0 0 0 0] / [null 0 null null 0] / [null null 0 null null];
+    timestamps and values [1 2 3 2 3].  Here the parts are decoded on the GPU column by column (K1) against the
+    table's global dictionaries, which must come out exactly like that."""
+    from frostdb_b200 import dynparquet as dp
+    schema = dp.SampleDefinition()
+    db = store.DB(None, "golden_arrow")
+    name = "t_arrow_test"
+    if name in db.tables:
+        store.engine.drop_table(name)
+        db.tables.pop(name)
+    t = db.Table(name, schema)
+    samples = [({"label1": "value1", "label2": "value2"}, 1, 1),
+               ({"label1": "value2", "label2": "value2", "label3": "value3"}, 2, 2),
+               ({"label1": "value3", "label2": "value2", "label4": "value4"}, 3, 3),
+               ({"label1": "value1", "label2": "value2"}, 2, 2),
+               ({"label1": "value1", "label2": "value2", "label3": "value3"}, 3, 3)]
+    pids = []
+    for labels, ts, val in samples:
+        cols = {"example_type": [""], "stacktrace": ["s"], "timestamp": [ts], "value": [val]}
+        cols.update({"labels." + k: [v] for k, v in labels.items()})
+        pids.append(t.Insert(cols))
+    expect = {"labels.label1": ([b"value1", b"value2", b"value3"], [0, 1, 2, 0, 0]),
+              "labels.label2": ([b"value2"], [0, 0, 0, 0, 0]),
+              "labels.label3": ([b"value3"], [None, 0, None, None, 0]),
+              "labels.label4": ([b"value4"], [None, None, 0, None, None]),
+              "example_type": ([b""], [0, 0, 0, 0, 0])}
+    for col, (dictionary, indices) in expect.items():
+        assert store.engine.dict_export(name, col) == dictionary, col
+        got = []
+        for i, pid in enumerate(pids):
+            try:
+                a = store.engine.decode_column(name, pid, col)
+            except _lib.FrostGPUError:
+                a = None  # the part has no such column: NULL for its rows (arrow.go:485-597)
+            if a is None or a.null_count == len(a):
+                got.append(None)
+                continue
+            assert pa.types.is_dictionary(a.type)
+            value = a.dictionary_decode()[0].as_py()
+            value = value if isinstance(value, bytes) else value.encode()
+            got.append(dictionary.index(value))
+        assert got == indices, col
+    for col in ("timestamp", "value"):
+        got = [store.engine.decode_column(name, pid, col)[0].as_py() for pid in pids]
+        assert got == [1, 2, 3, 2, 3], col
+    store.engine.drop_table(name)
+    db.tables.pop(name)
