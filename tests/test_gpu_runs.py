@@ -357,3 +357,60 @@ def test_global_max_skips_row_groups_below_the_running_maximum(pair):
     assert st["row_groups_pruned"] >= 12 and st["row_groups"] <= 4   # only the first part's row groups raise the maximum
     run3(p, lambda q: q.Aggregate([lp.Max(lp.Col("value"))], []))
     run3(p, lambda q: q.Aggregate([lp.Min(lp.Col("timestamp"))], []))    # no push-down for Min
+
+
+def test_locally_dense_runs_leave_the_staged_directory_window(pair):
+    """k_runs_tma stages 128 directory entries per key and 4096-row tile; a tile that holds more runs than that walks
+    the rest of the directory in global memory (cursor_global).  Row groups whose runs average >= 32 rows qualify for
+    the kernel, so: a row group whose first rows change group every 2-3 rows while the rest is a few huge groups."""
+    n = 200_000
+    rng = np.random.default_rng(77)
+    dense = 9_000                                  # rows with short runs (they sort first: small ids)
+    a = np.empty(n, np.int32)
+    b = np.empty(n, np.int32)
+    a[:dense] = 0
+    # runs of 8-12 rows (a Parquet writer only run-length encodes 8 repeats and more; shorter ones would leave the
+    # column bit-packed and with it the sorted-run kernel): ~400 runs in the first 4096-row tile
+    reps = rng.integers(8, 13, 2_000)
+    b[:dense] = np.repeat(np.arange(2_000, dtype=np.int32), reps)[:dense]
+    a[dense:] = np.sort(rng.integers(1, 4, n - dense)).astype(np.int32)
+    b[dense:] = 2_000 + rng.integers(0, 3, n - dense).astype(np.int32)
+    cols = {
+        "example_type": (np.zeros(n, np.int32), ["cpu"]),
+        "stacktrace": (rng.integers(0, 5, n).astype(np.int32), [f"stack{i:02d}" for i in range(5)]),
+        "timestamp": np.arange(n, dtype=np.int64),
+        "value": rng.integers(-1000, 1000, n).astype(np.int64),
+        "labels.a": (a, label_values(4)),
+        "labels.b": (b, label_values(2_003)),
+    }
+    p = pair("runs_dense_window")
+    p.insert(cols, row_group_size=n, data_page_size=1 << 20)
+    ts, val = lp.Col("timestamp"), lp.Col("value")
+    run3(p, lambda q: q.Aggregate(AGGS, KEYS))
+    st = scan_stats(p, None, AGGS, KEYS)
+    assert st["row_groups_runs"] == st["row_groups"] == 1
+    run3(p, lambda q: q.Filter(val.Gt(lp.Literal(0))).Aggregate(AGGS, KEYS))                       # row filter: 2048-row tiles... one column
+    run3(p, lambda q: q.Filter(lp.And(ts.GtEq(lp.Literal(1_000)), val.LtEq(lp.Literal(500)))).Aggregate(AGGS, KEYS))  # two staged columns
+    run3(p, lambda q: q.Filter(lp.Col("labels.b").NotEq(lp.Literal("v000007"))).Aggregate(AGGS, [lp.Col("labels.a")]))  # leaf cursor beyond the window
+    run3(p, lambda q: q.Filter(ts.Lt(lp.Literal(3_000))).Aggregate([lp.Sum(val), lp.Min(val), lp.Max(val)], KEYS))        # general reducers
+
+
+@pytest.mark.parametrize("env", [{"FROSTGPU_RT_TILE": "1024", "FROSTGPU_RT_WARPS": "4", "FROSTGPU_RT_SPAN": "1"},
+                                 {"FROSTGPU_RT_TILE": "8192", "FROSTGPU_RT_STAGES": "2", "FROSTGPU_RT_SPAN": "3"},
+                                 {"FROSTGPU_RT_TILE": "2048", "FROSTGPU_RT_STAGES": "4", "FROSTGPU_RT_SPAN": "16"}])
+def test_tile_ring_and_chunk_shapes_give_the_same_records(pair, env):
+    p = pair("runs_shapes")
+    for i in range(3):
+        p.insert(sorted_columns(70_001, 900 + i, t0=i * 70_001, third=3), row_group_size=33_000)
+    os.environ.update(env)
+    try:
+        ts = lp.Col("timestamp")
+        got, exp = p.run(lambda q: q.Aggregate(AGGS, KEYS))
+        assert_same(got, exp, ())
+        got, exp = p.run(lambda q: q.Filter(lp.And(ts.GtEq(lp.Literal(50_000)), ts.Lt(lp.Literal(150_000)))).Aggregate(AGGS, KEYS + [lp.Col("labels.c")]))
+        assert_same(got, exp, ())
+        got, exp = p.run(lambda q: q.Filter(lp.Col("value").Lt(lp.Literal(0))).Aggregate([lp.Count(lp.Col("value"))], []))
+        assert_same(got, exp, ())
+    finally:
+        for k in env:
+            os.environ.pop(k)
