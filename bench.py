@@ -308,6 +308,15 @@ def extra_configs(eng, lib, rows_per_gpu, peak):
     out["cfg2_1M_rows_latency"] = run_case(eng, lib, "bench_cfg2", n2, AGG, f2, [lp.Col("labels.l00")], [lp.Sum(val)], peak, reps=20,
                                            note="launch / latency bound: exec_ms is the number")
     eng.drop_table("bench_cfg2")
+    # cfg 4's key space on one GPU: C0 = C1 = 1024 (~1M groups, ~4 rows per group and 4 Mi-row part), Sum + Count by two
+    # keys.  Runs this short are bit-packed: the tile-aggregate kernel with its table in global memory (L2).  (The full
+    # config — 1 B rows, 64 label columns over 8 GPUs — is not run here.)
+    n4 = min(rows_per_gpu, env_int("FROSTGPU_BENCH_CFG4_ROWS", 32 * 1024 * 1024))
+    for pth in bd.generate_parts(n4, N_LABELS, c0=1024, c1=1024):
+        eng.put_parquet("bench_cfg4", np.fromfile(pth, dtype=np.uint8))
+    out["cfg4_keyspace_1M_groups"] = run_case(eng, lib, "bench_cfg4", n4, AGG, None, K01, SC, peak, reps=3,
+                                              note="1025 x 1025 dense slots (25 MB table in L2), result of ~1M rows: exec_ms includes its export")
+    eng.drop_table("bench_cfg4")
     return out
 
 

@@ -6,13 +6,15 @@
 // and rank.  Peers map each other's mailboxes (CUDA IPC between processes, plain peer access inside one process).
 // One collective Execute enqueues, on the rank's one stream and behind its scan:
 //   k_comm_push    the rank's partial aggregate table goes into slot [my rank] of EVERY rank's mailbox with
-//                  16-byte stores over NVLink (no host, no NCCL launch on the critical path);
-//   k_comm_signal  one release-ordered system-scope store per peer: flag[my rank] = sequence number
-//                  (kernel boundary + st.release.sys: the pushed bytes are visible before the flag);
-//   k_comm_wait    ONE CTA spins with ld.acquire.sys until every rank's flag of this set carries the sequence
-//                  number (bounded by a timeout, reported through the query's counters);
-//   k_merge_dense  dense tables: every slot of the final table = fold of the n mailbox slots (no atomics); hash
-//                  tables go through k_merge per rank (kernels.cu).
+//                  16-byte stores over NVLink (no host, no NCCL launch on the critical path); the last CTA to finish
+//                  raises flag[my rank] = sequence number in every mailbox (system fence + st.release.sys: the
+//                  pushed bytes are visible before the flag);
+//   k_finalize_dense (kernels.cu, cached dense plans) waits in every CTA with ld.acquire.sys until every rank's flag of
+//                  this set carries the sequence number (bounded by a timeout, reported through the query's
+//                  counters), then compacts the FOLD of the n mailbox slots into the result columns: wait, merge and
+//                  finalize are one launch;
+//   k_comm_wait + k_merge_dense  the same in two launches for the plans without an execution cache (the final table is
+//                  written back; hash tables go through k_merge per rank, kernels.cu).
 // Double buffering by sequence parity is enough: a rank can only push sequence k + 2 after it merged k + 1, which
 // needed every peer's push k + 1, which every peer enqueued behind its own merge of k.
 #include <cuda_runtime.h>
@@ -46,14 +48,24 @@ __global__ void __launch_bounds__(256) k_comm_push(CommPush p) {
 #pragma unroll 4
     for (int r = 0; r < p.n; r++) reinterpret_cast<uint4*>(p.dst[r])[i] = v;
   }
-}
-
-__global__ void k_comm_signal(CommPush p) {
-  const int r = threadIdx.x;
-  if (r < p.n) {
-    p.flag[r][1] = p.bytes;  // what was pushed (checked by the receiver against its own table shape)
+  // the last CTA to finish raises the flags: one release-ordered system-scope store per peer, behind a system fence
+  // of every CTA's copies (no second launch between the copies and the signal)
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative over the CTA's stores (ordered before it by the barrier): one fence per CTA, not per thread
+    last = atomicAdd(p.done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
     __threadfence_system();
-    st_release_sys(p.flag[r], p.seq);
+    const int r = threadIdx.x;
+    if (r < p.n) {
+      p.flag[r][1] = p.bytes;  // what was pushed (checked by the receiver against its own table shape)
+      __threadfence_system();
+      st_release_sys(p.flag[r], p.seq);
+    }
+    if (threadIdx.x == 0) *p.done = 0;
   }
 }
 
@@ -102,9 +114,6 @@ cudaError_t launch_comm_push(const CommPush& p, int sm_count, cudaStream_t st) {
   if (blocks > size_t(sm_count) * 2) blocks = size_t(sm_count) * 2;
   if (blocks < 1) blocks = 1;
   k_comm_push<<<unsigned(blocks), 256, 0, st>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  k_comm_signal<<<1, 32, 0, st>>>(p);
   return cudaGetLastError();
 }
 

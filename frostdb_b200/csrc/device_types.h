@@ -341,6 +341,8 @@ struct FlatJob {
   uint32_t _pad;
 };
 
+constexpr int kMaxRanks = 16;  // GPUs of one node exchanging partial tables (comm.cu)
+
 // Dense table -> compacted result columns for the cached Execute path (k_finalize_dense): dictionary indices as
 // uint32 (0xffffffff = NULL), aggregates as raw 8 bytes, so that the host only copies columns.
 struct DenseOut {
@@ -349,13 +351,23 @@ struct DenseOut {
   const unsigned long long* t_rows;
   const long long* t_agg[kMaxAggs];  // null: Count (the row count)
   const unsigned long long* counters;  // the query's counters: [0..3] travel in the header
+  // Collective Execute (n_src > 0): the table to compact is the fold of n_src partial tables sitting in this rank's
+  // mailbox; the kernel first waits for every peer's flag (the reference's Synchronizer + final aggregate in one
+  // launch).  Layout of a partial table: [rows S x 8][stored aggregates S x 8 each, agg_pos says which].
+  int32_t n_src, _pad_src;
+  const uint8_t* src[kMaxRanks];
+  const unsigned long long* flags;      // this rank's flags of the current set: {seq, bytes} per rank
+  unsigned long long seq, bytes, timeout_ns;
+  unsigned long long* err;              // the query's counters[3]: 1 timeout, 2 table shapes differ
+  uint8_t agg_func[kMaxAggs], agg_is_float[kMaxAggs];
+  int8_t agg_pos[kMaxAggs];             // index among the stored aggregates, -1: Count (= rows)
   uint32_t* hdr;  // 256 bytes of device memory, zero between launches (see k_finalize_dense)
   uint8_t* out;   // device or page-locked host memory: [header 256 B: count u32 @0, counters u64 x4 @32, any_null u32 per key @64][n_keys x max_out u32 (8-byte aligned)][n_aggs x max_out i64]
 };
 
 // ---- partial-table exchange between the GPUs of one node (comm.cu) ---------------------------------------
-constexpr int kMaxRanks = 16;
 struct CommPush {
+  unsigned int* done;                  // CTAs that finished their copies (the last one raises the flags); left zero
   const uint8_t* src;                  // this rank's partial table
   unsigned long long bytes;            // multiple of 16
   unsigned long long seq;

@@ -1519,6 +1519,7 @@ int32_t comm_push(fgpu_ctx* ctx, const void* table, size_t table_bytes, uint64_t
   if (bytes > cm.slot_bytes) return fail(FGPU_ERR_UNSUPPORTED, "partial table (" + std::to_string(bytes) + " bytes) larger than the exchange slot");
   const uint64_t seq = ++cm.seq, set = seq & 1u;
   CommPush p{};
+  p.done = reinterpret_cast<unsigned int*>(cm.mailbox + 2048);  // (inside the zeroed header region, behind the flags)
   p.src = static_cast<const uint8_t*>(table);
   p.bytes = bytes;
   p.seq = seq;
@@ -1581,6 +1582,26 @@ int32_t cached_tail(fgpu_ctx* ctx, ExecCache& x) {
   return FGPU_OK;
 }
 
+// Collective tail of a cached Execute: ONE launch waits for the peers' flags, folds the n partial tables of this rank's
+// mailbox and compacts the result into the page-locked block (synchronize.go:16-53 + the final aggregate of
+// physicalplan.go:438-471).
+int32_t cached_tail_merged(fgpu_ctx* ctx, ExecCache& x, uint64_t seq, uint64_t bytes) {
+  Comm& cm = ctx->comm;
+  const uint64_t set = seq & 1u;
+  DenseOut& f = x.dout;
+  f.n_src = cm.n;
+  for (int r = 0; r < cm.n; r++) f.src[r] = cm.mailbox + cm.data_off(set, r);
+  f.flags = reinterpret_cast<const unsigned long long*>(cm.mailbox + cm.flag_off(set, 0));
+  f.seq = seq;
+  f.bytes = bytes;
+  const char* to = getenv("FROSTGPU_COMM_TIMEOUT_MS");
+  f.timeout_ns = uint64_t(to ? std::max(1, atoi(to)) : 10000) * 1000000ull;
+  f.err = x.qd.counters + 3;
+  const int32_t rc = cached_tail(ctx, x);
+  f.n_src = 0;
+  return rc;
+}
+
 // collective: 0 no exchange, 1 push + wait + merge in one go, 2 push only (fgpu_query_execute_collective_begin)
 int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective) {
   PhaseClock pc;
@@ -1609,10 +1630,16 @@ int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective
       res->pending_bytes = bytes;
       return FGPU_OK;
     }
-    rc = comm_wait_merge(ctx, x.qd, x.table.p, seq, bytes);
-    if (rc) return rc;
+    if (x.qd.table_mode == TM_DENSE) {
+      if (int32_t rcm = cached_tail_merged(ctx, x, seq, bytes)) return rcm;
+    } else {
+      rc = comm_wait_merge(ctx, x.qd, x.table.p, seq, bytes);
+      if (rc) return rc;
+      if (int32_t rct = cached_tail(ctx, x)) return rct;
+    }
+  } else if (int32_t rc = cached_tail(ctx, x)) {
+    return rc;
   }
-  if (int32_t rc = cached_tail(ctx, x)) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev[3], s));
   pc.mark("launch");
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -2385,6 +2412,14 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       f.t_rows = qd.t_rows;
       for (int a = 0; a < kMaxAggs; a++) f.t_agg[a] = qd.t_agg[a];
       f.counters = qd.counters;
+      {  // what the collective tail needs to fold partial tables itself (layout of table_layout())
+        int pos = 0;
+        for (int a = 0; a < qd.n_aggs; a++) {
+          f.agg_func[a] = qd.aggs[a].func;
+          f.agg_is_float[a] = qd.aggs[a].is_float;
+          f.agg_pos[a] = qd.aggs[a].func == FGPU_AGG_COUNT ? int8_t(-1) : int8_t(pos++);
+        }
+      }
       x.out_bytes = 256 + size_t(qd.n_keys) * ((size_t(f.max_out) * 4 + 7) & ~size_t(7)) + size_t(qd.n_aggs) * f.max_out * 8;
       CUDA_TRY(x.out.alloc(256, s));  // working header (k_finalize_dense leaves it zero)
       CUDA_TRY(cudaMemsetAsync(x.out.p, 0, 256, s));
@@ -2856,9 +2891,13 @@ int32_t collective_end(fgpu_ctx* ctx, fgpu_result* res) {
   res->pending = false;
   cudaStream_t s = ctx->stream;
   if (ExecCache* x = static_cast<ExecCache*>(res->pending_cached)) {
-    int32_t rc = comm_wait_merge(ctx, x->qd, x->table.p, res->pending_seq, res->pending_bytes);
-    if (rc) return rc;
-    if (int32_t rct = cached_tail(ctx, *x)) return rct;
+    if (x->qd.table_mode == TM_DENSE) {
+      if (int32_t rcm = cached_tail_merged(ctx, *x, res->pending_seq, res->pending_bytes)) return rcm;
+    } else {
+      int32_t rc = comm_wait_merge(ctx, x->qd, x->table.p, res->pending_seq, res->pending_bytes);
+      if (rc) return rc;
+      if (int32_t rct = cached_tail(ctx, *x)) return rct;
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
     const unsigned long long* counters = reinterpret_cast<const unsigned long long*>(x->pinned + 32);
     res->stats.d2h_bytes += x->out_bytes;

@@ -1970,8 +1970,45 @@ __global__ void __launch_bounds__(256) k_finalize_dense(DenseOut f) {
   const int lane = threadIdx.x & 31;
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   const size_t S = f.table_slots, S_pad = (S + 31) & ~size_t(31);
-  for (size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x; s < S_pad; s += stride) {
-    const unsigned long long rows = s < S ? f.t_rows[s] : 0ull;
+  bool failed = false;
+  if (f.n_src > 0) {
+    // collective Execute: every CTA waits for the peers' flags itself (they are written into this rank's own memory)
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    if (int(threadIdx.x) < f.n_src) {
+      const int r = threadIdx.x;
+      unsigned long long t0 = 0, seen;
+      unsigned spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f.flags + 2 * r) : "memory");
+        if (seen >= f.seq) break;
+        __nanosleep(100);
+        if ((++spins & 1023u) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > f.timeout_ns) { atomicExch(&bad, 1); break; }
+        }
+      }
+      if (seen >= f.seq && f.flags[2 * r + 1] != f.bytes) atomicExch(&bad, 2);
+    }
+    __syncthreads();
+    __threadfence();
+    if (bad) {
+      failed = true;
+      if (threadIdx.x == 0) atomicExch(f.err, (unsigned long long)bad);
+    }
+  }
+  for (size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x; s < S_pad && !failed; s += stride) {
+    unsigned long long rows = 0;
+    if (s < S) {
+      if (f.n_src > 0) {
+        for (int r = 0; r < f.n_src; r++) rows += reinterpret_cast<const unsigned long long*>(f.src[r])[s];
+      } else {
+        rows = f.t_rows[s];
+      }
+    }
     const unsigned m = __ballot_sync(FULL, rows != 0);
     if (m == 0) continue;
     uint32_t base = 0;
@@ -1986,12 +2023,30 @@ __global__ void __launch_bounds__(256) k_finalize_dense(DenseOut f) {
       if (!code) hdr[16 + k] = 1u;
     }
     long long* aggs = reinterpret_cast<long long*>(f.out + 256 + size_t(f.n_keys) * key_bytes);
-    for (uint32_t a = 0; a < f.n_aggs; a++) aggs[size_t(a) * f.max_out + o] = f.t_agg[a] ? f.t_agg[a][s] : (long long)rows;
+    for (uint32_t a = 0; a < f.n_aggs; a++) {
+      long long v;
+      if (f.n_src > 0) {
+        if (f.agg_pos[a] < 0) {
+          v = (long long)rows;
+        } else {
+          v = agg_identity(f.agg_func[a], f.agg_is_float[a] != 0);
+          for (int r = 0; r < f.n_src; r++) {
+            if (reinterpret_cast<const unsigned long long*>(f.src[r])[s] == 0) continue;  // an empty group holds the identity, not a value
+            v = agg_combine(f.agg_func[a], f.agg_is_float[a] != 0, v, reinterpret_cast<const long long*>(f.src[r] + S * 8 * size_t(1 + f.agg_pos[a]))[s]);
+          }
+        }
+      } else {
+        v = f.t_agg[a] ? f.t_agg[a][s] : (long long)rows;
+      }
+      aggs[size_t(a) * f.max_out + o] = v;
+    }
   }
   __shared__ bool last;
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(hdr + 62, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative over the CTA's stores (ordered before it by the barrier): one fence per CTA, not per thread
+    last = atomicAdd(hdr + 62, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (last && threadIdx.x < 64) {
     __threadfence();

@@ -485,7 +485,12 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
   // ================================ epilogue: CTA table -> global table ================================
   if (SMEM) {
     const uint32_t* t_cnt = reinterpret_cast<const uint32_t*>(table);
-    for (uint32_t s = tid; s < d.table_slots; s += blockDim.x) {
+    // every CTA starts its fold at another slot: the CTAs of a launch finish together, and 148 of them walking the
+    // same addresses in the same order serialise in the L2 atomic units
+    const uint32_t rot = uint32_t((uint64_t(blockIdx.x) * d.table_slots) / gridDim.x);
+    for (uint32_t i = tid; i < d.table_slots; i += blockDim.x) {
+      uint32_t s = i + rot;
+      if (s >= d.table_slots) s -= d.table_slots;
       unsigned long long c = 0;
       for (uint32_t r = 0; r < R; r++) c += t_cnt[(s << d.rep_log2) + r];
       if (c == 0) continue;
