@@ -259,17 +259,24 @@ struct RunsDesc {
 
 // ---- filter-only plans over PLAIN columns (k_take_*, take_rows.cu) -----------------------------------
 constexpr int kTakeLeaves = 2, kTakeOut = 4;
+constexpr int kTakePreds = 2;  // dictionary-column leaves (==, !=, contains, regex, == NULL) evaluated from flat codes
 
 struct TakeRg {
   uint32_t n_rows;
   uint32_t all_pass;  // 1: statistics decided every leaf (all rows pass): the span is a plain copy
   long long lo[kTakeLeaves], hi[kTakeLeaves];
-  const uint8_t* leaf_col[kTakeLeaves];  // PLAIN int64 values of every leaf's column
+  const uint8_t* leaf_col[kTakeLeaves];  // PLAIN int64 values of every leaf's column (null: decided for this row group)
   const uint8_t* out_col[kTakeOut];      // PLAIN 8-byte values of every projected column
+  // dictionary leaves: flat code array of the leaf's column (k_flatten; null: decided, passes) and the leaf's result
+  // byte per GLOBAL dictionary id
+  const uint8_t* pred_codes[kTakePreds];
+  const uint8_t* pred_lut[kTakePreds];
+  uint8_t pred_w[kTakePreds], pred_bias[kTakePreds], pred_null[kTakePreds];  // bits per code; 1: code = id, 0: code = id + 1 (0 = NULL); result for NULL rows
+  uint8_t _pad_p[8 - (3 * kTakePreds) % 8];
 };
 
 struct TakeDesc {
-  uint32_t n_rg, n_spans, span_blocks, nl, n_out, _pad;
+  uint32_t n_rg, n_spans, span_blocks, nl, n_out, np;
   const TakeRg* rgs;
   const uint32_t* rg_first_span;      // [n_rg + 1]
   unsigned long long* span_count;     // [n_spans + 1]: passing rows per span, then their exclusive prefix

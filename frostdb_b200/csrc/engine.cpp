@@ -2153,11 +2153,21 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
   TakeDesc td{};
   std::vector<TakeRg> take_rgs;
   std::vector<uint32_t> take_first_span;
-  bool take_q = q.kind == FGPU_PLAN_FILTER && qd.n_out >= 1 && qd.n_out <= kTakeOut && n_leaves <= kTakeLeaves &&
+  bool take_q = q.kind == FGPU_PLAN_FILTER && qd.n_out >= 1 && qd.n_out <= kTakeOut && n_leaves <= kTakeLeaves + kTakePreds &&
                 (qd.n_filter_prog == 0 || qd.filter_kind == FK_AND) && gi > 0 && !getenv("FROSTGPU_NO_TAKE");
+  // range leaves (PLAIN int64 columns) and dictionary leaves (flat codes + result byte per dictionary id) of the plan
+  int take_range[kTakeLeaves] = {0}, take_pred[kTakePreds] = {0}, n_tr = 0, n_tp = 0;
   for (int l = 0; l < n_leaves && take_q; l++) {
     const LeafDesc& ld = qd.leaves[l];
-    if (ld.slot == 0xff || ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || c.leaves[size_t(l)].null_literal) take_q = false;
+    if (ld.slot == 0xff) { take_q = false; break; }
+    if (qd.slot_type[ld.slot] == ST_DICT) {
+      if (n_tp >= kTakePreds || gi != n_rg) take_q = false;
+      else take_pred[n_tp++] = l;
+    } else if (ld.cmp_float || ld.neg || qd.slot_type[ld.slot] != ST_I64 || c.leaves[size_t(l)].null_literal || n_tr >= kTakeLeaves) {
+      take_q = false;
+    } else {
+      take_range[n_tr++] = l;
+    }
   }
   for (int o = 0; o < qd.n_out && take_q; o++)
     if (qd.slot_type[qd.out_slot[o]] == ST_DICT) take_q = false;
@@ -2171,21 +2181,35 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       if (m != LM_ALL) all = false;
     }
     tr.all_pass = all ? 1 : 0;
-    for (int l = 0; l < n_leaves && take_q; l++) {
+    for (int i = 0; i < n_tr && take_q; i++) {
+      const int l = take_range[i];
       const bool decided = lrt[size_t(g) * n_leaves + l].mode == LM_ALL;
-      tr.lo[l] = decided ? std::numeric_limits<int64_t>::min() : qd.leaves[l].lo_i;
-      tr.hi[l] = decided ? std::numeric_limits<int64_t>::max() : qd.leaves[l].hi_i;
+      tr.lo[i] = decided ? std::numeric_limits<int64_t>::min() : qd.leaves[l].lo_i;
+      tr.hi[i] = decided ? std::numeric_limits<int64_t>::max() : qd.leaves[l].hi_i;
+      tr.leaf_col[i] = nullptr;  // decided (or nothing to evaluate at all): the kernels skip the leaf
+      if (all || decided) continue;
       const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.leaves[l].slot];
-      if (all) continue;  // the leaf columns are not read at all
-      if (decided) {  // its column may not even be uploaded: any evaluated leaf's column stands in below
-        tr.leaf_col[l] = nullptr;
-        continue;
-      }
       if (d.kind != CK_PLAIN64 || d.has_nulls) take_q = false;
-      tr.leaf_col[l] = d.values;
+      tr.leaf_col[i] = d.values;
     }
-    for (int l = 0; l < n_leaves && take_q && !all; l++)
-      if (!tr.leaf_col[l]) tr.leaf_col[l] = tr.leaf_col[l == 0 ? 1 : 0];
+    for (int i = 0; i < n_tp && take_q; i++) {
+      const int l = take_pred[i];
+      const LeafRt& rt = lrt[size_t(g) * n_leaves + l];
+      tr.pred_codes[i] = nullptr;
+      if (all || rt.mode == LM_ALL) continue;
+      const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.leaves[l].slot];
+      if (d.kind != CK_DICT_STR) { take_q = false; break; }
+      const std::string& name = c.slot_names[size_t(qd.leaves[l].slot)];
+      int32_t frc = ensure_flat(ctx, c.rgs[size_t(g)].part, name);  // (rows plans: every row group is a general one, g == its index in c.rgs)
+      if (frc) return frc;
+      const ChunkHost& ch = c.rgs[size_t(g)].rg->cols.at(name);
+      if (!ch.flat) { take_q = false; break; }
+      tr.pred_codes[i] = ch.flat;
+      tr.pred_w[i] = ch.flat_w;
+      tr.pred_bias[i] = ch.flat_bias;
+      tr.pred_null[i] = rt.null_result;
+      tr.pred_lut[i] = reinterpret_cast<const uint8_t*>(uintptr_t(c.leaves[size_t(l)].lut_off) + 1);  // offset + 1, rebased below
+    }
     for (int o = 0; o < qd.n_out && take_q; o++) {
       const ChunkDesc& d = chunks[size_t(g) * n_slots + qd.out_slot[o]];
       if (d.kind != CK_PLAIN64 || d.has_nulls) take_q = false;
@@ -2208,7 +2232,8 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     take_first_span.push_back(spans);
     td.n_spans = spans;
     td.n_rg = uint32_t(take_rgs.size());
-    td.nl = uint32_t(n_leaves);
+    td.nl = uint32_t(n_tr);
+    td.np = uint32_t(n_tp);
     td.n_out = uint32_t(qd.n_out);
   }
 
@@ -2306,6 +2331,9 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
     std::memcpy(hostaux.data() + TA.o_tile, TA.first_tile.data(), TA.first_tile.size() * 4);
   }
   if (take_q) {
+    for (TakeRg& r : take_rgs)
+      for (int i = 0; i < kTakePreds; i++)
+        if (r.pred_lut[i]) r.pred_lut[i] = aux + o_lut + (size_t(uintptr_t(r.pred_lut[i])) - 1);
     std::memcpy(hostaux.data() + o_take_rg, take_rgs.data(), take_rgs.size() * sizeof(TakeRg));
     std::memcpy(hostaux.data() + o_take_span, take_first_span.data(), take_first_span.size() * 4);
   }

@@ -2,9 +2,11 @@
 //
 // Takes over PredicateFilter.Callback's filter() (physicalplan/filter.go:276-323: bitmap -> index ranges ->
 // per-column Slice + Concatenate, i.e. an ORDER-PRESERVING compaction of every projected column) for the
-// plan shape of BASELINE config 5: a conjunction of <= 2 int64 range leaves on PLAIN non-null columns (any
-// of them possibly decided by the chunk statistics) and <= 4 projected PLAIN non-null int64/double columns.
-// Everything else (dictionary columns, NULLs, OR / regex leaves) stays with k_rows in kernels.cu.
+// plan shape of BASELINE config 5: a conjunction of <= 2 int64 range leaves on PLAIN non-null columns and <= 2
+// dictionary-column leaves (==, !=, contains, regex, == NULL: one result byte per dictionary id, the column read as a
+// flat code array, k_flatten) — any of them possibly decided by the chunk statistics — and <= 4 projected PLAIN
+// non-null int64/double columns.  Everything else (projected dictionary columns, NULL values, OR / nested leaves)
+// stays with k_rows in kernels.cu.
 //
 // Two passes over spans (the contiguous piece of a row group a warp takes per turn, in scan order):
 //   k_take_count  reads only the leaf columns and leaves the number of passing rows of every span;
@@ -47,16 +49,35 @@ __device__ __forceinline__ SpanPos locate(const TakeDesc& d, uint32_t span, uint
   return p;
 }
 
+struct Preds {  // the dictionary leaves of one row group
+  const uint8_t* codes[kTakePreds];
+  const uint8_t* lut[kTakePreds];
+  uint32_t w[kTakePreds], bias[kTakePreds], pnull[kTakePreds];
+};
+__device__ __forceinline__ Preds load_preds(const TakeRg* R) {
+  Preds P;
+#pragma unroll
+  for (int p = 0; p < kTakePreds; p++) {
+    P.codes[p] = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->pred_codes[p])));
+    P.lut[p] = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&R->pred_lut[p])));
+    P.w[p] = __ldg(&R->pred_w[p]);
+    P.bias[p] = __ldg(&R->pred_bias[p]);
+    P.pnull[p] = __ldg(&R->pred_null[p]);
+  }
+  return P;
+}
+
 // pass mask of the 8 steps of one block for this lane (bit j: row r0 + 32 j + lane passes every leaf)
-template <int NL>
+template <int NL, bool HP>
 __device__ __forceinline__ uint32_t block_mask(const long long* (&col)[NL > 0 ? NL : 1], const long long (&lo)[NL > 0 ? NL : 1],
-                                               const long long (&hi)[NL > 0 ? NL : 1], uint32_t r0, uint32_t row_end, int lane) {
+                                               const long long (&hi)[NL > 0 ? NL : 1], const Preds& P, uint32_t r0, uint32_t row_end, int lane) {
   uint32_t m = 0;
 #pragma unroll
   for (int j = 0; j < 8; j++)
     if (r0 + uint32_t(j) * 32u + uint32_t(lane) < row_end) m |= 1u << j;
 #pragma unroll
   for (int l = 0; l < NL; l++) {
+    if (col[l] == nullptr) continue;  // decided by the chunk statistics
     long long x[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) x[j] = ((m >> j) & 1u) ? __ldg(col[l] + r0 + uint32_t(j) * 32u + uint32_t(lane)) : 0;
@@ -64,10 +85,32 @@ __device__ __forceinline__ uint32_t block_mask(const long long* (&col)[NL > 0 ? 
     for (int j = 0; j < 8; j++)
       if (!(x[j] >= lo[l] && x[j] <= hi[l])) m &= ~(1u << j);
   }
+  if constexpr (HP) {
+#pragma unroll
+    for (int p = 0; p < kTakePreds; p++) {
+      if (P.codes[p] == nullptr) continue;
+      uint32_t code[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const size_t r = size_t(r0) + uint32_t(j) * 32u + uint32_t(lane);
+        code[j] = 0;
+        if ((m >> j) & 1u)
+          code[j] = P.w[p] == 8 ? uint32_t(__ldg(P.codes[p] + r))
+                                : (P.w[p] == 16 ? uint32_t(__ldg(reinterpret_cast<const uint16_t*>(P.codes[p]) + r)) : __ldg(reinterpret_cast<const uint32_t*>(P.codes[p]) + r));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (!((m >> j) & 1u)) continue;
+        const bool isnull = P.bias[p] == 0u && code[j] == 0u;
+        const bool pass = isnull ? (P.pnull[p] != 0u) : (__ldg(P.lut[p] + (code[j] + P.bias[p] - 1u)) != 0);
+        if (!pass) m &= ~(1u << j);
+      }
+    }
+  }
   return m;
 }
 
-template <int NL>
+template <int NL, bool HP>
 __global__ void __launch_bounds__(kTakeThreads) k_take_count(const __grid_constant__ TakeDesc d) {
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * kTakeWarps + (threadIdx.x >> 5), GW = gridDim.x * kTakeWarps;
@@ -75,7 +118,7 @@ __global__ void __launch_bounds__(kTakeThreads) k_take_count(const __grid_consta
   for (uint32_t span = gw; span < d.n_spans; span += GW) {
     const SpanPos p = locate(d, span, rg);
     uint32_t cnt = 0;
-    if (NL == 0 || __ldg(&p.R->all_pass)) {
+    if ((NL == 0 && !HP) || __ldg(&p.R->all_pass)) {
       if (lane == 0) d.span_count[span] = p.row_end - p.row0;
       continue;
     }
@@ -87,7 +130,9 @@ __global__ void __launch_bounds__(kTakeThreads) k_take_count(const __grid_consta
       lo[l] = __ldg(&p.R->lo[l]);
       hi[l] = __ldg(&p.R->hi[l]);
     }
-    for (uint32_t r0 = p.row0; r0 < p.row_end; r0 += kBlockRows) cnt += __popc(block_mask<NL>(col, lo, hi, r0, p.row_end, lane));
+    Preds P{};
+    if (HP) P = load_preds(p.R);
+    for (uint32_t r0 = p.row0; r0 < p.row_end; r0 += kBlockRows) cnt += __popc(block_mask<NL, HP>(col, lo, hi, P, r0, p.row_end, lane));
     cnt = __reduce_add_sync(FULL, cnt);
     if (lane == 0) d.span_count[span] = cnt;
   }
@@ -133,7 +178,7 @@ __global__ void __launch_bounds__(1024) k_take_scan(unsigned long long* counts, 
   }
 }
 
-template <int NL, int NO>
+template <int NL, int NO, bool HP>
 __global__ void __launch_bounds__(kTakeThreads) k_take_write(const __grid_constant__ TakeDesc d) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
@@ -146,7 +191,7 @@ __global__ void __launch_bounds__(kTakeThreads) k_take_write(const __grid_consta
     const long long* out_col[NO];
 #pragma unroll
     for (int o = 0; o < NO; o++) out_col[o] = reinterpret_cast<const long long*>(__ldg(reinterpret_cast<const unsigned long long*>(&p.R->out_col[o])));
-    if (NL == 0 || __ldg(&p.R->all_pass)) {  // plain copy of the span
+    if ((NL == 0 && !HP) || __ldg(&p.R->all_pass)) {  // plain copy of the span
       for (uint32_t r = p.row0 + uint32_t(lane); r < p.row_end; r += 32u) {
 #pragma unroll
         for (int o = 0; o < NO; o++) d.out_data[o][base + (r - p.row0)] = __ldg(out_col[o] + r);
@@ -161,8 +206,10 @@ __global__ void __launch_bounds__(kTakeThreads) k_take_write(const __grid_consta
       lo[l] = __ldg(&p.R->lo[l]);
       hi[l] = __ldg(&p.R->hi[l]);
     }
+    Preds P{};
+    if (HP) P = load_preds(p.R);
     for (uint32_t r0 = p.row0; r0 < p.row_end; r0 += kBlockRows) {
-      const uint32_t m = block_mask<NL>(col, lo, hi, r0, p.row_end, lane);
+      const uint32_t m = block_mask<NL, HP>(col, lo, hi, P, r0, p.row_end, lane);
       if (__ballot_sync(FULL, m != 0) == 0) continue;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -196,13 +243,32 @@ cudaError_t run(K kern, const TakeDesc& d, int sm_count, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int NL>
+template <int NL, bool HP>
 cudaError_t write_no(const TakeDesc& d, int sm_count, cudaStream_t st) {
   switch (d.n_out) {
-    case 1: return run(k_take_write<NL, 1>, d, sm_count, st);
-    case 2: return run(k_take_write<NL, 2>, d, sm_count, st);
-    case 3: return run(k_take_write<NL, 3>, d, sm_count, st);
-    default: return run(k_take_write<NL, 4>, d, sm_count, st);
+    case 1: return run(k_take_write<NL, 1, HP>, d, sm_count, st);
+    case 2: return run(k_take_write<NL, 2, HP>, d, sm_count, st);
+    case 3: return run(k_take_write<NL, 3, HP>, d, sm_count, st);
+    default: return run(k_take_write<NL, 4, HP>, d, sm_count, st);
+  }
+}
+
+template <bool HP>
+cudaError_t take_hp(const TakeDesc& d, int sm_count, cudaStream_t st) {
+  cudaError_t e;
+  switch (d.nl) {
+    case 0: e = run(k_take_count<0, HP>, d, sm_count, st); break;
+    case 1: e = run(k_take_count<1, HP>, d, sm_count, st); break;
+    default: e = run(k_take_count<2, HP>, d, sm_count, st); break;
+  }
+  if (e != cudaSuccess) return e;
+  k_take_scan<<<1, 1024, 0, st>>>(d.span_count, d.n_spans, d.total);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  switch (d.nl) {
+    case 0: return write_no<0, HP>(d, sm_count, st);
+    case 1: return write_no<1, HP>(d, sm_count, st);
+    default: return write_no<2, HP>(d, sm_count, st);
   }
 }
 
@@ -212,21 +278,7 @@ int take_resident_warps(int sm_count) { return sm_count * 8 * kTakeWarps; }  // 
 
 cudaError_t launch_take(const TakeDesc& d, int sm_count, cudaStream_t st) {
   if (d.n_spans == 0) return cudaSuccess;
-  cudaError_t e;
-  switch (d.nl) {
-    case 0: e = run(k_take_count<0>, d, sm_count, st); break;
-    case 1: e = run(k_take_count<1>, d, sm_count, st); break;
-    default: e = run(k_take_count<2>, d, sm_count, st); break;
-  }
-  if (e != cudaSuccess) return e;
-  k_take_scan<<<1, 1024, 0, st>>>(d.span_count, d.n_spans, d.total);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  switch (d.nl) {
-    case 0: return write_no<0>(d, sm_count, st);
-    case 1: return write_no<1>(d, sm_count, st);
-    default: return write_no<2>(d, sm_count, st);
-  }
+  return d.np ? take_hp<true>(d, sm_count, st) : take_hp<false>(d, sm_count, st);
 }
 
 }  // namespace fgpu

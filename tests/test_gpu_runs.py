@@ -414,3 +414,41 @@ def test_tile_ring_and_chunk_shapes_give_the_same_records(pair, env):
     finally:
         for k in env:
             os.environ.pop(k)
+
+
+def test_filter_only_plans_with_dictionary_leaves_take_path(pair):
+    """cfg 5 with a dict-string predicate: ==, !=, contains, regex and == NULL leaves on dictionary columns (sorted
+    and unsorted parts, NULLs in the column, a column missing from one part) — the ordered take kernels over flat
+    codes against the oracle and against k_rows (FROSTGPU_NO_TAKE), without sorting the rows."""
+    from tests.util import make_columns
+    p = pair("take_dict")
+    n = 30_011
+    p.insert(sorted_columns(n, 810, t0=0, third=5), row_group_size=11_000)
+    p.insert(make_columns(n, 811, {"a": (5, 0.0), "b": (23, 0.2), "c": (5, 0.5)}, t0=n), row_group_size=9_000, sort=False)
+    p.insert(make_columns(n, 812, {"a": (5, 0.1), "b": (23, 0.0)}, t0=2 * n), row_group_size=30_011)   # no labels.c here
+    ts, v = lp.Col("timestamp"), lp.Col("value")
+    a, b, c = lp.Col("labels.a"), lp.Col("labels.b"), lp.Col("labels.c")
+    filters = [
+        a.Eq(lp.Literal("v000002")), b.NotEq(lp.Literal("v000007")), c.Eq(lp.Literal(None)), c.NotEq(lp.Literal(None)),
+        b.Contains("0001"), b.RegexMatch("v00000[1-3]"), a.Eq(lp.Literal("nope")),
+        lp.And(a.Eq(lp.Literal("v000001")), ts.Lt(lp.Literal(2 * n + 100))),
+        lp.And(lp.And(b.NotEq(lp.Literal("v000003")), c.Eq(lp.Literal("v000004"))), v.Gt(lp.Literal(100))),
+        lp.And(c.Eq(lp.Literal("")), ts.GtEq(lp.Literal(n))),   # missing column == "": every row of the part without it
+    ]
+    for f in filters:
+        for proj in ([ts, v], [v]):
+            cols = [e.Name() for e in proj]
+            got, exp = p.run(lambda q: q.Filter(f).Project(*proj))
+            os.environ["FROSTGPU_NO_TAKE"] = "1"
+            try:
+                got2, _ = p.run(lambda q: q.Filter(f).Project(*proj))
+            finally:
+                os.environ.pop("FROSTGPU_NO_TAKE")
+
+            def flat(batches):
+                out = []
+                for bt in batches:
+                    if bt.num_rows:
+                        out.extend(zip(*[bt.column(bt.schema.get_field_index(cn)).to_pylist() for cn in cols]))
+                return out
+            assert flat(got) == flat(exp) == flat(got2), f"{f.Name()} -> {cols}"
