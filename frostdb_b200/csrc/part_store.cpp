@@ -391,8 +391,30 @@ void build_chunk(const ChunkMeta& cm, const SchemaLeaf& leaf, uint32_t n_rows, i
     if (w.device_seeds) out->dev_row_seeds = seed_job(out->off_row_runs, out->desc.n_row_runs, n_rows, true, /*use_val0=*/false);
     else out->off_row_seeds = w.section(seeds.data(), seeds.size() * sizeof(Seed));
   }
-  if (out->desc.kind == CK_DICT_STR) out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
-  if (out->desc.kind == CK_DICT64) out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
+  // Bit-packed indices are not range-checked row by row (neither here nor in the kernels): the tables they index are
+  // padded to 2^w entries instead (w = widest bit-packed run of the chunk), so that any w-bit pattern of a corrupt
+  // chunk reads a valid entry (dictionary entry 0) instead of memory behind the table.
+  uint32_t max_w = 0;
+  for (const HostRun& r : vruns)
+    if (r.meta & 1u) max_w = std::max<uint32_t>(max_w, (r.meta >> 8) & 0xffu);
+  const size_t padded = max_w > 0 && max_w <= 24 ? (size_t(1) << max_w) : 0;
+  if (max_w > 24 && out->desc.kind != CK_PLAIN64 && (uint64_t(1) << std::min<uint32_t>(max_w, 40)) > uint64_t(dict_size) * 2 + 2) {
+    out->error = "bit-packed dictionary indices wider than the dictionary";
+    return;
+  }
+  if (out->desc.kind == CK_DICT_STR) {
+    if (padded > out->lut_host.size()) {
+      std::vector<uint32_t> lut = out->lut_host;
+      lut.resize(padded, lut.empty() ? 0u : lut[0]);
+      out->off_lut = w.section(lut.data(), lut.size() * 4);
+    } else {
+      out->off_lut = w.section(out->lut_host.data(), out->lut_host.size() * 4);
+    }
+  }
+  if (out->desc.kind == CK_DICT64) {
+    if (padded > dict64.size()) dict64.resize(padded, dict64.empty() ? 0 : dict64[0]);
+    out->off_dict64 = w.section(dict64.data(), dict64.size() * 8);
+  }
   (void)plain_bytes;
   const size_t payload = vstream.size() + (has_nulls ? defstream.size() : 0);
   out->meta_bytes = (w.buf.size() - before) - std::min(w.buf.size() - before, payload);
