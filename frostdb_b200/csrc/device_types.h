@@ -337,9 +337,6 @@ struct TileAggDesc {
   unsigned long long* t_rows;
   long long* t_agg[kTaAggs];
   unsigned long long* counters;
-  // two-level fold of the CTA-private tables: every CTA stores its table into scratch[CTA] (coalesced 16-byte stores)
-  // and k_tile_fold adds the CTAs' tables up before touching the global table (null: every CTA folds with atomics)
-  uint8_t* scratch;
 };
 
 // One column chunk to turn into a flat code array (k_flatten).

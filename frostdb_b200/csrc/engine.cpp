@@ -222,20 +222,6 @@ struct fgpu_ctx {
   void pinned_give(uint8_t* p, size_t cap) { pinned->give(p, cap); }
   // page-locked scratch for the per-query descriptor upload and the counters read-back (guarded by mu)
   uint8_t* scratch = nullptr;
-  // scratch area of the tile-aggregate kernel's two-level fold (one table slice per CTA); every Execute runs on the
-  // context's one stream, so one buffer serves them all
-  DevBuf ta_scratch;
-  cudaError_t ta_scratch_for(TileAggDesc& td) {
-    const size_t need = getenv("FROSTGPU_TA_ATOMIC_FOLD") ? 0 : tile_agg_scratch_bytes(td, sm_count);
-    td.scratch = nullptr;
-    if (need == 0) return cudaSuccess;
-    if (ta_scratch.n < need) {
-      cudaError_t e = ta_scratch.alloc(need, stream);
-      if (e != cudaSuccess) return e;
-    }
-    td.scratch = static_cast<uint8_t*>(ta_scratch.p);
-    return cudaSuccess;
-  }
   size_t scratch_bytes = 0;
   cudaError_t ensure_scratch(size_t bytes) {
     if (bytes <= scratch_bytes) return cudaSuccess;
@@ -258,7 +244,7 @@ const std::string& env_switches() {
                                        "FROSTGPU_NO_TAKE", "FROSTGPU_TA_TILE", "FROSTGPU_TA_STAGES", "FROSTGPU_TA_GLOBAL", "FROSTGPU_TA_CHUNK", "FROSTGPU_TA_CARRY",
                                        "FROSTGPU_VL", "FROSTGPU_RING", "FROSTGPU_RUNS_BR", "FROSTGPU_RUNS_RING", "FROSTGPU_RUNS_SPAN",
                                        "FROSTGPU_RUNS_V1", "FROSTGPU_RT_TILE", "FROSTGPU_RT_STAGES", "FROSTGPU_RT_SPAN", "FROSTGPU_RT_WARPS",
-                                       "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE", "FROSTGPU_PROFILE", "FROSTGPU_TA_ATOMIC_FOLD"};
+                                       "FROSTGPU_NO_EXEC_CACHE", "FROSTGPU_NO_PLAN_CACHE", "FROSTGPU_PROFILE"};
   static std::mutex mu;
   static std::string cached;
   static uint64_t cached_sig = 0;
@@ -1630,10 +1616,7 @@ int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective
     if (x.runs_v1) CUDA_TRY(launch_runs(x.rd, x.runs_nl, x.runs_nk, x.runs_na, ctx->sm_count, s));
     else CUDA_TRY(launch_runs_tma(x.rd, x.runs_nl, x.runs_nk, x.runs_na, ctx->sm_count, s));
   }
-  if (x.has_ta) {
-    CUDA_TRY(ctx->ta_scratch_for(x.td));
-    CUDA_TRY(launch_tile_agg(x.td, ctx->sm_count, s));
-  }
+  if (x.has_ta) CUDA_TRY(launch_tile_agg(x.td, ctx->sm_count, s));
   CUDA_TRY(launch_scan(x.qdesc_dev, x.qd, ctx->sm_count, s));
   CUDA_TRY(cudaEventRecord(ctx->ev[2], s));
   if (collective) {
@@ -2420,7 +2403,6 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       td.t_rows = qd.t_rows;
       for (uint32_t a = 0; a < td.na; a++) td.t_agg[a] = qd.t_agg[TA.agg_index[a]];
       td.counters = qd.counters;
-      CUDA_TRY(ctx->ta_scratch_for(td));
       CUDA_TRY(launch_tile_agg(td, ctx->sm_count, s));
       st.kernel_launches++;
       st.row_groups_tiles += uint32_t(TA.rgs.size());

@@ -34,7 +34,6 @@ int take_resident_warps(int sm_count);
 // tile aggregate (tile_agg.cu): TMA-staged column tiles, CTA-private shared-memory table
 cudaError_t launch_tile_agg(const TileAggDesc& d, int sm_count, cudaStream_t st);
 size_t tile_agg_smem_bytes(const TileAggDesc& d);
-size_t tile_agg_scratch_bytes(const TileAggDesc& d, int sm_count);  // 0: the CTAs fold their tables with atomics
 // dictionary column chunks -> flat code arrays (kernels.cu)
 cudaError_t launch_flatten(const FlatJob* d_jobs, uint32_t n_jobs, uint32_t total_blocks, int sm_count, cudaStream_t st);
 // partial-table exchange over peer-mapped mailboxes (comm.cu)

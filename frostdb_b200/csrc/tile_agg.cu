@@ -483,12 +483,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
   }
   __syncthreads();
   // ================================ epilogue: CTA table -> global table ================================
-  if (SMEM && d.scratch != nullptr) {
-    // the CTA's table goes to its slice of the scratch area as it is; k_tile_fold adds the slices up
-    const uint4* src = reinterpret_cast<const uint4*>(table);
-    uint4* dst = reinterpret_cast<uint4*>(d.scratch + size_t(blockIdx.x) * d.table_bytes);
-    for (uint32_t i = tid; i < d.table_bytes / 16u; i += blockDim.x) dst[i] = src[i];
-  } else if (SMEM) {
+  if (SMEM) {
     const uint32_t* t_cnt = reinterpret_cast<const uint32_t*>(table);
     // every CTA starts its fold at another slot: the CTAs of a launch finish together, and 148 of them walking the
     // same addresses in the same order serialise in the L2 atomic units
@@ -516,54 +511,6 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tile_agg(const __grid_constan
         }
       }
     }
-  }
-}
-
-// Second level of the fold: slot s of the global table += sum over the CTAs' private tables (scratch slices).  The
-// CTAs are split over kFoldParts thread groups so that the reads spread over the whole chip; one atomic per slot,
-// aggregate and group instead of one per slot, aggregate and CTA.
-constexpr uint32_t kFoldParts = 8;
-__global__ void __launch_bounds__(256) k_tile_fold(const __grid_constant__ TileAggDesc d, uint32_t n_ctas) {
-  const uint32_t R = 1u << d.rep_log2;
-  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const uint32_t s = uint32_t(idx / kFoldParts), part = uint32_t(idx % kFoldParts);
-  if (s >= d.table_slots) return;
-  unsigned long long c = 0;
-  unsigned long long v32[kTaAggs];
-  long long v64[kTaAggs];
-#pragma unroll
-  for (int a = 0; a < kTaAggs; a++) {
-    v32[a] = 0;
-    v64[a] = uint32_t(a) < d.na && d.cell64[a] ? agg_identity(uint8_t(d.agg_func[a] & 0xffu), (d.agg_func[a] >> 8) != 0) : 0;
-  }
-  for (uint32_t b = part; b < n_ctas; b += kFoldParts) {
-    const uint8_t* t = d.scratch + size_t(b) * d.table_bytes;
-    const uint32_t* t_cnt = reinterpret_cast<const uint32_t*>(t);
-    unsigned long long cb = 0;
-    for (uint32_t r = 0; r < R; r++) cb += t_cnt[(s << d.rep_log2) + r];
-    if (cb == 0) continue;
-    c += cb;
-#pragma unroll
-    for (int a = 0; a < kTaAggs; a++) {
-      if (uint32_t(a) >= d.na) continue;
-      if (d.cell64[a]) {
-        const uint8_t func = uint8_t(d.agg_func[a] & 0xffu);
-        const bool isf = (d.agg_func[a] >> 8) != 0;
-        const long long* cells = reinterpret_cast<const long long*>(t + d.cell_off[a]) + (s << d.rep_log2);
-        for (uint32_t r = 0; r < R; r++) v64[a] = agg_combine(func, isf, v64[a], cells[r]);
-      } else {
-        const uint32_t* cells = reinterpret_cast<const uint32_t*>(t + d.cell_off[a]) + (s << d.rep_log2);
-        for (uint32_t r = 0; r < R; r++) v32[a] += cells[r];
-      }
-    }
-  }
-  if (c == 0) return;
-  atomicAdd(d.t_rows + s, c);
-#pragma unroll
-  for (int a = 0; a < kTaAggs; a++) {
-    if (uint32_t(a) >= d.na) continue;
-    if (d.cell64[a]) apply_agg(uint8_t(d.agg_func[a] & 0xffu), (d.agg_func[a] >> 8) != 0, d.t_agg[a] + s, v64[a]);
-    else if (v32[a]) atomicAdd(reinterpret_cast<unsigned long long*>(d.t_agg[a] + s), v32[a]);
   }
 }
 
@@ -624,17 +571,7 @@ cudaError_t launch_tile_agg(const TileAggDesc& d, int sm_count, cudaStream_t st)
   const uint32_t need = (d.n_tiles + d.chunk_tiles - 1) / d.chunk_tiles;
   if (grid > need) grid = need;
   kern<<<grid, kTaThreads, smem, st>>>(d);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess || !d.smem_table || d.scratch == nullptr) return e;
-  const size_t threads = size_t(d.table_slots) * kFoldParts;
-  k_tile_fold<<<unsigned((threads + 255) / 256), 256, 0, st>>>(d, grid);
   return cudaGetLastError();
-}
-
-size_t tile_agg_scratch_bytes(const TileAggDesc& d, int sm_count) {
-  // worth it when the tables are large: small ones fold with a handful of atomics per CTA anyway
-  if (!d.smem_table || d.table_bytes % 16u != 0 || d.table_slots < 2048u) return 0;
-  return size_t(sm_count) * d.table_bytes;
 }
 
 }  // namespace fgpu
