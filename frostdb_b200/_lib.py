@@ -139,6 +139,11 @@ _SIGNATURES = {
     "fgpu_rowgroup_leaf_mode": ([C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int32)], C.c_int32),
     "fgpu_part_decode_column": ([C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_void_p], C.c_int32),
     "fgpu_parquet_describe": ([C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int32),
+    "fgpu_xxhash64": ([C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int32),
+    "fgpu_bloom_check": ([C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)], C.c_int32),
+    "fgpu_bloom_insert": ([C.c_void_p, C.c_uint64, C.c_uint64], C.c_int32),
+    "fgpu_parquet_rowgroup_may_match_eq": ([C.c_char_p, C.c_uint64, C.c_int32, C.c_char_p, C.c_int32, C.c_int64, C.c_double, C.c_char_p, C.c_uint64,
+                                            C.POINTER(C.c_int32)], C.c_int32),
 }
 
 _lib = None

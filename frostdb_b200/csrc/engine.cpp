@@ -818,6 +818,28 @@ int stat_compare(const ChunkHost& ch, bool use_max, const ExprNode& lit, bool* o
   return 0;
 }
 
+// Split-block bloom filter of the chunk against a non-null literal (expr/binaryscalarexpr.go:104-118: parquet-go hashes
+// the PLAIN encoding of the value with XXH64): false = the value is definitely not in the chunk.  Chunks without a
+// filter, and literals whose type does not match the column's, answer true.
+bool bloom_may_contain(const ChunkHost& ch, const ExprNode& lit) {
+  if (ch.bloom.empty()) return true;
+  uint64_t h;
+  if (ch.phys == PT_INT64 && lit.lit_type == FGPU_SCALAR_INT64) {
+    uint8_t b[8];
+    std::memcpy(b, &lit.lit_i, 8);
+    h = xxhash64(b, 8, 0);
+  } else if (ch.phys == PT_DOUBLE && lit.lit_type == FGPU_SCALAR_FLOAT64) {
+    uint8_t b[8];
+    std::memcpy(b, &lit.lit_f, 8);
+    h = xxhash64(b, 8, 0);
+  } else if (ch.phys == PT_BYTE_ARRAY && lit.lit_type == FGPU_SCALAR_STRING) {
+    h = xxhash64(reinterpret_cast<const uint8_t*>(lit.lit_bytes.data()), lit.lit_bytes.size(), 0);
+  } else {
+    return true;
+  }
+  return sbbf_check(ch.bloom.data(), uint32_t(ch.bloom.size()), h);
+}
+
 bool rg_may_match(const QueryPlan& q, int node, const RowGroupHost& rg) {
   if (node < 0) return true;
   const ExprNode& e = q.exprs[size_t(node)];
@@ -847,6 +869,9 @@ bool rg_may_match(const QueryPlan& q, int node, const RowGroupHost& rg) {
   if (e.op == FGPU_OP_EQ) {
     if (lit.lit_type == FGPU_SCALAR_NULL) return nulls != 0;
     if (full_of_nulls) return false;
+    // the reference asks the bloom filter when the chunk has one and the bounds otherwise (:104-118); both are true
+    // negatives, so both are asked here
+    if (!bloom_may_contain(ch, lit)) return false;
     const int cmax = stat_compare(ch, true, lit, &ok);
     if (!ok) return true;
     const int cmin = stat_compare(ch, false, lit, &ok);
@@ -1164,6 +1189,11 @@ int32_t compile(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, Compiled* c) {
           const std::string& lit = lh.lit->lit_bytes;
           if (lit < it->second.min_str || lit > it->second.max_str) mode = LM_NONE;
         }
+        // equality with a value the chunk's bloom filter rules out: the leaf is false on every row of the row group
+        // (also under a disjunction, where the row group itself stays)
+        if (mode == LM_EVAL && it != v.rg->cols.end() && lh.op == FGPU_OP_EQ && !lh.null_literal && !v.part->arrow &&
+            !bloom_may_contain(it->second, *lh.lit))
+          mode = LM_NONE;
         v.leaf_mode[l] = mode;
         if (conj && mode == LM_NONE) drop = true;
       }
@@ -3511,6 +3541,59 @@ int32_t fgpu_rowgroup_leaf_mode(int32_t op, int64_t literal, int32_t has_bounds,
   bool neg;
   canonical_int_range(op, literal, &lo, &hi, &neg);
   *out_mode = chunk_leaf_mode(lo, hi, neg, has_bounds != 0, min_value, max_value, null_count, num_values);
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_xxhash64(const uint8_t* data, uint64_t len, uint64_t seed, uint64_t* out) {
+  API_TRY
+  if ((!data && len) || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  *out = xxhash64(data, size_t(len), seed);
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_bloom_check(const uint8_t* bitset, uint64_t nbytes, uint64_t hash, int32_t* out_may_contain) {
+  API_TRY
+  if (!bitset || !out_may_contain) return fail(FGPU_ERR_INVALID, "null argument");
+  if (nbytes < 32 || nbytes % 32 != 0 || nbytes > 0xffffffffull) return fail(FGPU_ERR_INVALID, "a split-block filter is a multiple of 32 bytes");
+  *out_may_contain = sbbf_check(bitset, uint32_t(nbytes), hash) ? 1 : 0;
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_bloom_insert(uint8_t* bitset, uint64_t nbytes, uint64_t hash) {
+  API_TRY
+  if (!bitset) return fail(FGPU_ERR_INVALID, "null argument");
+  if (nbytes < 32 || nbytes % 32 != 0 || nbytes > 0xffffffffull) return fail(FGPU_ERR_INVALID, "a split-block filter is a multiple of 32 bytes");
+  sbbf_insert(bitset, uint32_t(nbytes), hash);
+  return FGPU_OK;
+  API_CATCH
+}
+
+int32_t fgpu_parquet_rowgroup_may_match_eq(const uint8_t* file, uint64_t len, int32_t row_group, const char* column, int32_t lit_type,
+                                           int64_t lit_i64, double lit_f64, const uint8_t* lit_bytes, uint64_t lit_len, int32_t* out) {
+  API_TRY
+  if (!file || !column || !out) return fail(FGPU_ERR_INVALID, "null argument");
+  Part part;
+  std::string err;
+  if (!open_part(file, len, &part, &err)) return fail(FGPU_ERR_PARQUET, err);
+  if (row_group < 0 || size_t(row_group) >= part.rgs.size()) return fail(FGPU_ERR_INVALID, "no such row group");
+  QueryPlan q;
+  ExprNode col, lit, eq;
+  col.kind = FGPU_EXPR_COLUMN;
+  col.name = column;
+  lit.kind = FGPU_EXPR_LITERAL;
+  lit.lit_type = lit_type;
+  lit.lit_i = lit_i64;
+  lit.lit_f = lit_f64;
+  if (lit_bytes && lit_len) lit.lit_bytes.assign(reinterpret_cast<const char*>(lit_bytes), size_t(lit_len));
+  eq.kind = FGPU_EXPR_BINARY;
+  eq.op = FGPU_OP_EQ;
+  eq.left = 0;
+  eq.right = 1;
+  q.exprs = {col, lit, eq};
+  *out = rg_may_match(q, 2, part.rgs[size_t(row_group)]) ? 1 : 0;
   return FGPU_OK;
   API_CATCH
 }

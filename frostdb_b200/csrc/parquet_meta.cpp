@@ -151,6 +151,8 @@ struct RawColumnMeta {
   int32_t type = -1, codec = 0;
   int64_t num_values = 0, total_compressed = 0, data_page_offset = -1, dict_page_offset = -1;
   int64_t null_count = -1;
+  int64_t bloom_offset = -1;
+  int32_t bloom_length = -1;
   std::string stat_min, stat_max;  // raw PLAIN-encoded bounds, empty = not written
   bool stat_deprecated = false;    // the bounds come from the deprecated min / max fields (signed byte order for BYTE_ARRAY)
   std::vector<std::string> path;
@@ -195,10 +197,44 @@ RawColumnMeta read_column_meta(TReader& r) {
       case 9: m.data_page_offset = r.zigzag(); break;
       case 11: m.dict_page_offset = r.zigzag(); break;
       case 12: read_statistics(r, &m); break;
+      case 14: m.bloom_offset = r.zigzag(); break;
+      case 15: m.bloom_length = int32_t(r.zigzag()); break;
       default: r.skip(t);
     }
   }
   return m;
+}
+
+// BloomFilterHeader {1: i32 numBytes, 2: BloomFilterAlgorithm {1: BLOCK}, 3: BloomFilterHash {1: XXHASH},
+// 4: BloomFilterCompression {1: UNCOMPRESSED}} followed by the bitset.  Anything else: the filter is ignored.
+void read_bloom(const uint8_t* file, uint64_t len, int64_t offset, ChunkMeta* out) {
+  if (offset < 0 || uint64_t(offset) >= len) return;
+  try {
+    TReader r(file + offset, file + len);
+    int32_t num_bytes = -1;
+    bool ok = true;
+    int16_t last = 0, id; int t;
+    auto union_is_1 = [&](TReader& rr) {  // a union with exactly field 1 set (an empty struct)
+      bool one = false;
+      int16_t l2 = 0, id2; int t2;
+      while (rr.field(&l2, &id2, &t2)) {
+        if (id2 == 1) one = true;
+        else one = false;
+        rr.skip(t2);
+      }
+      return one;
+    };
+    while (r.field(&last, &id, &t)) {
+      if (id == 1) num_bytes = int32_t(r.zigzag());
+      else if ((id == 2 || id == 3 || id == 4) && t == 12) ok = union_is_1(r) && ok;
+      else r.skip(t);
+    }
+    if (!ok || num_bytes < 32 || num_bytes % 32 != 0) return;
+    if (uint64_t(r.pos() - file) + uint64_t(num_bytes) > len) return;
+    out->bloom = r.pos();
+    out->bloom_bytes = uint32_t(num_bytes);
+  } catch (ThriftError&) {
+  }
 }
 
 struct RawPageHeader {
@@ -509,6 +545,7 @@ bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::stri
     for (size_t c = 0; c < rg.cols.size(); c++) {
       m.chunks[c].leaf = int32_t(c);
       init_chunk(rg.cols[c], out->leaves[c], &m.chunks[c]);
+      if (rg.cols[c].bloom_offset >= 0) read_bloom(file, len, rg.cols[c].bloom_offset, &m.chunks[c]);
       if (walk_pages) walk_chunk_pages(file, len, out->leaves[c], rg.num_rows, &m.chunks[c]);
     }
     out->row_groups.push_back(std::move(m));
@@ -616,6 +653,88 @@ uint32_t hybrid_value_at(const uint8_t* stream, const std::vector<HostRun>& runs
   uint64_t window = 0;
   for (int i = 0; i < 5; i++) window |= uint64_t(p[i]) << (8 * i);  // callers pad streams by 8 bytes
   return uint32_t((window >> (bit & 7)) & ((w == 32) ? 0xffffffffull : ((1ull << w) - 1)));
+}
+
+
+// ---- bloom filters ---------------------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t kP1 = 11400714785074694791ull, kP2 = 14029467366897019727ull, kP3 = 1609587929392839161ull,
+                   kP4 = 9650029242287828579ull, kP5 = 2870177450012600261ull;
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline uint64_t rd64(const uint8_t* p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+inline uint64_t xx_round(uint64_t acc, uint64_t in) { return rotl64(acc + in * kP2, 31) * kP1; }
+inline uint64_t xx_merge(uint64_t acc, uint64_t v) { return (acc ^ xx_round(0, v)) * kP1 + kP4; }
+constexpr uint32_t kSalt[8] = {0x47b6137bu, 0x44974d91u, 0x8824ad5bu, 0xa2b7289du, 0x705495c7u, 0x2df1424bu, 0x9efc4947u, 0x5c6bfb31u};
+}  // namespace
+
+uint64_t xxhash64(const uint8_t* p, size_t len, uint64_t seed) {
+  const uint8_t* const end = p + len;
+  uint64_t h;
+  if (len >= 32) {
+    uint64_t v1 = seed + kP1 + kP2, v2 = seed + kP2, v3 = seed, v4 = seed - kP1;
+    do {
+      v1 = xx_round(v1, rd64(p));
+      v2 = xx_round(v2, rd64(p + 8));
+      v3 = xx_round(v3, rd64(p + 16));
+      v4 = xx_round(v4, rd64(p + 24));
+      p += 32;
+    } while (p + 32 <= end);
+    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = xx_merge(h, v1);
+    h = xx_merge(h, v2);
+    h = xx_merge(h, v3);
+    h = xx_merge(h, v4);
+  } else {
+    h = seed + kP5;
+  }
+  h += uint64_t(len);
+  while (p + 8 <= end) {
+    h ^= xx_round(0, rd64(p));
+    h = rotl64(h, 27) * kP1 + kP4;
+    p += 8;
+  }
+  if (p + 4 <= end) {
+    h ^= uint64_t(rd32(p)) * kP1;
+    h = rotl64(h, 23) * kP2 + kP3;
+    p += 4;
+  }
+  while (p < end) {
+    h ^= uint64_t(*p) * kP5;
+    h = rotl64(h, 11) * kP1;
+    p++;
+  }
+  h ^= h >> 33;
+  h *= kP2;
+  h ^= h >> 29;
+  h *= kP3;
+  h ^= h >> 32;
+  return h;
+}
+
+bool sbbf_check(const uint8_t* bitset, uint32_t bytes, uint64_t hash) {
+  const uint64_t n_blocks = bytes / 32;
+  if (n_blocks == 0) return true;
+  const uint64_t block = ((hash >> 32) * n_blocks) >> 32;
+  const uint32_t key = uint32_t(hash);
+  const uint8_t* b = bitset + block * 32;
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bit = 1u << ((key * kSalt[i]) >> 27);
+    if ((rd32(b + 4 * i) & bit) == 0) return false;
+  }
+  return true;
+}
+
+void sbbf_insert(uint8_t* bitset, uint32_t bytes, uint64_t hash) {
+  const uint64_t n_blocks = bytes / 32;
+  if (n_blocks == 0) return;
+  const uint64_t block = ((hash >> 32) * n_blocks) >> 32;
+  const uint32_t key = uint32_t(hash);
+  uint8_t* b = bitset + block * 32;
+  for (int i = 0; i < 8; i++) {
+    uint32_t w = rd32(b + 4 * i) | (1u << ((key * kSalt[i]) >> 27));
+    std::memcpy(b + 4 * i, &w, 4);
+  }
 }
 
 }  // namespace fgpu

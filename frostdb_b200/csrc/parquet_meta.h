@@ -50,6 +50,11 @@ struct ChunkMeta {
   int64_t min_bits = 0, max_bits = 0; // raw 8-byte bounds of the non-null values
   bool has_minmax_str = false;        // BYTE_ARRAY chunks: both (possibly truncated, still bounding) strings recorded
   std::string min_str, max_str;
+  // split-block bloom filter of the chunk (parquet-go writes one per sorting column, dynparquet/schema.go:1111-1157):
+  // the bitset (aliases `file`), null when the chunk has none or it uses an algorithm / hash / compression other than
+  // BLOCK / XXHASH / UNCOMPRESSED
+  const uint8_t* bloom = nullptr;
+  uint32_t bloom_bytes = 0;
   const uint8_t* dict = nullptr;      // dictionary page payload (PLAIN)
   uint32_t dict_len = 0;
   uint32_t dict_num_values = 0;
@@ -80,6 +85,14 @@ bool parse_parquet(const uint8_t* file, uint64_t len, ParsedFile* out, std::stri
 
 // Walks the page headers of one column chunk (idempotent): fills pages / dict, or sets error.
 void walk_chunk_pages(const uint8_t* file, uint64_t len, const SchemaLeaf& leaf, int64_t rg_rows, ChunkMeta* cm);
+
+// XXH64 (the hash of Parquet bloom filters, seed 0 over the PLAIN encoding of the value: the 8 little-endian bytes of an
+// INT64 / DOUBLE, the bytes of a BYTE_ARRAY without their length prefix).
+uint64_t xxhash64(const uint8_t* data, size_t len, uint64_t seed);
+// Split-block bloom filter check (Parquet format, BloomFilter.md): false = the value is definitely not in the chunk.
+bool sbbf_check(const uint8_t* bitset, uint32_t bytes, uint64_t hash);
+// Sets the bits of `hash` (the writer's half; used by the tests to build filters).
+void sbbf_insert(uint8_t* bitset, uint32_t bytes, uint64_t hash);
 
 // One run of an RLE/bit-packed hybrid stream (Parquet "RLE" encoding).
 struct HostRun {

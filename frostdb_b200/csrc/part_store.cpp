@@ -474,6 +474,9 @@ bool open_part(const uint8_t* file, uint64_t len, Part* part, std::string* err) 
       ch.has_minmax_str = rg.chunks[c].has_minmax_str;
       ch.min_str = rg.chunks[c].min_str;
       ch.max_str = rg.chunks[c].max_str;
+      // (parquet-go sizes the filter by the chunk's values, 10 bits each: anything beyond a few MB is left alone)
+      if (rg.chunks[c].bloom && rg.chunks[c].bloom_bytes <= (8u << 20))
+        ch.bloom.assign(rg.chunks[c].bloom, rg.chunks[c].bloom + rg.chunks[c].bloom_bytes);
       ch.desc.n_rows = h.n_rows;
       h.cols.emplace(part->pf.leaves[c].name, std::move(ch));
     }
@@ -502,6 +505,7 @@ void build_column(int index_rows, Table* table, Part* part, const std::string& c
     walk_chunk_pages(part->file, part->file_bytes, sl, rg.num_rows, &rg.chunks[leaf]);  // first touch of this chunk
     build_chunk(rg.chunks[leaf], sl, h.n_rows, index_rows, dict, w, &ch);
     if (!ch.error.empty() && img.error.empty()) img.error = ch.error;
+    ch.bloom = std::move(h.cols[column].bloom);  // (footer-level fact of the skeleton the built chunk replaces)
     h.cols[column] = std::move(ch);
   }
   finish_image(w, img, part, column);

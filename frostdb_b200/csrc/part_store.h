@@ -45,6 +45,7 @@ struct ChunkHost {
   int64_t null_count = -1;     // -1: not recorded
   bool has_minmax_str = false; // BYTE_ARRAY chunk: bounding strings of the non-null values
   std::string min_str, max_str;
+  std::vector<uint8_t> bloom;      // split-block bloom filter of the chunk (copied out of the file at put; empty: none)
   std::vector<uint32_t> lut_host;  // CK_DICT_STR: chunk dictionary index -> *local* global id
   // section offsets inside the part image (patched into desc after upload)
   int64_t off_values = -1, off_runs = -1, off_seeds = -1, off_def = -1, off_def_runs = -1, off_def_seeds = -1, off_lut = -1,

@@ -316,6 +316,19 @@ int32_t fgpu_part_decode_column(fgpu_ctx* ctx, const char* table, uint64_t part_
 int32_t fgpu_rowgroup_leaf_mode(int32_t op, int64_t literal, int32_t has_bounds, int64_t min_value, int64_t max_value,
                                 int64_t null_count, int64_t num_values, int32_t* out_mode);
 
+/* Split-block bloom filters (Parquet BloomFilter.md; parquet-go writes one per sorting column,
+ * dynparquet/schema.go:1111-1157; checked by expr/binaryscalarexpr.go:104-118): XXH64 of a value's PLAIN encoding, the
+ * check and — for tests that build filters — the insert. */
+int32_t fgpu_xxhash64(const uint8_t* data, uint64_t len, uint64_t seed, uint64_t* out);
+int32_t fgpu_bloom_check(const uint8_t* bitset, uint64_t nbytes, uint64_t hash, int32_t* out_may_contain);
+int32_t fgpu_bloom_insert(uint8_t* bitset, uint64_t nbytes, uint64_t hash);
+
+/* The row-group filter's answer for "column == literal" on one row group of a Parquet file, exactly as
+ * fgpu_query_execute decides it before anything is uploaded (null count, bloom filter, bounds; LSM.Scan,
+ * index/lsm.go:401-454 -> expr/binaryscalarexpr.go:84-128).  lit_type: FGPU_SCALAR_*.  *out: 1 may match, 0 cannot. */
+int32_t fgpu_parquet_rowgroup_may_match_eq(const uint8_t* file, uint64_t len, int32_t row_group, const char* column, int32_t lit_type,
+                                           int64_t lit_i64, double lit_f64, const uint8_t* lit_bytes, uint64_t lit_len, int32_t* out);
+
 /* Parses a Parquet file exactly as fgpu_part_put_parquet does (footer, page walk, run
  * directories) and writes a JSON description into buf.  Call with buf == NULL to size. */
 int32_t fgpu_parquet_describe(const uint8_t* file, uint64_t len, int32_t tile_rows, char* buf,

@@ -452,3 +452,62 @@ def test_filter_only_plans_with_dictionary_leaves_take_path(pair):
                         out.extend(zip(*[bt.column(bt.schema.get_field_index(cn)).to_pylist() for cn in cols]))
                 return out
             assert flat(got) == flat(exp) == flat(got2), f"{f.Name()} -> {cols}"
+
+
+def test_bloom_filters_prune_equality_leaves(store):
+    """Chunks with split-block bloom filters (what parquet-go writes for FrostDB's sorting columns): `x == v` with v
+    inside [min, max] but not in the chunk drops the row group before anything is uploaded; under a disjunction the row
+    group stays and the leaf is false on all of its rows; values that are there are found."""
+    from tests import bloom_file as bf
+    eng = store.engine
+    rng = np.random.default_rng(11)
+    parts = []
+    for i in range(3):
+        xs = [int(v) for v in rng.integers(0, 100_000, 5_000)]
+        ys = [int(v) for v in rng.integers(0, 10, 5_000)]
+        parts.append((xs, ys))
+        eng.put_parquet("bloomy", bf.write_int64_file({"x": xs, "y": ys}))
+    try:
+        x, y = lp.Col("x"), lp.Col("y")
+        all_x = [v for xs, _ in parts for v in xs]
+        absent = None
+        for v in range(50_000, 50_400):  # a value no part holds and every part's filter rejects
+            if v in all_x:
+                continue
+            if all(not bf.sbbf_check(_bits(xs), bf.xxh64(v.to_bytes(8, "little", signed=True))) for xs, _ in parts):
+                absent = v
+                break
+        assert absent is not None
+        def run(filt, aggs=None):
+            scan = GPUScan(eng, "bloomy", filt, _lib.PLAN_AGGREGATE, [], aggs or [lp.Count(x), lp.Sum(y)])
+            q, keep = scan.prepare()
+            lib = _lib.load()
+            res = C.c_void_p()
+            _lib.check(lib.fgpu_query_execute(eng.handle, q, eng.table_watermark("bloomy"), C.byref(res)))
+            st = eng.stats(res)
+            rows = rows_of(list(eng.drain(res)))
+            lib.fgpu_result_free(res)
+            lib.fgpu_query_free(q)
+            return st, rows
+        st, rows = run(x.Eq(lp.Literal(absent)))
+        assert st["row_groups_pruned"] == 3 and st["row_groups"] == 0 and rows == []
+        present = parts[1][0][17]
+        st, rows = run(x.Eq(lp.Literal(present)))
+        exp_n = sum(xs.count(present) for xs, _ in parts)
+        exp_s = sum(yv for xs, ys in parts for xv, yv in zip(xs, ys) if xv == present)
+        assert rows == [(exp_n, exp_s)]
+        assert st["row_groups_pruned"] >= 1  # the parts whose filters do not know the value
+        st, rows = run(lp.Or(x.Eq(lp.Literal(absent)), y.Eq(lp.Literal(3))))
+        exp_n = sum(1 for _, ys in parts for yv in ys if yv == 3)
+        assert st["row_groups_pruned"] == 0 and rows == [(exp_n, 3 * exp_n)]
+    finally:
+        eng.drop_table("bloomy")
+
+
+def _bits(xs):
+    from tests import bloom_file as bf
+    n_bytes = max(32, ((len(xs) * 10 // 8) + 31) // 32 * 32)
+    bits = bytearray(n_bytes)
+    for v in xs:
+        bf.sbbf_insert(bits, bf.xxh64(v.to_bytes(8, "little", signed=True)))
+    return bytes(bits)

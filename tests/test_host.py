@@ -178,3 +178,96 @@ def test_row_group_pruning_decisions_against_reference_vectors(built_lib):
             assert built_lib.fgpu_rowgroup_leaf_mode(op, lit, 1, 5, 9, 3, 10, C.byref(mode)) == 0 and mode.value == 0
     mode = C.c_int32(-1)
     assert built_lib.fgpu_rowgroup_leaf_mode(2, 7, 1, 7, 7, 2, 10, C.byref(mode)) == 0 and mode.value == 2   # != 7 on a chunk of 7s and NULLs
+
+
+# ---- split-block bloom filters (N2: expr/binaryscalarexpr.go:104-118, dynparquet/schema.go:1111-1157) ---------------
+def test_xxhash64_known_answers_and_python_reference():
+    """XXH64 (seed 0) known answers from the xxHash specification, then the library against the plain-Python
+    implementation of tests/bloom_file.py over every tail length."""
+    import ctypes as C
+    from tests import bloom_file as bf
+    lib = _lib.load()
+    def h(data, seed=0):
+        out = C.c_uint64(0)
+        assert lib.fgpu_xxhash64(data, len(data), seed, C.byref(out)) == 0
+        return out.value
+    assert h(b"") == 0xEF46DB3751D8E999
+    assert h(b"a") == 0xD24EC4F1A98C6E5B
+    assert h(b"abc") == 0x44BC2CF5AD770999
+    rng = np.random.default_rng(5)
+    for n in list(range(0, 70)) + [127, 128, 129, 1000]:
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        for seed in (0, 0x9E3779B185EBCA87):
+            assert h(data, seed) == bf.xxh64(data, seed), (n, seed)
+
+
+def test_split_block_filter_matches_the_format_description():
+    """Insert through the library, check in Python and the other way round (block selection, the eight salts, bit
+    positions: Parquet BloomFilter.md); values that were never inserted are mostly rejected, inserted ones never."""
+    import ctypes as C
+    from tests import bloom_file as bf
+    lib = _lib.load()
+    rng = np.random.default_rng(6)
+    for n_bytes in (32, 64, 1024, 4096 + 32):
+        a = bytearray(n_bytes)           # written by Python
+        b = (C.c_uint8 * n_bytes)()      # written by the library
+        hashes = [int(x) for x in rng.integers(0, 2**63, 200, dtype=np.int64)] + [0, 2**64 - 1, 2**32, 2**32 - 1]
+        for hv in hashes:
+            bf.sbbf_insert(a, hv)
+            assert lib.fgpu_bloom_insert(b, n_bytes, hv) == 0
+        assert bytes(a) == bytes(b)
+        a_c = (C.c_uint8 * n_bytes).from_buffer_copy(bytes(a))
+        out = C.c_int32(0)
+        for hv in hashes:
+            assert lib.fgpu_bloom_check(a_c, n_bytes, hv, C.byref(out)) == 0 and out.value == 1
+        others = [int(x) for x in rng.integers(0, 2**63, 500, dtype=np.int64)]
+        agree = 0
+        for hv in others:
+            assert lib.fgpu_bloom_check(a_c, n_bytes, hv, C.byref(out)) == 0
+            assert bool(out.value) == bf.sbbf_check(bytes(a), hv)
+            agree += 1 - out.value
+        if n_bytes >= 1024:
+            assert agree > 300  # a filter with >= 40 bits per value rejects nearly every stranger
+    assert lib.fgpu_bloom_check(a_c, 48, 1, C.byref(out)) != 0  # not a multiple of the 32-byte block
+
+
+def test_row_group_filter_asks_the_bloom_filter_for_equality():
+    """A Parquet file whose chunks carry bloom filters (tests/bloom_file.py: pyarrow cannot write them, it reads the
+    file back): `x == v` for a value inside [min, max] that is not in the chunk is ruled out by the filter
+    (expr/binaryscalarexpr.go:104-118), a value that is there never is; outside the bounds and `== NULL` on a required
+    column are ruled out as before.  The answers are compared with the plain-Python filter over 300 absent values."""
+    import ctypes as C
+    import io
+    import pyarrow.parquet as pq
+    from tests import bloom_file as bf
+    rng = np.random.default_rng(7)
+    xs = sorted(set(int(v) for v in rng.integers(0, 1_000_000, 2_000)))
+    ys = [int(v) for v in rng.integers(-50, 50, len(xs))]
+    buf = bf.write_int64_file({"x": xs, "y": ys})
+    assert pq.read_table(io.BytesIO(buf)).to_pydict() == {"x": xs, "y": ys}
+    d = _lib.describe_parquet(buf)
+    assert d["row_groups"][0]["n_rows"] == len(xs)
+    lib = _lib.load()
+    def may(col, v, lit_type=_lib.SCALAR_INT64):
+        out = C.c_int32(-1)
+        assert lib.fgpu_parquet_rowgroup_may_match_eq(buf, len(buf), 0, col.encode(), lit_type, int(v or 0), 0.0, None, 0, C.byref(out)) == 0
+        return bool(out.value)
+    for v in xs[::37]:
+        assert may("x", v)
+    # the bitset the writer produced, rebuilt here to predict the filter's answer for absent values
+    n_bytes = max(32, ((len(xs) * 10 // 8) + 31) // 32 * 32)
+    bits = bytearray(n_bytes)
+    for v in xs:
+        bf.sbbf_insert(bits, bf.xxh64(v.to_bytes(8, "little", signed=True)))
+    present, ruled_out = set(xs), 0
+    for v in (int(v) for v in rng.integers(xs[0] + 1, xs[-1], 300)):
+        if v in present:
+            continue
+        expect = bf.sbbf_check(bytes(bits), bf.xxh64(v.to_bytes(8, "little", signed=True)))
+        assert may("x", v) == expect, v
+        ruled_out += 0 if expect else 1
+    assert ruled_out > 250  # 10 bits per value: ~1 % false positives
+    assert not may("x", xs[-1] + 5) and not may("x", xs[0] - 1)    # outside the bounds
+    assert not may("x", None, _lib.SCALAR_NULL)                    # required column: no NULL to find
+    assert may("y", ys[3]) and not may("y", 77)
+    assert not may("nope", 1) and may("nope", None, _lib.SCALAR_NULL)  # missing column (:47-73)
