@@ -6,7 +6,7 @@
  *
  * Parity status: the reference is Go and cannot be compiled here (no Go toolchain), so this port
  * is pinned against the reference's own golden vectors transcribed in tests/golden/ (logictest
- * exec files, aggregate_test.go, db_test.go, filter_test.go) and cross-checked against pyarrow for
+ * exec files, aggregate_test.go, expr/binaryscalarexpr_test.go) and cross-checked against pyarrow for
  * the Parquet decoding, which in the reference lives in the un-vendored third-party module
  * github.com/parquet-go/parquet-go v0.24.0 (go.mod) and is restated here from the public Parquet
  * format specification.  Semantics with no reference test behind them are marked UNPINNED.
@@ -15,7 +15,11 @@
  *   scan       -> visible parts, row groups ruled out by the filter's  index/lsm.go:401-454
  *                 TrueNegativeFilter over the chunk statistics        query/expr/{filter,binaryscalarexpr}.go
  *                 (pinned by TestBinaryScalarOperation, expr/binaryscalarexpr_test.go:56-212 ->
- *                 tests/golden/rowgroup_filter_cases.py; it never changes a result)
+ *                 tests/golden/rowgroup_filter_cases.py; it never changes a result); `==` asks the
+ *                 chunk's split-block bloom filter when it has one, binaryscalarexpr.go:104-118
+ *                 (parquet-go's filter restated from the Parquet format's BloomFilter.md: XXH64 of the
+ *                 PLAIN-encoded value, 8 salted bits in one 32-byte block; pinned by the xxHash known
+ *                 answers and a plain-Python second implementation, tests/bloom_file.py)
  *   row group  -> decode projected columns to Arrow-like arrays    pqarrow/arrow.go:264-373,711-823
  *                 dictionary columns: one memo-table insert per row pqarrow/writer/writer.go:381-405
  *   filter     -> leaf bitmaps, AND/OR, compaction of all columns   query/physicalplan/filter.go:167-323
@@ -148,6 +152,10 @@ typedef struct {
   int64_t null_count;                  /* -1: not recorded */
   const uint8_t *smin, *smax;          /* PLAIN-encoded bounds inside the footer, NULL: not recorded */
   uint32_t smin_len, smax_len;
+  /* split-block bloom filter (parquet-go writes one per sorting column, dynparquet/schema.go:1111-1157) */
+  int64_t bloom_off;                   /* ColumnMetaData.bloom_filter_offset, -1: none */
+  const uint8_t* bloom;                /* the bitset inside the file, NULL: none / not BLOCK + XXHASH + UNCOMPRESSED */
+  uint32_t bloom_bytes;
 } o_chunk;
 
 typedef struct { int64_t num_rows; o_chunk* chunks; } o_rg;
@@ -197,7 +205,7 @@ static int parse_footer(o_part* part, char* err) {
             int et2; uint32_t nc; t_list(&r, &et2, &nc);
             rg->chunks = xcalloc(nc, sizeof(o_chunk));
             for (uint32_t c = 0; c < nc; c++) {
-              o_chunk* ch = &rg->chunks[c]; ch->data_off = -1; ch->dict_off = -1; ch->null_count = -1;
+              o_chunk* ch = &rg->chunks[c]; ch->data_off = -1; ch->dict_off = -1; ch->null_count = -1; ch->bloom_off = -1;
               int l3 = 0, id3, t3;
               while (t_field(&r, &l3, &id3, &t3)) {
                 if (id3 == 3) {
@@ -209,6 +217,7 @@ static int parse_footer(o_part* part, char* err) {
                     else if (id4 == 7) ch->total_compressed = t_zz(&r);
                     else if (id4 == 9) ch->data_off = t_zz(&r);
                     else if (id4 == 11) ch->dict_off = t_zz(&r);
+                    else if (id4 == 14) ch->bloom_off = t_zz(&r);
                     else if (id4 == 12) { /* Statistics: 5/6 max_value/min_value, 1/2 the deprecated pair, 3 null_count */
                       const uint8_t *omin = NULL, *omax = NULL; uint32_t ominl = 0, omaxl = 0;
                       int l5 = 0, id5, t5;
@@ -900,6 +909,64 @@ static int stat_cmp(int phys, const uint8_t* a, uint32_t al, const fgpu_scalar* 
   return 0;
 }
 
+/* ---- bloom filters: what parquet-go's ColumnChunk.BloomFilter().Check(value) computes (Parquet BloomFilter.md) ---- */
+static inline uint64_t xx_rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+#define XXP1 11400714785074694791ull
+#define XXP2 14029467366897019727ull
+#define XXP3 1609587929392839161ull
+#define XXP4 9650029242287828579ull
+#define XXP5 2870177450012600261ull
+static inline uint64_t xx_round(uint64_t acc, uint64_t in) { return xx_rotl(acc + in * XXP2, 31) * XXP1; }
+static inline uint64_t xx_merge(uint64_t acc, uint64_t v) { return (acc ^ xx_round(0, v)) * XXP1 + XXP4; }
+static uint64_t xxh64(const uint8_t* p, size_t len) { /* seed 0 */
+  const uint8_t* end = p + len; uint64_t h, k; uint32_t k4;
+  if (len >= 32) {
+    uint64_t v1 = XXP1 + XXP2, v2 = XXP2, v3 = 0, v4 = 0ull - XXP1;
+    do {
+      memcpy(&k, p, 8); v1 = xx_round(v1, k); memcpy(&k, p + 8, 8); v2 = xx_round(v2, k);
+      memcpy(&k, p + 16, 8); v3 = xx_round(v3, k); memcpy(&k, p + 24, 8); v4 = xx_round(v4, k);
+      p += 32;
+    } while (p + 32 <= end);
+    h = xx_rotl(v1, 1) + xx_rotl(v2, 7) + xx_rotl(v3, 12) + xx_rotl(v4, 18);
+    h = xx_merge(h, v1); h = xx_merge(h, v2); h = xx_merge(h, v3); h = xx_merge(h, v4);
+  } else h = XXP5;
+  h += (uint64_t)len;
+  while (p + 8 <= end) { memcpy(&k, p, 8); h ^= xx_round(0, k); h = xx_rotl(h, 27) * XXP1 + XXP4; p += 8; }
+  if (p + 4 <= end) { memcpy(&k4, p, 4); h ^= (uint64_t)k4 * XXP1; h = xx_rotl(h, 23) * XXP2 + XXP3; p += 4; }
+  while (p < end) { h ^= (uint64_t)*p * XXP5; h = xx_rotl(h, 11) * XXP1; p++; }
+  h ^= h >> 33; h *= XXP2; h ^= h >> 29; h *= XXP3; h ^= h >> 32;
+  return h;
+}
+static int sbbf_check(const uint8_t* bits, uint32_t bytes, uint64_t h) {
+  static const uint32_t salt[8] = {0x47b6137bu, 0x44974d91u, 0x8824ad5bu, 0xa2b7289du, 0x705495c7u, 0x2df1424bu, 0x9efc4947u, 0x5c6bfb31u};
+  uint64_t nb = bytes / 32; if (!nb) return 1;
+  const uint8_t* b = bits + (((h >> 32) * nb) >> 32) * 32;
+  uint32_t key = (uint32_t)h, w;
+  for (int i = 0; i < 8; i++) { memcpy(&w, b + 4 * i, 4); if (!(w & (1u << ((key * salt[i]) >> 27)))) return 0; }
+  return 1;
+}
+/* BloomFilterHeader {1 numBytes, 2 algorithm {1 BLOCK}, 3 hash {1 XXHASH}, 4 compression {1 UNCOMPRESSED}} + bitset */
+static void resolve_bloom(const o_part* part, o_chunk* ch) {
+  if (ch->bloom_off < 0 || (uint64_t)ch->bloom_off >= part->len) { ch->bloom_off = -1; return; }
+  trd r = {part->file + ch->bloom_off, part->file + part->len, 0};
+  int64_t nbytes = -1; int ok = 1, last = 0, id, t;
+  while (t_field(&r, &last, &id, &t)) {
+    if (id == 1) nbytes = t_zz(&r);
+    else if ((id == 2 || id == 3 || id == 4) && t == 12) { int one = 0, l2 = 0, id2, t2; while (t_field(&r, &l2, &id2, &t2)) { one = id2 == 1; t_skip(&r, t2, 0); } ok = ok && one; }
+    else t_skip(&r, t, 0);
+  }
+  ch->bloom_off = -1; /* resolved */
+  if (r.err || !ok || nbytes < 32 || nbytes % 32 || (uint64_t)(r.p - part->file) + (uint64_t)nbytes > part->len) return;
+  ch->bloom = r.p; ch->bloom_bytes = (uint32_t)nbytes;
+}
+/* 1: the filter may hold the literal (or cannot be asked), 0: it definitely does not */
+static int bloom_check_lit(const o_chunk* ch, const fgpu_scalar* lit) {
+  if (ch->phys == PQ_INT64 && lit->type == FGPU_SCALAR_INT64) { uint8_t b[8]; memcpy(b, &lit->i64, 8); return sbbf_check(ch->bloom, ch->bloom_bytes, xxh64(b, 8)); }
+  if (ch->phys == PQ_DOUBLE && lit->type == FGPU_SCALAR_FLOAT64) { uint8_t b[8]; memcpy(b, &lit->f64, 8); return sbbf_check(ch->bloom, ch->bloom_bytes, xxh64(b, 8)); }
+  if (ch->phys == PQ_BYTE_ARRAY && lit->type == FGPU_SCALAR_STRING) return sbbf_check(ch->bloom, ch->bloom_bytes, xxh64((const uint8_t*)lit->bytes, (size_t)lit->len));
+  return 1;
+}
+
 /* BinaryScalarOperation (expr/binaryscalarexpr.go:84-190) over one chunk's statistics.  nulls < 0: unknown. */
 static int chunk_may_match(const o_chunk* ch, int64_t nulls, int64_t num_rows, int op, const fgpu_scalar* lit) {
   int full_of_nulls = nulls >= 0 && nulls == num_rows;
@@ -907,6 +974,7 @@ static int chunk_may_match(const o_chunk* ch, int64_t nulls, int64_t num_rows, i
   if (op == FGPU_OP_EQ) {
     if (lit->type == FGPU_SCALAR_NULL) return nulls != 0; /* unknown count: maybe */
     if (full_of_nulls) return 0;
+    if (ch->bloom) return bloom_check_lit(ch, lit); /* :104-118: with a bloom filter the bounds are not consulted */
     if (!ch->smin || !ch->smax) return 1;
     int cmax = stat_cmp(ch->phys, ch->smax, ch->smax_len, lit, &ok); if (!ok) return 1;
     int cmin = stat_cmp(ch->phys, ch->smin, ch->smin_len, lit, &ok); if (!ok) return 1;
@@ -941,10 +1009,14 @@ static int rg_may_match(const fgpu_plan* plan, int node, const o_part* part, con
     if (lit->type == FGPU_SCALAR_STRING) { if (e->op == FGPU_OP_EQ && lit->len == 0) return 1; if (e->op == FGPU_OP_NOT_EQ && lit->len != 0) return 1; }
     return 0;
   }
-  const o_chunk* ch = &rg->chunks[ci];
+  o_chunk* ch = &rg->chunks[ci];
+  if (ch->bloom_off >= 0) resolve_bloom(part, ch); /* (idempotent; the result only depends on the file) */
   int64_t nulls = ch->null_count >= 0 ? ch->null_count : (part->leaves[ci].optional ? -1 : 0);
   return chunk_may_match(ch, nulls, rg->num_rows, e->op, lit);
 }
+
+/* Test hook: the row-group filter's answer for "column == int64 literal" on one row group of a Parquet file. */
+int oracle_parquet_rowgroup_may_match_eq_i64(const uint8_t* file, uint64_t len, int row_group, const char* column, int lit_is_null, int64_t lit);
 
 /* Test hook: BinaryScalarOperation on an int64 chunk described by its statistics alone, so that the cases of
    the reference's TestBinaryScalarOperation (expr/binaryscalarexpr_test.go:56-212) can be replayed. */
@@ -1016,6 +1088,26 @@ int oracle_table_add_parquet(oracle_table* t, const uint8_t* file, uint64_t len,
   return 0;
 }
 const char* oracle_table_error(oracle_table* t) { return t->err; }
+
+void oracle_table_free(oracle_table* t);
+/* Test hook (declared above): -1 on a malformed file / unknown row group. */
+int oracle_parquet_rowgroup_may_match_eq_i64(const uint8_t* file, uint64_t len, int row_group, const char* column, int lit_is_null, int64_t lit) {
+  oracle_table* t = oracle_table_new();
+  if (!t) return -1;
+  int rc = -1;
+  if (oracle_table_add_parquet(t, file, len, 1) == 0 && row_group >= 0 && row_group < t->parts[0]->n_rgs) {
+    fgpu_expr ex[3]; memset(ex, 0, sizeof ex);
+    ex[0].kind = FGPU_EXPR_COLUMN; ex[0].name = column; ex[0].left = ex[0].right = -1;
+    ex[1].kind = FGPU_EXPR_LITERAL; ex[1].left = ex[1].right = -1;
+    ex[1].literal.type = lit_is_null ? FGPU_SCALAR_NULL : FGPU_SCALAR_INT64; ex[1].literal.i64 = lit;
+    ex[2].kind = FGPU_EXPR_BINARY; ex[2].op = FGPU_OP_EQ; ex[2].left = 0; ex[2].right = 1;
+    fgpu_plan plan; memset(&plan, 0, sizeof plan);
+    plan.n_exprs = 3; plan.exprs = ex; plan.filter = 2;
+    rc = rg_may_match(&plan, 2, t->parts[0], &t->parts[0]->rgs[row_group]);
+  }
+  oracle_table_free(t);
+  return rc;
+}
 void oracle_table_free(oracle_table* t) {
   if (!t) return;
   for (int i = 0; i < t->n_parts; i++) { o_part* p = t->parts[i]; for (int l = 0; l < p->n_leaves; l++) free(p->leaves[l].name); free(p->leaves); for (int g = 0; g < p->n_rgs; g++) free(p->rgs[g].chunks); free(p->rgs); free(p); }

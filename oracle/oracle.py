@@ -47,6 +47,8 @@ def load() -> C.CDLL:
     lib.oracle_free.argtypes = [C.c_void_p]
     lib.oracle_chunk_may_match_i64.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64]
     lib.oracle_chunk_may_match_i64.restype = C.c_int
+    lib.oracle_parquet_rowgroup_may_match_eq_i64.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int64]
+    lib.oracle_parquet_rowgroup_may_match_eq_i64.restype = C.c_int
     _lib = lib
     return lib
 
@@ -163,3 +165,12 @@ class OracleResult:
 def chunk_may_match_i64(has_minmax: bool, mn: int, mx: int, null_count: int, num_values: int, op: int, literal) -> bool:
     """BinaryScalarOperation of the row-group filter on an int64 chunk given by its statistics (literal None = NULL)."""
     return bool(load().oracle_chunk_may_match_i64(int(has_minmax), mn, mx, null_count, num_values, op, int(literal is None), literal or 0))
+
+
+def parquet_rowgroup_may_match_eq_i64(buf: bytes, row_group: int, column: str, literal) -> bool:
+    """The oracle's row-group filter for `column == literal` (None: NULL) on one row group of a Parquet file: null count, then
+    the chunk's bloom filter when it has one, else its bounds (expr/binaryscalarexpr.go:84-128)."""
+    rc = load().oracle_parquet_rowgroup_may_match_eq_i64(buf, len(buf), row_group, column.encode(), int(literal is None), literal or 0)
+    if rc < 0:
+        raise ValueError("malformed Parquet file or unknown row group")
+    return bool(rc)

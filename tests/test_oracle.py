@@ -113,3 +113,29 @@ def test_row_group_filter_never_changes_a_result(monkeypatch):
         assert scanned[2] == 0 and scanned[0] > 0
     finally:
         eng.close()
+
+
+def test_oracle_row_group_filter_asks_bloom_filters():
+    """expr/binaryscalarexpr.go:104-118: a chunk WITH a bloom filter answers `column == v` from the filter alone (the
+    bounds are not consulted), one without from its bounds.  The oracle's XXH64 + split-block check against the
+    plain-Python implementation of tests/bloom_file.py on a file the tests write (pyarrow reads it back)."""
+    import numpy as np
+    from oracle import oracle as orc
+    from tests import bloom_file as bf
+    rng = np.random.default_rng(9)
+    xs = sorted(set(int(v) for v in rng.integers(0, 500_000, 3_000)))
+    buf = bf.write_int64_file({"x": xs})
+    n_bytes = max(32, ((len(xs) * 10 // 8) + 31) // 32 * 32)
+    bits = bytearray(n_bytes)
+    for v in xs:
+        bf.sbbf_insert(bits, bf.xxh64(v.to_bytes(8, "little", signed=True)))
+    for v in xs[::29]:
+        assert orc.parquet_rowgroup_may_match_eq_i64(buf, 0, "x", v)
+    out = 0
+    for v in (int(v) for v in rng.integers(-1000, 501_000, 400)):
+        expect = bf.sbbf_check(bytes(bits), bf.xxh64(v.to_bytes(8, "little", signed=True)))  # also OUTSIDE the bounds: the filter alone decides
+        assert orc.parquet_rowgroup_may_match_eq_i64(buf, 0, "x", v) == expect, v
+        out += 0 if expect else 1
+    assert out > 300
+    assert not orc.parquet_rowgroup_may_match_eq_i64(buf, 0, "x", None)   # required column: `== NULL` finds nothing
+    assert not orc.parquet_rowgroup_may_match_eq_i64(buf, 0, "nope", 3) and orc.parquet_rowgroup_may_match_eq_i64(buf, 0, "nope", None)
