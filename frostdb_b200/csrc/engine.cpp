@@ -1653,6 +1653,7 @@ int32_t run_cached(fgpu_ctx* ctx, ExecCache& x, fgpu_result* res, int collective
     uint64_t seq = 0, bytes = 0;
     int32_t rc = comm_push(ctx, x.table.p, x.table_bytes, &seq, &bytes);
     if (rc) return rc;
+    st.kernel_launches++;  // k_comm_push
     if (collective == 2) {  // the merge half follows in fgpu_query_execute_collective_end
       res->pending = true;
       res->pending_cached = &x;
@@ -2543,6 +2544,7 @@ int32_t run_scan(fgpu_ctx* ctx, const QueryPlan& q, uint64_t tx, fgpu_result* re
       x.agg_names.push_back(std::string(agg_string(q.aggs[a].func)) + "(" + q.expr_name(q.aggs[a].expr) + ")");
       x.agg_is_float.push_back(qd.aggs[a].func != FGPU_AGG_COUNT && qd.aggs[a].is_float);
     }
+    st.kernel_launches++;  // k_finalize_dense (cached_tail)
     x.stats = st;  // what a cached Execute reports: no uploads, no compile
     x.stats.h2d_bytes = 0;
     x.stats.d2h_bytes = 0;
