@@ -466,7 +466,7 @@ void prebuild_columns(Table* table, Part* part, const std::vector<std::string>& 
   }
   if (todo.size() < 2) return;  // a single column is built by its caller
   unsigned hw = std::thread::hardware_concurrency();
-  const size_t n_threads = std::min<size_t>(todo.size(), std::min<size_t>(hw ? hw : 4, 16));
+  const size_t n_threads = std::min<size_t>(todo.size(), std::min<size_t>(hw ? hw : 4, 32));  // (a part has ~20 columns: one wave)
   std::atomic<size_t> next{0};
   std::vector<std::thread> workers;
   for (size_t t = 0; t < n_threads; t++)
