@@ -225,7 +225,8 @@ int32_t fgpu_table_drop(fgpu_ctx* ctx, const char* table);
 int32_t fgpu_query_prepare(fgpu_ctx* ctx, const fgpu_plan* plan, fgpu_query** out);
 
 /* Blocking.  Scans every part of the table with tx <= tx_watermark (lsm.go:416) and produces the
- * final records.  Thread-safe for concurrent calls on one ctx. */
+ * final records.  Safe to call from several threads on one ctx: the calls are serialised by the context's mutex and run
+ * one after the other on its one stream (contexts on different GPUs, or several contexts on one GPU, run concurrently). */
 int32_t fgpu_query_execute(fgpu_ctx* ctx, fgpu_query* q, uint64_t tx_watermark, fgpu_result** out);
 
 /* Next result record as an Arrow struct array (one child per output column).  Ownership passes
